@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — decode tokens/s of the B200 engine on BASELINE.json's configs[1]
+(Llama-3.2-1B-shaped bf16, batch 1, 512-token KV cache, random-init weights, synthetic ids).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload 1b-bf16|1b-w4]
+
+A "step" is one decode step (one token per sequence).  Prints ONE JSON line (see DESIGN.md
+"Measurement").  `value` is device-timed (CUDA events on the engine's stream, token fed back on
+the device); `e2e` goes through mc_llama_decode with host buffers every step (H2D ids/pos, D2H id).
+`--impl reference` times the CPU oracle port of the reference path (the reference is Metal-only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+SHAPES = {
+    "1b": dict(dim=2048, n_layers=16, n_heads=32, n_kv_heads=8, head_dim=64, ffn_dim=8192, vocab=128256),
+    "8b": dict(dim=4096, n_layers=32, n_heads=32, n_kv_heads=8, head_dim=128, ffn_dim=14336, vocab=128256),
+}
+KV_LEN = 512
+METRIC = "decode_tokens_per_s"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def cpu_baseline(shape: dict, quant: int, steps: int):
+    """The oracle port of the reference path timed on this host's cores (checker code, timed as the baseline)."""
+    from oracle import orc
+
+    cfg = orc.make_cfg(**shape, max_seq_len=1024, quant=quant)
+    m = orc.Llama(cfg, orc.BF16)
+    m.init_random(0x5EED)
+    m.decode_timed(1, KV_LEN, 1)  # warm-up (page-in, thread pool)
+    sec, _ = m.decode_timed(1, KV_LEN + 1, steps)
+    threads = orc.num_threads()
+    m.close()
+    return {"value": steps / sec, "unit": "tokens/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} greedy decode steps of the full model at KV length {KV_LEN} (zero-filled cache), scalar C++ oracle with OpenMP over output rows",
+            "ms_per_step": 1e3 * sec / steps}
+
+
+def run_reference(args, shape, quant, workload):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from oracle import orc
+
+    cfg = orc.make_cfg(**shape, max_seq_len=1024, quant=quant)
+    m = orc.Llama(cfg, orc.BF16)
+    m.init_random(0x5EED)
+    budget_s = 150.0
+    t_probe, _ = m.decode_timed(1, KV_LEN, 1)
+    warm = max(0, min(args.warmup, int(10.0 / max(t_probe, 1e-3))))
+    if warm:
+        m.decode_timed(1, KV_LEN, warm)
+    steps = max(1, min(args.steps, int(budget_s / max(t_probe, 1e-3))))
+    sec, _ = m.decode_timed(1, KV_LEN, steps)
+    v = steps / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic ids, random-init weights (counter-hash seed 0x5EED)",
+        "config": {"workload": workload, "kv_len": KV_LEN, "batch": 1},
+        "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": orc.num_threads(), "kind": "port",
+                         "sample": f"{steps} decode steps at KV length {KV_LEN}; the reference is Metal-only, so this is the scalar C++ oracle port on host cores"},
+        "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def measure_gemv_family(capi, dev, shape, hbm_peak):
+    """Isolated CUDA-event timing of every GEMV shape of one decode step (weights larger than L2 in aggregate:
+    each shape is run over a ring of distinct weight buffers so that no launch re-reads L2-resident data)."""
+    import ctypes as C
+
+    try:
+        import torch
+    except Exception:
+        torch = None
+    D, F, V = shape["dim"], shape["ffn_dim"], shape["vocab"]
+    QKV = (shape["n_heads"] + 2 * shape["n_kv_heads"]) * shape["head_dim"]
+    QO = shape["n_heads"] * shape["head_dim"]
+    L = shape["n_layers"]
+    shapes = [("wqkv", QKV, D, L), ("wo", D, QO, L), ("w13", 2 * F, D, L), ("w2", D, F, L), ("head", V, D, 1)]
+    out = []
+    tot_b = tot_t = 0.0
+    for name, N, K, per_step in shapes:
+        wbytes = N * K * 2
+        ring = max(2, min(16, int(400e6 // wbytes) + 1))  # > 126 MB L2 in aggregate
+        ws = [dev.alloc(wbytes) for _ in range(ring)]
+        for w in ws:
+            capi.check(capi.lib().mc_memset(dev.h, w.h, 0, 0x3c, wbytes))
+        x = dev.upload(np.full(K, 0x3c00, np.uint16))
+        y = dev.alloc(N * 2)
+        reps = max(ring * 3, 24)
+        for i in range(ring):
+            capi.linear_bf16(dev, y, x, ws[i % ring], 1, N, K)
+        dev.synchronize()
+        t0 = time.perf_counter()
+        if torch is not None:
+            # events on the engine's own stream via an external stream handle
+            st = torch.cuda.ExternalStream(dev.stream())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for i in range(reps):
+                capi.linear_bf16(dev, y, x, ws[i % ring], 1, N, K)
+            e1.record(st)
+            dev.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+        else:
+            for i in range(reps):
+                capi.linear_bf16(dev, y, x, ws[i % ring], 1, N, K)
+            dev.synchronize()
+            ms = 1e3 * (time.perf_counter() - t0) / reps
+        alg = wbytes + K * 2 + N * 2
+        gbs = alg / (ms * 1e-3) / 1e9
+        out.append({"kernel": f"gemv_bf16 {name} [{N}x{K}]", "us": ms * 1e3, "GBps": gbs, "frac": gbs / hbm_peak, "launches_per_step": per_step})
+        tot_b += alg * per_step
+        tot_t += ms * 1e-3 * per_step
+        for w in ws:
+            w.release()
+    return out, tot_b / tot_t / 1e9
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="1b-bf16")
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    shape_name, fmt = args.workload.split("-")
+    shape = SHAPES[shape_name]
+    quant = 0 if fmt == "bf16" else 1
+    workload = f"llama-3.2-{shape_name} {fmt} decode, batch {args.batch}, {KV_LEN}-token KV cache (BASELINE.json configs[{1 if quant == 0 else 2}])"
+
+    if args.impl == "reference":
+        run_reference(args, shape, quant, workload)
+        return
+
+    rank, world, local = dist_env()
+    import torch
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from metalchat_b200 import capi
+
+    dev = capi.Device(local)
+    steps = min(args.steps, 1024 - KV_LEN - args.warmup - 8)
+    cfg = capi.llama_config(**shape, max_seq_len=1024, quant=quant, n_seqs=args.batch,
+                            flags=capi.LLAMA_W4_PACKED if quant else 0)
+    m = capi.Llama(dev, cfg)
+    m.init_random(0x5EED)
+    m.finalize()
+    streamed, resident = m.weight_bytes()
+    B = args.batch
+    # KV cache: KV_LEN positions per sequence written by the engine's own prefill of hash-generated ids
+    rng = np.random.default_rng(0x5EED + rank)
+    for s in range(B):
+        m.prefill(rng.integers(0, shape["vocab"], size=KV_LEN, dtype=np.int32), 0, s)
+    first = [int(np.argmax((m.logits(s).astype(np.uint32) << 16).view(np.float32))) for s in range(B)]
+    pos0 = [KV_LEN] * B
+
+    def barrier():
+        dev.synchronize()
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    # warm-up (instantiates the CUDA graph), then the timed region
+    m.decode_loop(first, pos0, args.warmup)
+    barrier()
+    l0 = dev.launches()
+    with ClockSampler(local) as clocks:
+        barrier()
+        toks, ms = m.decode_loop(first, [KV_LEN + args.warmup] * B, steps)
+        barrier()
+        # end-to-end through the public per-token call with host buffers
+        ids = np.array(first, np.int32)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            ids = m.decode(ids, np.full(B, KV_LEN + args.warmup + i, np.int32))
+        dev.synchronize()
+        e2e_s = time.perf_counter() - t0
+    launches = dev.launches() - l0
+    if dist is not None:
+        t = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+    else:
+        e2e_ms = e2e_s * 1e3
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_src = peaks()
+    tokens = steps * B * world
+    value = tokens / (ms * 1e-3)
+    kv_bytes = 2 * shape["n_layers"] * shape["n_kv_heads"] * shape["head_dim"] * 2 * (KV_LEN + args.warmup + steps // 2) * B
+    step_bytes = streamed + kv_bytes
+    step_gbs = step_bytes / (ms * 1e-3 / steps) / 1e9
+    roof = {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak, "traffic": None,
+            "kernel": "whole decode step (GEMV family streams >97% of the bytes)", "peak_source": peak_src,
+            "algorithmic_bytes_per_step": step_bytes}
+    if not args.no_roofline and quant == 0:
+        per, fam = measure_gemv_family(capi, dev, shape, hbm_peak)
+        roof.update({"kernel": "gemv_bf16_kernel (all GEMV launches of a step, isolated CUDA-event timing, weights cycled through >L2 ring)",
+                     "achieved": fam, "frac": fam / hbm_peak, "step_achieved": step_gbs, "step_frac": step_gbs / hbm_peak, "per_shape": per})
+    line = {
+        "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if quant == 0 else "bf16 activations, int4 weights (bf16 dequant), fp32 accumulate",
+        "data": "synthetic ids, random-init weights (counter-hash seed 0x5EED)",
+        "config": {"workload": workload, "kv_len": KV_LEN, "batch": B, "parallelism": f"{world} replica(s), one sequence stream per GPU",
+                   "l2": f"weights streamed per step {streamed / 1e6:.0f} MB > 126 MB L2 (no flush needed)"},
+        "e2e": {"value": tokens / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4 * B,
+                "ms_per_step": e2e_ms / steps},
+        "gpu_launches": int(launches), "launches_per_step": m.launches_per_step(),
+        "clocks": clocks.summary(), "roofline": roof,
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(shape, quant, 24)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,190 @@
+/* include/mc_cuda.h — C ABI of libmc_cuda.so, the B200 (sm_100a) accelerator backend.
+ *
+ * This is the drop-in boundary for the transformer decode hot path of
+ * ybubnov/metalchat.  The reference has no C ABI: its seam is five Metal-bound
+ * translation units behind opaque pimpl handles (include/metalchat/metal.h:14-34,
+ * src/metal_impl.h:19-112).  Every entry point below names the reference interface
+ * it replaces; a maintainer re-targets src/{metal,accelerator,allocator,kernel,
+ * kernel_thread}.cc onto these calls (see INTEGRATION.md for the binding).
+ *
+ * Conventions: plain C, plain pointers and sizes, no CUDA/torch types.  Every call
+ * returns an mc_status (0 = ok); the message of the last failure on the calling
+ * thread is available from mc_last_error().  Handles are reference counted where the
+ * reference uses std::shared_ptr.  A device owns ONE in-order CUDA stream (the
+ * reference: one MTL command queue, src/kernel_thread.cc:13-56); calls on one device
+ * must come from one producer thread at a time (kernel_thread is not synchronised
+ * either, kernel_thread.h:57-294).
+ */
+#ifndef MC_CUDA_H
+#define MC_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MC_API __attribute__((visibility("default")))
+
+typedef enum mc_status {
+    MC_OK = 0,
+    MC_ERR_INVALID = 1,   /* std::invalid_argument in the reference (kernel.h:126-140)      */
+    MC_ERR_RUNTIME = 2,   /* std::runtime_error (src/accelerator.cc:117-158, kernel_thread) */
+    MC_ERR_ALLOC = 3,     /* alloc_error : std::bad_alloc (allocator.h:20-34)               */
+    MC_ERR_NOT_FOUND = 4, /* "kernel not found" from hardware_accelerator::load            */
+    MC_ERR_FULL = 5       /* command buffer at capacity (kernel_thread.h:222-243)           */
+} mc_status;
+
+typedef struct mc_device mc_device;
+typedef struct mc_buffer mc_buffer;
+typedef struct mc_kernel mc_kernel;
+typedef struct mc_cmdbuf mc_cmdbuf;
+typedef struct mc_llama mc_llama;
+
+MC_API const char* mc_last_error(void);
+MC_API const char* mc_version(void);
+
+/* ---- device: metal::device / hardware_accelerator ctor ---------------------------
+ * replaces MTL::CreateSystemDefaultDevice + newCommandQueue + newLibrary
+ * (src/accelerator.cc:73-113, src/metal.cc:51-55).                                  */
+MC_API mc_status mc_device_count(int* count);
+MC_API mc_status mc_device_create(int ordinal, mc_device** out);
+MC_API mc_status mc_device_destroy(mc_device* dev);
+MC_API mc_status mc_device_name(mc_device* dev, char* out, size_t cap);           /* accelerator.h:108-113 name()             */
+MC_API mc_status mc_device_max_buffer(mc_device* dev, size_t* bytes);             /* MTL::Device::maxBufferLength             */
+MC_API mc_status mc_device_sm_count(mc_device* dev, int* count);
+MC_API mc_status mc_device_synchronize(mc_device* dev);
+/* raw cudaStream_t of the device (for event timing by a harness that shares the stream) */
+MC_API mc_status mc_device_stream(mc_device* dev, void** cuda_stream);
+
+/* ---- memory: hardware_memory_allocator / heap / nocopy (src/allocator.cc:46-275) -- */
+enum {
+    MC_MEM_DEVICE = 0, /* cudaMalloc: device resident, not host dereferenceable          */
+    MC_MEM_SHARED = 1, /* cudaMallocManaged: host dereferenceable like MTL Shared storage
+                          (src/metal.cc:21-25 contents()); valid on the host after mc_wait */
+    MC_MEM_PINNED = 2  /* cudaHostAlloc(mapped): host memory the GPU reads over PCIe     */
+};
+MC_API mc_status mc_alloc(mc_device* dev, size_t size, int flags, mc_buffer** out);                 /* newBuffer(size, Shared)        src/allocator.cc:46-60   */
+MC_API mc_status mc_alloc_copy(mc_device* dev, const void* src, size_t size, int flags, mc_buffer** out); /* newBuffer(ptr, size, ...)  src/allocator.cc:62-80   */
+MC_API mc_status mc_wrap_host(mc_device* dev, void* host, size_t size, mc_buffer** out);            /* nocopy_allocator newBuffer(noCopy) src/allocator.cc:127-173: cudaHostRegister */
+MC_API mc_status mc_buffer_retain(mc_buffer* buf);
+MC_API mc_status mc_buffer_release(mc_buffer* buf);
+MC_API mc_status mc_buffer_host_ptr(mc_buffer* buf, void** out);  /* metal::data(buffer)  metal.h:17-22 */
+MC_API mc_status mc_buffer_dev_ptr(mc_buffer* buf, void** out);
+MC_API mc_status mc_buffer_size(mc_buffer* buf, size_t* out);     /* metal::size(buffer)  metal.h:17-22 */
+/* Explicit copies on the device stream (no unified memory on B200). */
+MC_API mc_status mc_memcpy_h2d(mc_device* dev, mc_buffer* dst, size_t dst_off, const void* src, size_t size);
+MC_API mc_status mc_memcpy_d2h(mc_device* dev, void* dst, mc_buffer* src, size_t src_off, size_t size);
+MC_API mc_status mc_memset(mc_device* dev, mc_buffer* dst, size_t dst_off, int value, size_t size);
+/* hardware_heap_allocator: one fixed arena, bump sub-allocation (src/allocator.cc:82-125) */
+typedef struct mc_heap mc_heap;
+MC_API mc_status mc_heap_create(mc_device* dev, size_t capacity, mc_heap** out);
+MC_API mc_status mc_heap_alloc(mc_heap* heap, size_t size, mc_buffer** out);
+MC_API mc_status mc_heap_reset(mc_heap* heap);
+MC_API mc_status mc_heap_destroy(mc_heap* heap);
+
+/* ---- kernels: hardware_accelerator::load (src/accelerator.cc:117-158) ------------
+ * `name` is the reference's mangled host name, e.g. "softmax_bfloat", "bmm_8_float",
+ * "cumsum_2_bfloat", "hadamard_broadcast_bfloat_int8_t_float" (accelerator.h:175-218).
+ * All 71 names of metalchat.metallib resolve.                  */
+MC_API mc_status mc_kernel_lookup(mc_device* dev, const char* name, mc_kernel** out);
+MC_API mc_status mc_kernel_name(mc_kernel* k, const char** out);
+MC_API mc_status mc_kernel_max_threads(mc_kernel* k, size_t* out); /* 1024, src/kernel.cc:75-79 */
+MC_API mc_status mc_kernel_count(int* count);
+MC_API mc_status mc_kernel_name_at(int index, const char** out);
+
+/* ---- encode / dispatch: hardware_function_encoder + kernel_thread -----------------
+ * (src/kernel_thread.cc:69-120,134-144,185-199; kernel_thread.h:104-137).
+ * Arguments are bound by slot index in the reference's bind order: a tensor occupies
+ * two consecutive slots — tensor_layout<N> bytes {sizes[N],strides[N],offsets[N]} as
+ * uint32 (tensor/concept.h:24-33), then the buffer + byte offset; a scalar occupies one
+ * slot of raw bytes.  mc_dispatch consumes the bound slots and enqueues the kernel on
+ * the device stream; `grid` is total THREADS (Metal dispatchThreads) and is only
+ * validated (group <= 1024 threads, grid >= group per dimension; kernel.h:126-140) —
+ * the CUDA launch shape is chosen by the backend.                                     */
+MC_API mc_status mc_stream_begin(mc_device* dev, size_t capacity, mc_cmdbuf** out);
+MC_API mc_status mc_set_bytes(mc_cmdbuf* cb, uint32_t index, const void* bytes, size_t size);  /* setBytes   */
+MC_API mc_status mc_set_buffer(mc_cmdbuf* cb, uint32_t index, mc_buffer* buf, size_t offset);   /* setBuffer  */
+MC_API mc_status mc_barrier(mc_cmdbuf* cb, mc_buffer* buf);                                      /* memoryBarrier: no-op on an in-order stream */
+MC_API mc_status mc_dispatch(mc_cmdbuf* cb, mc_kernel* k, const uint32_t grid[3], const uint32_t group[3]);
+MC_API mc_status mc_on_completed(mc_cmdbuf* cb, void (*fn)(void* user, int status), void* user); /* addCompletedHandler */
+MC_API mc_status mc_commit(mc_cmdbuf* cb);                                                       /* commit()            */
+MC_API mc_status mc_wait(mc_cmdbuf* cb, char* err, size_t cap);                                  /* waitUntilCompleted + error() */
+MC_API mc_status mc_cmdbuf_size(mc_cmdbuf* cb, size_t* n);
+MC_API mc_status mc_cmdbuf_release(mc_cmdbuf* cb);
+MC_API mc_status mc_launch_count(mc_device* dev, uint64_t* launches); /* kernels launched by this backend so far */
+
+/* ---- fused decode engine: transformer<llama3>::transform --------------------------
+ * (transformer.h:357-364 -> nn/llama.h:113-134 -> nn/sampling.h:69-76).               */
+typedef struct mc_llama_config {
+    uint32_t dim, n_layers, n_heads, n_kv_heads, head_dim, ffn_dim, vocab, max_seq_len;
+    float rope_theta, norm_eps;
+    uint32_t quant;      /* 0: bf16 weights; 1: QLoRA layout (huggingface/llama.h:152-171)    */
+    uint32_t lora_rank;  /* 16                                                                  */
+    float lora_scale;    /* 2.0                                                                 */
+    uint32_t group_size; /* 32                                                                  */
+    uint32_t n_seqs;     /* independent bs=1 sequences decoded together (nn/llama.h:86 is 1)    */
+    uint32_t tp_rank, tp_world; /* tensor-parallel shard (0,1 = single GPU)                     */
+    uint32_t flags;      /* MC_LLAMA_* below                                                    */
+} mc_llama_config;
+enum {
+    MC_LLAMA_W4_PACKED = 1u << 0, /* store QLoRA int8-in-int4-range weights two per byte       */
+    MC_LLAMA_NO_GRAPH = 1u << 1,  /* launch kernels directly instead of replaying a CUDA graph  */
+    MC_LLAMA_NO_PDL = 1u << 2     /* no programmatic dependent launch between decode kernels    */
+};
+typedef struct mc_sampler_config {
+    uint32_t mode;       /* 0 greedy argmax (lowest index on ties); 1 top-k -> nucleus -> multinomial (nn/sampling.h:306-316) */
+    uint32_t top_k;      /* 50 (nn/sampling.h:309)                                              */
+    float temperature;   /* 0.6 (nn/sampling.h:179-181)                                         */
+    float top_p;         /* 0.9                                                                 */
+    uint32_t intended;   /* multinomial: 0 reference-exact a=input[row,S-1], 1 a=input[row,N-1] (kernel/multinomial.metal:107) */
+} mc_sampler_config;
+
+MC_API mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama** out);
+MC_API mc_status mc_llama_destroy(mc_llama* m);
+/* Parameters by the reference's registered layer paths, e.g.
+ * "layers.3.attention.wq.weight", "tok_embeddings.weight", "layers.0.feed_forward.w1.scales",
+ * "layers.0.attention.wo.adaptor.A.weight".  Data is the FULL (unsharded) tensor in host memory. */
+MC_API mc_status mc_llama_set_tensor(mc_llama* m, const char* name, const void* host, size_t nbytes);
+/* Device-side synthetic weights: counter-hash generator keyed by (seed, tensor id, index),
+ * distributions in DESIGN.md "Synthetic data"; bit-identical to the test oracle's generator. */
+MC_API mc_status mc_llama_init_random(mc_llama* m, uint64_t seed);
+/* Must be called after the weights are set and before prefill/decode (packs fused layouts). */
+MC_API mc_status mc_llama_finalize(mc_llama* m);
+MC_API mc_status mc_llama_weight_bytes(mc_llama* m, uint64_t* streamed_per_step, uint64_t* resident);
+/* ids[len] of sequence `seq` at positions [start_pos, start_pos+len): fills the KV cache and
+ * leaves the logits of the LAST position (nn/llama.h:128-133).                              */
+MC_API mc_status mc_llama_prefill(mc_llama* m, uint32_t seq, const int32_t* ids, uint32_t len, uint32_t start_pos);
+/* One decode step for sequences [0, n): ids[n] (host) at pos[n] -> out_ids[n] (host).
+ * uniforms[n] (host, may be NULL for greedy) are the injected multinomial draws.
+ * Includes the H2D of ids/pos/uniforms and the D2H of out_ids.                             */
+MC_API mc_status mc_llama_decode(mc_llama* m, uint32_t n, const int32_t* ids, const int32_t* pos, const float* uniforms,
+                                 const mc_sampler_config* sampler, int32_t* out_ids);
+/* `steps` greedy/sampled decode steps entirely on the device: the sampled id feeds the next
+ * step without a host round trip; out_ids[steps*n] (host, may be NULL) receives every id.
+ * elapsed_ms (may be NULL) receives the CUDA-event time of the loop.                        */
+MC_API mc_status mc_llama_decode_loop(mc_llama* m, uint32_t n, const int32_t* first_ids, const int32_t* first_pos,
+                                      uint32_t steps, const float* uniforms, const mc_sampler_config* sampler,
+                                      int32_t* out_ids, float* elapsed_ms);
+/* Copy out state for parity checks: logits [vocab] bf16, last hidden [dim] bf16, cache rows. */
+MC_API mc_status mc_llama_logits(mc_llama* m, uint32_t seq, void* host_bf16, size_t nbytes);
+MC_API mc_status mc_llama_hidden(mc_llama* m, uint32_t seq, void* host_bf16, size_t nbytes);
+MC_API mc_status mc_llama_cache(mc_llama* m, uint32_t seq, uint32_t layer, int which, uint32_t n_pos, void* host_bf16, size_t nbytes);
+MC_API mc_status mc_llama_launches_per_step(mc_llama* m, uint32_t* kernels);
+
+/* ---- stand-alone hot kernels (for roofline measurement and parity tests) -----------
+ * y[M,N] = x[M,K] * W[N,K]^T with fp32 accumulation and one RNE rounding to bf16
+ * (kernel/bmm.metal:24-82 through nn/linear.h:70-81).  M <= 8 takes the streaming GEMV path. */
+MC_API mc_status mc_linear_bf16(mc_device* dev, mc_buffer* y, mc_buffer* x, mc_buffer* w, uint32_t M, uint32_t N, uint32_t K);
+/* QLoRA base linear over packed int4: w4 [N,K/2] bytes (two weights per byte), scales fp32 [N,K/32]
+ * (quantization/lora.h:94-122 + kernel/mul.metal:59-85 fused). */
+MC_API mc_status mc_linear_w4(mc_device* dev, mc_buffer* y, mc_buffer* x, mc_buffer* w4, mc_buffer* scales, uint32_t M, uint32_t N, uint32_t K);
+/* pack int8 (values in [-8,7]) [N,K] into the engine's int4 stream layout and back (bit-exact). */
+MC_API mc_status mc_pack_w4(mc_device* dev, mc_buffer* w4, mc_buffer* q8, uint32_t N, uint32_t K);
+MC_API mc_status mc_unpack_w4(mc_device* dev, mc_buffer* q8, mc_buffer* w4, uint32_t N, uint32_t K);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MC_CUDA_H */

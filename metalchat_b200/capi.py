@@ -1,0 +1,409 @@
+"""ctypes binding of libmc_cuda.so (include/mc_cuda.h).
+
+Thin, allocation-explicit mirror of the C ABI used by the tests, bench.py and the Python host
+layer.  There is NO fallback: if the shared library is missing or no B200 is present the
+constructors raise.  Nothing in this package imports the test oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libmc_cuda.so"
+
+MC_OK, MC_ERR_INVALID, MC_ERR_RUNTIME, MC_ERR_ALLOC, MC_ERR_NOT_FOUND, MC_ERR_FULL = range(6)
+MEM_DEVICE, MEM_SHARED, MEM_PINNED = 0, 1, 2
+LLAMA_W4_PACKED, LLAMA_NO_GRAPH, LLAMA_NO_PDL = 1, 2, 4
+
+
+class McError(RuntimeError):
+    """std::runtime_error of the reference (command-buffer / library failures)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(msg)
+        self.code = code
+
+
+class McInvalidArgument(McError, ValueError):
+    """std::invalid_argument of the reference (shape / launch validation, kernel.h:126-140)."""
+
+
+class McAllocError(McError, MemoryError):
+    """alloc_error of the reference (allocator.h:20-34)."""
+
+
+class McNotFound(McError, KeyError):
+    pass
+
+
+class LlamaConfig(C.Structure):
+    _fields_ = [
+        ("dim", C.c_uint32), ("n_layers", C.c_uint32), ("n_heads", C.c_uint32), ("n_kv_heads", C.c_uint32),
+        ("head_dim", C.c_uint32), ("ffn_dim", C.c_uint32), ("vocab", C.c_uint32), ("max_seq_len", C.c_uint32),
+        ("rope_theta", C.c_float), ("norm_eps", C.c_float),
+        ("quant", C.c_uint32), ("lora_rank", C.c_uint32), ("lora_scale", C.c_float), ("group_size", C.c_uint32),
+        ("n_seqs", C.c_uint32), ("tp_rank", C.c_uint32), ("tp_world", C.c_uint32), ("flags", C.c_uint32),
+    ]
+
+
+class SamplerConfig(C.Structure):
+    _fields_ = [("mode", C.c_uint32), ("top_k", C.c_uint32), ("temperature", C.c_float), ("top_p", C.c_float),
+                ("intended", C.c_uint32)]
+
+
+def llama_config(dim=2048, n_layers=16, n_heads=32, n_kv_heads=8, head_dim=64, ffn_dim=8192, vocab=128256,
+                 max_seq_len=1024, rope_theta=500000.0, norm_eps=1e-5, quant=0, lora_rank=16, lora_scale=2.0,
+                 group_size=32, n_seqs=1, tp_rank=0, tp_world=1, flags=0) -> LlamaConfig:
+    return LlamaConfig(dim, n_layers, n_heads, n_kv_heads, head_dim, ffn_dim, vocab, max_seq_len, rope_theta, norm_eps,
+                       quant, lora_rank, lora_scale, group_size, n_seqs, tp_rank, tp_world, flags)
+
+
+# every exported symbol of include/mc_cuda.h (checked by tests/test_abi.py against the header)
+_SIGNATURES = {
+    "mc_last_error": (C.c_char_p, []),
+    "mc_version": (C.c_char_p, []),
+    "mc_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "mc_device_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "mc_device_destroy": (C.c_int, [C.c_void_p]),
+    "mc_device_name": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
+    "mc_device_max_buffer": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
+    "mc_device_sm_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "mc_device_synchronize": (C.c_int, [C.c_void_p]),
+    "mc_device_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mc_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+    "mc_alloc_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+    "mc_wrap_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "mc_buffer_retain": (C.c_int, [C.c_void_p]),
+    "mc_buffer_release": (C.c_int, [C.c_void_p]),
+    "mc_buffer_host_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mc_buffer_dev_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mc_buffer_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
+    "mc_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "mc_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "mc_memset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_size_t]),
+    "mc_heap_create": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "mc_heap_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "mc_heap_reset": (C.c_int, [C.c_void_p]),
+    "mc_heap_destroy": (C.c_int, [C.c_void_p]),
+    "mc_kernel_lookup": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mc_kernel_name": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p)]),
+    "mc_kernel_max_threads": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
+    "mc_kernel_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "mc_kernel_name_at": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
+    "mc_stream_begin": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "mc_set_bytes": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "mc_set_buffer": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "mc_barrier": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mc_dispatch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "mc_on_completed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mc_commit": (C.c_int, [C.c_void_p]),
+    "mc_wait": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
+    "mc_cmdbuf_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
+    "mc_cmdbuf_release": (C.c_int, [C.c_void_p]),
+    "mc_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "mc_llama_create": (C.c_int, [C.c_void_p, C.POINTER(LlamaConfig), C.POINTER(C.c_void_p)]),
+    "mc_llama_destroy": (C.c_int, [C.c_void_p]),
+    "mc_llama_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]),
+    "mc_llama_init_random": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "mc_llama_finalize": (C.c_int, [C.c_void_p]),
+    "mc_llama_weight_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "mc_llama_prefill": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "mc_llama_decode": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SamplerConfig), C.c_void_p]),
+    "mc_llama_decode_loop": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                       C.POINTER(SamplerConfig), C.c_void_p, C.POINTER(C.c_float)]),
+    "mc_llama_logits": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "mc_llama_hidden": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "mc_llama_cache": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "mc_llama_launches_per_step": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
+    "mc_linear_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "mc_linear_w4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "mc_pack_w4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "mc_unpack_w4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads libmc_cuda.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise McError(MC_ERR_RUNTIME, f"{LIB_PATH} is missing: run `python -m metalchat_b200.build` "
+                                          "(the CUDA backend has no CPU fallback)")
+        l = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(rc: int):
+    if rc == MC_OK:
+        return
+    msg = lib().mc_last_error().decode(errors="replace")
+    cls = {MC_ERR_INVALID: McInvalidArgument, MC_ERR_ALLOC: McAllocError, MC_ERR_NOT_FOUND: McNotFound}.get(rc, McError)
+    raise cls(rc, msg)
+
+
+def _vp(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return a
+
+
+class Device:
+    """mc_device: one GPU + one in-order stream (hardware_accelerator's device + queue)."""
+
+    def __init__(self, ordinal: int = 0):
+        h = C.c_void_p()
+        check(lib().mc_device_create(ordinal, C.byref(h)))
+        self.h = h
+        self.ordinal = ordinal
+
+    @staticmethod
+    def count() -> int:
+        n = C.c_int()
+        check(lib().mc_device_count(C.byref(n)))
+        return n.value
+
+    def name(self) -> str:
+        buf = C.create_string_buffer(256)
+        check(lib().mc_device_name(self.h, buf, 256))
+        return buf.value.decode()
+
+    def sm_count(self) -> int:
+        n = C.c_int()
+        check(lib().mc_device_sm_count(self.h, C.byref(n)))
+        return n.value
+
+    def max_buffer(self) -> int:
+        n = C.c_size_t()
+        check(lib().mc_device_max_buffer(self.h, C.byref(n)))
+        return n.value
+
+    def synchronize(self):
+        check(lib().mc_device_synchronize(self.h))
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        check(lib().mc_device_stream(self.h, C.byref(s)))
+        return s.value or 0
+
+    def launches(self) -> int:
+        n = C.c_uint64()
+        check(lib().mc_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def alloc(self, size: int, flags: int = MEM_DEVICE) -> "Buffer":
+        h = C.c_void_p()
+        check(lib().mc_alloc(self.h, size, flags, C.byref(h)))
+        return Buffer(self, h)
+
+    def upload(self, a: np.ndarray, flags: int = MEM_DEVICE) -> "Buffer":
+        a = np.ascontiguousarray(a)
+        h = C.c_void_p()
+        check(lib().mc_alloc_copy(self.h, _vp(a), a.nbytes, flags, C.byref(h)))
+        return Buffer(self, h)
+
+    def kernel(self, name: str) -> "Kernel":
+        h = C.c_void_p()
+        check(lib().mc_kernel_lookup(self.h, name.encode(), C.byref(h)))
+        return Kernel(h, name)
+
+    def command_buffer(self, capacity: int = 64) -> "CommandBuffer":
+        h = C.c_void_p()
+        check(lib().mc_stream_begin(self.h, capacity, C.byref(h)))
+        return CommandBuffer(self, h)
+
+    def close(self):
+        if self.h:
+            lib().mc_device_destroy(self.h)
+            self.h = None
+
+
+class Buffer:
+    def __init__(self, dev: Device, h):
+        self.dev, self.h = dev, h
+
+    @property
+    def size(self) -> int:
+        n = C.c_size_t()
+        check(lib().mc_buffer_size(self.h, C.byref(n)))
+        return n.value
+
+    def dev_ptr(self) -> int:
+        p = C.c_void_p()
+        check(lib().mc_buffer_dev_ptr(self.h, C.byref(p)))
+        return p.value or 0
+
+    def host_ptr(self) -> int:
+        p = C.c_void_p()
+        check(lib().mc_buffer_host_ptr(self.h, C.byref(p)))
+        return p.value or 0
+
+    def write(self, a: np.ndarray, offset: int = 0):
+        a = np.ascontiguousarray(a)
+        check(lib().mc_memcpy_h2d(self.dev.h, self.h, offset, _vp(a), a.nbytes))
+
+    def read(self, dtype, count: int | None = None, offset: int = 0) -> np.ndarray:
+        dt = np.dtype(dtype)
+        n = (self.size - offset) // dt.itemsize if count is None else count
+        out = np.empty(n, dtype=dt)
+        check(lib().mc_memcpy_d2h(self.dev.h, _vp(out), self.h, offset, out.nbytes))
+        return out
+
+    def release(self):
+        if self.h:
+            lib().mc_buffer_release(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class Kernel:
+    def __init__(self, h, name):
+        self.h, self.name = h, name
+
+    def max_threads(self) -> int:
+        n = C.c_size_t()
+        check(lib().mc_kernel_max_threads(self.h, C.byref(n)))
+        return n.value
+
+
+class CommandBuffer:
+    """mc_cmdbuf: the kernel_thread of the reference (kernel_thread.h:57-294)."""
+
+    def __init__(self, dev: Device, h):
+        self.dev, self.h = dev, h
+        self._keep = []
+
+    def set_bytes(self, index: int, data: bytes):
+        check(lib().mc_set_bytes(self.h, index, data, len(data)))
+
+    def set_buffer(self, index: int, buf: Buffer, offset: int = 0):
+        check(lib().mc_set_buffer(self.h, index, buf.h, offset))
+
+    def dispatch(self, kernel: Kernel, grid, group):
+        g = (C.c_uint32 * 3)(*grid)
+        t = (C.c_uint32 * 3)(*group)
+        check(lib().mc_dispatch(self.h, kernel.h, g, t))
+
+    def commit(self):
+        check(lib().mc_commit(self.h))
+
+    def wait(self):
+        err = C.create_string_buffer(512)
+        rc = lib().mc_wait(self.h, err, 512)
+        if rc != MC_OK:
+            raise McError(rc, err.value.decode(errors="replace"))
+
+    def size(self) -> int:
+        n = C.c_size_t()
+        check(lib().mc_cmdbuf_size(self.h, C.byref(n)))
+        return n.value
+
+    def release(self):
+        if self.h:
+            lib().mc_cmdbuf_release(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class Llama:
+    """mc_llama: the fused decode engine (transformer<llama3>::transform, transformer.h:357-364)."""
+
+    def __init__(self, dev: Device, cfg: LlamaConfig):
+        self.dev, self.cfg = dev, cfg
+        h = C.c_void_p()
+        check(lib().mc_llama_create(dev.h, C.byref(cfg), C.byref(h)))
+        self.h = h
+
+    def set_tensor(self, name: str, a: np.ndarray):
+        a = np.ascontiguousarray(a)
+        check(lib().mc_llama_set_tensor(self.h, name.encode(), _vp(a), a.nbytes))
+
+    def init_random(self, seed: int = 0x5EED):
+        check(lib().mc_llama_init_random(self.h, seed))
+
+    def finalize(self):
+        check(lib().mc_llama_finalize(self.h))
+
+    def weight_bytes(self):
+        s, r = C.c_uint64(), C.c_uint64()
+        check(lib().mc_llama_weight_bytes(self.h, C.byref(s), C.byref(r)))
+        return s.value, r.value
+
+    def prefill(self, ids, start_pos: int = 0, seq: int = 0):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        check(lib().mc_llama_prefill(self.h, seq, _vp(ids), len(ids), start_pos))
+
+    def decode(self, ids, pos, uniforms=None, sampler: SamplerConfig | None = None) -> np.ndarray:
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        pos = np.ascontiguousarray(pos, dtype=np.int32)
+        out = np.zeros(len(ids), dtype=np.int32)
+        u = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float32)
+        check(lib().mc_llama_decode(self.h, len(ids), _vp(ids), _vp(pos), _vp(u), C.byref(sampler) if sampler else None, _vp(out)))
+        return out
+
+    def decode_loop(self, first_ids, first_pos, steps: int, uniforms=None, sampler: SamplerConfig | None = None):
+        ids = np.ascontiguousarray(first_ids, dtype=np.int32)
+        pos = np.ascontiguousarray(first_pos, dtype=np.int32)
+        out = np.zeros((steps, len(ids)), dtype=np.int32)
+        ms = C.c_float()
+        u = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float32)
+        check(lib().mc_llama_decode_loop(self.h, len(ids), _vp(ids), _vp(pos), steps, _vp(u), C.byref(sampler) if sampler else None,
+                                         _vp(out), C.byref(ms)))
+        return out, ms.value
+
+    def logits(self, seq: int = 0) -> np.ndarray:
+        vl = self.cfg.vocab // max(1, self.cfg.tp_world)
+        out = np.zeros(vl, dtype=np.uint16)
+        check(lib().mc_llama_logits(self.h, seq, _vp(out), out.nbytes))
+        return out
+
+    def hidden(self, seq: int = 0) -> np.ndarray:
+        out = np.zeros(self.cfg.dim, dtype=np.uint16)
+        check(lib().mc_llama_hidden(self.h, seq, _vp(out), out.nbytes))
+        return out
+
+    def cache(self, seq: int, layer: int, which: int, n_pos: int) -> np.ndarray:
+        kvl = self.cfg.n_kv_heads // max(1, self.cfg.tp_world)
+        out = np.zeros((n_pos, kvl, self.cfg.head_dim), dtype=np.uint16)
+        check(lib().mc_llama_cache(self.h, seq, layer, which, n_pos, _vp(out), out.nbytes))
+        return out
+
+    def launches_per_step(self) -> int:
+        n = C.c_uint32()
+        check(lib().mc_llama_launches_per_step(self.h, C.byref(n)))
+        return n.value
+
+    def close(self):
+        if self.h:
+            lib().mc_llama_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def linear_bf16(dev: Device, y: Buffer, x: Buffer, w: Buffer, M: int, N: int, K: int):
+    check(lib().mc_linear_bf16(dev.h, y.h, x.h, w.h, M, N, K))

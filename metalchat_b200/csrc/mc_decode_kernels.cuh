@@ -1,0 +1,581 @@
+// metalchat_b200/csrc/mc_decode_kernels.cuh — the fused sm_100a kernels of the decode engine.
+//
+// Where the reference runs ~30 Metal kernels per transformer block and rounds to bf16 after each
+// (SURVEY.md §3.1, §8a "rounding chain"), the engine runs five kernels per block and keeps every
+// one of those rounding points r(.) inside them:
+//
+//   K1  gemv<PRO_RMSNORM, EPI_QKV>     attention_norm + wq|wk|wv + rope(q,k) + KV-cache append
+//   K5  attn_decode                    scores -> scale -> softmax(no max) -> PV, GQA by indexing
+//   K1  gemv<PRO_NONE,    EPI_RESIDUAL> wo + residual add
+//   K1  gemv<PRO_RMSNORM, EPI_SWIGLU>  ffn_norm + w1|w3 (row-interleaved) + silu*mul
+//   K1  gemv<PRO_NONE,    EPI_RESIDUAL> w2 + residual add
+//
+// The GEMV streams each weight row exactly once with 128-bit L1-bypassing loads, two rows per
+// warp, fp32 accumulation, warp-shuffle reduction; quantised weights are dequantised in
+// registers with the reference's double rounding r(r(q)*r(s)) (kernel/mul.metal:76-77).
+#pragma once
+#include "mc_common.cuh"
+
+namespace mc {
+
+constexpr int kGemvThreads = 256;
+constexpr int kGemvWarps = kGemvThreads / 32;
+constexpr int kMaxMB = 4; // activation rows handled by one GEMV pass
+
+enum { PRO_NONE = 0, PRO_RMSNORM = 1 };
+enum { EPI_NONE = 0, EPI_QKV = 1, EPI_RESIDUAL = 2, EPI_SWIGLU = 3 };
+enum { WF_BF16 = 0, WF_W4 = 1, WF_W8ROW = 2, WF_W8G = 3 };
+
+// ---- small device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_stream8(const void* p)
+{
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ float rbf(float f) { return bf16_bits_to_f32(f32_to_bf16_bits(f)); } // r(.)
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+// PDL: wait for the producer grid's memory / let the consumer grid start its prologue
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// silu evaluated in bf16 steps: x / (T(1) + T(exp(-x)))  (kernel/activation.metal:34-35, quirk Q5)
+__device__ __forceinline__ float silu_bf16(float g)
+{
+    const float e = rbf(expf(-g));
+    const float d = rbf(__fadd_rn(1.0f, e));
+    return rbf(__fdiv_rn(g, d));
+}
+
+struct gemv_params {
+    const void* W;         // weight rows, format WF_*
+    const float* scales;   // WF_W4/WF_W8G: [N, K/group]; WF_W8ROW: [N]
+    uint32_t N, K;         // local rows / reduction length
+    uint32_t rows;         // activation rows (<= MB)
+    const uint16_t* x;     // [rows, ldx] bf16 input
+    uint32_t ldx;
+    // PRO_RMSNORM
+    const uint16_t* norm_w; // [K]
+    float eps;
+    // EPI_NONE / EPI_RESIDUAL / EPI_SWIGLU
+    uint16_t* y;           // [rows, ldy]
+    uint32_t ldy;
+    const uint16_t* res;   // EPI_RESIDUAL: [rows, ldy]
+    // EPI_QKV
+    uint16_t* q;           // [rows, Hl*hd]
+    uint16_t* kcache;      // this layer: [n_seqs, KVl, S, hd]
+    uint16_t* vcache;
+    const float* fcos;     // [2S, hd/2]
+    const float* fsin;
+    const int32_t* row_seq; // [rows]
+    const int32_t* row_pos; // [rows]
+    uint32_t n_heads, n_kv_heads, head_dim, max_seq;
+    // LoRA epilogue (quantised layers): y += r(r(B . ax) * lora_scale) with ax = r(A . x) precomputed
+    const uint16_t* lora_b; // [N, rank]
+    const uint16_t* lora_ax; // [rows, rank] bf16
+    uint32_t lora_rank;
+    float lora_scale;      // already rounded to bf16
+    uint32_t units_per_cta_iter; // derived
+};
+
+// dot of 8 bf16 weights (uint4) with 8 bf16 activations (uint4), fp32 accumulate in ascending order
+__device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float acc)
+{
+    acc = fmaf(bf_lo(w.x), bf_lo(x.x), acc);
+    acc = fmaf(bf_hi(w.x), bf_hi(x.x), acc);
+    acc = fmaf(bf_lo(w.y), bf_lo(x.y), acc);
+    acc = fmaf(bf_hi(w.y), bf_hi(x.y), acc);
+    acc = fmaf(bf_lo(w.z), bf_lo(x.z), acc);
+    acc = fmaf(bf_hi(w.z), bf_hi(x.z), acc);
+    acc = fmaf(bf_lo(w.w), bf_lo(x.w), acc);
+    acc = fmaf(bf_hi(w.w), bf_hi(x.w), acc);
+    return acc;
+}
+
+// Block-wide sum with a fixed partition (warp butterfly, then 8 warp totals in order).
+__device__ __forceinline__ float block_sum_256(float v, float* scratch /* [8] */)
+{
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kGemvWarps; i++) t += scratch[i];
+    __syncthreads();
+    return t;
+}
+
+// unit -> the two weight rows a warp group computes
+template <int EPI> __device__ __forceinline__ void unit_rows(const gemv_params& p, uint32_t u, uint32_t& r0, uint32_t& r1)
+{
+    if (EPI == EPI_QKV) {
+        const uint32_t half = p.head_dim >> 1;
+        const uint32_t head = u / half, j = u - head * half;
+        r0 = head * p.head_dim + j; // rope pair (j, j + hd/2) of one head (kernel/rope.metal:50-57)
+        r1 = r0 + half;
+    } else {
+        r0 = 2 * u;
+        r1 = r0 + 1;
+    }
+}
+
+// K1: y = epilogue( prologue(x) . W^T ).  grid: any; CTA = 8 warps = (8/KSPLIT) units x KSPLIT k-slices.
+template <int MB, int KSPLIT, int PRO, int EPI>
+__global__ void __launch_bounds__(kGemvThreads, 2) gemv_bf16_kernel(const gemv_params p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint16_t* sx = reinterpret_cast<uint16_t*>(smem);                      // [MB][K] bf16
+    float* sred = reinterpret_cast<float*>(smem + size_t(MB) * p.K * 2);   // [8 warps][2][MB]
+    float* sscr = sred + kGemvWarps * 2 * MB;                              // [8]
+
+    constexpr int UPC = kGemvWarps / KSPLIT; // units per CTA iteration
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t slot = warp / KSPLIT, ks = warp % KSPLIT;
+    const uint32_t units = p.N >> 1;
+    const uint32_t kslice = p.K / KSPLIT;
+    const uint32_t kbeg = ks * kslice, kend = kbeg + kslice;
+    const uint16_t* Wb = static_cast<const uint16_t*>(p.W);
+
+    uint32_t u = blockIdx.x * UPC + slot;
+    const uint32_t ustride = gridDim.x * UPC;
+
+    // -- prefetch the first weight chunk before touching the activations (they may still be in
+    //    flight from the producer kernel under programmatic dependent launch)
+    constexpr int U = 4; // 16-byte loads in flight per row per lane
+    uint4 w0[U], w1[U];
+    uint32_t r0 = 0, r1 = 0;
+    if (u < units) {
+        unit_rows<EPI>(p, u, r0, r1);
+#pragma unroll
+        for (int i = 0; i < U; i++) {
+            const uint32_t k = kbeg + (i * 32 + lane) * 8;
+            if (k < kend) {
+                w0[i] = ldg_stream(Wb + size_t(r0) * p.K + k);
+                w1[i] = ldg_stream(Wb + size_t(r1) * p.K + k);
+            }
+        }
+    }
+    pdl_launch_dependents();
+    pdl_wait();
+
+    // -- prologue: stage the activation rows in shared memory as bf16
+    if (PRO == PRO_RMSNORM) {
+        // n = r((0 + w) * x * rsqrt(mean(x^2) + eps))  (kernel/rmsnorm.metal:53-89)
+        for (int m = 0; m < MB; m++) {
+            if (uint32_t(m) < p.rows) {
+                const uint16_t* xr = p.x + size_t(m) * p.ldx;
+                float part = 0.0f;
+                for (uint32_t k = threadIdx.x * 8; k < p.K; k += kGemvThreads * 8) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(xr + k);
+                    float f;
+                    f = bf_lo(v.x), part = fmaf(f, f, part);
+                    f = bf_hi(v.x), part = fmaf(f, f, part);
+                    f = bf_lo(v.y), part = fmaf(f, f, part);
+                    f = bf_hi(v.y), part = fmaf(f, f, part);
+                    f = bf_lo(v.z), part = fmaf(f, f, part);
+                    f = bf_hi(v.z), part = fmaf(f, f, part);
+                    f = bf_lo(v.w), part = fmaf(f, f, part);
+                    f = bf_hi(v.w), part = fmaf(f, f, part);
+                }
+                const float total = block_sum_256(part, sscr);
+                const float inv = 1.0f / sqrtf(__fadd_rn(total / float(p.K), p.eps));
+                for (uint32_t k = threadIdx.x * 8; k < p.K; k += kGemvThreads * 8) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(xr + k);
+                    const uint4 g = *reinterpret_cast<const uint4*>(p.norm_w + k);
+                    uint4 o;
+#define MC_NORM2(dst, vv, gg)                                                                                   \
+    dst = uint32_t(f32_to_bf16_bits(__fmul_rn(__fmul_rn(bf_lo(gg), bf_lo(vv)), inv))) |                         \
+          (uint32_t(f32_to_bf16_bits(__fmul_rn(__fmul_rn(bf_hi(gg), bf_hi(vv)), inv))) << 16)
+                    MC_NORM2(o.x, v.x, g.x);
+                    MC_NORM2(o.y, v.y, g.y);
+                    MC_NORM2(o.z, v.z, g.z);
+                    MC_NORM2(o.w, v.w, g.w);
+#undef MC_NORM2
+                    *reinterpret_cast<uint4*>(sx + size_t(m) * p.K + k) = o;
+                }
+            }
+        }
+    } else {
+        for (int m = 0; m < MB; m++) {
+            if (uint32_t(m) < p.rows) {
+                const uint16_t* xr = p.x + size_t(m) * p.ldx;
+                for (uint32_t k = threadIdx.x * 8; k < p.K; k += kGemvThreads * 8)
+                    *reinterpret_cast<uint4*>(sx + size_t(m) * p.K + k) = *reinterpret_cast<const uint4*>(xr + k);
+            }
+        }
+    }
+    __syncthreads();
+
+    for (; u - slot < units; u += ustride) { // loop bound is CTA-uniform (u - slot is the CTA's first unit)
+        const bool active = u < units;
+        float acc0[MB], acc1[MB];
+#pragma unroll
+        for (int m = 0; m < MB; m++) acc0[m] = 0.0f, acc1[m] = 0.0f;
+        uint32_t n0 = 0, n1 = 0;
+        const uint32_t un = u + ustride;
+        const bool next_active = un < units;
+        if (active) {
+            for (uint32_t kc = kbeg; kc < kend; kc += U * 256) {
+                // issue the next chunk (or the first chunk of this warp's next unit) before consuming
+                uint4 nw0[U], nw1[U];
+                const uint32_t kn = kc + U * 256;
+                const bool more = kn < kend;
+                if (more) {
+#pragma unroll
+                    for (int i = 0; i < U; i++) {
+                        const uint32_t k = kn + (i * 32 + lane) * 8;
+                        if (k < kend) {
+                            nw0[i] = ldg_stream(Wb + size_t(r0) * p.K + k);
+                            nw1[i] = ldg_stream(Wb + size_t(r1) * p.K + k);
+                        }
+                    }
+                } else if (next_active) {
+                    unit_rows<EPI>(p, un, n0, n1);
+#pragma unroll
+                    for (int i = 0; i < U; i++) {
+                        const uint32_t k = kbeg + (i * 32 + lane) * 8;
+                        if (k < kend) {
+                            nw0[i] = ldg_stream(Wb + size_t(n0) * p.K + k);
+                            nw1[i] = ldg_stream(Wb + size_t(n1) * p.K + k);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < U; i++) {
+                    const uint32_t k = kc + (i * 32 + lane) * 8;
+                    if (k < kend) {
+#pragma unroll
+                        for (int m = 0; m < MB; m++) {
+                            const uint4 xv = *reinterpret_cast<const uint4*>(sx + size_t(m) * p.K + k);
+                            acc0[m] = dot8(w0[i], xv, acc0[m]);
+                            acc1[m] = dot8(w1[i], xv, acc1[m]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < U; i++) w0[i] = nw0[i], w1[i] = nw1[i];
+            }
+        }
+        // -- reduce over lanes, then over the KSPLIT k-slices of the unit
+#pragma unroll
+        for (int m = 0; m < MB; m++) {
+            acc0[m] = warp_sum(acc0[m]);
+            acc1[m] = warp_sum(acc1[m]);
+        }
+        if (KSPLIT > 1) {
+            if (lane == 0) {
+#pragma unroll
+                for (int m = 0; m < MB; m++) {
+                    sred[(warp * 2 + 0) * MB + m] = acc0[m];
+                    sred[(warp * 2 + 1) * MB + m] = acc1[m];
+                }
+            }
+            __syncthreads();
+            if (ks == 0) {
+#pragma unroll
+                for (int m = 0; m < MB; m++) {
+                    float a = 0.0f, b = 0.0f;
+#pragma unroll
+                    for (int s = 0; s < KSPLIT; s++) {
+                        a += sred[((warp + s) * 2 + 0) * MB + m];
+                        b += sred[((warp + s) * 2 + 1) * MB + m];
+                    }
+                    acc0[m] = a, acc1[m] = b;
+                }
+            }
+            __syncthreads();
+        }
+        // -- epilogue: lane m finalises activation row m
+        if (active && ks == 0 && lane < p.rows && lane < MB) {
+            float a = 0.0f, b = 0.0f;
+#pragma unroll
+            for (int m = 0; m < MB; m++)
+                if (lane == uint32_t(m)) a = acc0[m], b = acc1[m];
+            const uint32_t m = lane;
+            float y0 = rbf(a), y1 = rbf(b); // the bmm output buffer is T (kernel/bmm.metal:76)
+            if (p.lora_b) {
+                // lora_linear: y = r(y + r(r(B . ax) * scale))  (quantization/lora.h:115-122)
+                float l0 = 0.0f, l1 = 0.0f;
+                for (uint32_t j = 0; j < p.lora_rank; j++) {
+                    const float axj = bf16_bits_to_f32(p.lora_ax[m * p.lora_rank + j]);
+                    l0 = fmaf(axj, bf16_bits_to_f32(p.lora_b[size_t(r0) * p.lora_rank + j]), l0);
+                    l1 = fmaf(axj, bf16_bits_to_f32(p.lora_b[size_t(r1) * p.lora_rank + j]), l1);
+                }
+                y0 = rbf(__fadd_rn(y0, rbf(__fmul_rn(rbf(l0), p.lora_scale))));
+                y1 = rbf(__fadd_rn(y1, rbf(__fmul_rn(rbf(l1), p.lora_scale))));
+            }
+            if (EPI == EPI_NONE) {
+                p.y[size_t(m) * p.ldy + r0] = f32_to_bf16_bits(y0);
+                p.y[size_t(m) * p.ldy + r1] = f32_to_bf16_bits(y1);
+            } else if (EPI == EPI_RESIDUAL) {
+                // h = r(x + a)  (nn/transformer.h:133,139; kernel/arithmetic.metal:21-43)
+                const float e0 = bf16_bits_to_f32(p.res[size_t(m) * p.ldy + r0]);
+                const float e1 = bf16_bits_to_f32(p.res[size_t(m) * p.ldy + r1]);
+                p.y[size_t(m) * p.ldy + r0] = f32_to_bf16_bits(__fadd_rn(e0, y0));
+                p.y[size_t(m) * p.ldy + r1] = f32_to_bf16_bits(__fadd_rn(e1, y1));
+            } else if (EPI == EPI_SWIGLU) {
+                // z = r(silu_T(g) * u), rows (2i, 2i+1) = (w1 row i, w3 row i)  (nn/transformer.h:57-59)
+                p.y[size_t(m) * p.ldy + (r0 >> 1)] = f32_to_bf16_bits(__fmul_rn(silu_bf16(y0), y1));
+            } else { // EPI_QKV
+                const uint32_t hd = p.head_dim, half = hd >> 1;
+                const uint32_t head = r0 / hd, j = r0 - head * hd;
+                const int32_t pos = p.row_pos[m], seq = p.row_seq[m];
+                if (head < p.n_heads + p.n_kv_heads) {
+                    // rope in fp32 with fp32 tables, one rounding (kernel/rope.metal:47-58)
+                    const float c = p.fcos[size_t(pos) * half + j], s = p.fsin[size_t(pos) * half + j];
+                    const float o0 = rbf(__fsub_rn(__fmul_rn(c, y0), __fmul_rn(s, y1)));
+                    const float o1 = rbf(__fadd_rn(__fmul_rn(s, y0), __fmul_rn(c, y1)));
+                    y0 = o0, y1 = o1;
+                }
+                if (head < p.n_heads) {
+                    uint16_t* dst = p.q + size_t(m) * p.n_heads * hd + size_t(head) * hd + j;
+                    dst[0] = f32_to_bf16_bits(y0);
+                    dst[half] = f32_to_bf16_bits(y1);
+                } else {
+                    // sink_cache::update: bit copy into position pos (nn/cache.h:207-214)
+                    const bool is_k = head < p.n_heads + p.n_kv_heads;
+                    const uint32_t kvh = is_k ? head - p.n_heads : head - p.n_heads - p.n_kv_heads;
+                    uint16_t* base = is_k ? p.kcache : p.vcache;
+                    uint16_t* dst = base + ((size_t(seq) * p.n_kv_heads + kvh) * p.max_seq + size_t(pos)) * hd + j;
+                    dst[0] = f32_to_bf16_bits(y0);
+                    dst[half] = f32_to_bf16_bits(y1);
+                }
+            }
+        }
+        r0 = n0, r1 = n1;
+    }
+}
+
+// ---- K5: decode attention ------------------------------------------------------------------------------------
+// One CTA per (head, activation row).  Reference chain per head (nn/attention.h:195-203):
+//   s = r(q . K[t]); s = r(s * scale); p = r(exp(s) * (1 / sum exp(s))) (no max shift, quirk Q1);
+//   o = r(sum_t p[t] * V[t]).  repeat_kv is replaced by kv = head / n_reps (no copies).
+struct attn_params {
+    const uint16_t* q;      // [rows, H*hd] (roped)
+    const uint16_t* kcache; // this layer: [n_seqs, KV, S, hd]
+    const uint16_t* vcache;
+    uint16_t* out;          // [rows, H*hd]
+    const int32_t* row_seq;
+    const int32_t* row_pos;
+    uint32_t n_heads, n_kv_heads, max_seq;
+    float scale;            // r(1/sqrt(hd)) stored as T (nn/attention.h:88,115; quirk Q4)
+};
+
+template <int HD> __global__ void __launch_bounds__(256) attn_decode_kernel(const attn_params p)
+{
+    constexpr int LPP = HD / 8;      // lanes per position row (16 bytes each)
+    constexpr int PPW = 32 / LPP;    // positions per warp load
+    constexpr int G = 256 / LPP;     // position groups in the PV phase
+    extern __shared__ __align__(16) unsigned char smem[];
+    float* sq = reinterpret_cast<float*>(smem);  // [HD]
+    float* scr = sq + HD;                        // [8]
+    float* spart = scr + 8;                      // [G][HD]
+    float* sp = spart + G * HD;                  // [P]
+
+    pdl_launch_dependents();
+    pdl_wait();
+
+    const uint32_t head = blockIdx.x, row = blockIdx.y;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t seq = p.row_seq[row];
+    const uint32_t P = uint32_t(p.row_pos[row]) + 1;
+    const uint32_t kvh = head / (p.n_heads / p.n_kv_heads);
+    const size_t coff = (size_t(seq) * p.n_kv_heads + kvh) * p.max_seq * HD;
+    const uint16_t* Kc = p.kcache + coff;
+    const uint16_t* Vc = p.vcache + coff;
+
+    if (threadIdx.x < HD) sq[threadIdx.x] = bf16_bits_to_f32(p.q[(size_t(row) * p.n_heads + head) * HD + threadIdx.x]);
+    __syncthreads();
+
+    // scores
+    const uint32_t sub = lane / LPP, dl = lane % LPP;
+    float qv[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) qv[i] = sq[dl * 8 + i];
+    for (uint32_t tb = warp * PPW; tb < P; tb += 8 * PPW) {
+        const uint32_t t = tb + sub;
+        float d = 0.0f;
+        if (t < P) {
+            const uint4 kv = *reinterpret_cast<const uint4*>(Kc + size_t(t) * HD + dl * 8);
+            d = fmaf(qv[0], bf_lo(kv.x), d);
+            d = fmaf(qv[1], bf_hi(kv.x), d);
+            d = fmaf(qv[2], bf_lo(kv.y), d);
+            d = fmaf(qv[3], bf_hi(kv.y), d);
+            d = fmaf(qv[4], bf_lo(kv.z), d);
+            d = fmaf(qv[5], bf_hi(kv.z), d);
+            d = fmaf(qv[6], bf_lo(kv.w), d);
+            d = fmaf(qv[7], bf_hi(kv.w), d);
+        }
+#pragma unroll
+        for (int off = LPP / 2; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+        if (t < P && dl == 0) sp[t] = rbf(__fmul_rn(rbf(d), p.scale));
+    }
+    __syncthreads();
+    // softmax without max subtraction (kernel/softmax.metal:40-80)
+    float part = 0.0f;
+    for (uint32_t t = threadIdx.x; t < P; t += 256) part += expf(sp[t]);
+    const float inv = 1.0f / block_sum_256(part, scr);
+    for (uint32_t t = threadIdx.x; t < P; t += 256) sp[t] = rbf(__fmul_rn(expf(sp[t]), inv));
+    __syncthreads();
+    // o = P . V
+    const uint32_t g = threadIdx.x / LPP, dc = threadIdx.x % LPP;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.0f;
+    for (uint32_t t = g; t < P; t += G) {
+        const uint4 vv = *reinterpret_cast<const uint4*>(Vc + size_t(t) * HD + dc * 8);
+        const float pt = sp[t];
+        acc[0] = fmaf(pt, bf_lo(vv.x), acc[0]);
+        acc[1] = fmaf(pt, bf_hi(vv.x), acc[1]);
+        acc[2] = fmaf(pt, bf_lo(vv.y), acc[2]);
+        acc[3] = fmaf(pt, bf_hi(vv.y), acc[3]);
+        acc[4] = fmaf(pt, bf_lo(vv.z), acc[4]);
+        acc[5] = fmaf(pt, bf_hi(vv.z), acc[5]);
+        acc[6] = fmaf(pt, bf_lo(vv.w), acc[6]);
+        acc[7] = fmaf(pt, bf_hi(vv.w), acc[7]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) spart[g * HD + dc * 8 + i] = acc[i];
+    __syncthreads();
+    if (threadIdx.x < HD) {
+        float o = 0.0f;
+        for (int gg = 0; gg < G; gg++) o += spart[gg * HD + threadIdx.x];
+        p.out[(size_t(row) * p.n_heads + head) * HD + threadIdx.x] = f32_to_bf16_bits(o);
+    }
+}
+
+// ---- K6: embedding gather (kernel/embedding.metal:38-66; lora_embedding quantization/lora.h:160-170) -----------
+__global__ void embed_kernel(uint16_t* x, uint32_t ldx, const void* table, const float* row_scales, int fmt, uint32_t D,
+                             uint32_t vocab, const int32_t* ids)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t row = blockIdx.x;
+    int32_t id = ids[row];
+    if (id < 0 || uint32_t(id) >= vocab) id = 0; // validated on the host for host-provided ids
+    if (fmt == WF_BF16) {
+        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(table) + size_t(id) * D);
+        uint4* dst = reinterpret_cast<uint4*>(x + size_t(row) * ldx);
+        for (uint32_t k = threadIdx.x; k < D / 8; k += blockDim.x) dst[k] = src[k];
+    } else {
+        const int8_t* src = static_cast<const int8_t*>(table) + size_t(id) * D;
+        const float s = rbf(row_scales[id]);
+        for (uint32_t k = threadIdx.x; k < D; k += blockDim.x)
+            x[size_t(row) * ldx + k] = f32_to_bf16_bits(__fmul_rn(float(src[k]), s)); // r(r(q) * r(s)), kernel/mul.metal:76-77
+    }
+}
+
+// ---- K7g: greedy argmax, lowest index on ties ---------------------------------------------------------------------
+constexpr int kArgmaxBlocks = 64;
+__global__ void __launch_bounds__(256) argmax_partial_kernel(const uint16_t* logits, uint32_t ld, uint32_t n, float* pval, int32_t* pidx)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ float sv[8];
+    __shared__ int32_t si[8];
+    const uint32_t row = blockIdx.y;
+    const uint16_t* l = logits + size_t(row) * ld;
+    const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+    const uint32_t beg = blockIdx.x * per, end = min(n, beg + per);
+    float bv = -INFINITY;
+    int32_t bi = 0x7fffffff;
+    for (uint32_t i = beg + threadIdx.x; i < end; i += 256) {
+        const float f = bf16_bits_to_f32(l[i]);
+        if (f > bv || (f == bv && int32_t(i) < bi)) bv = f, bi = int32_t(i);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi;
+    }
+    if ((threadIdx.x & 31) == 0) sv[threadIdx.x >> 5] = bv, si[threadIdx.x >> 5] = bi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++)
+            if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) bv = sv[w], bi = si[w];
+        pval[row * gridDim.x + blockIdx.x] = bv;
+        pidx[row * gridDim.x + blockIdx.x] = bi;
+    }
+}
+// final stage + feedback: next id -> ids[row] (input of the next step), pos[row] += 1, log
+__global__ void argmax_final_kernel(const float* pval, const int32_t* pidx, int nblk, int32_t* ids, int32_t* pos, int32_t* out_log,
+                                    int32_t* step_counter, uint32_t rows, int advance)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t row = threadIdx.x;
+    if (row >= rows) return;
+    float bv = -INFINITY;
+    int32_t bi = 0x7fffffff;
+    for (int b = 0; b < nblk; b++) {
+        const float v = pval[row * nblk + b];
+        const int32_t i = pidx[row * nblk + b];
+        if (v > bv || (v == bv && i < bi)) bv = v, bi = i;
+    }
+    if (bi == 0x7fffffff) bi = 0; // all-NaN / -inf row: argmax keeps index 0
+    const int32_t step = *step_counter;
+    out_log[size_t(step) * rows + row] = bi;
+    if (advance) {
+        ids[row] = bi;
+        pos[row] += 1;
+    }
+    __syncthreads();
+    if (row == 0) *step_counter = step + 1;
+}
+
+// ---- synthetic weights (DESIGN.md "Synthetic data"; same hash as the test oracle) ----------------------------------
+// dst[r * dst_ld + c] = value(src_row0 + r, src_col0 + c) of the [*, src_K] tensor `tid`
+__global__ void gen_bf16_kernel(uint16_t* dst, size_t dst_ld, uint32_t rows, uint32_t cols, uint32_t src_row0, uint32_t src_col0,
+                                uint32_t src_K, uint64_t seed, uint64_t tid, float scale, float bias)
+{
+    const uint64_t n = uint64_t(rows) * cols;
+    for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint32_t r = uint32_t(i / cols), c = uint32_t(i % cols);
+        const uint64_t flat = uint64_t(src_row0 + r) * src_K + (src_col0 + c);
+        const uint32_t u24 = uint32_t(hash3(seed, tid, flat) >> 40);
+        const float u = __fsub_rn(__fmul_rn(float(u24), 1.0f / 8388608.0f), 1.0f);
+        const float v = bias == 0.0f ? __fmul_rn(u, scale) : __fadd_rn(bias, __fmul_rn(scale, u));
+        dst[size_t(r) * dst_ld + c] = f32_to_bf16_bits(v);
+    }
+}
+__global__ void gen_f32_scales_kernel(float* dst, size_t dst_ld, uint32_t rows, uint32_t cols, uint32_t src_row0, uint32_t src_col0,
+                                      uint32_t src_K, uint64_t seed, uint64_t tid, float c0)
+{
+    const uint64_t n = uint64_t(rows) * cols;
+    for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint32_t r = uint32_t(i / cols), c = uint32_t(i % cols);
+        const uint64_t flat = uint64_t(src_row0 + r) * src_K + (src_col0 + c);
+        const uint32_t u24 = uint32_t(hash3(seed, tid, flat) >> 40);
+        const float u = __fsub_rn(__fmul_rn(float(u24), 1.0f / 8388608.0f), 1.0f);
+        dst[size_t(r) * dst_ld + c] = __fmul_rn(__fadd_rn(1.0f, __fmul_rn(0.5f, u)), c0);
+    }
+}
+__global__ void gen_i8_kernel(int8_t* dst, size_t dst_ld, uint32_t rows, uint32_t cols, uint32_t src_row0, uint32_t src_col0,
+                              uint32_t src_K, uint64_t seed, uint64_t tid, int32_t lo, uint32_t range)
+{
+    const uint64_t n = uint64_t(rows) * cols;
+    for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint32_t r = uint32_t(i / cols), c = uint32_t(i % cols);
+        const uint64_t flat = uint64_t(src_row0 + r) * src_K + (src_col0 + c);
+        const uint32_t u32 = uint32_t(hash3(seed, tid, flat) >> 32);
+        dst[size_t(r) * dst_ld + c] = int8_t(lo + int32_t((uint64_t(u32) * range) >> 32));
+    }
+}
+
+} // namespace mc

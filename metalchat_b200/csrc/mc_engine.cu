@@ -1,0 +1,756 @@
+// metalchat_b200/csrc/mc_engine.cu — the fused Llama-3 decode engine behind mc_llama_* (include/mc_cuda.h).
+//
+// Replaces the per-token host loop interpreter::read_until -> transformer::transform ->
+// nn::llama3::operator() -> sampler (interpreter.h:360-374, transformer.h:357-364,
+// nn/llama.h:113-134, nn/sampling.h:69-76) with one CUDA-graph replay per token: weights, KV cache
+// and activations stay resident in HBM, the sampled id feeds the next step on the device.
+//
+// HBM layout (local = this tensor-parallel shard):
+//   per layer   wqkv [(Hl+2KVl)*hd, D]   rows: q heads | k heads | v heads      (column-parallel)
+//               wo   [D, Hl*hd]                                                   (row-parallel)
+//               w13  [2*Fl, D]           row 2i = w1 row i (gate), 2i+1 = w3 row i (column-parallel)
+//               w2   [D, Fl]                                                      (row-parallel)
+//               attn_norm[D], ffn_norm[D]
+//   global      tok [V, D], norm [D], out [Vl, D] (aliases tok when tied, huggingface/llama.h:103)
+//   KV cache    [layer][seq][KVl][max_seq][hd] bf16 — one contiguous stream per (seq, kv head)
+//   rope tables fcos/fsin [2*max_seq, hd/2] fp32 (nn/embedding.h:160-176)
+#include "mc_decode_kernels.cuh"
+
+#include <cmath>
+#include <map>
+#include <memory>
+
+using namespace mc;
+
+namespace {
+
+struct dbuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    void alloc(size_t n)
+    {
+        release();
+        bytes = n;
+        cudaError_t e = cudaMalloc(&p, n ? n : 1);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            cudaGetLastError();
+            throw error(MC_ERR_ALLOC, "cuda: engine allocation of " + std::to_string(n) + " bytes failed: " + cudaGetErrorString(e));
+        }
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+// one linear layer in its device format
+struct dlinear {
+    uint32_t N = 0, K = 0; // local shape
+    int fmt = WF_BF16;
+    dbuf w;                // WF_BF16: bf16 [N,K]; WF_W8G/WF_W8ROW: int8 [N,K]; WF_W4: packed [N,K/2]
+    dbuf scales;           // fp32 [N,K/group] or [N]
+    dbuf lora_b;           // bf16 [N, rank]
+    size_t stream_bytes() const { return w.bytes + scales.bytes + lora_b.bytes; }
+};
+
+struct dlayer {
+    dbuf attn_norm, ffn_norm;
+    dlinear wqkv, wo, w13, w2;
+    dbuf lora_a_qkv, lora_a_o, lora_a_13, lora_a_2; // stacked bf16 [16*g, K]
+};
+
+} // namespace
+
+struct mc_llama {
+    mc_device* dev = nullptr;
+    mc_llama_config cfg{};
+    uint32_t Hl = 0, KVl = 0, Fl = 0, Vl = 0; // local (sharded) dims
+    bool finalized = false;
+    bool tied = true;
+    std::vector<dlayer> layers;
+    dlinear tok, out;
+    dbuf norm;
+    dbuf fcos, fsin;
+    dbuf kcache, vcache;
+    // activations
+    uint32_t max_rows = 0;
+    dbuf x, h, q, attn, z, logits, hidden_save;
+    dbuf ids, pos, row_seq, uniforms, out_log, step_counter, pval, pidx;
+    int32_t* pinned = nullptr; // host staging: ids | pos | out
+    float scale_bf16 = 0.0f;
+    std::map<uint64_t, cudaGraphExec_t> graphs;
+    uint32_t launches_per_step = 0;
+    std::vector<const uint16_t*> hidden_ptr; // per seq: where its last hidden row lives
+
+    ~mc_llama()
+    {
+        for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+        if (pinned) cudaFreeHost(pinned);
+        for (auto& l : layers) {
+            for (dbuf* b : {&l.attn_norm, &l.ffn_norm, &l.lora_a_qkv, &l.lora_a_o, &l.lora_a_13, &l.lora_a_2}) b->release();
+            for (dlinear* d : {&l.wqkv, &l.wo, &l.w13, &l.w2}) d->w.release(), d->scales.release(), d->lora_b.release();
+        }
+        for (dlinear* d : {&tok, &out}) d->w.release(), d->scales.release(), d->lora_b.release();
+        for (dbuf* b : {&norm, &fcos, &fsin, &kcache, &vcache, &x, &h, &q, &attn, &z, &logits, &hidden_save, &ids, &pos, &row_seq,
+                        &uniforms, &out_log, &step_counter, &pval, &pidx})
+            b->release();
+    }
+};
+
+namespace {
+
+constexpr uint32_t kMaxLogSteps = 4096;
+
+void use(mc_llama* m)
+{
+    MC_REQUIRE(m != nullptr, "null model");
+    MC_CUDA_CHECK(cudaSetDevice(m->dev->ordinal));
+}
+
+size_t kv_layer_elems(const mc_llama* m) { return size_t(m->cfg.n_seqs) * m->KVl * m->cfg.max_seq_len * m->cfg.head_dim; }
+
+// ---- launch helpers -------------------------------------------------------------------------------------------
+struct launcher {
+    mc_llama* m;
+    cudaStream_t s;
+    bool pdl;
+    uint32_t count = 0;
+    template <typename... KArgs, typename... Args>
+    void go(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args)
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid;
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        if (pdl) {
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+        }
+        MC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+        count++;
+        m->dev->launches.fetch_add(1);
+    }
+};
+
+size_t gemv_smem(uint32_t MB, uint32_t K) { return size_t(MB) * K * 2 + (kGemvWarps * 2 * MB + 8) * sizeof(float); }
+
+template <int MB, int KSPLIT, int PRO, int EPI> void gemv_launch_t(launcher& L, const gemv_params& p)
+{
+    auto kernel = gemv_bf16_kernel<MB, KSPLIT, PRO, EPI>;
+    static bool configured[8] = {false};
+    const int dev = L.m->dev->ordinal;
+    if (!configured[dev & 7]) {
+        MC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        configured[dev & 7] = true;
+    }
+    const size_t smem = gemv_smem(MB, p.K);
+    MC_REQUIRE(smem <= 100 * 1024, "gemv: activation rows do not fit in shared memory");
+    constexpr int UPC = kGemvWarps / KSPLIT;
+    const uint32_t units = p.N / 2;
+    const uint32_t ctas_needed = (units + UPC - 1) / UPC;
+    const uint32_t sms = uint32_t(L.m->dev->prop.multiProcessorCount);
+    const uint32_t grid = ctas_needed < 2 * sms ? ctas_needed : 2 * sms;
+    L.go(kernel, dim3(grid), dim3(kGemvThreads), smem, p);
+}
+
+// choose the k-split so that there is at least ~one unit per resident warp
+template <int MB, int PRO, int EPI> void gemv_launch_mb(launcher& L, const gemv_params& p)
+{
+    MC_REQUIRE(p.N % 2 == 0, "gemv: row count must be even");
+    const uint32_t units = p.N / 2;
+    const uint32_t warps = uint32_t(L.m->dev->prop.multiProcessorCount) * 2 * kGemvWarps;
+    int ksplit = 1;
+    while (ksplit < 8 && units * ksplit < warps && (p.K / (ksplit * 2)) % 256 == 0 && p.K / (ksplit * 2) >= 512) ksplit *= 2;
+    MC_REQUIRE(p.K % (uint32_t(ksplit) * 8) == 0 && p.K % 8 == 0, "gemv: K must be a multiple of 8");
+    switch (ksplit) {
+    case 1: gemv_launch_t<MB, 1, PRO, EPI>(L, p); break;
+    case 2: gemv_launch_t<MB, 2, PRO, EPI>(L, p); break;
+    case 4: gemv_launch_t<MB, 4, PRO, EPI>(L, p); break;
+    default: gemv_launch_t<MB, 8, PRO, EPI>(L, p); break;
+    }
+}
+template <int PRO, int EPI> void gemv_launch(launcher& L, const gemv_params& p)
+{
+    MC_REQUIRE(p.rows >= 1 && p.rows <= uint32_t(kMaxMB), "gemv: unsupported number of activation rows");
+    switch (p.rows) {
+    case 1: gemv_launch_mb<1, PRO, EPI>(L, p); break;
+    case 2: gemv_launch_mb<2, PRO, EPI>(L, p); break;
+    default: gemv_launch_mb<4, PRO, EPI>(L, p); break;
+    }
+}
+
+// Enqueue the forward pass of `rows` activation rows (<= kMaxMB) starting at row offset `row0` of the
+// activation buffers.  Row r reads ids[row0+r], pos[row0+r], row_seq[row0+r].
+//   head_mode: 0 none, 1 logits for every row -> logits[row_seq... caller passes dst], 2 last row only
+void enqueue_rows(mc_llama* m, launcher& L, uint32_t row0, uint32_t rows, int head_mode, uint16_t* logits_dst)
+{
+    const mc_llama_config& c = m->cfg;
+    const uint32_t D = c.dim, hd = c.head_dim;
+    const uint32_t QO = m->Hl * hd;
+    uint16_t* x = m->x.as<uint16_t>() + size_t(row0) * D;
+    uint16_t* h = m->h.as<uint16_t>() + size_t(row0) * D;
+    uint16_t* q = m->q.as<uint16_t>() + size_t(row0) * QO;
+    uint16_t* at = m->attn.as<uint16_t>() + size_t(row0) * QO;
+    uint16_t* z = m->z.as<uint16_t>() + size_t(row0) * m->Fl;
+    const int32_t* ids = m->ids.as<int32_t>() + row0;
+    const int32_t* pos = m->pos.as<int32_t>() + row0;
+    const int32_t* rseq = m->row_seq.as<int32_t>() + row0;
+
+    L.go(embed_kernel, dim3(rows), dim3(256), 0, x, D, (const void*)m->tok.w.p, (const float*)m->tok.scales.p, m->tok.fmt, D, c.vocab, ids);
+
+    for (uint32_t li = 0; li < c.n_layers; li++) {
+        dlayer& ly = m->layers[li];
+        uint16_t* kc = m->kcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
+        uint16_t* vc = m->vcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
+        {
+            gemv_params p{};
+            p.W = ly.wqkv.w.p, p.N = ly.wqkv.N, p.K = D, p.rows = rows;
+            p.x = x, p.ldx = D, p.norm_w = ly.attn_norm.as<uint16_t>(), p.eps = c.norm_eps;
+            p.q = q, p.kcache = kc, p.vcache = vc, p.fcos = m->fcos.as<float>(), p.fsin = m->fsin.as<float>();
+            p.row_seq = rseq, p.row_pos = pos;
+            p.n_heads = m->Hl, p.n_kv_heads = m->KVl, p.head_dim = hd, p.max_seq = c.max_seq_len;
+            gemv_launch<PRO_RMSNORM, EPI_QKV>(L, p);
+        }
+        {
+            attn_params a{};
+            a.q = q, a.kcache = kc, a.vcache = vc, a.out = at, a.row_seq = rseq, a.row_pos = pos;
+            a.n_heads = m->Hl, a.n_kv_heads = m->KVl, a.max_seq = c.max_seq_len, a.scale = m->scale_bf16;
+            if (hd == 64) {
+                const size_t smem = (64 + 8 + 32 * 64 + c.max_seq_len) * sizeof(float);
+                L.go(attn_decode_kernel<64>, dim3(m->Hl, rows), dim3(256), smem, a);
+            } else {
+                const size_t smem = (128 + 8 + 16 * 128 + c.max_seq_len) * sizeof(float);
+                L.go(attn_decode_kernel<128>, dim3(m->Hl, rows), dim3(256), smem, a);
+            }
+        }
+        {
+            gemv_params p{};
+            p.W = ly.wo.w.p, p.N = D, p.K = QO, p.rows = rows;
+            p.x = at, p.ldx = QO, p.y = h, p.ldy = D, p.res = x;
+            gemv_launch<PRO_NONE, EPI_RESIDUAL>(L, p);
+        }
+        {
+            gemv_params p{};
+            p.W = ly.w13.w.p, p.N = 2 * m->Fl, p.K = D, p.rows = rows;
+            p.x = h, p.ldx = D, p.norm_w = ly.ffn_norm.as<uint16_t>(), p.eps = c.norm_eps;
+            p.y = z, p.ldy = m->Fl;
+            gemv_launch<PRO_RMSNORM, EPI_SWIGLU>(L, p);
+        }
+        {
+            gemv_params p{};
+            p.W = ly.w2.w.p, p.N = D, p.K = m->Fl, p.rows = rows;
+            p.x = z, p.ldx = m->Fl, p.y = x, p.ldy = D, p.res = h;
+            gemv_launch<PRO_NONE, EPI_RESIDUAL>(L, p);
+        }
+    }
+    if (head_mode) {
+        const dlinear& hw = m->tied ? m->tok : m->out;
+        gemv_params p{};
+        p.W = hw.w.p, p.N = m->Vl, p.K = D;
+        p.norm_w = m->norm.as<uint16_t>(), p.eps = c.norm_eps;
+        p.ldx = D, p.ldy = m->Vl;
+        if (head_mode == 2) {
+            p.rows = 1, p.x = x + size_t(rows - 1) * D, p.y = logits_dst;
+        } else {
+            p.rows = rows, p.x = x, p.y = logits_dst;
+        }
+        gemv_launch<PRO_RMSNORM, EPI_NONE>(L, p);
+    }
+}
+
+void enqueue_sample(mc_llama* m, launcher& L, uint32_t rows, const mc_sampler_config& sc, int advance)
+{
+    MC_REQUIRE(sc.mode == 0, "sampler mode not supported by this build (greedy only)");
+    L.go(argmax_partial_kernel, dim3(kArgmaxBlocks, rows), dim3(256), 0, (const uint16_t*)m->logits.p, m->Vl, m->Vl,
+         m->pval.as<float>(), m->pidx.as<int32_t>());
+    L.go(argmax_final_kernel, dim3(1), dim3(((rows + 31) / 32) * 32), 0, (const float*)m->pval.p, (const int32_t*)m->pidx.p,
+         kArgmaxBlocks, m->ids.as<int32_t>(), m->pos.as<int32_t>(), m->out_log.as<int32_t>(), m->step_counter.as<int32_t>(), rows, advance);
+}
+
+// one decode step for rows [0, n): forward in chunks of kMaxMB rows, then sample
+void enqueue_decode_step(mc_llama* m, launcher& L, uint32_t n, const mc_sampler_config& sc, int advance)
+{
+    for (uint32_t r0 = 0; r0 < n; r0 += kMaxMB) {
+        const uint32_t rows = std::min<uint32_t>(kMaxMB, n - r0);
+        enqueue_rows(m, L, r0, rows, 1, m->logits.as<uint16_t>() + size_t(r0) * m->Vl);
+    }
+    enqueue_sample(m, L, n, sc, advance);
+}
+
+cudaGraphExec_t decode_graph(mc_llama* m, uint32_t n, const mc_sampler_config& sc, int advance)
+{
+    const uint64_t key = (uint64_t(n) << 32) | (uint64_t(sc.mode) << 8) | (uint64_t(sc.intended) << 4) | uint64_t(advance);
+    auto it = m->graphs.find(key);
+    if (it != m->graphs.end()) return it->second;
+    cudaStream_t s = m->dev->stream;
+    launcher L{m, s, !(m->cfg.flags & MC_LLAMA_NO_PDL)};
+    MC_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    cudaGraph_t g = nullptr;
+    try {
+        enqueue_decode_step(m, L, n, sc, advance);
+    } catch (...) {
+        cudaStreamEndCapture(s, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+    }
+    MC_CUDA_CHECK(cudaStreamEndCapture(s, &g));
+    cudaGraphExec_t ex = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    MC_CUDA_CHECK(e);
+    m->graphs[key] = ex;
+    m->launches_per_step = L.count;
+    return ex;
+}
+
+void run_decode_step(mc_llama* m, uint32_t n, const mc_sampler_config& sc, int advance)
+{
+    if (m->cfg.flags & MC_LLAMA_NO_GRAPH) {
+        launcher L{m, m->dev->stream, !(m->cfg.flags & MC_LLAMA_NO_PDL)};
+        enqueue_decode_step(m, L, n, sc, advance);
+        m->launches_per_step = L.count;
+    } else {
+        cudaGraphExec_t ex = decode_graph(m, n, sc, advance);
+        MC_CUDA_CHECK(cudaGraphLaunch(ex, m->dev->stream));
+        m->dev->launches.fetch_add(m->launches_per_step);
+    }
+}
+
+// ---- parameter names ---------------------------------------------------------------------------------------------
+struct slice2d {
+    void* dst;          // device destination of element (0,0) of the slice
+    size_t dst_ld;      // destination row pitch in elements
+    uint32_t rows, cols;
+    uint32_t src_row0, src_col0, src_K; // slice origin and row length of the full tensor
+    size_t elem;        // bytes per element
+    uint64_t full_elems;
+};
+
+bool parse_layer_name(const std::string& name, uint32_t& layer, std::string& rest)
+{
+    if (name.rfind("layers.", 0) != 0) return false;
+    const size_t dot = name.find('.', 7);
+    if (dot == std::string::npos) return false;
+    layer = uint32_t(std::stoul(name.substr(7, dot - 7)));
+    rest = name.substr(dot + 1);
+    return true;
+}
+
+// Resolves a reference parameter path to its destination slice(s) in the fused device layout.
+std::vector<slice2d> resolve(mc_llama* m, const std::string& name)
+{
+    const mc_llama_config& c = m->cfg;
+    const uint32_t D = c.dim, hd = c.head_dim, T = c.tp_world, r = c.tp_rank;
+    MC_REQUIRE(c.quant == 0, "quantised parameter layout is not available in this build");
+    std::vector<slice2d> out;
+    auto vec = [&](dbuf& b, uint32_t n) { out.push_back({b.p, n, 1, n, 0, 0, n, 2, n}); };
+    uint32_t li = 0;
+    std::string rest;
+    if (name == "tok_embeddings.weight") {
+        out.push_back({m->tok.w.p, D, c.vocab, D, 0, 0, D, 2, uint64_t(c.vocab) * D});
+        if (!m->tied || T > 1) {
+            // the head is vocab-sharded; when tied it is a slice copy of the embedding table
+        }
+    } else if (name == "output.weight") {
+        MC_REQUIRE(!m->tied, "output.weight is tied to tok_embeddings.weight in the bf16 model (huggingface/llama.h:103)");
+        out.push_back({m->out.w.p, D, m->Vl, D, r * m->Vl, 0, D, 2, uint64_t(c.vocab) * D});
+    } else if (name == "norm.weight") {
+        vec(m->norm, D);
+    } else if (parse_layer_name(name, li, rest)) {
+        MC_REQUIRE(li < c.n_layers, "layer index out of range: " + name);
+        dlayer& ly = m->layers[li];
+        uint16_t* wqkv = ly.wqkv.w.as<uint16_t>();
+        const uint32_t QO = c.n_heads * hd, KO = c.n_kv_heads * hd;
+        if (rest == "attention_norm.weight") vec(ly.attn_norm, D);
+        else if (rest == "ffn_norm.weight") vec(ly.ffn_norm, D);
+        else if (rest == "attention.wq.weight") out.push_back({wqkv, D, m->Hl * hd, D, r * m->Hl * hd, 0, D, 2, uint64_t(QO) * D});
+        else if (rest == "attention.wk.weight")
+            out.push_back({wqkv + size_t(m->Hl) * hd * D, D, m->KVl * hd, D, r * m->KVl * hd, 0, D, 2, uint64_t(KO) * D});
+        else if (rest == "attention.wv.weight")
+            out.push_back({wqkv + size_t(m->Hl + m->KVl) * hd * D, D, m->KVl * hd, D, r * m->KVl * hd, 0, D, 2, uint64_t(KO) * D});
+        else if (rest == "attention.wo.weight")
+            out.push_back({ly.wo.w.p, size_t(m->Hl) * hd, D, m->Hl * hd, 0, r * m->Hl * hd, QO, 2, uint64_t(D) * QO});
+        else if (rest == "feed_forward.w1.weight")
+            out.push_back({ly.w13.w.p, size_t(2) * D, m->Fl, D, r * m->Fl, 0, D, 2, uint64_t(c.ffn_dim) * D});
+        else if (rest == "feed_forward.w3.weight")
+            out.push_back({ly.w13.w.as<uint16_t>() + D, size_t(2) * D, m->Fl, D, r * m->Fl, 0, D, 2, uint64_t(c.ffn_dim) * D});
+        else if (rest == "feed_forward.w2.weight")
+            out.push_back({ly.w2.w.p, m->Fl, D, m->Fl, 0, r * m->Fl, c.ffn_dim, 2, uint64_t(D) * c.ffn_dim});
+        else throw error(MC_ERR_NOT_FOUND, "unknown parameter: " + name);
+    } else {
+        throw error(MC_ERR_NOT_FOUND, "unknown parameter: " + name);
+    }
+    return out;
+}
+
+void gen_bf16(mc_llama* m, const slice2d& s, uint64_t seed, uint64_t tid, float scale, float bias)
+{
+    const uint64_t n = uint64_t(s.rows) * s.cols;
+    const unsigned blocks = unsigned(std::min<uint64_t>((n + 255) / 256, 148 * 32));
+    gen_bf16_kernel<<<blocks, 256, 0, m->dev->stream>>>(static_cast<uint16_t*>(s.dst), s.dst_ld, s.rows, s.cols, s.src_row0, s.src_col0,
+                                                        s.src_K, seed, tid, scale, bias);
+    MC_CUDA_CHECK(cudaGetLastError());
+}
+
+// generator kinds shared with the test oracle (DESIGN.md "Synthetic data")
+enum : uint32_t { K_ATTN_NORM = 0, K_FFN_NORM = 1, K_WQ = 2, K_WK = 3, K_WV = 4, K_WO = 5, K_W1 = 6, K_W2 = 7, K_W3 = 8, G_TOK = 0, G_NORM = 1, G_OUT = 2 };
+uint64_t tid_layer(uint32_t layer, uint32_t kind) { return uint64_t(layer + 1) * 256 + kind; }
+
+} // namespace
+
+extern "C" {
+
+mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama** out)
+{
+    MC_API_BEGIN
+    MC_REQUIRE(dev && cfg && out, "bad arguments");
+    MC_CUDA_CHECK(cudaSetDevice(dev->ordinal));
+    mc_llama_config c = *cfg;
+    if (c.n_seqs == 0) c.n_seqs = 1;
+    if (c.tp_world == 0) c.tp_world = 1;
+    MC_REQUIRE(c.tp_world == 1, "tensor parallelism is not available in this build");
+    MC_REQUIRE(c.tp_rank < c.tp_world, "tp_rank out of range");
+    MC_REQUIRE(c.head_dim == 64 || c.head_dim == 128, "head_dim must be 64 or 128");
+    MC_REQUIRE(c.n_heads % c.n_kv_heads == 0, "n_heads must be a multiple of n_kv_heads");
+    MC_REQUIRE(c.n_heads % c.tp_world == 0 && c.n_kv_heads % c.tp_world == 0 && c.ffn_dim % c.tp_world == 0 && c.vocab % c.tp_world == 0,
+               "dimensions are not divisible by the tensor-parallel degree");
+    MC_REQUIRE(c.dim % 256 == 0 && c.ffn_dim % 256 == 0 && (c.n_heads * c.head_dim) % 256 == 0, "dim, ffn_dim and n_heads*head_dim must be multiples of 256");
+    MC_REQUIRE(c.vocab % 2 == 0, "vocab must be even");
+    MC_REQUIRE(c.max_seq_len >= 1 && c.max_seq_len <= 16384, "max_seq_len out of range");
+    MC_REQUIRE(c.quant == 0, "quantised weights are not available in this build");
+    auto m = std::make_unique<mc_llama>();
+    m->dev = dev;
+    m->cfg = c;
+    m->Hl = c.n_heads / c.tp_world, m->KVl = c.n_kv_heads / c.tp_world, m->Fl = c.ffn_dim / c.tp_world, m->Vl = c.vocab / c.tp_world;
+    m->tied = c.quant == 0;
+    const uint32_t D = c.dim, hd = c.head_dim;
+    m->layers.resize(c.n_layers);
+    for (auto& ly : m->layers) {
+        ly.attn_norm.alloc(size_t(D) * 2);
+        ly.ffn_norm.alloc(size_t(D) * 2);
+        ly.wqkv.N = (m->Hl + 2 * m->KVl) * hd, ly.wqkv.K = D;
+        ly.wo.N = D, ly.wo.K = m->Hl * hd;
+        ly.w13.N = 2 * m->Fl, ly.w13.K = D;
+        ly.w2.N = D, ly.w2.K = m->Fl;
+        for (dlinear* d : {&ly.wqkv, &ly.wo, &ly.w13, &ly.w2}) d->w.alloc(size_t(d->N) * d->K * 2);
+    }
+    m->tok.N = c.vocab, m->tok.K = D;
+    m->tok.w.alloc(size_t(c.vocab) * D * 2);
+    m->norm.alloc(size_t(D) * 2);
+    // rope tables on the host with the same libm calls as the scalar reference formula
+    // (kernel/rope.metal:93-97: 1/pow(theta, 2j/dim), cos/sin of pos*freq), 2*max_seq rows (nn/embedding.h:171)
+    {
+        const uint32_t rows = 2 * c.max_seq_len, half = hd / 2;
+        std::vector<float> hc(size_t(rows) * half), hs(size_t(rows) * half);
+        for (uint32_t i = 0; i < rows; i++) {
+            for (uint32_t j = 0; j < half; j++) {
+                const float freq = 1.0f / std::pow(c.rope_theta, 2.0f * float(j) / float(hd));
+                const float angle = float(i) * freq;
+                hc[size_t(i) * half + j] = std::cos(angle);
+                hs[size_t(i) * half + j] = std::sin(angle);
+            }
+        }
+        m->fcos.alloc(hc.size() * 4);
+        m->fsin.alloc(hs.size() * 4);
+        MC_CUDA_CHECK(cudaMemcpy(m->fcos.p, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice));
+        MC_CUDA_CHECK(cudaMemcpy(m->fsin.p, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice));
+    }
+    const size_t kv_bytes = size_t(c.n_layers) * kv_layer_elems(m.get()) * 2;
+    m->kcache.alloc(kv_bytes);
+    m->vcache.alloc(kv_bytes);
+    MC_CUDA_CHECK(cudaMemset(m->kcache.p, 0, kv_bytes));
+    MC_CUDA_CHECK(cudaMemset(m->vcache.p, 0, kv_bytes));
+    m->max_rows = std::max<uint32_t>(c.n_seqs, kMaxMB);
+    const uint32_t R = m->max_rows;
+    m->x.alloc(size_t(R) * D * 2), m->h.alloc(size_t(R) * D * 2);
+    m->q.alloc(size_t(R) * m->Hl * hd * 2), m->attn.alloc(size_t(R) * m->Hl * hd * 2);
+    m->z.alloc(size_t(R) * m->Fl * 2);
+    m->logits.alloc(size_t(R) * m->Vl * 2);
+    m->hidden_save.alloc(size_t(c.n_seqs) * D * 2);
+    m->ids.alloc(R * 4), m->pos.alloc(R * 4), m->row_seq.alloc(R * 4), m->uniforms.alloc(R * 4);
+    m->out_log.alloc(size_t(kMaxLogSteps) * R * 4);
+    m->step_counter.alloc(4);
+    m->pval.alloc(size_t(R) * kArgmaxBlocks * 4), m->pidx.alloc(size_t(R) * kArgmaxBlocks * 4);
+    MC_CUDA_CHECK(cudaMemset(m->logits.p, 0, m->logits.bytes));
+    MC_CUDA_CHECK(cudaMemset(m->hidden_save.p, 0, m->hidden_save.bytes));
+    MC_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&m->pinned), size_t(R) * 4 * 4 + 64, cudaHostAllocDefault));
+    m->scale_bf16 = bf16_bits_to_f32(f32_to_bf16_bits(1.0f / std::sqrt(float(hd))));
+    m->hidden_ptr.assign(c.n_seqs, nullptr);
+    *out = m.release();
+    MC_API_END
+}
+
+mc_status mc_llama_destroy(mc_llama* m)
+{
+    MC_API_BEGIN
+    if (m) {
+        cudaSetDevice(m->dev->ordinal);
+        cudaStreamSynchronize(m->dev->stream);
+        delete m;
+    }
+    MC_API_END
+}
+
+mc_status mc_llama_set_tensor(mc_llama* m, const char* name, const void* host, size_t nbytes)
+{
+    MC_API_BEGIN
+    use(m);
+    MC_REQUIRE(name && host, "bad arguments");
+    for (const slice2d& s : resolve(m, name)) {
+        if (nbytes != s.full_elems * s.elem) {
+            throw error(MC_ERR_INVALID, std::string("parameter ") + name + ": expected " + std::to_string(s.full_elems * s.elem) + " bytes, got " + std::to_string(nbytes));
+        }
+        const char* src = static_cast<const char*>(host) + (size_t(s.src_row0) * s.src_K + s.src_col0) * s.elem;
+        MC_CUDA_CHECK(cudaMemcpy2DAsync(s.dst, s.dst_ld * s.elem, src, size_t(s.src_K) * s.elem, size_t(s.cols) * s.elem, s.rows,
+                                        cudaMemcpyHostToDevice, m->dev->stream));
+    }
+    MC_CUDA_CHECK(cudaStreamSynchronize(m->dev->stream));
+    m->finalized = false;
+    MC_API_END
+}
+
+mc_status mc_llama_init_random(mc_llama* m, uint64_t seed)
+{
+    MC_API_BEGIN
+    use(m);
+    const mc_llama_config& c = m->cfg;
+    const float inv_sqrt_d = 1.0f / std::sqrt(float(c.dim));
+    const float inv_sqrt_qo = 1.0f / std::sqrt(float(c.n_heads * c.head_dim));
+    const float inv_sqrt_f = 1.0f / std::sqrt(float(c.ffn_dim));
+    auto one = [&](const std::string& name, uint64_t tid, float scale, float bias) {
+        for (const slice2d& s : resolve(m, name)) gen_bf16(m, s, seed, tid, scale, bias);
+    };
+    for (uint32_t i = 0; i < c.n_layers; i++) {
+        const std::string p = "layers." + std::to_string(i) + ".";
+        one(p + "attention_norm.weight", tid_layer(i, K_ATTN_NORM), 0.1f, 1.0f);
+        one(p + "ffn_norm.weight", tid_layer(i, K_FFN_NORM), 0.1f, 1.0f);
+        one(p + "attention.wq.weight", tid_layer(i, K_WQ), inv_sqrt_d, 0.0f);
+        one(p + "attention.wk.weight", tid_layer(i, K_WK), inv_sqrt_d, 0.0f);
+        one(p + "attention.wv.weight", tid_layer(i, K_WV), inv_sqrt_d, 0.0f);
+        one(p + "attention.wo.weight", tid_layer(i, K_WO), inv_sqrt_qo, 0.0f);
+        one(p + "feed_forward.w1.weight", tid_layer(i, K_W1), inv_sqrt_d, 0.0f);
+        one(p + "feed_forward.w2.weight", tid_layer(i, K_W2), inv_sqrt_f, 0.0f);
+        one(p + "feed_forward.w3.weight", tid_layer(i, K_W3), inv_sqrt_d, 0.0f);
+    }
+    one("norm.weight", G_NORM, 0.1f, 1.0f);
+    one("tok_embeddings.weight", G_TOK, 0.0625f, 0.0f);
+    MC_CUDA_CHECK(cudaStreamSynchronize(m->dev->stream));
+    m->finalized = false;
+    MC_API_END
+}
+
+mc_status mc_llama_finalize(mc_llama* m)
+{
+    MC_API_BEGIN
+    use(m);
+    m->finalized = true;
+    MC_API_END
+}
+
+mc_status mc_llama_weight_bytes(mc_llama* m, uint64_t* streamed_per_step, uint64_t* resident)
+{
+    MC_API_BEGIN
+    MC_REQUIRE(m, "null model");
+    uint64_t stream = 0, res = 0;
+    for (auto& ly : m->layers) {
+        for (const dlinear* d : {&ly.wqkv, &ly.wo, &ly.w13, &ly.w2}) stream += d->stream_bytes();
+        stream += ly.attn_norm.bytes + ly.ffn_norm.bytes + ly.lora_a_qkv.bytes + ly.lora_a_o.bytes + ly.lora_a_13.bytes + ly.lora_a_2.bytes;
+    }
+    const dlinear& hw = m->tied ? m->tok : m->out;
+    stream += size_t(m->Vl) * m->cfg.dim * (hw.fmt == WF_BF16 ? 2 : 1) + hw.scales.bytes + m->norm.bytes;
+    res = stream + m->kcache.bytes + m->vcache.bytes;
+    if (!m->tied) res += m->tok.stream_bytes();
+    else res += m->tok.w.bytes - size_t(m->Vl) * m->cfg.dim * 2;
+    if (streamed_per_step) *streamed_per_step = stream;
+    if (resident) *resident = res;
+    MC_API_END
+}
+
+mc_status mc_llama_prefill(mc_llama* m, uint32_t seq, const int32_t* ids, uint32_t len, uint32_t start_pos)
+{
+    MC_API_BEGIN
+    use(m);
+    MC_REQUIRE(m->finalized, "mc_llama_finalize must be called before prefill");
+    MC_REQUIRE(ids && len > 0, "prefill: empty input");
+    MC_REQUIRE(seq < m->cfg.n_seqs, "prefill: sequence index out of range");
+    // the sink-cache roll (nn/cache.h:183-204) is not modelled: positions must fit the cache
+    MC_REQUIRE(uint64_t(start_pos) + len <= m->cfg.max_seq_len, "prefill: start_pos + len exceeds max_seq_len");
+    for (uint32_t i = 0; i < len; i++) MC_REQUIRE(ids[i] >= 0 && uint32_t(ids[i]) < m->cfg.vocab, "prefill: token id out of range");
+    cudaStream_t s = m->dev->stream;
+    launcher L{m, s, false};
+    for (uint32_t t0 = 0; t0 < len; t0 += kMaxMB) {
+        const uint32_t rows = std::min<uint32_t>(kMaxMB, len - t0);
+        int32_t* st = m->pinned;
+        for (uint32_t r = 0; r < rows; r++) {
+            st[r] = ids[t0 + r];
+            st[kMaxMB + r] = int32_t(start_pos + t0 + r);
+            st[2 * kMaxMB + r] = int32_t(seq);
+        }
+        MC_CUDA_CHECK(cudaMemcpyAsync(m->ids.p, st, rows * 4, cudaMemcpyHostToDevice, s));
+        MC_CUDA_CHECK(cudaMemcpyAsync(m->pos.p, st + kMaxMB, rows * 4, cudaMemcpyHostToDevice, s));
+        MC_CUDA_CHECK(cudaMemcpyAsync(m->row_seq.p, st + 2 * kMaxMB, rows * 4, cudaMemcpyHostToDevice, s));
+        const bool last = t0 + rows >= len;
+        enqueue_rows(m, L, 0, rows, last ? 2 : 0, m->logits.as<uint16_t>() + size_t(seq) * m->Vl);
+        if (last) {
+            MC_CUDA_CHECK(cudaMemcpyAsync(m->hidden_save.as<uint16_t>() + size_t(seq) * m->cfg.dim,
+                                          m->x.as<uint16_t>() + size_t(rows - 1) * m->cfg.dim, size_t(m->cfg.dim) * 2, cudaMemcpyDeviceToDevice, s));
+        }
+        MC_CUDA_CHECK(cudaStreamSynchronize(s)); // the pinned staging area is reused by the next chunk
+    }
+    MC_API_END
+}
+
+static void stage_decode_inputs(mc_llama* m, uint32_t n, const int32_t* ids, const int32_t* pos)
+{
+    MC_REQUIRE(n >= 1 && n <= m->cfg.n_seqs, "decode: number of sequences out of range");
+    MC_REQUIRE(ids && pos, "decode: null ids/pos");
+    int32_t* st = m->pinned;
+    const uint32_t R = m->max_rows;
+    for (uint32_t r = 0; r < n; r++) {
+        MC_REQUIRE(ids[r] >= 0 && uint32_t(ids[r]) < m->cfg.vocab, "decode: token id out of range");
+        MC_REQUIRE(pos[r] >= 0 && uint32_t(pos[r]) < m->cfg.max_seq_len, "decode: position exceeds max_seq_len (sink roll not modelled)");
+        st[r] = ids[r], st[R + r] = pos[r], st[2 * R + r] = int32_t(r);
+    }
+    cudaStream_t s = m->dev->stream;
+    MC_CUDA_CHECK(cudaMemcpyAsync(m->ids.p, st, n * 4, cudaMemcpyHostToDevice, s));
+    MC_CUDA_CHECK(cudaMemcpyAsync(m->pos.p, st + R, n * 4, cudaMemcpyHostToDevice, s));
+    MC_CUDA_CHECK(cudaMemcpyAsync(m->row_seq.p, st + 2 * R, n * 4, cudaMemcpyHostToDevice, s));
+    MC_CUDA_CHECK(cudaMemsetAsync(m->step_counter.p, 0, 4, s));
+}
+
+mc_status mc_llama_decode(mc_llama* m, uint32_t n, const int32_t* ids, const int32_t* pos, const float* uniforms,
+                          const mc_sampler_config* sampler, int32_t* out_ids)
+{
+    MC_API_BEGIN
+    use(m);
+    MC_REQUIRE(m->finalized, "mc_llama_finalize must be called before decode");
+    MC_REQUIRE(out_ids, "decode: null output");
+    mc_sampler_config sc{};
+    if (sampler) sc = *sampler;
+    (void)uniforms;
+    stage_decode_inputs(m, n, ids, pos);
+    run_decode_step(m, n, sc, 0);
+    cudaStream_t s = m->dev->stream;
+    int32_t* st_out = m->pinned + 3 * m->max_rows;
+    MC_CUDA_CHECK(cudaMemcpyAsync(st_out, m->out_log.p, n * 4, cudaMemcpyDeviceToHost, s));
+    MC_CUDA_CHECK(cudaStreamSynchronize(s));
+    memcpy(out_ids, st_out, n * 4);
+    MC_API_END
+}
+
+mc_status mc_llama_decode_loop(mc_llama* m, uint32_t n, const int32_t* first_ids, const int32_t* first_pos, uint32_t steps,
+                               const float* uniforms, const mc_sampler_config* sampler, int32_t* out_ids, float* elapsed_ms)
+{
+    MC_API_BEGIN
+    use(m);
+    MC_REQUIRE(m->finalized, "mc_llama_finalize must be called before decode");
+    MC_REQUIRE(steps >= 1 && steps <= kMaxLogSteps, "decode_loop: steps out of range");
+    mc_sampler_config sc{};
+    if (sampler) sc = *sampler;
+    (void)uniforms;
+    stage_decode_inputs(m, n, first_ids, first_pos);
+    for (uint32_t r = 0; r < n; r++)
+        MC_REQUIRE(uint64_t(first_pos[r]) + steps <= m->cfg.max_seq_len, "decode_loop: positions would exceed max_seq_len");
+    cudaStream_t s = m->dev->stream;
+    cudaEvent_t e0, e1;
+    MC_CUDA_CHECK(cudaEventCreate(&e0));
+    MC_CUDA_CHECK(cudaEventCreate(&e1));
+    if (!(m->cfg.flags & MC_LLAMA_NO_GRAPH)) decode_graph(m, n, sc, 1); // instantiate outside the timed region
+    MC_CUDA_CHECK(cudaEventRecord(e0, s));
+    for (uint32_t i = 0; i < steps; i++) run_decode_step(m, n, sc, 1);
+    MC_CUDA_CHECK(cudaEventRecord(e1, s));
+    MC_CUDA_CHECK(cudaStreamSynchronize(s));
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    if (elapsed_ms) *elapsed_ms = ms;
+    if (out_ids) MC_CUDA_CHECK(cudaMemcpy(out_ids, m->out_log.p, size_t(steps) * n * 4, cudaMemcpyDeviceToHost));
+    MC_API_END
+}
+
+mc_status mc_llama_logits(mc_llama* m, uint32_t seq, void* host_bf16, size_t nbytes)
+{
+    MC_API_BEGIN
+    use(m);
+    MC_REQUIRE(seq < m->cfg.n_seqs && host_bf16, "bad arguments");
+    MC_REQUIRE(nbytes == size_t(m->Vl) * 2, "logits: expected vocab*2 bytes");
+    MC_CUDA_CHECK(cudaStreamSynchronize(m->dev->stream));
+    MC_CUDA_CHECK(cudaMemcpy(host_bf16, m->logits.as<uint16_t>() + size_t(seq) * m->Vl, nbytes, cudaMemcpyDeviceToHost));
+    MC_API_END
+}
+
+mc_status mc_llama_hidden(mc_llama* m, uint32_t seq, void* host_bf16, size_t nbytes)
+{
+    MC_API_BEGIN
+    use(m);
+    MC_REQUIRE(seq < m->cfg.n_seqs && host_bf16, "bad arguments");
+    MC_REQUIRE(nbytes == size_t(m->cfg.dim) * 2, "hidden: expected dim*2 bytes");
+    MC_CUDA_CHECK(cudaStreamSynchronize(m->dev->stream));
+    MC_CUDA_CHECK(cudaMemcpy(host_bf16, m->hidden_save.as<uint16_t>() + size_t(seq) * m->cfg.dim, nbytes, cudaMemcpyDeviceToHost));
+    MC_API_END
+}
+
+// Copies rows [0, n_pos) of the (seq, layer) cache in the reference layout [pos, n_kv_heads, head_dim]
+// (nn/cache.h:150-160); the device layout is [kv head][pos][hd].
+mc_status mc_llama_cache(mc_llama* m, uint32_t seq, uint32_t layer, int which, uint32_t n_pos, void* host_bf16, size_t nbytes)
+{
+    MC_API_BEGIN
+    use(m);
+    const mc_llama_config& c = m->cfg;
+    MC_REQUIRE(seq < c.n_seqs && layer < c.n_layers && host_bf16 && n_pos <= c.max_seq_len, "bad arguments");
+    MC_REQUIRE(nbytes == size_t(n_pos) * m->KVl * c.head_dim * 2, "cache: unexpected size");
+    MC_CUDA_CHECK(cudaStreamSynchronize(m->dev->stream));
+    const uint16_t* base = (which ? m->vcache : m->kcache).as<uint16_t>() + size_t(layer) * kv_layer_elems(m) +
+                           size_t(seq) * m->KVl * c.max_seq_len * c.head_dim;
+    for (uint32_t kvh = 0; kvh < m->KVl; kvh++) {
+        MC_CUDA_CHECK(cudaMemcpy2D(static_cast<uint16_t*>(host_bf16) + size_t(kvh) * c.head_dim, size_t(m->KVl) * c.head_dim * 2,
+                                   base + size_t(kvh) * c.max_seq_len * c.head_dim, size_t(c.head_dim) * 2, size_t(c.head_dim) * 2, n_pos,
+                                   cudaMemcpyDeviceToHost));
+    }
+    MC_API_END
+}
+
+mc_status mc_llama_launches_per_step(mc_llama* m, uint32_t* kernels)
+{
+    MC_API_BEGIN
+    MC_REQUIRE(m && kernels, "bad arguments");
+    *kernels = m->launches_per_step;
+    MC_API_END
+}
+
+// ---- stand-alone linear (roofline measurement, parity tests) ------------------------------------------------------------
+mc_status mc_linear_bf16(mc_device* dev, mc_buffer* y, mc_buffer* x, mc_buffer* w, uint32_t M, uint32_t N, uint32_t K)
+{
+    MC_API_BEGIN
+    MC_REQUIRE(dev && y && x && w, "bad arguments");
+    MC_CUDA_CHECK(cudaSetDevice(dev->ordinal));
+    MC_REQUIRE(M >= 1 && M <= uint32_t(kMaxMB), "linear_bf16: M must be in [1,4] for the streaming GEMV path");
+    MC_REQUIRE(N % 2 == 0 && K % 256 == 0, "linear_bf16: N must be even and K a multiple of 256");
+    MC_REQUIRE(w->size >= size_t(N) * K * 2 && x->size >= size_t(M) * K * 2 && y->size >= size_t(M) * N * 2, "linear_bf16: buffer too small");
+    mc_llama shim;
+    shim.dev = dev;
+    launcher L{&shim, dev->stream, false};
+    gemv_params p{};
+    p.W = w->dptr, p.N = N, p.K = K, p.rows = M;
+    p.x = static_cast<const uint16_t*>(x->dptr), p.ldx = K;
+    p.y = static_cast<uint16_t*>(y->dptr), p.ldy = N;
+    gemv_launch<PRO_NONE, EPI_NONE>(L, p);
+    MC_API_END
+}
+
+mc_status mc_linear_w4(mc_device*, mc_buffer*, mc_buffer*, mc_buffer*, mc_buffer*, uint32_t, uint32_t, uint32_t)
+{
+    return fail(MC_ERR_RUNTIME, "linear_w4 is not available in this build");
+}
+mc_status mc_pack_w4(mc_device*, mc_buffer*, mc_buffer*, uint32_t, uint32_t) { return fail(MC_ERR_RUNTIME, "pack_w4 is not available in this build"); }
+mc_status mc_unpack_w4(mc_device*, mc_buffer*, mc_buffer*, uint32_t, uint32_t) { return fail(MC_ERR_RUNTIME, "unpack_w4 is not available in this build"); }
+
+} // extern "C"
