@@ -131,7 +131,8 @@ typedef struct mc_llama_config {
 enum {
     MC_LLAMA_W4_PACKED = 1u << 0, /* store QLoRA int8-in-int4-range weights two per byte       */
     MC_LLAMA_NO_GRAPH = 1u << 1,  /* launch kernels directly instead of replaying a CUDA graph  */
-    MC_LLAMA_NO_PDL = 1u << 2     /* no programmatic dependent launch between decode kernels    */
+    MC_LLAMA_NO_PDL = 1u << 2,    /* no programmatic dependent launch between decode kernels    */
+    MC_LLAMA_MEGAKERNEL = 1u << 3 /* experimental: the whole decode step as ONE persistent kernel with grid barriers */
 };
 typedef struct mc_sampler_config {
     uint32_t mode;       /* 0 greedy argmax (lowest index on ties); 1 top-k -> nucleus -> multinomial (nn/sampling.h:306-316) */
@@ -172,6 +173,8 @@ MC_API mc_status mc_llama_logits(mc_llama* m, uint32_t seq, void* host_bf16, siz
 MC_API mc_status mc_llama_hidden(mc_llama* m, uint32_t seq, void* host_bf16, size_t nbytes);
 MC_API mc_status mc_llama_cache(mc_llama* m, uint32_t seq, uint32_t layer, int which, uint32_t n_pos, void* host_bf16, size_t nbytes);
 MC_API mc_status mc_llama_launches_per_step(mc_llama* m, uint32_t* kernels);
+/* Diagnostics: one ungraphed decode step with a CUDA event before every launch; us[i] = device time of launch i. */
+MC_API mc_status mc_llama_profile_step(mc_llama* m, uint32_t n, float* us, uint32_t cap, uint32_t* count);
 
 /* ---- stand-alone hot kernels (for roofline measurement and parity tests) -----------
  * y[M,N] = x[M,K] * W[N,K]^T with fp32 accumulation and one RNE rounding to bf16

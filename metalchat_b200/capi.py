@@ -16,7 +16,7 @@ LIB_PATH = HERE / "libmc_cuda.so"
 
 MC_OK, MC_ERR_INVALID, MC_ERR_RUNTIME, MC_ERR_ALLOC, MC_ERR_NOT_FOUND, MC_ERR_FULL = range(6)
 MEM_DEVICE, MEM_SHARED, MEM_PINNED = 0, 1, 2
-LLAMA_W4_PACKED, LLAMA_NO_GRAPH, LLAMA_NO_PDL = 1, 2, 4
+LLAMA_W4_PACKED, LLAMA_NO_GRAPH, LLAMA_NO_PDL, LLAMA_MEGAKERNEL = 1, 2, 4, 8
 
 
 class McError(RuntimeError):
@@ -118,6 +118,7 @@ _SIGNATURES = {
     "mc_llama_hidden": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
     "mc_llama_cache": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_size_t]),
     "mc_llama_launches_per_step": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
+    "mc_llama_profile_step": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
     "mc_linear_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "mc_linear_w4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "mc_pack_w4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
@@ -387,6 +388,12 @@ class Llama:
         out = np.zeros((n_pos, kvl, self.cfg.head_dim), dtype=np.uint16)
         check(lib().mc_llama_cache(self.h, seq, layer, which, n_pos, _vp(out), out.nbytes))
         return out
+
+    def profile_step(self, n: int = 1) -> np.ndarray:
+        us = np.zeros(4096, dtype=np.float32)
+        cnt = C.c_uint32()
+        check(lib().mc_llama_profile_step(self.h, n, _vp(us), len(us), C.byref(cnt)))
+        return us[: cnt.value]
 
     def launches_per_step(self) -> int:
         n = C.c_uint32()

@@ -90,8 +90,68 @@ struct gemv_params {
     const uint16_t* lora_ax; // [rows, rank] bf16
     uint32_t lora_rank;
     float lora_scale;      // already rounded to bf16
-    uint32_t units_per_cta_iter; // derived
+    uint32_t ksplit;       // warps per unit (1, 2, 4 or 8): intra-CTA split of the reduction
+    int32_t pro, epi;      // PRO_* / EPI_* for the megakernel, which selects them at run time (template value -1)
+    // megakernel only: the first phase gathers its input rows from the embedding table (and CTA 0 stores them to x)
+    const uint16_t* embed_table;
+    const int32_t* embed_ids;
+    uint16_t* embed_out;
+    // megakernel only: greedy argmax fused into the vocab projection; per-CTA partials [rows][gridDim.x]
+    float* am_val;
+    int32_t* am_idx;
 };
+
+// ---- grid-wide phase barrier of the persistent decode kernel ---------------------------------------------------
+// Monotonic arrival counter in global memory: a phase is complete when every CTA has arrived once more.  The wait
+// is placed AFTER a phase has requested its first weight chunk, so the weight stream never drains at a barrier.
+struct mega_sync {
+    unsigned* bar;       // arrival counter (reset to 0 by the last phase)
+    int* err;            // set to 1 if a wait times out (never hang the GPU)
+    unsigned target;     // arrivals that must be visible before this phase may read its input
+    const void* pf_ptr;  // weights of a later phase to pull into L2 while this phase runs
+    size_t pf_bytes;
+    unsigned long long* timing; // diagnostics (nullable): CTA 0 stamps globaltimer at phase entry / after wait / at arrive
+};
+__device__ __forceinline__ void stamp(unsigned long long* t, unsigned idx)
+{
+    if (t && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long v;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+        t[idx] = v;
+    }
+}
+__device__ __forceinline__ void grid_arrive(unsigned* bar)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+}
+__device__ __forceinline__ void grid_wait(const mega_sync& sy)
+{
+    if (threadIdx.x == 0) {
+        unsigned v = 0;
+        unsigned long long spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sy.bar) : "memory");
+            if (v >= sy.target) break;
+            ++spins;
+            if ((spins & 1023) == 0 && *reinterpret_cast<volatile int*>(sy.err) != 0) break; // another CTA gave up
+            if (spins > (1ull << 22)) { // ~a second: report instead of hanging the GPU
+                atomicExch(sy.err, 1);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+// every thread asks the L2 for one 4 KiB piece of [ptr, ptr+bytes), pieces dealt round-robin over CTAs
+__device__ __forceinline__ void l2_prefetch_slice(const void* ptr, size_t bytes)
+{
+    constexpr size_t kPiece = 4096;
+    const size_t pieces = bytes / kPiece;
+    for (size_t c = size_t(threadIdx.x) * gridDim.x + blockIdx.x; c < pieces; c += size_t(blockDim.x) * gridDim.x) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(static_cast<const char*>(ptr) + c * kPiece), "r"(uint32_t(kPiece)) : "memory");
+    }
+}
 
 // dot of 8 bf16 weights (uint4) with 8 bf16 activations (uint4), fp32 accumulate in ascending order
 __device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float acc)
@@ -121,9 +181,9 @@ __device__ __forceinline__ float block_sum_256(float v, float* scratch /* [8] */
 }
 
 // unit -> the two weight rows a warp group computes
-template <int EPI> __device__ __forceinline__ void unit_rows(const gemv_params& p, uint32_t u, uint32_t& r0, uint32_t& r1)
+__device__ __forceinline__ void unit_rows(int epi, const gemv_params& p, uint32_t u, uint32_t& r0, uint32_t& r1)
 {
-    if (EPI == EPI_QKV) {
+    if (epi == EPI_QKV) {
         const uint32_t half = p.head_dim >> 1;
         const uint32_t head = u / half, j = u - head * half;
         r0 = head * p.head_dim + j; // rope pair (j, j + hd/2) of one head (kernel/rope.metal:50-57)
@@ -134,33 +194,44 @@ template <int EPI> __device__ __forceinline__ void unit_rows(const gemv_params& 
     }
 }
 
-// K1: y = epilogue( prologue(x) . W^T ).  grid: any; CTA = 8 warps = (8/KSPLIT) units x KSPLIT k-slices.
-template <int MB, int KSPLIT, int PRO, int EPI>
-__global__ void __launch_bounds__(kGemvThreads, 2) gemv_bf16_kernel(const gemv_params p)
+// K1: y = epilogue( prologue(x) . W^T ).  grid: any; CTA = 8 warps = (8/ksplit) units x ksplit k-slices.
+// MEGA = false: a stand-alone kernel (programmatic dependent launch between kernels);
+// MEGA = true : one phase of the persistent decode kernel (grid barrier between phases).
+// PRO_T / EPI_T >= 0 fix the prologue / epilogue at compile time; -1 takes them from p.pro / p.epi.
+struct phase_adj {
+    size_t w_off;   // byte offset of this layer's weights / norm weights in the arena
+    size_t kv_off;  // element offset of this layer's KV cache
+    bool embed;     // gather the input rows from the embedding table
+};
+template <int MB, int PRO_T, int EPI_T, bool MEGA>
+__device__ __forceinline__ void gemv_body(const gemv_params& p, unsigned char* smem, const mega_sync& sy, const phase_adj& adj)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    const int PRO = PRO_T >= 0 ? PRO_T : p.pro;
+    const int EPI = EPI_T >= 0 ? EPI_T : p.epi;
     uint16_t* sx = reinterpret_cast<uint16_t*>(smem);                      // [MB][K] bf16
     float* sred = reinterpret_cast<float*>(smem + size_t(MB) * p.K * 2);   // [8 warps][2][MB]
     float* sscr = sred + kGemvWarps * 2 * MB;                              // [8]
 
-    constexpr int UPC = kGemvWarps / KSPLIT; // units per CTA iteration
+    const uint32_t KSPLIT = p.ksplit;
+    const uint32_t UPC = kGemvWarps / KSPLIT; // units per CTA iteration
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t slot = warp / KSPLIT, ks = warp % KSPLIT;
     const uint32_t units = p.N >> 1;
     const uint32_t kslice = p.K / KSPLIT;
     const uint32_t kbeg = ks * kslice, kend = kbeg + kslice;
-    const uint16_t* Wb = static_cast<const uint16_t*>(p.W);
+    const uint16_t* Wb = reinterpret_cast<const uint16_t*>(static_cast<const char*>(p.W) + adj.w_off);
+    const uint16_t* norm_w = reinterpret_cast<const uint16_t*>(reinterpret_cast<const char*>(p.norm_w) + adj.w_off);
 
     uint32_t u = blockIdx.x * UPC + slot;
     const uint32_t ustride = gridDim.x * UPC;
 
     // -- prefetch the first weight chunk before touching the activations (they may still be in
     //    flight from the producer kernel under programmatic dependent launch)
-    constexpr int U = 4; // 16-byte loads in flight per row per lane
+    constexpr int U = MEGA ? 2 : 4; // 16-byte loads in flight per row per lane (megakernel phases stream L2-prefetched data)
     uint4 w0[U], w1[U];
     uint32_t r0 = 0, r1 = 0;
     if (u < units) {
-        unit_rows<EPI>(p, u, r0, r1);
+        unit_rows(EPI, p, u, r0, r1);
 #pragma unroll
         for (int i = 0; i < U; i++) {
             const uint32_t k = kbeg + (i * 32 + lane) * 8;
@@ -170,8 +241,15 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_bf16_kernel(const gemv_p
             }
         }
     }
-    pdl_launch_dependents();
-    pdl_wait();
+    if (MEGA) {
+        stamp(sy.timing, 0);
+        if (sy.pf_bytes) l2_prefetch_slice(sy.pf_ptr, sy.pf_bytes);
+        grid_wait(sy);
+        stamp(sy.timing, 1);
+    } else {
+        pdl_launch_dependents();
+        pdl_wait();
+    }
 
     // -- prologue: stage the activation rows in shared memory as bf16
     if (PRO == PRO_RMSNORM) {
@@ -179,6 +257,14 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_bf16_kernel(const gemv_p
         for (int m = 0; m < MB; m++) {
             if (uint32_t(m) < p.rows) {
                 const uint16_t* xr = p.x + size_t(m) * p.ldx;
+                if (MEGA && adj.embed) {
+                    // embedding gather fused into the first phase (kernel/embedding.metal:38-66)
+                    xr = p.embed_table + size_t(p.embed_ids[m]) * p.K;
+                    if (blockIdx.x == 0) {
+                        for (uint32_t k = threadIdx.x * 8; k < p.K; k += kGemvThreads * 8)
+                            *reinterpret_cast<uint4*>(p.embed_out + size_t(m) * p.ldx + k) = *reinterpret_cast<const uint4*>(xr + k);
+                    }
+                }
                 float part = 0.0f;
                 for (uint32_t k = threadIdx.x * 8; k < p.K; k += kGemvThreads * 8) {
                     const uint4 v = *reinterpret_cast<const uint4*>(xr + k);
@@ -196,7 +282,7 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_bf16_kernel(const gemv_p
                 const float inv = 1.0f / sqrtf(__fadd_rn(total / float(p.K), p.eps));
                 for (uint32_t k = threadIdx.x * 8; k < p.K; k += kGemvThreads * 8) {
                     const uint4 v = *reinterpret_cast<const uint4*>(xr + k);
-                    const uint4 g = *reinterpret_cast<const uint4*>(p.norm_w + k);
+                    const uint4 g = *reinterpret_cast<const uint4*>(norm_w + k);
                     uint4 o;
 #define MC_NORM2(dst, vv, gg)                                                                                   \
     dst = uint32_t(f32_to_bf16_bits(__fmul_rn(__fmul_rn(bf_lo(gg), bf_lo(vv)), inv))) |                         \
@@ -219,10 +305,28 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_bf16_kernel(const gemv_p
             }
         }
     }
+    // epilogue operands are requested before the weight stream is consumed so that their latency overlaps it
+    const bool fin = ks == 0 && lane < p.rows && lane < uint32_t(MB); // this lane finalises activation row `lane`
+    int32_t my_pos = 0, my_seq = 0;
+    if (EPI == EPI_QKV && fin) my_pos = p.row_pos[lane], my_seq = p.row_seq[lane];
+    float best_v = -INFINITY; // fused greedy argmax (lowest index on ties)
+    int32_t best_i = 0x7fffffff;
     __syncthreads();
 
     for (; u - slot < units; u += ustride) { // loop bound is CTA-uniform (u - slot is the CTA's first unit)
         const bool active = u < units;
+        float ep0 = 0.0f, ep1 = 0.0f; // EPI_RESIDUAL: residual values; EPI_QKV: cos, sin
+        if (active && fin) {
+            if (EPI == EPI_RESIDUAL) {
+                ep0 = bf16_bits_to_f32(p.res[size_t(lane) * p.ldy + r0]);
+                ep1 = bf16_bits_to_f32(p.res[size_t(lane) * p.ldy + r1]);
+            } else if (EPI == EPI_QKV) {
+                const uint32_t half = p.head_dim >> 1;
+                const uint32_t j = r0 % p.head_dim;
+                ep0 = p.fcos[size_t(my_pos) * half + j];
+                ep1 = p.fsin[size_t(my_pos) * half + j];
+            }
+        }
         float acc0[MB], acc1[MB];
 #pragma unroll
         for (int m = 0; m < MB; m++) acc0[m] = 0.0f, acc1[m] = 0.0f;
@@ -245,7 +349,7 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_bf16_kernel(const gemv_p
                         }
                     }
                 } else if (next_active) {
-                    unit_rows<EPI>(p, un, n0, n1);
+                    unit_rows(EPI, p, un, n0, n1);
 #pragma unroll
                     for (int i = 0; i < U; i++) {
                         const uint32_t k = kbeg + (i * 32 + lane) * 8;
@@ -290,8 +394,7 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_bf16_kernel(const gemv_p
 #pragma unroll
                 for (int m = 0; m < MB; m++) {
                     float a = 0.0f, b = 0.0f;
-#pragma unroll
-                    for (int s = 0; s < KSPLIT; s++) {
+                    for (uint32_t s = 0; s < KSPLIT; s++) {
                         a += sred[((warp + s) * 2 + 0) * MB + m];
                         b += sred[((warp + s) * 2 + 1) * MB + m];
                     }
@@ -301,7 +404,7 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_bf16_kernel(const gemv_p
             __syncthreads();
         }
         // -- epilogue: lane m finalises activation row m
-        if (active && ks == 0 && lane < p.rows && lane < MB) {
+        if (active && fin) {
             float a = 0.0f, b = 0.0f;
 #pragma unroll
             for (int m = 0; m < MB; m++)
@@ -322,22 +425,24 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_bf16_kernel(const gemv_p
             if (EPI == EPI_NONE) {
                 p.y[size_t(m) * p.ldy + r0] = f32_to_bf16_bits(y0);
                 p.y[size_t(m) * p.ldy + r1] = f32_to_bf16_bits(y1);
+                if (MEGA) {
+                    if (y0 > best_v || (y0 == best_v && int32_t(r0) < best_i)) best_v = y0, best_i = int32_t(r0);
+                    if (y1 > best_v || (y1 == best_v && int32_t(r1) < best_i)) best_v = y1, best_i = int32_t(r1);
+                }
             } else if (EPI == EPI_RESIDUAL) {
                 // h = r(x + a)  (nn/transformer.h:133,139; kernel/arithmetic.metal:21-43)
-                const float e0 = bf16_bits_to_f32(p.res[size_t(m) * p.ldy + r0]);
-                const float e1 = bf16_bits_to_f32(p.res[size_t(m) * p.ldy + r1]);
-                p.y[size_t(m) * p.ldy + r0] = f32_to_bf16_bits(__fadd_rn(e0, y0));
-                p.y[size_t(m) * p.ldy + r1] = f32_to_bf16_bits(__fadd_rn(e1, y1));
+                p.y[size_t(m) * p.ldy + r0] = f32_to_bf16_bits(__fadd_rn(ep0, y0));
+                p.y[size_t(m) * p.ldy + r1] = f32_to_bf16_bits(__fadd_rn(ep1, y1));
             } else if (EPI == EPI_SWIGLU) {
                 // z = r(silu_T(g) * u), rows (2i, 2i+1) = (w1 row i, w3 row i)  (nn/transformer.h:57-59)
                 p.y[size_t(m) * p.ldy + (r0 >> 1)] = f32_to_bf16_bits(__fmul_rn(silu_bf16(y0), y1));
             } else { // EPI_QKV
                 const uint32_t hd = p.head_dim, half = hd >> 1;
                 const uint32_t head = r0 / hd, j = r0 - head * hd;
-                const int32_t pos = p.row_pos[m], seq = p.row_seq[m];
+                const int32_t pos = my_pos, seq = my_seq;
                 if (head < p.n_heads + p.n_kv_heads) {
                     // rope in fp32 with fp32 tables, one rounding (kernel/rope.metal:47-58)
-                    const float c = p.fcos[size_t(pos) * half + j], s = p.fsin[size_t(pos) * half + j];
+                    const float c = ep0, s = ep1;
                     const float o0 = rbf(__fsub_rn(__fmul_rn(c, y0), __fmul_rn(s, y1)));
                     const float o1 = rbf(__fadd_rn(__fmul_rn(s, y0), __fmul_rn(c, y1)));
                     y0 = o0, y1 = o1;
@@ -350,7 +455,7 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_bf16_kernel(const gemv_p
                     // sink_cache::update: bit copy into position pos (nn/cache.h:207-214)
                     const bool is_k = head < p.n_heads + p.n_kv_heads;
                     const uint32_t kvh = is_k ? head - p.n_heads : head - p.n_heads - p.n_kv_heads;
-                    uint16_t* base = is_k ? p.kcache : p.vcache;
+                    uint16_t* base = (is_k ? p.kcache : p.vcache) + adj.kv_off;
                     uint16_t* dst = base + ((size_t(seq) * p.n_kv_heads + kvh) * p.max_seq + size_t(pos)) * hd + j;
                     dst[0] = f32_to_bf16_bits(y0);
                     dst[half] = f32_to_bf16_bits(y1);
@@ -359,6 +464,37 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_bf16_kernel(const gemv_p
         }
         r0 = n0, r1 = n1;
     }
+    if (MEGA && EPI == EPI_NONE && p.am_val) {
+        // per-CTA argmax partial of every activation row
+        __syncthreads();
+        if (fin) {
+            sred[(warp * 2 + 0) * MB + lane] = best_v;
+            reinterpret_cast<int32_t*>(sred)[(warp * 2 + 1) * MB + lane] = best_i;
+        }
+        __syncthreads();
+        if (threadIdx.x < p.rows && threadIdx.x < uint32_t(MB)) {
+            float bv = -INFINITY;
+            int32_t bi = 0x7fffffff;
+            for (uint32_t w = 0; w < uint32_t(kGemvWarps); w += KSPLIT) {
+                const float v = sred[(w * 2 + 0) * MB + threadIdx.x];
+                const int32_t i = reinterpret_cast<const int32_t*>(sred)[(w * 2 + 1) * MB + threadIdx.x];
+                if (v > bv || (v == bv && i < bi)) bv = v, bi = i;
+            }
+            p.am_val[threadIdx.x * gridDim.x + blockIdx.x] = bv;
+            p.am_idx[threadIdx.x * gridDim.x + blockIdx.x] = bi;
+        }
+    }
+    if (MEGA) {
+        stamp(sy.timing, 2);
+        grid_arrive(sy.bar);
+    }
+}
+
+template <int MB, int PRO, int EPI>
+__global__ void __launch_bounds__(kGemvThreads, 2) gemv_bf16_kernel(const gemv_params p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    gemv_body<MB, PRO, EPI, false>(p, smem, mega_sync{}, phase_adj{0, 0, false});
 }
 
 // ---- K5: decode attention ------------------------------------------------------------------------------------
@@ -376,86 +512,269 @@ struct attn_params {
     float scale;            // r(1/sqrt(hd)) stored as T (nn/attention.h:88,115; quirk Q4)
 };
 
-template <int HD> __global__ void __launch_bounds__(256) attn_decode_kernel(const attn_params p)
+constexpr int kAttnCluster = 4; // CTAs per (head, row): split of the cached positions, joined through DSMEM
+
+// cluster helpers (raw PTX: barrier.cluster + mapa/ld.shared::cluster)
+__device__ __forceinline__ uint32_t cluster_ctarank()
 {
-    constexpr int LPP = HD / 8;      // lanes per position row (16 bytes each)
-    constexpr int PPW = 32 / LPP;    // positions per warp load
-    constexpr int G = 256 / LPP;     // position groups in the PV phase
-    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(const float* local_smem_ptr, uint32_t rank)
+{
+    const uint32_t a = uint32_t(__cvta_generic_to_shared(local_smem_ptr));
+    uint32_t ra;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
+}
+
+// grid (n_heads * kAttnCluster, rows), cluster (kAttnCluster,1,1), 256 threads.
+// Thread (slot = tid / LPP, dl = tid % LPP) owns positions slot, slot + SLOTS, ... of its CTA's chunk and the
+// 8 head dims [8*dl, 8*dl+8): the same mapping serves q.K and P.V, so K and V rows are requested together.
+template <int HD, int CL>
+__device__ __forceinline__ void attn_body(const attn_params& p, unsigned char* smem, uint32_t head, uint32_t row, uint32_t crank, size_t kv_off)
+{
+    constexpr int LPP = HD / 8;       // lanes per position row (16 bytes each)
+    constexpr int SLOTS = 256 / LPP;  // positions handled per sweep
+    constexpr int IT = 4;             // sweeps per block of loads kept in flight
     float* sq = reinterpret_cast<float*>(smem);  // [HD]
-    float* scr = sq + HD;                        // [8]
-    float* spart = scr + 8;                      // [G][HD]
-    float* sp = spart + G * HD;                  // [P]
+    float* scr = sq + HD;                        // [8] block-sum scratch
+    float* xch = scr + 8;                        // [4 + HD] exchanged through DSMEM: exp-sum, then partial o
+    float* spart = xch + 4 + HD;                 // [SLOTS][HD]
+    float* sp = spart + SLOTS * HD;              // [chunk] scores / probabilities of this CTA
 
-    pdl_launch_dependents();
-    pdl_wait();
-
-    const uint32_t head = blockIdx.x, row = blockIdx.y;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int32_t seq = p.row_seq[row];
     const uint32_t P = uint32_t(p.row_pos[row]) + 1;
     const uint32_t kvh = head / (p.n_heads / p.n_kv_heads);
-    const size_t coff = (size_t(seq) * p.n_kv_heads + kvh) * p.max_seq * HD;
+    const size_t coff = kv_off + (size_t(seq) * p.n_kv_heads + kvh) * p.max_seq * HD;
     const uint16_t* Kc = p.kcache + coff;
     const uint16_t* Vc = p.vcache + coff;
+    const uint32_t chunk = ((P + CL * SLOTS - 1) / (CL * SLOTS)) * SLOTS; // multiple of SLOTS
+    const uint32_t t0 = crank * chunk;
+    const uint32_t t1 = min(P, t0 + chunk);
+    const uint32_t slot = threadIdx.x / LPP, dl = threadIdx.x % LPP;
+    const bool vpre = chunk <= IT * SLOTS; // the whole chunk fits one block of loads: fetch V together with K
 
+    // first block of K (and V) rows: all requests are issued before anything is consumed
+    uint4 kreg[IT], vreg[IT];
+#pragma unroll
+    for (int i = 0; i < IT; i++) {
+        const uint32_t t = t0 + i * SLOTS + slot;
+        if (t < t1) {
+            kreg[i] = *reinterpret_cast<const uint4*>(Kc + size_t(t) * HD + dl * 8);
+            if (vpre) vreg[i] = *reinterpret_cast<const uint4*>(Vc + size_t(t) * HD + dl * 8);
+        }
+    }
     if (threadIdx.x < HD) sq[threadIdx.x] = bf16_bits_to_f32(p.q[(size_t(row) * p.n_heads + head) * HD + threadIdx.x]);
     __syncthreads();
-
-    // scores
-    const uint32_t sub = lane / LPP, dl = lane % LPP;
     float qv[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) qv[i] = sq[dl * 8 + i];
-    for (uint32_t tb = warp * PPW; tb < P; tb += 8 * PPW) {
-        const uint32_t t = tb + sub;
-        float d = 0.0f;
-        if (t < P) {
-            const uint4 kv = *reinterpret_cast<const uint4*>(Kc + size_t(t) * HD + dl * 8);
-            d = fmaf(qv[0], bf_lo(kv.x), d);
-            d = fmaf(qv[1], bf_hi(kv.x), d);
-            d = fmaf(qv[2], bf_lo(kv.y), d);
-            d = fmaf(qv[3], bf_hi(kv.y), d);
-            d = fmaf(qv[4], bf_lo(kv.z), d);
-            d = fmaf(qv[5], bf_hi(kv.z), d);
-            d = fmaf(qv[6], bf_lo(kv.w), d);
-            d = fmaf(qv[7], bf_hi(kv.w), d);
+
+    // s = r(r(q . K[t]) * scale)
+    for (uint32_t tb = t0; tb < t1; tb += IT * SLOTS) {
+        if (tb != t0) {
+#pragma unroll
+            for (int i = 0; i < IT; i++) {
+                const uint32_t t = tb + i * SLOTS + slot;
+                if (t < t1) kreg[i] = *reinterpret_cast<const uint4*>(Kc + size_t(t) * HD + dl * 8);
+            }
         }
 #pragma unroll
-        for (int off = LPP / 2; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-        if (t < P && dl == 0) sp[t] = rbf(__fmul_rn(rbf(d), p.scale));
+        for (int i = 0; i < IT; i++) {
+            const uint32_t t = tb + i * SLOTS + slot;
+            float d = 0.0f;
+            if (t < t1) {
+                const uint4 kv = kreg[i];
+                d = fmaf(qv[0], bf_lo(kv.x), d);
+                d = fmaf(qv[1], bf_hi(kv.x), d);
+                d = fmaf(qv[2], bf_lo(kv.y), d);
+                d = fmaf(qv[3], bf_hi(kv.y), d);
+                d = fmaf(qv[4], bf_lo(kv.z), d);
+                d = fmaf(qv[5], bf_hi(kv.z), d);
+                d = fmaf(qv[6], bf_lo(kv.w), d);
+                d = fmaf(qv[7], bf_hi(kv.w), d);
+            }
+#pragma unroll
+            for (int off = LPP / 2; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+            if (t < t1 && dl == 0) sp[t - t0] = rbf(__fmul_rn(rbf(d), p.scale));
+        }
     }
     __syncthreads();
-    // softmax without max subtraction (kernel/softmax.metal:40-80)
+    // softmax without max subtraction (kernel/softmax.metal:40-80): the exp-sum is joined across the cluster
+    const uint32_t n_local = t1 > t0 ? t1 - t0 : 0;
     float part = 0.0f;
-    for (uint32_t t = threadIdx.x; t < P; t += 256) part += expf(sp[t]);
-    const float inv = 1.0f / block_sum_256(part, scr);
-    for (uint32_t t = threadIdx.x; t < P; t += 256) sp[t] = rbf(__fmul_rn(expf(sp[t]), inv));
+    for (uint32_t t = threadIdx.x; t < n_local; t += 256) part += expf(sp[t]);
+    const float local_sum = block_sum_256(part, scr);
+    float total = local_sum;
+    if (CL > 1) {
+        if (threadIdx.x == 0) xch[0] = local_sum;
+        cluster_sync_all();
+        total = 0.0f;
+#pragma unroll
+        for (uint32_t r = 0; r < uint32_t(CL); r++) total += ld_dsmem_f32(&xch[0], r);
+    }
+    const float inv = 1.0f / total;
+    for (uint32_t t = threadIdx.x; t < n_local; t += 256) sp[t] = rbf(__fmul_rn(expf(sp[t]), inv));
     __syncthreads();
-    // o = P . V
-    const uint32_t g = threadIdx.x / LPP, dc = threadIdx.x % LPP;
+    // o = sum_t p[t] * V[t]
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] = 0.0f;
-    for (uint32_t t = g; t < P; t += G) {
-        const uint4 vv = *reinterpret_cast<const uint4*>(Vc + size_t(t) * HD + dc * 8);
-        const float pt = sp[t];
-        acc[0] = fmaf(pt, bf_lo(vv.x), acc[0]);
-        acc[1] = fmaf(pt, bf_hi(vv.x), acc[1]);
-        acc[2] = fmaf(pt, bf_lo(vv.y), acc[2]);
-        acc[3] = fmaf(pt, bf_hi(vv.y), acc[3]);
-        acc[4] = fmaf(pt, bf_lo(vv.z), acc[4]);
-        acc[5] = fmaf(pt, bf_hi(vv.z), acc[5]);
-        acc[6] = fmaf(pt, bf_lo(vv.w), acc[6]);
-        acc[7] = fmaf(pt, bf_hi(vv.w), acc[7]);
+    for (uint32_t tb = t0; tb < t1; tb += IT * SLOTS) {
+        if (!vpre) {
+#pragma unroll
+            for (int i = 0; i < IT; i++) {
+                const uint32_t t = tb + i * SLOTS + slot;
+                if (t < t1) vreg[i] = *reinterpret_cast<const uint4*>(Vc + size_t(t) * HD + dl * 8);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < IT; i++) {
+            const uint32_t t = tb + i * SLOTS + slot;
+            if (t < t1) {
+                const uint4 vv = vreg[i];
+                const float pt = sp[t - t0];
+                acc[0] = fmaf(pt, bf_lo(vv.x), acc[0]);
+                acc[1] = fmaf(pt, bf_hi(vv.x), acc[1]);
+                acc[2] = fmaf(pt, bf_lo(vv.y), acc[2]);
+                acc[3] = fmaf(pt, bf_hi(vv.y), acc[3]);
+                acc[4] = fmaf(pt, bf_lo(vv.z), acc[4]);
+                acc[5] = fmaf(pt, bf_hi(vv.z), acc[5]);
+                acc[6] = fmaf(pt, bf_lo(vv.w), acc[6]);
+                acc[7] = fmaf(pt, bf_hi(vv.w), acc[7]);
+            }
+        }
     }
 #pragma unroll
-    for (int i = 0; i < 8; i++) spart[g * HD + dc * 8 + i] = acc[i];
+    for (int i = 0; i < 8; i++) spart[slot * HD + dl * 8 + i] = acc[i];
     __syncthreads();
+    float o = 0.0f;
     if (threadIdx.x < HD) {
-        float o = 0.0f;
-        for (int gg = 0; gg < G; gg++) o += spart[gg * HD + threadIdx.x];
-        p.out[(size_t(row) * p.n_heads + head) * HD + threadIdx.x] = f32_to_bf16_bits(o);
+        for (int gg = 0; gg < SLOTS; gg++) o += spart[gg * HD + threadIdx.x];
+        xch[4 + threadIdx.x] = o;
+    }
+    if (CL > 1) {
+        cluster_sync_all();
+        if (crank == 0 && threadIdx.x < HD) {
+            o = 0.0f;
+#pragma unroll
+            for (uint32_t r = 0; r < uint32_t(CL); r++) o += ld_dsmem_f32(&xch[4 + threadIdx.x], r);
+        }
+    }
+    if (crank == 0 && threadIdx.x < HD) p.out[(size_t(row) * p.n_heads + head) * HD + threadIdx.x] = f32_to_bf16_bits(o);
+    if (CL > 1) cluster_sync_all(); // peers must not exit while rank 0 still reads their shared memory
+    else __syncthreads();           // shared memory is reused by the next work item
+}
+
+template <int HD> __global__ void __launch_bounds__(256) attn_decode_kernel(const attn_params p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    pdl_launch_dependents();
+    pdl_wait();
+    attn_body<HD, kAttnCluster>(p, smem, blockIdx.x / kAttnCluster, blockIdx.y, cluster_ctarank(), 0);
+}
+
+// ---- the persistent decode kernel: one launch per token ---------------------------------------------------------------
+// grid = (resident CTAs per SM) x 148, every CTA walks the same list of phases; a phase hands its output to the next
+// through the grid barrier above.  Phase list per block: QKV | attention | wo | w1-w3 | w2, then the vocab projection
+// with the greedy argmax fused, then one CTA picks the token and advances ids/pos for the next replay.
+struct mega_params {
+    gemv_params g[5];         // qkv, wo, w1-w3, w2 (layer 0 views; layer l adds l * layer_stride bytes to W / norm_w), head
+    attn_params attn;
+    size_t layer_stride;      // bytes between consecutive layers in the weight arena
+    size_t kv_layer_stride;   // elements between consecutive layers in the KV cache
+    size_t g_bytes[5];        // weight bytes of each of the above
+    uint32_t n_layers, rows, head_dim;
+    unsigned* bar;
+    int* err;
+    // sampler feedback
+    int32_t* ids;
+    int32_t* pos;
+    int32_t* out_log;
+    int32_t* step_counter;
+    int32_t advance;
+    unsigned long long* timing; // diagnostics: [phases][3] globaltimer stamps of CTA 0 (nullable)
+};
+
+__device__ __forceinline__ const void* shift(const void* p, size_t bytes) { return static_cast<const char*>(p) + bytes; }
+
+// The parameter block lives in __constant__ memory (one slot per captured graph); the phase loop contains exactly one
+// GEMV body (prologue / epilogue selected at run time, warp-uniform) and one attention body.
+constexpr int kMegaSlots = 24;
+__constant__ mega_params c_mega[kMegaSlots];
+
+template <int MB> __global__ void __launch_bounds__(kGemvThreads, 2) decode_megakernel(const int slot)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const mega_params& P = c_mega[slot];
+    const unsigned G = gridDim.x;
+    const unsigned n_phases = P.n_layers * 5 + 1;
+#pragma unroll 1
+    for (unsigned phase = 0; phase < n_phases; phase++) {
+        const unsigned li = phase / 5, kind = phase - li * 5; // 0 qkv, 1 attention, 2 wo, 3 w1-w3, 4 w2
+        const bool is_head = phase + 1 == n_phases;
+        const size_t w_off = is_head ? 0 : size_t(li) * P.layer_stride;
+        const size_t kv_off = size_t(li) * P.kv_layer_stride;
+        unsigned long long* tm = P.timing ? P.timing + size_t(phase) * 3 : nullptr;
+        if (kind == 1 && !is_head) {
+            stamp(tm, 0);
+            l2_prefetch_slice(shift(P.g[2].W, w_off), P.g_bytes[2]);
+            grid_wait(mega_sync{P.bar, P.err, phase * G, nullptr, 0, nullptr});
+            stamp(tm, 1);
+            for (uint32_t item = blockIdx.x; item < P.attn.n_heads * P.rows; item += G) {
+                if (P.head_dim == 64) attn_body<64, 1>(P.attn, smem, item % P.attn.n_heads, item / P.attn.n_heads, 0, kv_off);
+                else attn_body<128, 1>(P.attn, smem, item % P.attn.n_heads, item / P.attn.n_heads, 0, kv_off);
+            }
+            stamp(tm, 2);
+            grid_arrive(P.bar);
+        } else {
+            // which GEMV, and which later weights to pull into L2 meanwhile: qkv -> wo, wo -> w2, w1-w3 -> next qkv
+            const unsigned gi = is_head ? 4u : (kind == 0 ? 0u : kind - 1);
+            const void* pf = nullptr;
+            size_t pfb = 0;
+            if (!is_head) {
+                if (kind == 0) pf = shift(P.g[1].W, w_off), pfb = P.g_bytes[1];
+                else if (kind == 2) pf = shift(P.g[3].W, w_off), pfb = P.g_bytes[3];
+                else if (kind == 3 && li + 1 < P.n_layers) pf = shift(P.g[0].W, w_off + P.layer_stride), pfb = P.g_bytes[0];
+            }
+            gemv_body<MB, -1, -1, true>(P.g[gi], smem, mega_sync{P.bar, P.err, phase * G, pf, pfb, tm}, phase_adj{w_off, kv_off, phase == 0});
+        }
+    }
+    const unsigned phase = n_phases;
+    // sampler tail (greedy): CTA 0 joins the per-CTA partials, feeds the id back and advances the position
+    if (blockIdx.x == 0) {
+        grid_wait(mega_sync{P.bar, P.err, phase * G, nullptr, 0, nullptr});
+        stamp(P.timing, phase * 3);
+        if (threadIdx.x < P.rows) {
+            const uint32_t row = threadIdx.x;
+            float bv = -INFINITY;
+            int32_t bi = 0x7fffffff;
+            for (unsigned b = 0; b < G; b++) {
+                const float v = P.g[4].am_val[row * G + b];
+                const int32_t i = P.g[4].am_idx[row * G + b];
+                if (v > bv || (v == bv && i < bi)) bv = v, bi = i;
+            }
+            if (bi == 0x7fffffff) bi = 0;
+            const int32_t step = *P.step_counter;
+            P.out_log[size_t(step) * P.rows + row] = bi;
+            if (P.advance) {
+                P.ids[row] = bi;
+                P.pos[row] += 1;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            *P.step_counter += 1;
+            *P.bar = 0; // every CTA has made its last arrival: ready for the next replay
+        }
     }
 }
 

@@ -19,6 +19,7 @@
 #include <cmath>
 #include <map>
 #include <memory>
+#include <mutex>
 
 using namespace mc;
 
@@ -27,9 +28,16 @@ namespace {
 struct dbuf {
     void* p = nullptr;
     size_t bytes = 0;
+    bool owned = true;
+    void view(void* ptr, size_t n) // a slice of an arena owned by someone else
+    {
+        release();
+        p = ptr, bytes = n, owned = false;
+    }
     void alloc(size_t n)
     {
         release();
+        owned = true;
         bytes = n;
         cudaError_t e = cudaMalloc(&p, n ? n : 1);
         if (e != cudaSuccess) {
@@ -40,9 +48,10 @@ struct dbuf {
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p && owned) cudaFree(p);
         p = nullptr;
         bytes = 0;
+        owned = true;
     }
     template <typename T> T* as() const { return static_cast<T*>(p); }
 };
@@ -72,6 +81,12 @@ struct mc_llama {
     bool finalized = false;
     bool tied = true;
     std::vector<dlayer> layers;
+    dbuf layer_arena;          // all per-layer weights, one fixed stride per layer (the megakernel indexes by layer)
+    size_t layer_stride = 0;
+    dbuf bar, errflag;         // grid barrier counter / timeout flag of the megakernel
+    dbuf mega_timing;          // diagnostics: per-phase globaltimer stamps (allocated on demand)
+    bool mega_timing_on = false;
+    int mega_ctas_per_sm[3] = {0, 0, 0};
     dlinear tok, out;
     dbuf norm;
     dbuf fcos, fsin;
@@ -95,7 +110,7 @@ struct mc_llama {
             for (dlinear* d : {&l.wqkv, &l.wo, &l.w13, &l.w2}) d->w.release(), d->scales.release(), d->lora_b.release();
         }
         for (dlinear* d : {&tok, &out}) d->w.release(), d->scales.release(), d->lora_b.release();
-        for (dbuf* b : {&norm, &fcos, &fsin, &kcache, &vcache, &x, &h, &q, &attn, &z, &logits, &hidden_save, &ids, &pos, &row_seq,
+        for (dbuf* b : {&layer_arena, &bar, &errflag, &mega_timing, &norm, &fcos, &fsin, &kcache, &vcache, &x, &h, &q, &attn, &z, &logits, &hidden_save, &ids, &pos, &row_seq,
                         &uniforms, &out_log, &step_counter, &pval, &pidx})
             b->release();
     }
@@ -119,6 +134,41 @@ struct launcher {
     cudaStream_t s;
     bool pdl;
     uint32_t count = 0;
+    std::vector<cudaEvent_t>* events = nullptr; // profiling: one event before every launch (+ one at the end by the caller)
+    void mark()
+    {
+        if (events) {
+            cudaEvent_t e;
+            MC_CUDA_CHECK(cudaEventCreate(&e));
+            MC_CUDA_CHECK(cudaEventRecord(e, s));
+            events->push_back(e);
+        }
+    }
+    template <typename... KArgs, typename... Args>
+    void go_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, unsigned cluster_x, Args&&... args)
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid;
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cluster_x;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.numAttrs = 1;
+        if (pdl) {
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.numAttrs = 2;
+        }
+        cfg.attrs = attr;
+        mark();
+        MC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+        count++;
+        m->dev->launches.fetch_add(1);
+    }
     template <typename... KArgs, typename... Args>
     void go(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args)
     {
@@ -134,6 +184,7 @@ struct launcher {
             cfg.attrs = attr;
             cfg.numAttrs = 1;
         }
+        mark();
         MC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
         count++;
         m->dev->launches.fetch_add(1);
@@ -142,40 +193,47 @@ struct launcher {
 
 size_t gemv_smem(uint32_t MB, uint32_t K) { return size_t(MB) * K * 2 + (kGemvWarps * 2 * MB + 8) * sizeof(float); }
 
-template <int MB, int KSPLIT, int PRO, int EPI> void gemv_launch_t(launcher& L, const gemv_params& p)
+// CTAs per SM of a stand-alone GEMV launch.  Measured on B200 (tools/sweep_gemv_ctas.sh): two CTAs per SM everywhere
+// (16 warps x 8 x 16-byte loads in flight) beats one CTA per SM + earlier residency of the dependent kernel
+// (709 vs 894 us per 1B decode step), so the default is 2; MC_GEMV_CTAS_PER_SM=1 keeps the experiment reachable.
+uint32_t gemv_ctas_per_sm(uint32_t, uint32_t)
 {
-    auto kernel = gemv_bf16_kernel<MB, KSPLIT, PRO, EPI>;
+    static const int forced = [] {
+        const char* e = getenv("MC_GEMV_CTAS_PER_SM");
+        return e ? atoi(e) : 0;
+    }();
+    return forced == 1 ? 1u : 2u;
+}
+
+// k-split so that there is at least ~one unit per resident warp
+uint32_t choose_ksplit(const mc_device* dev, uint32_t N, uint32_t K)
+{
+    const uint32_t units = N / 2;
+    const uint32_t warps = uint32_t(dev->prop.multiProcessorCount) * gemv_ctas_per_sm(N, K) * kGemvWarps;
+    uint32_t ksplit = 1;
+    while (ksplit < 8 && units * ksplit < warps && (K / (ksplit * 2)) % 256 == 0 && K / (ksplit * 2) >= 512) ksplit *= 2;
+    return ksplit;
+}
+
+template <int MB, int PRO, int EPI> void gemv_launch_mb(launcher& L, gemv_params p)
+{
+    auto kernel = gemv_bf16_kernel<MB, PRO, EPI>;
     static bool configured[8] = {false};
     const int dev = L.m->dev->ordinal;
     if (!configured[dev & 7]) {
         MC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         configured[dev & 7] = true;
     }
+    MC_REQUIRE(p.N % 2 == 0 && p.K % 256 == 0, "gemv: N must be even and K a multiple of 256");
+    p.ksplit = choose_ksplit(L.m->dev, p.N, p.K);
     const size_t smem = gemv_smem(MB, p.K);
     MC_REQUIRE(smem <= 100 * 1024, "gemv: activation rows do not fit in shared memory");
-    constexpr int UPC = kGemvWarps / KSPLIT;
+    const uint32_t upc = kGemvWarps / p.ksplit;
     const uint32_t units = p.N / 2;
-    const uint32_t ctas_needed = (units + UPC - 1) / UPC;
-    const uint32_t sms = uint32_t(L.m->dev->prop.multiProcessorCount);
-    const uint32_t grid = ctas_needed < 2 * sms ? ctas_needed : 2 * sms;
+    const uint32_t ctas_needed = (units + upc - 1) / upc;
+    const uint32_t cap = uint32_t(L.m->dev->prop.multiProcessorCount) * gemv_ctas_per_sm(p.N, p.K);
+    const uint32_t grid = ctas_needed < cap ? ctas_needed : cap;
     L.go(kernel, dim3(grid), dim3(kGemvThreads), smem, p);
-}
-
-// choose the k-split so that there is at least ~one unit per resident warp
-template <int MB, int PRO, int EPI> void gemv_launch_mb(launcher& L, const gemv_params& p)
-{
-    MC_REQUIRE(p.N % 2 == 0, "gemv: row count must be even");
-    const uint32_t units = p.N / 2;
-    const uint32_t warps = uint32_t(L.m->dev->prop.multiProcessorCount) * 2 * kGemvWarps;
-    int ksplit = 1;
-    while (ksplit < 8 && units * ksplit < warps && (p.K / (ksplit * 2)) % 256 == 0 && p.K / (ksplit * 2) >= 512) ksplit *= 2;
-    MC_REQUIRE(p.K % (uint32_t(ksplit) * 8) == 0 && p.K % 8 == 0, "gemv: K must be a multiple of 8");
-    switch (ksplit) {
-    case 1: gemv_launch_t<MB, 1, PRO, EPI>(L, p); break;
-    case 2: gemv_launch_t<MB, 2, PRO, EPI>(L, p); break;
-    case 4: gemv_launch_t<MB, 4, PRO, EPI>(L, p); break;
-    default: gemv_launch_t<MB, 8, PRO, EPI>(L, p); break;
-    }
 }
 template <int PRO, int EPI> void gemv_launch(launcher& L, const gemv_params& p)
 {
@@ -187,83 +245,184 @@ template <int PRO, int EPI> void gemv_launch(launcher& L, const gemv_params& p)
     }
 }
 
+// parameter blocks of the five GEMVs of layer `li` and of the head, shared by the per-kernel path and the megakernel
+gemv_params qkv_params(mc_llama* m, uint32_t li, uint32_t row0, uint32_t rows)
+{
+    const mc_llama_config& c = m->cfg;
+    dlayer& ly = m->layers[li];
+    gemv_params p{};
+    p.W = ly.wqkv.w.p, p.N = ly.wqkv.N, p.K = c.dim, p.rows = rows;
+    p.x = m->x.as<uint16_t>() + size_t(row0) * c.dim, p.ldx = c.dim, p.norm_w = ly.attn_norm.as<uint16_t>(), p.eps = c.norm_eps;
+    p.q = m->q.as<uint16_t>() + size_t(row0) * m->Hl * c.head_dim;
+    p.kcache = m->kcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
+    p.vcache = m->vcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
+    p.fcos = m->fcos.as<float>(), p.fsin = m->fsin.as<float>();
+    p.row_seq = m->row_seq.as<int32_t>() + row0, p.row_pos = m->pos.as<int32_t>() + row0;
+    p.n_heads = m->Hl, p.n_kv_heads = m->KVl, p.head_dim = c.head_dim, p.max_seq = c.max_seq_len;
+    p.ksplit = choose_ksplit(m->dev, p.N, p.K);
+    return p;
+}
+attn_params attn_params_of(mc_llama* m, uint32_t li, uint32_t row0)
+{
+    const mc_llama_config& c = m->cfg;
+    attn_params a{};
+    a.q = m->q.as<uint16_t>() + size_t(row0) * m->Hl * c.head_dim;
+    a.kcache = m->kcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
+    a.vcache = m->vcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
+    a.out = m->attn.as<uint16_t>() + size_t(row0) * m->Hl * c.head_dim;
+    a.row_seq = m->row_seq.as<int32_t>() + row0, a.row_pos = m->pos.as<int32_t>() + row0;
+    a.n_heads = m->Hl, a.n_kv_heads = m->KVl, a.max_seq = c.max_seq_len, a.scale = m->scale_bf16;
+    return a;
+}
+gemv_params wo_params(mc_llama* m, uint32_t li, uint32_t row0, uint32_t rows)
+{
+    const uint32_t D = m->cfg.dim, QO = m->Hl * m->cfg.head_dim;
+    gemv_params p{};
+    p.W = m->layers[li].wo.w.p, p.N = D, p.K = QO, p.rows = rows;
+    p.x = m->attn.as<uint16_t>() + size_t(row0) * QO, p.ldx = QO;
+    p.y = m->h.as<uint16_t>() + size_t(row0) * D, p.ldy = D, p.res = m->x.as<uint16_t>() + size_t(row0) * D;
+    p.ksplit = choose_ksplit(m->dev, p.N, p.K);
+    return p;
+}
+gemv_params w13_params(mc_llama* m, uint32_t li, uint32_t row0, uint32_t rows)
+{
+    const uint32_t D = m->cfg.dim;
+    dlayer& ly = m->layers[li];
+    gemv_params p{};
+    p.W = ly.w13.w.p, p.N = 2 * m->Fl, p.K = D, p.rows = rows;
+    p.x = m->h.as<uint16_t>() + size_t(row0) * D, p.ldx = D, p.norm_w = ly.ffn_norm.as<uint16_t>(), p.eps = m->cfg.norm_eps;
+    p.y = m->z.as<uint16_t>() + size_t(row0) * m->Fl, p.ldy = m->Fl;
+    p.ksplit = choose_ksplit(m->dev, p.N, p.K);
+    return p;
+}
+gemv_params w2_params(mc_llama* m, uint32_t li, uint32_t row0, uint32_t rows)
+{
+    const uint32_t D = m->cfg.dim;
+    gemv_params p{};
+    p.W = m->layers[li].w2.w.p, p.N = D, p.K = m->Fl, p.rows = rows;
+    p.x = m->z.as<uint16_t>() + size_t(row0) * m->Fl, p.ldx = m->Fl;
+    p.y = m->x.as<uint16_t>() + size_t(row0) * D, p.ldy = D, p.res = m->h.as<uint16_t>() + size_t(row0) * D;
+    p.ksplit = choose_ksplit(m->dev, p.N, p.K);
+    return p;
+}
+gemv_params head_params(mc_llama* m, const uint16_t* x, uint32_t rows, uint16_t* logits_dst)
+{
+    const dlinear& hw = m->tied ? m->tok : m->out;
+    gemv_params p{};
+    p.W = hw.w.p, p.N = m->Vl, p.K = m->cfg.dim, p.rows = rows;
+    p.norm_w = m->norm.as<uint16_t>(), p.eps = m->cfg.norm_eps;
+    p.x = x, p.ldx = m->cfg.dim, p.y = logits_dst, p.ldy = m->Vl;
+    p.ksplit = choose_ksplit(m->dev, p.N, p.K);
+    return p;
+}
+
+size_t attn_smem(const mc_llama* m, uint32_t cluster)
+{
+    const uint32_t hd = m->cfg.head_dim, slots = 256 / (hd / 8);
+    const uint32_t chunk = ((m->cfg.max_seq_len + cluster * slots - 1) / (cluster * slots)) * slots;
+    return (hd + 8 + 4 + hd + size_t(slots) * hd + chunk) * sizeof(float);
+}
+
 // Enqueue the forward pass of `rows` activation rows (<= kMaxMB) starting at row offset `row0` of the
-// activation buffers.  Row r reads ids[row0+r], pos[row0+r], row_seq[row0+r].
-//   head_mode: 0 none, 1 logits for every row -> logits[row_seq... caller passes dst], 2 last row only
+// activation buffers, one kernel per fused op.  Row r reads ids[row0+r], pos[row0+r], row_seq[row0+r].
+//   head_mode: 0 none, 1 logits for every row, 2 last row only
 void enqueue_rows(mc_llama* m, launcher& L, uint32_t row0, uint32_t rows, int head_mode, uint16_t* logits_dst)
 {
     const mc_llama_config& c = m->cfg;
     const uint32_t D = c.dim, hd = c.head_dim;
-    const uint32_t QO = m->Hl * hd;
     uint16_t* x = m->x.as<uint16_t>() + size_t(row0) * D;
-    uint16_t* h = m->h.as<uint16_t>() + size_t(row0) * D;
-    uint16_t* q = m->q.as<uint16_t>() + size_t(row0) * QO;
-    uint16_t* at = m->attn.as<uint16_t>() + size_t(row0) * QO;
-    uint16_t* z = m->z.as<uint16_t>() + size_t(row0) * m->Fl;
     const int32_t* ids = m->ids.as<int32_t>() + row0;
-    const int32_t* pos = m->pos.as<int32_t>() + row0;
-    const int32_t* rseq = m->row_seq.as<int32_t>() + row0;
 
     L.go(embed_kernel, dim3(rows), dim3(256), 0, x, D, (const void*)m->tok.w.p, (const float*)m->tok.scales.p, m->tok.fmt, D, c.vocab, ids);
-
     for (uint32_t li = 0; li < c.n_layers; li++) {
-        dlayer& ly = m->layers[li];
-        uint16_t* kc = m->kcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
-        uint16_t* vc = m->vcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
-        {
-            gemv_params p{};
-            p.W = ly.wqkv.w.p, p.N = ly.wqkv.N, p.K = D, p.rows = rows;
-            p.x = x, p.ldx = D, p.norm_w = ly.attn_norm.as<uint16_t>(), p.eps = c.norm_eps;
-            p.q = q, p.kcache = kc, p.vcache = vc, p.fcos = m->fcos.as<float>(), p.fsin = m->fsin.as<float>();
-            p.row_seq = rseq, p.row_pos = pos;
-            p.n_heads = m->Hl, p.n_kv_heads = m->KVl, p.head_dim = hd, p.max_seq = c.max_seq_len;
-            gemv_launch<PRO_RMSNORM, EPI_QKV>(L, p);
-        }
-        {
-            attn_params a{};
-            a.q = q, a.kcache = kc, a.vcache = vc, a.out = at, a.row_seq = rseq, a.row_pos = pos;
-            a.n_heads = m->Hl, a.n_kv_heads = m->KVl, a.max_seq = c.max_seq_len, a.scale = m->scale_bf16;
-            if (hd == 64) {
-                const size_t smem = (64 + 8 + 32 * 64 + c.max_seq_len) * sizeof(float);
-                L.go(attn_decode_kernel<64>, dim3(m->Hl, rows), dim3(256), smem, a);
-            } else {
-                const size_t smem = (128 + 8 + 16 * 128 + c.max_seq_len) * sizeof(float);
-                L.go(attn_decode_kernel<128>, dim3(m->Hl, rows), dim3(256), smem, a);
-            }
-        }
-        {
-            gemv_params p{};
-            p.W = ly.wo.w.p, p.N = D, p.K = QO, p.rows = rows;
-            p.x = at, p.ldx = QO, p.y = h, p.ldy = D, p.res = x;
-            gemv_launch<PRO_NONE, EPI_RESIDUAL>(L, p);
-        }
-        {
-            gemv_params p{};
-            p.W = ly.w13.w.p, p.N = 2 * m->Fl, p.K = D, p.rows = rows;
-            p.x = h, p.ldx = D, p.norm_w = ly.ffn_norm.as<uint16_t>(), p.eps = c.norm_eps;
-            p.y = z, p.ldy = m->Fl;
-            gemv_launch<PRO_RMSNORM, EPI_SWIGLU>(L, p);
-        }
-        {
-            gemv_params p{};
-            p.W = ly.w2.w.p, p.N = D, p.K = m->Fl, p.rows = rows;
-            p.x = z, p.ldx = m->Fl, p.y = x, p.ldy = D, p.res = h;
-            gemv_launch<PRO_NONE, EPI_RESIDUAL>(L, p);
-        }
+        gemv_launch<PRO_RMSNORM, EPI_QKV>(L, qkv_params(m, li, row0, rows));
+        const attn_params a = attn_params_of(m, li, row0);
+        const size_t smem = attn_smem(m, kAttnCluster);
+        if (hd == 64) L.go_cluster(attn_decode_kernel<64>, dim3(m->Hl * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
+        else L.go_cluster(attn_decode_kernel<128>, dim3(m->Hl * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
+        gemv_launch<PRO_NONE, EPI_RESIDUAL>(L, wo_params(m, li, row0, rows));
+        gemv_launch<PRO_RMSNORM, EPI_SWIGLU>(L, w13_params(m, li, row0, rows));
+        gemv_launch<PRO_NONE, EPI_RESIDUAL>(L, w2_params(m, li, row0, rows));
     }
-    if (head_mode) {
-        const dlinear& hw = m->tied ? m->tok : m->out;
-        gemv_params p{};
-        p.W = hw.w.p, p.N = m->Vl, p.K = D;
-        p.norm_w = m->norm.as<uint16_t>(), p.eps = c.norm_eps;
-        p.ldx = D, p.ldy = m->Vl;
-        if (head_mode == 2) {
-            p.rows = 1, p.x = x + size_t(rows - 1) * D, p.y = logits_dst;
-        } else {
-            p.rows = rows, p.x = x, p.y = logits_dst;
+    if (head_mode == 2) gemv_launch<PRO_RMSNORM, EPI_NONE>(L, head_params(m, x + size_t(rows - 1) * D, 1, logits_dst));
+    else if (head_mode == 1) gemv_launch<PRO_RMSNORM, EPI_NONE>(L, head_params(m, x, rows, logits_dst));
+}
+
+// __constant__ parameter slots of the megakernel: a process-wide pool per device, one slot per (model, rows, advance).
+std::mutex g_slot_mutex;
+const mc_llama* g_slot_owner[8][kMegaSlots] = {};
+uint32_t g_slot_key[8][kMegaSlots] = {};
+int mega_slot(mc_llama* m, uint32_t rows, int advance)
+{
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
+    const int d = m->dev->ordinal & 7;
+    const uint32_t key = rows * 2 + uint32_t(advance);
+    for (int i = 0; i < kMegaSlots; i++)
+        if (g_slot_owner[d][i] == m && g_slot_key[d][i] == key) return i;
+    for (int i = 0; i < kMegaSlots; i++)
+        if (g_slot_owner[d][i] == nullptr) {
+            g_slot_owner[d][i] = m, g_slot_key[d][i] = key;
+            return i;
         }
-        gemv_launch<PRO_RMSNORM, EPI_NONE>(L, p);
+    throw error(MC_ERR_RUNTIME, "megakernel: no free parameter slot (too many live models on this device)");
+}
+void release_mega_slots(const mc_llama* m)
+{
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
+    for (auto& dev : g_slot_owner)
+        for (auto& o : dev)
+            if (o == m) o = nullptr;
+}
+
+// The whole decode step of rows [0, rows) as ONE persistent kernel (greedy sampling fused).
+template <int MB> void launch_megakernel(mc_llama* m, launcher& L, uint32_t rows, int advance)
+{
+    auto kernel = decode_megakernel<MB>;
+    const mc_llama_config& c = m->cfg;
+    const uint32_t kmax = std::max(std::max(c.dim, m->Hl * c.head_dim), m->Fl);
+    const size_t smem = std::max(gemv_smem(MB, kmax), attn_smem(m, 1));
+    MC_REQUIRE(smem <= 100 * 1024, "megakernel: activation rows do not fit in shared memory");
+    const int slot = MB == 1 ? 0 : (MB == 2 ? 1 : 2);
+    if (m->mega_ctas_per_sm[slot] == 0) {
+        MC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        int occ = 0;
+        MC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kGemvThreads, smem));
+        MC_REQUIRE(occ >= 1, "megakernel: does not fit on an SM");
+        m->mega_ctas_per_sm[slot] = std::min(occ, 2);
     }
+    const uint32_t grid = uint32_t(m->dev->prop.multiProcessorCount) * m->mega_ctas_per_sm[slot];
+    mega_params P{};
+    P.g[0] = qkv_params(m, 0, 0, rows), P.g[1] = wo_params(m, 0, 0, rows), P.g[2] = w13_params(m, 0, 0, rows), P.g[3] = w2_params(m, 0, 0, rows);
+    P.g[4] = head_params(m, m->x.as<uint16_t>(), rows, m->logits.as<uint16_t>());
+    P.g[0].pro = PRO_RMSNORM, P.g[0].epi = EPI_QKV;
+    P.g[1].pro = PRO_NONE, P.g[1].epi = EPI_RESIDUAL;
+    P.g[2].pro = PRO_RMSNORM, P.g[2].epi = EPI_SWIGLU;
+    P.g[3].pro = PRO_NONE, P.g[3].epi = EPI_RESIDUAL;
+    P.g[4].pro = PRO_RMSNORM, P.g[4].epi = EPI_NONE;
+    P.attn = attn_params_of(m, 0, 0);
+    P.g[0].embed_table = m->tok.w.as<uint16_t>(), P.g[0].embed_ids = m->ids.as<int32_t>(), P.g[0].embed_out = m->x.as<uint16_t>();
+    P.g[4].am_val = m->pval.as<float>(), P.g[4].am_idx = m->pidx.as<int32_t>();
+    P.layer_stride = m->layer_stride, P.kv_layer_stride = kv_layer_elems(m);
+    P.g_bytes[0] = m->layers[0].wqkv.w.bytes, P.g_bytes[1] = m->layers[0].wo.w.bytes, P.g_bytes[2] = m->layers[0].w13.w.bytes;
+    P.g_bytes[3] = m->layers[0].w2.w.bytes, P.g_bytes[4] = size_t(m->Vl) * c.dim * 2;
+    P.n_layers = c.n_layers, P.rows = rows, P.head_dim = c.head_dim;
+    P.bar = m->bar.as<unsigned>(), P.err = m->errflag.as<int>();
+    P.ids = m->ids.as<int32_t>(), P.pos = m->pos.as<int32_t>(), P.out_log = m->out_log.as<int32_t>();
+    P.step_counter = m->step_counter.as<int32_t>(), P.advance = advance;
+    P.timing = m->mega_timing_on ? m->mega_timing.as<unsigned long long>() : nullptr;
+    // the parameter block goes to a __constant__ slot owned by this (model, rows, advance) combination
+    const int pslot = mega_slot(m, rows, advance);
+    MC_CUDA_CHECK(cudaMemcpyToSymbol(c_mega, &P, sizeof(P), size_t(pslot) * sizeof(mega_params), cudaMemcpyHostToDevice));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kGemvThreads), cfg.dynamicSmemBytes = smem, cfg.stream = L.s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative; // all CTAs must be co-resident for the grid barrier
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    L.mark();
+    MC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, pslot));
+    L.count++;
+    m->dev->launches.fetch_add(1);
 }
 
 void enqueue_sample(mc_llama* m, launcher& L, uint32_t rows, const mc_sampler_config& sc, int advance)
@@ -278,6 +437,12 @@ void enqueue_sample(mc_llama* m, launcher& L, uint32_t rows, const mc_sampler_co
 // one decode step for rows [0, n): forward in chunks of kMaxMB rows, then sample
 void enqueue_decode_step(mc_llama* m, launcher& L, uint32_t n, const mc_sampler_config& sc, int advance)
 {
+    if (n <= uint32_t(kMaxMB) && sc.mode == 0 && m->tok.fmt == WF_BF16 && (m->cfg.flags & MC_LLAMA_MEGAKERNEL)) {
+        if (n == 1) launch_megakernel<1>(m, L, n, advance);
+        else if (n == 2) launch_megakernel<2>(m, L, n, advance);
+        else launch_megakernel<4>(m, L, n, advance);
+        return;
+    }
     for (uint32_t r0 = 0; r0 < n; r0 += kMaxMB) {
         const uint32_t rows = std::min<uint32_t>(kMaxMB, n - r0);
         enqueue_rows(m, L, r0, rows, 1, m->logits.as<uint16_t>() + size_t(r0) * m->Vl);
@@ -433,15 +598,32 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
     m->tied = c.quant == 0;
     const uint32_t D = c.dim, hd = c.head_dim;
     m->layers.resize(c.n_layers);
-    for (auto& ly : m->layers) {
-        ly.attn_norm.alloc(size_t(D) * 2);
-        ly.ffn_norm.alloc(size_t(D) * 2);
-        ly.wqkv.N = (m->Hl + 2 * m->KVl) * hd, ly.wqkv.K = D;
-        ly.wo.N = D, ly.wo.K = m->Hl * hd;
-        ly.w13.N = 2 * m->Fl, ly.w13.K = D;
-        ly.w2.N = D, ly.w2.K = m->Fl;
-        for (dlinear* d : {&ly.wqkv, &ly.wo, &ly.w13, &ly.w2}) d->w.alloc(size_t(d->N) * d->K * 2);
+    {
+        // one arena, fixed stride per layer: attn_norm | ffn_norm | wqkv | wo | w13 | w2 (256-byte aligned pieces)
+        auto al = [](size_t n) { return (n + 255) & ~size_t(255); };
+        const size_t QKVN = size_t(m->Hl + 2 * m->KVl) * hd;
+        const size_t sz[6] = {al(size_t(D) * 2), al(size_t(D) * 2), al(QKVN * D * 2), al(size_t(D) * m->Hl * hd * 2),
+                              al(size_t(2) * m->Fl * D * 2), al(size_t(D) * m->Fl * 2)};
+        m->layer_stride = sz[0] + sz[1] + sz[2] + sz[3] + sz[4] + sz[5];
+        m->layer_arena.alloc(m->layer_stride * c.n_layers);
+        for (uint32_t li = 0; li < c.n_layers; li++) {
+            dlayer& ly = m->layers[li];
+            char* base = m->layer_arena.as<char>() + size_t(li) * m->layer_stride;
+            ly.attn_norm.view(base, size_t(D) * 2), base += sz[0];
+            ly.ffn_norm.view(base, size_t(D) * 2), base += sz[1];
+            ly.wqkv.N = uint32_t(QKVN), ly.wqkv.K = D;
+            ly.wqkv.w.view(base, QKVN * D * 2), base += sz[2];
+            ly.wo.N = D, ly.wo.K = m->Hl * hd;
+            ly.wo.w.view(base, size_t(D) * m->Hl * hd * 2), base += sz[3];
+            ly.w13.N = 2 * m->Fl, ly.w13.K = D;
+            ly.w13.w.view(base, size_t(2) * m->Fl * D * 2), base += sz[4];
+            ly.w2.N = D, ly.w2.K = m->Fl;
+            ly.w2.w.view(base, size_t(D) * m->Fl * 2);
+        }
     }
+    m->bar.alloc(256), m->errflag.alloc(256);
+    MC_CUDA_CHECK(cudaMemset(m->bar.p, 0, 256));
+    MC_CUDA_CHECK(cudaMemset(m->errflag.p, 0, 256));
     m->tok.N = c.vocab, m->tok.K = D;
     m->tok.w.alloc(size_t(c.vocab) * D * 2);
     m->norm.alloc(size_t(D) * 2);
@@ -478,10 +660,10 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
     m->ids.alloc(R * 4), m->pos.alloc(R * 4), m->row_seq.alloc(R * 4), m->uniforms.alloc(R * 4);
     m->out_log.alloc(size_t(kMaxLogSteps) * R * 4);
     m->step_counter.alloc(4);
-    m->pval.alloc(size_t(R) * kArgmaxBlocks * 4), m->pidx.alloc(size_t(R) * kArgmaxBlocks * 4);
+    m->pval.alloc(size_t(R) * 1024 * 4), m->pidx.alloc(size_t(R) * 1024 * 4);
     MC_CUDA_CHECK(cudaMemset(m->logits.p, 0, m->logits.bytes));
     MC_CUDA_CHECK(cudaMemset(m->hidden_save.p, 0, m->hidden_save.bytes));
-    MC_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&m->pinned), size_t(R) * 4 * 4 + 64, cudaHostAllocDefault));
+    MC_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&m->pinned), size_t(R) * 4 * 4 + 256, cudaHostAllocDefault));
     m->scale_bf16 = bf16_bits_to_f32(f32_to_bf16_bits(1.0f / std::sqrt(float(hd))));
     m->hidden_ptr.assign(c.n_seqs, nullptr);
     *out = m.release();
@@ -494,6 +676,7 @@ mc_status mc_llama_destroy(mc_llama* m)
     if (m) {
         cudaSetDevice(m->dev->ordinal);
         cudaStreamSynchronize(m->dev->stream);
+        release_mega_slots(m);
         delete m;
     }
     MC_API_END
@@ -608,6 +791,15 @@ mc_status mc_llama_prefill(mc_llama* m, uint32_t seq, const int32_t* ids, uint32
     MC_API_END
 }
 
+static void check_mega_error(mc_llama* m, int flag)
+{
+    if (flag) {
+        cudaMemset(m->errflag.p, 0, 4);
+        cudaMemset(m->bar.p, 0, 4);
+        throw error(MC_ERR_RUNTIME, "megakernel: grid barrier timed out (CTAs not co-resident?)");
+    }
+}
+
 static void stage_decode_inputs(mc_llama* m, uint32_t n, const int32_t* ids, const int32_t* pos)
 {
     MC_REQUIRE(n >= 1 && n <= m->cfg.n_seqs, "decode: number of sequences out of range");
@@ -641,7 +833,9 @@ mc_status mc_llama_decode(mc_llama* m, uint32_t n, const int32_t* ids, const int
     cudaStream_t s = m->dev->stream;
     int32_t* st_out = m->pinned + 3 * m->max_rows;
     MC_CUDA_CHECK(cudaMemcpyAsync(st_out, m->out_log.p, n * 4, cudaMemcpyDeviceToHost, s));
+    MC_CUDA_CHECK(cudaMemcpyAsync(st_out + n, m->errflag.p, 4, cudaMemcpyDeviceToHost, s));
     MC_CUDA_CHECK(cudaStreamSynchronize(s));
+    check_mega_error(m, st_out[n]);
     memcpy(out_ids, st_out, n * 4);
     MC_API_END
 }
@@ -672,6 +866,9 @@ mc_status mc_llama_decode_loop(mc_llama* m, uint32_t n, const int32_t* first_ids
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0), cudaEventDestroy(e1);
     if (elapsed_ms) *elapsed_ms = ms;
+    int errv = 0;
+    MC_CUDA_CHECK(cudaMemcpy(&errv, m->errflag.p, 4, cudaMemcpyDeviceToHost));
+    check_mega_error(m, errv);
     if (out_ids) MC_CUDA_CHECK(cudaMemcpy(out_ids, m->out_log.p, size_t(steps) * n * 4, cudaMemcpyDeviceToHost));
     MC_API_END
 }
@@ -715,6 +912,62 @@ mc_status mc_llama_cache(mc_llama* m, uint32_t seq, uint32_t layer, int which, u
                                    base + size_t(kvh) * c.max_seq_len * c.head_dim, size_t(c.head_dim) * 2, size_t(c.head_dim) * 2, n_pos,
                                    cudaMemcpyDeviceToHost));
     }
+    MC_API_END
+}
+
+// One ungraphed decode step of sequences [0,n) at their current device-side ids/pos with a CUDA event before
+// every launch: us[i] = time from launch i to launch i+1 (the last entry ends at step completion).
+mc_status mc_llama_profile_step(mc_llama* m, uint32_t n, float* us, uint32_t cap, uint32_t* count)
+{
+    MC_API_BEGIN
+    use(m);
+    MC_REQUIRE(m->finalized && us && count, "bad arguments");
+    MC_REQUIRE(n >= 1 && n <= m->cfg.n_seqs, "profile_step: number of sequences out of range");
+    mc_sampler_config sc{};
+    if (n <= uint32_t(kMaxMB) && (m->cfg.flags & MC_LLAMA_MEGAKERNEL)) {
+        // megakernel: per-phase stamps of CTA 0; us[3k..3k+2] = {wait, work, until next phase entry} of phase k
+        const uint32_t phases = m->cfg.n_layers * 5 + 1;
+        if (!m->mega_timing.p) m->mega_timing.alloc(size_t(phases + 1) * 3 * 8);
+        MC_CUDA_CHECK(cudaMemsetAsync(m->mega_timing.p, 0, m->mega_timing.bytes, m->dev->stream));
+        MC_CUDA_CHECK(cudaMemsetAsync(m->step_counter.p, 0, 4, m->dev->stream));
+        m->mega_timing_on = true;
+        launcher L{m, m->dev->stream, false};
+        try {
+            enqueue_decode_step(m, L, n, sc, 0);
+        } catch (...) {
+            m->mega_timing_on = false;
+            throw;
+        }
+        m->mega_timing_on = false;
+        MC_CUDA_CHECK(cudaStreamSynchronize(m->dev->stream));
+        std::vector<unsigned long long> t(size_t(phases + 1) * 3);
+        MC_CUDA_CHECK(cudaMemcpy(t.data(), m->mega_timing.p, t.size() * 8, cudaMemcpyDeviceToHost));
+        *count = phases * 3;
+        for (uint32_t k = 0; k < phases; k++) {
+            const float wait = float(t[k * 3 + 1] - t[k * 3 + 0]) * 1e-3f, work = float(t[k * 3 + 2] - t[k * 3 + 1]) * 1e-3f;
+            const float gap = float(t[(k + 1) * 3] - t[k * 3 + 2]) * 1e-3f;
+            if (k * 3 + 2 < cap) us[k * 3] = wait, us[k * 3 + 1] = work, us[k * 3 + 2] = gap;
+        }
+        // the constant slot of (n, advance=0) now holds a timing pointer: refresh it on the next plain launch
+        release_mega_slots(m);
+        for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
+        m->graphs.clear();
+        return MC_OK;
+    }
+    std::vector<cudaEvent_t> ev;
+    launcher L{m, m->dev->stream, false};
+    L.events = &ev;
+    MC_CUDA_CHECK(cudaMemsetAsync(m->step_counter.p, 0, 4, m->dev->stream));
+    enqueue_decode_step(m, L, n, sc, 0);
+    L.mark();
+    MC_CUDA_CHECK(cudaStreamSynchronize(m->dev->stream));
+    *count = uint32_t(ev.size() - 1);
+    for (size_t i = 0; i + 1 < ev.size(); i++) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+        if (i < cap) us[i] = ms * 1e3f;
+    }
+    for (auto e : ev) cudaEventDestroy(e);
     MC_API_END
 }
 

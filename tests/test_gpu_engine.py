@@ -57,7 +57,7 @@ def test_device_generator_matches_oracle_bits():
     assert np.array_equal(a.cache(0, 2, 0, len(ids)), b.cache(0, 2, 0, len(ids)))
 
 
-@pytest.mark.parametrize("flags", [0, 2, 4])  # graph+PDL, no graph, no PDL
+@pytest.mark.parametrize("flags", [0, 2, 4, 8, 10])  # graph+PDL, no graph, no PDL, megakernel, megakernel without graph
 def test_prefill_and_greedy_decode_match_oracle(flags):
     o = orc.Llama(orc.make_cfg(**SMALL), BF16)
     o.init_random(0x5EED)
