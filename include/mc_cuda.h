@@ -180,12 +180,14 @@ MC_API mc_status mc_llama_profile_step(mc_llama* m, uint32_t n, float* us, uint3
  * y[M,N] = x[M,K] * W[N,K]^T with fp32 accumulation and one RNE rounding to bf16
  * (kernel/bmm.metal:24-82 through nn/linear.h:70-81).  M <= 8 takes the streaming GEMV path. */
 MC_API mc_status mc_linear_bf16(mc_device* dev, mc_buffer* y, mc_buffer* x, mc_buffer* w, uint32_t M, uint32_t N, uint32_t K);
-/* QLoRA base linear over packed int4: w4 [N,K/2] bytes (two weights per byte), scales fp32 [N,K/32]
- * (quantization/lora.h:94-122 + kernel/mul.metal:59-85 fused). */
-MC_API mc_status mc_linear_w4(mc_device* dev, mc_buffer* y, mc_buffer* x, mc_buffer* w4, mc_buffer* scales, uint32_t M, uint32_t N, uint32_t K);
-/* pack int8 (values in [-8,7]) [N,K] into the engine's int4 stream layout and back (bit-exact). */
-MC_API mc_status mc_pack_w4(mc_device* dev, mc_buffer* w4, mc_buffer* q8, uint32_t N, uint32_t K);
+/* QLoRA base linear over packed int4 (quantization/lora.h:94-122 + kernel/mul.metal:59-85 fused, without the adaptor):
+ * y[M,N] = r( x[M,K] . r(r(q) * r(s))^T ), M <= 8.  w4 / scales_packed come from mc_pack_w4. */
+MC_API mc_status mc_linear_w4(mc_device* dev, mc_buffer* y, mc_buffer* x, mc_buffer* w4, mc_buffer* scales_packed, uint32_t M, uint32_t N, uint32_t K);
+/* Packs int8 [N,K] (values in [-8,7]; anything else is MC_ERR_INVALID) and fp32 scales [N,K/32] into the engine's
+ * streaming layout (two weights per byte in tensor-core fragment order, bf16 r(scale)); mc_unpack_w4 is the exact inverse. */
+MC_API mc_status mc_pack_w4(mc_device* dev, mc_buffer* w4, mc_buffer* scales_packed, mc_buffer* q8, mc_buffer* scales_f32, uint32_t N, uint32_t K);
 MC_API mc_status mc_unpack_w4(mc_device* dev, mc_buffer* q8, mc_buffer* w4, uint32_t N, uint32_t K);
+MC_API mc_status mc_w4_sizes(uint32_t N, uint32_t K, size_t* w4_nbytes, size_t* scales_nbytes);
 
 #ifdef __cplusplus
 }

@@ -121,7 +121,8 @@ _SIGNATURES = {
     "mc_llama_profile_step": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
     "mc_linear_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "mc_linear_w4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
-    "mc_pack_w4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "mc_pack_w4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "mc_w4_sizes": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "mc_unpack_w4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
 }
 
@@ -414,3 +415,29 @@ class Llama:
 
 def linear_bf16(dev: Device, y: Buffer, x: Buffer, w: Buffer, M: int, N: int, K: int):
     check(lib().mc_linear_bf16(dev.h, y.h, x.h, w.h, M, N, K))
+
+
+def w4_sizes(N: int, K: int):
+    a, b = C.c_size_t(), C.c_size_t()
+    check(lib().mc_w4_sizes(N, K, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def pack_w4(dev: Device, q8: np.ndarray, scales: np.ndarray):
+    """int8 [N,K] in [-8,7] + fp32 scales [N,K/32] -> (packed weights, packed bf16 scales) device buffers."""
+    N, K = q8.shape
+    wb, sb = w4_sizes(N, K)
+    dq, ds = dev.upload(np.ascontiguousarray(q8, np.int8)), dev.upload(np.ascontiguousarray(scales, np.float32))
+    w4, sp = dev.alloc(wb), dev.alloc(sb)
+    check(lib().mc_pack_w4(dev.h, w4.h, sp.h, dq.h, ds.h, N, K))
+    return w4, sp
+
+
+def unpack_w4(dev: Device, w4: Buffer, N: int, K: int) -> np.ndarray:
+    out = dev.alloc(N * K)
+    check(lib().mc_unpack_w4(dev.h, out.h, w4.h, N, K))
+    return out.read(np.int8).reshape(N, K)
+
+
+def linear_w4(dev: Device, y: Buffer, x: Buffer, w4: Buffer, sp: Buffer, M: int, N: int, K: int):
+    check(lib().mc_linear_w4(dev.h, y.h, x.h, w4.h, sp.h, M, N, K))

@@ -203,7 +203,7 @@ struct phase_adj {
     size_t kv_off;  // element offset of this layer's KV cache
     bool embed;     // gather the input rows from the embedding table
 };
-template <int MB, int PRO_T, int EPI_T, bool MEGA>
+template <int MB, int PRO_T, int EPI_T, bool MEGA, int KS_T>
 __device__ __forceinline__ void gemv_body(const gemv_params& p, unsigned char* smem, const mega_sync& sy, const phase_adj& adj)
 {
     const int PRO = PRO_T >= 0 ? PRO_T : p.pro;
@@ -212,7 +212,7 @@ __device__ __forceinline__ void gemv_body(const gemv_params& p, unsigned char* s
     float* sred = reinterpret_cast<float*>(smem + size_t(MB) * p.K * 2);   // [8 warps][2][MB]
     float* sscr = sred + kGemvWarps * 2 * MB;                              // [8]
 
-    const uint32_t KSPLIT = p.ksplit;
+    const uint32_t KSPLIT = KS_T > 0 ? uint32_t(KS_T) : p.ksplit; // compile-time in the stand-alone kernels
     const uint32_t UPC = kGemvWarps / KSPLIT; // units per CTA iteration
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t slot = warp / KSPLIT, ks = warp % KSPLIT;
@@ -490,11 +490,11 @@ __device__ __forceinline__ void gemv_body(const gemv_params& p, unsigned char* s
     }
 }
 
-template <int MB, int PRO, int EPI>
+template <int MB, int PRO, int EPI, int KS>
 __global__ void __launch_bounds__(kGemvThreads, 2) gemv_bf16_kernel(const gemv_params p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    gemv_body<MB, PRO, EPI, false>(p, smem, mega_sync{}, phase_adj{0, 0, false});
+    gemv_body<MB, PRO, EPI, false, KS>(p, smem, mega_sync{}, phase_adj{0, 0, false});
 }
 
 // ---- K5: decode attention ------------------------------------------------------------------------------------
@@ -745,7 +745,7 @@ template <int MB> __global__ void __launch_bounds__(kGemvThreads, 2) decode_mega
                 else if (kind == 2) pf = shift(P.g[3].W, w_off), pfb = P.g_bytes[3];
                 else if (kind == 3 && li + 1 < P.n_layers) pf = shift(P.g[0].W, w_off + P.layer_stride), pfb = P.g_bytes[0];
             }
-            gemv_body<MB, -1, -1, true>(P.g[gi], smem, mega_sync{P.bar, P.err, phase * G, pf, pfb, tm}, phase_adj{w_off, kv_off, phase == 0});
+            gemv_body<MB, -1, -1, true, 0>(P.g[gi], smem, mega_sync{P.bar, P.err, phase * G, pf, pfb, tm}, phase_adj{w_off, kv_off, phase == 0});
         }
     }
     const unsigned phase = n_phases;

@@ -14,7 +14,7 @@
 //   global      tok [V, D], norm [D], out [Vl, D] (aliases tok when tied, huggingface/llama.h:103)
 //   KV cache    [layer][seq][KVl][max_seq][hd] bf16 — one contiguous stream per (seq, kv head)
 //   rope tables fcos/fsin [2*max_seq, hd/2] fp32 (nn/embedding.h:160-176)
-#include "mc_decode_kernels.cuh"
+#include "mc_quant_kernels.cuh"
 
 #include <cmath>
 #include <map>
@@ -63,6 +63,7 @@ struct dlinear {
     dbuf w;                // WF_BF16: bf16 [N,K]; WF_W8G/WF_W8ROW: int8 [N,K]; WF_W4: packed [N,K/2]
     dbuf scales;           // fp32 [N,K/group] or [N]
     dbuf lora_b;           // bf16 [N, rank]
+    dbuf q8, s32;          // staging until finalize: int8 [N,K] and fp32 [N,K/32] (or [N]) in the reference layout
     size_t stream_bytes() const { return w.bytes + scales.bytes + lora_b.bytes; }
 };
 
@@ -94,7 +95,7 @@ struct mc_llama {
     // activations
     uint32_t max_rows = 0;
     dbuf x, h, q, attn, z, logits, hidden_save;
-    dbuf ids, pos, row_seq, uniforms, out_log, step_counter, pval, pidx;
+    dbuf ids, pos, row_seq, uniforms, out_log, step_counter, pval, pidx, lora_ax, pack_bad;
     int32_t* pinned = nullptr; // host staging: ids | pos | out
     float scale_bf16 = 0.0f;
     std::map<uint64_t, cudaGraphExec_t> graphs;
@@ -107,11 +108,11 @@ struct mc_llama {
         if (pinned) cudaFreeHost(pinned);
         for (auto& l : layers) {
             for (dbuf* b : {&l.attn_norm, &l.ffn_norm, &l.lora_a_qkv, &l.lora_a_o, &l.lora_a_13, &l.lora_a_2}) b->release();
-            for (dlinear* d : {&l.wqkv, &l.wo, &l.w13, &l.w2}) d->w.release(), d->scales.release(), d->lora_b.release();
+            for (dlinear* d : {&l.wqkv, &l.wo, &l.w13, &l.w2}) d->w.release(), d->scales.release(), d->lora_b.release(), d->q8.release(), d->s32.release();
         }
-        for (dlinear* d : {&tok, &out}) d->w.release(), d->scales.release(), d->lora_b.release();
+        for (dlinear* d : {&tok, &out}) d->w.release(), d->scales.release(), d->lora_b.release(), d->q8.release(), d->s32.release();
         for (dbuf* b : {&layer_arena, &bar, &errflag, &mega_timing, &norm, &fcos, &fsin, &kcache, &vcache, &x, &h, &q, &attn, &z, &logits, &hidden_save, &ids, &pos, &row_seq,
-                        &uniforms, &out_log, &step_counter, &pval, &pidx})
+                        &uniforms, &out_log, &step_counter, &pval, &pidx, &lora_ax, &pack_bad})
             b->release();
     }
 };
@@ -215,17 +216,15 @@ uint32_t choose_ksplit(const mc_device* dev, uint32_t N, uint32_t K)
     return ksplit;
 }
 
-template <int MB, int PRO, int EPI> void gemv_launch_mb(launcher& L, gemv_params p)
+template <int MB, int PRO, int EPI, int KS> void gemv_launch_ks(launcher& L, const gemv_params& p)
 {
-    auto kernel = gemv_bf16_kernel<MB, PRO, EPI>;
+    auto kernel = gemv_bf16_kernel<MB, PRO, EPI, KS>;
     static bool configured[8] = {false};
     const int dev = L.m->dev->ordinal;
     if (!configured[dev & 7]) {
         MC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         configured[dev & 7] = true;
     }
-    MC_REQUIRE(p.N % 2 == 0 && p.K % 256 == 0, "gemv: N must be even and K a multiple of 256");
-    p.ksplit = choose_ksplit(L.m->dev, p.N, p.K);
     const size_t smem = gemv_smem(MB, p.K);
     MC_REQUIRE(smem <= 100 * 1024, "gemv: activation rows do not fit in shared memory");
     const uint32_t upc = kGemvWarps / p.ksplit;
@@ -235,6 +234,17 @@ template <int MB, int PRO, int EPI> void gemv_launch_mb(launcher& L, gemv_params
     const uint32_t grid = ctas_needed < cap ? ctas_needed : cap;
     L.go(kernel, dim3(grid), dim3(kGemvThreads), smem, p);
 }
+template <int MB, int PRO, int EPI> void gemv_launch_mb(launcher& L, gemv_params p)
+{
+    MC_REQUIRE(p.N % 2 == 0 && p.K % 256 == 0, "gemv: N must be even and K a multiple of 256");
+    p.ksplit = choose_ksplit(L.m->dev, p.N, p.K);
+    switch (p.ksplit) {
+    case 1: gemv_launch_ks<MB, PRO, EPI, 1>(L, p); break;
+    case 2: gemv_launch_ks<MB, PRO, EPI, 2>(L, p); break;
+    case 4: gemv_launch_ks<MB, PRO, EPI, 4>(L, p); break;
+    default: gemv_launch_ks<MB, PRO, EPI, 8>(L, p); break;
+    }
+}
 template <int PRO, int EPI> void gemv_launch(launcher& L, const gemv_params& p)
 {
     MC_REQUIRE(p.rows >= 1 && p.rows <= uint32_t(kMaxMB), "gemv: unsupported number of activation rows");
@@ -242,6 +252,45 @@ template <int PRO, int EPI> void gemv_launch(launcher& L, const gemv_params& p)
     case 1: gemv_launch_mb<1, PRO, EPI>(L, p); break;
     case 2: gemv_launch_mb<2, PRO, EPI>(L, p); break;
     default: gemv_launch_mb<4, PRO, EPI>(L, p); break;
+    }
+}
+
+// ---- quantised GEMV launch ---------------------------------------------------------------------------------------
+size_t qgemv_smem(uint32_t rows, uint32_t K) { return size_t(rows + 1) * (K + kQPad) * 2 + (kGemvWarps * 32 * 4 + 8) * sizeof(float); }
+
+uint32_t choose_qsplit(const mc_device* dev, uint32_t N, uint32_t K, uint32_t kt)
+{
+    const uint32_t supers = (N / 2 + 7) / 8, ktiles = K / kt;
+    const uint32_t warps = uint32_t(dev->prop.multiProcessorCount) * 2 * kGemvWarps;
+    uint32_t ks = 1;
+    while (ks < 8 && supers * ks < warps && ktiles % (ks * 2) == 0 && ktiles / (ks * 2) >= 2) ks *= 2;
+    return ks;
+}
+template <int FMT, int PRO, int EPI, int KS> void qgemv_launch_ks(launcher& L, const qgemv_params& q)
+{
+    auto kernel = gemv_q_kernel<FMT, PRO, EPI, KS>;
+    static bool configured[8] = {false};
+    const int dev = L.m->dev->ordinal;
+    if (!configured[dev & 7]) {
+        MC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured[dev & 7] = true;
+    }
+    const size_t smem = qgemv_smem(q.g.rows, q.g.K);
+    MC_REQUIRE(smem <= 200 * 1024, "quantised gemv: activation rows do not fit in shared memory");
+    const uint32_t supers = (q.g.N / 2 + 7) / 8, upc = kGemvWarps / KS;
+    const uint32_t ctas_needed = (supers + upc - 1) / upc;
+    const uint32_t cap = uint32_t(L.m->dev->prop.multiProcessorCount) * 2;
+    L.go(kernel, dim3(ctas_needed < cap ? ctas_needed : cap), dim3(kGemvThreads), smem, q);
+}
+template <int FMT, int PRO, int EPI> void qgemv_launch(launcher& L, const qgemv_params& q)
+{
+    MC_REQUIRE(q.g.rows >= 1 && q.g.rows <= uint32_t(kQMaxMB), "quantised gemv: unsupported number of activation rows");
+    MC_REQUIRE(q.g.N % 2 == 0 && q.g.K % 256 == 0, "quantised gemv: N must be even and K a multiple of 256");
+    switch (choose_qsplit(L.m->dev, q.g.N, q.g.K, FMT == WF_W4 ? 64 : 32)) {
+    case 1: qgemv_launch_ks<FMT, PRO, EPI, 1>(L, q); break;
+    case 2: qgemv_launch_ks<FMT, PRO, EPI, 2>(L, q); break;
+    case 4: qgemv_launch_ks<FMT, PRO, EPI, 4>(L, q); break;
+    default: qgemv_launch_ks<FMT, PRO, EPI, 8>(L, q); break;
     }
 }
 
@@ -323,6 +372,59 @@ size_t attn_smem(const mc_llama* m, uint32_t cluster)
     return (hd + 8 + 4 + hd + size_t(slots) * hd + chunk) * sizeof(float);
 }
 
+// QLoRA blocks (quantization/lora.h:94-122): every linear is  y = r(x . dq(W)^T) + r(2.0 * B(A(x)))  with
+// ax = r(A . x) from a small bf16 GEMV over the stacked adaptors of the linears that share the input.
+void enqueue_rows_quant(mc_llama* m, launcher& L, uint32_t row0, uint32_t rows, int head_mode, uint16_t* logits_dst)
+{
+    const mc_llama_config& c = m->cfg;
+    const uint32_t D = c.dim, hd = c.head_dim, rank = c.lora_rank;
+    const uint32_t ax_ld = 3 * rank;
+    uint16_t* ax = m->lora_ax.as<uint16_t>() + size_t(row0) * ax_ld;
+    const float lscale = bf16_bits_to_f32(f32_to_bf16_bits(c.lora_scale));
+    auto lora_a = [&](const gemv_params& main, const dbuf& A, uint32_t n_rows_a, bool norm) {
+        gemv_params p{};
+        p.W = A.p, p.N = n_rows_a, p.K = main.K, p.rows = rows;
+        p.x = main.x, p.ldx = main.ldx, p.norm_w = main.norm_w, p.eps = main.eps;
+        p.y = ax, p.ldy = ax_ld;
+        if (norm) gemv_launch<PRO_RMSNORM, EPI_NONE>(L, p);
+        else gemv_launch<PRO_NONE, EPI_NONE>(L, p);
+    };
+    auto quant = [&](const gemv_params& g, const dlinear& d, uint32_t slices) {
+        qgemv_params q{};
+        q.g = g;
+        q.scales = d.scales.p, q.lora_b = d.lora_b.as<uint16_t>(), q.lora_ax = ax, q.ax_ld = ax_ld, q.ax_slices = slices;
+        q.slice_rows0 = m->Hl * hd, q.slice_rows1 = (m->Hl + m->KVl) * hd;
+        q.rank = rank, q.lora_scale = lscale;
+        return q;
+    };
+    for (uint32_t li = 0; li < c.n_layers; li++) {
+        dlayer& ly = m->layers[li];
+        const gemv_params gq = qkv_params(m, li, row0, rows);
+        lora_a(gq, ly.lora_a_qkv, 3 * rank, true);
+        qgemv_launch<WF_W4, PRO_RMSNORM, EPI_QKV>(L, quant(gq, ly.wqkv, 3));
+        const attn_params a = attn_params_of(m, li, row0);
+        const size_t smem = attn_smem(m, kAttnCluster);
+        if (hd == 64) L.go_cluster(attn_decode_kernel<64>, dim3(m->Hl * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
+        else L.go_cluster(attn_decode_kernel<128>, dim3(m->Hl * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
+        const gemv_params go = wo_params(m, li, row0, rows);
+        lora_a(go, ly.lora_a_o, rank, false);
+        qgemv_launch<WF_W4, PRO_NONE, EPI_RESIDUAL>(L, quant(go, ly.wo, 1));
+        const gemv_params g13 = w13_params(m, li, row0, rows);
+        lora_a(g13, ly.lora_a_13, 2 * rank, true);
+        qgemv_launch<WF_W4, PRO_RMSNORM, EPI_SWIGLU>(L, quant(g13, ly.w13, 2));
+        const gemv_params g2 = w2_params(m, li, row0, rows);
+        lora_a(g2, ly.lora_a_2, rank, false);
+        qgemv_launch<WF_W4, PRO_NONE, EPI_RESIDUAL>(L, quant(g2, ly.w2, 1));
+    }
+    if (head_mode) {
+        uint16_t* x = m->x.as<uint16_t>() + size_t(row0) * D;
+        qgemv_params q{};
+        q.g = head_mode == 2 ? head_params(m, x + size_t(rows - 1) * D, 1, logits_dst) : head_params(m, x, rows, logits_dst);
+        q.scales = m->out.scales.p; // output is a quantization::linear: int8 with one scale per row, no adaptor (quantization/linear.h:17-64)
+        qgemv_launch<WF_W8ROW, PRO_RMSNORM, EPI_NONE>(L, q);
+    }
+}
+
 // Enqueue the forward pass of `rows` activation rows (<= kMaxMB) starting at row offset `row0` of the
 // activation buffers, one kernel per fused op.  Row r reads ids[row0+r], pos[row0+r], row_seq[row0+r].
 //   head_mode: 0 none, 1 logits for every row, 2 last row only
@@ -334,6 +436,10 @@ void enqueue_rows(mc_llama* m, launcher& L, uint32_t row0, uint32_t rows, int he
     const int32_t* ids = m->ids.as<int32_t>() + row0;
 
     L.go(embed_kernel, dim3(rows), dim3(256), 0, x, D, (const void*)m->tok.w.p, (const float*)m->tok.scales.p, m->tok.fmt, D, c.vocab, ids);
+    if (c.quant) {
+        enqueue_rows_quant(m, L, row0, rows, head_mode, logits_dst);
+        return;
+    }
     for (uint32_t li = 0; li < c.n_layers; li++) {
         gemv_launch<PRO_RMSNORM, EPI_QKV>(L, qkv_params(m, li, row0, rows));
         const attn_params a = attn_params_of(m, li, row0);
@@ -490,6 +596,8 @@ void run_decode_step(mc_llama* m, uint32_t n, const mc_sampler_config& sc, int a
 }
 
 // ---- parameter names ---------------------------------------------------------------------------------------------
+// A reference parameter (full, unsharded, host) maps to a 2-D slice of a fused device tensor.
+enum { GEN_BF16 = 0, GEN_I8 = 1, GEN_SCALE = 2 };
 struct slice2d {
     void* dst;          // device destination of element (0,0) of the slice
     size_t dst_ld;      // destination row pitch in elements
@@ -497,6 +605,7 @@ struct slice2d {
     uint32_t src_row0, src_col0, src_K; // slice origin and row length of the full tensor
     size_t elem;        // bytes per element
     uint64_t full_elems;
+    int gen;            // which synthetic generator fills it
 };
 
 bool parse_layer_name(const std::string& name, uint32_t& layer, std::string& rest)
@@ -504,8 +613,47 @@ bool parse_layer_name(const std::string& name, uint32_t& layer, std::string& res
     if (name.rfind("layers.", 0) != 0) return false;
     const size_t dot = name.find('.', 7);
     if (dot == std::string::npos) return false;
+    for (size_t i = 7; i < dot; i++)
+        if (name[i] < '0' || name[i] > '9') return false;
+    if (dot == 7 || dot - 7 > 6) return false;
     layer = uint32_t(std::stoul(name.substr(7, dot - 7)));
     rest = name.substr(dot + 1);
+    return true;
+}
+
+// where one of the seven reference linears of a block lives inside the fused device tensors
+struct linspec {
+    dlinear* d = nullptr;
+    dbuf* lora_a = nullptr;
+    uint32_t a_row0 = 0;       // first row of its adaptor A inside the stacked A matrix
+    uint32_t dst_row0 = 0;     // first fused row
+    uint32_t dst_step = 1;     // fused row step (2 = interleaved w1/w3)
+    uint32_t rows = 0;         // local rows
+    uint32_t src_row0 = 0;     // first row of the full tensor held by this shard
+    uint32_t Kl = 0;           // local reduction length
+    uint32_t src_col0 = 0;     // first column of the full tensor held by this shard
+    uint32_t K_full = 0, N_full = 0;
+};
+bool linear_spec(mc_llama* m, dlayer& ly, const std::string& lin, linspec& o)
+{
+    const mc_llama_config& c = m->cfg;
+    const uint32_t D = c.dim, hd = c.head_dim, r = c.tp_rank, rank = c.lora_rank;
+    const uint32_t QO = c.n_heads * hd, KO = c.n_kv_heads * hd;
+    if (lin == "attention.wq") o = {&ly.wqkv, &ly.lora_a_qkv, 0, 0, 1, m->Hl * hd, r * m->Hl * hd, D, 0, D, QO};
+    else if (lin == "attention.wk") o = {&ly.wqkv, &ly.lora_a_qkv, rank, m->Hl * hd, 1, m->KVl * hd, r * m->KVl * hd, D, 0, D, KO};
+    else if (lin == "attention.wv") o = {&ly.wqkv, &ly.lora_a_qkv, 2 * rank, (m->Hl + m->KVl) * hd, 1, m->KVl * hd, r * m->KVl * hd, D, 0, D, KO};
+    else if (lin == "attention.wo") o = {&ly.wo, &ly.lora_a_o, 0, 0, 1, D, 0, m->Hl * hd, r * m->Hl * hd, QO, D};
+    else if (lin == "feed_forward.w1") o = {&ly.w13, &ly.lora_a_13, 0, 0, 2, m->Fl, r * m->Fl, D, 0, D, c.ffn_dim};
+    else if (lin == "feed_forward.w3") o = {&ly.w13, &ly.lora_a_13, rank, 1, 2, m->Fl, r * m->Fl, D, 0, D, c.ffn_dim};
+    else if (lin == "feed_forward.w2") o = {&ly.w2, &ly.lora_a_2, 0, 0, 1, D, 0, m->Fl, r * m->Fl, c.ffn_dim, D};
+    else return false;
+    return true;
+}
+
+bool ends_with(const std::string& s, const std::string& suf, std::string& stem)
+{
+    if (s.size() <= suf.size() || s.compare(s.size() - suf.size(), suf.size(), suf) != 0) return false;
+    stem = s.substr(0, s.size() - suf.size());
     return true;
 }
 
@@ -513,61 +661,91 @@ bool parse_layer_name(const std::string& name, uint32_t& layer, std::string& res
 std::vector<slice2d> resolve(mc_llama* m, const std::string& name)
 {
     const mc_llama_config& c = m->cfg;
-    const uint32_t D = c.dim, hd = c.head_dim, T = c.tp_world, r = c.tp_rank;
-    MC_REQUIRE(c.quant == 0, "quantised parameter layout is not available in this build");
+    const uint32_t D = c.dim, r = c.tp_rank, G = c.group_size, rank = c.lora_rank;
+    const bool Q = c.quant != 0;
     std::vector<slice2d> out;
-    auto vec = [&](dbuf& b, uint32_t n) { out.push_back({b.p, n, 1, n, 0, 0, n, 2, n}); };
+    auto vec = [&](dbuf& b, uint32_t n) { out.push_back({b.p, n, 1, n, 0, 0, n, 2, n, GEN_BF16}); };
+    auto staged = [&](dbuf& b, const char* what) {
+        if (!b.p) throw error(MC_ERR_INVALID, std::string("parameter ") + name + ": " + what + " were already packed by mc_llama_finalize");
+        return b.p;
+    };
     uint32_t li = 0;
-    std::string rest;
+    std::string rest, stem;
     if (name == "tok_embeddings.weight") {
-        out.push_back({m->tok.w.p, D, c.vocab, D, 0, 0, D, 2, uint64_t(c.vocab) * D});
-        if (!m->tied || T > 1) {
-            // the head is vocab-sharded; when tied it is a slice copy of the embedding table
-        }
+        if (Q) out.push_back({m->tok.w.p, D, c.vocab, D, 0, 0, D, 1, uint64_t(c.vocab) * D, GEN_I8});
+        else out.push_back({m->tok.w.p, D, c.vocab, D, 0, 0, D, 2, uint64_t(c.vocab) * D, GEN_BF16});
+    } else if (name == "tok_embeddings.scales" && Q) {
+        out.push_back({m->tok.scales.p, 1, c.vocab, 1, 0, 0, 1, 4, uint64_t(c.vocab), GEN_SCALE});
     } else if (name == "output.weight") {
         MC_REQUIRE(!m->tied, "output.weight is tied to tok_embeddings.weight in the bf16 model (huggingface/llama.h:103)");
-        out.push_back({m->out.w.p, D, m->Vl, D, r * m->Vl, 0, D, 2, uint64_t(c.vocab) * D});
+        out.push_back({staged(m->out.q8, "the weights"), D, m->Vl, D, r * m->Vl, 0, D, 1, uint64_t(c.vocab) * D, GEN_I8});
+    } else if (name == "output.scales" && Q) {
+        out.push_back({m->out.scales.p, 1, m->Vl, 1, r * m->Vl, 0, 1, 4, uint64_t(c.vocab), GEN_SCALE});
     } else if (name == "norm.weight") {
         vec(m->norm, D);
     } else if (parse_layer_name(name, li, rest)) {
-        MC_REQUIRE(li < c.n_layers, "layer index out of range: " + name);
+        if (li >= c.n_layers) throw error(MC_ERR_NOT_FOUND, "layer index out of range: " + name);
         dlayer& ly = m->layers[li];
-        uint16_t* wqkv = ly.wqkv.w.as<uint16_t>();
-        const uint32_t QO = c.n_heads * hd, KO = c.n_kv_heads * hd;
+        linspec sp;
         if (rest == "attention_norm.weight") vec(ly.attn_norm, D);
         else if (rest == "ffn_norm.weight") vec(ly.ffn_norm, D);
-        else if (rest == "attention.wq.weight") out.push_back({wqkv, D, m->Hl * hd, D, r * m->Hl * hd, 0, D, 2, uint64_t(QO) * D});
-        else if (rest == "attention.wk.weight")
-            out.push_back({wqkv + size_t(m->Hl) * hd * D, D, m->KVl * hd, D, r * m->KVl * hd, 0, D, 2, uint64_t(KO) * D});
-        else if (rest == "attention.wv.weight")
-            out.push_back({wqkv + size_t(m->Hl + m->KVl) * hd * D, D, m->KVl * hd, D, r * m->KVl * hd, 0, D, 2, uint64_t(KO) * D});
-        else if (rest == "attention.wo.weight")
-            out.push_back({ly.wo.w.p, size_t(m->Hl) * hd, D, m->Hl * hd, 0, r * m->Hl * hd, QO, 2, uint64_t(D) * QO});
-        else if (rest == "feed_forward.w1.weight")
-            out.push_back({ly.w13.w.p, size_t(2) * D, m->Fl, D, r * m->Fl, 0, D, 2, uint64_t(c.ffn_dim) * D});
-        else if (rest == "feed_forward.w3.weight")
-            out.push_back({ly.w13.w.as<uint16_t>() + D, size_t(2) * D, m->Fl, D, r * m->Fl, 0, D, 2, uint64_t(c.ffn_dim) * D});
-        else if (rest == "feed_forward.w2.weight")
-            out.push_back({ly.w2.w.p, m->Fl, D, m->Fl, 0, r * m->Fl, c.ffn_dim, 2, uint64_t(D) * c.ffn_dim});
-        else throw error(MC_ERR_NOT_FOUND, "unknown parameter: " + name);
+        else if (ends_with(rest, ".adaptor.A.weight", stem) && Q && linear_spec(m, ly, stem, sp))
+            out.push_back({sp.lora_a->as<uint16_t>() + size_t(sp.a_row0) * sp.Kl, sp.Kl, rank, sp.Kl, 0, sp.src_col0, sp.K_full, 2, uint64_t(rank) * sp.K_full, GEN_BF16});
+        else if (ends_with(rest, ".adaptor.B.weight", stem) && Q && linear_spec(m, ly, stem, sp))
+            out.push_back({sp.d->lora_b.as<uint16_t>() + size_t(sp.dst_row0) * rank, size_t(rank) * sp.dst_step, sp.rows, rank, sp.src_row0, 0, rank, 2,
+                           uint64_t(sp.N_full) * rank, GEN_BF16});
+        else if (ends_with(rest, ".scales", stem) && Q && linear_spec(m, ly, stem, sp))
+            out.push_back({static_cast<float*>(staged(sp.d->s32, "the scales")) + size_t(sp.dst_row0) * (sp.Kl / G), size_t(sp.Kl / G) * sp.dst_step, sp.rows,
+                           sp.Kl / G, sp.src_row0, sp.src_col0 / G, sp.K_full / G, 4, uint64_t(sp.N_full) * (sp.K_full / G), GEN_SCALE});
+        else if (ends_with(rest, ".weight", stem) && linear_spec(m, ly, stem, sp)) {
+            if (Q)
+                out.push_back({static_cast<int8_t*>(staged(sp.d->q8, "the weights")) + size_t(sp.dst_row0) * sp.Kl, size_t(sp.Kl) * sp.dst_step, sp.rows, sp.Kl,
+                               sp.src_row0, sp.src_col0, sp.K_full, 1, uint64_t(sp.N_full) * sp.K_full, GEN_I8});
+            else
+                out.push_back({sp.d->w.as<uint16_t>() + size_t(sp.dst_row0) * sp.Kl, size_t(sp.Kl) * sp.dst_step, sp.rows, sp.Kl, sp.src_row0, sp.src_col0,
+                               sp.K_full, 2, uint64_t(sp.N_full) * sp.K_full, GEN_BF16});
+        } else throw error(MC_ERR_NOT_FOUND, "unknown parameter: " + name);
     } else {
         throw error(MC_ERR_NOT_FOUND, "unknown parameter: " + name);
     }
     return out;
 }
 
+unsigned gen_blocks(uint64_t n) { return unsigned(std::min<uint64_t>((n + 255) / 256, 148 * 32)); }
 void gen_bf16(mc_llama* m, const slice2d& s, uint64_t seed, uint64_t tid, float scale, float bias)
 {
-    const uint64_t n = uint64_t(s.rows) * s.cols;
-    const unsigned blocks = unsigned(std::min<uint64_t>((n + 255) / 256, 148 * 32));
-    gen_bf16_kernel<<<blocks, 256, 0, m->dev->stream>>>(static_cast<uint16_t*>(s.dst), s.dst_ld, s.rows, s.cols, s.src_row0, s.src_col0,
-                                                        s.src_K, seed, tid, scale, bias);
+    gen_bf16_kernel<<<gen_blocks(uint64_t(s.rows) * s.cols), 256, 0, m->dev->stream>>>(static_cast<uint16_t*>(s.dst), s.dst_ld, s.rows, s.cols, s.src_row0,
+                                                                                        s.src_col0, s.src_K, seed, tid, scale, bias);
+    MC_CUDA_CHECK(cudaGetLastError());
+}
+void gen_i8(mc_llama* m, const slice2d& s, uint64_t seed, uint64_t tid, int32_t lo, uint32_t range)
+{
+    gen_i8_kernel<<<gen_blocks(uint64_t(s.rows) * s.cols), 256, 0, m->dev->stream>>>(static_cast<int8_t*>(s.dst), s.dst_ld, s.rows, s.cols, s.src_row0, s.src_col0,
+                                                                                      s.src_K, seed, tid, lo, range);
+    MC_CUDA_CHECK(cudaGetLastError());
+}
+void gen_scales(mc_llama* m, const slice2d& s, uint64_t seed, uint64_t tid, float c0)
+{
+    gen_f32_scales_kernel<<<gen_blocks(uint64_t(s.rows) * s.cols), 256, 0, m->dev->stream>>>(static_cast<float*>(s.dst), s.dst_ld, s.rows, s.cols, s.src_row0,
+                                                                                              s.src_col0, s.src_K, seed, tid, c0);
     MC_CUDA_CHECK(cudaGetLastError());
 }
 
 // generator kinds shared with the test oracle (DESIGN.md "Synthetic data")
-enum : uint32_t { K_ATTN_NORM = 0, K_FFN_NORM = 1, K_WQ = 2, K_WK = 3, K_WV = 4, K_WO = 5, K_W1 = 6, K_W2 = 7, K_W3 = 8, G_TOK = 0, G_NORM = 1, G_OUT = 2 };
+enum : uint32_t { K_ATTN_NORM = 0, K_FFN_NORM = 1, K_WQ = 2, K_WK = 3, K_WV = 4, K_WO = 5, K_W1 = 6, K_W2 = 7, K_W3 = 8, K_SCALES = 16, K_LORA_A = 32,
+                  K_LORA_B = 48, G_TOK = 0, G_NORM = 1, G_OUT = 2 };
 uint64_t tid_layer(uint32_t layer, uint32_t kind) { return uint64_t(layer + 1) * 256 + kind; }
+
+size_t w4_bytes(uint32_t N, uint32_t K) { return size_t((N / 2 + 7) / 8) * (K / 64) * 512; }
+size_t w4_scale_bytes(uint32_t N, uint32_t K) { return size_t((N / 2 + 7) / 8) * (K / 64) * 64; }
+size_t w8_bytes(uint32_t N, uint32_t K) { return size_t((N / 2 + 7) / 8) * (K / 32) * 512; }
+
+gemv_params shape_only(uint32_t N, uint32_t K, uint32_t head_dim)
+{
+    gemv_params p{};
+    p.N = N, p.K = K, p.head_dim = head_dim;
+    return p;
+}
 
 } // namespace
 
@@ -590,7 +768,11 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
     MC_REQUIRE(c.dim % 256 == 0 && c.ffn_dim % 256 == 0 && (c.n_heads * c.head_dim) % 256 == 0, "dim, ffn_dim and n_heads*head_dim must be multiples of 256");
     MC_REQUIRE(c.vocab % 2 == 0, "vocab must be even");
     MC_REQUIRE(c.max_seq_len >= 1 && c.max_seq_len <= 16384, "max_seq_len out of range");
-    MC_REQUIRE(c.quant == 0, "quantised weights are not available in this build");
+    if (c.quant) {
+        MC_REQUIRE(c.group_size == 32, "quantised layout: group_size must be 32 (huggingface/llama.h:167)");
+        MC_REQUIRE(c.lora_rank >= 1 && c.lora_rank <= 64, "quantised layout: lora_rank out of range");
+        MC_REQUIRE(c.tp_world == 1, "quantised layout: tensor parallelism is not available");
+    }
     auto m = std::make_unique<mc_llama>();
     m->dev = dev;
     m->cfg = c;
@@ -598,11 +780,11 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
     m->tied = c.quant == 0;
     const uint32_t D = c.dim, hd = c.head_dim;
     m->layers.resize(c.n_layers);
-    {
+    const uint32_t QKVN = (m->Hl + 2 * m->KVl) * hd, QOl = m->Hl * hd;
+    if (!c.quant) {
         // one arena, fixed stride per layer: attn_norm | ffn_norm | wqkv | wo | w13 | w2 (256-byte aligned pieces)
         auto al = [](size_t n) { return (n + 255) & ~size_t(255); };
-        const size_t QKVN = size_t(m->Hl + 2 * m->KVl) * hd;
-        const size_t sz[6] = {al(size_t(D) * 2), al(size_t(D) * 2), al(QKVN * D * 2), al(size_t(D) * m->Hl * hd * 2),
+        const size_t sz[6] = {al(size_t(D) * 2), al(size_t(D) * 2), al(size_t(QKVN) * D * 2), al(size_t(D) * QOl * 2),
                               al(size_t(2) * m->Fl * D * 2), al(size_t(D) * m->Fl * 2)};
         m->layer_stride = sz[0] + sz[1] + sz[2] + sz[3] + sz[4] + sz[5];
         m->layer_arena.alloc(m->layer_stride * c.n_layers);
@@ -611,21 +793,53 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
             char* base = m->layer_arena.as<char>() + size_t(li) * m->layer_stride;
             ly.attn_norm.view(base, size_t(D) * 2), base += sz[0];
             ly.ffn_norm.view(base, size_t(D) * 2), base += sz[1];
-            ly.wqkv.N = uint32_t(QKVN), ly.wqkv.K = D;
-            ly.wqkv.w.view(base, QKVN * D * 2), base += sz[2];
-            ly.wo.N = D, ly.wo.K = m->Hl * hd;
-            ly.wo.w.view(base, size_t(D) * m->Hl * hd * 2), base += sz[3];
+            ly.wqkv.N = QKVN, ly.wqkv.K = D;
+            ly.wqkv.w.view(base, size_t(QKVN) * D * 2), base += sz[2];
+            ly.wo.N = D, ly.wo.K = QOl;
+            ly.wo.w.view(base, size_t(D) * QOl * 2), base += sz[3];
             ly.w13.N = 2 * m->Fl, ly.w13.K = D;
             ly.w13.w.view(base, size_t(2) * m->Fl * D * 2), base += sz[4];
             ly.w2.N = D, ly.w2.K = m->Fl;
             ly.w2.w.view(base, size_t(D) * m->Fl * 2);
         }
+        m->tok.N = c.vocab, m->tok.K = D;
+        m->tok.w.alloc(size_t(c.vocab) * D * 2);
+    } else {
+        // QLoRA layout (huggingface/llama.h:152-171): int4-range weights packed two per byte in mma fragment order +
+        // bf16 r(scale) per 32 weights + LoRA A/B in bf16; int8 per-row tables for tok_embeddings / output.
+        const uint32_t rank = c.lora_rank;
+        for (dlayer& ly : m->layers) {
+            ly.attn_norm.alloc(size_t(D) * 2), ly.ffn_norm.alloc(size_t(D) * 2);
+            ly.wqkv.N = QKVN, ly.wqkv.K = D;
+            ly.wo.N = D, ly.wo.K = QOl;
+            ly.w13.N = 2 * m->Fl, ly.w13.K = D;
+            ly.w2.N = D, ly.w2.K = m->Fl;
+            for (dlinear* d : {&ly.wqkv, &ly.wo, &ly.w13, &ly.w2}) {
+                MC_REQUIRE(d->K % 256 == 0 && d->N % 2 == 0, "quantised layout: K must be a multiple of 256");
+                d->fmt = WF_W4;
+                d->w.alloc(w4_bytes(d->N, d->K));
+                d->scales.alloc(w4_scale_bytes(d->N, d->K));
+                d->lora_b.alloc(size_t(d->N) * rank * 2);
+                d->q8.alloc(size_t(d->N) * d->K);
+                d->s32.alloc(size_t(d->N) * (d->K / 32) * 4);
+            }
+            ly.lora_a_qkv.alloc(size_t(3) * rank * D * 2), ly.lora_a_o.alloc(size_t(rank) * QOl * 2);
+            ly.lora_a_13.alloc(size_t(2) * rank * D * 2), ly.lora_a_2.alloc(size_t(rank) * m->Fl * 2);
+        }
+        m->tok.N = c.vocab, m->tok.K = D, m->tok.fmt = WF_W8ROW;
+        m->tok.w.alloc(size_t(c.vocab) * D);      // natural row-major int8: the embedding gather reads whole rows
+        m->tok.scales.alloc(size_t(c.vocab) * 4);
+        m->out.N = m->Vl, m->out.K = D, m->out.fmt = WF_W8ROW;
+        m->out.w.alloc(w8_bytes(m->Vl, D));
+        m->out.scales.alloc(size_t(m->Vl) * 4);
+        m->out.q8.alloc(size_t(m->Vl) * D);
+        m->lora_ax.alloc(size_t(std::max<uint32_t>(c.n_seqs, kMaxMB)) * 3 * rank * 2);
+        m->pack_bad.alloc(4);
+        MC_CUDA_CHECK(cudaMemset(m->pack_bad.p, 0, 4));
     }
     m->bar.alloc(256), m->errflag.alloc(256);
     MC_CUDA_CHECK(cudaMemset(m->bar.p, 0, 256));
     MC_CUDA_CHECK(cudaMemset(m->errflag.p, 0, 256));
-    m->tok.N = c.vocab, m->tok.K = D;
-    m->tok.w.alloc(size_t(c.vocab) * D * 2);
     m->norm.alloc(size_t(D) * 2);
     // rope tables on the host with the same libm calls as the scalar reference formula
     // (kernel/rope.metal:93-97: 1/pow(theta, 2j/dim), cos/sin of pos*freq), 2*max_seq rows (nn/embedding.h:171)
@@ -705,35 +919,88 @@ mc_status mc_llama_init_random(mc_llama* m, uint64_t seed)
     MC_API_BEGIN
     use(m);
     const mc_llama_config& c = m->cfg;
-    const float inv_sqrt_d = 1.0f / std::sqrt(float(c.dim));
-    const float inv_sqrt_qo = 1.0f / std::sqrt(float(c.n_heads * c.head_dim));
-    const float inv_sqrt_f = 1.0f / std::sqrt(float(c.ffn_dim));
-    auto one = [&](const std::string& name, uint64_t tid, float scale, float bias) {
+    const bool Q = c.quant != 0;
+    auto bf = [&](const std::string& name, uint64_t tid, float scale, float bias) {
         for (const slice2d& s : resolve(m, name)) gen_bf16(m, s, seed, tid, scale, bias);
+    };
+    auto i8 = [&](const std::string& name, uint64_t tid, int32_t lo, uint32_t range) {
+        for (const slice2d& s : resolve(m, name)) gen_i8(m, s, seed, tid, lo, range);
+    };
+    auto sc = [&](const std::string& name, uint64_t tid, float c0) {
+        for (const slice2d& s : resolve(m, name)) gen_scales(m, s, seed, tid, c0);
+    };
+    // one reference linear [N, K]: bf16 U/sqrt(K), or int4-range q + group scales + LoRA A/B
+    auto linear = [&](const std::string& prefix, uint64_t tid, uint32_t K) {
+        const float inv_sqrt_k = 1.0f / std::sqrt(float(K));
+        if (!Q) {
+            bf(prefix + ".weight", tid, inv_sqrt_k, 0.0f);
+        } else {
+            i8(prefix + ".weight", tid, -8, 16);
+            sc(prefix + ".scales", tid + K_SCALES, inv_sqrt_k * 0.125f);
+            bf(prefix + ".adaptor.A.weight", tid + K_LORA_A, inv_sqrt_k, 0.0f);
+            bf(prefix + ".adaptor.B.weight", tid + K_LORA_B, 1.0f / std::sqrt(float(c.lora_rank)), 0.0f);
+        }
     };
     for (uint32_t i = 0; i < c.n_layers; i++) {
         const std::string p = "layers." + std::to_string(i) + ".";
-        one(p + "attention_norm.weight", tid_layer(i, K_ATTN_NORM), 0.1f, 1.0f);
-        one(p + "ffn_norm.weight", tid_layer(i, K_FFN_NORM), 0.1f, 1.0f);
-        one(p + "attention.wq.weight", tid_layer(i, K_WQ), inv_sqrt_d, 0.0f);
-        one(p + "attention.wk.weight", tid_layer(i, K_WK), inv_sqrt_d, 0.0f);
-        one(p + "attention.wv.weight", tid_layer(i, K_WV), inv_sqrt_d, 0.0f);
-        one(p + "attention.wo.weight", tid_layer(i, K_WO), inv_sqrt_qo, 0.0f);
-        one(p + "feed_forward.w1.weight", tid_layer(i, K_W1), inv_sqrt_d, 0.0f);
-        one(p + "feed_forward.w2.weight", tid_layer(i, K_W2), inv_sqrt_f, 0.0f);
-        one(p + "feed_forward.w3.weight", tid_layer(i, K_W3), inv_sqrt_d, 0.0f);
+        bf(p + "attention_norm.weight", tid_layer(i, K_ATTN_NORM), 0.1f, 1.0f);
+        bf(p + "ffn_norm.weight", tid_layer(i, K_FFN_NORM), 0.1f, 1.0f);
+        linear(p + "attention.wq", tid_layer(i, K_WQ), c.dim);
+        linear(p + "attention.wk", tid_layer(i, K_WK), c.dim);
+        linear(p + "attention.wv", tid_layer(i, K_WV), c.dim);
+        linear(p + "attention.wo", tid_layer(i, K_WO), c.n_heads * c.head_dim);
+        linear(p + "feed_forward.w1", tid_layer(i, K_W1), c.dim);
+        linear(p + "feed_forward.w2", tid_layer(i, K_W2), c.ffn_dim);
+        linear(p + "feed_forward.w3", tid_layer(i, K_W3), c.dim);
     }
-    one("norm.weight", G_NORM, 0.1f, 1.0f);
-    one("tok_embeddings.weight", G_TOK, 0.0625f, 0.0f);
+    bf("norm.weight", G_NORM, 0.1f, 1.0f);
+    if (!Q) {
+        bf("tok_embeddings.weight", G_TOK, 0.0625f, 0.0f);
+    } else {
+        i8("tok_embeddings.weight", G_TOK, -127, 255);
+        sc("tok_embeddings.scales", G_TOK + K_SCALES, 0.0625f / 127.0f);
+        i8("output.weight", G_OUT, -127, 255);
+        sc("output.scales", G_OUT + K_SCALES, (1.0f / std::sqrt(float(c.dim))) / 127.0f);
+    }
     MC_CUDA_CHECK(cudaStreamSynchronize(m->dev->stream));
     m->finalized = false;
     MC_API_END
 }
 
+// Packs the staged reference-layout tensors into the streaming layouts (bit-exact, see mc_unpack_w4) and frees the staging.
 mc_status mc_llama_finalize(mc_llama* m)
 {
     MC_API_BEGIN
     use(m);
+    if (m->cfg.quant && !m->finalized) {
+        cudaStream_t s = m->dev->stream;
+        auto pack = [&](dlinear& d, int epi) {
+            if (!d.q8.p) return; // already packed
+            const gemv_params sh = shape_only(d.N, d.K, m->cfg.head_dim);
+            const uint64_t words = uint64_t(d.w.bytes / 4);
+            pack_w4_kernel<<<gen_blocks(words), 256, 0, s>>>(d.w.as<uint32_t>(), d.q8.as<int8_t>(), sh, epi, m->pack_bad.as<int>());
+            pack_w4_scales_kernel<<<gen_blocks(d.scales.bytes / 2), 256, 0, s>>>(d.scales.as<uint16_t>(), d.s32.as<float>(), sh, epi);
+            MC_CUDA_CHECK(cudaGetLastError());
+        };
+        for (dlayer& ly : m->layers) {
+            pack(ly.wqkv, EPI_QKV), pack(ly.wo, EPI_RESIDUAL), pack(ly.w13, EPI_SWIGLU), pack(ly.w2, EPI_RESIDUAL);
+        }
+        if (m->out.q8.p) {
+            pack_w8_kernel<<<gen_blocks(m->out.w.bytes / 4), 256, 0, s>>>(m->out.w.as<uint32_t>(), m->out.q8.as<int8_t>(), shape_only(m->out.N, m->out.K, 0),
+                                                                           EPI_NONE);
+            MC_CUDA_CHECK(cudaGetLastError());
+        }
+        int bad = 0;
+        MC_CUDA_CHECK(cudaMemcpyAsync(&bad, m->pack_bad.p, 4, cudaMemcpyDeviceToHost, s));
+        MC_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (bad) {
+            MC_CUDA_CHECK(cudaMemset(m->pack_bad.p, 0, 4));
+            throw error(MC_ERR_INVALID, "quantised weights outside the int4 range [-8, 7] cannot be packed (quantization/lora.h stores int4-range values in int8)");
+        }
+        for (dlayer& ly : m->layers)
+            for (dlinear* d : {&ly.wqkv, &ly.wo, &ly.w13, &ly.w2}) d->q8.release(), d->s32.release();
+        m->out.q8.release();
+    }
     m->finalized = true;
     MC_API_END
 }
@@ -749,6 +1016,7 @@ mc_status mc_llama_weight_bytes(mc_llama* m, uint64_t* streamed_per_step, uint64
     }
     const dlinear& hw = m->tied ? m->tok : m->out;
     stream += size_t(m->Vl) * m->cfg.dim * (hw.fmt == WF_BF16 ? 2 : 1) + hw.scales.bytes + m->norm.bytes;
+    stream += size_t(m->cfg.dim) * (m->tok.fmt == WF_BF16 ? 2 : 1); // one embedding row
     res = stream + m->kcache.bytes + m->vcache.bytes;
     if (!m->tied) res += m->tok.stream_bytes();
     else res += m->tok.w.bytes - size_t(m->Vl) * m->cfg.dim * 2;
@@ -999,11 +1267,76 @@ mc_status mc_linear_bf16(mc_device* dev, mc_buffer* y, mc_buffer* x, mc_buffer* 
     MC_API_END
 }
 
-mc_status mc_linear_w4(mc_device*, mc_buffer*, mc_buffer*, mc_buffer*, mc_buffer*, uint32_t, uint32_t, uint32_t)
+mc_status mc_pack_w4(mc_device* dev, mc_buffer* w4, mc_buffer* scales_packed, mc_buffer* q8, mc_buffer* scales_f32, uint32_t N, uint32_t K)
 {
-    return fail(MC_ERR_RUNTIME, "linear_w4 is not available in this build");
+    MC_API_BEGIN
+    MC_REQUIRE(dev && w4 && q8, "bad arguments");
+    MC_CUDA_CHECK(cudaSetDevice(dev->ordinal));
+    MC_REQUIRE(N % 2 == 0 && K % 256 == 0, "pack_w4: N must be even and K a multiple of 256");
+    MC_REQUIRE(q8->size >= size_t(N) * K && w4->size >= w4_bytes(N, K), "pack_w4: buffer too small");
+    int* bad = nullptr;
+    MC_CUDA_CHECK(cudaMalloc(&bad, 4));
+    MC_CUDA_CHECK(cudaMemsetAsync(bad, 0, 4, dev->stream));
+    const gemv_params sh = shape_only(N, K, 0);
+    pack_w4_kernel<<<gen_blocks(w4_bytes(N, K) / 4), 256, 0, dev->stream>>>(static_cast<uint32_t*>(w4->dptr), static_cast<const int8_t*>(q8->dptr), sh, EPI_NONE, bad);
+    if (scales_packed && scales_f32) {
+        MC_REQUIRE(scales_f32->size >= size_t(N) * (K / 32) * 4 && scales_packed->size >= w4_scale_bytes(N, K), "pack_w4: scale buffer too small");
+        pack_w4_scales_kernel<<<gen_blocks(w4_scale_bytes(N, K) / 2), 256, 0, dev->stream>>>(static_cast<uint16_t*>(scales_packed->dptr),
+                                                                                             static_cast<const float*>(scales_f32->dptr), sh, EPI_NONE);
+    }
+    int h = 0;
+    cudaError_t e = cudaMemcpyAsync(&h, bad, 4, cudaMemcpyDeviceToHost, dev->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(dev->stream);
+    cudaFree(bad);
+    MC_CUDA_CHECK(e);
+    MC_CUDA_CHECK(cudaGetLastError());
+    if (h) throw error(MC_ERR_INVALID, "pack_w4: weight outside the int4 range [-8, 7]");
+    dev->launches.fetch_add(2);
+    MC_API_END
 }
-mc_status mc_pack_w4(mc_device*, mc_buffer*, mc_buffer*, uint32_t, uint32_t) { return fail(MC_ERR_RUNTIME, "pack_w4 is not available in this build"); }
-mc_status mc_unpack_w4(mc_device*, mc_buffer*, mc_buffer*, uint32_t, uint32_t) { return fail(MC_ERR_RUNTIME, "unpack_w4 is not available in this build"); }
+
+mc_status mc_unpack_w4(mc_device* dev, mc_buffer* q8, mc_buffer* w4, uint32_t N, uint32_t K)
+{
+    MC_API_BEGIN
+    MC_REQUIRE(dev && w4 && q8, "bad arguments");
+    MC_CUDA_CHECK(cudaSetDevice(dev->ordinal));
+    MC_REQUIRE(N % 2 == 0 && K % 256 == 0, "unpack_w4: N must be even and K a multiple of 256");
+    MC_REQUIRE(q8->size >= size_t(N) * K && w4->size >= w4_bytes(N, K), "unpack_w4: buffer too small");
+    unpack_w4_kernel<<<gen_blocks(w4_bytes(N, K) / 4), 256, 0, dev->stream>>>(static_cast<int8_t*>(q8->dptr), static_cast<const uint32_t*>(w4->dptr),
+                                                                               shape_only(N, K, 0), EPI_NONE);
+    MC_CUDA_CHECK(cudaGetLastError());
+    dev->launches.fetch_add(1);
+    MC_API_END
+}
+
+mc_status mc_w4_sizes(uint32_t N, uint32_t K, size_t* w4_nbytes, size_t* scales_nbytes)
+{
+    MC_API_BEGIN
+    MC_REQUIRE(N % 2 == 0 && K % 256 == 0, "w4_sizes: N must be even and K a multiple of 256");
+    if (w4_nbytes) *w4_nbytes = w4_bytes(N, K);
+    if (scales_nbytes) *scales_nbytes = w4_scale_bytes(N, K);
+    MC_API_END
+}
+
+mc_status mc_linear_w4(mc_device* dev, mc_buffer* y, mc_buffer* x, mc_buffer* w4, mc_buffer* scales_packed, uint32_t M, uint32_t N, uint32_t K)
+{
+    MC_API_BEGIN
+    MC_REQUIRE(dev && y && x && w4 && scales_packed, "bad arguments");
+    MC_CUDA_CHECK(cudaSetDevice(dev->ordinal));
+    MC_REQUIRE(M >= 1 && M <= uint32_t(kQMaxMB), "linear_w4: M must be in [1,8] for the streaming GEMV path");
+    MC_REQUIRE(N % 2 == 0 && K % 256 == 0, "linear_w4: N must be even and K a multiple of 256");
+    MC_REQUIRE(w4->size >= w4_bytes(N, K) && scales_packed->size >= w4_scale_bytes(N, K) && x->size >= size_t(M) * K * 2 && y->size >= size_t(M) * N * 2,
+               "linear_w4: buffer too small");
+    mc_llama shim;
+    shim.dev = dev;
+    launcher L{&shim, dev->stream, false};
+    qgemv_params q{};
+    q.g.W = w4->dptr, q.g.N = N, q.g.K = K, q.g.rows = M;
+    q.g.x = static_cast<const uint16_t*>(x->dptr), q.g.ldx = K;
+    q.g.y = static_cast<uint16_t*>(y->dptr), q.g.ldy = N;
+    q.scales = scales_packed->dptr;
+    qgemv_launch<WF_W4, PRO_NONE, EPI_NONE>(L, q);
+    MC_API_END
+}
 
 } // extern "C"

@@ -187,3 +187,107 @@ def test_config2_full_1b_greedy_tokens_match_golden():
     toks, ms = m.decode_loop([first], [g["prompt_len"]], g["steps"] - 1)
     got = [first] + toks[:, 0].tolist()
     assert got == g["tokens"], (got, g["tokens"], g["top2_gap_ulps"])
+
+
+# ---- quantised (QLoRA layout) path: BASELINE.json configs[2] -----------------------------------------------------------
+QNAMES = [f"{l}.{s}" for l in ("attention.wq", "attention.wk", "attention.wv", "attention.wo", "feed_forward.w1", "feed_forward.w2", "feed_forward.w3")
+          for s in ("weight", "scales", "adaptor.A.weight", "adaptor.B.weight")]
+QDT = {"weight": np.int8, "scales": np.float32, "adaptor.A.weight": np.uint16, "adaptor.B.weight": np.uint16}
+
+
+def make_qengine(cfgd, seed=0x5EED, n_seqs=1, from_oracle=None):
+    from metalchat_b200 import capi
+
+    gpu = accelerator()
+    m = capi.Llama(gpu.dev, capi.llama_config(**cfgd, quant=1, n_seqs=n_seqs))
+    if from_oracle is None:
+        m.init_random(seed)
+    else:
+        o = from_oracle
+        for i in range(cfgd["n_layers"]):
+            for n in QNAMES:
+                name = f"layers.{i}.{n}"
+                m.set_tensor(name, o.tensor(name, QDT[n.split(".", 2)[2]]))
+            for n in ("attention_norm.weight", "ffn_norm.weight"):
+                m.set_tensor(f"layers.{i}.{n}", o.tensor(f"layers.{i}.{n}", np.uint16))
+        m.set_tensor("norm.weight", o.tensor("norm.weight", np.uint16))
+        for t in ("tok_embeddings", "output"):
+            m.set_tensor(t + ".weight", o.tensor(t + ".weight", np.int8))
+            m.set_tensor(t + ".scales", o.tensor(t + ".scales", np.float32))
+    m.finalize()
+    return m
+
+
+def test_w4_pack_roundtrip_and_linear(rng):
+    # int4 unpack must be bit-exact; the base linear r(x . r(r(q) r(s))^T) against the oracle's dequant + bmm
+    from metalchat_b200 import capi
+
+    gpu = accelerator()
+    for (N, K, M) in [(64, 256, 1), (512, 2048, 3), (2048, 8192, 8), (34, 512, 2)]:
+        q = rng.integers(-8, 8, size=(N, K), dtype=np.int8)
+        s = (rng.random((N, K // 32), dtype=np.float32) + 0.5) * 0.01
+        w4, sp = capi.pack_w4(gpu.dev, q, s)
+        assert np.array_equal(capi.unpack_w4(gpu.dev, w4, N, K), q)
+        x = orc.f32_to_bf16(rng.standard_normal((M, K)).astype(np.float32))
+        dx, dy = gpu.dev.upload(x), gpu.dev.alloc(M * N * 2)
+        capi.linear_w4(gpu.dev, dy, dx, w4, sp, M, N, K)
+        got = dy.read(np.uint16).reshape(M, N)
+        # oracle: hadamard_broadcast (group rows of 32) then bmm through the transposed view
+        wd = np.zeros((N * (K // 32), 32), np.uint16)
+        orc.hadamard_broadcast(BF16, F32, wd, q.reshape(-1, 32), s.reshape(-1))
+        want = np.zeros((1, M, N), np.uint16)
+        orc.bmm(BF16, want, x.reshape(1, M, K), wd.reshape(1, N, K).transpose(0, 2, 1))
+        # fp32 accumulation order differs (tensor-core k-blocks vs ascending k): almost every output is bit-identical,
+        # the rest within one bf16 ulp of the largest output (near-zero sums can be many of their own ulps apart)
+        exact = np.mean(got == want[0])
+        err = np.abs(unbf(got) - unbf(want[0])).max() / np.abs(unbf(want[0])).max()
+        assert exact > 0.98 and err < 2.0 ** -8, (N, K, M, exact, err)
+    with pytest.raises(capi.McInvalidArgument, match="int4 range"):
+        capi.pack_w4(gpu.dev, np.full((16, 256), 9, np.int8), np.ones((16, 8), np.float32))
+
+
+def test_quant_engine_matches_oracle():
+    cfgd = SMALL
+    o = orc.Llama(orc.make_cfg(**cfgd, quant=1), BF16)
+    o.init_random(0x5EED)
+    of = orc.Llama(orc.make_cfg(**cfgd, quant=1), F32)
+    of.init_random(0x5EED)
+    a = make_qengine(cfgd)
+    b = make_qengine(cfgd, from_oracle=o)
+    ids = [3, 77, 512, 999, 0, 41, 41, 7, 1500, 2]
+    a.prefill(ids)
+    b.prefill(ids)
+    assert np.array_equal(a.logits(), b.logits())  # device generator == oracle generator, both load paths
+    want_logits, want_hidden = o.forward(ids, 0, want_hidden=True)
+    f32_logits, f32_hidden = of.forward(ids, 0, want_hidden=True)
+    # north_star tolerance is 1e-2 max-rel PER LAYER vs the fp32 oracle (whose weights are not rounded to bf16)
+    assert max_rel(unbf(a.hidden()), f32_hidden[-1]) < 1e-2 * cfgd["n_layers"]
+    assert max_rel(unbf(a.logits()), f32_logits) < 1e-2 * cfgd["n_layers"]
+    assert max_rel(unbf(a.hidden()), unbf(want_hidden[-1])) < 1e-2
+    assert max_rel(unbf(a.logits()), unbf(want_logits)) < 1e-2
+    assert np.mean(a.hidden() == want_hidden[-1]) > 0.9
+    first = orc.argmax(BF16, want_logits)
+    assert int(np.argmax(unbf(a.logits()))) == first
+    steps = 24
+    toks, _ = a.decode_loop([first], [len(ids)], steps)
+    want, tok, pos = [], first, len(ids)
+    for _ in range(steps):
+        tok = orc.argmax(BF16, o.forward([tok], pos))
+        want.append(tok)
+        pos += 1
+    assert toks[:, 0].tolist() == want
+
+
+def test_config3_full_1b_quant_greedy_tokens_match_golden():
+    path = GOLDEN / "llama1b_L16_q1_p512_s64.json"
+    if not path.exists():
+        pytest.skip("golden fixture not generated")
+    g = json.loads(path.read_text())
+    cfgd = dict(dim=2048, n_layers=16, n_heads=32, n_kv_heads=8, head_dim=64, ffn_dim=8192, vocab=128256, max_seq_len=1024)
+    m = make_qengine(cfgd)
+    ids = [int(orc.lib().orc_hash_int(0x5EED, 0xFFFF, i, 0, cfgd["vocab"])) for i in range(g["prompt_len"])]
+    m.prefill(ids)
+    first = int(np.lexsort((np.arange(cfgd["vocab"]), -unbf(m.logits())))[0])
+    toks, ms = m.decode_loop([first], [g["prompt_len"]], g["steps"] - 1)
+    got = [first] + toks[:, 0].tolist()
+    assert got == g["tokens"], (got, g["tokens"], g["top2_gap_ulps"])
