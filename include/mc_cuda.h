@@ -173,8 +173,21 @@ MC_API mc_status mc_llama_logits(mc_llama* m, uint32_t seq, void* host_bf16, siz
 MC_API mc_status mc_llama_hidden(mc_llama* m, uint32_t seq, void* host_bf16, size_t nbytes);
 MC_API mc_status mc_llama_cache(mc_llama* m, uint32_t seq, uint32_t layer, int which, uint32_t n_pos, void* host_bf16, size_t nbytes);
 MC_API mc_status mc_llama_launches_per_step(mc_llama* m, uint32_t* kernels);
+/* Tensor parallelism (no reference counterpart: the reference is single-device, nn/llama.h:86).  One process per GPU;
+ * every rank creates the model with (tp_rank, tp_world), exports a 64-byte IPC handle of its exchange region, the host
+ * gathers all handles (torch.distributed / MPI / files) and hands the world x 64 bytes to every rank.  The all-reduce
+ * after wo and w2 is fused into the GEMV kernels over NVLink peer memory (DESIGN.md "Multi-GPU"). */
+MC_API mc_status mc_llama_tp_export(mc_llama* m, void* handle, size_t cap);
+MC_API mc_status mc_llama_tp_connect(mc_llama* m, const void* handles, size_t nbytes);
 /* Diagnostics: one ungraphed decode step with a CUDA event before every launch; us[i] = device time of launch i. */
 MC_API mc_status mc_llama_profile_step(mc_llama* m, uint32_t n, float* us, uint32_t cap, uint32_t* count);
+
+/* The default sampler chain (make_default_sampler, nn/sampling.h:306-316: top-k -> nucleus -> multinomial) over
+ * logits [rows, vocab] bf16 on the device, with injected uniforms[rows]; host outputs (any may be NULL):
+ * topk_idx[rows,k], probs_sorted[rows,k] (bf16 bits after the top-p mask), probs_idx[rows,k], choice[rows], token[rows]. */
+MC_API mc_status mc_sample_default(mc_device* dev, mc_buffer* logits_bf16, uint32_t rows, uint32_t vocab, const mc_sampler_config* cfg,
+                                   const float* uniforms, int32_t* topk_idx, uint16_t* probs_sorted, int32_t* probs_idx, int32_t* choice,
+                                   int32_t* token);
 
 /* ---- stand-alone hot kernels (for roofline measurement and parity tests) -----------
  * y[M,N] = x[M,K] * W[N,K]^T with fp32 accumulation and one RNE rounding to bf16

@@ -118,7 +118,11 @@ _SIGNATURES = {
     "mc_llama_hidden": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
     "mc_llama_cache": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_size_t]),
     "mc_llama_launches_per_step": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
+    "mc_llama_tp_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "mc_llama_tp_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "mc_llama_profile_step": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "mc_sample_default": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(SamplerConfig), C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "mc_linear_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "mc_linear_w4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "mc_pack_w4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
@@ -396,6 +400,15 @@ class Llama:
         check(lib().mc_llama_profile_step(self.h, n, _vp(us), len(us), C.byref(cnt)))
         return us[: cnt.value]
 
+    def tp_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(lib().mc_llama_tp_export(self.h, buf, 64))
+        return buf.raw
+
+    def tp_connect(self, handles: list[bytes]):
+        blob = b"".join(handles)
+        check(lib().mc_llama_tp_connect(self.h, blob, len(blob)))
+
     def launches_per_step(self) -> int:
         n = C.c_uint32()
         check(lib().mc_llama_launches_per_step(self.h, C.byref(n)))
@@ -441,3 +454,19 @@ def unpack_w4(dev: Device, w4: Buffer, N: int, K: int) -> np.ndarray:
 
 def linear_w4(dev: Device, y: Buffer, x: Buffer, w4: Buffer, sp: Buffer, M: int, N: int, K: int):
     check(lib().mc_linear_w4(dev.h, y.h, x.h, w4.h, sp.h, M, N, K))
+
+
+def sample_default(dev: Device, logits_bf16: np.ndarray, uniforms, top_k=50, temperature=0.6, top_p=0.9, intended=0):
+    """make_default_sampler on the device; logits_bf16 is [rows, vocab] uint16."""
+    logits_bf16 = np.ascontiguousarray(logits_bf16, np.uint16)
+    rows, vocab = logits_bf16.shape
+    buf = dev.upload(logits_bf16)
+    cfg = SamplerConfig(1, top_k, temperature, top_p, intended)
+    u = np.ascontiguousarray(uniforms, np.float32)
+    k = min(top_k, vocab)
+    topk = np.zeros((rows, k), np.int32)
+    ps = np.zeros((rows, k), np.uint16)
+    pi = np.zeros((rows, k), np.int32)
+    ch, tok = np.zeros(rows, np.int32), np.zeros(rows, np.int32)
+    check(lib().mc_sample_default(dev.h, buf.h, rows, vocab, C.byref(cfg), _vp(u), _vp(topk), _vp(ps), _vp(pi), _vp(ch), _vp(tok)))
+    return dict(topk_idx=topk, probs_sorted=ps, probs_idx=pi, choice=ch, token=tok)

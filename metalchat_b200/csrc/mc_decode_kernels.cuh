@@ -23,7 +23,7 @@ constexpr int kGemvWarps = kGemvThreads / 32;
 constexpr int kMaxMB = 4; // activation rows handled by one GEMV pass
 
 enum { PRO_NONE = 0, PRO_RMSNORM = 1 };
-enum { EPI_NONE = 0, EPI_QKV = 1, EPI_RESIDUAL = 2, EPI_SWIGLU = 3 };
+enum { EPI_NONE = 0, EPI_QKV = 1, EPI_RESIDUAL = 2, EPI_SWIGLU = 3, EPI_PARTIAL_TP = 4 };
 enum { WF_BF16 = 0, WF_W4 = 1, WF_W8ROW = 2, WF_W8G = 3 };
 
 // ---- small device helpers ---------------------------------------------------------------------------
@@ -60,6 +60,67 @@ __device__ __forceinline__ float silu_bf16(float g)
     const float e = rbf(expf(-g));
     const float d = rbf(__fadd_rn(1.0f, e));
     return rbf(__fdiv_rn(g, d));
+}
+
+// ---- TP exchange: all-reduce fused into the producing GEMV and the consuming GEMV -----------------------------------
+// Row-parallel linears (wo, w2) end in an all-reduce of `rows x dim` partial sums.  Instead of a
+// collective call between kernels, the PRODUCER GEMV's epilogue pushes its fp32 partials straight into every peer's
+// exchange buffer over NVLink (P2P stores), the last CTA to finish publishes an epoch flag to all peers, and the
+// CONSUMER GEMV's prologue waits for the flags and sums the `world` partials from LOCAL memory in rank order, adds the
+// residual and rounds once:  h = r(x + r(sum_k partial_k)).  Buffers are double-buffered by epoch parity.
+constexpr int kTpMaxWorld = 8;
+struct tp_exchange {
+    uint32_t world, rank;
+    uint32_t rows_max, dim;            // buffer geometry: buf[parity][src_rank][rows_max][dim] fp32
+    float* peer_buf[kTpMaxWorld];      // exchange buffer of every rank (this rank's own included), mapped on this GPU
+    uint32_t* peer_flag[kTpMaxWorld];  // flags[src_rank] of every rank
+    unsigned* done;                    // local: CTAs of the producer that have finished
+    unsigned* epoch;                   // local: exchanges published so far
+    int* err;                          // local: set when a flag wait times out
+};
+__device__ __forceinline__ float* tp_slot(const tp_exchange& t, float* buf, uint32_t parity, uint32_t src)
+{
+    return buf + (size_t(parity) * t.world + src) * t.rows_max * t.dim;
+}
+// producer side, after the epilogue stores: the last CTA publishes the new epoch to every peer
+__device__ __forceinline__ void tp_publish(const tp_exchange& t)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned prev = atomicAdd(t.done, 1u);
+        if (prev == gridDim.x - 1) {
+            *t.done = 0;
+            const unsigned e = *t.epoch + 1;
+            *t.epoch = e;
+            __threadfence_system();
+            for (uint32_t k = 0; k < t.world; k++) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(t.peer_flag[k] + t.rank), "r"(e) : "memory");
+        }
+    }
+}
+// consumer side: wait until every rank has published epoch e; returns e (0 on timeout)
+__device__ __forceinline__ unsigned tp_wait(const tp_exchange& t, unsigned* smem_word)
+{
+    if (threadIdx.x == 0) {
+        const unsigned e = *reinterpret_cast<volatile unsigned*>(t.epoch);
+        unsigned ok = e;
+        for (uint32_t k = 0; k < t.world; k++) {
+            unsigned v = 0;
+            unsigned long long spins = 0;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(t.peer_flag[t.rank] + k) : "memory");
+                if (v >= e) break;
+                if (++spins > (1ull << 23)) {
+                    atomicExch(t.err, 2);
+                    ok = 0;
+                    break;
+                }
+            }
+        }
+        *smem_word = ok;
+    }
+    __syncthreads();
+    return *smem_word;
 }
 
 struct gemv_params {
@@ -99,6 +160,11 @@ struct gemv_params {
     // megakernel only: greedy argmax fused into the vocab projection; per-CTA partials [rows][gridDim.x]
     float* am_val;
     int32_t* am_idx;
+    // tensor parallelism (see "TP exchange" below); tp.world == 0 when unused
+    tp_exchange tp;
+    int32_t tp_reduce;         // prologue: build the input rows from the peers' partial sums (+ residual)
+    const uint16_t* tp_res;    // [rows, ldx] residual added to the reduced sum
+    uint16_t* tp_out;          // [rows, ldx] where CTA 0 stores the reduced rows (the next residual)
 };
 
 // ---- grid-wide phase barrier of the persistent decode kernel ---------------------------------------------------
@@ -251,12 +317,32 @@ __device__ __forceinline__ void gemv_body(const gemv_params& p, unsigned char* s
         pdl_wait();
     }
 
+    // -- tensor-parallel input: h = r(res + r(sum over ranks of the pushed fp32 partials)), summed in rank order
+    const uint16_t* x_in = p.x;
+    if (p.tp_reduce) {
+        const unsigned e = tp_wait(p.tp, reinterpret_cast<unsigned*>(sscr));
+        const uint32_t parity = (e - 1) & 1u;
+        const float* mine = p.tp.peer_buf[p.tp.rank];
+        for (uint32_t m = 0; m < p.rows; m++) {
+            for (uint32_t k = threadIdx.x; k < p.K; k += kGemvThreads) {
+                float sum = 0.0f;
+                for (uint32_t src = 0; src < p.tp.world; src++)
+                    sum += tp_slot(p.tp, const_cast<float*>(mine), parity, src)[size_t(m) * p.tp.dim + k];
+                const uint16_t h = f32_to_bf16_bits(__fadd_rn(bf16_bits_to_f32(p.tp_res[size_t(m) * p.ldx + k]), rbf(sum)));
+                sx[size_t(m) * p.K + k] = h;
+                if (blockIdx.x == 0) p.tp_out[size_t(m) * p.ldx + k] = h;
+            }
+        }
+        __syncthreads();
+        x_in = nullptr; // the rows are already staged in shared memory
+    }
+
     // -- prologue: stage the activation rows in shared memory as bf16
     if (PRO == PRO_RMSNORM) {
         // n = r((0 + w) * x * rsqrt(mean(x^2) + eps))  (kernel/rmsnorm.metal:53-89)
         for (int m = 0; m < MB; m++) {
             if (uint32_t(m) < p.rows) {
-                const uint16_t* xr = p.x + size_t(m) * p.ldx;
+                const uint16_t* xr = x_in ? x_in + size_t(m) * p.ldx : sx + size_t(m) * p.K;
                 if (MEGA && adj.embed) {
                     // embedding gather fused into the first phase (kernel/embedding.metal:38-66)
                     xr = p.embed_table + size_t(p.embed_ids[m]) * p.K;
@@ -296,10 +382,10 @@ __device__ __forceinline__ void gemv_body(const gemv_params& p, unsigned char* s
                 }
             }
         }
-    } else {
+    } else if (x_in) {
         for (int m = 0; m < MB; m++) {
             if (uint32_t(m) < p.rows) {
-                const uint16_t* xr = p.x + size_t(m) * p.ldx;
+                const uint16_t* xr = x_in + size_t(m) * p.ldx;
                 for (uint32_t k = threadIdx.x * 8; k < p.K; k += kGemvThreads * 8)
                     *reinterpret_cast<uint4*>(sx + size_t(m) * p.K + k) = *reinterpret_cast<const uint4*>(xr + k);
             }
@@ -309,6 +395,8 @@ __device__ __forceinline__ void gemv_body(const gemv_params& p, unsigned char* s
     const bool fin = ks == 0 && lane < p.rows && lane < uint32_t(MB); // this lane finalises activation row `lane`
     int32_t my_pos = 0, my_seq = 0;
     if (EPI == EPI_QKV && fin) my_pos = p.row_pos[lane], my_seq = p.row_seq[lane];
+    uint32_t tp_parity = 0;
+    if (EPI == EPI_PARTIAL_TP) tp_parity = *reinterpret_cast<volatile unsigned*>(p.tp.epoch) & 1u; // the epoch this launch will publish is +1
     float best_v = -INFINITY; // fused greedy argmax (lowest index on ties)
     int32_t best_i = 0x7fffffff;
     __syncthreads();
@@ -422,7 +510,15 @@ __device__ __forceinline__ void gemv_body(const gemv_params& p, unsigned char* s
                 y0 = rbf(__fadd_rn(y0, rbf(__fmul_rn(rbf(l0), p.lora_scale))));
                 y1 = rbf(__fadd_rn(y1, rbf(__fmul_rn(rbf(l1), p.lora_scale))));
             }
-            if (EPI == EPI_NONE) {
+            if (EPI == EPI_PARTIAL_TP) {
+                // unrounded fp32 partial sums go to every rank's exchange buffer (P2P stores over NVLink)
+                const uint32_t parity = tp_parity;
+                for (uint32_t k = 0; k < p.tp.world; k++) {
+                    float* dst = tp_slot(p.tp, p.tp.peer_buf[k], parity, p.tp.rank) + size_t(m) * p.tp.dim;
+                    dst[r0] = a;
+                    dst[r1] = b;
+                }
+            } else if (EPI == EPI_NONE) {
                 p.y[size_t(m) * p.ldy + r0] = f32_to_bf16_bits(y0);
                 p.y[size_t(m) * p.ldy + r1] = f32_to_bf16_bits(y1);
                 if (MEGA) {
@@ -484,6 +580,7 @@ __device__ __forceinline__ void gemv_body(const gemv_params& p, unsigned char* s
             p.am_idx[threadIdx.x * gridDim.x + blockIdx.x] = bi;
         }
     }
+    if (EPI == EPI_PARTIAL_TP) tp_publish(p.tp);
     if (MEGA) {
         stamp(sy.timing, 2);
         grid_arrive(sy.bar);
@@ -856,6 +953,85 @@ __global__ void argmax_final_kernel(const float* pval, const int32_t* pidx, int 
     }
     __syncthreads();
     if (row == 0) *step_counter = step + 1;
+}
+
+// Vocabulary-sharded head: every rank pushes its local (value, global index) winner to all peers, waits for the
+// others and picks the global winner in rank order (lowest index on ties) — all ranks arrive at the same token.
+struct am_exchange {
+    uint32_t world, rank, rows_max;
+    float* peer_val[kTpMaxWorld];      // [parity][src_rank][rows_max]
+    int32_t* peer_idx[kTpMaxWorld];
+    uint32_t* peer_flag[kTpMaxWorld];  // flags[src_rank]
+    unsigned* epoch;                   // local
+    int* err;
+};
+__global__ void argmax_final_tp_kernel(const float* pval, const int32_t* pidx, int nblk, int32_t index_base, am_exchange x, int32_t* ids, int32_t* pos,
+                                       int32_t* out_log, int32_t* step_counter, uint32_t rows, int advance)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ unsigned ok;
+    const uint32_t row = threadIdx.x;
+    const unsigned e = *x.epoch + 1;
+    const uint32_t parity = e & 1u;
+    if (row < rows) {
+        float bv = -INFINITY;
+        int32_t bi = 0x7fffffff;
+        for (int b = 0; b < nblk; b++) {
+            const float v = pval[row * nblk + b];
+            const int32_t i = pidx[row * nblk + b];
+            if (v > bv || (v == bv && i < bi)) bv = v, bi = i;
+        }
+        if (bi != 0x7fffffff) bi += index_base;
+        for (uint32_t k = 0; k < x.world; k++) {
+            const size_t o = (size_t(parity) * x.world + x.rank) * x.rows_max + row;
+            x.peer_val[k][o] = bv;
+            x.peer_idx[k][o] = bi;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        for (uint32_t k = 0; k < x.world; k++) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(x.peer_flag[k] + x.rank), "r"(e) : "memory");
+        unsigned good = 1;
+        for (uint32_t k = 0; k < x.world; k++) {
+            unsigned v = 0;
+            unsigned long long spins = 0;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(x.peer_flag[x.rank] + k) : "memory");
+                if (v >= e) break;
+                if (++spins > (1ull << 23)) {
+                    atomicExch(x.err, 3);
+                    good = 0;
+                    break;
+                }
+            }
+        }
+        ok = good;
+        *x.epoch = e;
+    }
+    __syncthreads();
+    if (row < rows) {
+        float bv = -INFINITY;
+        int32_t bi = 0x7fffffff;
+        if (ok) {
+            for (uint32_t k = 0; k < x.world; k++) {
+                const size_t o = (size_t(parity) * x.world + k) * x.rows_max + row;
+                const float v = x.peer_val[x.rank][o];
+                const int32_t i = x.peer_idx[x.rank][o];
+                if (v > bv || (v == bv && i < bi)) bv = v, bi = i;
+            }
+        }
+        if (bi == 0x7fffffff) bi = 0;
+        const int32_t step = *step_counter;
+        out_log[size_t(step) * rows + row] = bi;
+        if (advance) {
+            ids[row] = bi;
+            pos[row] += 1;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *step_counter += 1;
 }
 
 // ---- synthetic weights (DESIGN.md "Synthetic data"; same hash as the test oracle) ----------------------------------

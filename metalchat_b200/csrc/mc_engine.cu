@@ -15,6 +15,7 @@
 //   KV cache    [layer][seq][KVl][max_seq][hd] bf16 — one contiguous stream per (seq, kv head)
 //   rope tables fcos/fsin [2*max_seq, hd/2] fp32 (nn/embedding.h:160-176)
 #include "mc_quant_kernels.cuh"
+#include "mc_sample_kernels.cuh"
 
 #include <cmath>
 #include <map>
@@ -85,6 +86,11 @@ struct mc_llama {
     dbuf layer_arena;          // all per-layer weights, one fixed stride per layer (the megakernel indexes by layer)
     size_t layer_stride = 0;
     dbuf bar, errflag;         // grid barrier counter / timeout flag of the megakernel
+    // tensor parallelism: one exchange region per rank (partials | flags | argmax values | argmax flags), IPC-mapped on the peers
+    dbuf tp_region, tp_local;  // tp_local: done counter, epoch, argmax epoch
+    void* tp_peer_base[kTpMaxWorld] = {};
+    bool tp_connected = false;
+    size_t tp_off_flags = 0, tp_off_amval = 0, tp_off_amidx = 0, tp_off_amflags = 0;
     dbuf mega_timing;          // diagnostics: per-phase globaltimer stamps (allocated on demand)
     bool mega_timing_on = false;
     int mega_ctas_per_sm[3] = {0, 0, 0};
@@ -94,8 +100,8 @@ struct mc_llama {
     dbuf kcache, vcache;
     // activations
     uint32_t max_rows = 0;
-    dbuf x, h, q, attn, z, logits, hidden_save;
-    dbuf ids, pos, row_seq, uniforms, out_log, step_counter, pval, pidx, lora_ax, pack_bad;
+    dbuf x, h, q, attn, z, logits, logits_tmp, hidden_save;
+    dbuf ids, pos, row_seq, uniforms, out_log, step_counter, pval, pidx, lora_ax, pack_bad, cand;
     int32_t* pinned = nullptr; // host staging: ids | pos | out
     float scale_bf16 = 0.0f;
     std::map<uint64_t, cudaGraphExec_t> graphs;
@@ -111,8 +117,10 @@ struct mc_llama {
             for (dlinear* d : {&l.wqkv, &l.wo, &l.w13, &l.w2}) d->w.release(), d->scales.release(), d->lora_b.release(), d->q8.release(), d->s32.release();
         }
         for (dlinear* d : {&tok, &out}) d->w.release(), d->scales.release(), d->lora_b.release(), d->q8.release(), d->s32.release();
-        for (dbuf* b : {&layer_arena, &bar, &errflag, &mega_timing, &norm, &fcos, &fsin, &kcache, &vcache, &x, &h, &q, &attn, &z, &logits, &hidden_save, &ids, &pos, &row_seq,
-                        &uniforms, &out_log, &step_counter, &pval, &pidx, &lora_ax, &pack_bad})
+        for (int k = 0; k < kTpMaxWorld; k++)
+            if (tp_peer_base[k] && uint32_t(k) != cfg.tp_rank) cudaIpcCloseMemHandle(tp_peer_base[k]);
+        for (dbuf* b : {&layer_arena, &bar, &errflag, &mega_timing, &tp_region, &tp_local, &norm, &fcos, &fsin, &kcache, &vcache, &x, &h, &q, &attn, &z, &logits, &logits_tmp, &hidden_save, &ids, &pos, &row_seq,
+                        &uniforms, &out_log, &step_counter, &pval, &pidx, &lora_ax, &pack_bad, &cand})
             b->release();
     }
 };
@@ -354,11 +362,30 @@ gemv_params w2_params(mc_llama* m, uint32_t li, uint32_t row0, uint32_t rows)
     p.ksplit = choose_ksplit(m->dev, p.N, p.K);
     return p;
 }
+tp_exchange tp_of(mc_llama* m)
+{
+    tp_exchange t{};
+    t.world = m->cfg.tp_world, t.rank = m->cfg.tp_rank, t.rows_max = kMaxMB, t.dim = m->cfg.dim;
+    for (uint32_t k = 0; k < t.world; k++) {
+        t.peer_buf[k] = static_cast<float*>(m->tp_peer_base[k]);
+        t.peer_flag[k] = reinterpret_cast<uint32_t*>(static_cast<char*>(m->tp_peer_base[k]) + m->tp_off_flags);
+    }
+    t.done = m->tp_local.as<unsigned>(), t.epoch = m->tp_local.as<unsigned>() + 1, t.err = m->errflag.as<int>();
+    return t;
+}
+// makes `p` consume the previous row-parallel GEMV's partial sums: rows = r(res + r(sum)), stored to `out` by CTA 0
+void tp_consume(mc_llama* m, gemv_params& p, const uint16_t* res, uint16_t* out)
+{
+    p.tp = tp_of(m), p.tp_reduce = 1, p.tp_res = res, p.tp_out = out;
+}
+
 gemv_params head_params(mc_llama* m, const uint16_t* x, uint32_t rows, uint16_t* logits_dst)
 {
     const dlinear& hw = m->tied ? m->tok : m->out;
     gemv_params p{};
-    p.W = hw.w.p, p.N = m->Vl, p.K = m->cfg.dim, p.rows = rows;
+    // vocabulary-sharded head: this rank projects rows [rank*Vl, (rank+1)*Vl) of the (tied) table
+    p.W = m->tied ? static_cast<const void*>(hw.w.as<uint16_t>() + size_t(m->cfg.tp_rank) * m->Vl * m->cfg.dim) : hw.w.p;
+    p.N = m->Vl, p.K = m->cfg.dim, p.rows = rows;
     p.norm_w = m->norm.as<uint16_t>(), p.eps = m->cfg.norm_eps;
     p.x = x, p.ldx = m->cfg.dim, p.y = logits_dst, p.ldy = m->Vl;
     p.ksplit = choose_ksplit(m->dev, p.N, p.K);
@@ -440,15 +467,41 @@ void enqueue_rows(mc_llama* m, launcher& L, uint32_t row0, uint32_t rows, int he
         enqueue_rows_quant(m, L, row0, rows, head_mode, logits_dst);
         return;
     }
+    const bool tp = c.tp_world > 1;
+    if (tp) MC_REQUIRE(m->tp_connected, "tensor parallel model: mc_llama_tp_connect has not been called");
+    uint16_t* h = m->h.as<uint16_t>() + size_t(row0) * D;
     for (uint32_t li = 0; li < c.n_layers; li++) {
-        gemv_launch<PRO_RMSNORM, EPI_QKV>(L, qkv_params(m, li, row0, rows));
+        gemv_params gq = qkv_params(m, li, row0, rows);
+        if (tp && li > 0) tp_consume(m, gq, h, x); // x = r(h + all-reduced w2 output of the previous block)
+        gemv_launch<PRO_RMSNORM, EPI_QKV>(L, gq);
         const attn_params a = attn_params_of(m, li, row0);
         const size_t smem = attn_smem(m, kAttnCluster);
         if (hd == 64) L.go_cluster(attn_decode_kernel<64>, dim3(m->Hl * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
         else L.go_cluster(attn_decode_kernel<128>, dim3(m->Hl * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
-        gemv_launch<PRO_NONE, EPI_RESIDUAL>(L, wo_params(m, li, row0, rows));
-        gemv_launch<PRO_RMSNORM, EPI_SWIGLU>(L, w13_params(m, li, row0, rows));
-        gemv_launch<PRO_NONE, EPI_RESIDUAL>(L, w2_params(m, li, row0, rows));
+        gemv_params go = wo_params(m, li, row0, rows), g13 = w13_params(m, li, row0, rows), g2 = w2_params(m, li, row0, rows);
+        if (!tp) {
+            gemv_launch<PRO_NONE, EPI_RESIDUAL>(L, go);
+            gemv_launch<PRO_RMSNORM, EPI_SWIGLU>(L, g13);
+            gemv_launch<PRO_NONE, EPI_RESIDUAL>(L, g2);
+        } else {
+            // row-parallel wo / w2 push fp32 partials to every rank; the next GEMV's prologue finishes the all-reduce
+            go.tp = tp_of(m), g2.tp = tp_of(m);
+            gemv_launch<PRO_NONE, EPI_PARTIAL_TP>(L, go);
+            tp_consume(m, g13, x, h); // h = r(x + all-reduced wo output)
+            gemv_launch<PRO_RMSNORM, EPI_SWIGLU>(L, g13);
+            gemv_launch<PRO_NONE, EPI_PARTIAL_TP>(L, g2);
+        }
+    }
+    if (tp) {
+        // the head's prologue completes the last block's all-reduce; without logits the reduction is not needed at all
+        if (head_mode == 0) return;
+        uint16_t* dst = head_mode == 2 ? m->logits_tmp.as<uint16_t>() : logits_dst;
+        gemv_params gh = head_params(m, x, rows, dst);
+        tp_consume(m, gh, h, x);
+        gemv_launch<PRO_RMSNORM, EPI_NONE>(L, gh);
+        if (head_mode == 2)
+            MC_CUDA_CHECK(cudaMemcpyAsync(logits_dst, dst + size_t(rows - 1) * m->Vl, size_t(m->Vl) * 2, cudaMemcpyDeviceToDevice, L.s));
+        return;
     }
     if (head_mode == 2) gemv_launch<PRO_RMSNORM, EPI_NONE>(L, head_params(m, x + size_t(rows - 1) * D, 1, logits_dst));
     else if (head_mode == 1) gemv_launch<PRO_RMSNORM, EPI_NONE>(L, head_params(m, x, rows, logits_dst));
@@ -531,9 +584,62 @@ template <int MB> void launch_megakernel(mc_llama* m, launcher& L, uint32_t rows
     m->dev->launches.fetch_add(1);
 }
 
+// launches the two sampling kernels over logits [rows, vocab] (bf16, row pitch ld)
+void launch_sampler(launcher& L, sample_params sp, const mc_sampler_config& sc, uint32_t rows, uint32_t vocab, unsigned long long* cand)
+{
+    MC_REQUIRE(sc.top_k >= 1 && sc.top_k <= uint32_t(kSampleMaxK), "sampler: top_k must be in [1, 64]");
+    MC_REQUIRE(sc.top_k <= vocab, "sampler: top_k exceeds the vocabulary");
+    MC_REQUIRE(sc.temperature > 0.0f, "sampler: temperature must be positive");
+    const uint32_t blocks = (vocab + kSampleSlice - 1) / kSampleSlice;
+    L.go(sample_select_kernel, dim3(blocks, rows), dim3(256), 0, sp.logits, sp.ld, vocab, sp.index_base, cand);
+    sp.cand = cand, sp.n_cand = blocks * kSampleKeep;
+    sp.sort_n = 64;
+    while (sp.sort_n < sp.n_cand) sp.sort_n <<= 1;
+    sp.top_k = sc.top_k, sp.intended = sc.intended, sp.rows = rows;
+    const float temp_t = bf16_bits_to_f32(f32_to_bf16_bits(sc.temperature));       // T(temperature)
+    sp.inv_t = bf16_bits_to_f32(f32_to_bf16_bits(1.0f / temp_t));                   // T(1 / T(temperature))
+    sp.top_p = bf16_bits_to_f32(f32_to_bf16_bits(sc.top_p));
+    static bool configured = false;
+    if (!configured) {
+        MC_CUDA_CHECK(cudaFuncSetAttribute(sample_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured = true;
+    }
+    MC_REQUIRE(size_t(sp.sort_n) * 8 <= 160 * 1024, "sampler: vocabulary shard too large for the candidate sort");
+    L.go(sample_finish_kernel, dim3(rows), dim3(1024), size_t(sp.sort_n) * 8, sp);
+}
+
 void enqueue_sample(mc_llama* m, launcher& L, uint32_t rows, const mc_sampler_config& sc, int advance)
 {
-    MC_REQUIRE(sc.mode == 0, "sampler mode not supported by this build (greedy only)");
+    if (sc.mode == 1) {
+        MC_REQUIRE(m->cfg.tp_world == 1, "the multinomial sampler is not available under tensor parallelism (greedy only)");
+        // make_default_sampler (nn/sampling.h:306-316): top-k -> nucleus -> multinomial, all on the device
+        sample_params sp{};
+        sp.logits = m->logits.as<uint16_t>(), sp.ld = m->Vl, sp.index_base = 0;
+        sp.uniforms = m->uniforms.as<float>();
+        sp.ids = m->ids.as<int32_t>(), sp.pos = m->pos.as<int32_t>(), sp.out_log = m->out_log.as<int32_t>();
+        sp.step_counter = m->step_counter.as<int32_t>(), sp.advance = advance;
+        launch_sampler(L, sp, sc, rows, m->Vl, m->cand.as<unsigned long long>());
+        L.go(sample_step_kernel, dim3(1), dim3(32), 0, m->step_counter.as<int32_t>());
+        return;
+    }
+    MC_REQUIRE(sc.mode == 0, "unknown sampler mode");
+    if (m->cfg.tp_world > 1) {
+        L.go(argmax_partial_kernel, dim3(kArgmaxBlocks, rows), dim3(256), 0, (const uint16_t*)m->logits.p, m->Vl, m->Vl, m->pval.as<float>(),
+             m->pidx.as<int32_t>());
+        am_exchange x{};
+        x.world = m->cfg.tp_world, x.rank = m->cfg.tp_rank, x.rows_max = kMaxMB;
+        for (uint32_t k = 0; k < x.world; k++) {
+            char* base = static_cast<char*>(m->tp_peer_base[k]);
+            x.peer_val[k] = reinterpret_cast<float*>(base + m->tp_off_amval);
+            x.peer_idx[k] = reinterpret_cast<int32_t*>(base + m->tp_off_amidx);
+            x.peer_flag[k] = reinterpret_cast<uint32_t*>(base + m->tp_off_amflags);
+        }
+        x.epoch = m->tp_local.as<unsigned>() + 2, x.err = m->errflag.as<int>();
+        L.go(argmax_final_tp_kernel, dim3(1), dim3(((rows + 31) / 32) * 32), 0, (const float*)m->pval.p, (const int32_t*)m->pidx.p, kArgmaxBlocks,
+             int32_t(m->cfg.tp_rank * m->Vl), x, m->ids.as<int32_t>(), m->pos.as<int32_t>(), m->out_log.as<int32_t>(), m->step_counter.as<int32_t>(), rows,
+             advance);
+        return;
+    }
     L.go(argmax_partial_kernel, dim3(kArgmaxBlocks, rows), dim3(256), 0, (const uint16_t*)m->logits.p, m->Vl, m->Vl,
          m->pval.as<float>(), m->pidx.as<int32_t>());
     L.go(argmax_final_kernel, dim3(1), dim3(((rows + 31) / 32) * 32), 0, (const float*)m->pval.p, (const int32_t*)m->pidx.p,
@@ -543,7 +649,7 @@ void enqueue_sample(mc_llama* m, launcher& L, uint32_t rows, const mc_sampler_co
 // one decode step for rows [0, n): forward in chunks of kMaxMB rows, then sample
 void enqueue_decode_step(mc_llama* m, launcher& L, uint32_t n, const mc_sampler_config& sc, int advance)
 {
-    if (n <= uint32_t(kMaxMB) && sc.mode == 0 && m->tok.fmt == WF_BF16 && (m->cfg.flags & MC_LLAMA_MEGAKERNEL)) {
+    if (n <= uint32_t(kMaxMB) && sc.mode == 0 && m->tok.fmt == WF_BF16 && m->cfg.tp_world == 1 && (m->cfg.flags & MC_LLAMA_MEGAKERNEL)) {
         if (n == 1) launch_megakernel<1>(m, L, n, advance);
         else if (n == 2) launch_megakernel<2>(m, L, n, advance);
         else launch_megakernel<4>(m, L, n, advance);
@@ -558,7 +664,10 @@ void enqueue_decode_step(mc_llama* m, launcher& L, uint32_t n, const mc_sampler_
 
 cudaGraphExec_t decode_graph(mc_llama* m, uint32_t n, const mc_sampler_config& sc, int advance)
 {
-    const uint64_t key = (uint64_t(n) << 32) | (uint64_t(sc.mode) << 8) | (uint64_t(sc.intended) << 4) | uint64_t(advance);
+    uint32_t tbits, pbits;
+    memcpy(&tbits, &sc.temperature, 4), memcpy(&pbits, &sc.top_p, 4);
+    const uint64_t key = mix64((uint64_t(n) << 40) ^ (uint64_t(sc.mode) << 36) ^ (uint64_t(sc.intended) << 35) ^ (uint64_t(advance) << 34) ^
+                               (uint64_t(sc.top_k) << 24) ^ (uint64_t(tbits) * 0x9E3779B97F4A7C15ull) ^ (uint64_t(pbits) << 1));
     auto it = m->graphs.find(key);
     if (it != m->graphs.end()) return it->second;
     cudaStream_t s = m->dev->stream;
@@ -759,7 +868,7 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
     mc_llama_config c = *cfg;
     if (c.n_seqs == 0) c.n_seqs = 1;
     if (c.tp_world == 0) c.tp_world = 1;
-    MC_REQUIRE(c.tp_world == 1, "tensor parallelism is not available in this build");
+    MC_REQUIRE(c.tp_world <= uint32_t(kTpMaxWorld), "tensor-parallel degree must be <= 8");
     MC_REQUIRE(c.tp_rank < c.tp_world, "tp_rank out of range");
     MC_REQUIRE(c.head_dim == 64 || c.head_dim == 128, "head_dim must be 64 or 128");
     MC_REQUIRE(c.n_heads % c.n_kv_heads == 0, "n_heads must be a multiple of n_kv_heads");
@@ -840,6 +949,19 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
     m->bar.alloc(256), m->errflag.alloc(256);
     MC_CUDA_CHECK(cudaMemset(m->bar.p, 0, 256));
     MC_CUDA_CHECK(cudaMemset(m->errflag.p, 0, 256));
+    if (c.tp_world > 1) {
+        const size_t rows_max = kMaxMB, T = c.tp_world;
+        const size_t part = 2 * T * rows_max * D * sizeof(float);
+        m->tp_off_flags = part;
+        m->tp_off_amval = m->tp_off_flags + 256;
+        m->tp_off_amidx = m->tp_off_amval + ((2 * T * rows_max * 4 + 255) & ~size_t(255));
+        m->tp_off_amflags = m->tp_off_amidx + ((2 * T * rows_max * 4 + 255) & ~size_t(255));
+        m->tp_region.alloc(m->tp_off_amflags + 256);
+        MC_CUDA_CHECK(cudaMemset(m->tp_region.p, 0, m->tp_region.bytes));
+        m->tp_local.alloc(256);
+        MC_CUDA_CHECK(cudaMemset(m->tp_local.p, 0, 256));
+        m->tp_peer_base[c.tp_rank] = m->tp_region.p;
+    }
     m->norm.alloc(size_t(D) * 2);
     // rope tables on the host with the same libm calls as the scalar reference formula
     // (kernel/rope.metal:93-97: 1/pow(theta, 2j/dim), cos/sin of pos*freq), 2*max_seq rows (nn/embedding.h:171)
@@ -870,8 +992,10 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
     m->q.alloc(size_t(R) * m->Hl * hd * 2), m->attn.alloc(size_t(R) * m->Hl * hd * 2);
     m->z.alloc(size_t(R) * m->Fl * 2);
     m->logits.alloc(size_t(R) * m->Vl * 2);
+    if (c.tp_world > 1) m->logits_tmp.alloc(size_t(kMaxMB) * m->Vl * 2);
     m->hidden_save.alloc(size_t(c.n_seqs) * D * 2);
-    m->ids.alloc(R * 4), m->pos.alloc(R * 4), m->row_seq.alloc(R * 4), m->uniforms.alloc(R * 4);
+    m->ids.alloc(R * 4), m->pos.alloc(R * 4), m->row_seq.alloc(R * 4), m->uniforms.alloc(size_t(kMaxLogSteps) * R * 4);
+    m->cand.alloc(size_t(R) * ((m->Vl + kSampleSlice - 1) / kSampleSlice) * kSampleKeep * 8);
     m->out_log.alloc(size_t(kMaxLogSteps) * R * 4);
     m->step_counter.alloc(4);
     m->pval.alloc(size_t(R) * 1024 * 4), m->pidx.alloc(size_t(R) * 1024 * 4);
@@ -1095,8 +1219,11 @@ mc_status mc_llama_decode(mc_llama* m, uint32_t n, const int32_t* ids, const int
     MC_REQUIRE(out_ids, "decode: null output");
     mc_sampler_config sc{};
     if (sampler) sc = *sampler;
-    (void)uniforms;
     stage_decode_inputs(m, n, ids, pos);
+    if (sc.mode == 1) {
+        MC_REQUIRE(uniforms, "decode: the multinomial sampler needs one injected uniform per sequence");
+        MC_CUDA_CHECK(cudaMemcpyAsync(m->uniforms.p, uniforms, n * 4, cudaMemcpyHostToDevice, m->dev->stream));
+    }
     run_decode_step(m, n, sc, 0);
     cudaStream_t s = m->dev->stream;
     int32_t* st_out = m->pinned + 3 * m->max_rows;
@@ -1117,8 +1244,11 @@ mc_status mc_llama_decode_loop(mc_llama* m, uint32_t n, const int32_t* first_ids
     MC_REQUIRE(steps >= 1 && steps <= kMaxLogSteps, "decode_loop: steps out of range");
     mc_sampler_config sc{};
     if (sampler) sc = *sampler;
-    (void)uniforms;
     stage_decode_inputs(m, n, first_ids, first_pos);
+    if (sc.mode == 1) {
+        MC_REQUIRE(uniforms, "decode_loop: the multinomial sampler needs steps*n injected uniforms");
+        MC_CUDA_CHECK(cudaMemcpyAsync(m->uniforms.p, uniforms, size_t(steps) * n * 4, cudaMemcpyHostToDevice, m->dev->stream));
+    }
     for (uint32_t r = 0; r < n; r++)
         MC_REQUIRE(uint64_t(first_pos[r]) + steps <= m->cfg.max_seq_len, "decode_loop: positions would exceed max_seq_len");
     cudaStream_t s = m->dev->stream;
@@ -1192,7 +1322,7 @@ mc_status mc_llama_profile_step(mc_llama* m, uint32_t n, float* us, uint32_t cap
     MC_REQUIRE(m->finalized && us && count, "bad arguments");
     MC_REQUIRE(n >= 1 && n <= m->cfg.n_seqs, "profile_step: number of sequences out of range");
     mc_sampler_config sc{};
-    if (n <= uint32_t(kMaxMB) && (m->cfg.flags & MC_LLAMA_MEGAKERNEL)) {
+    if (n <= uint32_t(kMaxMB) && m->cfg.tp_world == 1 && (m->cfg.flags & MC_LLAMA_MEGAKERNEL)) {
         // megakernel: per-phase stamps of CTA 0; us[3k..3k+2] = {wait, work, until next phase entry} of phase k
         const uint32_t phases = m->cfg.n_layers * 5 + 1;
         if (!m->mega_timing.p) m->mega_timing.alloc(size_t(phases + 1) * 3 * 8);
@@ -1239,11 +1369,81 @@ mc_status mc_llama_profile_step(mc_llama* m, uint32_t n, float* us, uint32_t cap
     MC_API_END
 }
 
+// ---- tensor parallel wiring: every rank exports one IPC handle, all ranks import all handles ------------------------------------
+mc_status mc_llama_tp_export(mc_llama* m, void* handle, size_t cap)
+{
+    MC_API_BEGIN
+    use(m);
+    MC_REQUIRE(handle && cap >= sizeof(cudaIpcMemHandle_t), "tp_export: handle buffer must hold 64 bytes");
+    MC_REQUIRE(m->cfg.tp_world > 1, "tp_export: the model is not tensor parallel");
+    cudaIpcMemHandle_t h;
+    MC_CUDA_CHECK(cudaIpcGetMemHandle(&h, m->tp_region.p));
+    memcpy(handle, &h, sizeof(h));
+    MC_API_END
+}
+
+mc_status mc_llama_tp_connect(mc_llama* m, const void* handles, size_t nbytes)
+{
+    MC_API_BEGIN
+    use(m);
+    const uint32_t T = m->cfg.tp_world;
+    MC_REQUIRE(T > 1, "tp_connect: the model is not tensor parallel");
+    MC_REQUIRE(handles && nbytes == size_t(T) * sizeof(cudaIpcMemHandle_t), "tp_connect: expected world x 64 bytes of handles");
+    for (uint32_t k = 0; k < T; k++) {
+        if (k == m->cfg.tp_rank || m->tp_peer_base[k]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(handles) + size_t(k) * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        MC_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        m->tp_peer_base[k] = p;
+    }
+    m->tp_connected = true;
+    MC_API_END
+}
+
 mc_status mc_llama_launches_per_step(mc_llama* m, uint32_t* kernels)
 {
     MC_API_BEGIN
     MC_REQUIRE(m && kernels, "bad arguments");
     *kernels = m->launches_per_step;
+    MC_API_END
+}
+
+// ---- stand-alone sampler (parity tests against the oracle's sample_default) ------------------------------------------------
+mc_status mc_sample_default(mc_device* dev, mc_buffer* logits_bf16, uint32_t rows, uint32_t vocab, const mc_sampler_config* cfg, const float* uniforms,
+                            int32_t* topk_idx, uint16_t* probs_sorted, int32_t* probs_idx, int32_t* choice, int32_t* token)
+{
+    MC_API_BEGIN
+    MC_REQUIRE(dev && logits_bf16 && cfg && uniforms && rows >= 1, "bad arguments");
+    MC_CUDA_CHECK(cudaSetDevice(dev->ordinal));
+    MC_REQUIRE(logits_bf16->size >= size_t(rows) * vocab * 2, "sample_default: logits buffer too small");
+    const uint32_t k = cfg->top_k, blocks = (vocab + kSampleSlice - 1) / kSampleSlice;
+    dbuf cand, du, d_topk, d_ps, d_pi, d_ch, d_tok;
+    struct guard {
+        std::vector<dbuf*> b;
+        ~guard()
+        {
+            for (auto* x : b) x->release();
+        }
+    } g{{&cand, &du, &d_topk, &d_ps, &d_pi, &d_ch, &d_tok}};
+    cand.alloc(size_t(rows) * blocks * kSampleKeep * 8), du.alloc(rows * 4);
+    d_topk.alloc(size_t(rows) * kSampleMaxK * 4), d_ps.alloc(size_t(rows) * kSampleMaxK * 2), d_pi.alloc(size_t(rows) * kSampleMaxK * 4);
+    d_ch.alloc(rows * 4), d_tok.alloc(rows * 4);
+    MC_CUDA_CHECK(cudaMemcpyAsync(du.p, uniforms, rows * 4, cudaMemcpyHostToDevice, dev->stream));
+    mc_llama shim;
+    shim.dev = dev;
+    launcher L{&shim, dev->stream, false};
+    sample_params sp{};
+    sp.logits = static_cast<const uint16_t*>(logits_bf16->dptr), sp.ld = vocab, sp.index_base = 0, sp.uniforms = du.as<float>();
+    sp.topk_idx = d_topk.as<int32_t>(), sp.probs_sorted = d_ps.as<uint16_t>(), sp.probs_idx = d_pi.as<int32_t>();
+    sp.choice = d_ch.as<int32_t>(), sp.token = d_tok.as<int32_t>();
+    launch_sampler(L, sp, *cfg, rows, vocab, cand.as<unsigned long long>());
+    MC_CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+    if (topk_idx) MC_CUDA_CHECK(cudaMemcpy(topk_idx, d_topk.p, size_t(rows) * k * 4, cudaMemcpyDeviceToHost));
+    if (probs_sorted) MC_CUDA_CHECK(cudaMemcpy(probs_sorted, d_ps.p, size_t(rows) * k * 2, cudaMemcpyDeviceToHost));
+    if (probs_idx) MC_CUDA_CHECK(cudaMemcpy(probs_idx, d_pi.p, size_t(rows) * k * 4, cudaMemcpyDeviceToHost));
+    if (choice) MC_CUDA_CHECK(cudaMemcpy(choice, d_ch.p, rows * 4, cudaMemcpyDeviceToHost));
+    if (token) MC_CUDA_CHECK(cudaMemcpy(token, d_tok.p, rows * 4, cudaMemcpyDeviceToHost));
     MC_API_END
 }
 

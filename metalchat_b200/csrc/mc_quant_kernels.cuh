@@ -44,6 +44,12 @@ __device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b)
     asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
     return d;
 }
+// byte `sel` (0..3) of w as a signed int8 -> fp32, exactly, without the conversion pipe: the byte (xor 0x80, i.e. +128)
+// is permuted into the mantissa of 2^23, then (2^23 + 128) is subtracted
+__device__ __forceinline__ float s8_to_f32(uint32_t w_xor80, uint32_t sel)
+{
+    return __uint_as_float(__byte_perm(w_xor80, 0x4b000000u, 0x7650u + sel)) - 8388736.0f;
+}
 // two fp32 -> packed bf16x2 (lo = first), round to nearest even
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
 {
@@ -244,12 +250,12 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_q_kernel(const qgemv_par
                             const uint32_t words[4] = {wv[i].x, wv[i].y, wv[i].z, wv[i].w};
 #pragma unroll
                             for (int j = 0; j < 2; j++) {
-                                const uint32_t lo = words[2 * j], hi = words[2 * j + 1];
+                                const uint32_t lo = words[2 * j] ^ 0x80808080u, hi = words[2 * j + 1] ^ 0x80808080u;
                                 // int8 -> fp32 (exact) * r(s) (exact in fp32) -> one rounding to bf16
-                                const uint32_t a0 = pack_bf16x2(float(int8_t(lo)) * rs0, float(int8_t(lo >> 8)) * rs0);
-                                const uint32_t a1 = pack_bf16x2(float(int8_t(lo >> 16)) * rs1, float(int8_t(lo >> 24)) * rs1);
-                                const uint32_t a2 = pack_bf16x2(float(int8_t(hi)) * rs0, float(int8_t(hi >> 8)) * rs0);
-                                const uint32_t a3 = pack_bf16x2(float(int8_t(hi >> 16)) * rs1, float(int8_t(hi >> 24)) * rs1);
+                                const uint32_t a0 = pack_bf16x2(__fmul_rn(s8_to_f32(lo, 0), rs0), __fmul_rn(s8_to_f32(lo, 1), rs0));
+                                const uint32_t a1 = pack_bf16x2(__fmul_rn(s8_to_f32(lo, 2), rs1), __fmul_rn(s8_to_f32(lo, 3), rs1));
+                                const uint32_t a2 = pack_bf16x2(__fmul_rn(s8_to_f32(hi, 0), rs0), __fmul_rn(s8_to_f32(hi, 1), rs0));
+                                const uint32_t a3 = pack_bf16x2(__fmul_rn(s8_to_f32(hi, 2), rs1), __fmul_rn(s8_to_f32(hi, 3), rs1));
                                 const uint32_t b0 = *reinterpret_cast<const uint32_t*>(xk + j * 16);
                                 const uint32_t b1 = *reinterpret_cast<const uint32_t*>(xk + j * 16 + 8);
                                 mma_bf16_16816(c, a0, a1, a2, a3, b0, b1);
@@ -285,13 +291,24 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_q_kernel(const qgemv_par
                 const uint32_t m = 2 * t + bsel;
                 float y0 = rbf(bsel == 0 ? c[0] : c[1]), y1 = rbf(bsel == 0 ? c[2] : c[3]);
                 if (qp.lora_b) {
-                    // y = r(y + r(r(B . ax) * scale))   (quantization/lora.h:115-122)
+                    // y = r(y + r(r(B . ax) * scale))   (quantization/lora.h:115-122); 16-byte loads, all issued before use
                     const uint16_t* ax0 = qp.lora_ax + size_t(m) * qp.ax_ld + lora_slice(qp, r0) * qp.rank;
                     const uint16_t* ax1 = qp.lora_ax + size_t(m) * qp.ax_ld + lora_slice(qp, r1) * qp.rank;
+                    const uint16_t* b0p = qp.lora_b + size_t(r0) * qp.rank;
+                    const uint16_t* b1p = qp.lora_b + size_t(r1) * qp.rank;
                     float l0 = 0.0f, l1 = 0.0f;
-                    for (uint32_t j = 0; j < qp.rank; j++) {
-                        l0 = fmaf(bf16_bits_to_f32(ax0[j]), bf16_bits_to_f32(qp.lora_b[size_t(r0) * qp.rank + j]), l0);
-                        l1 = fmaf(bf16_bits_to_f32(ax1[j]), bf16_bits_to_f32(qp.lora_b[size_t(r1) * qp.rank + j]), l1);
+                    if ((qp.rank & 7u) == 0) {
+                        for (uint32_t j = 0; j < qp.rank; j += 8) {
+                            const uint4 xa = *reinterpret_cast<const uint4*>(ax0 + j), xb2 = *reinterpret_cast<const uint4*>(ax1 + j);
+                            const uint4 wa = *reinterpret_cast<const uint4*>(b0p + j), wb = *reinterpret_cast<const uint4*>(b1p + j);
+                            l0 = dot8(wa, xa, l0);
+                            l1 = dot8(wb, xb2, l1);
+                        }
+                    } else {
+                        for (uint32_t j = 0; j < qp.rank; j++) {
+                            l0 = fmaf(bf16_bits_to_f32(ax0[j]), bf16_bits_to_f32(b0p[j]), l0);
+                            l1 = fmaf(bf16_bits_to_f32(ax1[j]), bf16_bits_to_f32(b1p[j]), l1);
+                        }
                     }
                     y0 = rbf(__fadd_rn(y0, rbf(__fmul_rn(rbf(l0), qp.lora_scale))));
                     y1 = rbf(__fadd_rn(y1, rbf(__fmul_rn(rbf(l1), qp.lora_scale))));
