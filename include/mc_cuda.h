@@ -132,7 +132,8 @@ enum {
     MC_LLAMA_W4_PACKED = 1u << 0, /* store QLoRA int8-in-int4-range weights two per byte       */
     MC_LLAMA_NO_GRAPH = 1u << 1,  /* launch kernels directly instead of replaying a CUDA graph  */
     MC_LLAMA_NO_PDL = 1u << 2,    /* no programmatic dependent launch between decode kernels    */
-    MC_LLAMA_MEGAKERNEL = 1u << 3 /* experimental: the whole decode step as ONE persistent kernel with grid barriers */
+    MC_LLAMA_MEGAKERNEL = 1u << 3, /* experimental: the whole decode step as ONE persistent kernel with grid barriers */
+    MC_LLAMA_NO_STREAM = 1u << 4   /* do not use the streaming persistent kernel (TMA weight ring): per-op kernels under a CUDA graph */
 };
 typedef struct mc_sampler_config {
     uint32_t mode;       /* 0 greedy argmax (lowest index on ties); 1 top-k -> nucleus -> multinomial (nn/sampling.h:306-316) */

@@ -16,6 +16,7 @@
 //   rope tables fcos/fsin [2*max_seq, hd/2] fp32 (nn/embedding.h:160-176)
 #include "mc_quant_kernels.cuh"
 #include "mc_sample_kernels.cuh"
+#include "mc_stream_kernel.cuh"
 
 #include <cmath>
 #include <map>
@@ -91,6 +92,11 @@ struct mc_llama {
     void* tp_peer_base[kTpMaxWorld] = {};
     bool tp_connected = false;
     size_t tp_off_flags = 0, tp_off_amval = 0, tp_off_amidx = 0, tp_off_amflags = 0;
+    // streaming persistent kernel (mc_stream_kernel.cuh): un-rotated q|k|v rows, split-attention exchange, step flag
+    dbuf qkv, opart, xsum, acnt, step_done, st_timing;
+    bool st_timing_on = false;
+    int st_ok = -1;            // -1 not probed yet, 0 not usable on this device / shape, 1 usable
+    uint32_t st_grid = 0;
     dbuf mega_timing;          // diagnostics: per-phase globaltimer stamps (allocated on demand)
     bool mega_timing_on = false;
     int mega_ctas_per_sm[3] = {0, 0, 0};
@@ -119,7 +125,7 @@ struct mc_llama {
         for (dlinear* d : {&tok, &out}) d->w.release(), d->scales.release(), d->lora_b.release(), d->q8.release(), d->s32.release();
         for (int k = 0; k < kTpMaxWorld; k++)
             if (tp_peer_base[k] && uint32_t(k) != cfg.tp_rank) cudaIpcCloseMemHandle(tp_peer_base[k]);
-        for (dbuf* b : {&layer_arena, &bar, &errflag, &mega_timing, &tp_region, &tp_local, &norm, &fcos, &fsin, &kcache, &vcache, &x, &h, &q, &attn, &z, &logits, &logits_tmp, &hidden_save, &ids, &pos, &row_seq,
+        for (dbuf* b : {&qkv, &opart, &xsum, &acnt, &step_done, &st_timing, &layer_arena, &bar, &errflag, &mega_timing, &tp_region, &tp_local, &norm, &fcos, &fsin, &kcache, &vcache, &x, &h, &q, &attn, &z, &logits, &logits_tmp, &hidden_save, &ids, &pos, &row_seq,
                         &uniforms, &out_log, &step_counter, &pval, &pidx, &lora_ax, &pack_bad, &cand})
             b->release();
     }
@@ -584,6 +590,102 @@ template <int MB> void launch_megakernel(mc_llama* m, launcher& L, uint32_t rows
     m->dev->launches.fetch_add(1);
 }
 
+// ---- the streaming persistent kernel (mc_stream_kernel.cuh) ---------------------------------------------------------------
+uint32_t stream_kc(uint32_t K)
+{
+    for (uint32_t kc : {1024u, 768u, 512u, 256u})
+        if (K % kc == 0) return kc;
+    return 0;
+}
+struct stream_geom {
+    uint32_t act_pitch, act_bytes, n_stages;
+    size_t smem;
+};
+bool stream_geometry(const mc_llama* m, uint32_t rows, stream_geom& g)
+{
+    const mc_llama_config& c = m->cfg;
+    const uint32_t kmax = std::max(std::max(c.dim, m->Hl * c.head_dim), m->Fl);
+    g.act_pitch = kmax * 2 + kStPad;
+    const size_t attn_scratch = (size_t(3) * c.head_dim + 2048 + (c.max_seq_len + kStSplits - 1) / kStSplits + 8) * sizeof(float);
+    g.act_bytes = uint32_t((std::max(size_t(rows) * g.act_pitch, attn_scratch) + 127) & ~size_t(127));
+    const size_t fixed = kStHdrBytes + kStRedBytes + g.act_bytes;
+    const size_t cap = 232448; // 227 KiB of dynamic shared memory per CTA on sm_100
+    if (fixed + 2 * size_t(kStStageBytes) > cap) return false;
+    g.n_stages = uint32_t(std::min<size_t>(kStMaxStages, (cap - fixed) / kStStageBytes));
+    g.smem = fixed + size_t(g.n_stages) * kStStageBytes;
+    return true;
+}
+// the streaming kernel serves greedy bf16 decode of up to 8 sequences on one GPU; everything else takes the per-op path
+bool stream_eligible(mc_llama* m, uint32_t n, const mc_sampler_config& sc)
+{
+    const mc_llama_config& c = m->cfg;
+    static const bool env_off = getenv("MC_NO_STREAM") != nullptr;
+    if (env_off || (c.flags & (MC_LLAMA_NO_STREAM | MC_LLAMA_MEGAKERNEL))) return false;
+    if (c.quant || c.tp_world != 1 || sc.mode != 0 || n > uint32_t(kStMaxRows) || m->tok.fmt != WF_BF16) return false;
+    if (m->st_ok < 0) {
+        m->st_ok = 0;
+        stream_geom g;
+        const bool shapes = stream_kc(c.dim) && stream_kc(m->Hl * c.head_dim) && stream_kc(m->Fl) && stream_geometry(m, kStMaxRows, g);
+        if (shapes) {
+            if (cudaFuncSetAttribute(decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) == cudaSuccess) {
+                int occ = 0, coop = 0;
+                cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, m->dev->ordinal);
+                if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decode_stream_kernel, kStThreads, g.smem) == cudaSuccess && occ >= 1) {
+                    m->st_ok = 1;
+                    m->st_grid = uint32_t(m->dev->prop.multiProcessorCount);
+                }
+            }
+            cudaGetLastError();
+        }
+    }
+    return m->st_ok == 1;
+}
+void launch_stream(mc_llama* m, launcher& L, uint32_t rows, int advance, uint32_t steps)
+{
+    const mc_llama_config& c = m->cfg;
+    const uint32_t D = c.dim, hd = c.head_dim, QO = m->Hl * hd, QKVN = (m->Hl + 2 * m->KVl) * hd;
+    MC_REQUIRE(steps == 1 || advance, "stream kernel: several steps per launch need the sampled id fed back");
+    stream_geom geo;
+    MC_REQUIRE(stream_geometry(m, rows, geo), "stream kernel: activation rows do not fit in shared memory");
+    st_params P{};
+    const dlayer& l0 = m->layers[0];
+    auto gemv = [&](const void* W, const dbuf* norm, const uint16_t* x, uint16_t* y, const uint16_t* res, uint32_t N, uint32_t K, uint32_t ldx, uint32_t ldy,
+                    int pro, int epi, int in_kind, int layered) {
+        st_gemv g{};
+        g.W = static_cast<const uint16_t*>(W), g.norm_w = norm ? norm->as<uint16_t>() : nullptr, g.x = x, g.y = y, g.res = res;
+        g.N = N, g.K = K, g.KC = stream_kc(K), g.ldx = ldx, g.ldy = ldy, g.pro = pro, g.epi = epi, g.in_kind = in_kind, g.layered = layered;
+        return g;
+    };
+    uint16_t *x = m->x.as<uint16_t>(), *h = m->h.as<uint16_t>(), *z = m->z.as<uint16_t>(), *qkv = m->qkv.as<uint16_t>();
+    P.g[0] = gemv(l0.wqkv.w.p, &l0.attn_norm, x, qkv, nullptr, QKVN, D, D, QKVN, PRO_RMSNORM, EPI_NONE, ST_IN_ROWS, 1);
+    P.g[1] = gemv(l0.wo.w.p, nullptr, nullptr, h, x, D, QO, QO, D, PRO_NONE, EPI_RESIDUAL, ST_IN_ATTN, 1);
+    P.g[2] = gemv(l0.w13.w.p, &l0.ffn_norm, h, z, nullptr, 2 * m->Fl, D, D, m->Fl, PRO_RMSNORM, EPI_SWIGLU, ST_IN_ROWS, 1);
+    P.g[3] = gemv(l0.w2.w.p, nullptr, z, x, h, D, m->Fl, m->Fl, D, PRO_NONE, EPI_RESIDUAL, ST_IN_ROWS, 1);
+    P.g[4] = gemv(m->tok.w.p, &m->norm, x, m->logits.as<uint16_t>(), nullptr, m->Vl, D, D, m->Vl, PRO_RMSNORM, EPI_NONE, ST_IN_ROWS, 0);
+    P.layer_stride = m->layer_stride, P.kv_layer_stride = kv_layer_elems(m);
+    P.n_layers = c.n_layers, P.rows = rows, P.steps = steps, P.n_stages = geo.n_stages, P.act_pitch = geo.act_pitch, P.act_bytes = geo.act_bytes;
+    P.eps = c.norm_eps;
+    P.qkv = qkv, P.kcache = m->kcache.as<uint16_t>(), P.vcache = m->vcache.as<uint16_t>(), P.fcos = m->fcos.as<float>(), P.fsin = m->fsin.as<float>();
+    P.row_seq = m->row_seq.as<int32_t>(), P.pos = m->pos.as<int32_t>(), P.ids = m->ids.as<int32_t>();
+    P.n_heads = m->Hl, P.n_kv_heads = m->KVl, P.head_dim = hd, P.max_seq = c.max_seq_len, P.vocab = c.vocab, P.scale = m->scale_bf16;
+    P.xsum = m->xsum.as<float>(), P.acnt = m->acnt.as<unsigned>(), P.opart = m->opart.as<float>();
+    P.embed_table = m->tok.w.as<uint16_t>(), P.embed_out = x;
+    P.bar = m->bar.as<unsigned>(), P.step_done = m->step_done.as<unsigned>(), P.err = m->errflag.as<int>();
+    P.am_val = m->pval.as<float>(), P.am_idx = m->pidx.as<int32_t>(), P.out_log = m->out_log.as<int32_t>();
+    P.step_counter = m->step_counter.as<int32_t>(), P.advance = advance;
+    P.timing = m->st_timing_on ? m->st_timing.as<unsigned long long>() : nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(m->st_grid), cfg.blockDim = dim3(kStThreads), cfg.dynamicSmemBytes = geo.smem, cfg.stream = L.s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative; // all CTAs must be co-resident for the grid barriers
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    L.mark();
+    MC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, decode_stream_kernel, P));
+    L.count++;
+    m->dev->launches.fetch_add(1);
+}
+
 // launches the two sampling kernels over logits [rows, vocab] (bf16, row pitch ld)
 void launch_sampler(launcher& L, sample_params sp, const mc_sampler_config& sc, uint32_t rows, uint32_t vocab, unsigned long long* cand)
 {
@@ -649,6 +751,10 @@ void enqueue_sample(mc_llama* m, launcher& L, uint32_t rows, const mc_sampler_co
 // one decode step for rows [0, n): forward in chunks of kMaxMB rows, then sample
 void enqueue_decode_step(mc_llama* m, launcher& L, uint32_t n, const mc_sampler_config& sc, int advance)
 {
+    if (stream_eligible(m, n, sc)) {
+        launch_stream(m, L, n, advance, 1);
+        return;
+    }
     if (n <= uint32_t(kMaxMB) && sc.mode == 0 && m->tok.fmt == WF_BF16 && m->cfg.tp_world == 1 && (m->cfg.flags & MC_LLAMA_MEGAKERNEL)) {
         if (n == 1) launch_megakernel<1>(m, L, n, advance);
         else if (n == 2) launch_megakernel<2>(m, L, n, advance);
@@ -693,7 +799,7 @@ cudaGraphExec_t decode_graph(mc_llama* m, uint32_t n, const mc_sampler_config& s
 
 void run_decode_step(mc_llama* m, uint32_t n, const mc_sampler_config& sc, int advance)
 {
-    if (m->cfg.flags & MC_LLAMA_NO_GRAPH) {
+    if ((m->cfg.flags & MC_LLAMA_NO_GRAPH) || stream_eligible(m, n, sc)) {
         launcher L{m, m->dev->stream, !(m->cfg.flags & MC_LLAMA_NO_PDL)};
         enqueue_decode_step(m, L, n, sc, advance);
         m->launches_per_step = L.count;
@@ -991,6 +1097,13 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
     m->x.alloc(size_t(R) * D * 2), m->h.alloc(size_t(R) * D * 2);
     m->q.alloc(size_t(R) * m->Hl * hd * 2), m->attn.alloc(size_t(R) * m->Hl * hd * 2);
     m->z.alloc(size_t(R) * m->Fl * 2);
+    m->qkv.alloc(size_t(kStMaxRows) * QKVN * 2);
+    m->opart.alloc(size_t(kStMaxRows) * kStSplits * QOl * sizeof(float));
+    m->xsum.alloc(size_t(kStMaxRows) * m->Hl * kStSplits * sizeof(float));
+    m->acnt.alloc(size_t(kStMaxRows) * m->Hl * sizeof(unsigned));
+    m->step_done.alloc(256);
+    MC_CUDA_CHECK(cudaMemset(m->acnt.p, 0, m->acnt.bytes));
+    MC_CUDA_CHECK(cudaMemset(m->step_done.p, 0, 256));
     m->logits.alloc(size_t(R) * m->Vl * 2);
     if (c.tp_world > 1) m->logits_tmp.alloc(size_t(kMaxMB) * m->Vl * 2);
     m->hidden_save.alloc(size_t(c.n_seqs) * D * 2);
@@ -1188,7 +1301,7 @@ static void check_mega_error(mc_llama* m, int flag)
     if (flag) {
         cudaMemset(m->errflag.p, 0, 4);
         cudaMemset(m->bar.p, 0, 4);
-        throw error(MC_ERR_RUNTIME, "megakernel: grid barrier timed out (CTAs not co-resident?)");
+        throw error(MC_ERR_RUNTIME, "persistent decode kernel: a barrier wait timed out (code " + std::to_string(flag) + "; CTAs not co-resident?)");
     }
 }
 
@@ -1255,9 +1368,17 @@ mc_status mc_llama_decode_loop(mc_llama* m, uint32_t n, const int32_t* first_ids
     cudaEvent_t e0, e1;
     MC_CUDA_CHECK(cudaEventCreate(&e0));
     MC_CUDA_CHECK(cudaEventCreate(&e1));
-    if (!(m->cfg.flags & MC_LLAMA_NO_GRAPH)) decode_graph(m, n, sc, 1); // instantiate outside the timed region
+    const bool stream = stream_eligible(m, n, sc);
+    if (!stream && !(m->cfg.flags & MC_LLAMA_NO_GRAPH)) decode_graph(m, n, sc, 1); // instantiate outside the timed region
     MC_CUDA_CHECK(cudaEventRecord(e0, s));
-    for (uint32_t i = 0; i < steps; i++) run_decode_step(m, n, sc, 1);
+    if (stream) {
+        // the persistent kernel loops over the steps itself: the weight stream of step i+1 starts under the sampler tail of step i
+        launcher L{m, s, false};
+        launch_stream(m, L, n, 1, steps);
+        m->launches_per_step = 1;
+    } else {
+        for (uint32_t i = 0; i < steps; i++) run_decode_step(m, n, sc, 1);
+    }
     MC_CUDA_CHECK(cudaEventRecord(e1, s));
     MC_CUDA_CHECK(cudaStreamSynchronize(s));
     float ms = 0.0f;
@@ -1322,6 +1443,32 @@ mc_status mc_llama_profile_step(mc_llama* m, uint32_t n, float* us, uint32_t cap
     MC_REQUIRE(m->finalized && us && count, "bad arguments");
     MC_REQUIRE(n >= 1 && n <= m->cfg.n_seqs, "profile_step: number of sequences out of range");
     mc_sampler_config sc{};
+    if (stream_eligible(m, n, sc)) {
+        // streaming kernel: four stamps of CTA 0 per phase; us[4k..4k+3] = {wait, stage input, consume tiles, until next phase entry}
+        const uint32_t phases = m->cfg.n_layers * 5 + 1;
+        if (!m->st_timing.p) m->st_timing.alloc(size_t(phases + 1) * 4 * 8);
+        MC_CUDA_CHECK(cudaMemsetAsync(m->st_timing.p, 0, m->st_timing.bytes, m->dev->stream));
+        MC_CUDA_CHECK(cudaMemsetAsync(m->step_counter.p, 0, 4, m->dev->stream));
+        m->st_timing_on = true;
+        launcher L{m, m->dev->stream, false};
+        try {
+            launch_stream(m, L, n, 0, 1);
+        } catch (...) {
+            m->st_timing_on = false;
+            throw;
+        }
+        m->st_timing_on = false;
+        MC_CUDA_CHECK(cudaStreamSynchronize(m->dev->stream));
+        std::vector<unsigned long long> t(size_t(phases + 1) * 4);
+        MC_CUDA_CHECK(cudaMemcpy(t.data(), m->st_timing.p, t.size() * 8, cudaMemcpyDeviceToHost));
+        *count = phases * 4;
+        for (uint32_t k = 0; k < phases; k++) {
+            if (k * 4 + 3 >= cap) break;
+            for (int j = 0; j < 3; j++) us[k * 4 + j] = float(t[k * 4 + j + 1] - t[k * 4 + j]) * 1e-3f;
+            us[k * 4 + 3] = k + 1 < phases ? float(t[(k + 1) * 4] - t[k * 4 + 3]) * 1e-3f : 0.0f;
+        }
+        return MC_OK;
+    }
     if (n <= uint32_t(kMaxMB) && m->cfg.tp_world == 1 && (m->cfg.flags & MC_LLAMA_MEGAKERNEL)) {
         // megakernel: per-phase stamps of CTA 0; us[3k..3k+2] = {wait, work, until next phase entry} of phase k
         const uint32_t phases = m->cfg.n_layers * 5 + 1;
