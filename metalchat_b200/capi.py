@@ -395,7 +395,7 @@ class Llama:
         return out
 
     def profile_step(self, n: int = 1) -> np.ndarray:
-        us = np.zeros(4096, dtype=np.float32)
+        us = np.zeros(1 << 18, dtype=np.float32)
         cnt = C.c_uint32()
         check(lib().mc_llama_profile_step(self.h, n, _vp(us), len(us), C.byref(cnt)))
         return us[: cnt.value]

@@ -93,7 +93,9 @@ struct mc_llama {
     bool tp_connected = false;
     size_t tp_off_flags = 0, tp_off_amval = 0, tp_off_amidx = 0, tp_off_amflags = 0;
     // streaming persistent kernel (mc_stream_kernel.cuh): un-rotated q|k|v rows, split-attention exchange, step flag
-    dbuf qkv, opart, xsum, acnt, step_done, st_timing;
+    dbuf st_ll, st_timing;     // one arena of tagged words: x | h | z | qkv | attn | scores | argmax partials | ids
+    size_t st_off[8] = {};
+    uint32_t st_sc_words = 0, st_seq = 0;
     bool st_timing_on = false;
     int st_ok = -1;            // -1 not probed yet, 0 not usable on this device / shape, 1 usable
     uint32_t st_grid = 0;
@@ -125,7 +127,7 @@ struct mc_llama {
         for (dlinear* d : {&tok, &out}) d->w.release(), d->scales.release(), d->lora_b.release(), d->q8.release(), d->s32.release();
         for (int k = 0; k < kTpMaxWorld; k++)
             if (tp_peer_base[k] && uint32_t(k) != cfg.tp_rank) cudaIpcCloseMemHandle(tp_peer_base[k]);
-        for (dbuf* b : {&qkv, &opart, &xsum, &acnt, &step_done, &st_timing, &layer_arena, &bar, &errflag, &mega_timing, &tp_region, &tp_local, &norm, &fcos, &fsin, &kcache, &vcache, &x, &h, &q, &attn, &z, &logits, &logits_tmp, &hidden_save, &ids, &pos, &row_seq,
+        for (dbuf* b : {&st_ll, &st_timing, &layer_arena, &bar, &errflag, &mega_timing, &tp_region, &tp_local, &norm, &fcos, &fsin, &kcache, &vcache, &x, &h, &q, &attn, &z, &logits, &logits_tmp, &hidden_save, &ids, &pos, &row_seq,
                         &uniforms, &out_log, &step_counter, &pval, &pidx, &lora_ax, &pack_bad, &cand})
             b->release();
     }
@@ -606,7 +608,7 @@ bool stream_geometry(const mc_llama* m, uint32_t rows, stream_geom& g)
     const mc_llama_config& c = m->cfg;
     const uint32_t kmax = std::max(std::max(c.dim, m->Hl * c.head_dim), m->Fl);
     g.act_pitch = kmax * 2 + kStPad;
-    const size_t attn_scratch = (size_t(3) * c.head_dim + 2048 + (c.max_seq_len + kStSplits - 1) / kStSplits + 8) * sizeof(float);
+    const size_t attn_scratch = (size_t(5) * c.head_dim + 1024 + c.max_seq_len + 8) * sizeof(float);
     g.act_bytes = uint32_t((std::max(size_t(rows) * g.act_pitch, attn_scratch) + 127) & ~size_t(127));
     const size_t fixed = kStHdrBytes + kStRedBytes + g.act_bytes;
     const size_t cap = 232448; // 227 KiB of dynamic shared memory per CTA on sm_100
@@ -625,7 +627,8 @@ bool stream_eligible(mc_llama* m, uint32_t n, const mc_sampler_config& sc)
     if (m->st_ok < 0) {
         m->st_ok = 0;
         stream_geom g;
-        const bool shapes = stream_kc(c.dim) && stream_kc(m->Hl * c.head_dim) && stream_kc(m->Fl) && stream_geometry(m, kStMaxRows, g);
+        const bool shapes = stream_kc(c.dim) && stream_kc(m->Hl * c.head_dim) && stream_kc(m->Fl) && c.dim <= 4096 && m->Fl % 2 == 0 && m->Vl % 2 == 0 &&
+                            m->dev->prop.multiProcessorCount <= 256 && stream_geometry(m, kStMaxRows, g);
         if (shapes) {
             if (cudaFuncSetAttribute(decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) == cudaSuccess) {
                 int occ = 0, coop = 0;
@@ -644,40 +647,55 @@ void launch_stream(mc_llama* m, launcher& L, uint32_t rows, int advance, uint32_
 {
     const mc_llama_config& c = m->cfg;
     const uint32_t D = c.dim, hd = c.head_dim, QO = m->Hl * hd, QKVN = (m->Hl + 2 * m->KVl) * hd;
+    const uint32_t phases = c.n_layers * 5 + 1;
     MC_REQUIRE(steps == 1 || advance, "stream kernel: several steps per launch need the sampled id fed back");
+    MC_REQUIRE(uint64_t(steps) * phases + 2 < 65536, "stream kernel: too many steps for one launch");
     stream_geom geo;
     MC_REQUIRE(stream_geometry(m, rows, geo), "stream kernel: activation rows do not fit in shared memory");
+    // tags of a launch are (sequence number << 16) + phase + 1: never 0, unique until the 16-bit sequence wraps
+    if ((++m->st_seq & 0xffffu) == 0) {
+        MC_CUDA_CHECK(cudaMemsetAsync(m->st_ll.p, 0, m->st_ll.bytes, L.s));
+        ++m->st_seq;
+    }
     st_params P{};
     const dlayer& l0 = m->layers[0];
-    auto gemv = [&](const void* W, const dbuf* norm, const uint16_t* x, uint16_t* y, const uint16_t* res, uint32_t N, uint32_t K, uint32_t ldx, uint32_t ldy,
-                    int pro, int epi, int in_kind, int layered) {
+    uint64_t* ll = m->st_ll.as<uint64_t>();
+    uint64_t *x_ll = ll + m->st_off[0], *h_ll = ll + m->st_off[1], *z_ll = ll + m->st_off[2], *qkv_ll = ll + m->st_off[3], *attn_ll = ll + m->st_off[4];
+    auto gemv = [&](const void* W, const dbuf* norm, const uint64_t* in_ll, uint64_t* out_ll, const uint64_t* res_ll, uint32_t N, uint32_t K, int pro, int epi,
+                    int layered) {
         st_gemv g{};
-        g.W = static_cast<const uint16_t*>(W), g.norm_w = norm ? norm->as<uint16_t>() : nullptr, g.x = x, g.y = y, g.res = res;
-        g.N = N, g.K = K, g.KC = stream_kc(K), g.ldx = ldx, g.ldy = ldy, g.pro = pro, g.epi = epi, g.in_kind = in_kind, g.layered = layered;
+        g.W = static_cast<const uint16_t*>(W), g.norm_w = norm ? norm->as<uint16_t>() : nullptr, g.in_ll = in_ll, g.out_ll = out_ll, g.res_ll = res_ll;
+        g.N = N, g.K = K, g.KC = stream_kc(K), g.gran = epi == EPI_SWIGLU ? 4 : 2, g.pro = pro, g.epi = epi, g.layered = layered;
         return g;
     };
-    uint16_t *x = m->x.as<uint16_t>(), *h = m->h.as<uint16_t>(), *z = m->z.as<uint16_t>(), *qkv = m->qkv.as<uint16_t>();
-    P.g[0] = gemv(l0.wqkv.w.p, &l0.attn_norm, x, qkv, nullptr, QKVN, D, D, QKVN, PRO_RMSNORM, EPI_NONE, ST_IN_ROWS, 1);
-    P.g[1] = gemv(l0.wo.w.p, nullptr, nullptr, h, x, D, QO, QO, D, PRO_NONE, EPI_RESIDUAL, ST_IN_ATTN, 1);
-    P.g[2] = gemv(l0.w13.w.p, &l0.ffn_norm, h, z, nullptr, 2 * m->Fl, D, D, m->Fl, PRO_RMSNORM, EPI_SWIGLU, ST_IN_ROWS, 1);
-    P.g[3] = gemv(l0.w2.w.p, nullptr, z, x, h, D, m->Fl, m->Fl, D, PRO_NONE, EPI_RESIDUAL, ST_IN_ROWS, 1);
-    P.g[4] = gemv(m->tok.w.p, &m->norm, x, m->logits.as<uint16_t>(), nullptr, m->Vl, D, D, m->Vl, PRO_RMSNORM, EPI_NONE, ST_IN_ROWS, 0);
+    P.g[0] = gemv(l0.wqkv.w.p, &l0.attn_norm, x_ll, qkv_ll, nullptr, QKVN, D, PRO_RMSNORM, EPI_NONE, 1);
+    P.g[1] = gemv(l0.wo.w.p, nullptr, attn_ll, h_ll, x_ll, D, QO, PRO_NONE, EPI_RESIDUAL, 1);
+    P.g[2] = gemv(l0.w13.w.p, &l0.ffn_norm, h_ll, z_ll, nullptr, 2 * m->Fl, D, PRO_RMSNORM, EPI_SWIGLU, 1);
+    P.g[3] = gemv(l0.w2.w.p, nullptr, z_ll, x_ll, h_ll, D, m->Fl, PRO_NONE, EPI_RESIDUAL, 1);
+    P.g[4] = gemv(m->tok.w.p, &m->norm, x_ll, nullptr, nullptr, m->Vl, D, PRO_RMSNORM, EPI_NONE, 0);
+    P.g[4].y = m->logits.as<uint16_t>();
     P.layer_stride = m->layer_stride, P.kv_layer_stride = kv_layer_elems(m);
     P.n_layers = c.n_layers, P.rows = rows, P.steps = steps, P.n_stages = geo.n_stages, P.act_pitch = geo.act_pitch, P.act_bytes = geo.act_bytes;
+    static const int env_pf = getenv("MC_STREAM_PF") ? atoi(getenv("MC_STREAM_PF")) : 0;
+    static const int env_pfm = getenv("MC_STREAM_PF_MODE") ? atoi(getenv("MC_STREAM_PF_MODE")) : 0;
+    P.pf_tiles = uint32_t(env_pf), P.pf_mode = uint32_t(env_pfm);
+    P.tag_base = m->st_seq << 16;
+    static const int env_ns = getenv("MC_STREAM_POLL_NS") ? atoi(getenv("MC_STREAM_POLL_NS")) : 0;
+    P.poll_ns = uint32_t(env_ns);
     P.eps = c.norm_eps;
-    P.qkv = qkv, P.kcache = m->kcache.as<uint16_t>(), P.vcache = m->vcache.as<uint16_t>(), P.fcos = m->fcos.as<float>(), P.fsin = m->fsin.as<float>();
+    P.qkv_ll = qkv_ll, P.sc_ll = ll + m->st_off[5], P.attn_ll = attn_ll, P.sc_words = m->st_sc_words;
+    P.kcache = m->kcache.as<uint16_t>(), P.vcache = m->vcache.as<uint16_t>(), P.fcos = m->fcos.as<float>(), P.fsin = m->fsin.as<float>();
     P.row_seq = m->row_seq.as<int32_t>(), P.pos = m->pos.as<int32_t>(), P.ids = m->ids.as<int32_t>();
     P.n_heads = m->Hl, P.n_kv_heads = m->KVl, P.head_dim = hd, P.max_seq = c.max_seq_len, P.vocab = c.vocab, P.scale = m->scale_bf16;
-    P.xsum = m->xsum.as<float>(), P.acnt = m->acnt.as<unsigned>(), P.opart = m->opart.as<float>();
-    P.embed_table = m->tok.w.as<uint16_t>(), P.embed_out = x;
-    P.bar = m->bar.as<unsigned>(), P.step_done = m->step_done.as<unsigned>(), P.err = m->errflag.as<int>();
-    P.am_val = m->pval.as<float>(), P.am_idx = m->pidx.as<int32_t>(), P.out_log = m->out_log.as<int32_t>();
-    P.step_counter = m->step_counter.as<int32_t>(), P.advance = advance;
+    P.embed_table = m->tok.w.as<uint16_t>();
+    P.am_ll = ll + m->st_off[6], P.ids_ll = ll + m->st_off[7];
+    P.out_log = m->out_log.as<int32_t>(), P.step_counter = m->step_counter.as<int32_t>(), P.advance = advance;
+    P.err = m->errflag.as<int>();
     P.timing = m->st_timing_on ? m->st_timing.as<unsigned long long>() : nullptr;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(m->st_grid), cfg.blockDim = dim3(kStThreads), cfg.dynamicSmemBytes = geo.smem, cfg.stream = L.s;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative; // all CTAs must be co-resident for the grid barriers
+    attr[0].id = cudaLaunchAttributeCooperative; // the CTAs poll each other's output: all of them must be co-resident
     attr[0].val.cooperative = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
     L.mark();
@@ -1097,13 +1115,16 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
     m->x.alloc(size_t(R) * D * 2), m->h.alloc(size_t(R) * D * 2);
     m->q.alloc(size_t(R) * m->Hl * hd * 2), m->attn.alloc(size_t(R) * m->Hl * hd * 2);
     m->z.alloc(size_t(R) * m->Fl * 2);
-    m->qkv.alloc(size_t(kStMaxRows) * QKVN * 2);
-    m->opart.alloc(size_t(kStMaxRows) * kStSplits * QOl * sizeof(float));
-    m->xsum.alloc(size_t(kStMaxRows) * m->Hl * kStSplits * sizeof(float));
-    m->acnt.alloc(size_t(kStMaxRows) * m->Hl * sizeof(unsigned));
-    m->step_done.alloc(256);
-    MC_CUDA_CHECK(cudaMemset(m->acnt.p, 0, m->acnt.bytes));
-    MC_CUDA_CHECK(cudaMemset(m->step_done.p, 0, 256));
+    {
+        // tagged-word exchange buffers of the streaming kernel (8 bytes per word = two bf16 + tag)
+        const size_t R8 = kStMaxRows;
+        m->st_sc_words = (c.max_seq_len + 1) / 2 + 1;
+        const size_t words[8] = {R8 * D / 2, R8 * D / 2, R8 * m->Fl / 2, R8 * QKVN / 2, R8 * QOl / 2, R8 * m->Hl * m->st_sc_words, R8 * 256 * 2, 64};
+        size_t total = 0;
+        for (int i = 0; i < 8; i++) m->st_off[i] = total, total += (words[i] + 31) & ~size_t(31);
+        m->st_ll.alloc(total * 8);
+        MC_CUDA_CHECK(cudaMemset(m->st_ll.p, 0, m->st_ll.bytes));
+    }
     m->logits.alloc(size_t(R) * m->Vl * 2);
     if (c.tp_world > 1) m->logits_tmp.alloc(size_t(kMaxMB) * m->Vl * 2);
     m->hidden_save.alloc(size_t(c.n_seqs) * D * 2);
@@ -1374,7 +1395,8 @@ mc_status mc_llama_decode_loop(mc_llama* m, uint32_t n, const int32_t* first_ids
     if (stream) {
         // the persistent kernel loops over the steps itself: the weight stream of step i+1 starts under the sampler tail of step i
         launcher L{m, s, false};
-        launch_stream(m, L, n, 1, steps);
+        const uint32_t per_launch = std::max<uint32_t>(1, std::min<uint32_t>(512, 60000 / (m->cfg.n_layers * 5 + 1)));
+        for (uint32_t done = 0; done < steps; done += per_launch) launch_stream(m, L, n, 1, std::min(per_launch, steps - done));
         m->launches_per_step = 1;
     } else {
         for (uint32_t i = 0; i < steps; i++) run_decode_step(m, n, sc, 1);
@@ -1438,35 +1460,37 @@ mc_status mc_llama_cache(mc_llama* m, uint32_t seq, uint32_t layer, int which, u
 // every launch: us[i] = time from launch i to launch i+1 (the last entry ends at step completion).
 mc_status mc_llama_profile_step(mc_llama* m, uint32_t n, float* us, uint32_t cap, uint32_t* count)
 {
+    const uint32_t n_rows = n;
     MC_API_BEGIN
     use(m);
     MC_REQUIRE(m->finalized && us && count, "bad arguments");
     MC_REQUIRE(n >= 1 && n <= m->cfg.n_seqs, "profile_step: number of sequences out of range");
     mc_sampler_config sc{};
     if (stream_eligible(m, n, sc)) {
-        // streaming kernel: four stamps of CTA 0 per phase; us[4k..4k+3] = {wait, stage input, consume tiles, until next phase entry}
-        const uint32_t phases = m->cfg.n_layers * 5 + 1;
-        if (!m->st_timing.p) m->st_timing.alloc(size_t(phases + 1) * 4 * 8);
+        // streaming kernel: four globaltimer stamps per (CTA, phase) = phase entry, (unused), input staged, tiles consumed;
+        // us[(cta * phases + k) * 4 + j] = microseconds since the earliest stamp of the launch
+        const uint32_t phases = m->cfg.n_layers * 5 + 1, G = m->st_grid;
+        const size_t n = size_t(G) * phases * 4;
+        if (!m->st_timing.p) m->st_timing.alloc(n * 8);
         MC_CUDA_CHECK(cudaMemsetAsync(m->st_timing.p, 0, m->st_timing.bytes, m->dev->stream));
         MC_CUDA_CHECK(cudaMemsetAsync(m->step_counter.p, 0, 4, m->dev->stream));
         m->st_timing_on = true;
         launcher L{m, m->dev->stream, false};
         try {
-            launch_stream(m, L, n, 0, 1);
+            launch_stream(m, L, n_rows, 0, 1);
         } catch (...) {
             m->st_timing_on = false;
             throw;
         }
         m->st_timing_on = false;
         MC_CUDA_CHECK(cudaStreamSynchronize(m->dev->stream));
-        std::vector<unsigned long long> t(size_t(phases + 1) * 4);
-        MC_CUDA_CHECK(cudaMemcpy(t.data(), m->st_timing.p, t.size() * 8, cudaMemcpyDeviceToHost));
-        *count = phases * 4;
-        for (uint32_t k = 0; k < phases; k++) {
-            if (k * 4 + 3 >= cap) break;
-            for (int j = 0; j < 3; j++) us[k * 4 + j] = float(t[k * 4 + j + 1] - t[k * 4 + j]) * 1e-3f;
-            us[k * 4 + 3] = k + 1 < phases ? float(t[(k + 1) * 4] - t[k * 4 + 3]) * 1e-3f : 0.0f;
-        }
+        std::vector<unsigned long long> t(n);
+        MC_CUDA_CHECK(cudaMemcpy(t.data(), m->st_timing.p, n * 8, cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull;
+        for (auto v : t)
+            if (v && v < t0) t0 = v;
+        *count = uint32_t(std::min<size_t>(n, cap));
+        for (size_t i = 0; i < n && i < cap; i++) us[i] = t[i] ? float(t[i] - t0) * 1e-3f : 0.0f;
         return MC_OK;
     }
     if (n <= uint32_t(kMaxMB) && m->cfg.tp_world == 1 && (m->cfg.flags & MC_LLAMA_MEGAKERNEL)) {

@@ -32,7 +32,8 @@ namespace mc {
 
 constexpr int kStWarps = 8;                           // consumer warps
 constexpr int kStConsumers = kStWarps * 32;           // 256 consumer threads
-constexpr int kStThreads = kStConsumers + 32;         // + one producer warp
+constexpr int kStEpiThreads = 64;                     // two epilogue warps: join the k-slices, finish and publish the outputs
+constexpr int kStThreads = kStConsumers + kStEpiThreads + 32; // + one producer warp
 constexpr int kStTileRows = 16;                       // weight rows per tile (the m of the mma)
 constexpr int kStMaxKC = 1024;                        // k elements per tile row
 constexpr int kStPad = 64;                            // bytes of padding per staged row
@@ -40,19 +41,24 @@ constexpr int kStStageBytes = kStTileRows * (kStMaxKC * 2 + kStPad);
 constexpr int kStMaxStages = 8;
 constexpr int kStSplits = 4;                          // CTAs per (row, head) in the attention phase
 constexpr int kStMaxRows = 8;                         // activation rows (the n of the mma)
-constexpr int kStHdrBytes = 512;                      // mbarriers + flags + reduce scratch
-constexpr int kStRedBytes = 2 * kStWarps * 16 * 8 * 4; // double-buffered cross-warp partials
+constexpr int kStHdrBytes = 896;                      // mbarriers + flags + reduce scratch
+constexpr int kStRedBufs = 3;                         // cross-warp partial buffers in flight between the mma and the epilogue warps
+constexpr int kStRedBytes = kStRedBufs * kStWarps * 16 * 8 * 4;
 
-enum { ST_IN_ROWS = 0, ST_IN_EMBED = 1, ST_IN_ATTN = 2 };
-
+// Activations travel between CTAs as TAGGED WORDS: one 8-byte word = two bf16 values (low half) + a 32-bit epoch tag
+// (high half), written with one 8-byte store and read with 8/16-byte volatile loads.  The tag is unique per
+// (launch, step, phase), so a consumer simply polls the data it needs until the tags match: no release fence, no
+// arrival counter, no separate flag round trip (the scheme of low-latency collectives).  Every GEMV phase needs the whole
+// input vector, i.e. data from every CTA, so the polling doubles as the phase barrier.
 struct st_gemv {
     const uint16_t* W;       // [N, K] bf16 row-major; layer l adds l * layer_stride bytes when `layered`
     const uint16_t* norm_w;  // PRO_RMSNORM: [K] (same layer stride)
-    const uint16_t* x;       // ST_IN_ROWS: [rows, ldx]
-    uint16_t* y;             // [rows, ldy]
-    const uint16_t* res;     // EPI_RESIDUAL: [rows, ldy]
-    uint32_t N, K, KC, ldx, ldy;
-    int32_t pro, epi, in_kind, layered;
+    const uint64_t* in_ll;   // tagged input rows [rows][K/2] (null: embedding gather)
+    uint64_t* out_ll;        // tagged output rows: [rows][N/2], EPI_SWIGLU [rows][N/4]; null for the head
+    const uint64_t* res_ll;  // EPI_RESIDUAL: [rows][N/2], written earlier by this same CTA
+    uint16_t* y;             // head only: plain bf16 logits [rows][N]
+    uint32_t N, K, KC, gran; // gran = row granularity of the CTA split (2; 4 for the gate/up pairs)
+    int32_t pro, epi, layered;
 };
 
 struct st_params {
@@ -60,37 +66,37 @@ struct st_params {
     size_t layer_stride;     // bytes between consecutive layers in the weight arena
     size_t kv_layer_stride;  // elements between consecutive layers in the KV cache
     uint32_t n_layers, rows, steps, n_stages;
+    uint32_t pf_tiles;       // tiles of L2 prefetch distance ahead of the ring (0 = none)
+    uint32_t pf_mode;        // 0: prefetch.global.L2 per line, 1: cp.async.bulk.prefetch.L2 per row
     uint32_t act_pitch;      // bytes between staged activation rows
     uint32_t act_bytes;
+    uint32_t tag_base;       // tags of this launch are tag_base + phase + 1
+    uint32_t poll_ns;
     float eps;
     // attention
-    const uint16_t* qkv;     // [rows, (H + 2 KV) * hd]: r(x.W^T), not yet rotated
+    const uint64_t* qkv_ll;  // [rows][(H + 2 KV) * hd / 2]: r(x.W^T), not yet rotated
+    uint64_t* sc_ll;         // [rows * H][sc_words]: scores r(r(q.k) * scale) of all positions
+    uint64_t* attn_ll;       // [rows][H * hd / 2]
+    uint32_t sc_words;
     uint16_t* kcache;        // [layer][n_seqs, KV, S, hd]
     uint16_t* vcache;
     const float* fcos;       // [2S, hd/2]
     const float* fsin;
     const int32_t* row_seq;  // [rows]
-    int32_t* pos;            // [rows], advanced by the sampler tail
-    int32_t* ids;            // [rows], next input ids
+    int32_t* pos;            // [rows]: positions of the first step; advanced by `steps` at the end when `advance`
+    int32_t* ids;            // [rows]: ids of the first step; the last sampled ids at the end when `advance`
     uint32_t n_heads, n_kv_heads, head_dim, max_seq, vocab;
     float scale;             // r(1/sqrt(hd)) (nn/attention.h:88,115)
-    float* xsum;             // [rows * H][4] exp-sums of the splits
-    unsigned* acnt;          // [rows * H] arrival counters of the split groups
-    float* opart;            // [rows][4][H * hd] fp32 partial attention outputs
     // embedding
     const uint16_t* embed_table;
-    uint16_t* embed_out;     // x rows (the first residual)
-    // grid synchronisation
-    unsigned* bar;           // phase arrivals (monotonic inside a launch, reset by the last phase)
-    unsigned* step_done;     // steps completed inside this launch
-    int* err;
     // sampler tail
-    float* am_val;           // [rows][G]
-    int32_t* am_idx;
+    uint64_t* am_ll;         // [rows][G][2]: per-CTA argmax partial {value bits, index}
+    uint64_t* ids_ll;        // [rows]: sampled id of the step, tagged with the head phase
     int32_t* out_log;
     int32_t* step_counter;
     int32_t advance;
-    unsigned long long* timing; // diagnostics (nullable): 4 globaltimer stamps of CTA 0 per phase
+    int* err;
+    unsigned long long* timing; // diagnostics (nullable): 4 globaltimer stamps per (CTA, phase)
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------------------------------
@@ -160,6 +166,8 @@ __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;"
 // shared-memory carve-up of one CTA
 struct st_ctx {
     uint32_t full0, empty0;   // shared addresses of full[kStMaxStages], empty[kStMaxStages]
+    uint32_t rdy0, fre0;      // shared addresses of ready[kStRedBufs] (partials written), free[kStRedBufs] (partials consumed)
+    float* escr;              // [128] scratch of the epilogue warps
     volatile int* dead;       // set when a wait timed out somewhere: every later wait falls through
     float* scr;               // [16] block-reduce scratch
     float* red;               // [2][8 warps][16 rows][8 cols]
@@ -167,6 +175,7 @@ struct st_ctx {
     uint32_t act_addr;        // shared address of act
     uint32_t ring_addr;       // shared address of stage 0
     int* err;
+    uint32_t poll_ns;         // back-off between failed polls of a tagged word (all CTAs poll the same words)
 };
 
 // bounded waits: a lost arrival must end in an error code, never in a hung GPU
@@ -190,41 +199,51 @@ __device__ __forceinline__ void st_mbar_wait(const st_ctx& c, uint32_t a, uint32
         }
     }
 }
-__device__ __forceinline__ void st_spin_ge(const st_ctx& c, const unsigned* addr, unsigned target)
+// ---- tagged words ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_ll_store(uint64_t* p, uint32_t payload, uint32_t tag)
 {
-    if (*c.dead) return;
-    unsigned spins = 0;
-    for (;;) {
-        unsigned v;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
-        if (int(v - target) >= 0) return;
-        if ((++spins & 1023u) == 0) {
-            if (*reinterpret_cast<volatile int*>(c.err) != 0) {
-                *c.dead = 1;
-                return;
-            }
-            if (spins > (1u << 22)) {
-                atomicExch(c.err, 1);
-                *c.dead = 1;
-                return;
-            }
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"((uint64_t(tag) << 32) | payload) : "memory");
+}
+__device__ __forceinline__ void st_ll_load2(const uint64_t* p, uint64_t& a, uint64_t& b)
+{
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ uint64_t st_ll_load1(const uint64_t* p)
+{
+    uint64_t a;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
+    return a;
+}
+// one failed poll: returns true when the caller should give up (another wait timed out, or this one did)
+__device__ __forceinline__ bool st_poll_backoff(const st_ctx& c, unsigned& spins)
+{
+    if (*c.dead) return true;
+    if (c.poll_ns) __nanosleep(c.poll_ns);
+    if ((++spins & 1023u) == 0) {
+        if (*reinterpret_cast<volatile int*>(c.err) != 0) {
+            *c.dead = 1;
+            return true;
+        }
+        if (spins > (1u << 21)) {
+            atomicExch(c.err, 1);
+            *c.dead = 1;
+            return true;
         }
     }
+    return false;
 }
-// consumers: thread 0 waits for `target` arrivals, then everybody passes the CTA barrier
-__device__ __forceinline__ void st_grid_wait(const st_ctx& c, const unsigned* counter, unsigned target)
+__device__ __forceinline__ uint32_t st_poll1(const st_ctx& c, const uint64_t* p, uint32_t tag)
 {
-    if (threadIdx.x == 0) st_spin_ge(c, counter, target);
-    consumer_bar();
-}
-__device__ __forceinline__ void st_grid_arrive(unsigned* bar)
-{
-    consumer_bar();
-    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    unsigned spins = 0;
+    for (;;) {
+        const uint64_t a = st_ll_load1(p);
+        if (uint32_t(a >> 32) == tag) return uint32_t(a);
+        if (st_poll_backoff(c, spins)) return 0;
+    }
 }
 __device__ __forceinline__ void st_stamp(unsigned long long* t, unsigned idx)
 {
-    if (t && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (t && (threadIdx.x == 0 || threadIdx.x == kStConsumers)) {
         unsigned long long v;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
         t[idx] = v;
@@ -242,13 +261,14 @@ __device__ __forceinline__ float st_block_sum(float v, float* scr)
     consumer_bar();
     return t;
 }
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) { return uint32_t(f32_to_bf16_bits(lo)) | (uint32_t(f32_to_bf16_bits(hi)) << 16); }
 
-// rows [rb, re) of an N-row matrix owned by this CTA (units of two rows, balanced to +-1 unit)
-__device__ __forceinline__ void st_my_rows(uint32_t N, uint32_t& rb, uint32_t& re)
+// rows [rb, re) of an N-row matrix owned by this CTA (units of `gran` rows, balanced to +-1 unit)
+__device__ __forceinline__ void st_my_rows(uint32_t N, uint32_t gran, uint32_t& rb, uint32_t& re)
 {
-    const uint64_t units = N >> 1;
-    rb = uint32_t(units * blockIdx.x / gridDim.x) * 2;
-    re = uint32_t(units * (blockIdx.x + 1) / gridDim.x) * 2;
+    const uint64_t units = N / gran;
+    rb = uint32_t(units * blockIdx.x / gridDim.x) * gran;
+    re = uint32_t(units * (blockIdx.x + 1) / gridDim.x) * gran;
 }
 
 struct st_pipe {
@@ -259,109 +279,198 @@ struct st_pipe {
     }
 };
 
-// ---- producer: the weight tiles of one GEMV phase ---------------------------------------------------------------------
-__device__ __forceinline__ void st_produce_gemv(const st_params& P, const st_gemv& g, uint32_t li, const st_ctx& c, st_pipe& pp, uint64_t policy)
+// ---- producer: the static schedule of weight tiles of this CTA ----------------------------------------------------------
+// A tile = up to 16 consecutive weight rows x KC k of one GEMV phase.  The iterator enumerates the tiles of this CTA in
+// consumption order over all phases, layers and steps of the launch.  (A second iterator can run `pf_tiles` ahead and
+// only ask the L2 for the rows; measured on B200 this LOWERS throughput - demand loads land on in-flight fills - so it
+// is off by default and kept as an experiment knob.)
+struct st_tile {
+    const char* src;      // first row chunk
+    size_t row_stride;    // bytes between consecutive rows in global memory
+    uint32_t nr, row_bytes, pitch;
+};
+struct st_tile_iter {
+    uint32_t step = 0, li = 0, gi = 0, r0 = 0, re = 0, kc = 0;
+    bool ranged = false;
+    __device__ __forceinline__ bool next(const st_params& P, st_tile& t)
+    {
+        for (;;) {
+            if (step >= P.steps) return false;
+            const st_gemv& g = P.g[gi];
+            if (!ranged) {
+                st_my_rows(g.N, g.gran, r0, re);
+                kc = 0, ranged = true;
+            }
+            if (r0 < re) {
+                const char* W = reinterpret_cast<const char*>(g.W) + (g.layered ? size_t(li) * P.layer_stride : 0);
+                t.nr = min(uint32_t(kStTileRows), re - r0);
+                t.src = W + (size_t(r0) * g.K + kc) * 2;
+                t.row_stride = size_t(g.K) * 2, t.row_bytes = g.KC * 2, t.pitch = g.KC * 2 + kStPad;
+                kc += g.KC;
+                if (kc >= g.K) kc = 0, r0 += kStTileRows;
+                return true;
+            }
+            ranged = false;
+            if (gi == 4) gi = 0, li = 0, step++;
+            else if (gi == 3) {
+                li++;
+                gi = li == P.n_layers ? 4 : 0;
+            } else gi++;
+        }
+    }
+};
+__device__ __forceinline__ void st_prefetch_tile(const st_tile& t, uint32_t lane, uint32_t mode)
+{
+    if (mode == 1) {
+        if (lane < t.nr) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(t.src + size_t(lane) * t.row_stride), "r"(t.row_bytes) : "memory");
+    } else {
+        const uint32_t lpr = t.row_bytes >> 7, lines = t.nr * lpr;
+        for (uint32_t i = lane; i < lines; i += 32) {
+            const uint32_t r = i / lpr, o = (i - r * lpr) << 7;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(t.src + size_t(r) * t.row_stride + o) : "memory");
+        }
+    }
+}
+__device__ __forceinline__ void st_producer(const st_params& P, const st_ctx& c)
 {
     const uint32_t lane = threadIdx.x & 31;
-    const char* W = reinterpret_cast<const char*>(g.W) + (g.layered ? size_t(li) * P.layer_stride : 0);
-    const uint32_t pitch = g.KC * 2 + kStPad, row_bytes = g.KC * 2;
-    uint32_t rb, re;
-    st_my_rows(g.N, rb, re);
-    for (uint32_t r0 = rb; r0 < re; r0 += kStTileRows) {
-        const uint32_t nr = min(uint32_t(kStTileRows), re - r0);
-        for (uint32_t kc = 0; kc < g.K; kc += g.KC) {
-            st_mbar_wait(c, c.empty0 + pp.stage * 8, pp.parity ^ 1u);
-            const uint32_t full = c.full0 + pp.stage * 8;
-            if (lane == 0) mbar_expect_tx(full, nr * row_bytes);
-            __syncwarp();
-            if (lane < nr)
-                bulk_g2s(c.ring_addr + pp.stage * kStStageBytes + lane * pitch, W + (size_t(r0 + lane) * g.K + kc) * 2, row_bytes, full, policy);
-            pp.advance(P.n_stages);
-        }
+    const uint64_t policy = policy_evict_first();
+    st_pipe pp{0, 0};
+    st_tile_iter ld, pf;
+    st_tile t, tp;
+    for (uint32_t i = 0; i < P.pf_tiles; i++)
+        if (pf.next(P, tp)) st_prefetch_tile(tp, lane, P.pf_mode);
+    while (ld.next(P, t)) {
+        if (P.pf_tiles && pf.next(P, tp)) st_prefetch_tile(tp, lane, P.pf_mode);
+        st_mbar_wait(c, c.empty0 + pp.stage * 8, pp.parity ^ 1u);
+        const uint32_t full = c.full0 + pp.stage * 8;
+        if (lane == 0) mbar_expect_tx(full, t.nr * t.row_bytes);
+        __syncwarp();
+        if (lane < t.nr) bulk_g2s(c.ring_addr + pp.stage * kStStageBytes + lane * t.pitch, t.src + size_t(lane) * t.row_stride, t.row_bytes, full, policy);
+        pp.advance(P.n_stages);
     }
 }
 
 // ---- consumers: stage the activation rows of a GEMV phase ----------------------------------------------------------------
-__device__ __forceinline__ void st_stage_input(const st_params& P, const st_gemv& g, uint32_t li, const st_ctx& c)
+// Polls the tagged input rows (or gathers the embedding rows), applies RMSNorm when the phase has one, and leaves the rows
+// as bf16 in shared memory.  `xres_ll` (first phase of a step only): this CTA also publishes the raw embedding values of
+// the rows it will later own in the wo phase - they are the first residual.
+__device__ __forceinline__ void st_stage_input(const st_params& P, const st_gemv& g, uint32_t li, const st_ctx& c, bool embed, uint32_t step, uint32_t tag_in,
+                                               uint32_t tag_out)
 {
-    const uint32_t tid = threadIdx.x, K = g.K;
+    constexpr int NB = 4; // tagged 16-byte loads in flight per thread
+    const uint32_t tid = threadIdx.x, K = g.K, n_words = K >> 1;
     const uint16_t* norm_w = g.pro == PRO_RMSNORM ? reinterpret_cast<const uint16_t*>(reinterpret_cast<const char*>(g.norm_w) + (g.layered ? size_t(li) * P.layer_stride : 0)) : nullptr;
+    // norm weights of this thread's elements: requested before anything is polled
+    uint2 nw[NB];
+    if (norm_w) {
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+            const uint32_t w = tid * 2 + j * (kStConsumers * 2);
+            if (w < n_words) nw[j] = *reinterpret_cast<const uint2*>(norm_w + w * 2);
+        }
+    }
+    int32_t* sids = reinterpret_cast<int32_t*>(c.scr + 8);
+    if (embed) {
+        if (tid < P.rows) {
+            int32_t id = step == 0 ? P.ids[tid] : int32_t(st_poll1(c, P.ids_ll + tid, tag_in));
+            if (id < 0 || uint32_t(id) >= P.vocab) id = 0;
+            sids[tid] = id;
+        }
+        consumer_bar();
+    }
     for (uint32_t m = 0; m < P.rows; m++) {
         uint16_t* dst = reinterpret_cast<uint16_t*>(c.act + size_t(m) * P.act_pitch);
         float part = 0.0f;
-        if (g.in_kind == ST_IN_ATTN) {
-            // o = r(sum_t p[t] V[t]): the four position splits are joined in split order (nn/attention.h:201-203)
-            const float* src = P.opart + size_t(m) * kStSplits * K;
-            for (uint32_t k = tid * 4; k < K; k += kStConsumers * 4) {
-                float4 a = ldcg_f4(src + k);
-#pragma unroll
-                for (int s = 1; s < kStSplits; s++) {
-                    const float4 b = ldcg_f4(src + size_t(s) * K + k);
-                    a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
-                }
-                uint2 o;
-                o.x = uint32_t(f32_to_bf16_bits(a.x)) | (uint32_t(f32_to_bf16_bits(a.y)) << 16);
-                o.y = uint32_t(f32_to_bf16_bits(a.z)) | (uint32_t(f32_to_bf16_bits(a.w)) << 16);
-                *reinterpret_cast<uint2*>(dst + k) = o;
-            }
-        } else {
-            const uint16_t* xr;
-            if (g.in_kind == ST_IN_EMBED) {
+        for (uint32_t w0 = tid * 2; w0 < n_words; w0 += NB * kStConsumers * 2) {
+            uint64_t a[NB], b[NB];
+            if (embed) {
                 // embedding gather fused into the first phase (kernel/embedding.metal:38-66)
-                int32_t id = ldcg_s32(P.ids + m);
-                if (id < 0 || uint32_t(id) >= P.vocab) id = 0;
-                xr = P.embed_table + size_t(id) * K;
+                const uint16_t* xr = P.embed_table + size_t(sids[m]) * K;
+#pragma unroll
+                for (int j = 0; j < NB; j++) {
+                    const uint32_t w = w0 + j * (kStConsumers * 2);
+                    if (w < n_words) {
+                        const uint2 v = *reinterpret_cast<const uint2*>(xr + w * 2);
+                        a[j] = v.x, b[j] = v.y;
+                    }
+                }
             } else {
-                xr = g.x + size_t(m) * g.ldx;
+                const uint64_t* src = g.in_ll + size_t(m) * n_words;
+#pragma unroll
+                for (int j = 0; j < NB; j++) {
+                    const uint32_t w = w0 + j * (kStConsumers * 2);
+                    if (w < n_words) st_ll_load2(src + w, a[j], b[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < NB; j++) {
+                    const uint32_t w = w0 + j * (kStConsumers * 2);
+                    if (w < n_words) {
+                        unsigned spins = 0;
+                        while (uint32_t(a[j] >> 32) != tag_in || uint32_t(b[j] >> 32) != tag_in) {
+                            if (st_poll_backoff(c, spins)) break;
+                            st_ll_load2(src + w, a[j], b[j]);
+                        }
+                    }
+                }
             }
-            for (uint32_t k = tid * 8; k < K; k += kStConsumers * 8) {
-                const uint4 v = ldcg128(xr + k);
-                *reinterpret_cast<uint4*>(dst + k) = v;
-                if (g.in_kind == ST_IN_EMBED && blockIdx.x == 0) *reinterpret_cast<uint4*>(P.embed_out + size_t(m) * K + k) = v;
-                if (g.pro == PRO_RMSNORM) {
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                const uint32_t w = w0 + j * (kStConsumers * 2);
+                if (w < n_words) {
+                    const uint32_t lo = uint32_t(a[j]), hi = uint32_t(b[j]);
+                    *reinterpret_cast<uint2*>(dst + w * 2) = make_uint2(lo, hi);
                     float f;
-                    f = bf_lo(v.x), part = fmaf(f, f, part);
-                    f = bf_hi(v.x), part = fmaf(f, f, part);
-                    f = bf_lo(v.y), part = fmaf(f, f, part);
-                    f = bf_hi(v.y), part = fmaf(f, f, part);
-                    f = bf_lo(v.z), part = fmaf(f, f, part);
-                    f = bf_hi(v.z), part = fmaf(f, f, part);
-                    f = bf_lo(v.w), part = fmaf(f, f, part);
-                    f = bf_hi(v.w), part = fmaf(f, f, part);
+                    f = bf_lo(lo), part = fmaf(f, f, part);
+                    f = bf_hi(lo), part = fmaf(f, f, part);
+                    f = bf_lo(hi), part = fmaf(f, f, part);
+                    f = bf_hi(hi), part = fmaf(f, f, part);
                 }
             }
         }
         if (g.pro == PRO_RMSNORM) {
-            // n = r((0 + w) * x * rsqrt(mean(x^2) + eps))  (kernel/rmsnorm.metal:53-89); each thread re-reads its own elements
+            // n = r((0 + w) * x * rsqrt(mean(x^2) + eps))  (kernel/rmsnorm.metal:53-89)
             const float total = st_block_sum(part, c.scr);
             const float inv = 1.0f / sqrtf(__fadd_rn(total / float(K), P.eps));
-            for (uint32_t k = tid * 8; k < K; k += kStConsumers * 8) {
-                const uint4 v = *reinterpret_cast<const uint4*>(dst + k);
-                const uint4 gw = *reinterpret_cast<const uint4*>(norm_w + k);
-                uint4 o;
+            if (embed) {
+                // the raw rows are the residual of the first wo phase: publish the part this CTA will need there
+                uint32_t rb, re;
+                st_my_rows(P.g[1].N, P.g[1].gran, rb, re);
+                for (uint32_t w = (rb >> 1) + tid; w < (re >> 1); w += kStConsumers)
+                    st_ll_store(const_cast<uint64_t*>(P.g[1].res_ll) + size_t(m) * (P.g[1].N >> 1) + w, *reinterpret_cast<const uint32_t*>(dst + w * 2), tag_out);
+                consumer_bar();
+            }
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                const uint32_t w = tid * 2 + j * (kStConsumers * 2);
+                if (w < n_words) {
+                    const uint2 v = *reinterpret_cast<const uint2*>(dst + w * 2);
+                    uint2 o;
 #define MC_NORM2(d, vv, gg)                                                                          \
     d = uint32_t(f32_to_bf16_bits(__fmul_rn(__fmul_rn(bf_lo(gg), bf_lo(vv)), inv))) |                \
         (uint32_t(f32_to_bf16_bits(__fmul_rn(__fmul_rn(bf_hi(gg), bf_hi(vv)), inv))) << 16)
-                MC_NORM2(o.x, v.x, gw.x);
-                MC_NORM2(o.y, v.y, gw.y);
-                MC_NORM2(o.z, v.z, gw.z);
-                MC_NORM2(o.w, v.w, gw.w);
+                    MC_NORM2(o.x, v.x, nw[j].x);
+                    MC_NORM2(o.y, v.y, nw[j].y);
 #undef MC_NORM2
-                *reinterpret_cast<uint4*>(dst + k) = o;
+                    *reinterpret_cast<uint2*>(dst + w * 2) = o;
+                }
             }
         }
     }
     consumer_bar();
 }
 
-// greedy argmax state of one epilogue thread (lowest index on ties)
-struct st_best {
-    float v;
-    int32_t i;
+// ---- one GEMV phase: the mma warps ---------------------------------------------------------------------------------------
+// Each of the 8 mma warps multiplies its k-slice of every tile and hands the 16 x 8 partial block to the epilogue warps
+// through one of kStRedBufs buffers (ready / free mbarriers): the mma warps never wait for an epilogue to finish.
+struct st_blk {
+    uint32_t buf, parity; // next partial buffer and the parity of its current use
+    __device__ __forceinline__ void advance()
+    {
+        if (++buf == uint32_t(kStRedBufs)) buf = 0, parity ^= 1u;
+    }
 };
-
-// ---- consumers: one GEMV phase -----------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_consume_gemv(const st_params& P, const st_gemv& g, const st_ctx& c, st_pipe& cp, uint32_t& red_buf, st_best& best, bool track)
+__device__ __forceinline__ void st_mma_gemv(const st_params& P, const st_gemv& g, const st_ctx& c, st_pipe& cp, st_blk& bl)
 {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t gq = lane >> 2, t = lane & 3;
@@ -371,15 +480,9 @@ __device__ __forceinline__ void st_consume_gemv(const st_params& P, const st_gem
     const uint32_t brow = gq < P.rows ? gq : 0;   // batch row of this lane's B fragment (unused columns read row 0)
     const uint32_t b_base = c.act_addr + brow * P.act_pitch + (kw + t * 8) * 2;
     const uint32_t a_off = gq * pitch + (kw + t * 8) * 2;
-    // epilogue role: thread (row, col) of the 16 x 8 output block
-    const uint32_t erow = tid >> 3, ecol = tid & 7;
-    const bool etask = tid < 128 && ecol < P.rows;
     uint32_t rb, re;
-    st_my_rows(g.N, rb, re);
+    st_my_rows(g.N, g.gran, rb, re);
     for (uint32_t r0 = rb; r0 < re; r0 += kStTileRows) {
-        const uint32_t nr = min(uint32_t(kStTileRows), re - r0);
-        float resv = 0.0f;
-        if (g.epi == EPI_RESIDUAL && etask && erow < nr) resv = bf16_bits_to_f32(ldcg_u16(g.res + size_t(ecol) * g.ldy + r0 + erow));
         float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         for (uint32_t kc = 0; kc < g.K; kc += g.KC) {
             st_mbar_wait(c, c.full0 + cp.stage * 8, cp.parity);
@@ -397,104 +500,160 @@ __device__ __forceinline__ void st_consume_gemv(const st_params& P, const st_gem
             if (lane == 0) mbar_arrive(c.empty0 + cp.stage * 8);
             cp.advance(P.n_stages);
         }
-        // join the 8 k-slices in warp order
-        float* rw = c.red + red_buf * (kStWarps * 128) + warp * 128;
+        st_mbar_wait(c, c.fre0 + bl.buf * 8, bl.parity ^ 1u); // the epilogue of the previous use of this buffer is done
+        float* rw = c.red + bl.buf * (kStWarps * 128) + warp * 128;
         *reinterpret_cast<float2*>(rw + gq * 8 + 2 * t) = make_float2(acc[0], acc[1]);
         *reinterpret_cast<float2*>(rw + (gq + 8) * 8 + 2 * t) = make_float2(acc[2], acc[3]);
-        consumer_bar();
-        if (etask && erow < nr && !(g.epi == EPI_SWIGLU && (erow & 1u))) {
-            const float* rr = c.red + red_buf * (kStWarps * 128) + erow * 8 + ecol;
-            float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll
-            for (int w = 0; w < kStWarps; w++) s0 += rr[w * 128];
-            const uint32_t R = r0 + erow;
-            const float y0 = rbf(s0); // the bmm output buffer is T (kernel/bmm.metal:76)
-            if (g.epi == EPI_SWIGLU) {
-                // z = r(silu_T(g) * u), rows (2i, 2i+1) = (w1 row i, w3 row i)  (nn/transformer.h:57-59)
-#pragma unroll
-                for (int w = 0; w < kStWarps; w++) s1 += rr[w * 128 + 8];
-                g.y[size_t(ecol) * g.ldy + (R >> 1)] = f32_to_bf16_bits(__fmul_rn(silu_bf16(y0), rbf(s1)));
-            } else if (g.epi == EPI_RESIDUAL) {
-                // h = r(x + a)  (nn/transformer.h:133,139)
-                g.y[size_t(ecol) * g.ldy + R] = f32_to_bf16_bits(__fadd_rn(resv, y0));
-            } else {
-                g.y[size_t(ecol) * g.ldy + R] = f32_to_bf16_bits(y0);
-                if (track && (y0 > best.v || (y0 == best.v && int32_t(R) < best.i))) best.v = y0, best.i = int32_t(R);
-            }
-        }
-        red_buf ^= 1u;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(c.rdy0 + bl.buf * 8);
+        bl.advance();
     }
 }
 
-// ---- consumers: attention phase ---------------------------------------------------------------------------------------
-// item = (row, head, split): rotate q and the new k (kernel/rope.metal:47-58), append k', v to the cache
-// (nn/cache.h:207-214), s = r(r(q.K[t]) * scale), p = r(exp(s) / sum exp(s)) with the sum joined across the four splits,
-// partial o = sum_t p[t] V[t] over this split's positions.
-template <int HD>
-__device__ __forceinline__ void st_attention(const st_params& P, uint32_t li, uint32_t gstep, const st_ctx& c)
+// greedy argmax state of one epilogue thread (lowest index on ties)
+struct st_best {
+    float v;
+    int32_t i;
+};
+
+// ---- one GEMV phase: the epilogue warps ------------------------------------------------------------------------------------
+// Thread (row group, col) of the 16 x 8 output block joins the 8 k-slices in warp order and finishes `gran` consecutive rows.
+__device__ __forceinline__ void st_epi_gemv(const st_params& P, const st_gemv& g, const st_ctx& c, st_blk& bl, st_best& best, bool is_head, uint32_t tag_out)
 {
-    constexpr int LPP = HD / 8;        // lanes per cached position (16 bytes each)
-    constexpr int SLOTS = kStConsumers / LPP;
-    constexpr int IT = 5;              // position sweeps kept in flight
+    const uint32_t et = threadIdx.x - kStConsumers, lane = et & 31;
+    const uint32_t ecol = et & 7, egrp = et >> 3;
+    const uint32_t erow = egrp * g.gran;
+    const bool etask = erow < uint32_t(kStTileRows) && ecol < P.rows;
+    const uint32_t out_pitch = g.epi == EPI_SWIGLU ? g.N >> 2 : g.N >> 1;
+    uint32_t rb, re;
+    st_my_rows(g.N, g.gran, rb, re);
+    for (uint32_t r0 = rb; r0 < re; r0 += kStTileRows) {
+        const uint32_t nr = min(uint32_t(kStTileRows), re - r0);
+        const bool act = etask && erow < nr;
+        uint32_t resw = 0;
+        if (g.epi == EPI_RESIDUAL && act) resw = uint32_t(st_ll_load1(g.res_ll + size_t(ecol) * out_pitch + ((r0 + erow) >> 1)));
+        st_mbar_wait(c, c.rdy0 + bl.buf * 8, bl.parity);
+        if (act) {
+            const float* rr = c.red + bl.buf * (kStWarps * 128) + erow * 8 + ecol;
+            float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+            for (int w = 0; w < kStWarps; w++) s0 += rr[w * 128], s1 += rr[w * 128 + 8];
+            const uint32_t R = r0 + erow;
+            const float y0 = rbf(s0), y1 = rbf(s1); // the bmm output buffer is T (kernel/bmm.metal:76)
+            if (g.epi == EPI_SWIGLU) {
+                // z = r(silu_T(g) * u), rows (2i, 2i+1) = (w1 row i, w3 row i)  (nn/transformer.h:57-59); two outputs per word
+                float s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+                for (int w = 0; w < kStWarps; w++) s2 += rr[w * 128 + 16], s3 += rr[w * 128 + 24];
+                const float z0 = __fmul_rn(silu_bf16(y0), y1), z1 = __fmul_rn(silu_bf16(rbf(s2)), rbf(s3));
+                st_ll_store(g.out_ll + size_t(ecol) * out_pitch + (R >> 2), pack2(z0, z1), tag_out);
+            } else if (g.epi == EPI_RESIDUAL) {
+                // h = r(x + a)  (nn/transformer.h:133,139)
+                st_ll_store(g.out_ll + size_t(ecol) * out_pitch + (R >> 1), pack2(__fadd_rn(bf_lo(resw), y0), __fadd_rn(bf_hi(resw), y1)), tag_out);
+            } else if (!is_head) {
+                st_ll_store(g.out_ll + size_t(ecol) * out_pitch + (R >> 1), pack2(y0, y1), tag_out);
+            } else {
+                *reinterpret_cast<uint32_t*>(g.y + size_t(ecol) * g.N + R) = pack2(y0, y1);
+                if (y0 > best.v || (y0 == best.v && int32_t(R) < best.i)) best.v = y0, best.i = int32_t(R);
+                if (y1 > best.v || (y1 == best.v && int32_t(R + 1) < best.i)) best.v = y1, best.i = int32_t(R + 1);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(c.fre0 + bl.buf * 8);
+        bl.advance();
+    }
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
+
+// ---- consumers: attention phase ---------------------------------------------------------------------------------------
+// item = (row, head, part).  The four parts of a head split the cached positions for the scores and the head dimensions
+// for the output:
+//   1. rotate q and (position owner only) the new k (kernel/rope.metal:47-58); the owner of a kv head appends k', v to the
+//      cache (nn/cache.h:207-214);
+//   2. s[t] = r(r(q.K[t]) * scale) for this part's quarter of the positions, published as tagged words;
+//   3. every part polls ALL scores of the head, p = r(exp(s) / sum exp(s)) (no max shift, kernel/softmax.metal:40-80) in
+//      one fixed order, identical on the four parts;
+//   4. o[d] = r(sum_t p[t] V[t][d]) for this part's quarter of the head dimensions, published as tagged words.
+template <int HD>
+__device__ __forceinline__ void st_attention(const st_params& P, uint32_t li, uint32_t step, const st_ctx& c, uint32_t tag_in, uint32_t tag_out)
+{
+    constexpr int LPP = HD / 8;                 // lanes per cached K position (16 bytes each)
+    constexpr int SLOTS = kStConsumers / LPP;   // K positions per sweep
+    constexpr int IT = 5;                       // K sweeps kept in flight
+    constexpr int DQ = HD / kStSplits;          // head dims finished by this part
+    constexpr int VL = DQ / 4;                  // lanes per cached V position (8 bytes = 4 dims each)
+    constexpr int VSLOTS = kStConsumers / VL;   // V positions per sweep
+    constexpr int VIT = HD == 64 ? 9 : 18;      // V sweeps held in registers while the scores are exchanged
     const uint32_t tid = threadIdx.x;
-    const uint32_t H = P.n_heads, KV = P.n_kv_heads, half = HD / 2, QO = H * HD, QKVN = (H + 2 * KV) * HD;
-    float* sq = reinterpret_cast<float*>(c.act); // [HD] rotated q
-    float* sk = sq + HD;                          // [HD] rotated new k
-    float* sv = sk + HD;                          // [HD] new v
-    float* spart = sv + HD;                       // [SLOTS][HD]
-    float* sp = spart + SLOTS * HD;               // [chunk] scores / probabilities
+    const uint32_t H = P.n_heads, KV = P.n_kv_heads, half = HD / 2, QKVW = (H + 2 * KV) * HD / 2;
+    float* rawq = reinterpret_cast<float*>(c.act); // [HD] q as stored by the QKV phase
+    float* rawk = rawq + HD;                        // [HD]
+    float* sq = rawk + HD;                          // [HD] rotated q
+    float* sk = sq + HD;                            // [HD] rotated new k
+    float* sv = sk + HD;                            // [HD] new v
+    float* spart = sv + HD;                         // [VSLOTS][DQ] = 1024 floats
+    float* sp = spart + VSLOTS * DQ;                // [np] scores, then probabilities
     const uint32_t slot = tid / LPP, dl = tid % LPP;
+    const uint32_t vslot = tid / VL, vl = tid % VL;
     const size_t kv_off = size_t(li) * P.kv_layer_stride;
     const uint32_t n_items = P.rows * H * kStSplits;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const uint32_t split = item & (kStSplits - 1), head = (item / kStSplits) % H, row = (item / kStSplits) / H;
+        const uint32_t part = item & (kStSplits - 1), head = (item / kStSplits) % H, row = (item / kStSplits) / H;
         const int32_t seq = P.row_seq[row];
-        const uint32_t pos = uint32_t(ldcg_s32(P.pos + row));
+        const uint32_t pos = uint32_t(P.pos[row]) + step;
         const uint32_t np = pos + 1;
         const uint32_t kvh = head / (H / KV);
-        const uint32_t chunk = (np + kStSplits - 1) / kStSplits;
-        const uint32_t t0 = min(np, split * chunk), t1 = min(np, t0 + chunk);
+        const uint32_t chunk = (((np + kStSplits - 1) / kStSplits) + 1) & ~1u; // even: two scores per tagged word
+        const uint32_t t0 = min(np, part * chunk), t1 = min(np, t0 + chunk);
         const uint32_t tc1 = min(t1, pos); // positions below `pos` come from the cache, `pos` itself is fresh
         const bool own = pos >= t0 && pos < t1;
+        const bool writer = own && head % (H / KV) == 0;
         const size_t coff = kv_off + (size_t(seq) * KV + kvh) * P.max_seq * HD;
         const uint16_t* Kc = P.kcache + coff;
         const uint16_t* Vc = P.vcache + coff;
 
         // first block of K rows: requested before anything else is touched
-        uint4 kreg[IT], vreg[IT];
+        uint4 kreg[IT];
 #pragma unroll
         for (int i = 0; i < IT; i++) {
             const uint32_t tt = t0 + i * SLOTS + slot;
             if (tt < tc1) kreg[i] = ldcg128(Kc + size_t(tt) * HD + dl * 8);
         }
-        const uint16_t* qrow = P.qkv + size_t(row) * QKVN;
+        // q, v (and k for the owner) of this head from the QKV phase
+        {
+            const uint64_t* qrow = P.qkv_ll + size_t(row) * QKVW;
+            const uint32_t grp = tid / half, i = tid % half; // 0: q, 1: v, 2: k
+            if (grp < 2 || (grp == 2 && own)) {
+                const uint32_t base = grp == 0 ? head * HD : (grp == 1 ? (H + KV + kvh) * HD : (H + kvh) * HD);
+                const uint32_t w = st_poll1(c, qrow + (base >> 1) + i, tag_in);
+                float* d = grp == 0 ? rawq : (grp == 1 ? sv : rawk);
+                d[2 * i] = bf_lo(w), d[2 * i + 1] = bf_hi(w);
+                if (grp == 1 && writer) *reinterpret_cast<uint32_t*>(P.vcache + coff + size_t(pos) * HD + 2 * i) = w;
+            }
+        }
+        consumer_bar();
         if (tid < half) {
             const float cs = P.fcos[size_t(pos) * half + tid], sn = P.fsin[size_t(pos) * half + tid];
-            const float q0 = bf16_bits_to_f32(ldcg_u16(qrow + head * HD + tid)), q1 = bf16_bits_to_f32(ldcg_u16(qrow + head * HD + tid + half));
+            const float q0 = rawq[tid], q1 = rawq[tid + half];
             sq[tid] = rbf(__fsub_rn(__fmul_rn(cs, q0), __fmul_rn(sn, q1)));
             sq[tid + half] = rbf(__fadd_rn(__fmul_rn(sn, q0), __fmul_rn(cs, q1)));
             if (own) {
-                const uint16_t* kr = qrow + (H + kvh) * HD;
-                const float k0 = bf16_bits_to_f32(ldcg_u16(kr + tid)), k1 = bf16_bits_to_f32(ldcg_u16(kr + tid + half));
+                const float k0 = rawk[tid], k1 = rawk[tid + half];
                 const float o0 = rbf(__fsub_rn(__fmul_rn(cs, k0), __fmul_rn(sn, k1)));
                 const float o1 = rbf(__fadd_rn(__fmul_rn(sn, k0), __fmul_rn(cs, k1)));
                 sk[tid] = o0, sk[tid + half] = o1;
-                if (head % (H / KV) == 0) { // one writer per kv head
+                if (writer) {
                     uint16_t* kd = P.kcache + coff + size_t(pos) * HD;
                     kd[tid] = f32_to_bf16_bits(o0), kd[tid + half] = f32_to_bf16_bits(o1);
                 }
             }
-        } else if (own && tid >= 64 && tid < 64 + HD) {
-            const uint32_t d = tid - 64;
-            const uint16_t vb = ldcg_u16(qrow + (H + KV + kvh) * HD + d);
-            sv[d] = bf16_bits_to_f32(vb);
-            if (head % (H / KV) == 0) P.vcache[coff + size_t(pos) * HD + d] = vb;
         }
+        if (writer) __threadfence(); // the appended row is read by other CTAs in the next step, long after the tagged words below
         consumer_bar();
         float qv[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) qv[i] = sq[dl * 8 + i];
-        // scores of the cached positions
+        // scores of this part's cached positions
         for (uint32_t tb = t0; tb < tc1; tb += IT * SLOTS) {
             if (tb != t0) {
 #pragma unroll
@@ -520,76 +679,74 @@ __device__ __forceinline__ void st_attention(const st_params& P, uint32_t li, ui
                 }
 #pragma unroll
                 for (int off = LPP / 2; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-                if (tt < tc1 && dl == 0) sp[tt - t0] = rbf(__fmul_rn(rbf(d), P.scale));
+                if (tt < tc1 && dl == 0) sp[tt] = rbf(__fmul_rn(rbf(d), P.scale));
             }
         }
-        // first block of V rows goes in flight before the exchange
+        // V rows of ALL cached positions, this part's dims: in flight while the scores are exchanged
+        uint2 vreg[VIT];
 #pragma unroll
-        for (int i = 0; i < IT; i++) {
-            const uint32_t tt = t0 + i * SLOTS + slot;
-            if (tt < tc1) vreg[i] = ldcg128(Vc + size_t(tt) * HD + dl * 8);
+        for (int i = 0; i < VIT; i++) {
+            const uint32_t tt = i * VSLOTS + vslot;
+            if (tt < pos) {
+                const uint16_t* vp = Vc + size_t(tt) * HD + part * DQ + vl * 4;
+                asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(vreg[i].x), "=r"(vreg[i].y) : "l"(vp));
+            }
         }
         if (own && tid < 32) {
             float d = 0.0f;
             for (uint32_t i = tid; i < uint32_t(HD); i += 32) d = fmaf(sq[i], sk[i], d);
             d = warp_sum(d);
-            if (tid == 0) sp[pos - t0] = rbf(__fmul_rn(rbf(d), P.scale));
+            if (tid == 0) sp[pos] = rbf(__fmul_rn(rbf(d), P.scale));
         }
         consumer_bar();
-        // softmax without max subtraction (kernel/softmax.metal:40-80); the exp-sum is joined across the 4 splits
-        const uint32_t n_local = t1 - t0;
-        float part = 0.0f;
-        for (uint32_t i = tid; i < n_local; i += kStConsumers) part += expf(sp[i]);
-        const float local_sum = st_block_sum(part, c.scr);
-        const uint32_t group = item / kStSplits;
-        if (tid == 0) {
-            P.xsum[size_t(group) * kStSplits + split] = local_sum;
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(P.acnt + group) : "memory");
-            st_spin_ge(c, P.acnt + group, kStSplits * (gstep * P.n_layers + li + 1));
+        // publish this part's scores, two per word
+        uint64_t* sc = P.sc_ll + size_t(item / kStSplits) * P.sc_words;
+        for (uint32_t tt = t0 + 2 * tid; tt < t1; tt += 2 * kStConsumers)
+            st_ll_store(sc + (tt >> 1), pack2(sp[tt], tt + 1 < t1 ? sp[tt + 1] : 0.0f), tag_out);
+        consumer_bar(); // sp is about to be overwritten with everybody's scores
+        for (uint32_t w = tid; w < (np + 1) / 2; w += kStConsumers) {
+            const uint32_t v = st_poll1(c, sc + w, tag_out);
+            sp[2 * w] = bf_lo(v), sp[2 * w + 1] = bf_hi(v);
         }
         consumer_bar();
-        float total = 0.0f;
-#pragma unroll
-        for (int s = 0; s < kStSplits; s++) total += ldcg_f32(P.xsum + size_t(group) * kStSplits + s);
+        float part_sum = 0.0f;
+        for (uint32_t i = tid; i < np; i += kStConsumers) part_sum += expf(sp[i]);
+        const float total = st_block_sum(part_sum, c.scr);
         const float inv = 1.0f / total;
-        for (uint32_t i = tid; i < n_local; i += kStConsumers) sp[i] = rbf(__fmul_rn(expf(sp[i]), inv));
+        for (uint32_t i = tid; i < np; i += kStConsumers) sp[i] = rbf(__fmul_rn(expf(sp[i]), inv));
         consumer_bar();
-        float acc[8];
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-        for (int i = 0; i < 8; i++) acc[i] = 0.0f;
-        for (uint32_t tb = t0; tb < tc1; tb += IT * SLOTS) {
-            if (tb != t0) {
-#pragma unroll
-                for (int i = 0; i < IT; i++) {
-                    const uint32_t tt = tb + i * SLOTS + slot;
-                    if (tt < tc1) vreg[i] = ldcg128(Vc + size_t(tt) * HD + dl * 8);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < IT; i++) {
-                const uint32_t tt = tb + i * SLOTS + slot;
-                if (tt < tc1) {
-                    const uint4 vv = vreg[i];
-                    const float pt = sp[tt - t0];
-                    acc[0] = fmaf(pt, bf_lo(vv.x), acc[0]);
-                    acc[1] = fmaf(pt, bf_hi(vv.x), acc[1]);
-                    acc[2] = fmaf(pt, bf_lo(vv.y), acc[2]);
-                    acc[3] = fmaf(pt, bf_hi(vv.y), acc[3]);
-                    acc[4] = fmaf(pt, bf_lo(vv.z), acc[4]);
-                    acc[5] = fmaf(pt, bf_hi(vv.z), acc[5]);
-                    acc[6] = fmaf(pt, bf_lo(vv.w), acc[6]);
-                    acc[7] = fmaf(pt, bf_hi(vv.w), acc[7]);
-                }
+        for (int i = 0; i < VIT; i++) {
+            const uint32_t tt = i * VSLOTS + vslot;
+            if (tt < pos) {
+                const float pt = sp[tt];
+                acc[0] = fmaf(pt, bf_lo(vreg[i].x), acc[0]);
+                acc[1] = fmaf(pt, bf_hi(vreg[i].x), acc[1]);
+                acc[2] = fmaf(pt, bf_lo(vreg[i].y), acc[2]);
+                acc[3] = fmaf(pt, bf_hi(vreg[i].y), acc[3]);
             }
         }
+        for (uint32_t tt = VIT * VSLOTS + vslot; tt < pos; tt += VSLOTS) {
+            uint2 vv;
+            const uint16_t* vp = Vc + size_t(tt) * HD + part * DQ + vl * 4;
+            asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(vv.x), "=r"(vv.y) : "l"(vp));
+            const float pt = sp[tt];
+            acc[0] = fmaf(pt, bf_lo(vv.x), acc[0]);
+            acc[1] = fmaf(pt, bf_hi(vv.x), acc[1]);
+            acc[2] = fmaf(pt, bf_lo(vv.y), acc[2]);
+            acc[3] = fmaf(pt, bf_hi(vv.y), acc[3]);
+        }
 #pragma unroll
-        for (int i = 0; i < 8; i++) spart[slot * HD + dl * 8 + i] = acc[i];
+        for (int i = 0; i < 4; i++) spart[vslot * DQ + vl * 4 + i] = acc[i];
         consumer_bar();
-        if (tid < HD) {
-            float o = 0.0f;
-            for (int s = 0; s < SLOTS; s++) o += spart[s * HD + tid];
-            if (own) o = fmaf(sp[pos - t0], sv[tid], o);
-            P.opart[(size_t(row) * kStSplits + split) * QO + head * HD + tid] = o;
+        if (tid < DQ / 2) {
+            float o0 = 0.0f, o1 = 0.0f;
+            for (int s = 0; s < VSLOTS; s++) o0 += spart[s * DQ + 2 * tid], o1 += spart[s * DQ + 2 * tid + 1];
+            const float pp = sp[pos];
+            o0 = fmaf(pp, sv[part * DQ + 2 * tid], o0);
+            o1 = fmaf(pp, sv[part * DQ + 2 * tid + 1], o1);
+            st_ll_store(P.attn_ll + size_t(row) * (H * HD / 2) + ((head * HD + part * DQ) >> 1) + tid, pack2(o0, o1), tag_out);
         }
         consumer_bar(); // the scratch is reused by the next item
     }
@@ -598,23 +755,31 @@ __device__ __forceinline__ void st_attention(const st_params& P, uint32_t li, ui
 // ---- the kernel ----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kStThreads, 1) decode_stream_kernel(const __grid_constant__ st_params P)
 {
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(16) unsigned char smem[];
     st_ctx c;
     c.full0 = smem_u32(smem);
     c.empty0 = c.full0 + kStMaxStages * 8;
-    c.dead = reinterpret_cast<volatile int*>(smem + 2 * kStMaxStages * 8);
+    c.rdy0 = c.empty0 + kStMaxStages * 8;
+    c.fre0 = c.rdy0 + kStRedBufs * 8;
+    c.dead = reinterpret_cast<volatile int*>(smem + 224);
     c.scr = reinterpret_cast<float*>(smem + 256);
+    c.escr = reinterpret_cast<float*>(smem + 320);
     c.red = reinterpret_cast<float*>(smem + kStHdrBytes);
     c.act = smem + kStHdrBytes + kStRedBytes;
     c.act_addr = smem_u32(c.act);
     c.ring_addr = c.act_addr + P.act_bytes;
     c.err = P.err;
+    c.poll_ns = P.poll_ns;
     const uint32_t tid = threadIdx.x;
     const unsigned G = gridDim.x;
     if (tid == 0) {
         for (uint32_t s = 0; s < P.n_stages; s++) {
             mbar_init(c.full0 + s * 8, 1);
             mbar_init(c.empty0 + s * 8, kStWarps);
+        }
+        for (uint32_t s = 0; s < uint32_t(kStRedBufs); s++) {
+            mbar_init(c.rdy0 + s * 8, kStWarps);
+            mbar_init(c.fre0 + s * 8, kStEpiThreads / 32);
         }
         *c.dead = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -623,112 +788,101 @@ __global__ void __launch_bounds__(kStThreads, 1) decode_stream_kernel(const __gr
     __syncthreads();
     const uint32_t phases_per_step = P.n_layers * 5 + 1;
 
+    if (tid >= kStConsumers + kStEpiThreads) {
+        // ---- producer warp: the whole launch's weight stream, never blocked by anything but a full ring
+        st_producer(P, c);
+        return;
+    }
     if (tid >= kStConsumers) {
-        // ---- producer warp: the whole launch's weight stream, never blocked by a phase barrier
-        st_pipe pp{0, 0};
-        const uint64_t policy = policy_evict_first();
+        // ---- epilogue warps: finish every 16-row block of every GEMV phase, then the sampler tail
+        const uint32_t et = tid - kStConsumers, ewarp = et >> 5, lane = et & 31;
+        st_blk bl{0, 0};
+        const int32_t log0 = P.step_counter[0];
         for (uint32_t step = 0; step < P.steps; step++) {
-            for (uint32_t li = 0; li < P.n_layers; li++) {
-                st_produce_gemv(P, P.g[0], li, c, pp, policy);
-                st_produce_gemv(P, P.g[1], li, c, pp, policy);
-                st_produce_gemv(P, P.g[2], li, c, pp, policy);
-                st_produce_gemv(P, P.g[3], li, c, pp, policy);
+            unsigned gphase = step * phases_per_step;
+            st_best best{-INFINITY, 0x7fffffff};
+            for (uint32_t li = 0; li <= P.n_layers; li++) {
+                const bool is_head = li == P.n_layers;
+                for (uint32_t kind = 0; kind < (is_head ? 1u : 5u); kind++, gphase++) {
+                    if (!is_head && kind == 1) continue;
+                    st_epi_gemv(P, P.g[is_head ? 4u : (kind == 0 ? 0u : kind - 1)], c, bl, best, is_head, P.tag_base + gphase + 1);
+                    st_stamp(P.timing ? P.timing + (size_t(blockIdx.x) * (P.steps * phases_per_step) + gphase) * 4 : nullptr, 1);
+                }
             }
-            st_produce_gemv(P, P.g[4], 0, c, pp, policy);
+            // sampler tail (greedy): every CTA publishes its argmax partial, CTA 0 joins them and publishes the next id
+            const uint32_t tag_head = P.tag_base + gphase; // = tag_out of the head phase
+            float* bv = c.escr;
+            int32_t* bi = reinterpret_cast<int32_t*>(c.escr + 64);
+            bv[et] = best.v, bi[et] = best.i;
+            epi_bar();
+            if (et < P.rows) {
+                float v = -INFINITY;
+                int32_t i = 0x7fffffff;
+                for (int r = 0; r < 8; r++) {
+                    const float ov = bv[r * 8 + et];
+                    const int32_t oi = bi[r * 8 + et];
+                    if (ov > v || (ov == v && oi < i)) v = ov, i = oi;
+                }
+                uint64_t* dst = P.am_ll + (size_t(et) * G + blockIdx.x) * 2;
+                st_ll_store(dst, __float_as_uint(v), tag_head);
+                st_ll_store(dst + 1, uint32_t(i), tag_head);
+            }
+            epi_bar();
+            if (blockIdx.x == 0) {
+                for (uint32_t row = ewarp; row < P.rows; row += kStEpiThreads / 32) {
+                    float v = -INFINITY;
+                    int32_t i = 0x7fffffff;
+                    for (unsigned b = lane; b < G; b += 32) {
+                        const uint64_t* src = P.am_ll + (size_t(row) * G + b) * 2;
+                        const float ov = __uint_as_float(st_poll1(c, src, tag_head));
+                        const int32_t oi = int32_t(st_poll1(c, src + 1, tag_head));
+                        if (ov > v || (ov == v && oi < i)) v = ov, i = oi;
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, v, off);
+                        const int32_t oi = __shfl_xor_sync(0xffffffffu, i, off);
+                        if (ov > v || (ov == v && oi < i)) v = ov, i = oi;
+                    }
+                    if (lane == 0) {
+                        if (i == 0x7fffffff) i = 0; // all-NaN / -inf row: argmax keeps index 0
+                        st_ll_store(P.ids_ll + row, uint32_t(i), tag_head);
+                        P.out_log[size_t(log0 + int32_t(step)) * P.rows + row] = i;
+                        if (P.advance && step + 1 == P.steps) {
+                            P.ids[row] = i;
+                            P.pos[row] = P.pos[row] + int32_t(P.steps);
+                        }
+                    }
+                }
+                if (et == 0 && step + 1 == P.steps) P.step_counter[0] = log0 + int32_t(P.steps);
+            }
         }
         return;
     }
 
-    // ---- consumer warps
+    // ---- mma / staging / attention warps
     st_pipe cp{0, 0};
-    uint32_t red_buf = 0;
+    st_blk bl{0, 0};
     for (uint32_t step = 0; step < P.steps; step++) {
-        unsigned gphase = step * phases_per_step; // phases completed before this one, launch-wide
-        st_best best{-INFINITY, 0x7fffffff};
+        unsigned gphase = step * phases_per_step;
         for (uint32_t li = 0; li <= P.n_layers; li++) {
             const bool is_head = li == P.n_layers;
             for (uint32_t kind = 0; kind < (is_head ? 1u : 5u); kind++, gphase++) {
-                unsigned long long* tm = P.timing ? P.timing + size_t(gphase) * 4 : nullptr;
+                // the output of phase k carries tag_base + k + 1; a phase consumes the output of the phase before it
+                const uint32_t tag_in = P.tag_base + gphase, tag_out = tag_in + 1;
+                unsigned long long* tm = P.timing ? P.timing + (size_t(blockIdx.x) * (P.steps * phases_per_step) + gphase) * 4 : nullptr;
                 st_stamp(tm, 0);
-                // wait for this phase's input: the previous phase of every CTA, or (first phase of a later step) the sampler tail
-                if (gphase != 0) {
-                    if (li == 0 && kind == 0) st_grid_wait(c, P.step_done, step);
-                    else st_grid_wait(c, P.bar, gphase * G);
-                }
-                st_stamp(tm, 1);
                 if (!is_head && kind == 1) {
-                    if (P.head_dim == 64) st_attention<64>(P, li, step, c);
-                    else st_attention<128>(P, li, step, c);
+                    if (P.head_dim == 64) st_attention<64>(P, li, step, c, tag_in, tag_out);
+                    else st_attention<128>(P, li, step, c, tag_in, tag_out);
                     st_stamp(tm, 2);
                 } else {
                     const st_gemv& g = P.g[is_head ? 4u : (kind == 0 ? 0u : kind - 1)];
-                    st_stage_input(P, g, is_head ? 0 : li, c);
+                    st_stage_input(P, g, is_head ? 0 : li, c, li == 0 && kind == 0 && !is_head, step, tag_in, tag_out);
                     st_stamp(tm, 2);
-                    st_consume_gemv(P, g, c, cp, red_buf, best, is_head);
+                    st_mma_gemv(P, g, c, cp, bl);
                 }
                 st_stamp(tm, 3);
-                if (is_head) {
-                    // per-CTA argmax partial of every activation row
-                    consumer_bar();
-                    float* bv = c.red;
-                    int32_t* bi = reinterpret_cast<int32_t*>(c.red + 128);
-                    if (tid < 128) bv[tid] = best.v, bi[tid] = best.i;
-                    consumer_bar();
-                    if (tid < P.rows) {
-                        float v = -INFINITY;
-                        int32_t i = 0x7fffffff;
-                        for (int r = 0; r < 16; r++) {
-                            const float ov = bv[r * 8 + tid];
-                            const int32_t oi = bi[r * 8 + tid];
-                            if (ov > v || (ov == v && oi < i)) v = ov, i = oi;
-                        }
-                        P.am_val[tid * G + blockIdx.x] = v;
-                        P.am_idx[tid * G + blockIdx.x] = i;
-                    }
-                }
-                st_grid_arrive(P.bar);
-            }
-        }
-        // ---- sampler tail (greedy): CTA 0 joins the per-CTA partials, feeds the id back and advances the position
-        if (blockIdx.x == 0) {
-            st_grid_wait(c, P.bar, gphase * G);
-            const uint32_t warp = tid >> 5, lane = tid & 31;
-            if (warp < P.rows) {
-                float v = -INFINITY;
-                int32_t i = 0x7fffffff;
-                for (unsigned b = lane; b < G; b += 32) {
-                    const float ov = ldcg_f32(P.am_val + warp * G + b);
-                    const int32_t oi = ldcg_s32(P.am_idx + warp * G + b);
-                    if (ov > v || (ov == v && oi < i)) v = ov, i = oi;
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const float ov = __shfl_xor_sync(0xffffffffu, v, off);
-                    const int32_t oi = __shfl_xor_sync(0xffffffffu, i, off);
-                    if (ov > v || (ov == v && oi < i)) v = ov, i = oi;
-                }
-                if (lane == 0) {
-                    if (i == 0x7fffffff) i = 0; // all-NaN / -inf row: argmax keeps index 0
-                    const int32_t sc = ldcg_s32(P.step_counter);
-                    P.out_log[size_t(sc) * P.rows + warp] = i;
-                    if (P.advance) {
-                        P.ids[warp] = i;
-                        P.pos[warp] = ldcg_s32(P.pos + warp) + 1;
-                    }
-                }
-            }
-            consumer_bar();
-            if (tid == 0) {
-                *P.step_counter = ldcg_s32(P.step_counter) + 1;
-                if (step + 1 == P.steps) {
-                    // every CTA has made its last arrival and left its last wait: ready for the next launch
-                    *P.bar = 0;
-                    for (uint32_t i = 0; i < P.rows * P.n_heads; i++) P.acnt[i] = 0;
-                    *P.step_done = 0;
-                } else {
-                    __threadfence();
-                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(P.step_done), "r"(step + 1) : "memory");
-                }
             }
         }
     }

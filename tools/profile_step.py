@@ -21,22 +21,36 @@ m.decode_loop([1], [512], 8)
 L = shape["n_layers"]
 if mode == "stream":
     names = ["qkv", "attn", "wo", "w13", "w2"] * L + ["head"]
-    acc = {}
+    P = len(names)
+    reps = []
     for rep in range(4):
-        us = m.profile_step(1).reshape(-1, 4)
+        t = m.profile_step(1).reshape(-1, P, 4)  # [cta][phase][entry, -, staged, done] in us
         m.decode_loop([1], [512], 2)
-        if rep == 0:
-            continue
-        for n, t in zip(names, us):
-            acc.setdefault(n, []).append(t)
-    tot = 0
-    for n, v in acc.items():
-        v = np.array(v)
-        per = v.mean(axis=0)
-        cnt = len(v) / 3
-        tot += per.sum() * cnt
-        print(f"{n:6s} wait {per[0]:7.2f}  stage {per[1]:7.2f}  tiles {per[2]:7.2f}  gap {per[3]:7.2f} us  x{cnt:3.0f} = {per.sum() * cnt:8.1f} us")
-    print("sum", tot)
+        if rep:
+            reps.append(t)
+    t = np.mean(reps, axis=0)
+    G = t.shape[0]
+    print(f"{G} CTAs, step = {t[:, -1, 3].max() - t[:, 0, 0].min():.1f} us")
+    print("phase   | first entry -> last done | stage(wait+stage) med/max | tiles med/max | done skew (max-min) | slowest CTA")
+    for kind in ["qkv", "attn", "wo", "w13", "w2", "head"]:
+        idx = [i for i, n in enumerate(names) if n == kind]
+        span = np.mean([t[:, i, 3].max() - t[:, i, 0].min() for i in idx])
+        stage = t[:, idx, 2] - t[:, idx, 0]
+        tiles = t[:, idx, 3] - t[:, idx, 2]
+        skew = np.mean([t[:, i, 3].max() - t[:, i, 3].min() for i in idx])
+        slow = np.bincount(np.concatenate([[int(t[:, i, 3].argmax())] for i in idx]), minlength=G).argmax()
+        print(f"{kind:6s}  | {span:7.2f} | {np.median(stage):6.2f} / {stage.max(axis=0).mean():6.2f} | {np.median(tiles):6.2f} / {tiles.max(axis=0).mean():6.2f} | {skew:6.2f} | {slow}")
+    # epilogue lag: last epilogue store of a phase vs the mma warps leaving it; propagation: next phase staged vs the last epilogue store anywhere
+    for kind, nxt in [("qkv", "attn"), ("wo", "w13"), ("w13", "w2"), ("w2", "qkv")]:
+        idx = [i for i, n in enumerate(names) if n == kind and i + 1 < P and names[i + 1] == nxt]
+        lag = np.array([t[:, i, 1] - t[:, i, 3] for i in idx])
+        prop = np.array([t[:, i + 1, 2] - t[:, i, 1].max() for i in idx])
+        print(f"{kind}->{nxt}: epilogue lag med {np.median(lag):.2f} max {lag.max(axis=1).mean():.2f} us; staged after last epilogue: med {np.median(prop):.2f} max {prop.max(axis=1).mean():.2f} us")
+    done = t[:, :, 3]
+    lag = (done - done.min(axis=0, keepdims=True)).mean(axis=1)
+    order = np.argsort(lag)
+    print("mean lag behind the first finisher per CTA: min", lag[order[:5]].round(2), order[:5], "max", lag[order[-8:]].round(2), order[-8:])
+    np.save("gpurun_out/stream_stamps.npy", t)
 elif mode == "mega":
     names = ["qkv", "attn", "wo", "w13", "w2"] * L + ["head"]
     acc = {}
