@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("MC_NVCC_EXTRA", "").split(), "-c", str(src), "-o", str(obj)]
         res = subprocess.run(cmd, capture_output=True, text=True)
         (OBJ / (src.stem + ".ptxas.log")).write_text(res.stderr)
         if res.returncode != 0:

@@ -94,7 +94,7 @@ struct mc_llama {
     size_t tp_off_flags = 0, tp_off_amval = 0, tp_off_amidx = 0, tp_off_amflags = 0;
     // streaming persistent kernel (mc_stream_kernel.cuh): un-rotated q|k|v rows, split-attention exchange, step flag
     dbuf st_ll, st_timing;     // one arena of tagged words: x | h | z | qkv | attn | scores | argmax partials | ids
-    size_t st_off[8] = {};
+    size_t st_off[9] = {};
     uint32_t st_sc_words = 0, st_seq = 0;
     bool st_timing_on = false;
     int st_ok = -1;            // -1 not probed yet, 0 not usable on this device / shape, 1 usable
@@ -599,17 +599,26 @@ uint32_t stream_kc(uint32_t K)
         if (K % kc == 0) return kc;
     return 0;
 }
+// the kernel is specialised on (packed layers + adaptors, head_dim): each instantiation carries only the code it runs
+using stream_kernel_t = void (*)(const st_params);
+stream_kernel_t stream_kernel_of(bool quant, uint32_t head_dim)
+{
+    if (quant) return head_dim == 64 ? decode_stream_kernel<true, 64> : decode_stream_kernel<true, 128>;
+    return head_dim == 64 ? decode_stream_kernel<false, 64> : decode_stream_kernel<false, 128>;
+}
 struct stream_geom {
-    uint32_t act_pitch, act_bytes, n_stages;
+    uint32_t act_pitch, act_bytes, sax_off, n_stages;
     size_t smem;
 };
 bool stream_geometry(const mc_llama* m, uint32_t rows, stream_geom& g)
 {
     const mc_llama_config& c = m->cfg;
     const uint32_t kmax = std::max(std::max(c.dim, m->Hl * c.head_dim), m->Fl);
-    g.act_pitch = kmax * 2 + kStPad;
+    // row pad: 64 bytes make the 16-byte fragment loads of the bf16 path conflict-free, 16 bytes the 4-byte loads of the packed paths
+    g.act_pitch = kmax * 2 + (c.quant ? 16 : kStPad);
     const size_t attn_scratch = (size_t(5) * c.head_dim + 1024 + c.max_seq_len + 8) * sizeof(float);
-    g.act_bytes = uint32_t((std::max(size_t(rows) * g.act_pitch, attn_scratch) + 127) & ~size_t(127));
+    g.sax_off = uint32_t((std::max(size_t(rows) * g.act_pitch, attn_scratch) + 127) & ~size_t(127));
+    g.act_bytes = g.sax_off + (c.quant ? uint32_t(kStMaxRows * 3 * c.lora_rank * sizeof(float) + 127) & ~127u : 0u);
     const size_t fixed = kStHdrBytes + kStRedBytes + g.act_bytes;
     const size_t cap = 232448; // 227 KiB of dynamic shared memory per CTA on sm_100
     if (fixed + 2 * size_t(kStStageBytes) > cap) return false;
@@ -617,23 +626,33 @@ bool stream_geometry(const mc_llama* m, uint32_t rows, stream_geom& g)
     g.smem = fixed + size_t(g.n_stages) * kStStageBytes;
     return true;
 }
+uint32_t stream_kc_packed(uint32_t K)
+{
+    for (uint32_t kc : {2048u, 1024u, 512u, 256u})
+        if (K % kc == 0) return kc;
+    return 0;
+}
 // the streaming kernel serves greedy bf16 decode of up to 8 sequences on one GPU; everything else takes the per-op path
 bool stream_eligible(mc_llama* m, uint32_t n, const mc_sampler_config& sc)
 {
     const mc_llama_config& c = m->cfg;
     static const bool env_off = getenv("MC_NO_STREAM") != nullptr;
     if (env_off || (c.flags & (MC_LLAMA_NO_STREAM | MC_LLAMA_MEGAKERNEL))) return false;
-    if (c.quant || c.tp_world != 1 || sc.mode != 0 || n > uint32_t(kStMaxRows) || m->tok.fmt != WF_BF16) return false;
+    if (c.tp_world != 1 || sc.mode != 0 || n > uint32_t(kStMaxRows)) return false;
     if (m->st_ok < 0) {
         m->st_ok = 0;
         stream_geom g;
-        const bool shapes = stream_kc(c.dim) && stream_kc(m->Hl * c.head_dim) && stream_kc(m->Fl) && c.dim <= 4096 && m->Fl % 2 == 0 && m->Vl % 2 == 0 &&
-                            m->dev->prop.multiProcessorCount <= 256 && stream_geometry(m, kStMaxRows, g);
+        bool shapes = stream_kc(c.dim) && stream_kc(m->Hl * c.head_dim) && stream_kc(m->Fl) && c.dim <= 4096 && m->Fl % 2 == 0 && m->Vl % 2 == 0 &&
+                      m->dev->prop.multiProcessorCount <= 256 && stream_geometry(m, kStMaxRows, g);
+        if (c.quant) // packed layouts: whole super-units of 16 rows, adaptor rows in pairs, rank in 16-byte steps
+            shapes = shapes && ((m->Hl + 2 * m->KVl) * c.head_dim) % 16 == 0 && c.dim % 16 == 0 && (2 * m->Fl) % 16 == 0 && m->Vl % 16 == 0 && c.lora_rank % 8 == 0 &&
+                     3 * c.lora_rank <= 128 && (c.head_dim / 2) % 8 == 0;
         if (shapes) {
-            if (cudaFuncSetAttribute(decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) == cudaSuccess) {
+            auto kernel = stream_kernel_of(c.quant != 0, c.head_dim);
+            if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) == cudaSuccess) {
                 int occ = 0, coop = 0;
                 cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, m->dev->ordinal);
-                if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decode_stream_kernel, kStThreads, g.smem) == cudaSuccess && occ >= 1) {
+                if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kStThreads, g.smem) == cudaSuccess && occ >= 1) {
                     m->st_ok = 1;
                     m->st_grid = uint32_t(m->dev->prop.multiProcessorCount);
                 }
@@ -661,24 +680,36 @@ void launch_stream(mc_llama* m, launcher& L, uint32_t rows, int advance, uint32_
     const dlayer& l0 = m->layers[0];
     uint64_t* ll = m->st_ll.as<uint64_t>();
     uint64_t *x_ll = ll + m->st_off[0], *h_ll = ll + m->st_off[1], *z_ll = ll + m->st_off[2], *qkv_ll = ll + m->st_off[3], *attn_ll = ll + m->st_off[4];
-    auto gemv = [&](const void* W, const dbuf* norm, const uint64_t* in_ll, uint64_t* out_ll, const uint64_t* res_ll, uint32_t N, uint32_t K, int pro, int epi,
-                    int layered) {
+    uint64_t* ax_ll = ll + m->st_off[8];
+    const bool Q = c.quant != 0;
+    const uint32_t rank = c.lora_rank;
+    auto gemv = [&](const dlinear& d, const dbuf* lora_a, uint32_t slices, int which, const dbuf* norm, const uint64_t* in_ll, uint64_t* out_ll,
+                    const uint64_t* res_ll, uint32_t N, uint32_t K, int pro, int epi, int layered) {
         st_gemv g{};
-        g.W = static_cast<const uint16_t*>(W), g.norm_w = norm ? norm->as<uint16_t>() : nullptr, g.in_ll = in_ll, g.out_ll = out_ll, g.res_ll = res_ll;
-        g.N = N, g.K = K, g.KC = stream_kc(K), g.gran = epi == EPI_SWIGLU ? 4 : 2, g.pro = pro, g.epi = epi, g.layered = layered;
+        g.W = d.w.p, g.norm_w = norm ? norm->as<uint16_t>() : nullptr, g.in_ll = in_ll, g.out_ll = out_ll, g.res_ll = res_ll;
+        g.N = N, g.K = K, g.fmt = d.fmt, g.pro = pro, g.epi = epi, g.layered = layered;
+        if (d.fmt == WF_BF16) g.KC = stream_kc(K), g.gran = epi == EPI_SWIGLU ? 4 : 2;
+        else g.KC = stream_kc_packed(K), g.gran = 16, g.scales = d.scales.p;
+        if (lora_a && lora_a->p) {
+            g.lora_a = lora_a->as<uint16_t>(), g.lora_b = d.lora_b.as<uint16_t>(), g.n_a = slices * rank, g.ax_slices = slices;
+            g.slice_rows0 = m->Hl * hd, g.slice_rows1 = (m->Hl + m->KVl) * hd;
+            g.ax_ll = ax_ll + size_t(which) * kStMaxRows * 128;
+        }
         return g;
     };
-    P.g[0] = gemv(l0.wqkv.w.p, &l0.attn_norm, x_ll, qkv_ll, nullptr, QKVN, D, PRO_RMSNORM, EPI_NONE, 1);
-    P.g[1] = gemv(l0.wo.w.p, nullptr, attn_ll, h_ll, x_ll, D, QO, PRO_NONE, EPI_RESIDUAL, 1);
-    P.g[2] = gemv(l0.w13.w.p, &l0.ffn_norm, h_ll, z_ll, nullptr, 2 * m->Fl, D, PRO_RMSNORM, EPI_SWIGLU, 1);
-    P.g[3] = gemv(l0.w2.w.p, nullptr, z_ll, x_ll, h_ll, D, m->Fl, PRO_NONE, EPI_RESIDUAL, 1);
-    P.g[4] = gemv(m->tok.w.p, &m->norm, x_ll, nullptr, nullptr, m->Vl, D, PRO_RMSNORM, EPI_NONE, 0);
+    const dlinear& head = m->tied ? m->tok : m->out;
+    P.g[0] = gemv(l0.wqkv, &l0.lora_a_qkv, 3, 0, &l0.attn_norm, x_ll, qkv_ll, nullptr, QKVN, D, PRO_RMSNORM, EPI_NONE, 1);
+    P.g[0].qkv_map = Q; // the int4 q|k|v rows were packed as rope pairs (mc_llama_finalize)
+    P.g[1] = gemv(l0.wo, &l0.lora_a_o, 1, 1, nullptr, attn_ll, h_ll, x_ll, D, QO, PRO_NONE, EPI_RESIDUAL, 1);
+    P.g[2] = gemv(l0.w13, &l0.lora_a_13, 2, 2, &l0.ffn_norm, h_ll, z_ll, nullptr, 2 * m->Fl, D, PRO_RMSNORM, EPI_SWIGLU, 1);
+    P.g[3] = gemv(l0.w2, &l0.lora_a_2, 1, 3, nullptr, z_ll, x_ll, h_ll, D, m->Fl, PRO_NONE, EPI_RESIDUAL, 1);
+    P.g[4] = gemv(head, nullptr, 0, 0, &m->norm, x_ll, nullptr, nullptr, m->Vl, D, PRO_RMSNORM, EPI_NONE, 0);
+    if (m->tied) P.g[4].W = m->tok.w.as<uint16_t>() + size_t(c.tp_rank) * m->Vl * D;
     P.g[4].y = m->logits.as<uint16_t>();
+    P.lora_rank = rank, P.lora_scale = bf16_bits_to_f32(f32_to_bf16_bits(c.lora_scale));
+    P.tok_fmt = m->tok.fmt, P.tok_scales = m->tok.scales.as<float>();
     P.layer_stride = m->layer_stride, P.kv_layer_stride = kv_layer_elems(m);
-    P.n_layers = c.n_layers, P.rows = rows, P.steps = steps, P.n_stages = geo.n_stages, P.act_pitch = geo.act_pitch, P.act_bytes = geo.act_bytes;
-    static const int env_pf = getenv("MC_STREAM_PF") ? atoi(getenv("MC_STREAM_PF")) : 0;
-    static const int env_pfm = getenv("MC_STREAM_PF_MODE") ? atoi(getenv("MC_STREAM_PF_MODE")) : 0;
-    P.pf_tiles = uint32_t(env_pf), P.pf_mode = uint32_t(env_pfm);
+    P.n_layers = c.n_layers, P.rows = rows, P.steps = steps, P.n_stages = geo.n_stages, P.act_pitch = geo.act_pitch, P.act_bytes = geo.act_bytes, P.sax_off = geo.sax_off;
     P.tag_base = m->st_seq << 16;
     static const int env_ns = getenv("MC_STREAM_POLL_NS") ? atoi(getenv("MC_STREAM_POLL_NS")) : 0;
     P.poll_ns = uint32_t(env_ns);
@@ -687,7 +718,7 @@ void launch_stream(mc_llama* m, launcher& L, uint32_t rows, int advance, uint32_
     P.kcache = m->kcache.as<uint16_t>(), P.vcache = m->vcache.as<uint16_t>(), P.fcos = m->fcos.as<float>(), P.fsin = m->fsin.as<float>();
     P.row_seq = m->row_seq.as<int32_t>(), P.pos = m->pos.as<int32_t>(), P.ids = m->ids.as<int32_t>();
     P.n_heads = m->Hl, P.n_kv_heads = m->KVl, P.head_dim = hd, P.max_seq = c.max_seq_len, P.vocab = c.vocab, P.scale = m->scale_bf16;
-    P.embed_table = m->tok.w.as<uint16_t>();
+    P.embed_table = m->tok.w.p;
     P.am_ll = ll + m->st_off[6], P.ids_ll = ll + m->st_off[7];
     P.out_log = m->out_log.as<int32_t>(), P.step_counter = m->step_counter.as<int32_t>(), P.advance = advance;
     P.err = m->errflag.as<int>();
@@ -699,7 +730,7 @@ void launch_stream(mc_llama* m, launcher& L, uint32_t rows, int advance, uint32_
     attr[0].val.cooperative = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
     L.mark();
-    MC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, decode_stream_kernel, P));
+    MC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, stream_kernel_of(Q, hd), P));
     L.count++;
     m->dev->launches.fetch_add(1);
 }
@@ -1041,23 +1072,38 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
         // QLoRA layout (huggingface/llama.h:152-171): int4-range weights packed two per byte in mma fragment order +
         // bf16 r(scale) per 32 weights + LoRA A/B in bf16; int8 per-row tables for tok_embeddings / output.
         const uint32_t rank = c.lora_rank;
-        for (dlayer& ly : m->layers) {
-            ly.attn_norm.alloc(size_t(D) * 2), ly.ffn_norm.alloc(size_t(D) * 2);
-            ly.wqkv.N = QKVN, ly.wqkv.K = D;
-            ly.wo.N = D, ly.wo.K = QOl;
-            ly.w13.N = 2 * m->Fl, ly.w13.K = D;
-            ly.w2.N = D, ly.w2.K = m->Fl;
-            for (dlinear* d : {&ly.wqkv, &ly.wo, &ly.w13, &ly.w2}) {
-                MC_REQUIRE(d->K % 256 == 0 && d->N % 2 == 0, "quantised layout: K must be a multiple of 256");
-                d->fmt = WF_W4;
-                d->w.alloc(w4_bytes(d->N, d->K));
-                d->scales.alloc(w4_scale_bytes(d->N, d->K));
-                d->lora_b.alloc(size_t(d->N) * rank * 2);
+        // one arena with a fixed stride per layer (the streaming kernel indexes by layer): norms | per linear: packed weights,
+        // packed scales, LoRA B, stacked LoRA A.  The reference-layout staging (q8, s32) is separate and released by
+        // mc_llama_finalize.
+        auto al = [](size_t n) { return (n + 255) & ~size_t(255); };
+        struct shape {
+            uint32_t N, K;
+        } const sh[4] = {{QKVN, D}, {D, QOl}, {2 * m->Fl, D}, {D, m->Fl}};
+        const uint32_t a_rows[4] = {3 * rank, rank, 2 * rank, rank};
+        size_t stride = 2 * al(size_t(D) * 2);
+        for (int i = 0; i < 4; i++) {
+            MC_REQUIRE(sh[i].K % 256 == 0 && sh[i].N % 2 == 0, "quantised layout: K must be a multiple of 256");
+            stride += al(w4_bytes(sh[i].N, sh[i].K)) + al(w4_scale_bytes(sh[i].N, sh[i].K)) + al(size_t(sh[i].N) * rank * 2) + al(size_t(a_rows[i]) * sh[i].K * 2);
+        }
+        m->layer_stride = stride;
+        m->layer_arena.alloc(stride * c.n_layers);
+        for (uint32_t li = 0; li < c.n_layers; li++) {
+            dlayer& ly = m->layers[li];
+            char* base = m->layer_arena.as<char>() + size_t(li) * stride;
+            ly.attn_norm.view(base, size_t(D) * 2), base += al(size_t(D) * 2);
+            ly.ffn_norm.view(base, size_t(D) * 2), base += al(size_t(D) * 2);
+            dlinear* lin[4] = {&ly.wqkv, &ly.wo, &ly.w13, &ly.w2};
+            dbuf* la[4] = {&ly.lora_a_qkv, &ly.lora_a_o, &ly.lora_a_13, &ly.lora_a_2};
+            for (int i = 0; i < 4; i++) {
+                dlinear* d = lin[i];
+                d->N = sh[i].N, d->K = sh[i].K, d->fmt = WF_W4;
+                d->w.view(base, w4_bytes(d->N, d->K)), base += al(w4_bytes(d->N, d->K));
+                d->scales.view(base, w4_scale_bytes(d->N, d->K)), base += al(w4_scale_bytes(d->N, d->K));
+                d->lora_b.view(base, size_t(d->N) * rank * 2), base += al(size_t(d->N) * rank * 2);
+                la[i]->view(base, size_t(a_rows[i]) * d->K * 2), base += al(size_t(a_rows[i]) * d->K * 2);
                 d->q8.alloc(size_t(d->N) * d->K);
                 d->s32.alloc(size_t(d->N) * (d->K / 32) * 4);
             }
-            ly.lora_a_qkv.alloc(size_t(3) * rank * D * 2), ly.lora_a_o.alloc(size_t(rank) * QOl * 2);
-            ly.lora_a_13.alloc(size_t(2) * rank * D * 2), ly.lora_a_2.alloc(size_t(rank) * m->Fl * 2);
         }
         m->tok.N = c.vocab, m->tok.K = D, m->tok.fmt = WF_W8ROW;
         m->tok.w.alloc(size_t(c.vocab) * D);      // natural row-major int8: the embedding gather reads whole rows
@@ -1119,9 +1165,9 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
         // tagged-word exchange buffers of the streaming kernel (8 bytes per word = two bf16 + tag)
         const size_t R8 = kStMaxRows;
         m->st_sc_words = (c.max_seq_len + 1) / 2 + 1;
-        const size_t words[8] = {R8 * D / 2, R8 * D / 2, R8 * m->Fl / 2, R8 * QKVN / 2, R8 * QOl / 2, R8 * m->Hl * m->st_sc_words, R8 * 256 * 2, 64};
+        const size_t words[9] = {R8 * D / 2, R8 * D / 2, R8 * m->Fl / 2, R8 * QKVN / 2, R8 * QOl / 2, R8 * m->Hl * m->st_sc_words, R8 * 256 * 2, 64, 4 * R8 * 128};
         size_t total = 0;
-        for (int i = 0; i < 8; i++) m->st_off[i] = total, total += (words[i] + 31) & ~size_t(31);
+        for (int i = 0; i < 9; i++) m->st_off[i] = total, total += (words[i] + 31) & ~size_t(31);
         m->st_ll.alloc(total * 8);
         MC_CUDA_CHECK(cudaMemset(m->st_ll.p, 0, m->st_ll.bytes));
     }

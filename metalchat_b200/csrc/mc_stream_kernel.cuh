@@ -33,7 +33,11 @@ namespace mc {
 constexpr int kStWarps = 8;                           // consumer warps
 constexpr int kStConsumers = kStWarps * 32;           // 256 consumer threads
 constexpr int kStEpiThreads = 64;                     // two epilogue warps: join the k-slices, finish and publish the outputs
-constexpr int kStThreads = kStConsumers + kStEpiThreads + 32; // + one producer warp
+#ifdef ST_USE_SETMAXNREG
+constexpr int kStThreads = kStConsumers + kStEpiThreads + 64;
+#else
+constexpr int kStThreads = kStConsumers + kStEpiThreads + 32;
+#endif
 constexpr int kStTileRows = 16;                       // weight rows per tile (the m of the mma)
 constexpr int kStMaxKC = 1024;                        // k elements per tile row
 constexpr int kStPad = 64;                            // bytes of padding per staged row
@@ -51,14 +55,22 @@ constexpr int kStRedBytes = kStRedBufs * kStWarps * 16 * 8 * 4;
 // arrival counter, no separate flag round trip (the scheme of low-latency collectives).  Every GEMV phase needs the whole
 // input vector, i.e. data from every CTA, so the polling doubles as the phase barrier.
 struct st_gemv {
-    const uint16_t* W;       // [N, K] bf16 row-major; layer l adds l * layer_stride bytes when `layered`
-    const uint16_t* norm_w;  // PRO_RMSNORM: [K] (same layer stride)
+    const void* W;           // WF_BF16: [N, K] bf16 row-major; WF_W4 / WF_W8ROW: fragment-packed (mc_quant_kernels.cuh).
+                             // layer l adds l * layer_stride bytes when `layered` (also to norm_w, scales, lora_a, lora_b)
+    const uint16_t* norm_w;  // PRO_RMSNORM: [K]
+    const void* scales;      // WF_W4: packed bf16 group scales; WF_W8ROW: fp32 [N]
+    const uint16_t* lora_a;  // quantised layers: stacked adaptor A rows [n_a, K] bf16, or null
+    const uint16_t* lora_b;  // [N, rank] bf16
     const uint64_t* in_ll;   // tagged input rows [rows][K/2] (null: embedding gather)
     uint64_t* out_ll;        // tagged output rows: [rows][N/2], EPI_SWIGLU [rows][N/4]; null for the head
     const uint64_t* res_ll;  // EPI_RESIDUAL: [rows][N/2], written earlier by this same CTA
+    uint64_t* ax_ll;         // tagged r(A . x) of this phase: [rows][n_a/2]
     uint16_t* y;             // head only: plain bf16 logits [rows][N]
-    uint32_t N, K, KC, gran; // gran = row granularity of the CTA split (2; 4 for the gate/up pairs)
-    int32_t pro, epi, layered;
+    uint32_t N, K, KC, gran; // KC: k per tile; gran = row granularity of the CTA split (bf16: 2, 4 for gate/up pairs; packed: 16)
+    uint32_t n_a;            // rows of lora_a (0: no adaptor)
+    uint32_t ax_slices, slice_rows0, slice_rows1; // which rank-wide slice of ax a weight row uses (see lora_slice)
+    int32_t fmt, pro, epi, layered;
+    int32_t qkv_map;         // packed layouts: block rows are the rope pairs (j, j + hd/2) of EPI_QKV packing
 };
 
 struct st_params {
@@ -66,10 +78,13 @@ struct st_params {
     size_t layer_stride;     // bytes between consecutive layers in the weight arena
     size_t kv_layer_stride;  // elements between consecutive layers in the KV cache
     uint32_t n_layers, rows, steps, n_stages;
-    uint32_t pf_tiles;       // tiles of L2 prefetch distance ahead of the ring (0 = none)
-    uint32_t pf_mode;        // 0: prefetch.global.L2 per line, 1: cp.async.bulk.prefetch.L2 per row
+    uint32_t lora_rank;
+    float lora_scale;        // r(scale) as fp32
+    int32_t tok_fmt;         // WF_BF16, or WF_W8ROW: int8 embedding rows with one fp32 scale per row
+    const float* tok_scales;
     uint32_t act_pitch;      // bytes between staged activation rows
     uint32_t act_bytes;
+    uint32_t sax_off;        // quantised models: offset of the [8][n_a] r(A . x) scratch inside the activation region
     uint32_t tag_base;       // tags of this launch are tag_base + phase + 1
     uint32_t poll_ns;
     float eps;
@@ -88,7 +103,7 @@ struct st_params {
     uint32_t n_heads, n_kv_heads, head_dim, max_seq, vocab;
     float scale;             // r(1/sqrt(hd)) (nn/attention.h:88,115)
     // embedding
-    const uint16_t* embed_table;
+    const void* embed_table;
     // sampler tail
     uint64_t* am_ll;         // [rows][G][2]: per-CTA argmax partial {value bits, index}
     uint64_t* ids_ll;        // [rows]: sampled id of the step, tagged with the head phase
@@ -279,74 +294,118 @@ struct st_pipe {
     }
 };
 
-// ---- producer: the static schedule of weight tiles of this CTA ----------------------------------------------------------
-// A tile = up to 16 consecutive weight rows x KC k of one GEMV phase.  The iterator enumerates the tiles of this CTA in
-// consumption order over all phases, layers and steps of the launch.  (A second iterator can run `pf_tiles` ahead and
-// only ask the L2 for the rows; measured on B200 this LOWERS throughput - demand loads land on in-flight fills - so it
-// is off by default and kept as an experiment knob.)
-struct st_tile {
-    const char* src;      // first row chunk
-    size_t row_stride;    // bytes between consecutive rows in global memory
-    uint32_t nr, row_bytes, pitch;
+// ---- the static schedule of weight tiles of this CTA --------------------------------------------------------------------
+// A GEMV phase of this CTA is a list of BLOCKS of up to 16 output rows; a block is a list of TILES (k-chunks) that travel
+// through the ring.  Quantised layers put one extra block in front: two rows of the stacked LoRA adaptor A (bf16), owned
+// by CTA c < n_a / 2, whose output r(A . x) every CTA needs in its epilogue (quantization/lora.h:115-122).
+//   bf16 block  = rows [r0, r0 + nr) of a row-major matrix, tile = nr row chunks of KC k, one bulk copy per row,
+//                 staged with a 64-byte row pad;
+//   packed block = one super-unit of 16 rows in mma fragment order, tile = KC k = one contiguous run of weights
+//                 (+ one run of group scales for int4).
+enum { ST_T_ROWS = 0, ST_T_W4 = 1, ST_T_W8 = 2 };
+constexpr uint32_t kStW4ScaleOff = 16384; // int4 tiles: group scales sit behind the (at most 16 KiB of) weights
+struct st_block {
+    uint32_t r0, nr;   // bf16: first row / rows; packed: super-unit index / 16
+    bool is_a;         // the LoRA-A block
 };
-struct st_tile_iter {
-    uint32_t step = 0, li = 0, gi = 0, r0 = 0, re = 0, kc = 0;
-    bool ranged = false;
+// the blocks of phase g for this CTA: the A block (if owned), then the main blocks [b0, b1)
+struct st_range {
+    bool has_a;
+    uint32_t b0, b1;   // bf16: rows, step 16; packed: super-units, step 1
+    __device__ __forceinline__ st_range(const st_gemv& g, bool quant)
+    {
+        has_a = quant && g.n_a != 0 && 2 * blockIdx.x < g.n_a;
+        if (!quant || g.fmt == WF_BF16) st_my_rows(g.N, g.gran, b0, b1);
+        else st_my_rows(g.N >> 4, 1, b0, b1);
+    }
+};
+__device__ __forceinline__ const char* st_layer_ptr(const st_params& P, const st_gemv& g, const void* p, uint32_t li)
+{
+    return static_cast<const char*>(p) + (g.layered ? size_t(li) * P.layer_stride : 0);
+}
+struct st_tile {
+    int kind;
+    const char* src;      // ST_T_ROWS: first row chunk; packed: the weights
+    const char* src2;     // ST_T_W4: the group scales
+    size_t row_stride;    // ST_T_ROWS: bytes between consecutive rows in global memory
+    uint32_t nr, bytes, bytes2, pitch;
+};
+template <bool Q> struct st_tile_iter {
+    uint32_t step = 0, li = 0, gi = 0, blk = 0, b1 = 0, kc = 0;
+    int stage = 0; // 0: phase not started, 1: A block, 2: main blocks
+    __device__ __forceinline__ void next_phase(const st_params& P)
+    {
+        stage = 0;
+        if (gi == 4) gi = 0, li = 0, step++;
+        else if (gi == 3) {
+            li++;
+            gi = li == P.n_layers ? 4 : 0;
+        } else gi++;
+    }
     __device__ __forceinline__ bool next(const st_params& P, st_tile& t)
     {
         for (;;) {
             if (step >= P.steps) return false;
             const st_gemv& g = P.g[gi];
-            if (!ranged) {
-                st_my_rows(g.N, g.gran, r0, re);
-                kc = 0, ranged = true;
+            if (stage == 0) {
+                const st_range r(g, Q);
+                blk = r.b0, b1 = r.b1, kc = 0;
+                stage = r.has_a ? 1 : 2;
             }
-            if (r0 < re) {
-                const char* W = reinterpret_cast<const char*>(g.W) + (g.layered ? size_t(li) * P.layer_stride : 0);
-                t.nr = min(uint32_t(kStTileRows), re - r0);
-                t.src = W + (size_t(r0) * g.K + kc) * 2;
-                t.row_stride = size_t(g.K) * 2, t.row_bytes = g.KC * 2, t.pitch = g.KC * 2 + kStPad;
-                kc += g.KC;
-                if (kc >= g.K) kc = 0, r0 += kStTileRows;
+            if (Q && stage == 1) {
+                const uint32_t kca = P.g[gi].K % 1024 == 0 ? 1024u : (g.K % 512 == 0 ? 512u : 256u);
+                t.kind = ST_T_ROWS, t.nr = 2;
+                t.src = st_layer_ptr(P, g, g.lora_a, li) + (size_t(2 * blockIdx.x) * g.K + kc) * 2;
+                t.row_stride = size_t(g.K) * 2, t.bytes = kca * 2, t.pitch = kca * 2 + kStPad;
+                kc += kca;
+                if (kc >= g.K) kc = 0, stage = 2;
                 return true;
             }
-            ranged = false;
-            if (gi == 4) gi = 0, li = 0, step++;
-            else if (gi == 3) {
-                li++;
-                gi = li == P.n_layers ? 4 : 0;
-            } else gi++;
+            if (blk < b1) {
+                const char* W = st_layer_ptr(P, g, g.W, li);
+                if (!Q || g.fmt == WF_BF16) {
+                    t.kind = ST_T_ROWS, t.nr = min(uint32_t(kStTileRows), b1 - blk);
+                    t.src = W + (size_t(blk) * g.K + kc) * 2;
+                    t.row_stride = size_t(g.K) * 2, t.bytes = g.KC * 2, t.pitch = g.KC * 2 + kStPad;
+                } else if (g.fmt == WF_W4) {
+                    // [super][ktile of 64 k][lane][16 B] and scales [super][ktile][8][4] bf16
+                    const size_t kt0 = size_t(blk) * (g.K >> 6) + (kc >> 6);
+                    t.kind = ST_T_W4, t.src = W + kt0 * 512, t.bytes = (g.KC >> 6) * 512;
+                    t.src2 = st_layer_ptr(P, g, g.scales, li) + kt0 * 64, t.bytes2 = (g.KC >> 6) * 64;
+                } else {
+                    // [super][ktile of 32 k][lane][16 B]
+                    const size_t kt0 = size_t(blk) * (g.K >> 5) + (kc >> 5);
+                    t.kind = ST_T_W8, t.src = W + kt0 * 512, t.bytes = (g.KC >> 5) * 512;
+                }
+                kc += g.KC;
+                if (kc >= g.K) kc = 0, blk += (!Q || g.fmt == WF_BF16) ? uint32_t(kStTileRows) : 1u;
+                return true;
+            }
+            next_phase(P);
         }
     }
 };
-__device__ __forceinline__ void st_prefetch_tile(const st_tile& t, uint32_t lane, uint32_t mode)
-{
-    if (mode == 1) {
-        if (lane < t.nr) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(t.src + size_t(lane) * t.row_stride), "r"(t.row_bytes) : "memory");
-    } else {
-        const uint32_t lpr = t.row_bytes >> 7, lines = t.nr * lpr;
-        for (uint32_t i = lane; i < lines; i += 32) {
-            const uint32_t r = i / lpr, o = (i - r * lpr) << 7;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(t.src + size_t(r) * t.row_stride + o) : "memory");
-        }
-    }
-}
-__device__ __forceinline__ void st_producer(const st_params& P, const st_ctx& c)
+template <bool Q> __device__ __forceinline__ void st_producer(const st_params& P, const st_ctx& c)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t policy = policy_evict_first();
     st_pipe pp{0, 0};
-    st_tile_iter ld, pf;
-    st_tile t, tp;
-    for (uint32_t i = 0; i < P.pf_tiles; i++)
-        if (pf.next(P, tp)) st_prefetch_tile(tp, lane, P.pf_mode);
+    st_tile_iter<Q> ld;
+    st_tile t;
     while (ld.next(P, t)) {
-        if (P.pf_tiles && pf.next(P, tp)) st_prefetch_tile(tp, lane, P.pf_mode);
         st_mbar_wait(c, c.empty0 + pp.stage * 8, pp.parity ^ 1u);
-        const uint32_t full = c.full0 + pp.stage * 8;
-        if (lane == 0) mbar_expect_tx(full, t.nr * t.row_bytes);
-        __syncwarp();
-        if (lane < t.nr) bulk_g2s(c.ring_addr + pp.stage * kStStageBytes + lane * t.pitch, t.src + size_t(lane) * t.row_stride, t.row_bytes, full, policy);
+        const uint32_t full = c.full0 + pp.stage * 8, dst = c.ring_addr + pp.stage * kStStageBytes;
+        if (!Q || t.kind == ST_T_ROWS) {
+            if (lane == 0) mbar_expect_tx(full, t.nr * t.bytes);
+            __syncwarp();
+            if (lane < t.nr) bulk_g2s(dst + lane * t.pitch, t.src + size_t(lane) * t.row_stride, t.bytes, full, policy);
+        } else {
+            if (lane == 0) {
+                mbar_expect_tx(full, t.bytes + (t.kind == ST_T_W4 ? t.bytes2 : 0u));
+                bulk_g2s(dst, t.src, t.bytes, full, policy);
+                if (t.kind == ST_T_W4) bulk_g2s(dst + kStW4ScaleOff, t.src2, t.bytes2, full, policy);
+            }
+        }
         pp.advance(P.n_stages);
     }
 }
@@ -355,7 +414,7 @@ __device__ __forceinline__ void st_producer(const st_params& P, const st_ctx& c)
 // Polls the tagged input rows (or gathers the embedding rows), applies RMSNorm when the phase has one, and leaves the rows
 // as bf16 in shared memory.  `xres_ll` (first phase of a step only): this CTA also publishes the raw embedding values of
 // the rows it will later own in the wo phase - they are the first residual.
-__device__ __forceinline__ void st_stage_input(const st_params& P, const st_gemv& g, uint32_t li, const st_ctx& c, bool embed, uint32_t step, uint32_t tag_in,
+template <bool Q> __device__ __forceinline__ void st_stage_input(const st_params& P, const st_gemv& g, uint32_t li, const st_ctx& c, bool embed, uint32_t step, uint32_t tag_in,
                                                uint32_t tag_out)
 {
     constexpr int NB = 4; // tagged 16-byte loads in flight per thread
@@ -386,13 +445,28 @@ __device__ __forceinline__ void st_stage_input(const st_params& P, const st_gemv
             uint64_t a[NB], b[NB];
             if (embed) {
                 // embedding gather fused into the first phase (kernel/embedding.metal:38-66)
-                const uint16_t* xr = P.embed_table + size_t(sids[m]) * K;
+                if (!Q || P.tok_fmt == WF_BF16) {
+                    const uint16_t* xr = static_cast<const uint16_t*>(P.embed_table) + size_t(sids[m]) * K;
 #pragma unroll
-                for (int j = 0; j < NB; j++) {
-                    const uint32_t w = w0 + j * (kStConsumers * 2);
-                    if (w < n_words) {
-                        const uint2 v = *reinterpret_cast<const uint2*>(xr + w * 2);
-                        a[j] = v.x, b[j] = v.y;
+                    for (int j = 0; j < NB; j++) {
+                        const uint32_t w = w0 + j * (kStConsumers * 2);
+                        if (w < n_words) {
+                            const uint2 v = *reinterpret_cast<const uint2*>(xr + w * 2);
+                            a[j] = v.x, b[j] = v.y;
+                        }
+                    }
+                } else {
+                    // lora_embedding: int8 row with one scale, x = r(r(q) * r(s))  (quantization/lora.h:160-170, kernel/mul.metal:76-77)
+                    const int8_t* xr = static_cast<const int8_t*>(P.embed_table) + size_t(sids[m]) * K;
+                    const float sc = rbf(P.tok_scales[sids[m]]);
+#pragma unroll
+                    for (int j = 0; j < NB; j++) {
+                        const uint32_t w = w0 + j * (kStConsumers * 2);
+                        if (w < n_words) {
+                            const char4 q = *reinterpret_cast<const char4*>(xr + w * 2);
+                            a[j] = pack2(__fmul_rn(float(q.x), sc), __fmul_rn(float(q.y), sc));
+                            b[j] = pack2(__fmul_rn(float(q.z), sc), __fmul_rn(float(q.w), sc));
+                        }
                     }
                 }
             } else {
@@ -463,6 +537,7 @@ __device__ __forceinline__ void st_stage_input(const st_params& P, const st_gemv
 // ---- one GEMV phase: the mma warps ---------------------------------------------------------------------------------------
 // Each of the 8 mma warps multiplies its k-slice of every tile and hands the 16 x 8 partial block to the epilogue warps
 // through one of kStRedBufs buffers (ready / free mbarriers): the mma warps never wait for an epilogue to finish.
+// Partial block layout: [warp][block row][col], block row = position of the output row inside the block.
 struct st_blk {
     uint32_t buf, parity; // next partial buffer and the parity of its current use
     __device__ __forceinline__ void advance()
@@ -470,100 +545,298 @@ struct st_blk {
         if (++buf == uint32_t(kStRedBufs)) buf = 0, parity ^= 1u;
     }
 };
-__device__ __forceinline__ void st_mma_gemv(const st_params& P, const st_gemv& g, const st_ctx& c, st_pipe& cp, st_blk& bl)
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
 {
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a)
+{
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a));
+    return r;
+}
+// hands acc (c0,c1 -> block row ra; c2,c3 -> block row rb) to the epilogue warps
+__device__ __forceinline__ void st_hand_over(const st_ctx& c, st_blk& bl, const float (&acc)[4], uint32_t ra, uint32_t rb)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = lane & 3;
+    st_mbar_wait(c, c.fre0 + bl.buf * 8, bl.parity ^ 1u); // the epilogue of the previous use of this buffer is done
+    float* rw = c.red + bl.buf * (kStWarps * 128) + warp * 128;
+    *reinterpret_cast<float2*>(rw + ra * 8 + 2 * t) = make_float2(acc[0], acc[1]);
+    *reinterpret_cast<float2*>(rw + rb * 8 + 2 * t) = make_float2(acc[2], acc[3]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(c.rdy0 + bl.buf * 8);
+    bl.advance();
+}
+// one block of bf16 rows: K / kc tiles of `kc` k, the 64-byte padded row-major staging
+__device__ __forceinline__ void st_mma_rows(const st_params& P, const st_ctx& c, st_pipe& cp, st_blk& bl, uint32_t K, uint32_t kc_tile)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t gq = lane >> 2, t = lane & 3;
-    const uint32_t pitch = g.KC * 2 + kStPad;
-    const uint32_t kw = warp * (g.KC / kStWarps); // this warp's k-slice inside a tile
-    const uint32_t ksteps = g.KC / kStWarps / 32;
-    const uint32_t brow = gq < P.rows ? gq : 0;   // batch row of this lane's B fragment (unused columns read row 0)
+    const uint32_t pitch = kc_tile * 2 + kStPad;
+    const uint32_t kw = warp * (kc_tile / kStWarps); // this warp's k-slice inside a tile
+    const uint32_t ksteps = kc_tile / kStWarps / 32;
+    const uint32_t brow = gq < P.rows ? gq : 0;      // batch row of this lane's B fragment (unused columns read row 0)
     const uint32_t b_base = c.act_addr + brow * P.act_pitch + (kw + t * 8) * 2;
     const uint32_t a_off = gq * pitch + (kw + t * 8) * 2;
-    uint32_t rb, re;
-    st_my_rows(g.N, g.gran, rb, re);
-    for (uint32_t r0 = rb; r0 < re; r0 += kStTileRows) {
-        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        for (uint32_t kc = 0; kc < g.K; kc += g.KC) {
-            st_mbar_wait(c, c.full0 + cp.stage * 8, cp.parity);
-            const uint32_t tile = c.ring_addr + cp.stage * kStStageBytes + a_off;
-            const uint32_t bk = b_base + kc * 2;
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (uint32_t kc = 0; kc < K; kc += kc_tile) {
+        st_mbar_wait(c, c.full0 + cp.stage * 8, cp.parity);
+        const uint32_t tile = c.ring_addr + cp.stage * kStStageBytes + a_off;
+        const uint32_t bk = b_base + kc * 2;
+        // the k permutation (lane t reads 8 consecutive k) is applied to both operands
 #pragma unroll 4
-            for (uint32_t s = 0; s < ksteps; s++) {
-                const uint4 alo = lds128(tile + s * 64);
-                const uint4 ahi = lds128(tile + 8 * pitch + s * 64);
-                const uint4 b = lds128(bk + s * 64);
-                mma_bf16_16816(acc, alo.x, ahi.x, alo.y, ahi.y, b.x, b.y);
-                mma_bf16_16816(acc, alo.z, ahi.z, alo.w, ahi.w, b.z, b.w);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(c.empty0 + cp.stage * 8);
-            cp.advance(P.n_stages);
+        for (uint32_t s = 0; s < ksteps; s++) {
+            const uint4 alo = lds128(tile + s * 64);
+            const uint4 ahi = lds128(tile + 8 * pitch + s * 64);
+            const uint4 b = lds128(bk + s * 64);
+            mma_bf16_16816(acc, alo.x, ahi.x, alo.y, ahi.y, b.x, b.y);
+            mma_bf16_16816(acc, alo.z, ahi.z, alo.w, ahi.w, b.z, b.w);
         }
-        st_mbar_wait(c, c.fre0 + bl.buf * 8, bl.parity ^ 1u); // the epilogue of the previous use of this buffer is done
-        float* rw = c.red + bl.buf * (kStWarps * 128) + warp * 128;
-        *reinterpret_cast<float2*>(rw + gq * 8 + 2 * t) = make_float2(acc[0], acc[1]);
-        *reinterpret_cast<float2*>(rw + (gq + 8) * 8 + 2 * t) = make_float2(acc[2], acc[3]);
         __syncwarp();
-        if (lane == 0) mbar_arrive(c.rdy0 + bl.buf * 8);
-        bl.advance();
+        if (lane == 0) mbar_arrive(c.empty0 + cp.stage * 8);
+        cp.advance(P.n_stages);
+    }
+    st_hand_over(c, bl, acc, gq, gq + 8);
+}
+// one super-unit of packed weights: in-register dequant with the reference's two roundings r(r(q) * r(s))
+// (kernel/mul.metal:76-77), then mma; see gemv_q_kernel for the fragment layout
+template <int FMT>
+__device__ __forceinline__ void st_mma_packed(const st_params& P, const st_gemv& g, const st_ctx& c, st_pipe& cp, st_blk& bl, float rs0, float rs1)
+{
+    constexpr uint32_t KT = FMT == WF_W4 ? 64 : 32;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t gq = lane >> 2, t = lane & 3;
+    const uint32_t kts = g.KC / KT;                                   // k-tiles per ring tile
+    const uint32_t per = (kts + kStWarps - 1) / kStWarps;             // k-tiles of this warp
+    const uint32_t kt_b = min(kts, warp * per), kt_e = min(kts, kt_b + per);
+    const uint32_t brow = gq < P.rows ? gq : 0;
+    const uint32_t xb = c.act_addr + brow * P.act_pitch + 4 * t;      // B fragment base of this lane
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc2[4] = {0.0f, 0.0f, 0.0f, 0.0f}; // two chains: consecutive mma do not wait for each other
+    for (uint32_t kc = 0; kc < g.K; kc += g.KC) {
+        st_mbar_wait(c, c.full0 + cp.stage * 8, cp.parity);
+        const uint32_t tile = c.ring_addr + cp.stage * kStStageBytes;
+#pragma unroll 2
+        for (uint32_t kt = kt_b; kt < kt_e; kt++) {
+            const uint4 wv = lds128(tile + (kt * 32 + lane) * 16);
+            const uint32_t xk = xb + (kc + kt * KT) * 2;
+            const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
+            if (FMT == WF_W4) {
+                const uint2 sv = lds64(tile + kStW4ScaleOff + (kt * 8 + gq) * 8);
+                // scales of (row r0, row r1) for k-groups 0 and 1 of this k-tile, as (s,s) bf16x2
+                const uint32_t s_g0 = __byte_perm(sv.x, 0, 0x1010), s_g1 = __byte_perm(sv.x, 0, 0x3232);
+                const uint32_t s_h0 = __byte_perm(sv.y, 0, 0x1010), s_h1 = __byte_perm(sv.y, 0, 0x3232);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t w = words[j];
+                    const uint32_t sg = j < 2 ? s_g0 : s_g1, sh = j < 2 ? s_h0 : s_h1;
+                    const uint32_t a0 = hmul2_bf16(hsub2_bf16((w & 0x000f000fu) | 0x43004300u, 0x43084308u), sg);
+                    const uint32_t a1 = hmul2_bf16(hsub2_bf16(((w >> 4) & 0x000f000fu) | 0x43004300u, 0x43084308u), sh);
+                    const uint32_t a2 = hmul2_bf16(hsub2_bf16(((w >> 8) & 0x000f000fu) | 0x43004300u, 0x43084308u), sg);
+                    const uint32_t a3 = hmul2_bf16(hsub2_bf16(((w >> 12) & 0x000f000fu) | 0x43004300u, 0x43084308u), sh);
+                    if (j & 1) mma_bf16_16816(acc2, a0, a1, a2, a3, lds32(xk + j * 32), lds32(xk + j * 32 + 16));
+                    else mma_bf16_16816(acc, a0, a1, a2, a3, lds32(xk + j * 32), lds32(xk + j * 32 + 16));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const uint32_t lo = words[2 * j] ^ 0x80808080u, hi = words[2 * j + 1] ^ 0x80808080u;
+                    const uint32_t a0 = pack_bf16x2(__fmul_rn(s8_to_f32(lo, 0), rs0), __fmul_rn(s8_to_f32(lo, 1), rs0));
+                    const uint32_t a1 = pack_bf16x2(__fmul_rn(s8_to_f32(lo, 2), rs1), __fmul_rn(s8_to_f32(lo, 3), rs1));
+                    const uint32_t a2 = pack_bf16x2(__fmul_rn(s8_to_f32(hi, 0), rs0), __fmul_rn(s8_to_f32(hi, 1), rs0));
+                    const uint32_t a3 = pack_bf16x2(__fmul_rn(s8_to_f32(hi, 2), rs1), __fmul_rn(s8_to_f32(hi, 3), rs1));
+                    if (j & 1) mma_bf16_16816(acc2, a0, a1, a2, a3, lds32(xk + j * 32), lds32(xk + j * 32 + 16));
+                    else mma_bf16_16816(acc, a0, a1, a2, a3, lds32(xk + j * 32), lds32(xk + j * 32 + 16));
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(c.empty0 + cp.stage * 8);
+        cp.advance(P.n_stages);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) acc[i] += acc2[i];
+    // mma row g = unit su*8+g row r0, row g+8 = its row r1: rope pairs keep that order, adjacent-row units interleave
+    if (g.qkv_map) st_hand_over(c, bl, acc, gq, gq + 8);
+    else st_hand_over(c, bl, acc, 2 * gq, 2 * gq + 1);
+}
+__device__ __forceinline__ uint32_t st_kc_a(uint32_t K) { return K % 1024 == 0 ? 1024u : (K % 512 == 0 ? 512u : 256u); }
+template <bool Q> __device__ __forceinline__ void st_mma_gemv(const st_params& P, const st_gemv& g, const st_ctx& c, st_pipe& cp, st_blk& bl, uint32_t li)
+{
+    const st_range r(g, Q);
+    if (Q && r.has_a) st_mma_rows(P, c, cp, bl, g.K, st_kc_a(g.K));
+    if (!Q || g.fmt == WF_BF16) {
+        for (uint32_t r0 = r.b0; r0 < r.b1; r0 += kStTileRows) st_mma_rows(P, c, cp, bl, g.K, g.KC);
+    } else if (g.fmt == WF_W4) {
+        for (uint32_t su = r.b0; su < r.b1; su++) st_mma_packed<WF_W4>(P, g, c, cp, bl, 0.0f, 0.0f);
+    } else {
+        // int8 rows with one fp32 scale per row: the scales of the next super-unit are requested one block ahead
+        const uint32_t gq = (threadIdx.x & 31) >> 2;
+        const float* sc = reinterpret_cast<const float*>(st_layer_ptr(P, g, g.scales, li));
+        float s0 = 0.0f, s1 = 0.0f;
+        if (r.b0 < r.b1) s0 = sc[r.b0 * 16 + 2 * gq], s1 = sc[r.b0 * 16 + 2 * gq + 1];
+        for (uint32_t su = r.b0; su < r.b1; su++) {
+            float n0 = 0.0f, n1 = 0.0f;
+            if (su + 1 < r.b1) n0 = sc[(su + 1) * 16 + 2 * gq], n1 = sc[(su + 1) * 16 + 2 * gq + 1];
+            st_mma_packed<WF_W8ROW>(P, g, c, cp, bl, rbf(s0), rbf(s1));
+            s0 = n0, s1 = n1;
+        }
     }
 }
 
-// greedy argmax state of one epilogue thread (lowest index on ties)
+// greedy argmax state of one storing epilogue lane, one slot per column (lowest index on ties)
 struct st_best {
-    float v;
-    int32_t i;
+    float v[kStMaxRows];
+    int32_t i[kStMaxRows];
 };
 
 // ---- one GEMV phase: the epilogue warps ------------------------------------------------------------------------------------
-// Thread (row group, col) of the 16 x 8 output block joins the 8 k-slices in warp order and finishes `gran` consecutive rows.
-__device__ __forceinline__ void st_epi_gemv(const st_params& P, const st_gemv& g, const st_ctx& c, st_blk& bl, st_best& best, bool is_head, uint32_t tag_out)
+// Thread (row group, col) of the 16 x 8 output block joins the 8 k-slices in warp order and finishes `fin` consecutive rows
+// (two; four for the gate/up pairs) so that every store is one tagged word.
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
+__device__ __forceinline__ float st_lora_dot(const uint16_t* brow, const float* ax, uint32_t rank)
 {
+    float l = 0.0f;
+    for (uint32_t j = 0; j < rank; j += 8) {
+        const uint4 w = *reinterpret_cast<const uint4*>(brow + j);
+        l = fmaf(ax[j + 0], bf_lo(w.x), l), l = fmaf(ax[j + 1], bf_hi(w.x), l);
+        l = fmaf(ax[j + 2], bf_lo(w.y), l), l = fmaf(ax[j + 3], bf_hi(w.y), l);
+        l = fmaf(ax[j + 4], bf_lo(w.z), l), l = fmaf(ax[j + 5], bf_hi(w.z), l);
+        l = fmaf(ax[j + 6], bf_lo(w.w), l), l = fmaf(ax[j + 7], bf_hi(w.w), l);
+    }
+    return l;
+}
+template <bool Q> __device__ __forceinline__ void st_epi_gemv(const st_params& P, const st_gemv& g, const st_ctx& c, st_blk& bl, st_best& best, bool is_head, uint32_t li,
+                                            uint32_t tag_out, uint32_t res_tag)
+{
+    // Thread (block row, quarter): four consecutive lanes share one of the 16 block rows; each joins two of the eight
+    // k-slices and a quarter of the LoRA dot product, the quarters meet through two shuffles.  Rows meet their neighbours
+    // (pairs; gate/up quads) through shuffles too, so that every store is one tagged word.  Columns (batch rows) are looped.
     const uint32_t et = threadIdx.x - kStConsumers, lane = et & 31;
-    const uint32_t ecol = et & 7, egrp = et >> 3;
-    const uint32_t erow = egrp * g.gran;
-    const bool etask = erow < uint32_t(kStTileRows) && ecol < P.rows;
+    const uint32_t erow = et >> 2, sub = et & 3;
+    const uint32_t fin = g.epi == EPI_SWIGLU ? 4u : 2u;
     const uint32_t out_pitch = g.epi == EPI_SWIGLU ? g.N >> 2 : g.N >> 1;
-    uint32_t rb, re;
-    st_my_rows(g.N, g.gran, rb, re);
-    for (uint32_t r0 = rb; r0 < re; r0 += kStTileRows) {
-        const uint32_t nr = min(uint32_t(kStTileRows), re - r0);
-        const bool act = etask && erow < nr;
-        uint32_t resw = 0;
-        if (g.epi == EPI_RESIDUAL && act) resw = uint32_t(st_ll_load1(g.res_ll + size_t(ecol) * out_pitch + ((r0 + erow) >> 1)));
+    const bool storer = sub == 0 && (erow & (fin - 1)) == 0;
+    const st_range r(g, Q);
+    float* sax = reinterpret_cast<float*>(c.act + P.sax_off); // [8 rows][n_a] r(A . x) of this phase
+    if (Q && r.has_a) {
+        // the two adaptor rows owned by this CTA: ax = r(A . x) (quantization/lora.h:115), one tagged word per batch row
         st_mbar_wait(c, c.rdy0 + bl.buf * 8, bl.parity);
-        if (act) {
-            const float* rr = c.red + bl.buf * (kStWarps * 128) + erow * 8 + ecol;
+        if (et < P.rows) {
+            const float* rr = c.red + bl.buf * (kStWarps * 128) + et;
             float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
             for (int w = 0; w < kStWarps; w++) s0 += rr[w * 128], s1 += rr[w * 128 + 8];
-            const uint32_t R = r0 + erow;
-            const float y0 = rbf(s0), y1 = rbf(s1); // the bmm output buffer is T (kernel/bmm.metal:76)
-            if (g.epi == EPI_SWIGLU) {
-                // z = r(silu_T(g) * u), rows (2i, 2i+1) = (w1 row i, w3 row i)  (nn/transformer.h:57-59); two outputs per word
-                float s2 = 0.0f, s3 = 0.0f;
-#pragma unroll
-                for (int w = 0; w < kStWarps; w++) s2 += rr[w * 128 + 16], s3 += rr[w * 128 + 24];
-                const float z0 = __fmul_rn(silu_bf16(y0), y1), z1 = __fmul_rn(silu_bf16(rbf(s2)), rbf(s3));
-                st_ll_store(g.out_ll + size_t(ecol) * out_pitch + (R >> 2), pack2(z0, z1), tag_out);
-            } else if (g.epi == EPI_RESIDUAL) {
-                // h = r(x + a)  (nn/transformer.h:133,139)
-                st_ll_store(g.out_ll + size_t(ecol) * out_pitch + (R >> 1), pack2(__fadd_rn(bf_lo(resw), y0), __fadd_rn(bf_hi(resw), y1)), tag_out);
-            } else if (!is_head) {
-                st_ll_store(g.out_ll + size_t(ecol) * out_pitch + (R >> 1), pack2(y0, y1), tag_out);
-            } else {
-                *reinterpret_cast<uint32_t*>(g.y + size_t(ecol) * g.N + R) = pack2(y0, y1);
-                if (y0 > best.v || (y0 == best.v && int32_t(R) < best.i)) best.v = y0, best.i = int32_t(R);
-                if (y1 > best.v || (y1 == best.v && int32_t(R + 1) < best.i)) best.v = y1, best.i = int32_t(R + 1);
-            }
+            st_ll_store(g.ax_ll + size_t(et) * (g.n_a >> 1) + blockIdx.x, pack2(s0, s1), tag_out);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(c.fre0 + bl.buf * 8);
         bl.advance();
     }
+    const uint32_t hd = P.head_dim, half = hd >> 1;
+    const uint32_t rank = P.lora_rank, rq = rank >> 2; // adaptor columns of this quarter: [sub * rq, sub * rq + rq)
+    const uint16_t* lora_b = Q && g.n_a ? reinterpret_cast<const uint16_t*>(st_layer_ptr(P, g, g.lora_b, li)) : nullptr;
+    const bool fast_b = lora_b != nullptr && rank == 16; // the adaptor quarter of a block is requested one block ahead
+    const uint32_t bstep = (!Q || g.fmt == WF_BF16) ? uint32_t(kStTileRows) : 1u;
+    // output row of this thread's block row, and the rows of the block
+    auto row_of = [&](uint32_t b, uint32_t& R, uint32_t& nr) {
+        if (!Q || g.fmt == WF_BF16) R = b + erow, nr = min(uint32_t(kStTileRows), r.b1 - b);
+        else if (!g.qkv_map) R = b * 16 + erow, nr = 16;
+        else {
+            const uint32_t unit0 = b * 8, head = unit0 / half, j0 = unit0 - head * half;
+            R = head * hd + j0 + (erow & 7u) + (erow >> 3) * half, nr = 16;
+        }
+    };
+    // epilogue operands of a block, requested early: the residual words (lane `sub` holds those of columns sub and sub + 4;
+    // verified by their tag when used: the epilogue warps of a CTA without blocks run ahead of everybody else) and the
+    // adaptor quarter
+    uint64_t resw[2] = {0, 0}, n_resw[2] = {0, 0};
+    uint2 bq = make_uint2(0, 0), n_bq = make_uint2(0, 0);
+    auto fetch = [&](uint32_t b, uint64_t (&rw)[2], uint2& q) {
+        uint32_t R, nr;
+        row_of(b, R, nr);
+        if (erow >= nr) return;
+        if (g.epi == EPI_RESIDUAL && (erow & 1u) == 0) {
+            if (sub < P.rows) rw[0] = st_ll_load1(g.res_ll + size_t(sub) * out_pitch + (R >> 1));
+            if (sub + 4 < P.rows) rw[1] = st_ll_load1(g.res_ll + size_t(sub + 4) * out_pitch + (R >> 1));
+        }
+        if (fast_b) q = *reinterpret_cast<const uint2*>(lora_b + size_t(R) * 16 + 4 * sub);
+    };
+    if (r.b0 < r.b1) fetch(r.b0, resw, bq);
+    if (Q && g.n_a && r.b0 < r.b1) {
+        // every CTA needs all of ax for its LoRA-B epilogue (the barrier: the previous phase may still be reading its own)
+        epi_bar();
+        for (uint32_t i = et; i < P.rows * (g.n_a >> 1); i += kStEpiThreads) {
+            const uint32_t m = i / (g.n_a >> 1), w = i - m * (g.n_a >> 1);
+            const uint32_t v = st_poll1(c, g.ax_ll + size_t(m) * (g.n_a >> 1) + w, tag_out);
+            sax[m * g.n_a + 2 * w] = bf_lo(v), sax[m * g.n_a + 2 * w + 1] = bf_hi(v);
+        }
+        epi_bar();
+    }
+    for (uint32_t b = r.b0; b < r.b1; b += bstep) {
+        uint32_t R, nr;
+        row_of(b, R, nr);
+        if (b + bstep < r.b1) fetch(b + bstep, n_resw, n_bq); // in flight while this block is finished
+        uint32_t sl = 0; // which rank-wide slice of ax this weight row multiplies
+        if (g.ax_slices == 2) sl = R & 1u;
+        else if (g.ax_slices == 3) sl = R < g.slice_rows0 ? 0u : (R < g.slice_rows1 ? 1u : 2u);
+        st_mbar_wait(c, c.rdy0 + bl.buf * 8, bl.parity);
+        const float* rr = c.red + bl.buf * (kStWarps * 128) + (2 * sub) * 128 + erow * 8;
+        for (uint32_t col = 0; col < P.rows; col++) {
+            float sum = rr[col] + rr[128 + col];
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            float y = rbf(sum); // the bmm output buffer is T (kernel/bmm.metal:76)
+            if (lora_b) {
+                // y = r(y + r(r(B . ax) * scale))   (quantization/lora.h:115-122)
+                const float* ax = sax + col * g.n_a + sl * rank + sub * rq;
+                float l = 0.0f;
+                if (fast_b) {
+                    const float4 x4 = *reinterpret_cast<const float4*>(ax);
+                    l = fmaf(x4.x, bf_lo(bq.x), l), l = fmaf(x4.y, bf_hi(bq.x), l), l = fmaf(x4.z, bf_lo(bq.y), l), l = fmaf(x4.w, bf_hi(bq.y), l);
+                } else if (erow < nr) {
+                    const uint16_t* br = lora_b + size_t(R) * rank + sub * rq;
+                    for (uint32_t j = 0; j < rq; j++) l = fmaf(ax[j], bf16_bits_to_f32(br[j]), l);
+                }
+                l += __shfl_xor_sync(0xffffffffu, l, 1);
+                l += __shfl_xor_sync(0xffffffffu, l, 2);
+                y = rbf(__fadd_rn(y, rbf(__fmul_rn(rbf(l), P.lora_scale))));
+            }
+            const float y1 = __shfl_xor_sync(0xffffffffu, y, 4); // the next block row
+            const bool st = storer && erow < nr;
+            if (g.epi == EPI_SWIGLU) {
+                // z = r(silu_T(g) * u), rows (2i, 2i+1) = (w1 row i, w3 row i)  (nn/transformer.h:57-59); two outputs per word
+                const float z = __fmul_rn(silu_bf16(y), y1);
+                const float z1 = __shfl_xor_sync(0xffffffffu, z, 8);
+                if (st) st_ll_store(g.out_ll + size_t(col) * out_pitch + (R >> 2), pack2(z, z1), tag_out);
+            } else if (g.epi == EPI_RESIDUAL) {
+                // h = r(x + a)  (nn/transformer.h:133,139); the residual word of column `col` sits in lane (col & 3) of this row
+                const uint64_t a0 = __shfl_sync(0xffffffffu, resw[0], (lane & ~3u) | (col & 3u));
+                const uint64_t a1 = __shfl_sync(0xffffffffu, resw[1], (lane & ~3u) | (col & 3u));
+                if (st) {
+                    const uint64_t rw = col < 4 ? a0 : a1;
+                    uint32_t rv = uint32_t(rw);
+                    if (uint32_t(rw >> 32) != res_tag) rv = st_poll1(c, g.res_ll + size_t(col) * out_pitch + (R >> 1), res_tag);
+                    st_ll_store(g.out_ll + size_t(col) * out_pitch + (R >> 1), pack2(__fadd_rn(bf_lo(rv), y), __fadd_rn(bf_hi(rv), y1)), tag_out);
+                }
+            } else if (!is_head) {
+                if (st) st_ll_store(g.out_ll + size_t(col) * out_pitch + (R >> 1), pack2(y, y1), tag_out);
+            } else if (st) {
+                *reinterpret_cast<uint32_t*>(g.y + size_t(col) * g.N + R) = pack2(y, y1);
+                // greedy argmax of column `col`: kept by the storing lanes, one slot per column
+                float& bv = best.v[col];
+                int32_t& bi = best.i[col];
+                if (y > bv || (y == bv && int32_t(R) < bi)) bv = y, bi = int32_t(R);
+                if (y1 > bv || (y1 == bv && int32_t(R + 1) < bi)) bv = y1, bi = int32_t(R + 1);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(c.fre0 + bl.buf * 8);
+        bl.advance();
+        resw[0] = n_resw[0], resw[1] = n_resw[1], bq = n_bq;
+    }
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
 
 // ---- consumers: attention phase ---------------------------------------------------------------------------------------
 // item = (row, head, part).  The four parts of a head split the cached positions for the scores and the head dimensions
@@ -753,7 +1026,8 @@ __device__ __forceinline__ void st_attention(const st_params& P, uint32_t li, ui
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kStThreads, 1) decode_stream_kernel(const __grid_constant__ st_params P)
+// Q = the model has packed (int4 / int8) layers and LoRA adaptors; the bf16 instantiation carries none of that code
+template <bool Q, int HD> __global__ void __launch_bounds__(kStThreads, 1) decode_stream_kernel(const __grid_constant__ st_params P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     st_ctx c;
@@ -788,9 +1062,14 @@ __global__ void __launch_bounds__(kStThreads, 1) decode_stream_kernel(const __gr
     __syncthreads();
     const uint32_t phases_per_step = P.n_layers * 5 + 1;
 
+#ifdef ST_USE_SETMAXNREG
+    // register budget: 384 threads x 168 at launch; warpgroup 2 (epilogue + producer warps) hands registers to the two mma warpgroups
+    if (tid >= kStConsumers) asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+#endif
     if (tid >= kStConsumers + kStEpiThreads) {
         // ---- producer warp: the whole launch's weight stream, never blocked by anything but a full ring
-        st_producer(P, c);
+        if (tid < kStConsumers + kStEpiThreads + 32) st_producer<Q>(P, c);
         return;
     }
     if (tid >= kStConsumers) {
@@ -800,27 +1079,35 @@ __global__ void __launch_bounds__(kStThreads, 1) decode_stream_kernel(const __gr
         const int32_t log0 = P.step_counter[0];
         for (uint32_t step = 0; step < P.steps; step++) {
             unsigned gphase = step * phases_per_step;
-            st_best best{-INFINITY, 0x7fffffff};
+            st_best best;
+#pragma unroll
+            for (int k = 0; k < kStMaxRows; k++) best.v[k] = -INFINITY, best.i[k] = 0x7fffffff;
             for (uint32_t li = 0; li <= P.n_layers; li++) {
                 const bool is_head = li == P.n_layers;
                 for (uint32_t kind = 0; kind < (is_head ? 1u : 5u); kind++, gphase++) {
                     if (!is_head && kind == 1) continue;
-                    st_epi_gemv(P, P.g[is_head ? 4u : (kind == 0 ? 0u : kind - 1)], c, bl, best, is_head, P.tag_base + gphase + 1);
+                    // the residual of wo is the x of this layer (embedding: this step's first phase; else the w2 before), of w2 the h of wo
+                    const uint32_t tag_out = P.tag_base + gphase + 1;
+                    const uint32_t res_tag = kind == 2 ? (li == 0 ? tag_out - 2 : tag_out - 3) : tag_out - 2;
+                    st_epi_gemv<Q>(P, P.g[is_head ? 4u : (kind == 0 ? 0u : kind - 1)], c, bl, best, is_head, is_head ? 0 : li, tag_out, res_tag);
                     st_stamp(P.timing ? P.timing + (size_t(blockIdx.x) * (P.steps * phases_per_step) + gphase) * 4 : nullptr, 1);
                 }
             }
             // sampler tail (greedy): every CTA publishes its argmax partial, CTA 0 joins them and publishes the next id
             const uint32_t tag_head = P.tag_base + gphase; // = tag_out of the head phase
-            float* bv = c.escr;
+            float* bv = c.escr;                                     // [8 cols][8 storing lanes]
             int32_t* bi = reinterpret_cast<int32_t*>(c.escr + 64);
-            bv[et] = best.v, bi[et] = best.i;
+            if ((et & 7u) == 0) {
+#pragma unroll
+                for (int k = 0; k < kStMaxRows; k++) bv[k * 8 + (et >> 3)] = best.v[k], bi[k * 8 + (et >> 3)] = best.i[k];
+            }
             epi_bar();
             if (et < P.rows) {
                 float v = -INFINITY;
                 int32_t i = 0x7fffffff;
                 for (int r = 0; r < 8; r++) {
-                    const float ov = bv[r * 8 + et];
-                    const int32_t oi = bi[r * 8 + et];
+                    const float ov = bv[et * 8 + r];
+                    const int32_t oi = bi[et * 8 + r];
                     if (ov > v || (ov == v && oi < i)) v = ov, i = oi;
                 }
                 uint64_t* dst = P.am_ll + (size_t(et) * G + blockIdx.x) * 2;
@@ -873,14 +1160,13 @@ __global__ void __launch_bounds__(kStThreads, 1) decode_stream_kernel(const __gr
                 unsigned long long* tm = P.timing ? P.timing + (size_t(blockIdx.x) * (P.steps * phases_per_step) + gphase) * 4 : nullptr;
                 st_stamp(tm, 0);
                 if (!is_head && kind == 1) {
-                    if (P.head_dim == 64) st_attention<64>(P, li, step, c, tag_in, tag_out);
-                    else st_attention<128>(P, li, step, c, tag_in, tag_out);
+                    st_attention<HD>(P, li, step, c, tag_in, tag_out);
                     st_stamp(tm, 2);
                 } else {
                     const st_gemv& g = P.g[is_head ? 4u : (kind == 0 ? 0u : kind - 1)];
-                    st_stage_input(P, g, is_head ? 0 : li, c, li == 0 && kind == 0 && !is_head, step, tag_in, tag_out);
+                    st_stage_input<Q>(P, g, is_head ? 0 : li, c, li == 0 && kind == 0 && !is_head, step, tag_in, tag_out);
                     st_stamp(tm, 2);
-                    st_mma_gemv(P, g, c, cp, bl);
+                    st_mma_gemv<Q>(P, g, c, cp, bl, is_head ? 0 : li);
                 }
                 st_stamp(tm, 3);
             }

@@ -11,9 +11,10 @@ import bench
 
 shape = bench.SHAPES[sys.argv[1] if len(sys.argv) > 1 else "1b"]
 mode = sys.argv[2] if len(sys.argv) > 2 else "stream"
+quant = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 dev = capi.Device(0)
 FLAGS = {"mega": capi.LLAMA_MEGAKERNEL, "ops": capi.LLAMA_NO_STREAM, "stream": 0}
-m = capi.Llama(dev, capi.llama_config(**shape, max_seq_len=1024, flags=FLAGS[mode]))
+m = capi.Llama(dev, capi.llama_config(**shape, max_seq_len=1024, flags=FLAGS[mode], quant=quant))
 m.init_random(0x5EED)
 m.finalize()
 m.prefill(np.arange(512, dtype=np.int32) % shape["vocab"])

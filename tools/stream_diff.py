@@ -8,10 +8,12 @@ def unbf(a):
     return (a.astype(np.uint32) << 16).view(np.float32)
 
 SMALL = dict(dim=512, n_layers=3, n_heads=8, n_kv_heads=2, head_dim=64, ffn_dim=1024, vocab=2000, max_seq_len=96)
+import sys as _sys
+Q = int(_sys.argv[1]) if len(_sys.argv) > 1 else 0
 dev = capi.Device(0)
 ms = []
 for flags in (0, 16):
-    m = capi.Llama(dev, capi.llama_config(**SMALL, flags=flags))
+    m = capi.Llama(dev, capi.llama_config(**SMALL, flags=flags, quant=Q))
     m.init_random(0x5EED)
     m.finalize()
     ids = [3, 77, 512, 999, 0, 41, 41, 7, 1500, 2]

@@ -9,8 +9,9 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 launches = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 shape = bench.SHAPES[sys.argv[3] if len(sys.argv) > 3 else "1b"]
 kv = int(sys.argv[4]) if len(sys.argv) > 4 else 512
+quant = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 dev = capi.Device(0)
-m = capi.Llama(dev, capi.llama_config(**shape, max_seq_len=1024))
+m = capi.Llama(dev, capi.llama_config(**shape, max_seq_len=1024, quant=quant))
 m.init_random(0x5EED)
 m.finalize()
 m.prefill(np.arange(kv, dtype=np.int32) % shape["vocab"])
