@@ -2,7 +2,7 @@
 """bench.py — decode tokens/s of the B200 engine on BASELINE.json's configs[1]
 (Llama-3.2-1B-shaped bf16, batch 1, 512-token KV cache, random-init weights, synthetic ids).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload 1b-bf16|1b-w4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload 1b-bf16|1b-w4] [--batch B] [--per-op]
 
 A "step" is one decode step (one token per sequence).  Prints ONE JSON line (see DESIGN.md
 "Measurement").  `value` is device-timed (CUDA events on the engine's stream, token fed back on
@@ -196,7 +196,9 @@ def main():
     ap.add_argument("--workload", default="1b-bf16")
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the isolated per-shape GEMV timing of the per-op path")
+    ap.add_argument("--roofline-gemv", action="store_true", help="add the isolated per-shape timing of the per-op GEMV kernel")
+    ap.add_argument("--per-op", action="store_true", help="per-op kernels under a CUDA graph instead of the streaming persistent kernel")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     shape_name, fmt = args.workload.split("-")
@@ -223,7 +225,7 @@ def main():
     dev = capi.Device(local)
     steps = min(args.steps, 1024 - KV_LEN - args.warmup - 8)
     cfg = capi.llama_config(**shape, max_seq_len=1024, quant=quant, n_seqs=args.batch,
-                            flags=capi.LLAMA_W4_PACKED if quant else 0)
+                            flags=(capi.LLAMA_W4_PACKED if quant else 0) | (capi.LLAMA_NO_STREAM if args.per_op else 0))
     m = capi.Llama(dev, cfg)
     m.init_random(0x5EED)
     m.finalize()
@@ -275,19 +277,33 @@ def main():
     kv_bytes = 2 * shape["n_layers"] * shape["n_kv_heads"] * shape["head_dim"] * 2 * (KV_LEN + args.warmup + steps // 2) * B
     step_bytes = streamed + kv_bytes
     step_gbs = step_bytes / (ms * 1e-3 / steps) / 1e9
+    streaming = m.launches_per_step() == 1
+    kname = ("decode_stream_kernel (persistent: the whole decode step is one kernel; `steps` steps per launch)" if streaming
+             else "whole decode step (per-op kernels under one CUDA graph; the GEMV family streams >97% of the bytes)")
+    # algorithmic bytes of one step (weights + norms + adaptors streamed once, KV read once) / device time of one step, both of the
+    # timed region above (CUDA events on the engine's stream around the launches)
     roof = {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak, "traffic": None,
-            "kernel": "whole decode step (GEMV family streams >97% of the bytes)", "peak_source": peak_src,
-            "algorithmic_bytes_per_step": step_bytes}
-    if not args.no_roofline and quant == 0:
+            "kernel": kname, "peak_source": peak_src, "algorithmic_bytes_per_step": step_bytes}
+    ncu = ROOT / "profiles" / "r01_ncu_stream_summary.json"
+    if streaming and ncu.exists():
+        try:
+            t = json.loads(ncu.read_text()).get(args.workload if B == 1 else "", {})
+            if t:
+                roof["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
+                roof["traffic_source"] = t.get("source", "ncu --set full, one launch of one step")
+        except Exception:
+            pass
+    if args.roofline_gemv and quant == 0:
         per, fam = measure_gemv_family(capi, dev, shape, hbm_peak)
-        roof.update({"kernel": "gemv_bf16_kernel (all GEMV launches of a step, isolated CUDA-event timing, weights cycled through >L2 ring)",
-                     "achieved": fam, "frac": fam / hbm_peak, "step_achieved": step_gbs, "step_frac": step_gbs / hbm_peak, "per_shape": per})
+        roof.update({"per_op_gemv_family": {"achieved": fam, "frac": fam / hbm_peak, "per_shape": per,
+                                            "note": "isolated CUDA-event timing of the per-op GEMV kernel, weights cycled through a >L2 ring"}})
     line = {
         "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if quant == 0 else "bf16 activations, int4 weights (bf16 dequant), fp32 accumulate",
         "data": "synthetic ids, random-init weights (counter-hash seed 0x5EED)",
         "config": {"workload": workload, "kv_len": KV_LEN, "batch": B, "parallelism": f"{world} replica(s), one sequence stream per GPU",
+                   "path": "streaming persistent kernel" if streaming else "per-op kernels + CUDA graph",
                    "l2": f"weights streamed per step {streamed / 1e6:.0f} MB > 126 MB L2 (no flush needed)"},
         "e2e": {"value": tokens / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4 * B,
                 "ms_per_step": e2e_ms / steps},

@@ -96,6 +96,7 @@ struct mc_llama {
     dbuf st_ll, st_timing;     // one arena of tagged words: x | h | z | qkv | attn | scores | argmax partials | ids
     size_t st_off[9] = {};
     uint32_t st_sc_words = 0, st_seq = 0;
+    size_t st_words = 0;       // words of one copy of the tagged-word arena (the arena holds kStMaxRep copies)
     bool st_timing_on = false;
     int st_ok = -1;            // -1 not probed yet, 0 not usable on this device / shape, 1 usable
     uint32_t st_grid = 0;
@@ -109,6 +110,7 @@ struct mc_llama {
     // activations
     uint32_t max_rows = 0;
     dbuf x, h, q, attn, z, logits, logits_tmp, hidden_save;
+    dbuf io_in, io_out;        // contiguous decode inputs / outputs (views below)
     dbuf ids, pos, row_seq, uniforms, out_log, step_counter, pval, pidx, lora_ax, pack_bad, cand;
     int32_t* pinned = nullptr; // host staging: ids | pos | out
     float scale_bf16 = 0.0f;
@@ -127,7 +129,7 @@ struct mc_llama {
         for (dlinear* d : {&tok, &out}) d->w.release(), d->scales.release(), d->lora_b.release(), d->q8.release(), d->s32.release();
         for (int k = 0; k < kTpMaxWorld; k++)
             if (tp_peer_base[k] && uint32_t(k) != cfg.tp_rank) cudaIpcCloseMemHandle(tp_peer_base[k]);
-        for (dbuf* b : {&st_ll, &st_timing, &layer_arena, &bar, &errflag, &mega_timing, &tp_region, &tp_local, &norm, &fcos, &fsin, &kcache, &vcache, &x, &h, &q, &attn, &z, &logits, &logits_tmp, &hidden_save, &ids, &pos, &row_seq,
+        for (dbuf* b : {&st_ll, &st_timing, &layer_arena, &bar, &errflag, &mega_timing, &tp_region, &tp_local, &norm, &fcos, &fsin, &kcache, &vcache, &x, &h, &q, &attn, &z, &logits, &logits_tmp, &hidden_save, &io_in, &io_out, &ids, &pos, &row_seq,
                         &uniforms, &out_log, &step_counter, &pval, &pidx, &lora_ax, &pack_bad, &cand})
             b->release();
     }
@@ -238,11 +240,11 @@ template <int MB, int PRO, int EPI, int KS> void gemv_launch_ks(launcher& L, con
     static bool configured[8] = {false};
     const int dev = L.m->dev->ordinal;
     if (!configured[dev & 7]) {
-        MC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        MC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured[dev & 7] = true;
     }
     const size_t smem = gemv_smem(MB, p.K);
-    MC_REQUIRE(smem <= 100 * 1024, "gemv: activation rows do not fit in shared memory");
+    MC_REQUIRE(smem <= 200 * 1024, "gemv: activation rows do not fit in shared memory");
     const uint32_t upc = kGemvWarps / p.ksplit;
     const uint32_t units = p.N / 2;
     const uint32_t ctas_needed = (units + upc - 1) / upc;
@@ -711,6 +713,8 @@ void launch_stream(mc_llama* m, launcher& L, uint32_t rows, int advance, uint32_
     P.layer_stride = m->layer_stride, P.kv_layer_stride = kv_layer_elems(m);
     P.n_layers = c.n_layers, P.rows = rows, P.steps = steps, P.n_stages = geo.n_stages, P.act_pitch = geo.act_pitch, P.act_bytes = geo.act_bytes, P.sax_off = geo.sax_off;
     P.tag_base = m->st_seq << 16;
+    static const int env_rep = getenv("MC_STREAM_REP") ? atoi(getenv("MC_STREAM_REP")) : 1;
+    P.n_rep = uint32_t(std::min(std::max(env_rep, 1), kStMaxRep)), P.rep_stride = uint32_t(m->st_words);
     static const int env_ns = getenv("MC_STREAM_POLL_NS") ? atoi(getenv("MC_STREAM_POLL_NS")) : 0;
     P.poll_ns = uint32_t(env_ns);
     P.eps = c.norm_eps;
@@ -1116,9 +1120,8 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
         m->pack_bad.alloc(4);
         MC_CUDA_CHECK(cudaMemset(m->pack_bad.p, 0, 4));
     }
-    m->bar.alloc(256), m->errflag.alloc(256);
+    m->bar.alloc(256);
     MC_CUDA_CHECK(cudaMemset(m->bar.p, 0, 256));
-    MC_CUDA_CHECK(cudaMemset(m->errflag.p, 0, 256));
     if (c.tp_world > 1) {
         const size_t rows_max = kMaxMB, T = c.tp_world;
         const size_t part = 2 * T * rows_max * D * sizeof(float);
@@ -1168,20 +1171,27 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
         const size_t words[9] = {R8 * D / 2, R8 * D / 2, R8 * m->Fl / 2, R8 * QKVN / 2, R8 * QOl / 2, R8 * m->Hl * m->st_sc_words, R8 * 256 * 2, 64, 4 * R8 * 128};
         size_t total = 0;
         for (int i = 0; i < 9; i++) m->st_off[i] = total, total += (words[i] + 31) & ~size_t(31);
-        m->st_ll.alloc(total * 8);
+        m->st_words = total;
+        m->st_ll.alloc(total * 8 * kStMaxRep);
         MC_CUDA_CHECK(cudaMemset(m->st_ll.p, 0, m->st_ll.bytes));
     }
     m->logits.alloc(size_t(R) * m->Vl * 2);
     if (c.tp_world > 1) m->logits_tmp.alloc(size_t(kMaxMB) * m->Vl * 2);
     m->hidden_save.alloc(size_t(c.n_seqs) * D * 2);
-    m->ids.alloc(R * 4), m->pos.alloc(R * 4), m->row_seq.alloc(R * 4), m->uniforms.alloc(size_t(kMaxLogSteps) * R * 4);
+    // decode inputs and outputs are contiguous so that a per-token call moves them with ONE copy each way:
+    //   io_in  = ids[R] | pos[R] | row_seq[R] | step_counter      io_out = error flag (16 B) | out_log
+    m->io_in.alloc((size_t(3) * R + 4) * 4);
+    m->ids.view(m->io_in.p, R * 4), m->pos.view(m->io_in.as<int32_t>() + R, R * 4), m->row_seq.view(m->io_in.as<int32_t>() + 2 * R, R * 4);
+    m->step_counter.view(m->io_in.as<int32_t>() + 3 * R, 4);
+    m->io_out.alloc(16 + size_t(kMaxLogSteps) * R * 4);
+    MC_CUDA_CHECK(cudaMemset(m->io_out.p, 0, 16));
+    m->errflag.view(m->io_out.p, 16), m->out_log.view(m->io_out.as<char>() + 16, size_t(kMaxLogSteps) * R * 4);
+    m->uniforms.alloc(size_t(kMaxLogSteps) * R * 4);
     m->cand.alloc(size_t(R) * ((m->Vl + kSampleSlice - 1) / kSampleSlice) * kSampleKeep * 8);
-    m->out_log.alloc(size_t(kMaxLogSteps) * R * 4);
-    m->step_counter.alloc(4);
     m->pval.alloc(size_t(R) * 1024 * 4), m->pidx.alloc(size_t(R) * 1024 * 4);
     MC_CUDA_CHECK(cudaMemset(m->logits.p, 0, m->logits.bytes));
     MC_CUDA_CHECK(cudaMemset(m->hidden_save.p, 0, m->hidden_save.bytes));
-    MC_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&m->pinned), size_t(R) * 4 * 4 + 256, cudaHostAllocDefault));
+    MC_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&m->pinned), (size_t(16) * R + 512) * 4, cudaHostAllocDefault));
     m->scale_bf16 = bf16_bits_to_f32(f32_to_bf16_bits(1.0f / std::sqrt(float(hd))));
     m->hidden_ptr.assign(c.n_seqs, nullptr);
     *out = m.release();
@@ -1376,18 +1386,15 @@ static void stage_decode_inputs(mc_llama* m, uint32_t n, const int32_t* ids, con
 {
     MC_REQUIRE(n >= 1 && n <= m->cfg.n_seqs, "decode: number of sequences out of range");
     MC_REQUIRE(ids && pos, "decode: null ids/pos");
-    int32_t* st = m->pinned;
     const uint32_t R = m->max_rows;
+    int32_t* st = m->pinned + 4 * R + 64; // staging image of io_in: ids | pos | row_seq | step counter
     for (uint32_t r = 0; r < n; r++) {
         MC_REQUIRE(ids[r] >= 0 && uint32_t(ids[r]) < m->cfg.vocab, "decode: token id out of range");
         MC_REQUIRE(pos[r] >= 0 && uint32_t(pos[r]) < m->cfg.max_seq_len, "decode: position exceeds max_seq_len (sink roll not modelled)");
         st[r] = ids[r], st[R + r] = pos[r], st[2 * R + r] = int32_t(r);
     }
-    cudaStream_t s = m->dev->stream;
-    MC_CUDA_CHECK(cudaMemcpyAsync(m->ids.p, st, n * 4, cudaMemcpyHostToDevice, s));
-    MC_CUDA_CHECK(cudaMemcpyAsync(m->pos.p, st + R, n * 4, cudaMemcpyHostToDevice, s));
-    MC_CUDA_CHECK(cudaMemcpyAsync(m->row_seq.p, st + 2 * R, n * 4, cudaMemcpyHostToDevice, s));
-    MC_CUDA_CHECK(cudaMemsetAsync(m->step_counter.p, 0, 4, s));
+    st[3 * R] = 0; // step counter
+    MC_CUDA_CHECK(cudaMemcpyAsync(m->io_in.p, st, (size_t(3) * R + 1) * 4, cudaMemcpyHostToDevice, m->dev->stream));
 }
 
 mc_status mc_llama_decode(mc_llama* m, uint32_t n, const int32_t* ids, const int32_t* pos, const float* uniforms,
@@ -1406,12 +1413,11 @@ mc_status mc_llama_decode(mc_llama* m, uint32_t n, const int32_t* ids, const int
     }
     run_decode_step(m, n, sc, 0);
     cudaStream_t s = m->dev->stream;
-    int32_t* st_out = m->pinned + 3 * m->max_rows;
-    MC_CUDA_CHECK(cudaMemcpyAsync(st_out, m->out_log.p, n * 4, cudaMemcpyDeviceToHost, s));
-    MC_CUDA_CHECK(cudaMemcpyAsync(st_out + n, m->errflag.p, 4, cudaMemcpyDeviceToHost, s));
+    int32_t* st_out = m->pinned + 8 * m->max_rows + 128; // image of io_out: error flag (16 B) | first n log entries
+    MC_CUDA_CHECK(cudaMemcpyAsync(st_out, m->io_out.p, 16 + n * 4, cudaMemcpyDeviceToHost, s));
     MC_CUDA_CHECK(cudaStreamSynchronize(s));
-    check_mega_error(m, st_out[n]);
-    memcpy(out_ids, st_out, n * 4);
+    check_mega_error(m, st_out[0]);
+    memcpy(out_ids, st_out + 4, n * 4);
     MC_API_END
 }
 

@@ -44,6 +44,7 @@ constexpr int kStPad = 64;                            // bytes of padding per st
 constexpr int kStStageBytes = kStTileRows * (kStMaxKC * 2 + kStPad);
 constexpr int kStMaxStages = 8;
 constexpr int kStSplits = 4;                          // CTAs per (row, head) in the attention phase
+constexpr int kStMaxRep = 8;                          // copies of every exchanged vector (spreads the pollers over L2 lines)
 constexpr int kStMaxRows = 8;                         // activation rows (the n of the mma)
 constexpr int kStHdrBytes = 896;                      // mbarriers + flags + reduce scratch
 constexpr int kStRedBufs = 3;                         // cross-warp partial buffers in flight between the mma and the epilogue warps
@@ -86,6 +87,8 @@ struct st_params {
     uint32_t act_bytes;
     uint32_t sax_off;        // quantised models: offset of the [8][n_a] r(A . x) scratch inside the activation region
     uint32_t tag_base;       // tags of this launch are tag_base + phase + 1
+    uint32_t n_rep;          // every exchanged vector exists in n_rep copies (each polled by 1/n_rep of the CTAs), rep_stride words apart
+    uint32_t rep_stride;
     uint32_t poll_ns;
     float eps;
     // attention
@@ -218,6 +221,10 @@ __device__ __forceinline__ void st_mbar_wait(const st_ctx& c, uint32_t a, uint32
 __device__ __forceinline__ void st_ll_store(uint64_t* p, uint32_t payload, uint32_t tag)
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"((uint64_t(tag) << 32) | payload) : "memory");
+}
+__device__ __forceinline__ void st_ll_store_rep(const st_params& P, uint64_t* p, uint32_t payload, uint32_t tag)
+{
+    for (uint32_t r = 0; r < P.n_rep; r++) st_ll_store(p + size_t(r) * P.rep_stride, payload, tag);
 }
 __device__ __forceinline__ void st_ll_load2(const uint64_t* p, uint64_t& a, uint64_t& b)
 {
@@ -470,7 +477,7 @@ template <bool Q> __device__ __forceinline__ void st_stage_input(const st_params
                     }
                 }
             } else {
-                const uint64_t* src = g.in_ll + size_t(m) * n_words;
+                const uint64_t* src = g.in_ll + size_t(blockIdx.x % P.n_rep) * P.rep_stride + size_t(m) * n_words;
 #pragma unroll
                 for (int j = 0; j < NB; j++) {
                     const uint32_t w = w0 + j * (kStConsumers * 2);
@@ -809,7 +816,7 @@ template <bool Q> __device__ __forceinline__ void st_epi_gemv(const st_params& P
                 // z = r(silu_T(g) * u), rows (2i, 2i+1) = (w1 row i, w3 row i)  (nn/transformer.h:57-59); two outputs per word
                 const float z = __fmul_rn(silu_bf16(y), y1);
                 const float z1 = __shfl_xor_sync(0xffffffffu, z, 8);
-                if (st) st_ll_store(g.out_ll + size_t(col) * out_pitch + (R >> 2), pack2(z, z1), tag_out);
+                if (st) st_ll_store_rep(P, g.out_ll + size_t(col) * out_pitch + (R >> 2), pack2(z, z1), tag_out);
             } else if (g.epi == EPI_RESIDUAL) {
                 // h = r(x + a)  (nn/transformer.h:133,139); the residual word of column `col` sits in lane (col & 3) of this row
                 const uint64_t a0 = __shfl_sync(0xffffffffu, resw[0], (lane & ~3u) | (col & 3u));
@@ -818,10 +825,10 @@ template <bool Q> __device__ __forceinline__ void st_epi_gemv(const st_params& P
                     const uint64_t rw = col < 4 ? a0 : a1;
                     uint32_t rv = uint32_t(rw);
                     if (uint32_t(rw >> 32) != res_tag) rv = st_poll1(c, g.res_ll + size_t(col) * out_pitch + (R >> 1), res_tag);
-                    st_ll_store(g.out_ll + size_t(col) * out_pitch + (R >> 1), pack2(__fadd_rn(bf_lo(rv), y), __fadd_rn(bf_hi(rv), y1)), tag_out);
+                    st_ll_store_rep(P, g.out_ll + size_t(col) * out_pitch + (R >> 1), pack2(__fadd_rn(bf_lo(rv), y), __fadd_rn(bf_hi(rv), y1)), tag_out);
                 }
             } else if (!is_head) {
-                if (st) st_ll_store(g.out_ll + size_t(col) * out_pitch + (R >> 1), pack2(y, y1), tag_out);
+                if (st) st_ll_store_rep(P, g.out_ll + size_t(col) * out_pitch + (R >> 1), pack2(y, y1), tag_out);
             } else if (st) {
                 *reinterpret_cast<uint32_t*>(g.y + size_t(col) * g.N + R) = pack2(y, y1);
                 // greedy argmax of column `col`: kept by the storing lanes, one slot per column
@@ -894,7 +901,7 @@ __device__ __forceinline__ void st_attention(const st_params& P, uint32_t li, ui
         }
         // q, v (and k for the owner) of this head from the QKV phase
         {
-            const uint64_t* qrow = P.qkv_ll + size_t(row) * QKVW;
+            const uint64_t* qrow = P.qkv_ll + size_t(blockIdx.x % P.n_rep) * P.rep_stride + size_t(row) * QKVW;
             const uint32_t grp = tid / half, i = tid % half; // 0: q, 1: v, 2: k
             if (grp < 2 || (grp == 2 && own)) {
                 const uint32_t base = grp == 0 ? head * HD : (grp == 1 ? (H + KV + kvh) * HD : (H + kvh) * HD);
@@ -1019,7 +1026,7 @@ __device__ __forceinline__ void st_attention(const st_params& P, uint32_t li, ui
             const float pp = sp[pos];
             o0 = fmaf(pp, sv[part * DQ + 2 * tid], o0);
             o1 = fmaf(pp, sv[part * DQ + 2 * tid + 1], o1);
-            st_ll_store(P.attn_ll + size_t(row) * (H * HD / 2) + ((head * HD + part * DQ) >> 1) + tid, pack2(o0, o1), tag_out);
+            st_ll_store_rep(P, P.attn_ll + size_t(row) * (H * HD / 2) + ((head * HD + part * DQ) >> 1) + tid, pack2(o0, o1), tag_out);
         }
         consumer_bar(); // the scratch is reused by the next item
     }
