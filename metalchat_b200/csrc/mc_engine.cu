@@ -609,7 +609,7 @@ stream_kernel_t stream_kernel_of(bool quant, uint32_t head_dim)
     return head_dim == 64 ? decode_stream_kernel<false, 64> : decode_stream_kernel<false, 128>;
 }
 struct stream_geom {
-    uint32_t act_pitch, act_bytes, sax_off, n_stages;
+    uint32_t act_pitch, act_bytes, sax_off, n_stages, stage_bytes;
     size_t smem;
 };
 bool stream_geometry(const mc_llama* m, uint32_t rows, stream_geom& g)
@@ -623,14 +623,17 @@ bool stream_geometry(const mc_llama* m, uint32_t rows, stream_geom& g)
     g.act_bytes = g.sax_off + (c.quant ? uint32_t(kStMaxRows * 3 * c.lora_rank * sizeof(float) + 127) & ~127u : 0u);
     const size_t fixed = kStHdrBytes + kStRedBytes + g.act_bytes;
     const size_t cap = 232448; // 227 KiB of dynamic shared memory per CTA on sm_100
-    if (fixed + 2 * size_t(kStStageBytes) > cap) return false;
-    g.n_stages = uint32_t(std::min<size_t>(kStMaxStages, (cap - fixed) / kStStageBytes));
-    g.smem = fixed + size_t(g.n_stages) * kStStageBytes;
+    g.stage_bytes = c.quant ? kStStageBytesPacked : kStStageBytes;
+    if (fixed + 2 * size_t(g.stage_bytes) > cap) return false;
+    g.n_stages = uint32_t(std::min<size_t>(kStMaxStages, (cap - fixed) / g.stage_bytes));
+    g.smem = fixed + size_t(g.n_stages) * g.stage_bytes;
     return true;
 }
-uint32_t stream_kc_packed(uint32_t K)
+uint32_t stream_kc_packed(uint32_t K, uint32_t kmax)
 {
     for (uint32_t kc : {2048u, 1024u, 512u, 256u})
+        if (kc > kmax) continue;
+        else
         if (K % kc == 0) return kc;
     return 0;
 }
@@ -691,7 +694,7 @@ void launch_stream(mc_llama* m, launcher& L, uint32_t rows, int advance, uint32_
         g.W = d.w.p, g.norm_w = norm ? norm->as<uint16_t>() : nullptr, g.in_ll = in_ll, g.out_ll = out_ll, g.res_ll = res_ll;
         g.N = N, g.K = K, g.fmt = d.fmt, g.pro = pro, g.epi = epi, g.layered = layered;
         if (d.fmt == WF_BF16) g.KC = stream_kc(K), g.gran = epi == EPI_SWIGLU ? 4 : 2;
-        else g.KC = stream_kc_packed(K), g.gran = 16, g.scales = d.scales.p;
+        else g.KC = stream_kc_packed(K, d.fmt == WF_W4 ? 2048 : 1024), g.gran = 16, g.scales = d.scales.p; // 16 KiB tiles
         if (lora_a && lora_a->p) {
             g.lora_a = lora_a->as<uint16_t>(), g.lora_b = d.lora_b.as<uint16_t>(), g.n_a = slices * rank, g.ax_slices = slices;
             g.slice_rows0 = m->Hl * hd, g.slice_rows1 = (m->Hl + m->KVl) * hd;
@@ -708,10 +711,19 @@ void launch_stream(mc_llama* m, launcher& L, uint32_t rows, int advance, uint32_
     P.g[4] = gemv(head, nullptr, 0, 0, &m->norm, x_ll, nullptr, nullptr, m->Vl, D, PRO_RMSNORM, EPI_NONE, 0);
     if (m->tied) P.g[4].W = m->tok.w.as<uint16_t>() + size_t(c.tp_rank) * m->Vl * D;
     P.g[4].y = m->logits.as<uint16_t>();
+    // LoRA-A rows travel two at a time: the largest k chunk whose two padded rows fit one stage
+    for (int i = 0; i < 4; i++) {
+        P.kc_a[i] = 256;
+        for (uint32_t kc : {4096u, 2048u, 1024u, 512u})
+            if (P.g[i].K % kc == 0 && 2 * (kc * 2 + kStPad) <= geo.stage_bytes) {
+                P.kc_a[i] = kc;
+                break;
+            }
+    }
     P.lora_rank = rank, P.lora_scale = bf16_bits_to_f32(f32_to_bf16_bits(c.lora_scale));
     P.tok_fmt = m->tok.fmt, P.tok_scales = m->tok.scales.as<float>();
     P.layer_stride = m->layer_stride, P.kv_layer_stride = kv_layer_elems(m);
-    P.n_layers = c.n_layers, P.rows = rows, P.steps = steps, P.n_stages = geo.n_stages, P.act_pitch = geo.act_pitch, P.act_bytes = geo.act_bytes, P.sax_off = geo.sax_off;
+    P.n_layers = c.n_layers, P.rows = rows, P.steps = steps, P.n_stages = geo.n_stages, P.stage_bytes = geo.stage_bytes, P.act_pitch = geo.act_pitch, P.act_bytes = geo.act_bytes, P.sax_off = geo.sax_off;
     P.tag_base = m->st_seq << 16;
     static const int env_rep = getenv("MC_STREAM_REP") ? atoi(getenv("MC_STREAM_REP")) : 1;
     P.n_rep = uint32_t(std::min(std::max(env_rep, 1), kStMaxRep)), P.rep_stride = uint32_t(m->st_words);
@@ -727,6 +739,7 @@ void launch_stream(mc_llama* m, launcher& L, uint32_t rows, int advance, uint32_
     P.out_log = m->out_log.as<int32_t>(), P.step_counter = m->step_counter.as<int32_t>(), P.advance = advance;
     P.err = m->errflag.as<int>();
     P.timing = m->st_timing_on ? m->st_timing.as<unsigned long long>() : nullptr;
+    P.dbg = m->st_timing_on ? m->st_timing.as<unsigned long long>() + size_t(m->st_grid) * (c.n_layers * 5 + 1) * 4 : nullptr;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(m->st_grid), cfg.blockDim = dim3(kStThreads), cfg.dynamicSmemBytes = geo.smem, cfg.stream = L.s;
     cudaLaunchAttribute attr[1];
@@ -1185,6 +1198,7 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
     m->step_counter.view(m->io_in.as<int32_t>() + 3 * R, 4);
     m->io_out.alloc(16 + size_t(kMaxLogSteps) * R * 4);
     MC_CUDA_CHECK(cudaMemset(m->io_out.p, 0, 16));
+    MC_CUDA_CHECK(cudaMemset(m->io_out.as<char>() + 8, 0x7f, 4)); // (diagnostics: lowest failing wait, see check_mega_error)
     m->errflag.view(m->io_out.p, 16), m->out_log.view(m->io_out.as<char>() + 16, size_t(kMaxLogSteps) * R * 4);
     m->uniforms.alloc(size_t(kMaxLogSteps) * R * 4);
     m->cand.alloc(size_t(R) * ((m->Vl + kSampleSlice - 1) / kSampleSlice) * kSampleKeep * 8);
@@ -1376,9 +1390,27 @@ mc_status mc_llama_prefill(mc_llama* m, uint32_t seq, const int32_t* ids, uint32
 static void check_mega_error(mc_llama* m, int flag)
 {
     if (flag) {
-        cudaMemset(m->errflag.p, 0, 4);
+#ifdef ST_DEBUG_WHERE
+        int w[148 * 4];
+        cudaMemcpyFromSymbol(w, g_st_where, sizeof(w));
+        for (int i = 0; i < 148; i++) fprintf(stderr, "CTA %d: mma %d epi %d prod %d\n", i, w[i * 4], w[i * 4 + 1], w[i * 4 + 2]);
+        {
+            std::vector<uint64_t> am(148 * 2);
+            cudaMemcpy(am.data(), m->st_ll.as<uint64_t>() + m->st_off[6], am.size() * 8, cudaMemcpyDeviceToHost);
+            uint64_t idw = 0;
+            cudaMemcpy(&idw, m->st_ll.as<uint64_t>() + m->st_off[7], 8, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "tag_base %u ids tag %u\n", m->st_seq << 16, unsigned(idw >> 32));
+            for (int i = 0; i < 148; i++) fprintf(stderr, "am[%d] tags %u %u\n", i, unsigned(am[2 * i] >> 32) - (m->st_seq << 16), unsigned(am[2 * i + 1] >> 32) - (m->st_seq << 16));
+        }
+#endif
+        int info[4] = {0, 0, 0, 0};
+        cudaMemcpy(info, m->errflag.p, 16, cudaMemcpyDeviceToHost);
+        cudaMemset(m->errflag.p, 0, 16);
         cudaMemset(m->bar.p, 0, 4);
-        throw error(MC_ERR_RUNTIME, "persistent decode kernel: a barrier wait timed out (code " + std::to_string(flag) + "; CTAs not co-resident?)");
+        cudaMemset(static_cast<char*>(m->errflag.p) + 8, 0x7f, 4);
+        throw error(MC_ERR_RUNTIME, "persistent decode kernel: a bounded wait timed out (code " + std::to_string(flag) + ", wait kinds mask " + std::to_string(info[1]) +
+                                        ", first: kind " + std::to_string(info[2] >> 20) + " CTA " + std::to_string((info[2] >> 10) & 1023) + " thread " +
+                                        std::to_string(info[2] & 1023) + "; CTAs not co-resident?)");
     }
 }
 
@@ -1522,7 +1554,7 @@ mc_status mc_llama_profile_step(mc_llama* m, uint32_t n, float* us, uint32_t cap
         // streaming kernel: four globaltimer stamps per (CTA, phase) = phase entry, (unused), input staged, tiles consumed;
         // us[(cta * phases + k) * 4 + j] = microseconds since the earliest stamp of the launch
         const uint32_t phases = m->cfg.n_layers * 5 + 1, G = m->st_grid;
-        const size_t n = size_t(G) * phases * 4;
+        const size_t n = size_t(G) * phases * 4 + 512; // + per-block stamps of CTA 0 in the vocabulary projection
         if (!m->st_timing.p) m->st_timing.alloc(n * 8);
         MC_CUDA_CHECK(cudaMemsetAsync(m->st_timing.p, 0, m->st_timing.bytes, m->dev->stream));
         MC_CUDA_CHECK(cudaMemsetAsync(m->step_counter.p, 0, 4, m->dev->stream));

@@ -42,7 +42,8 @@ constexpr int kStTileRows = 16;                       // weight rows per tile (t
 constexpr int kStMaxKC = 1024;                        // k elements per tile row
 constexpr int kStPad = 64;                            // bytes of padding per staged row
 constexpr int kStStageBytes = kStTileRows * (kStMaxKC * 2 + kStPad);
-constexpr int kStMaxStages = 8;
+constexpr int kStMaxStages = 12;
+constexpr int kStStageBytesPacked = 18432;            // quantised models: an int4 tile (16 KiB + 2 KiB of scales) per stage, more stages
 constexpr int kStSplits = 4;                          // CTAs per (row, head) in the attention phase
 constexpr int kStMaxRep = 8;                          // copies of every exchanged vector (spreads the pollers over L2 lines)
 constexpr int kStMaxRows = 8;                         // activation rows (the n of the mma)
@@ -79,6 +80,8 @@ struct st_params {
     size_t layer_stride;     // bytes between consecutive layers in the weight arena
     size_t kv_layer_stride;  // elements between consecutive layers in the KV cache
     uint32_t n_layers, rows, steps, n_stages;
+    uint32_t stage_bytes;    // bytes of one ring stage
+    uint32_t kc_a[4];        // k per tile of the LoRA-A rows of the four linears of a block
     uint32_t lora_rank;
     float lora_scale;        // r(scale) as fp32
     int32_t tok_fmt;         // WF_BF16, or WF_W8ROW: int8 embedding rows with one fp32 scale per row
@@ -115,6 +118,7 @@ struct st_params {
     int32_t advance;
     int* err;
     unsigned long long* timing; // diagnostics (nullable): 4 globaltimer stamps per (CTA, phase)
+    unsigned long long* dbg;    // diagnostics (nullable): per-block stamps of CTA 0 in the vocabulary projection: [block][8]
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------------------------------
@@ -185,6 +189,7 @@ __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;"
 struct st_ctx {
     uint32_t full0, empty0;   // shared addresses of full[kStMaxStages], empty[kStMaxStages]
     uint32_t rdy0, fre0;      // shared addresses of ready[kStRedBufs] (partials written), free[kStRedBufs] (partials consumed)
+    uint32_t sbar;            // shared address of the end-of-step mbarrier
     float* escr;              // [128] scratch of the epilogue warps
     volatile int* dead;       // set when a wait timed out somewhere: every later wait falls through
     float* scr;               // [16] block-reduce scratch
@@ -197,9 +202,21 @@ struct st_ctx {
 };
 
 // bounded waits: a lost arrival must end in an error code, never in a hung GPU
+#ifdef ST_DEBUG_WHERE
+__device__ int g_st_where[148 * 4];
+__device__ int g_st_frozen;
+__device__ __forceinline__ void st_where(int kind)
+{
+    const int role = threadIdx.x == 0 ? 0 : (threadIdx.x == kStConsumers ? 1 : (threadIdx.x == kStConsumers + kStEpiThreads ? 2 : -1));
+    if (role >= 0 && *reinterpret_cast<volatile int*>(&g_st_frozen) == 0) g_st_where[blockIdx.x * 4 + role] = kind;
+}
+#else
+__device__ __forceinline__ void st_where(int) {}
+#endif
 __device__ __forceinline__ void st_mbar_wait(const st_ctx& c, uint32_t a, uint32_t parity)
 {
     if (mbar_try_wait(a, parity)) return;
+    st_where(100 + int((a - c.full0) >> 3));
     if (*c.dead) return;
     unsigned spins = 0;
     while (!mbar_try_wait(a, parity)) {
@@ -210,6 +227,9 @@ __device__ __forceinline__ void st_mbar_wait(const st_ctx& c, uint32_t a, uint32
                 return;
             }
             if (spins > (1u << 22)) {
+#ifdef ST_DEBUG_WHERE
+                g_st_frozen = 1;
+#endif
                 atomicExch(c.err, 4);
                 *c.dead = 1;
                 return;
@@ -237,8 +257,9 @@ __device__ __forceinline__ uint64_t st_ll_load1(const uint64_t* p)
     return a;
 }
 // one failed poll: returns true when the caller should give up (another wait timed out, or this one did)
-__device__ __forceinline__ bool st_poll_backoff(const st_ctx& c, unsigned& spins)
+__device__ __forceinline__ bool st_poll_backoff(const st_ctx& c, unsigned& spins, int where = 0)
 {
+    if (spins == 0) st_where(where);
     if (*c.dead) return true;
     if (c.poll_ns) __nanosleep(c.poll_ns);
     if ((++spins & 1023u) == 0) {
@@ -247,20 +268,30 @@ __device__ __forceinline__ bool st_poll_backoff(const st_ctx& c, unsigned& spins
             return true;
         }
         if (spins > (1u << 21)) {
-            atomicExch(c.err, 1);
+#ifdef ST_DEBUG_WHERE
+            g_st_frozen = 1;
+#endif
+            atomicCAS(c.err, 0, 1);
+            atomicOr(c.err + 1, 1 << where); // which kinds of wait failed
+            atomicMin(c.err + 2, int(blockIdx.x) * 1024 + int(threadIdx.x) + (where << 20)); // lowest (kind, CTA, thread)
             *c.dead = 1;
             return true;
         }
     }
     return false;
 }
-__device__ __forceinline__ uint32_t st_poll1(const st_ctx& c, const uint64_t* p, uint32_t tag)
+__device__ __forceinline__ uint32_t st_poll1(const st_ctx& c, const uint64_t* p, uint32_t tag, int where = 0)
 {
     unsigned spins = 0;
     for (;;) {
         const uint64_t a = st_ll_load1(p);
         if (uint32_t(a >> 32) == tag) return uint32_t(a);
-        if (st_poll_backoff(c, spins)) return 0;
+        if (st_poll_backoff(c, spins, where)) {
+#ifdef ST_DEBUG_WHERE
+            if (spins > (1u << 21)) printf("cta %d tid %d kind %d expects tag %u saw %u payload %u\n", blockIdx.x, threadIdx.x, where, tag, uint32_t(a >> 32), uint32_t(a));
+#endif
+            return 0;
+        }
     }
 }
 __device__ __forceinline__ void st_stamp(unsigned long long* t, unsigned idx)
@@ -360,7 +391,7 @@ template <bool Q> struct st_tile_iter {
                 stage = r.has_a ? 1 : 2;
             }
             if (Q && stage == 1) {
-                const uint32_t kca = P.g[gi].K % 1024 == 0 ? 1024u : (g.K % 512 == 0 ? 512u : 256u);
+                const uint32_t kca = P.kc_a[gi];
                 t.kind = ST_T_ROWS, t.nr = 2;
                 t.src = st_layer_ptr(P, g, g.lora_a, li) + (size_t(2 * blockIdx.x) * g.K + kc) * 2;
                 t.row_stride = size_t(g.K) * 2, t.bytes = kca * 2, t.pitch = kca * 2 + kStPad;
@@ -401,17 +432,19 @@ template <bool Q> __device__ __forceinline__ void st_producer(const st_params& P
     st_tile t;
     while (ld.next(P, t)) {
         st_mbar_wait(c, c.empty0 + pp.stage * 8, pp.parity ^ 1u);
-        const uint32_t full = c.full0 + pp.stage * 8, dst = c.ring_addr + pp.stage * kStStageBytes;
+        const uint32_t full = c.full0 + pp.stage * 8, dst = c.ring_addr + pp.stage * P.stage_bytes;
         if (!Q || t.kind == ST_T_ROWS) {
             if (lane == 0) mbar_expect_tx(full, t.nr * t.bytes);
             __syncwarp();
             if (lane < t.nr) bulk_g2s(dst + lane * t.pitch, t.src + size_t(lane) * t.row_stride, t.bytes, full, policy);
         } else {
-            if (lane == 0) {
-                mbar_expect_tx(full, t.bytes + (t.kind == ST_T_W4 ? t.bytes2 : 0u));
-                bulk_g2s(dst, t.src, t.bytes, full, policy);
-                if (t.kind == ST_T_W4) bulk_g2s(dst + kStW4ScaleOff, t.src2, t.bytes2, full, policy);
-            }
+            // a packed tile is one contiguous run; it still goes as 2 KiB pieces (one per lane): many small bulk copies keep more
+            // memory requests in flight than one large one
+            const uint32_t piece = 2048, n_pieces = (t.bytes + piece - 1) / piece;
+            if (lane == 0) mbar_expect_tx(full, t.bytes + (t.kind == ST_T_W4 ? t.bytes2 : 0u));
+            __syncwarp();
+            if (lane < n_pieces) bulk_g2s(dst + lane * piece, t.src + size_t(lane) * piece, min(piece, t.bytes - lane * piece), full, policy);
+            else if (lane == n_pieces && t.kind == ST_T_W4) bulk_g2s(dst + kStW4ScaleOff, t.src2, t.bytes2, full, policy);
         }
         pp.advance(P.n_stages);
     }
@@ -439,7 +472,7 @@ template <bool Q> __device__ __forceinline__ void st_stage_input(const st_params
     int32_t* sids = reinterpret_cast<int32_t*>(c.scr + 8);
     if (embed) {
         if (tid < P.rows) {
-            int32_t id = step == 0 ? P.ids[tid] : int32_t(st_poll1(c, P.ids_ll + tid, tag_in));
+            int32_t id = step == 0 ? P.ids[tid] : int32_t(st_poll1(c, P.ids_ll + tid, tag_in, 2));
             if (id < 0 || uint32_t(id) >= P.vocab) id = 0;
             sids[tid] = id;
         }
@@ -489,7 +522,7 @@ template <bool Q> __device__ __forceinline__ void st_stage_input(const st_params
                     if (w < n_words) {
                         unsigned spins = 0;
                         while (uint32_t(a[j] >> 32) != tag_in || uint32_t(b[j] >> 32) != tag_in) {
-                            if (st_poll_backoff(c, spins)) break;
+                            if (st_poll_backoff(c, spins, 1)) break;
                             st_ll_load2(src + w, a[j], b[j]);
                         }
                     }
@@ -577,7 +610,7 @@ __device__ __forceinline__ void st_hand_over(const st_ctx& c, st_blk& bl, const 
     bl.advance();
 }
 // one block of bf16 rows: K / kc tiles of `kc` k, the 64-byte padded row-major staging
-__device__ __forceinline__ void st_mma_rows(const st_params& P, const st_ctx& c, st_pipe& cp, st_blk& bl, uint32_t K, uint32_t kc_tile)
+__device__ __forceinline__ void st_mma_rows(const st_params& P, const st_ctx& c, st_pipe& cp, st_blk& bl, uint32_t K, uint32_t kc_tile, uint32_t nr)
 {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t gq = lane >> 2, t = lane & 3;
@@ -586,17 +619,19 @@ __device__ __forceinline__ void st_mma_rows(const st_params& P, const st_ctx& c,
     const uint32_t ksteps = kc_tile / kStWarps / 32;
     const uint32_t brow = gq < P.rows ? gq : 0;      // batch row of this lane's B fragment (unused columns read row 0)
     const uint32_t b_base = c.act_addr + brow * P.act_pitch + (kw + t * 8) * 2;
-    const uint32_t a_off = gq * pitch + (kw + t * 8) * 2;
+    // rows beyond the block read a valid row instead (their results are never stored)
+    const uint32_t a_off = min(gq, nr - 1) * pitch + (kw + t * 8) * 2;
+    const uint32_t a_hi = (min(gq + 8, nr - 1) - min(gq, nr - 1)) * pitch;
     float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     for (uint32_t kc = 0; kc < K; kc += kc_tile) {
         st_mbar_wait(c, c.full0 + cp.stage * 8, cp.parity);
-        const uint32_t tile = c.ring_addr + cp.stage * kStStageBytes + a_off;
+        const uint32_t tile = c.ring_addr + cp.stage * P.stage_bytes + a_off;
         const uint32_t bk = b_base + kc * 2;
         // the k permutation (lane t reads 8 consecutive k) is applied to both operands
 #pragma unroll 4
         for (uint32_t s = 0; s < ksteps; s++) {
             const uint4 alo = lds128(tile + s * 64);
-            const uint4 ahi = lds128(tile + 8 * pitch + s * 64);
+            const uint4 ahi = lds128(tile + a_hi + s * 64);
             const uint4 b = lds128(bk + s * 64);
             mma_bf16_16816(acc, alo.x, ahi.x, alo.y, ahi.y, b.x, b.y);
             mma_bf16_16816(acc, alo.z, ahi.z, alo.w, ahi.w, b.z, b.w);
@@ -609,8 +644,16 @@ __device__ __forceinline__ void st_mma_rows(const st_params& P, const st_ctx& c,
 }
 // one super-unit of packed weights: in-register dequant with the reference's two roundings r(r(q) * r(s))
 // (kernel/mul.metal:76-77), then mma; see gemv_q_kernel for the fragment layout
+__device__ __forceinline__ void st_dbg(unsigned long long* d, uint32_t blk, uint32_t slot, uint32_t who)
+{
+    if (d && blockIdx.x == 0 && threadIdx.x == who && blk < 64) {
+        unsigned long long v;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+        d[blk * 8 + slot] = v;
+    }
+}
 template <int FMT>
-__device__ __forceinline__ void st_mma_packed(const st_params& P, const st_gemv& g, const st_ctx& c, st_pipe& cp, st_blk& bl, float rs0, float rs1)
+__device__ __forceinline__ void st_mma_packed(const st_params& P, const st_gemv& g, const st_ctx& c, st_pipe& cp, st_blk& bl, float rs0, float rs1, unsigned long long* dbg = nullptr, uint32_t dblk = 0)
 {
     constexpr uint32_t KT = FMT == WF_W4 ? 64 : 32;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -621,60 +664,84 @@ __device__ __forceinline__ void st_mma_packed(const st_params& P, const st_gemv&
     const uint32_t brow = gq < P.rows ? gq : 0;
     const uint32_t xb = c.act_addr + brow * P.act_pitch + 4 * t;      // B fragment base of this lane
     float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc2[4] = {0.0f, 0.0f, 0.0f, 0.0f}; // two chains: consecutive mma do not wait for each other
+    st_dbg(dbg, dblk, 0, 0);
+    // operands of one k-tile: the packed weights, (int4) the group scales, the B fragments.  The loads are volatile asm, i.e.
+    // kept in program order, so the k-tile loop is software-pipelined by hand: the operands of k-tile i+1 are requested
+    // before k-tile i is dequantised and multiplied.
+    constexpr int NJ = FMT == WF_W4 ? 4 : 2;
+    struct ops {
+        uint4 wv;
+        uint2 sv;
+        uint32_t b0[NJ], b1[NJ];
+    };
+    auto load = [&](ops& o, uint32_t tile, uint32_t kc, uint32_t kt) {
+        o.wv = lds128(tile + (kt * 32 + lane) * 16);
+        if (FMT == WF_W4) o.sv = lds64(tile + kStW4ScaleOff + (kt * 8 + gq) * 8);
+        const uint32_t xk = xb + (kc + kt * KT) * 2;
+#pragma unroll
+        for (int j = 0; j < NJ; j++) o.b0[j] = lds32(xk + j * 32), o.b1[j] = lds32(xk + j * 32 + 16);
+    };
+    auto compute = [&](const ops& o) {
+        const uint32_t words[4] = {o.wv.x, o.wv.y, o.wv.z, o.wv.w};
+        if (FMT == WF_W4) {
+            // scales of (row r0, row r1) for k-groups 0 and 1 of this k-tile, as (s,s) bf16x2
+            const uint32_t s_g0 = __byte_perm(o.sv.x, 0, 0x1010), s_g1 = __byte_perm(o.sv.x, 0, 0x3232);
+            const uint32_t s_h0 = __byte_perm(o.sv.y, 0, 0x1010), s_h1 = __byte_perm(o.sv.y, 0, 0x3232);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t w = words[j];
+                const uint32_t sg = j < 2 ? s_g0 : s_g1, sh = j < 2 ? s_h0 : s_h1;
+                const uint32_t a0 = hmul2_bf16(hsub2_bf16((w & 0x000f000fu) | 0x43004300u, 0x43084308u), sg);
+                const uint32_t a1 = hmul2_bf16(hsub2_bf16(((w >> 4) & 0x000f000fu) | 0x43004300u, 0x43084308u), sh);
+                const uint32_t a2 = hmul2_bf16(hsub2_bf16(((w >> 8) & 0x000f000fu) | 0x43004300u, 0x43084308u), sg);
+                const uint32_t a3 = hmul2_bf16(hsub2_bf16(((w >> 12) & 0x000f000fu) | 0x43004300u, 0x43084308u), sh);
+                if (j & 1) mma_bf16_16816(acc2, a0, a1, a2, a3, o.b0[j], o.b1[j]);
+                else mma_bf16_16816(acc, a0, a1, a2, a3, o.b0[j], o.b1[j]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const uint32_t lo = words[2 * j] ^ 0x80808080u, hi = words[2 * j + 1] ^ 0x80808080u;
+                const uint32_t a0 = pack_bf16x2(__fmul_rn(s8_to_f32(lo, 0), rs0), __fmul_rn(s8_to_f32(lo, 1), rs0));
+                const uint32_t a1 = pack_bf16x2(__fmul_rn(s8_to_f32(lo, 2), rs1), __fmul_rn(s8_to_f32(lo, 3), rs1));
+                const uint32_t a2 = pack_bf16x2(__fmul_rn(s8_to_f32(hi, 0), rs0), __fmul_rn(s8_to_f32(hi, 1), rs0));
+                const uint32_t a3 = pack_bf16x2(__fmul_rn(s8_to_f32(hi, 2), rs1), __fmul_rn(s8_to_f32(hi, 3), rs1));
+                if (j & 1) mma_bf16_16816(acc2, a0, a1, a2, a3, o.b0[j], o.b1[j]);
+                else mma_bf16_16816(acc, a0, a1, a2, a3, o.b0[j], o.b1[j]);
+            }
+        }
+    };
     for (uint32_t kc = 0; kc < g.K; kc += g.KC) {
         st_mbar_wait(c, c.full0 + cp.stage * 8, cp.parity);
-        const uint32_t tile = c.ring_addr + cp.stage * kStStageBytes;
-#pragma unroll 2
-        for (uint32_t kt = kt_b; kt < kt_e; kt++) {
-            const uint4 wv = lds128(tile + (kt * 32 + lane) * 16);
-            const uint32_t xk = xb + (kc + kt * KT) * 2;
-            const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
-            if (FMT == WF_W4) {
-                const uint2 sv = lds64(tile + kStW4ScaleOff + (kt * 8 + gq) * 8);
-                // scales of (row r0, row r1) for k-groups 0 and 1 of this k-tile, as (s,s) bf16x2
-                const uint32_t s_g0 = __byte_perm(sv.x, 0, 0x1010), s_g1 = __byte_perm(sv.x, 0, 0x3232);
-                const uint32_t s_h0 = __byte_perm(sv.y, 0, 0x1010), s_h1 = __byte_perm(sv.y, 0, 0x3232);
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t w = words[j];
-                    const uint32_t sg = j < 2 ? s_g0 : s_g1, sh = j < 2 ? s_h0 : s_h1;
-                    const uint32_t a0 = hmul2_bf16(hsub2_bf16((w & 0x000f000fu) | 0x43004300u, 0x43084308u), sg);
-                    const uint32_t a1 = hmul2_bf16(hsub2_bf16(((w >> 4) & 0x000f000fu) | 0x43004300u, 0x43084308u), sh);
-                    const uint32_t a2 = hmul2_bf16(hsub2_bf16(((w >> 8) & 0x000f000fu) | 0x43004300u, 0x43084308u), sg);
-                    const uint32_t a3 = hmul2_bf16(hsub2_bf16(((w >> 12) & 0x000f000fu) | 0x43004300u, 0x43084308u), sh);
-                    if (j & 1) mma_bf16_16816(acc2, a0, a1, a2, a3, lds32(xk + j * 32), lds32(xk + j * 32 + 16));
-                    else mma_bf16_16816(acc, a0, a1, a2, a3, lds32(xk + j * 32), lds32(xk + j * 32 + 16));
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    const uint32_t lo = words[2 * j] ^ 0x80808080u, hi = words[2 * j + 1] ^ 0x80808080u;
-                    const uint32_t a0 = pack_bf16x2(__fmul_rn(s8_to_f32(lo, 0), rs0), __fmul_rn(s8_to_f32(lo, 1), rs0));
-                    const uint32_t a1 = pack_bf16x2(__fmul_rn(s8_to_f32(lo, 2), rs1), __fmul_rn(s8_to_f32(lo, 3), rs1));
-                    const uint32_t a2 = pack_bf16x2(__fmul_rn(s8_to_f32(hi, 0), rs0), __fmul_rn(s8_to_f32(hi, 1), rs0));
-                    const uint32_t a3 = pack_bf16x2(__fmul_rn(s8_to_f32(hi, 2), rs1), __fmul_rn(s8_to_f32(hi, 3), rs1));
-                    if (j & 1) mma_bf16_16816(acc2, a0, a1, a2, a3, lds32(xk + j * 32), lds32(xk + j * 32 + 16));
-                    else mma_bf16_16816(acc, a0, a1, a2, a3, lds32(xk + j * 32), lds32(xk + j * 32 + 16));
-                }
+        if (kc == 0) st_dbg(dbg, dblk, 1, 0);
+        const uint32_t tile = c.ring_addr + cp.stage * P.stage_bytes;
+        if (kt_b < kt_e) {
+            ops cur, nxt;
+            load(cur, tile, kc, kt_b);
+            for (uint32_t kt = kt_b; kt < kt_e; kt++) {
+                if (kt + 1 < kt_e) load(nxt, tile, kc, kt + 1);
+                compute(cur);
+                cur = nxt;
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(c.empty0 + cp.stage * 8);
         cp.advance(P.n_stages);
     }
+    st_dbg(dbg, dblk, 2, 0);
 #pragma unroll
     for (int i = 0; i < 4; i++) acc[i] += acc2[i];
     // mma row g = unit su*8+g row r0, row g+8 = its row r1: rope pairs keep that order, adjacent-row units interleave
     if (g.qkv_map) st_hand_over(c, bl, acc, gq, gq + 8);
     else st_hand_over(c, bl, acc, 2 * gq, 2 * gq + 1);
+    st_dbg(dbg, dblk, 3, 0);
 }
-__device__ __forceinline__ uint32_t st_kc_a(uint32_t K) { return K % 1024 == 0 ? 1024u : (K % 512 == 0 ? 512u : 256u); }
 template <bool Q> __device__ __forceinline__ void st_mma_gemv(const st_params& P, const st_gemv& g, const st_ctx& c, st_pipe& cp, st_blk& bl, uint32_t li)
 {
     const st_range r(g, Q);
-    if (Q && r.has_a) st_mma_rows(P, c, cp, bl, g.K, st_kc_a(g.K));
+    if (Q && r.has_a) st_mma_rows(P, c, cp, bl, g.K, P.kc_a[&g - P.g], 2);
     if (!Q || g.fmt == WF_BF16) {
-        for (uint32_t r0 = r.b0; r0 < r.b1; r0 += kStTileRows) st_mma_rows(P, c, cp, bl, g.K, g.KC);
+        for (uint32_t r0 = r.b0; r0 < r.b1; r0 += kStTileRows) st_mma_rows(P, c, cp, bl, g.K, g.KC, min(uint32_t(kStTileRows), r.b1 - r0));
     } else if (g.fmt == WF_W4) {
         for (uint32_t su = r.b0; su < r.b1; su++) st_mma_packed<WF_W4>(P, g, c, cp, bl, 0.0f, 0.0f);
     } else {
@@ -686,7 +753,7 @@ template <bool Q> __device__ __forceinline__ void st_mma_gemv(const st_params& P
         for (uint32_t su = r.b0; su < r.b1; su++) {
             float n0 = 0.0f, n1 = 0.0f;
             if (su + 1 < r.b1) n0 = sc[(su + 1) * 16 + 2 * gq], n1 = sc[(su + 1) * 16 + 2 * gq + 1];
-            st_mma_packed<WF_W8ROW>(P, g, c, cp, bl, rbf(s0), rbf(s1));
+            st_mma_packed<WF_W8ROW>(P, g, c, cp, bl, rbf(s0), rbf(s1), P.dbg, su - r.b0);
             s0 = n0, s1 = n1;
         }
     }
@@ -776,7 +843,7 @@ template <bool Q> __device__ __forceinline__ void st_epi_gemv(const st_params& P
         epi_bar();
         for (uint32_t i = et; i < P.rows * (g.n_a >> 1); i += kStEpiThreads) {
             const uint32_t m = i / (g.n_a >> 1), w = i - m * (g.n_a >> 1);
-            const uint32_t v = st_poll1(c, g.ax_ll + size_t(m) * (g.n_a >> 1) + w, tag_out);
+            const uint32_t v = st_poll1(c, g.ax_ll + size_t(m) * (g.n_a >> 1) + w, tag_out, 5);
             sax[m * g.n_a + 2 * w] = bf_lo(v), sax[m * g.n_a + 2 * w + 1] = bf_hi(v);
         }
         epi_bar();
@@ -789,8 +856,11 @@ template <bool Q> __device__ __forceinline__ void st_epi_gemv(const st_params& P
         if (g.ax_slices == 2) sl = R & 1u;
         else if (g.ax_slices == 3) sl = R < g.slice_rows0 ? 0u : (R < g.slice_rows1 ? 1u : 2u);
         st_mbar_wait(c, c.rdy0 + bl.buf * 8, bl.parity);
+        if (is_head) st_dbg(P.dbg, (b - r.b0) / bstep, 4, kStConsumers);
         const float* rr = c.red + bl.buf * (kStWarps * 128) + (2 * sub) * 128 + erow * 8;
-        for (uint32_t col = 0; col < P.rows; col++) {
+#pragma unroll
+        for (uint32_t col = 0; col < uint32_t(kStMaxRows); col++) {
+            if (col >= P.rows) break; // (uniform) the loop is unrolled so that the per-column state stays in registers
             float sum = rr[col] + rr[128 + col];
             sum += __shfl_xor_sync(0xffffffffu, sum, 1);
             sum += __shfl_xor_sync(0xffffffffu, sum, 2);
@@ -819,12 +889,10 @@ template <bool Q> __device__ __forceinline__ void st_epi_gemv(const st_params& P
                 if (st) st_ll_store_rep(P, g.out_ll + size_t(col) * out_pitch + (R >> 2), pack2(z, z1), tag_out);
             } else if (g.epi == EPI_RESIDUAL) {
                 // h = r(x + a)  (nn/transformer.h:133,139); the residual word of column `col` sits in lane (col & 3) of this row
-                const uint64_t a0 = __shfl_sync(0xffffffffu, resw[0], (lane & ~3u) | (col & 3u));
-                const uint64_t a1 = __shfl_sync(0xffffffffu, resw[1], (lane & ~3u) | (col & 3u));
+                const uint64_t rw = __shfl_sync(0xffffffffu, col < 4 ? resw[0] : resw[1], (lane & ~3u) | (col & 3u));
                 if (st) {
-                    const uint64_t rw = col < 4 ? a0 : a1;
                     uint32_t rv = uint32_t(rw);
-                    if (uint32_t(rw >> 32) != res_tag) rv = st_poll1(c, g.res_ll + size_t(col) * out_pitch + (R >> 1), res_tag);
+                    if (uint32_t(rw >> 32) != res_tag) rv = st_poll1(c, g.res_ll + size_t(col) * out_pitch + (R >> 1), res_tag, 6);
                     st_ll_store_rep(P, g.out_ll + size_t(col) * out_pitch + (R >> 1), pack2(__fadd_rn(bf_lo(rv), y), __fadd_rn(bf_hi(rv), y1)), tag_out);
                 }
             } else if (!is_head) {
@@ -832,14 +900,13 @@ template <bool Q> __device__ __forceinline__ void st_epi_gemv(const st_params& P
             } else if (st) {
                 *reinterpret_cast<uint32_t*>(g.y + size_t(col) * g.N + R) = pack2(y, y1);
                 // greedy argmax of column `col`: kept by the storing lanes, one slot per column
-                float& bv = best.v[col];
-                int32_t& bi = best.i[col];
-                if (y > bv || (y == bv && int32_t(R) < bi)) bv = y, bi = int32_t(R);
-                if (y1 > bv || (y1 == bv && int32_t(R + 1) < bi)) bv = y1, bi = int32_t(R + 1);
+                if (y > best.v[col] || (y == best.v[col] && int32_t(R) < best.i[col])) best.v[col] = y, best.i[col] = int32_t(R);
+                if (y1 > best.v[col] || (y1 == best.v[col] && int32_t(R + 1) < best.i[col])) best.v[col] = y1, best.i[col] = int32_t(R + 1);
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(c.fre0 + bl.buf * 8);
+        if (is_head) st_dbg(P.dbg, (b - r.b0) / bstep, 5, kStConsumers);
         bl.advance();
         resw[0] = n_resw[0], resw[1] = n_resw[1], bq = n_bq;
     }
@@ -905,7 +972,7 @@ __device__ __forceinline__ void st_attention(const st_params& P, uint32_t li, ui
             const uint32_t grp = tid / half, i = tid % half; // 0: q, 1: v, 2: k
             if (grp < 2 || (grp == 2 && own)) {
                 const uint32_t base = grp == 0 ? head * HD : (grp == 1 ? (H + KV + kvh) * HD : (H + kvh) * HD);
-                const uint32_t w = st_poll1(c, qrow + (base >> 1) + i, tag_in);
+                const uint32_t w = st_poll1(c, qrow + (base >> 1) + i, tag_in, 3);
                 float* d = grp == 0 ? rawq : (grp == 1 ? sv : rawk);
                 d[2 * i] = bf_lo(w), d[2 * i + 1] = bf_hi(w);
                 if (grp == 1 && writer) *reinterpret_cast<uint32_t*>(P.vcache + coff + size_t(pos) * HD + 2 * i) = w;
@@ -985,7 +1052,7 @@ __device__ __forceinline__ void st_attention(const st_params& P, uint32_t li, ui
             st_ll_store(sc + (tt >> 1), pack2(sp[tt], tt + 1 < t1 ? sp[tt + 1] : 0.0f), tag_out);
         consumer_bar(); // sp is about to be overwritten with everybody's scores
         for (uint32_t w = tid; w < (np + 1) / 2; w += kStConsumers) {
-            const uint32_t v = st_poll1(c, sc + w, tag_out);
+            const uint32_t v = st_poll1(c, sc + w, tag_out, 4);
             sp[2 * w] = bf_lo(v), sp[2 * w + 1] = bf_hi(v);
         }
         consumer_bar();
@@ -1039,10 +1106,11 @@ template <bool Q, int HD> __global__ void __launch_bounds__(kStThreads, 1) decod
     extern __shared__ __align__(16) unsigned char smem[];
     st_ctx c;
     c.full0 = smem_u32(smem);
-    c.empty0 = c.full0 + kStMaxStages * 8;
-    c.rdy0 = c.empty0 + kStMaxStages * 8;
-    c.fre0 = c.rdy0 + kStRedBufs * 8;
-    c.dead = reinterpret_cast<volatile int*>(smem + 224);
+    c.empty0 = c.full0 + kStMaxStages * 8;   // 96
+    c.rdy0 = c.empty0 + kStMaxStages * 8;    // 192
+    c.fre0 = c.rdy0 + kStRedBufs * 8;        // 216
+    c.sbar = c.fre0 + kStRedBufs * 8;        // 240: the mma warps finished the last phase of a step
+    c.dead = reinterpret_cast<volatile int*>(smem + 248);
     c.scr = reinterpret_cast<float*>(smem + 256);
     c.escr = reinterpret_cast<float*>(smem + 320);
     c.red = reinterpret_cast<float*>(smem + kStHdrBytes);
@@ -1062,6 +1130,7 @@ template <bool Q, int HD> __global__ void __launch_bounds__(kStThreads, 1) decod
             mbar_init(c.rdy0 + s * 8, kStWarps);
             mbar_init(c.fre0 + s * 8, kStEpiThreads / 32);
         }
+        mbar_init(c.sbar, kStWarps);
         *c.dead = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1100,7 +1169,10 @@ template <bool Q, int HD> __global__ void __launch_bounds__(kStThreads, 1) decod
                     st_stamp(P.timing ? P.timing + (size_t(blockIdx.x) * (P.steps * phases_per_step) + gphase) * 4 : nullptr, 1);
                 }
             }
-            // sampler tail (greedy): every CTA publishes its argmax partial, CTA 0 joins them and publishes the next id
+            // sampler tail (greedy): every CTA publishes its argmax partial, CTA 0 joins them and publishes the next id.
+            // The epilogue warps of a CTA without blocks run ahead of everybody: they may publish the partial of step s only when
+            // the mma warps of this CTA have finished step s (else the partials of later steps would overwrite it unread).
+            st_mbar_wait(c, c.sbar, step & 1u);
             const uint32_t tag_head = P.tag_base + gphase; // = tag_out of the head phase
             float* bv = c.escr;                                     // [8 cols][8 storing lanes]
             int32_t* bi = reinterpret_cast<int32_t*>(c.escr + 64);
@@ -1128,7 +1200,7 @@ template <bool Q, int HD> __global__ void __launch_bounds__(kStThreads, 1) decod
                     int32_t i = 0x7fffffff;
                     for (unsigned b = lane; b < G; b += 32) {
                         const uint64_t* src = P.am_ll + (size_t(row) * G + b) * 2;
-                        const float ov = __uint_as_float(st_poll1(c, src, tag_head));
+                        const float ov = __uint_as_float(st_poll1(c, src, tag_head, 7));
                         const int32_t oi = int32_t(st_poll1(c, src + 1, tag_head));
                         if (ov > v || (ov == v && oi < i)) v = ov, i = oi;
                     }
@@ -1174,6 +1246,10 @@ template <bool Q, int HD> __global__ void __launch_bounds__(kStThreads, 1) decod
                     st_stage_input<Q>(P, g, is_head ? 0 : li, c, li == 0 && kind == 0 && !is_head, step, tag_in, tag_out);
                     st_stamp(tm, 2);
                     st_mma_gemv<Q>(P, g, c, cp, bl, is_head ? 0 : li);
+                    if (is_head) {
+                        __syncwarp();
+                        if ((tid & 31) == 0) mbar_arrive(c.sbar);
+                    }
                 }
                 st_stamp(tm, 3);
             }

@@ -25,7 +25,9 @@ if mode == "stream":
     P = len(names)
     reps = []
     for rep in range(4):
-        t = m.profile_step(1).reshape(-1, P, 4)  # [cta][phase][entry, -, staged, done] in us
+        raw = m.profile_step(1)
+        dbg = raw[-512:].reshape(64, 8)
+        t = raw[:-512].reshape(-1, P, 4)  # [cta][phase][entry, -, staged, done] in us
         m.decode_loop([1], [512], 2)
         if rep:
             reps.append(t)
@@ -52,6 +54,11 @@ if mode == "stream":
     order = np.argsort(lag)
     print("mean lag behind the first finisher per CTA: min", lag[order[:5]].round(2), order[:5], "max", lag[order[-8:]].round(2), order[-8:])
     np.save("gpurun_out/stream_stamps.npy", t)
+    if dbg[:, 0].any():
+        d = dbg[:40]
+        print("head blocks of CTA 0 (us): wait-full, mma, hand-over | epilogue: ready after mma-done, epilogue time")
+        for i in range(0, 40, 4):
+            print(i, " ".join(f"[{d[j,1]-d[j,0]:.2f} {d[j,2]-d[j,1]:.2f} {d[j,3]-d[j,2]:.2f} | {d[j,4]-d[j,3]:.2f} {d[j,5]-d[j,4]:.2f}]" for j in range(i, i + 4)))
 elif mode == "mega":
     names = ["qkv", "attn", "wo", "w13", "w2"] * L + ["head"]
     acc = {}
