@@ -609,6 +609,13 @@ __device__ __forceinline__ void st_hand_over(const st_ctx& c, st_blk& bl, const 
     if (lane == 0) mbar_arrive(c.rdy0 + bl.buf * 8);
     bl.advance();
 }
+// (x & mask) | magic in one LOP3 (the compiler emits two when both are immediates)
+__device__ __forceinline__ uint32_t and_or(uint32_t x, uint32_t mask, uint32_t magic)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(x), "r"(mask), "r"(magic));
+    return d;
+}
 // one block of bf16 rows: K / kc tiles of `kc` k, the 64-byte padded row-major staging
 __device__ __forceinline__ void st_mma_rows(const st_params& P, const st_ctx& c, st_pipe& cp, st_blk& bl, uint32_t K, uint32_t kc_tile, uint32_t nr)
 {
@@ -681,6 +688,9 @@ __device__ __forceinline__ void st_mma_packed(const st_params& P, const st_gemv&
 #pragma unroll
         for (int j = 0; j < NJ; j++) o.b0[j] = lds32(xk + j * 32), o.b1[j] = lds32(xk + j * 32 + 16);
     };
+    // (kept in registers through volatile asm so that the compiler does not fold them back into immediates)
+    uint32_t nib_mask = 0x000f000fu, nib_magic = 0x43004300u;
+    asm volatile("" : "+r"(nib_mask), "+r"(nib_magic));
     auto compute = [&](const ops& o) {
         const uint32_t words[4] = {o.wv.x, o.wv.y, o.wv.z, o.wv.w};
         if (FMT == WF_W4) {
@@ -691,10 +701,10 @@ __device__ __forceinline__ void st_mma_packed(const st_params& P, const st_gemv&
             for (int j = 0; j < 4; j++) {
                 const uint32_t w = words[j];
                 const uint32_t sg = j < 2 ? s_g0 : s_g1, sh = j < 2 ? s_h0 : s_h1;
-                const uint32_t a0 = hmul2_bf16(hsub2_bf16((w & 0x000f000fu) | 0x43004300u, 0x43084308u), sg);
-                const uint32_t a1 = hmul2_bf16(hsub2_bf16(((w >> 4) & 0x000f000fu) | 0x43004300u, 0x43084308u), sh);
-                const uint32_t a2 = hmul2_bf16(hsub2_bf16(((w >> 8) & 0x000f000fu) | 0x43004300u, 0x43084308u), sg);
-                const uint32_t a3 = hmul2_bf16(hsub2_bf16(((w >> 12) & 0x000f000fu) | 0x43004300u, 0x43084308u), sh);
+                const uint32_t a0 = hmul2_bf16(hsub2_bf16(and_or(w, nib_mask, nib_magic), 0x43084308u), sg);
+                const uint32_t a1 = hmul2_bf16(hsub2_bf16(and_or(w >> 4, nib_mask, nib_magic), 0x43084308u), sh);
+                const uint32_t a2 = hmul2_bf16(hsub2_bf16(and_or(w >> 8, nib_mask, nib_magic), 0x43084308u), sg);
+                const uint32_t a3 = hmul2_bf16(hsub2_bf16(and_or(w >> 12, nib_mask, nib_magic), 0x43084308u), sh);
                 if (j & 1) mma_bf16_16816(acc2, a0, a1, a2, a3, o.b0[j], o.b1[j]);
                 else mma_bf16_16816(acc, a0, a1, a2, a3, o.b0[j], o.b1[j]);
             }
@@ -716,12 +726,15 @@ __device__ __forceinline__ void st_mma_packed(const st_params& P, const st_gemv&
         if (kc == 0) st_dbg(dbg, dblk, 1, 0);
         const uint32_t tile = c.ring_addr + cp.stage * P.stage_bytes;
         if (kt_b < kt_e) {
-            ops cur, nxt;
-            load(cur, tile, kc, kt_b);
-            for (uint32_t kt = kt_b; kt < kt_e; kt++) {
-                if (kt + 1 < kt_e) load(nxt, tile, kc, kt + 1);
-                compute(cur);
-                cur = nxt;
+            ops p0, p1; // ping-pong: no register copies between iterations
+            load(p0, tile, kc, kt_b);
+            for (uint32_t kt = kt_b; kt < kt_e; kt += 2) {
+                if (kt + 1 < kt_e) load(p1, tile, kc, kt + 1);
+                compute(p0);
+                if (kt + 1 < kt_e) {
+                    if (kt + 2 < kt_e) load(p0, tile, kc, kt + 2);
+                    compute(p1);
+                }
             }
         }
         __syncwarp();

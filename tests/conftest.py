@@ -17,3 +17,10 @@ def rng():
     import numpy as np
 
     return np.random.default_rng(0x5EED)
+
+
+# the streaming decode kernel serves one sequence by default (faster than the per-op path only there); the GPU tests
+# exercise its multi-sequence code as well
+import os
+
+os.environ.setdefault("MC_STREAM_MAX_ROWS", "8")
