@@ -2,7 +2,7 @@
 """bench.py — decode tokens/s of the B200 engine on BASELINE.json's configs[1]
 (Llama-3.2-1B-shaped bf16, batch 1, 512-token KV cache, random-init weights, synthetic ids).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload 1b-bf16|1b-w4] [--batch B] [--per-op]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload 1b-bf16|1b-w4|1b-bf16-prefill|8b-bf16-prefill] [--batch B] [--per-op] [--prompt S]
 
 A "step" is one decode step (one token per sequence).  Prints ONE JSON line (see DESIGN.md
 "Measurement").  `value` is device-timed (CUDA events on the engine's stream, token fed back on
@@ -187,6 +187,162 @@ def measure_gemv_family(capi, dev, shape, hbm_peak):
     return out, tot_b / tot_t / 1e9
 
 
+def tensor_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained: the GEMMs run back to back inside a long step)"
+    return 1373.0, "fallback (B200_PROFILING.md sustained)"
+
+
+def prefill_flops(shape: dict, S: int):
+    """Algorithmic flops of one prompt of S positions: 2 flop per (weight, position) in the blocks, causal attention
+    (half of the S x S score / value products), the vocabulary projection of the LAST position only (nn/llama.h:128-133)."""
+    D, F, hd, H, KV, L = shape["dim"], shape["ffn_dim"], shape["head_dim"], shape["n_heads"], shape["n_kv_heads"], shape["n_layers"]
+    per_layer_w = D * (H + 2 * KV) * hd + H * hd * D + 3 * D * F
+    linear = 2.0 * per_layer_w * S * L
+    attn = 2.0 * (S * (S + 1) / 2) * hd * H * 2 * L
+    head = 2.0 * shape["vocab"] * D
+    return linear, attn, head
+
+
+def run_prefill(args, shape_name, shape):
+    """Prompt throughput (BASELINE.json metric "prefill tok/s @2048"): a step = one prompt of --prompt positions through the
+    tensor-core prompt path (tcgen05 GEMMs + causal attention), logits of the last position produced."""
+    rank, world, local = dist_env()
+    S = args.prompt
+    workload = f"llama-{shape_name} bf16 prefill of {S} positions (BASELINE.json configs[3] prompt phase), 1 sequence per GPU"
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import orc
+
+        n = 64
+        m = orc.Llama(orc.make_cfg(**shape, max_seq_len=max(128, n)), orc.BF16)
+        m.init_random(0x5EED)
+        ids = np.random.default_rng(1).integers(0, shape["vocab"], size=n).tolist()
+        t0 = time.perf_counter()
+        m.forward(ids, 0)
+        sec = time.perf_counter() - t0
+        v = n / sec
+        print(json.dumps({"impl": "reference", "metric": "prefill_tokens_per_s", "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+                          "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                          "data": "synthetic ids, random-init weights (counter-hash seed 0x5EED)", "config": {"workload": workload, "prompt": S},
+                          "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": orc.num_threads(), "kind": "port",
+                                           "sample": f"one {n}-position prompt through the full model (scalar C++ oracle port, OpenMP over output rows)"},
+                          "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
+    import torch
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from metalchat_b200 import capi
+
+    dev = capi.Device(local)
+    m = capi.Llama(dev, capi.llama_config(**shape, max_seq_len=S, quant=0, n_seqs=1, flags=capi.LLAMA_NO_TC_PREFILL if args.per_op else 0))
+    m.init_random(0x5EED)
+    m.finalize()
+    rng = np.random.default_rng(0x5EED + rank)
+    prompts = [rng.integers(0, shape["vocab"], size=S, dtype=np.int32) for _ in range(4)]
+    steps = min(args.steps, 32)
+
+    def barrier():
+        dev.synchronize()
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    for i in range(args.warmup):
+        m.prefill(prompts[i % 4], 0, 0)
+    barrier()
+    st = torch.cuda.ExternalStream(dev.stream())
+    l0 = dev.launches()
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for i in range(steps):
+            m.prefill(prompts[i % 4], 0, 0)
+        e1.record(st)
+        dev.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = dev.launches() - l0
+        barrier()
+        # end to end: host ids in, logits of the last position back on the host, every step
+        t0 = time.perf_counter()
+        for i in range(steps):
+            m.prefill(prompts[i % 4], 0, 0)
+            lg = m.logits(0)
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+    if dist is not None:
+        t = torch.tensor([ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    lin, att, head = prefill_flops(shape, S)
+    peak, peak_src = tensor_peak()
+    tf = (lin + att + head) / (ms / steps * 1e-3) / 1e12
+    roof = {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None, "peak_source": peak_src,
+            "kernel": "whole prompt step (gemm_tc_kernel = tcgen05 GEMMs carry %.1f%% of the flops; causal attention on mma.sync)" % (100 * lin / (lin + att + head)),
+            "algorithmic_flops_per_step": lin + att + head}
+    if not args.per_op:
+        # the dominant kernel alone: the four GEMM shapes of a block, CUDA events on the engine stream (mc_gemm_bf16)
+        D, F = shape["dim"], shape["ffn_dim"]
+        QKV = (shape["n_heads"] + 2 * shape["n_kv_heads"]) * shape["head_dim"]
+        QO = shape["n_heads"] * shape["head_dim"]
+        per = []
+        tot_f = tot_t = 0.0
+        for name, N, K, mode in [("wqkv", QKV, D, 0), ("wo", D, QO, 2), ("w13", 2 * F, D, 3), ("w2", D, F, 2)]:
+            x, w = dev.alloc(S * K * 2), dev.alloc(N * K * 2)
+            ncols = N // 2 if mode == 3 else N
+            y, r = dev.alloc(S * ncols * 2), dev.alloc(S * N * 2) if mode == 2 else None
+            for b, n in ((x, S * K * 2), (w, N * K * 2)) + (((r, S * N * 2),) if r is not None else ()):
+                capi.check(capi.lib().mc_memset(dev.h, b.h, 0, 0x3c, n))
+            capi.gemm_bf16(dev, y, x, w, S, N, K, mode=mode, res=r, iters=3)
+            g_ms = capi.gemm_bf16(dev, y, x, w, S, N, K, mode=mode, res=r, iters=20) / 20
+            fl = 2.0 * S * N * K
+            per.append({"kernel": f"gemm_tc_kernel {name} [{S}x{N}x{K}]", "us": g_ms * 1e3, "TFLOPs": fl / (g_ms * 1e-3) / 1e12, "frac": fl / (g_ms * 1e-3) / 1e12 / peak})
+            tot_f += fl
+            tot_t += g_ms * 1e-3
+            for b in (x, w, y, r):
+                if b is not None:
+                    b.release()
+        roof["gemm_tc_kernel"] = {"achieved": tot_f / tot_t / 1e12, "frac": tot_f / tot_t / 1e12 / peak, "per_shape": per,
+                                  "note": "the four GEMMs of one block timed alone (20 back-to-back launches each, operands L2-resident between launches)"}
+    tokens = steps * S * world
+    line = {
+        "metric": "prefill_tokens_per_s", "value": tokens / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic ids, random-init weights (counter-hash seed 0x5EED)",
+        "config": {"workload": workload, "prompt": S, "parallelism": f"{world} replica(s)",
+                   "path": "4-row GEMV prompt path" if args.per_op else "tcgen05 GEMM prompt path",
+                   "l2": "weights of one pass (%.0f MB) > 126 MB L2; four distinct prompts cycled" % (m.weight_bytes()[0] / 1e6)},
+        "e2e": {"value": tokens / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 4 * S, "d2h_bytes_per_step": 2 * shape["vocab"],
+                "ms_per_step": e2e_ms / steps},
+        "gpu_launches": int(launches), "launches_per_step": launches // steps, "clocks": clocks.summary(), "roofline": roof,
+    }
+    if not args.no_cpu_baseline:
+        from oracle import orc
+
+        n = 32
+        o = orc.Llama(orc.make_cfg(**shape, max_seq_len=128), orc.BF16)
+        o.init_random(0x5EED)
+        t0 = time.perf_counter()
+        o.forward(prompts[0][:n].tolist(), 0)
+        sec = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": n / sec, "unit": "tokens/s", "cores": orc.num_threads(), "kind": "port",
+                                "sample": f"one {n}-position prompt through the full model (scalar C++ oracle port, OpenMP over output rows)"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -199,8 +355,13 @@ def main():
     ap.add_argument("--no-roofline", action="store_true", help="skip the isolated per-shape GEMV timing of the per-op path")
     ap.add_argument("--roofline-gemv", action="store_true", help="add the isolated per-shape timing of the per-op GEMV kernel")
     ap.add_argument("--per-op", action="store_true", help="per-op kernels under a CUDA graph instead of the streaming persistent kernel")
+    ap.add_argument("--prompt", type=int, default=2048, help="prompt length of the *-prefill workloads")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
+    if args.workload.endswith("-prefill"):
+        shape_name = args.workload.split("-")[0]
+        run_prefill(args, shape_name, SHAPES[shape_name])
+        return
     shape_name, fmt = args.workload.split("-")
     shape = SHAPES[shape_name]
     quant = 0 if fmt == "bf16" else 1

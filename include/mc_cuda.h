@@ -133,7 +133,8 @@ enum {
     MC_LLAMA_NO_GRAPH = 1u << 1,  /* launch kernels directly instead of replaying a CUDA graph  */
     MC_LLAMA_NO_PDL = 1u << 2,    /* no programmatic dependent launch between decode kernels    */
     MC_LLAMA_MEGAKERNEL = 1u << 3, /* experimental: the whole decode step as ONE persistent kernel with grid barriers */
-    MC_LLAMA_NO_STREAM = 1u << 4   /* do not use the streaming persistent kernel (TMA weight ring): per-op kernels under a CUDA graph */
+    MC_LLAMA_NO_STREAM = 1u << 4,  /* do not use the streaming persistent kernel (TMA weight ring): per-op kernels under a CUDA graph */
+    MC_LLAMA_NO_TC_PREFILL = 1u << 5 /* prompts go through the 4-row GEMV kernels instead of the tcgen05 GEMM path */
 };
 typedef struct mc_sampler_config {
     uint32_t mode;       /* 0 greedy argmax (lowest index on ties); 1 top-k -> nucleus -> multinomial (nn/sampling.h:306-316) */
@@ -192,8 +193,15 @@ MC_API mc_status mc_sample_default(mc_device* dev, mc_buffer* logits_bf16, uint3
 
 /* ---- stand-alone hot kernels (for roofline measurement and parity tests) -----------
  * y[M,N] = x[M,K] * W[N,K]^T with fp32 accumulation and one RNE rounding to bf16
- * (kernel/bmm.metal:24-82 through nn/linear.h:70-81).  M <= 8 takes the streaming GEMV path. */
+ * (kernel/bmm.metal:24-82 through nn/linear.h:70-81).  M <= 4 takes the streaming GEMV path, larger M mc_gemm_bf16. */
 MC_API mc_status mc_linear_bf16(mc_device* dev, mc_buffer* y, mc_buffer* x, mc_buffer* w, uint32_t M, uint32_t N, uint32_t K);
+/* The prefill linear on the tcgen05 tensor cores (TMA-fed, fp32 accumulators in tensor memory), any M:
+ *   mode 0: y[M,N]   = r(x . W^T)                               (nn/linear.h:70-81, kernel/bmm.metal:24-82)
+ *   mode 2: y[M,N]   = r(res + r(x . W^T))                      (nn/transformer.h:133,139 residual add fused)
+ *   mode 3: y[M,N/2] = r(silu_T(g) * u), (g,u) = columns (2i, 2i+1) of r(x . W^T), W = w1|w3 row-interleaved (nn/transformer.h:57-59)
+ * K % 64 == 0, N % 32 == 0.  Runs `iters` times; elapsed_ms (may be NULL) receives the CUDA-event time of all of them. */
+MC_API mc_status mc_gemm_bf16(mc_device* dev, mc_buffer* y, mc_buffer* x, mc_buffer* w, mc_buffer* res, uint32_t M, uint32_t N, uint32_t K, int mode,
+                              uint32_t iters, float* elapsed_ms);
 /* QLoRA base linear over packed int4 (quantization/lora.h:94-122 + kernel/mul.metal:59-85 fused, without the adaptor):
  * y[M,N] = r( x[M,K] . r(r(q) * r(s))^T ), M <= 8.  w4 / scales_packed come from mc_pack_w4. */
 MC_API mc_status mc_linear_w4(mc_device* dev, mc_buffer* y, mc_buffer* x, mc_buffer* w4, mc_buffer* scales_packed, uint32_t M, uint32_t N, uint32_t K);

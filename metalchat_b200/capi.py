@@ -16,7 +16,7 @@ LIB_PATH = HERE / "libmc_cuda.so"
 
 MC_OK, MC_ERR_INVALID, MC_ERR_RUNTIME, MC_ERR_ALLOC, MC_ERR_NOT_FOUND, MC_ERR_FULL = range(6)
 MEM_DEVICE, MEM_SHARED, MEM_PINNED = 0, 1, 2
-LLAMA_W4_PACKED, LLAMA_NO_GRAPH, LLAMA_NO_PDL, LLAMA_MEGAKERNEL, LLAMA_NO_STREAM = 1, 2, 4, 8, 16
+LLAMA_W4_PACKED, LLAMA_NO_GRAPH, LLAMA_NO_PDL, LLAMA_MEGAKERNEL, LLAMA_NO_STREAM, LLAMA_NO_TC_PREFILL = 1, 2, 4, 8, 16, 32
 
 
 class McError(RuntimeError):
@@ -124,6 +124,8 @@ _SIGNATURES = {
     "mc_sample_default": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(SamplerConfig), C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "mc_linear_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "mc_gemm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32,
+                               C.POINTER(C.c_float)]),
     "mc_linear_w4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "mc_pack_w4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
     "mc_w4_sizes": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
@@ -428,6 +430,16 @@ class Llama:
 
 def linear_bf16(dev: Device, y: Buffer, x: Buffer, w: Buffer, M: int, N: int, K: int):
     check(lib().mc_linear_bf16(dev.h, y.h, x.h, w.h, M, N, K))
+
+
+GEMM_STORE, GEMM_RESIDUAL, GEMM_SWIGLU = 0, 2, 3
+
+
+def gemm_bf16(dev: Device, y: Buffer, x: Buffer, w: Buffer, M: int, N: int, K: int, mode: int = GEMM_STORE, res: Buffer | None = None, iters: int = 1) -> float:
+    """The tcgen05 prefill GEMM (mc_gemm_bf16): returns the CUDA-event time of `iters` launches in ms."""
+    ms = C.c_float()
+    check(lib().mc_gemm_bf16(dev.h, y.h, x.h, w.h, res.h if res is not None else None, M, N, K, mode, iters, C.byref(ms)))
+    return ms.value
 
 
 def w4_sizes(N: int, K: int):

@@ -17,6 +17,7 @@
 #include "mc_quant_kernels.cuh"
 #include "mc_sample_kernels.cuh"
 #include "mc_stream_kernel.cuh"
+#include "mc_prefill.h"
 
 #include <cmath>
 #include <map>
@@ -111,6 +112,9 @@ struct mc_llama {
     uint32_t max_rows = 0;
     dbuf x, h, q, attn, z, logits, logits_tmp, hidden_save;
     dbuf io_in, io_out;        // contiguous decode inputs / outputs (views below)
+    // tensor-core prefill (mc_prefill.cu): activations of one prompt chunk, allocated on first use
+    dbuf pf_ids, pf_x, pf_h, pf_n, pf_qkv, pf_q, pf_attn, pf_z;
+    uint32_t pf_rows = 0;
     dbuf ids, pos, row_seq, uniforms, out_log, step_counter, pval, pidx, lora_ax, pack_bad, cand;
     int32_t* pinned = nullptr; // host staging: ids | pos | out
     float scale_bf16 = 0.0f;
@@ -130,7 +134,7 @@ struct mc_llama {
         for (int k = 0; k < kTpMaxWorld; k++)
             if (tp_peer_base[k] && uint32_t(k) != cfg.tp_rank) cudaIpcCloseMemHandle(tp_peer_base[k]);
         for (dbuf* b : {&st_ll, &st_timing, &layer_arena, &bar, &errflag, &mega_timing, &tp_region, &tp_local, &norm, &fcos, &fsin, &kcache, &vcache, &x, &h, &q, &attn, &z, &logits, &logits_tmp, &hidden_save, &io_in, &io_out, &ids, &pos, &row_seq,
-                        &uniforms, &out_log, &step_counter, &pval, &pidx, &lora_ax, &pack_bad, &cand})
+                        &uniforms, &out_log, &step_counter, &pval, &pidx, &lora_ax, &pack_bad, &cand, &pf_ids, &pf_x, &pf_h, &pf_n, &pf_qkv, &pf_q, &pf_attn, &pf_z})
             b->release();
     }
 };
@@ -1357,6 +1361,84 @@ mc_status mc_llama_weight_bytes(mc_llama* m, uint64_t* streamed_per_step, uint64
     MC_API_END
 }
 
+namespace {
+
+// ---- tensor-core prefill (mc_prefill.cu) ---------------------------------------------------------------------------------
+// Prompts of bf16 models on one GPU take the tcgen05 GEMM path: a chunk of up to kPfChunk positions goes through every
+// block as ONE [rows, K] x [N, K]^T product per linear (weights read once per chunk, not once per 4 rows).
+constexpr uint32_t kPfChunk = 2048;
+uint32_t prefill_tc_min_rows()
+{
+    static const uint32_t v = [] {
+        const char* e = getenv("MC_TC_PREFILL_MIN");
+        return e ? uint32_t(atoi(e)) : 8u;
+    }();
+    return v;
+}
+bool prefill_tc_eligible(const mc_llama* m, uint32_t len)
+{
+    const mc_llama_config& c = m->cfg;
+    static const bool env_off = getenv("MC_NO_TC_PREFILL") != nullptr;
+    if (env_off || (c.flags & MC_LLAMA_NO_TC_PREFILL) || c.quant || c.tp_world != 1 || m->tok.fmt != WF_BF16 || len < prefill_tc_min_rows()) return false;
+    if (c.head_dim != 64 && c.head_dim != 128) return false;
+    const uint32_t D = c.dim, QO = m->Hl * c.head_dim, QKV = (m->Hl + 2 * m->KVl) * c.head_dim, F = m->Fl;
+    return tc::gemm_supported(QKV, D, D, QKV) && tc::gemm_supported(D, QO, QO, D) && tc::gemm_supported(2 * F, D, D, F) && tc::gemm_supported(D, F, F, D);
+}
+void prefill_tc(mc_llama* m, uint32_t seq, const int32_t* ids, uint32_t len, uint32_t start_pos)
+{
+    const mc_llama_config& c = m->cfg;
+    const uint32_t D = c.dim, hd = c.head_dim, H = m->Hl, KV = m->KVl, QO = H * hd, QKV = (H + 2 * KV) * hd, F = m->Fl;
+    cudaStream_t s = m->dev->stream;
+    const int sms = m->dev->prop.multiProcessorCount;
+    const uint32_t cap = std::min<uint32_t>(kPfChunk, c.max_seq_len);
+    if (m->pf_rows < cap) {
+        m->pf_ids.alloc(size_t(cap) * 4);
+        m->pf_x.alloc(size_t(cap) * D * 2), m->pf_h.alloc(size_t(cap) * D * 2), m->pf_n.alloc(size_t(cap) * D * 2);
+        m->pf_qkv.alloc(size_t(cap) * QKV * 2), m->pf_q.alloc(size_t(cap) * QO * 2), m->pf_attn.alloc(size_t(cap) * QO * 2);
+        m->pf_z.alloc(size_t(cap) * F * 2);
+        m->pf_rows = cap;
+    }
+    uint16_t *x = m->pf_x.as<uint16_t>(), *h = m->pf_h.as<uint16_t>(), *n = m->pf_n.as<uint16_t>(), *qkv = m->pf_qkv.as<uint16_t>();
+    uint16_t *q = m->pf_q.as<uint16_t>(), *attn = m->pf_attn.as<uint16_t>(), *z = m->pf_z.as<uint16_t>();
+    int* err = m->errflag.as<int>();
+    uint32_t launches = 0;
+    launcher L{m, s, false};
+    for (uint32_t t0 = 0; t0 < len; t0 += cap) {
+        const uint32_t rows = std::min(cap, len - t0), pos0 = start_pos + t0;
+        MC_CUDA_CHECK(cudaMemcpyAsync(m->pf_ids.p, ids + t0, size_t(rows) * 4, cudaMemcpyHostToDevice, s));
+        launches += tc::embed_rows(s, x, m->tok.w.as<uint16_t>(), m->pf_ids.as<int32_t>(), rows, D);
+        for (uint32_t li = 0; li < c.n_layers; li++) {
+            dlayer& ly = m->layers[li];
+            uint16_t* kc = m->kcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
+            uint16_t* vc = m->vcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
+            launches += tc::rmsnorm_rows(s, n, x, ly.attn_norm.as<uint16_t>(), rows, D, c.norm_eps);
+            launches += tc::gemm(s, sms, tc::GEMM_STORE, n, D, ly.wqkv.w.as<uint16_t>(), qkv, nullptr, rows, QKV, D, QKV, err);
+            launches += tc::rope_append(s, qkv, q, kc, vc, m->fcos.as<float>(), m->fsin.as<float>(), rows, seq, pos0, H, KV, hd, c.max_seq_len);
+            launches += tc::prefill_attn(s, q, kc, vc, attn, rows, seq, pos0, H, KV, hd, c.max_seq_len, m->scale_bf16);
+            launches += tc::gemm(s, sms, tc::GEMM_RESIDUAL, attn, QO, ly.wo.w.as<uint16_t>(), h, x, rows, D, QO, D, err);
+            launches += tc::rmsnorm_rows(s, n, h, ly.ffn_norm.as<uint16_t>(), rows, D, c.norm_eps);
+            launches += tc::gemm(s, sms, tc::GEMM_SWIGLU, n, D, ly.w13.w.as<uint16_t>(), z, nullptr, rows, 2 * F, D, F, err);
+            launches += tc::gemm(s, sms, tc::GEMM_RESIDUAL, z, F, ly.w2.w.as<uint16_t>(), x, h, rows, D, F, D, err);
+        }
+        if (t0 + rows >= len) {
+            // only the last position is projected (nn/llama.h:128-133)
+            const uint16_t* last = x + size_t(rows - 1) * D;
+            gemv_launch<PRO_RMSNORM, EPI_NONE>(L, head_params(m, last, 1, m->logits.as<uint16_t>() + size_t(seq) * m->Vl));
+            MC_CUDA_CHECK(cudaMemcpyAsync(m->hidden_save.as<uint16_t>() + size_t(seq) * D, last, size_t(D) * 2, cudaMemcpyDeviceToDevice, s));
+        }
+        MC_CUDA_CHECK(cudaStreamSynchronize(s)); // pf_ids is reused by the next chunk; `ids` may be pageable
+    }
+    m->dev->launches.fetch_add(launches);
+    int flag = 0;
+    MC_CUDA_CHECK(cudaMemcpy(&flag, err, 4, cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaMemset(err, 0, 4);
+        throw error(MC_ERR_RUNTIME, "prefill: a bounded wait of the tensor-core GEMM timed out (code " + std::to_string(flag) + ")");
+    }
+}
+
+} // namespace
+
 mc_status mc_llama_prefill(mc_llama* m, uint32_t seq, const int32_t* ids, uint32_t len, uint32_t start_pos)
 {
     MC_API_BEGIN
@@ -1367,6 +1449,10 @@ mc_status mc_llama_prefill(mc_llama* m, uint32_t seq, const int32_t* ids, uint32
     // the sink-cache roll (nn/cache.h:183-204) is not modelled: positions must fit the cache
     MC_REQUIRE(uint64_t(start_pos) + len <= m->cfg.max_seq_len, "prefill: start_pos + len exceeds max_seq_len");
     for (uint32_t i = 0; i < len; i++) MC_REQUIRE(ids[i] >= 0 && uint32_t(ids[i]) < m->cfg.vocab, "prefill: token id out of range");
+    if (prefill_tc_eligible(m, len)) {
+        prefill_tc(m, seq, ids, len, start_pos);
+        return MC_OK;
+    }
     cudaStream_t s = m->dev->stream;
     launcher L{m, s, false};
     for (uint32_t t0 = 0; t0 < len; t0 += kMaxMB) {
@@ -1707,14 +1793,52 @@ mc_status mc_sample_default(mc_device* dev, mc_buffer* logits_bf16, uint32_t row
 }
 
 // ---- stand-alone linear (roofline measurement, parity tests) ------------------------------------------------------------
+mc_status mc_gemm_bf16(mc_device* dev, mc_buffer* y, mc_buffer* x, mc_buffer* w, mc_buffer* res, uint32_t M, uint32_t N, uint32_t K, int mode, uint32_t iters,
+                       float* elapsed_ms)
+{
+    MC_API_BEGIN
+    MC_REQUIRE(dev && y && x && w, "bad arguments");
+    MC_CUDA_CHECK(cudaSetDevice(dev->ordinal));
+    MC_REQUIRE(mode == tc::GEMM_STORE || mode == tc::GEMM_RESIDUAL || mode == tc::GEMM_SWIGLU, "gemm_bf16: mode must be 0 (store), 2 (residual) or 3 (swiglu)");
+    MC_REQUIRE(M >= 1 && iters >= 1 && tc::gemm_supported(N, K, K, N), "gemm_bf16: K must be a multiple of 64 and N a multiple of 32");
+    const uint32_t ncols = mode == tc::GEMM_SWIGLU ? N / 2 : N;
+    MC_REQUIRE(w->size >= size_t(N) * K * 2 && x->size >= size_t(M) * K * 2 && y->size >= size_t(M) * ncols * 2, "gemm_bf16: buffer too small");
+    MC_REQUIRE(mode != tc::GEMM_RESIDUAL || (res && res->size >= size_t(M) * N * 2), "gemm_bf16: residual buffer missing or too small");
+    dbuf err;
+    err.alloc(4);
+    cudaStream_t s = dev->stream;
+    MC_CUDA_CHECK(cudaMemsetAsync(err.p, 0, 4, s));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    MC_CUDA_CHECK(cudaEventCreate(&e0));
+    MC_CUDA_CHECK(cudaEventCreate(&e1));
+    MC_CUDA_CHECK(cudaEventRecord(e0, s));
+    for (uint32_t i = 0; i < iters; i++)
+        tc::gemm(s, dev->prop.multiProcessorCount, mode, static_cast<const uint16_t*>(x->dptr), K, static_cast<const uint16_t*>(w->dptr), static_cast<uint16_t*>(y->dptr),
+                 res ? static_cast<const uint16_t*>(res->dptr) : nullptr, M, N, K, ncols, err.as<int>());
+    MC_CUDA_CHECK(cudaEventRecord(e1, s));
+    int flag = 0;
+    cudaError_t ce = cudaMemcpyAsync(&flag, err.p, 4, cudaMemcpyDeviceToHost, s);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    float ms = 0.0f;
+    if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    err.release();
+    MC_CUDA_CHECK(ce);
+    dev->launches.fetch_add(iters);
+    if (flag) throw error(MC_ERR_RUNTIME, "gemm_bf16: a bounded wait of the tensor-core GEMM timed out (code " + std::to_string(flag) + ")");
+    if (elapsed_ms) *elapsed_ms = ms;
+    MC_API_END
+}
+
 mc_status mc_linear_bf16(mc_device* dev, mc_buffer* y, mc_buffer* x, mc_buffer* w, uint32_t M, uint32_t N, uint32_t K)
 {
     MC_API_BEGIN
     MC_REQUIRE(dev && y && x && w, "bad arguments");
     MC_CUDA_CHECK(cudaSetDevice(dev->ordinal));
-    MC_REQUIRE(M >= 1 && M <= uint32_t(kMaxMB), "linear_bf16: M must be in [1,4] for the streaming GEMV path");
-    MC_REQUIRE(N % 2 == 0 && K % 256 == 0, "linear_bf16: N must be even and K a multiple of 256");
     MC_REQUIRE(w->size >= size_t(N) * K * 2 && x->size >= size_t(M) * K * 2 && y->size >= size_t(M) * N * 2, "linear_bf16: buffer too small");
+    if (M > uint32_t(kMaxMB)) return mc_gemm_bf16(dev, y, x, w, nullptr, M, N, K, 0, 1, nullptr); // many rows: the tensor-core GEMM
+    MC_REQUIRE(M >= 1, "linear_bf16: M must be positive");
+    MC_REQUIRE(N % 2 == 0 && K % 256 == 0, "linear_bf16: N must be even and K a multiple of 256");
     mc_llama shim;
     shim.dev = dev;
     launcher L{&shim, dev->stream, false};

@@ -1,0 +1,500 @@
+// metalchat_b200/csrc/mc_gemm_tc.cuh — prefill on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Y[M, N] = epilogue( X[M, K] . W[N, K]^T )   bf16 x bf16 -> fp32 accumulators in tensor memory -> ONE bf16 rounding,
+// i.e. the rounding point of kernel/bmm.metal:76 (the fp32 sum is re-associated by the tensor core: stated tolerance).
+//
+// Persistent, warp-specialised kernel, one CTA per SM, 192 threads:
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d (SASS UTMALDG) moves a 128 x 64 tile of X and a BN x 64 tile of W
+//               (both K-major, 128-byte swizzle) into a ring of stages guarded by full/empty mbarriers;
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN, K=16), four per stage;
+//               tcgen05.commit frees the stage and, after the last k block, publishes the accumulator;
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns) -> r(.) -> fused tail (store | residual add | SiLU*mul on
+//               the row-interleaved w1|w3) -> global.  The accumulator is double-buffered in TMEM (2 x BN columns), so the
+//               epilogue of tile i overlaps the MMAs of tile i+1.
+// Tiles are dealt m-fastest: the CTAs running at the same time share a handful of W tiles, so every weight byte comes from
+// HBM once per prefill chunk and the activations (a few MB) stay in L2.
+// The row-wise kernels around the GEMMs (RMSNorm, RoPE + KV append) and the causal prefill attention (mma.sync, the
+// reference's rounding points: nn/attention.h:195-200) are at the end of the file.
+#pragma once
+#include <cuda.h>
+#include "mc_common.cuh"
+
+namespace mc {
+namespace tc {
+
+// epilogues of the prefill GEMM (same meaning as the EPI_* of the decode GEMV kernels)
+enum { EPI_NONE = 0, EPI_RESIDUAL = 2, EPI_SWIGLU = 3 };
+
+// ---- helpers (this translation unit is independent of the decode kernels) -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t a, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    return ok;
+}
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ float rbf(float f) { return bf16_bits_to_f32(f32_to_bf16_bits(f)); } // r(.)
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) { return uint32_t(f32_to_bf16_bits(lo)) | (uint32_t(f32_to_bf16_bits(hi)) << 16); }
+// silu evaluated in bf16 steps: x / (T(1) + T(exp(-x)))  (kernel/activation.metal:34-35, quirk Q5)
+__device__ __forceinline__ float silu_bf16(float g)
+{
+    const float e = rbf(expf(-g));
+    const float d = rbf(__fadd_rn(1.0f, e));
+    return rbf(__fdiv_rn(g, d));
+}
+// block-wide sum of 256 threads with a fixed partition (warp butterfly, then the 8 warp totals in order)
+__device__ __forceinline__ float block_sum_256(float v, float* scratch /* [8] */)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += scratch[i];
+    __syncthreads();
+    return t;
+}
+
+constexpr int kTcBM = 128;      // prompt rows per tile (the M of the MMA = the 128 TMEM lanes)
+constexpr int kTcBK = 64;       // k per stage: 128 bytes per row = one swizzle atom, four MMAs of K = 16
+constexpr int kTcThreads = 192; // producer warp | MMA warp | 4 epilogue warps
+constexpr int kTcHdr = 1024;    // barriers + TMEM base slot
+
+__host__ __device__ constexpr int tc_stages(int BN) { return BN >= 256 ? 4 : 6; }
+__host__ __device__ constexpr int tc_stage_bytes(int BN) { return (kTcBM + BN) * kTcBK * 2; }
+__host__ __device__ constexpr int tc_smem_bytes(int BN) { return kTcHdr + tc_stages(BN) * tc_stage_bytes(BN) + 1024; }
+
+struct gemm_tc_params {
+    uint16_t* Y;         // EPI_NONE / EPI_RESIDUAL: [M, ldy]; EPI_SWIGLU: [M, ldy] holding N/2 columns
+    const uint16_t* res; // EPI_RESIDUAL: [M, ldy]
+    uint32_t M, N, K, ldy;
+    int* err;            // set when a bounded wait times out (never hang the device)
+};
+
+// shared-memory matrix descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 bytes apart (UMMA descriptor v1)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr >> 4) & 0x3fffu);  // start address
+    d |= uint64_t(1) << 16;                     // leading byte offset: unused for swizzled K-major operands
+    d |= uint64_t(1024 >> 4) << 32;             // stride byte offset between 8-row core-matrix groups
+    d |= uint64_t(1) << 46;                     // descriptor version (Blackwell)
+    d |= uint64_t(2) << 61;                     // layout: SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D = fp32, A = B = bf16, both K-major, M x N
+__host__ __device__ constexpr uint32_t tc_idesc(uint32_t M, uint32_t N)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b),
+                 "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t mbar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tc_tma_load(uint32_t dst, const CUtensorMap* map, uint32_t c0, uint32_t c1, uint32_t mbar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(mbar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// bounded mbarrier wait: a lost arrival raises the error flag and lets every later wait fall through
+__device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity, volatile int* dead, int* err)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 1023u) == 0) {
+            if (*dead) return;
+            if (spins > (1u << 22)) {
+                *dead = 1;
+                atomicExch(err, 5);
+                return;
+            }
+        }
+    }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const gemm_tc_params p)
+{
+    constexpr int STAGES = tc_stages(BN);
+    constexpr uint32_t A_BYTES = kTcBM * kTcBK * 2, B_BYTES = BN * kTcBK * 2;
+    extern __shared__ unsigned char smem_raw[];
+    // 128-byte swizzle: tiles on 1024-byte boundaries
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t base = smem_u32(smem);
+    const uint32_t bar_full = base, bar_empty = base + 64, bar_tfull = base + 128, bar_tempty = base + 144, tmem_slot = base + 160;
+    volatile int* dead = reinterpret_cast<volatile int*>(smem + 176);
+    const uint32_t a0 = base + kTcHdr, b0 = a0 + STAGES * A_BYTES;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) mbar_init(bar_full + s * 8, 1), mbar_init(bar_empty + s * 8, 1);
+        for (int s = 0; s < 2; s++) mbar_init(bar_tfull + s * 8, 1), mbar_init(bar_tempty + s * 8, 4);
+        *dead = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+    }
+    if (warp == 1) {
+        // two accumulator buffers of BN fp32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(uint32_t(2 * BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + 160);
+
+    const uint32_t m_blocks = (p.M + kTcBM - 1) / kTcBM, n_blocks = (p.N + BN - 1) / BN;
+    const uint32_t n_tiles = m_blocks * n_blocks, k_blocks = p.K / kTcBK;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const uint32_t mb = tile % m_blocks, nb = tile / m_blocks;
+                for (uint32_t kb = 0; kb < k_blocks; kb++, it++) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                    tc_wait(bar_empty + s * 8, ph ^ 1u, dead, p.err);
+                    mbar_expect_tx(bar_full + s * 8, A_BYTES + B_BYTES);
+                    tc_tma_load(a0 + s * A_BYTES, &tmX, kb * kTcBK, mb * kTcBM, bar_full + s * 8);
+                    tc_tma_load(b0 + s * B_BYTES, &tmW, kb * kTcBK, nb * BN, bar_full + s * 8);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc_idesc(kTcBM, BN);
+            uint32_t it = 0, lt = 0;
+            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, lt++) {
+                const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
+                tc_wait(bar_tempty + as * 8, aph ^ 1u, dead, p.err); // the epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem + as * BN;
+                for (uint32_t kb = 0; kb < k_blocks; kb++, it++) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                    tc_wait(bar_full + s * 8, ph, dead, p.err);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t da = tc_smem_desc(a0 + s * A_BYTES), db = tc_smem_desc(b0 + s * B_BYTES);
+#pragma unroll
+                    for (uint32_t k = 0; k < kTcBK / 16; k++) // 16 elements = 32 bytes along k inside the swizzle atom: +2 in the address field
+                        tc_mma(d_tmem, da + k * 2, db + k * 2, idesc, (kb | k) != 0);
+                    tc_commit(bar_empty + s * 8); // arrives when these MMAs have read the stage
+                }
+                tc_commit(bar_tfull + as * 8); // ... and when the accumulator is complete
+            }
+        }
+    } else {
+        const uint32_t quarter = warp & 3u; // a warp reaches TMEM lanes 32 (warp % 4) .. +31
+        uint32_t lt = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, lt++) {
+            const uint32_t mb = tile % m_blocks, nb = tile / m_blocks;
+            const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
+            tc_wait(bar_tfull + as * 8, aph, dead, p.err);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t row = mb * kTcBM + quarter * 32 + lane;
+            const uint32_t n0 = nb * BN;
+#pragma unroll 1
+            for (uint32_t cb = 0; cb < uint32_t(BN); cb += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem + ((quarter * 32) << 16) + as * BN + cb;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                      "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                      "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+                      "=r"(v[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < p.M && n0 + cb < p.N) {
+                    float y[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) y[j] = rbf(__uint_as_float(v[j])); // the bmm output buffer is T (kernel/bmm.metal:76)
+                    if (EPI == EPI_SWIGLU) {
+                        // z = r(silu_T(g) * u), columns (2i, 2i+1) = (w1 row i, w3 row i)  (nn/transformer.h:57-59)
+                        uint32_t o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) o[j] = pack2(__fmul_rn(silu_bf16(y[4 * j]), y[4 * j + 1]), __fmul_rn(silu_bf16(y[4 * j + 2]), y[4 * j + 3]));
+                        uint4* dst = reinterpret_cast<uint4*>(p.Y + size_t(row) * p.ldy + ((n0 + cb) >> 1));
+                        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                    } else {
+                        uint32_t o[16];
+                        if (EPI == EPI_RESIDUAL) {
+                            // h = r(x + a)  (nn/transformer.h:133,139)
+                            const uint4* rp = reinterpret_cast<const uint4*>(p.res + size_t(row) * p.ldy + n0 + cb);
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const uint4 r = rp[q];
+                                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                                for (int j = 0; j < 4; j++)
+                                    o[q * 4 + j] = pack2(__fadd_rn(bf_lo(rw[j]), y[(q * 4 + j) * 2]), __fadd_rn(bf_hi(rw[j]), y[(q * 4 + j) * 2 + 1]));
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; j++) o[j] = pack2(y[2 * j], y[2 * j + 1]);
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(p.Y + size_t(row) * p.ldy + n0 + cb);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) dst[q] = make_uint4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + as * 8);
+        }
+    }
+    __syncwarp();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(uint32_t(2 * BN)) : "memory");
+    }
+}
+
+// ---- the row-wise kernels around the prefill GEMMs --------------------------------------------------------------
+// gather the embedding rows of a prompt chunk (kernel/embedding.metal:25-70), bf16 table
+__global__ void __launch_bounds__(256) embed_rows_kernel(uint16_t* out, const uint16_t* table, const int32_t* ids, uint32_t D)
+{
+    const uint4* src = reinterpret_cast<const uint4*>(table + size_t(ids[blockIdx.x]) * D);
+    uint4* dst = reinterpret_cast<uint4*>(out + size_t(blockIdx.x) * D);
+    for (uint32_t k = threadIdx.x; k < D / 8; k += 256) dst[k] = src[k];
+}
+// n = r((0 + w) * x * rsqrt(mean(x^2) + eps))  (kernel/rmsnorm.metal:53-89), one CTA per row
+__global__ void __launch_bounds__(256) rmsnorm_rows_kernel(uint16_t* out, const uint16_t* x, const uint16_t* w, uint32_t D, float eps)
+{
+    __shared__ float scr[8];
+    const uint16_t* xr = x + size_t(blockIdx.x) * D;
+    float part = 0.0f;
+    for (uint32_t k = threadIdx.x * 8; k < D; k += 256 * 8) {
+        const uint4 v = *reinterpret_cast<const uint4*>(xr + k);
+        float f;
+        f = bf_lo(v.x), part = fmaf(f, f, part), f = bf_hi(v.x), part = fmaf(f, f, part);
+        f = bf_lo(v.y), part = fmaf(f, f, part), f = bf_hi(v.y), part = fmaf(f, f, part);
+        f = bf_lo(v.z), part = fmaf(f, f, part), f = bf_hi(v.z), part = fmaf(f, f, part);
+        f = bf_lo(v.w), part = fmaf(f, f, part), f = bf_hi(v.w), part = fmaf(f, f, part);
+    }
+    const float total = block_sum_256(part, scr);
+    const float inv = 1.0f / sqrtf(__fadd_rn(total / float(D), eps));
+    for (uint32_t k = threadIdx.x * 8; k < D; k += 256 * 8) {
+        const uint4 v = *reinterpret_cast<const uint4*>(xr + k);
+        const uint4 g = *reinterpret_cast<const uint4*>(w + k);
+        uint4 o;
+#define MC_NORM2(d, vv, gg)                                                                          \
+    d = uint32_t(f32_to_bf16_bits(__fmul_rn(__fmul_rn(bf_lo(gg), bf_lo(vv)), inv))) |                \
+        (uint32_t(f32_to_bf16_bits(__fmul_rn(__fmul_rn(bf_hi(gg), bf_hi(vv)), inv))) << 16)
+        MC_NORM2(o.x, v.x, g.x);
+        MC_NORM2(o.y, v.y, g.y);
+        MC_NORM2(o.z, v.z, g.z);
+        MC_NORM2(o.w, v.w, g.w);
+#undef MC_NORM2
+        *reinterpret_cast<uint4*>(out + size_t(blockIdx.x) * D + k) = o;
+    }
+}
+// rotate q and k (kernel/rope.metal:47-58), store q, append k', v to the cache (nn/cache.h:207-214); grid (H + 2 KV, rows)
+__global__ void rope_append_kernel(const uint16_t* qkv, uint32_t ld, uint16_t* q, uint16_t* kcache, uint16_t* vcache, const float* fcos, const float* fsin,
+                                   uint32_t seq, uint32_t start_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq)
+{
+    const uint32_t head = blockIdx.x, row = blockIdx.y, half = hd >> 1, j = threadIdx.x;
+    if (j >= half) return;
+    const uint32_t pos = start_pos + row;
+    const uint16_t* src = qkv + size_t(row) * ld + size_t(head) * hd;
+    const float a = bf16_bits_to_f32(src[j]), b = bf16_bits_to_f32(src[j + half]);
+    if (head < H + KV) {
+        const float cs = fcos[size_t(pos) * half + j], sn = fsin[size_t(pos) * half + j];
+        const uint16_t o0 = f32_to_bf16_bits(__fsub_rn(__fmul_rn(cs, a), __fmul_rn(sn, b)));
+        const uint16_t o1 = f32_to_bf16_bits(__fadd_rn(__fmul_rn(sn, a), __fmul_rn(cs, b)));
+        uint16_t* dst = head < H ? q + size_t(row) * H * hd + size_t(head) * hd : kcache + ((size_t(seq) * KV + (head - H)) * max_seq + size_t(pos)) * hd;
+        dst[j] = o0, dst[j + half] = o1;
+    } else {
+        uint16_t* dst = vcache + ((size_t(seq) * KV + (head - H - KV)) * max_seq + size_t(pos)) * hd;
+        dst[j] = src[j], dst[j + half] = src[j + half];
+    }
+}
+
+// ---- causal prefill attention -------------------------------------------------------------------------------------------
+// One CTA = 64 consecutive prompt rows of one head (4 warps x 16 rows), keys in tiles of 64 from the KV cache.
+// The reference's chain (nn/attention.h:195-200, kernel/softmax.metal:40-80) has no running maximum and rounds to bf16 after
+// each of bmm / scale / softmax / bmm, so the kernel makes two passes over the keys:
+//   pass 1   s = r(r(q.K) * scale) for every visible key, total = sum exp(s)               (fp32, fixed order per thread)
+//   pass 2   p = r(exp(s) * (1 / total)), o += p . V with p as the bf16 A operand of the second mma; o = r(o) at the end
+// Masked keys (t > pos) contribute exactly 0, as exp(r(s + -inf)) does in the reference.
+struct pattn_params {
+    const uint16_t* q;  // [rows, H*hd] rotated
+    const uint16_t* kc; // this layer, this sequence: [KV][max_seq][hd]
+    const uint16_t* vc;
+    uint16_t* out;      // [rows, H*hd]
+    uint32_t rows, start_pos, H, KV, max_seq;
+    float scale;        // r(1/sqrt(hd)) stored as T (quirk Q4)
+};
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void pa_cp16(uint32_t dst, const void* src, bool valid)
+{
+    const uint32_t n = valid ? 16u : 0u; // src-size 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+template <int HD> __global__ void __launch_bounds__(128) prefill_attn_kernel(const pattn_params p)
+{
+    constexpr int PITCH = HD + 8;             // bf16 elements per smem row: 16-byte aligned, conflict-free fragment loads
+    constexpr int TILE = 64 * PITCH * 2;      // bytes of one 64-key K (or V) tile
+    extern __shared__ __align__(16) unsigned char psm[]; // [2 buffers][K tile | V tile]
+    const uint32_t sbase = smem_u32(psm);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const uint32_t head = blockIdx.y, kvh = head / (p.H / p.KV);
+    const uint32_t q0 = blockIdx.x * 64;
+    const uint32_t r_lo = q0 + warp * 16 + g, r_hi = r_lo + 8; // the two prompt rows of this thread
+    const uint32_t rows_end = min(q0 + 64u, p.rows);
+    const uint32_t n_keys = p.start_pos + rows_end; // keys visible to the last row of the CTA
+    const uint32_t n_tiles = (n_keys + 63) / 64;
+    const uint16_t* kbase = p.kc + size_t(kvh) * p.max_seq * HD;
+    const uint16_t* vbase = p.vc + size_t(kvh) * p.max_seq * HD;
+
+    // Q fragments (A operand, row-major 16 x HD)
+    uint32_t qa[HD / 16][4];
+    {
+        const uint16_t* ql = p.q + size_t(min(r_lo, p.rows - 1)) * p.H * HD + size_t(head) * HD;
+        const uint16_t* qh = p.q + size_t(min(r_hi, p.rows - 1)) * p.H * HD + size_t(head) * HD;
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ks++) {
+            qa[ks][0] = *reinterpret_cast<const uint32_t*>(ql + ks * 16 + 2 * t);
+            qa[ks][1] = *reinterpret_cast<const uint32_t*>(qh + ks * 16 + 2 * t);
+            qa[ks][2] = *reinterpret_cast<const uint32_t*>(ql + ks * 16 + 8 + 2 * t);
+            qa[ks][3] = *reinterpret_cast<const uint32_t*>(qh + ks * 16 + 8 + 2 * t);
+        }
+    }
+    const uint32_t pos_lo = p.start_pos + r_lo, pos_hi = p.start_pos + r_hi; // last visible key of each row
+
+    // job j < n_tiles: pass 1 on key tile j (K only); job j >= n_tiles: pass 2 on key tile j - n_tiles (K and V)
+    auto issue = [&](uint32_t job) {
+        const bool second = job >= n_tiles;
+        const uint32_t kt = second ? job - n_tiles : job;
+        const uint32_t buf = sbase + (job & 1u) * 2 * TILE;
+        constexpr int CH = HD / 8; // 16-byte chunks per row
+        for (uint32_t c = tid; c < 64 * CH; c += 128) {
+            const uint32_t r = c / CH, cc = c % CH, key = kt * 64 + r;
+            const bool ok = key < n_keys;
+            const size_t off = size_t(ok ? key : 0) * HD + cc * 8;
+            pa_cp16(buf + (r * PITCH + cc * 8) * 2, kbase + off, ok);
+            if (second) pa_cp16(buf + TILE + (r * PITCH + cc * 8) * 2, vbase + off, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    float sum_lo = 0.0f, sum_hi = 0.0f, inv_lo = 0.0f, inv_hi = 0.0f;
+    float o[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; i++) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f;
+
+    const uint32_t n_jobs = 2 * n_tiles;
+    issue(0);
+    for (uint32_t job = 0; job < n_jobs; job++) {
+        if (job + 1 < n_jobs) {
+            issue(job + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const bool second = job >= n_tiles;
+        const uint32_t kt = second ? job - n_tiles : job;
+        const uint32_t kbuf = sbase + (job & 1u) * 2 * TILE, vbuf = kbuf + TILE;
+        if (job == n_tiles) {
+            // between the passes: the four lanes of a quad hold the partial sums of one row
+            sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1), sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
+            sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1), sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
+            inv_lo = 1.0f / sum_lo, inv_hi = 1.0f / sum_hi;
+        }
+        // this warp's rows see keys <= pos_hi: skip tiles entirely above the diagonal
+        if (kt * 64 <= p.start_pos + q0 + warp * 16 + 15) {
+            // S = Q . K^T for 64 keys: 8 n-tiles of 8 keys
+            float s[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) {
+                s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+#pragma unroll
+                for (int ks = 0; ks < HD / 16; ks++) {
+                    // B[k = d][n = key] = K[key][d]: lane (g, t) reads K[nt*8 + g][ks*16 + 2t ..] and [.. + 8 ..]
+                    const uint32_t addr = kbuf + ((nt * 8 + g) * PITCH + ks * 16 + 2 * t) * 2;
+                    uint32_t b0, b1;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(b0) : "r"(addr));
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(b1) : "r"(addr + 16));
+                    mma_bf16_16816(s[nt], qa[ks], b0, b1);
+                }
+            }
+            // s = r(r(q.K) * scale); masked keys drop out  (kernel/bmm.metal:76, kernel/arithmetic.metal scalar_mul)
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) {
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const uint32_t key = kt * 64 + nt * 8 + 2 * t + (e & 1);
+                    const uint32_t lim = (e & 2) ? pos_hi : pos_lo;
+                    const float sv = rbf(__fmul_rn(rbf(s[nt][e]), p.scale));
+                    const float ex = key <= lim ? expf(sv) : 0.0f;
+                    if (!second) {
+                        if (e & 2) sum_hi += ex;
+                        else sum_lo += ex;
+                    } else {
+                        s[nt][e] = rbf(__fmul_rn(ex, (e & 2) ? inv_hi : inv_lo)); // p = r(exp(s) * (1/total))  (kernel/softmax.metal:79)
+                    }
+                }
+            }
+            if (second) {
+                // O += P . V: k = 16 keys per step, P from the S registers (C layout of two n-tiles = A layout of one k step)
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+                    uint32_t pa[4];
+                    pa[0] = pack2(s[2 * kk][0], s[2 * kk][1]);
+                    pa[1] = pack2(s[2 * kk][2], s[2 * kk][3]);
+                    pa[2] = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+                    pa[3] = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+                    for (int dp = 0; dp < HD / 16; dp++) {
+                        // ldmatrix.x4.trans: matrices (keys 0-7 | 8-15) x (d 0-7 | 8-15) of the 16 x 16 block of V
+                        const uint32_t mi = lane >> 3, mr = lane & 7;
+                        const uint32_t addr = vbuf + ((kk * 16 + (mi & 1) * 8 + mr) * PITCH + dp * 16 + (mi >> 1) * 8) * 2;
+                        uint32_t v0, v1, v2, v3;
+                        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(addr));
+                        mma_bf16_16816(o[2 * dp], pa, v0, v1);
+                        mma_bf16_16816(o[2 * dp + 1], pa, v2, v3);
+                    }
+                }
+            }
+        }
+        __syncthreads(); // the buffer is refilled by the job after next
+    }
+    // o = r(sum p.V)  (kernel/bmm.metal:76); the reference's transposed copy back to [rows, H*hd] (nn/attention.h:90-102)
+#pragma unroll
+    for (int nt = 0; nt < HD / 8; nt++) {
+        if (r_lo < p.rows) *reinterpret_cast<uint32_t*>(p.out + size_t(r_lo) * p.H * HD + size_t(head) * HD + nt * 8 + 2 * t) = pack2(rbf(o[nt][0]), rbf(o[nt][1]));
+        if (r_hi < p.rows) *reinterpret_cast<uint32_t*>(p.out + size_t(r_hi) * p.H * HD + size_t(head) * HD + nt * 8 + 2 * t) = pack2(rbf(o[nt][2]), rbf(o[nt][3]));
+    }
+}
+
+} // namespace tc
+} // namespace mc

@@ -1,0 +1,162 @@
+// metalchat_b200/csrc/mc_prefill.cu — launchers of the tensor-core prefill kernels (mc_gemm_tc.cuh).
+//
+// Replaces, for prompts, the chain nn::linear -> kernel::bmm (nn/linear.h:70-81, kernel/bmm.h:27-89) and the attention of
+// nn/attention.h:161-206 when many positions are processed at once: tcgen05/TMEM GEMMs fed by TMA, a two-pass causal
+// attention on mma.sync, row-wise RMSNorm / RoPE / KV append around them.
+#include "mc_gemm_tc.cuh"
+#include "mc_prefill.h"
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace mc {
+namespace tc {
+
+namespace {
+
+using encode_fn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                               CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime (libcuda is not linked)
+encode_fn tensor_map_encoder()
+{
+    static encode_fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+            cudaGetLastError();
+            throw error(MC_ERR_RUNTIME, "cuda: cuTensorMapEncodeTiled is not available from this driver (the prefill GEMM needs TMA)");
+        }
+        return reinterpret_cast<encode_fn>(p);
+    }();
+    return fn;
+}
+
+// K-major bf16 matrix [rows, K] with row pitch ld elements; box = box_rows x 64 elements, 128-byte swizzle, zero fill
+CUtensorMap make_map(const uint16_t* base, uint32_t rows, uint32_t K, uint32_t ld, uint32_t box_rows)
+{
+    using key_t = std::tuple<const void*, uint32_t, uint32_t, uint32_t, uint32_t>;
+    static std::mutex mu;
+    static std::map<key_t, CUtensorMap> cache;
+    const key_t key{base, rows, K, ld, box_rows};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {K, rows};
+    const cuuint64_t strides[1] = {cuuint64_t(ld) * 2};
+    const cuuint32_t box[2] = {uint32_t(kTcBK), box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = tensor_map_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw error(MC_ERR_RUNTIME, "cuda: cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, m);
+    return m;
+}
+
+template <int BN, int EPI> void launch_gemm(cudaStream_t s, int sm_count, const CUtensorMap& mx, const CUtensorMap& mw, const gemm_tc_params& p)
+{
+    auto kernel = gemm_tc_kernel<BN, EPI>;
+    static bool configured[8] = {false};
+    int dev = 0;
+    MC_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!configured[dev & 7]) {
+        MC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(BN)));
+        configured[dev & 7] = true;
+    }
+    const uint32_t tiles = ((p.M + kTcBM - 1) / kTcBM) * ((p.N + BN - 1) / BN);
+    const uint32_t grid = tiles < uint32_t(sm_count) ? tiles : uint32_t(sm_count);
+    kernel<<<grid, kTcThreads, tc_smem_bytes(BN), s>>>(mx, mw, p);
+    MC_CUDA_CHECK(cudaGetLastError());
+}
+template <int BN> void launch_gemm_epi(cudaStream_t s, int sm_count, int mode, const CUtensorMap& mx, const CUtensorMap& mw, const gemm_tc_params& p)
+{
+    switch (mode) {
+    case GEMM_STORE: launch_gemm<BN, EPI_NONE>(s, sm_count, mx, mw, p); break;
+    case GEMM_RESIDUAL: launch_gemm<BN, EPI_RESIDUAL>(s, sm_count, mx, mw, p); break;
+    case GEMM_SWIGLU: launch_gemm<BN, EPI_SWIGLU>(s, sm_count, mx, mw, p); break;
+    default: throw error(MC_ERR_INVALID, "prefill gemm: unknown epilogue");
+    }
+}
+
+} // namespace
+
+bool gemm_supported(uint32_t N, uint32_t K, uint32_t ldx, uint32_t ldy)
+{
+    return K >= uint32_t(kTcBK) && K % kTcBK == 0 && N % 32 == 0 && ldx % 8 == 0 && ldy % 8 == 0;
+}
+
+int gemm(cudaStream_t stream, int sm_count, int mode, const uint16_t* X, uint32_t ldx, const uint16_t* W, uint16_t* Y, const uint16_t* res, uint32_t M, uint32_t N,
+         uint32_t K, uint32_t ldy, int* err)
+{
+    MC_REQUIRE(M >= 1 && gemm_supported(N, K, ldx, ldy), "prefill gemm: unsupported shape (K % 64, N % 32, pitches % 8)");
+    MC_REQUIRE((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(res)) % 16 == 0,
+               "prefill gemm: operands must be 16-byte aligned");
+    gemm_tc_params p{};
+    p.Y = Y, p.res = res, p.M = M, p.N = N, p.K = K, p.ldy = ldy, p.err = err;
+    const uint32_t m_blocks = (M + kTcBM - 1) / kTcBM;
+    // 256-wide tiles unless they would leave SMs idle
+    const bool wide = m_blocks * ((N + 255) / 256) >= uint32_t(sm_count);
+    const CUtensorMap mx = make_map(X, M, K, ldx, kTcBM);
+    if (wide) {
+        const CUtensorMap mw = make_map(W, N, K, K, 256);
+        launch_gemm_epi<256>(stream, sm_count, mode, mx, mw, p);
+    } else {
+        const CUtensorMap mw = make_map(W, N, K, K, 128);
+        launch_gemm_epi<128>(stream, sm_count, mode, mx, mw, p);
+    }
+    return 1;
+}
+
+int embed_rows(cudaStream_t stream, uint16_t* out, const uint16_t* table, const int32_t* ids, uint32_t rows, uint32_t D)
+{
+    MC_REQUIRE(D % 8 == 0, "prefill embedding: dim must be a multiple of 8");
+    embed_rows_kernel<<<rows, 256, 0, stream>>>(out, table, ids, D);
+    MC_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+int rmsnorm_rows(cudaStream_t stream, uint16_t* out, const uint16_t* x, const uint16_t* w, uint32_t rows, uint32_t D, float eps)
+{
+    MC_REQUIRE(D % 8 == 0, "prefill rmsnorm: dim must be a multiple of 8");
+    rmsnorm_rows_kernel<<<rows, 256, 0, stream>>>(out, x, w, D, eps);
+    MC_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+int rope_append(cudaStream_t stream, const uint16_t* qkv, uint16_t* q, uint16_t* kcache_layer, uint16_t* vcache_layer, const float* fcos, const float* fsin,
+                uint32_t rows, uint32_t seq, uint32_t start_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq)
+{
+    rope_append_kernel<<<dim3(H + 2 * KV, rows), hd / 2, 0, stream>>>(qkv, (H + 2 * KV) * hd, q, kcache_layer, vcache_layer, fcos, fsin, seq, start_pos, H, KV, hd, max_seq);
+    MC_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+int prefill_attn(cudaStream_t stream, const uint16_t* q, const uint16_t* kcache_layer, const uint16_t* vcache_layer, uint16_t* out, uint32_t rows, uint32_t seq,
+                 uint32_t start_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, float scale)
+{
+    MC_REQUIRE(hd == 64 || hd == 128, "prefill attention: head_dim must be 64 or 128");
+    pattn_params p{};
+    p.q = q, p.out = out, p.rows = rows, p.start_pos = start_pos, p.H = H, p.KV = KV, p.max_seq = max_seq, p.scale = scale;
+    p.kc = kcache_layer + size_t(seq) * KV * max_seq * hd;
+    p.vc = vcache_layer + size_t(seq) * KV * max_seq * hd;
+    const dim3 grid((rows + 63) / 64, H);
+    const size_t smem = size_t(4) * 64 * (hd + 8) * 2;
+    if (hd == 64) {
+        prefill_attn_kernel<64><<<grid, 128, smem, stream>>>(p);
+    } else {
+        static bool configured[8] = {false};
+        int dev = 0;
+        MC_CUDA_CHECK(cudaGetDevice(&dev));
+        if (!configured[dev & 7]) {
+            MC_CUDA_CHECK(cudaFuncSetAttribute(prefill_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            configured[dev & 7] = true;
+        }
+        prefill_attn_kernel<128><<<grid, 128, smem, stream>>>(p);
+    }
+    MC_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
+} // namespace tc
+} // namespace mc

@@ -1,0 +1,30 @@
+// metalchat_b200/csrc/mc_prefill.h — host interface of the tensor-core prefill kernels (mc_prefill.cu / mc_gemm_tc.cuh).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace mc {
+namespace tc {
+
+enum { GEMM_STORE = 0, GEMM_RESIDUAL = 2, GEMM_SWIGLU = 3 };
+
+// shapes the tcgen05 GEMM accepts (TMA needs 16-byte row pitches; tiles are 64 wide in k and 32 wide in the epilogue)
+bool gemm_supported(uint32_t N, uint32_t K, uint32_t ldx, uint32_t ldy);
+
+// Y[M, ldy] = epilogue(X[M, ldx(:K)] . W[N, K]^T) on `stream`; `err` is the device error flag of bounded waits.
+// mode GEMM_SWIGLU writes N/2 columns.  Returns the number of kernels launched (1).
+int gemm(cudaStream_t stream, int sm_count, int mode, const uint16_t* X, uint32_t ldx, const uint16_t* W, uint16_t* Y, const uint16_t* res, uint32_t M, uint32_t N,
+         uint32_t K, uint32_t ldy, int* err);
+
+int embed_rows(cudaStream_t stream, uint16_t* out, const uint16_t* table, const int32_t* ids, uint32_t rows, uint32_t D);
+int rmsnorm_rows(cudaStream_t stream, uint16_t* out, const uint16_t* x, const uint16_t* w, uint32_t rows, uint32_t D, float eps);
+// qkv [rows, (H + 2 KV) hd] -> q [rows, H hd] rotated, K/V cache rows [seq][kv][start_pos + row] of one layer
+int rope_append(cudaStream_t stream, const uint16_t* qkv, uint16_t* q, uint16_t* kcache_layer, uint16_t* vcache_layer, const float* fcos, const float* fsin,
+                uint32_t rows, uint32_t seq, uint32_t start_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq);
+// causal attention of `rows` consecutive positions of sequence `seq` against its cache (positions 0 .. start_pos + row)
+int prefill_attn(cudaStream_t stream, const uint16_t* q, const uint16_t* kcache_layer, const uint16_t* vcache_layer, uint16_t* out, uint32_t rows, uint32_t seq,
+                 uint32_t start_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, float scale);
+
+} // namespace tc
+} // namespace mc
