@@ -115,6 +115,7 @@ struct mc_llama {
     // tensor-core prefill (mc_prefill.cu): activations of one prompt chunk, allocated on first use
     dbuf pf_ids, pf_x, pf_h, pf_n, pf_qkv, pf_q, pf_attn, pf_z;
     uint32_t pf_rows = 0;
+    dbuf dt_n, dt_qkv;         // batched decode on the tensor cores: normed rows and un-rotated q|k|v rows of one step
     dbuf ids, pos, row_seq, uniforms, out_log, step_counter, pval, pidx, lora_ax, pack_bad, cand;
     int32_t* pinned = nullptr; // host staging: ids | pos | out
     float scale_bf16 = 0.0f;
@@ -134,7 +135,7 @@ struct mc_llama {
         for (int k = 0; k < kTpMaxWorld; k++)
             if (tp_peer_base[k] && uint32_t(k) != cfg.tp_rank) cudaIpcCloseMemHandle(tp_peer_base[k]);
         for (dbuf* b : {&st_ll, &st_timing, &layer_arena, &bar, &errflag, &mega_timing, &tp_region, &tp_local, &norm, &fcos, &fsin, &kcache, &vcache, &x, &h, &q, &attn, &z, &logits, &logits_tmp, &hidden_save, &io_in, &io_out, &ids, &pos, &row_seq,
-                        &uniforms, &out_log, &step_counter, &pval, &pidx, &lora_ax, &pack_bad, &cand, &pf_ids, &pf_x, &pf_h, &pf_n, &pf_qkv, &pf_q, &pf_attn, &pf_z})
+                        &uniforms, &out_log, &step_counter, &pval, &pidx, &lora_ax, &pack_bad, &cand, &pf_ids, &pf_x, &pf_h, &pf_n, &pf_qkv, &pf_q, &pf_attn, &pf_z, &dt_n, &dt_qkv})
             b->release();
     }
 };
@@ -822,6 +823,65 @@ void enqueue_sample(mc_llama* m, launcher& L, uint32_t rows, const mc_sampler_co
          kArgmaxBlocks, m->ids.as<int32_t>(), m->pos.as<int32_t>(), m->out_log.as<int32_t>(), m->step_counter.as<int32_t>(), rows, advance);
 }
 
+// ---- batched decode on the tensor cores -------------------------------------------------------------------------------------
+// Many sequences per step (BASELINE.json "batch 32"): every linear of the step is ONE tcgen05 GEMM over all rows, so the
+// weights are streamed once per step instead of once per 4 rows; attention stays the per-(row, head) cluster kernel.
+uint32_t decode_tc_min_rows()
+{
+    static const uint32_t v = [] {
+        const char* e = getenv("MC_TC_DECODE_MIN");
+        return e ? uint32_t(atoi(e)) : 9u;
+    }();
+    return v;
+}
+bool decode_tc_eligible(const mc_llama* m, uint32_t n)
+{
+    const mc_llama_config& c = m->cfg;
+    if ((c.flags & MC_LLAMA_NO_TC_PREFILL) || c.quant || c.tp_world != 1 || m->tok.fmt != WF_BF16 || n < decode_tc_min_rows() || !m->dt_n.p) return false;
+    const uint32_t D = c.dim, QO = m->Hl * c.head_dim, QKV = (m->Hl + 2 * m->KVl) * c.head_dim, F = m->Fl;
+    return tc::gemm_supported(QKV, D, D, QKV) && tc::gemm_supported(D, QO, QO, D) && tc::gemm_supported(2 * F, D, D, F) && tc::gemm_supported(D, F, F, D) &&
+           tc::gemm_supported(m->Vl, D, D, m->Vl);
+}
+void enqueue_rows_tc(mc_llama* m, launcher& L, uint32_t rows)
+{
+    const mc_llama_config& c = m->cfg;
+    const uint32_t D = c.dim, hd = c.head_dim, H = m->Hl, KV = m->KVl, QO = H * hd, QKV = (H + 2 * KV) * hd, F = m->Fl;
+    cudaStream_t s = L.s;
+    const int sms = m->dev->prop.multiProcessorCount;
+    uint16_t *x = m->x.as<uint16_t>(), *h = m->h.as<uint16_t>(), *n = m->dt_n.as<uint16_t>(), *qkv = m->dt_qkv.as<uint16_t>();
+    uint16_t *q = m->q.as<uint16_t>(), *attn = m->attn.as<uint16_t>(), *z = m->z.as<uint16_t>();
+    int* err = m->errflag.as<int>();
+    auto count = [&](int k) { L.count += uint32_t(k), m->dev->launches.fetch_add(uint64_t(k)); };
+    L.go(embed_kernel, dim3(rows), dim3(256), 0, x, D, (const void*)m->tok.w.p, (const float*)m->tok.scales.p, m->tok.fmt, D, c.vocab, m->ids.as<int32_t>());
+    for (uint32_t li = 0; li < c.n_layers; li++) {
+        dlayer& ly = m->layers[li];
+        uint16_t* kc = m->kcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
+        uint16_t* vc = m->vcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
+        count(tc::rmsnorm_rows(s, n, x, ly.attn_norm.as<uint16_t>(), rows, D, c.norm_eps));
+        count(tc::gemm(s, sms, tc::GEMM_STORE, n, D, ly.wqkv.w.as<uint16_t>(), qkv, nullptr, rows, QKV, D, QKV, err));
+        count(tc::rope_append(s, qkv, q, kc, vc, m->fcos.as<float>(), m->fsin.as<float>(), rows, 0, 0, H, KV, hd, c.max_seq_len, m->row_seq.as<int32_t>(),
+                              m->pos.as<int32_t>()));
+        if (tc::decode_attn_gqa_supported(H, KV, hd)) {
+            count(tc::decode_attn_gqa(s, q, kc, vc, attn, rows, m->row_seq.as<int32_t>(), m->pos.as<int32_t>(), H, KV, hd, c.max_seq_len, m->scale_bf16));
+        } else {
+            const attn_params a = attn_params_of(m, li, 0);
+            const size_t smem = attn_smem(m, kAttnCluster);
+            const bool pdl = L.pdl;
+            L.pdl = false; // the producer above is a plain launch
+            if (hd == 64) L.go_cluster(attn_decode_kernel<64>, dim3(H * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
+            else L.go_cluster(attn_decode_kernel<128>, dim3(H * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
+            L.pdl = pdl;
+        }
+        count(tc::gemm(s, sms, tc::GEMM_RESIDUAL, attn, QO, ly.wo.w.as<uint16_t>(), h, x, rows, D, QO, D, err));
+        count(tc::rmsnorm_rows(s, n, h, ly.ffn_norm.as<uint16_t>(), rows, D, c.norm_eps));
+        count(tc::gemm(s, sms, tc::GEMM_SWIGLU, n, D, ly.w13.w.as<uint16_t>(), z, nullptr, rows, 2 * F, D, F, err));
+        count(tc::gemm(s, sms, tc::GEMM_RESIDUAL, z, F, ly.w2.w.as<uint16_t>(), x, h, rows, D, F, D, err));
+    }
+    count(tc::rmsnorm_rows(s, n, x, m->norm.as<uint16_t>(), rows, D, c.norm_eps));
+    const dlinear& hw = m->tied ? m->tok : m->out;
+    count(tc::gemm(s, sms, tc::GEMM_STORE, n, D, hw.w.as<uint16_t>(), m->logits.as<uint16_t>(), nullptr, rows, m->Vl, D, m->Vl, err));
+}
+
 // one decode step for rows [0, n): forward in chunks of kMaxMB rows, then sample
 void enqueue_decode_step(mc_llama* m, launcher& L, uint32_t n, const mc_sampler_config& sc, int advance)
 {
@@ -833,6 +893,14 @@ void enqueue_decode_step(mc_llama* m, launcher& L, uint32_t n, const mc_sampler_
         if (n == 1) launch_megakernel<1>(m, L, n, advance);
         else if (n == 2) launch_megakernel<2>(m, L, n, advance);
         else launch_megakernel<4>(m, L, n, advance);
+        return;
+    }
+    if (decode_tc_eligible(m, n)) {
+        enqueue_rows_tc(m, L, n);
+        const bool pdl = L.pdl;
+        L.pdl = false;
+        enqueue_sample(m, L, n, sc, advance);
+        L.pdl = pdl;
         return;
     }
     for (uint32_t r0 = 0; r0 < n; r0 += kMaxMB) {
@@ -1185,6 +1253,10 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
     m->x.alloc(size_t(R) * D * 2), m->h.alloc(size_t(R) * D * 2);
     m->q.alloc(size_t(R) * m->Hl * hd * 2), m->attn.alloc(size_t(R) * m->Hl * hd * 2);
     m->z.alloc(size_t(R) * m->Fl * 2);
+    if (!c.quant && c.tp_world == 1 && c.n_seqs >= decode_tc_min_rows()) {
+        m->dt_n.alloc(size_t(R) * D * 2);
+        m->dt_qkv.alloc(size_t(R) * (m->Hl + 2 * m->KVl) * hd * 2);
+    }
     {
         // tagged-word exchange buffers of the streaming kernel (8 bytes per word = two bf16 + tag)
         const size_t R8 = kStMaxRows;

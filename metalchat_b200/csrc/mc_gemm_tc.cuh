@@ -69,9 +69,17 @@ constexpr int kTcBK = 64;       // k per stage: 128 bytes per row = one swizzle 
 constexpr int kTcThreads = 192; // producer warp | MMA warp | 4 epilogue warps
 constexpr int kTcHdr = 1024;    // barriers + TMEM base slot
 
-__host__ __device__ constexpr int tc_stages(int BN) { return BN >= 256 ? 4 : 6; }
-__host__ __device__ constexpr int tc_stage_bytes(int BN) { return (kTcBM + BN) * kTcBK * 2; }
-__host__ __device__ constexpr int tc_smem_bytes(int BN) { return kTcHdr + tc_stages(BN) * tc_stage_bytes(BN) + 1024; }
+// AROWS = prompt rows actually staged per A tile.  A prompt chunk stages all 128; a decode batch of <= 32 rows stages 32 and lets
+// the MMA read the remaining (stale) rows of its 128-row operand window -- they only reach accumulator rows nobody reads -- so
+// that a stage costs 4 KiB + the weight tile and the ring holds several times more weight bytes in flight (HBM-bound regime).
+constexpr int kTcRing = 192 * 1024;
+__host__ __device__ constexpr int tc_stage_bytes(int BN, int AROWS) { return (AROWS + BN) * kTcBK * 2; }
+__host__ __device__ constexpr int tc_a_slack(int AROWS) { return (kTcBM - AROWS) * kTcBK * 2; }
+__host__ __device__ constexpr int tc_stages(int BN, int AROWS)
+{
+    return (kTcRing - tc_a_slack(AROWS)) / tc_stage_bytes(BN, AROWS) > 24 ? 24 : (kTcRing - tc_a_slack(AROWS)) / tc_stage_bytes(BN, AROWS);
+}
+__host__ __device__ constexpr int tc_smem_bytes(int BN, int AROWS) { return kTcHdr + tc_stages(BN, AROWS) * tc_stage_bytes(BN, AROWS) + tc_a_slack(AROWS) + 1024; }
 
 struct gemm_tc_params {
     uint16_t* Y;         // EPI_NONE / EPI_RESIDUAL: [M, ldy]; EPI_SWIGLU: [M, ldy] holding N/2 columns
@@ -129,18 +137,18 @@ __device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity, volatile 
     }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int AROWS>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const gemm_tc_params p)
 {
-    constexpr int STAGES = tc_stages(BN);
-    constexpr uint32_t A_BYTES = kTcBM * kTcBK * 2, B_BYTES = BN * kTcBK * 2;
+    constexpr int STAGES = tc_stages(BN, AROWS);
+    constexpr uint32_t A_BYTES = AROWS * kTcBK * 2, B_BYTES = BN * kTcBK * 2;
     extern __shared__ unsigned char smem_raw[];
     // 128-byte swizzle: tiles on 1024-byte boundaries
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t base = smem_u32(smem);
-    const uint32_t bar_full = base, bar_empty = base + 64, bar_tfull = base + 128, bar_tempty = base + 144, tmem_slot = base + 160;
-    volatile int* dead = reinterpret_cast<volatile int*>(smem + 176);
-    const uint32_t a0 = base + kTcHdr, b0 = a0 + STAGES * A_BYTES;
+    const uint32_t bar_full = base, bar_empty = base + 192, bar_tfull = base + 384, bar_tempty = base + 400, tmem_slot = base + 416;
+    volatile int* dead = reinterpret_cast<volatile int*>(smem + 432);
+    const uint32_t a0 = base + kTcHdr, b0 = a0 + STAGES * A_BYTES + tc_a_slack(AROWS);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -159,7 +167,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + 160);
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + 416);
 
     const uint32_t m_blocks = (p.M + kTcBM - 1) / kTcBM, n_blocks = (p.N + BN - 1) / BN;
     const uint32_t n_tiles = m_blocks * n_blocks, k_blocks = p.K / kTcBK;
@@ -169,12 +177,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             uint32_t it = 0;
             for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const uint32_t mb = tile % m_blocks, nb = tile / m_blocks;
+                // every tile walks k from its own starting block: CTAs that share an X (or W) tile would otherwise request the
+                // same L2 lines in lockstep, and a line's slice serves them one after the other (measured: ~540 cycles per k block
+                // for ANY tile size before the rotation).  The start depends only on the 256-column group and the 128-row block of
+                // the outputs, so a row's bits do not depend on the tile width or on how many rows share the call.
+                const uint32_t rot = (((nb * BN) >> 8) * 11u + mb * 5u) % k_blocks;
                 for (uint32_t kb = 0; kb < k_blocks; kb++, it++) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                    const uint32_t kk = kb + rot < k_blocks ? kb + rot : kb + rot - k_blocks;
                     tc_wait(bar_empty + s * 8, ph ^ 1u, dead, p.err);
                     mbar_expect_tx(bar_full + s * 8, A_BYTES + B_BYTES);
-                    tc_tma_load(a0 + s * A_BYTES, &tmX, kb * kTcBK, mb * kTcBM, bar_full + s * 8);
-                    tc_tma_load(b0 + s * B_BYTES, &tmW, kb * kTcBK, nb * BN, bar_full + s * 8);
+                    tc_tma_load(a0 + s * A_BYTES, &tmX, kk * kTcBK, mb * kTcBM, bar_full + s * 8);
+                    tc_tma_load(b0 + s * B_BYTES, &tmW, kk * kTcBK, nb * BN, bar_full + s * 8);
                 }
             }
         }
@@ -312,32 +326,46 @@ __global__ void __launch_bounds__(256) rmsnorm_rows_kernel(uint16_t* out, const 
         *reinterpret_cast<uint4*>(out + size_t(blockIdx.x) * D + k) = o;
     }
 }
-// rotate q and k (kernel/rope.metal:47-58), store q, append k', v to the cache (nn/cache.h:207-214); grid (H + 2 KV, rows)
-__global__ void rope_append_kernel(const uint16_t* qkv, uint32_t ld, uint16_t* q, uint16_t* kcache, uint16_t* vcache, const float* fcos, const float* fsin,
-                                   uint32_t seq, uint32_t start_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq)
+// rotate q and k (kernel/rope.metal:47-58), store q, append k', v to the cache (nn/cache.h:207-214); one CTA per prompt row
+__global__ void __launch_bounds__(256) rope_append_kernel(const uint16_t* qkv, uint32_t ld, uint16_t* q, uint16_t* kcache, uint16_t* vcache, const float* fcos,
+                                                          const float* fsin, const int32_t* row_seq, const int32_t* row_pos, uint32_t seq, uint32_t start_pos, uint32_t H,
+                                                          uint32_t KV, uint32_t hd, uint32_t max_seq)
 {
-    const uint32_t head = blockIdx.x, row = blockIdx.y, half = hd >> 1, j = threadIdx.x;
-    if (j >= half) return;
-    const uint32_t pos = start_pos + row;
-    const uint16_t* src = qkv + size_t(row) * ld + size_t(head) * hd;
-    const float a = bf16_bits_to_f32(src[j]), b = bf16_bits_to_f32(src[j + half]);
-    if (head < H + KV) {
-        const float cs = fcos[size_t(pos) * half + j], sn = fsin[size_t(pos) * half + j];
-        const uint16_t o0 = f32_to_bf16_bits(__fsub_rn(__fmul_rn(cs, a), __fmul_rn(sn, b)));
-        const uint16_t o1 = f32_to_bf16_bits(__fadd_rn(__fmul_rn(sn, a), __fmul_rn(cs, b)));
+    // prompt: rows are consecutive positions of one sequence; batched decode: every row carries its own (sequence, position)
+    const uint32_t row = blockIdx.x, half = hd >> 1, pos = row_pos ? uint32_t(row_pos[row]) : start_pos + row;
+    if (row_seq) seq = uint32_t(row_seq[row]);
+    const uint16_t* src_row = qkv + size_t(row) * ld;
+    // rotated heads (q heads then k heads): thread = one pair of adjacent j -> (j, j+1) and (j + half, j + half + 1)
+    const uint32_t pairs = (H + KV) * (half >> 1);
+    for (uint32_t i = threadIdx.x; i < pairs; i += 256) {
+        const uint32_t head = i / (half >> 1), j = (i % (half >> 1)) * 2;
+        const uint16_t* src = src_row + size_t(head) * hd;
+        const uint32_t lo = *reinterpret_cast<const uint32_t*>(src + j), hi = *reinterpret_cast<const uint32_t*>(src + j + half);
+        const float2 cs = *reinterpret_cast<const float2*>(fcos + size_t(pos) * half + j), sn = *reinterpret_cast<const float2*>(fsin + size_t(pos) * half + j);
+        const float a0 = bf_lo(lo), a1 = bf_hi(lo), b0 = bf_lo(hi), b1 = bf_hi(hi);
+        const uint32_t o_lo = pack2(__fsub_rn(__fmul_rn(cs.x, a0), __fmul_rn(sn.x, b0)), __fsub_rn(__fmul_rn(cs.y, a1), __fmul_rn(sn.y, b1)));
+        const uint32_t o_hi = pack2(__fadd_rn(__fmul_rn(sn.x, a0), __fmul_rn(cs.x, b0)), __fadd_rn(__fmul_rn(sn.y, a1), __fmul_rn(cs.y, b1)));
         uint16_t* dst = head < H ? q + size_t(row) * H * hd + size_t(head) * hd : kcache + ((size_t(seq) * KV + (head - H)) * max_seq + size_t(pos)) * hd;
-        dst[j] = o0, dst[j + half] = o1;
-    } else {
-        uint16_t* dst = vcache + ((size_t(seq) * KV + (head - H - KV)) * max_seq + size_t(pos)) * hd;
-        dst[j] = src[j], dst[j + half] = src[j + half];
+        *reinterpret_cast<uint32_t*>(dst + j) = o_lo;
+        *reinterpret_cast<uint32_t*>(dst + j + half) = o_hi;
+    }
+    // values: bit copy, 16 bytes per thread
+    const uint32_t chunks = KV * (hd >> 3);
+    for (uint32_t i = threadIdx.x; i < chunks; i += 256) {
+        const uint32_t kvh = i / (hd >> 3), c = (i % (hd >> 3)) * 8;
+        *reinterpret_cast<uint4*>(vcache + ((size_t(seq) * KV + kvh) * max_seq + size_t(pos)) * hd + c) =
+            *reinterpret_cast<const uint4*>(src_row + size_t(H + KV + kvh) * hd + c);
     }
 }
 
 // ---- causal prefill attention -------------------------------------------------------------------------------------------
-// One CTA = 64 consecutive prompt rows of one head (4 warps x 16 rows), keys in tiles of 64 from the KV cache.
+// One CTA = 8 warps x 16 prompt rows: `rep` query heads of one KV head (grouped-query attention: they read the same K/V tiles)
+// times 128 / rep consecutive rows; keys in tiles of 64 from the KV cache, double-buffered with cp.async.  The heaviest
+// row tiles (most visible keys) are scheduled first.
 // The reference's chain (nn/attention.h:195-200, kernel/softmax.metal:40-80) has no running maximum and rounds to bf16 after
 // each of bmm / scale / softmax / bmm, so the kernel makes two passes over the keys:
-//   pass 1   s = r(r(q.K) * scale) for every visible key, total = sum exp(s)               (fp32, fixed order per thread)
+//   pass 1   s = r(r(q.K) * scale) for every visible key, total = sum exp(s)               (fp32, fixed order per thread;
+//            exp = ex2.approx(s * log2 e), 2 ulp of fp32 -- far inside the bf16 rounding that follows)
 //   pass 2   p = r(exp(s) * (1 / total)), o += p . V with p as the bf16 A operand of the second mma; o = r(o) at the end
 // Masked keys (t > pos) contribute exactly 0, as exp(r(s + -inf)) does in the reference.
 struct pattn_params {
@@ -346,6 +374,7 @@ struct pattn_params {
     const uint16_t* vc;
     uint16_t* out;      // [rows, H*hd]
     uint32_t rows, start_pos, H, KV, max_seq;
+    uint32_t rep;       // query heads per CTA: H / KV when that is 1, 2, 4 or 8, else 1
     float scale;        // r(1/sqrt(hd)) stored as T (quirk Q4)
 };
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
@@ -354,22 +383,45 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// two fp32 -> packed bf16 pair with one cvt.rn.bf16x2.f32 (round to nearest even; same bits as pack2 for every non-NaN input)
+__device__ __forceinline__ uint32_t pack2_rn(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float exp2f_approx(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ void pa_cp16(uint32_t dst, const void* src, bool valid)
 {
     const uint32_t n = valid ? 16u : 0u; // src-size 0: the 16 bytes are zero-filled
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
 }
-template <int HD> __global__ void __launch_bounds__(128) prefill_attn_kernel(const pattn_params p)
+// RNE to bf16 on the integer pipe (the conversion unit is the busiest pipe of this kernel); same bits as rbf() for every non-NaN input
+__device__ __forceinline__ float rbf_alu(float x)
+{
+    const uint32_t u = __float_as_uint(x);
+    return __uint_as_float((u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u);
+}
+// POW2: the stored scale r(1/sqrt(hd)) is a power of two (head_dim 64: 0.125), so r(r(q.K) * scale) == r(q.K) * scale exactly
+// and the second rounding is skipped.
+template <int HD, bool POW2> __global__ void __launch_bounds__(256, HD == 64 ? 2 : 1) prefill_attn_kernel(const pattn_params p)
 {
     constexpr int PITCH = HD + 8;             // bf16 elements per smem row: 16-byte aligned, conflict-free fragment loads
     constexpr int TILE = 64 * PITCH * 2;      // bytes of one 64-key K (or V) tile
     extern __shared__ __align__(16) unsigned char psm[]; // [2 buffers][K tile | V tile]
     const uint32_t sbase = smem_u32(psm);
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const uint32_t head = blockIdx.y, kvh = head / (p.H / p.KV);
-    const uint32_t q0 = blockIdx.x * 64;
-    const uint32_t r_lo = q0 + warp * 16 + g, r_hi = r_lo + 8; // the two prompt rows of this thread
-    const uint32_t rows_end = min(q0 + 64u, p.rows);
+    const uint32_t head = blockIdx.x * p.rep + warp % p.rep, kvh = head / (p.H / p.KV);
+    const uint32_t qt = 128u / p.rep;                       // prompt rows of this CTA
+    const uint32_t q0 = (gridDim.y - 1 - blockIdx.y) * qt;  // row tile = the slow grid index, heaviest (most visible keys) first
+    const uint32_t wr0 = q0 + (warp / p.rep) * 16;          // first row of this warp
+    const uint32_t r_lo = wr0 + g, r_hi = r_lo + 8;         // the two prompt rows of this thread
+    const uint32_t rows_end = min(q0 + qt, p.rows);
     const uint32_t n_keys = p.start_pos + rows_end; // keys visible to the last row of the CTA
     const uint32_t n_tiles = (n_keys + 63) / 64;
     const uint16_t* kbase = p.kc + size_t(kvh) * p.max_seq * HD;
@@ -396,7 +448,7 @@ template <int HD> __global__ void __launch_bounds__(128) prefill_attn_kernel(con
         const uint32_t kt = second ? job - n_tiles : job;
         const uint32_t buf = sbase + (job & 1u) * 2 * TILE;
         constexpr int CH = HD / 8; // 16-byte chunks per row
-        for (uint32_t c = tid; c < 64 * CH; c += 128) {
+        for (uint32_t c = tid; c < 64 * CH; c += 256) {
             const uint32_t r = c / CH, cc = c % CH, key = kt * 64 + r;
             const bool ok = key < n_keys;
             const size_t off = size_t(ok ? key : 0) * HD + cc * 8;
@@ -431,37 +483,48 @@ template <int HD> __global__ void __launch_bounds__(128) prefill_attn_kernel(con
             inv_lo = 1.0f / sum_lo, inv_hi = 1.0f / sum_hi;
         }
         // this warp's rows see keys <= pos_hi: skip tiles entirely above the diagonal
-        if (kt * 64 <= p.start_pos + q0 + warp * 16 + 15) {
+        if (kt * 64 <= p.start_pos + wr0 + 15) {
             // S = Q . K^T for 64 keys: 8 n-tiles of 8 keys
             float s[8][4];
 #pragma unroll
             for (int nt = 0; nt < 8; nt++) {
                 s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
 #pragma unroll
-                for (int ks = 0; ks < HD / 16; ks++) {
-                    // B[k = d][n = key] = K[key][d]: lane (g, t) reads K[nt*8 + g][ks*16 + 2t ..] and [.. + 8 ..]
-                    const uint32_t addr = kbuf + ((nt * 8 + g) * PITCH + ks * 16 + 2 * t) * 2;
-                    uint32_t b0, b1;
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(b0) : "r"(addr));
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(b1) : "r"(addr + 16));
-                    mma_bf16_16816(s[nt], qa[ks], b0, b1);
+                for (int k2 = 0; k2 < HD / 32; k2++) {
+                    // B[k = d][n = key] = K[key][d]: ldmatrix.x4 = the 8 keys of the n-tile x d chunks (0-7 | 8-15 | 16-23 | 24-31) of this k pair
+                    const uint32_t addr = kbuf + ((nt * 8 + (lane & 7)) * PITCH + k2 * 32 + (lane >> 3) * 8) * 2;
+                    uint32_t b0, b1, b2, b3;
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
+                    mma_bf16_16816(s[nt], qa[2 * k2], b0, b1);
+                    mma_bf16_16816(s[nt], qa[2 * k2 + 1], b2, b3);
                 }
             }
-            // s = r(r(q.K) * scale); masked keys drop out  (kernel/bmm.metal:76, kernel/arithmetic.metal scalar_mul)
+            // s = r(r(q.K) * scale), e = exp(s) = ex2(s * log2 e); masked keys drop out  (kernel/bmm.metal:76, scalar_mul,
+            // kernel/softmax.metal:46)
+            const bool diagonal = kt * 64 + 63 > p.start_pos + wr0; // some key of the tile is above some row of the warp
+            const float sl2e = p.scale * 1.4426950408889634f;
 #pragma unroll
             for (int nt = 0; nt < 8; nt++) {
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const uint32_t key = kt * 64 + nt * 8 + 2 * t + (e & 1);
-                    const uint32_t lim = (e & 2) ? pos_hi : pos_lo;
-                    const float sv = rbf(__fmul_rn(rbf(s[nt][e]), p.scale));
-                    const float ex = key <= lim ? expf(sv) : 0.0f;
-                    if (!second) {
-                        if (e & 2) sum_hi += ex;
-                        else sum_lo += ex;
-                    } else {
-                        s[nt][e] = rbf(__fmul_rn(ex, (e & 2) ? inv_hi : inv_lo)); // p = r(exp(s) * (1/total))  (kernel/softmax.metal:79)
-                    }
+                float e0, e1, e2, e3;
+                if (POW2) {
+                    e0 = exp2f_approx(rbf_alu(s[nt][0]) * sl2e), e1 = exp2f_approx(rbf_alu(s[nt][1]) * sl2e);
+                    e2 = exp2f_approx(rbf_alu(s[nt][2]) * sl2e), e3 = exp2f_approx(rbf_alu(s[nt][3]) * sl2e);
+                } else {
+                    const uint32_t lo2 = pack2_rn(__fmul_rn(rbf_alu(s[nt][0]), p.scale), __fmul_rn(rbf_alu(s[nt][1]), p.scale));
+                    const uint32_t hi2 = pack2_rn(__fmul_rn(rbf_alu(s[nt][2]), p.scale), __fmul_rn(rbf_alu(s[nt][3]), p.scale));
+                    e0 = __expf(bf_lo(lo2)), e1 = __expf(bf_hi(lo2)), e2 = __expf(bf_lo(hi2)), e3 = __expf(bf_hi(hi2));
+                }
+                if (diagonal) {
+                    const uint32_t key = kt * 64 + nt * 8 + 2 * t;
+                    e0 = key <= pos_lo ? e0 : 0.0f, e1 = key + 1 <= pos_lo ? e1 : 0.0f;
+                    e2 = key <= pos_hi ? e2 : 0.0f, e3 = key + 1 <= pos_hi ? e3 : 0.0f;
+                }
+                if (!second) {
+                    sum_lo += e0 + e1, sum_hi += e2 + e3;
+                } else {
+                    // p = r(exp(s) * (1/total))  (kernel/softmax.metal:79), kept packed: the A operand of the second product
+                    s[nt][0] = __uint_as_float(pack2_rn(__fmul_rn(e0, inv_lo), __fmul_rn(e1, inv_lo)));
+                    s[nt][2] = __uint_as_float(pack2_rn(__fmul_rn(e2, inv_hi), __fmul_rn(e3, inv_hi)));
                 }
             }
             if (second) {
@@ -469,10 +532,10 @@ template <int HD> __global__ void __launch_bounds__(128) prefill_attn_kernel(con
 #pragma unroll
                 for (int kk = 0; kk < 4; kk++) {
                     uint32_t pa[4];
-                    pa[0] = pack2(s[2 * kk][0], s[2 * kk][1]);
-                    pa[1] = pack2(s[2 * kk][2], s[2 * kk][3]);
-                    pa[2] = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-                    pa[3] = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+                    pa[0] = __float_as_uint(s[2 * kk][0]);
+                    pa[1] = __float_as_uint(s[2 * kk][2]);
+                    pa[2] = __float_as_uint(s[2 * kk + 1][0]);
+                    pa[3] = __float_as_uint(s[2 * kk + 1][2]);
 #pragma unroll
                     for (int dp = 0; dp < HD / 16; dp++) {
                         // ldmatrix.x4.trans: matrices (keys 0-7 | 8-15) x (d 0-7 | 8-15) of the 16 x 16 block of V
@@ -493,6 +556,144 @@ template <int HD> __global__ void __launch_bounds__(128) prefill_attn_kernel(con
     for (int nt = 0; nt < HD / 8; nt++) {
         if (r_lo < p.rows) *reinterpret_cast<uint32_t*>(p.out + size_t(r_lo) * p.H * HD + size_t(head) * HD + nt * 8 + 2 * t) = pack2(rbf(o[nt][0]), rbf(o[nt][1]));
         if (r_hi < p.rows) *reinterpret_cast<uint32_t*>(p.out + size_t(r_hi) * p.H * HD + size_t(head) * HD + nt * 8 + 2 * t) = pack2(rbf(o[nt][2]), rbf(o[nt][3]));
+    }
+}
+
+
+// ---- batched decode attention (grouped-query) -------------------------------------------------------------------------------
+// One CTA = one (sequence, KV head): the H / KV query heads that share the KV head are the rows of one m16 mma tile, so the
+// cached keys / values of the head are read ONCE for all of them (the per-(row, head) decode kernel reads them H / KV times).
+// Keys go in tiles of 64; warp w owns keys [16w, 16w + 16) of every tile (two score n-tiles, one k step of the value product).
+// Same two passes and rounding points as the prompt kernel above; the four per-warp partial sums / outputs are joined in
+// warp order through shared memory.
+struct dattn_params {
+    const uint16_t* q;  // [rows, H*hd] rotated
+    const uint16_t* kc; // this layer: [n_seqs][KV][max_seq][hd]
+    const uint16_t* vc;
+    uint16_t* out;      // [rows, H*hd]
+    const int32_t* row_seq;
+    const int32_t* row_pos;
+    uint32_t H, KV, max_seq;
+    float scale;
+};
+template <int HD, bool POW2> __global__ void __launch_bounds__(128) decode_attn_gqa_kernel(const dattn_params p)
+{
+    constexpr int PITCH = HD + 8;
+    constexpr int TILE = 64 * PITCH * 2;
+    extern __shared__ __align__(16) unsigned char psm[]; // [2 buffers][K tile | V tile] | float red[4][8]
+    float* red = reinterpret_cast<float*>(psm + 4 * TILE);
+    const uint32_t sbase = smem_u32(psm);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const uint32_t kvh = blockIdx.x, row = blockIdx.y, n_rep = p.H / p.KV;
+    const uint32_t seq = uint32_t(p.row_seq[row]), pos = uint32_t(p.row_pos[row]);
+    const uint32_t n_keys = pos + 1, n_tiles = (n_keys + 63) / 64;
+    const uint16_t* kbase = p.kc + (size_t(seq) * p.KV + kvh) * p.max_seq * HD;
+    const uint16_t* vbase = p.vc + (size_t(seq) * p.KV + kvh) * p.max_seq * HD;
+
+    // Q fragments: mma row g = query head kvh * n_rep + g (rows >= n_rep and rows 8..15 are zero padding)
+    uint32_t qa[HD / 16][4];
+    {
+        const bool valid = g < n_rep;
+        const uint16_t* ql = p.q + size_t(row) * p.H * HD + size_t(kvh * n_rep + (valid ? g : 0)) * HD;
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ks++) {
+            qa[ks][0] = valid ? *reinterpret_cast<const uint32_t*>(ql + ks * 16 + 2 * t) : 0u;
+            qa[ks][2] = valid ? *reinterpret_cast<const uint32_t*>(ql + ks * 16 + 8 + 2 * t) : 0u;
+            qa[ks][1] = qa[ks][3] = 0u;
+        }
+    }
+    auto issue = [&](uint32_t job) {
+        const bool second = job >= n_tiles;
+        const uint32_t kt = second ? job - n_tiles : job;
+        const uint32_t buf = sbase + (job & 1u) * 2 * TILE;
+        constexpr int CH = HD / 8;
+        for (uint32_t c = tid; c < 64 * CH; c += 128) {
+            const uint32_t r = c / CH, cc = c % CH, key = kt * 64 + r;
+            const bool ok = key < n_keys;
+            const size_t off = size_t(ok ? key : 0) * HD + cc * 8;
+            pa_cp16(buf + (r * PITCH + cc * 8) * 2, kbase + off, ok);
+            if (second) pa_cp16(buf + TILE + (r * PITCH + cc * 8) * 2, vbase + off, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    float sum = 0.0f, inv = 0.0f;
+    float o[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; i++) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f;
+    const float sl2e = p.scale * 1.4426950408889634f;
+    const uint32_t n_jobs = 2 * n_tiles;
+    issue(0);
+    for (uint32_t job = 0; job < n_jobs; job++) {
+        if (job == n_tiles) {
+            // end of pass 1: quad partial -> warp partial (row g), published for the join below
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1), sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            if (t == 0) red[warp * 8 + g] = sum;
+        }
+        if (job + 1 < n_jobs) {
+            issue(job + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const bool second = job >= n_tiles;
+        const uint32_t kt = second ? job - n_tiles : job;
+        const uint32_t kbuf = sbase + (job & 1u) * 2 * TILE, vbuf = kbuf + TILE;
+        if (job == n_tiles) inv = 1.0f / (((red[g] + red[8 + g]) + red[16 + g]) + red[24 + g]);
+        if (kt * 64 + warp * 16 < n_keys) {
+            float s[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++) {
+                s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+#pragma unroll
+                for (int k2 = 0; k2 < HD / 32; k2++) {
+                    const uint32_t addr = kbuf + ((warp * 16 + nt * 8 + (lane & 7)) * PITCH + k2 * 32 + (lane >> 3) * 8) * 2;
+                    uint32_t b0, b1, b2, b3;
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
+                    mma_bf16_16816(s[nt], qa[2 * k2], b0, b1);
+                    mma_bf16_16816(s[nt], qa[2 * k2 + 1], b2, b3);
+                }
+            }
+            uint32_t pa[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++) {
+                float e0, e1;
+                if (POW2) {
+                    e0 = exp2f_approx(rbf_alu(s[nt][0]) * sl2e), e1 = exp2f_approx(rbf_alu(s[nt][1]) * sl2e);
+                } else {
+                    const uint32_t lo2 = pack2_rn(__fmul_rn(rbf_alu(s[nt][0]), p.scale), __fmul_rn(rbf_alu(s[nt][1]), p.scale));
+                    e0 = __expf(bf_lo(lo2)), e1 = __expf(bf_hi(lo2));
+                }
+                const uint32_t key = kt * 64 + warp * 16 + nt * 8 + 2 * t;
+                e0 = key <= pos ? e0 : 0.0f, e1 = key + 1 <= pos ? e1 : 0.0f;
+                if (!second) sum += e0 + e1;
+                else pa[2 * nt] = pack2_rn(__fmul_rn(e0, inv), __fmul_rn(e1, inv)); // p = r(exp(s) * (1/total))
+            }
+            if (second) {
+#pragma unroll
+                for (int dp = 0; dp < HD / 16; dp++) {
+                    const uint32_t mi = lane >> 3, mr = lane & 7;
+                    const uint32_t addr = vbuf + ((warp * 16 + (mi & 1) * 8 + mr) * PITCH + dp * 16 + (mi >> 1) * 8) * 2;
+                    uint32_t v0, v1, v2, v3;
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(addr));
+                    mma_bf16_16816(o[2 * dp], pa, v0, v1);
+                    mma_bf16_16816(o[2 * dp + 1], pa, v2, v3);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // join the four per-warp partial outputs in warp order, o = r(sum p.V)  (kernel/bmm.metal:76)
+    float* part = reinterpret_cast<float*>(psm); // [4 warps][8 rows][HD]
+    if (g < n_rep) {
+#pragma unroll
+        for (int nt = 0; nt < HD / 8; nt++) *reinterpret_cast<float2*>(part + (warp * 8 + g) * HD + nt * 8 + 2 * t) = make_float2(o[nt][0], o[nt][1]);
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n_rep * HD; i += 128) {
+        const uint32_t r = i / HD, d = i % HD;
+        const float v = ((part[r * HD + d] + part[(8 + r) * HD + d]) + part[(16 + r) * HD + d]) + part[(24 + r) * HD + d];
+        p.out[size_t(row) * p.H * HD + size_t(kvh * n_rep + r) * HD + d] = f32_to_bf16_bits(v);
     }
 }
 

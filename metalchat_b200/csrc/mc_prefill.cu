@@ -57,28 +57,52 @@ CUtensorMap make_map(const uint16_t* base, uint32_t rows, uint32_t K, uint32_t l
     return m;
 }
 
-template <int BN, int EPI> void launch_gemm(cudaStream_t s, int sm_count, const CUtensorMap& mx, const CUtensorMap& mw, const gemm_tc_params& p)
+template <int BN, int EPI, int AROWS> void launch_gemm(cudaStream_t s, int sm_count, const CUtensorMap& mx, const CUtensorMap& mw, const gemm_tc_params& p)
 {
-    auto kernel = gemm_tc_kernel<BN, EPI>;
+    auto kernel = gemm_tc_kernel<BN, EPI, AROWS>;
     static bool configured[8] = {false};
     int dev = 0;
     MC_CUDA_CHECK(cudaGetDevice(&dev));
     if (!configured[dev & 7]) {
-        MC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(BN)));
+        MC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(BN, AROWS)));
         configured[dev & 7] = true;
     }
     const uint32_t tiles = ((p.M + kTcBM - 1) / kTcBM) * ((p.N + BN - 1) / BN);
     const uint32_t grid = tiles < uint32_t(sm_count) ? tiles : uint32_t(sm_count);
-    kernel<<<grid, kTcThreads, tc_smem_bytes(BN), s>>>(mx, mw, p);
+    kernel<<<grid, kTcThreads, tc_smem_bytes(BN, AROWS), s>>>(mx, mw, p);
     MC_CUDA_CHECK(cudaGetLastError());
 }
-template <int BN> void launch_gemm_epi(cudaStream_t s, int sm_count, int mode, const CUtensorMap& mx, const CUtensorMap& mw, const gemm_tc_params& p)
+template <int BN, int AROWS> void launch_gemm_epi(cudaStream_t s, int sm_count, int mode, const CUtensorMap& mx, const CUtensorMap& mw, const gemm_tc_params& p)
 {
     switch (mode) {
-    case GEMM_STORE: launch_gemm<BN, EPI_NONE>(s, sm_count, mx, mw, p); break;
-    case GEMM_RESIDUAL: launch_gemm<BN, EPI_RESIDUAL>(s, sm_count, mx, mw, p); break;
-    case GEMM_SWIGLU: launch_gemm<BN, EPI_SWIGLU>(s, sm_count, mx, mw, p); break;
+    case GEMM_STORE: launch_gemm<BN, EPI_NONE, AROWS>(s, sm_count, mx, mw, p); break;
+    case GEMM_RESIDUAL: launch_gemm<BN, EPI_RESIDUAL, AROWS>(s, sm_count, mx, mw, p); break;
+    case GEMM_SWIGLU: launch_gemm<BN, EPI_SWIGLU, AROWS>(s, sm_count, mx, mw, p); break;
     default: throw error(MC_ERR_INVALID, "prefill gemm: unknown epilogue");
+    }
+}
+template <int AROWS>
+void launch_gemm_bn(cudaStream_t stream, int sm_count, int mode, const uint16_t* X, uint32_t ldx, const uint16_t* W, const gemm_tc_params& p)
+{
+    const uint32_t M = p.M, N = p.N, K = p.K;
+    const uint32_t m_blocks = (M + kTcBM - 1) / kTcBM;
+    // the widest tile that still gives every SM a tile: 256 for prompts (highest flop per byte staged), down to 32 weight rows
+    // per CTA for a decode batch, where the weights are streamed once and the point is to keep all SMs loading
+    const CUtensorMap mx = make_map(X, M, K, ldx, AROWS);
+    static const int forced = [] {
+        const char* e = getenv("MC_TC_BN"); // experiments: force the tile width
+        return e ? atoi(e) : 0;
+    }();
+    // (an M = 128, K = 16 MMA occupies the tensor core for >= 128 cycles whatever its N -- the A operand is read at 32 bytes per
+    // cycle -- so a 128-wide tile runs at half rate: 256 wins as soon as it fills half of the SMs)
+    if (forced == 256 || (!forced && m_blocks * ((N + 255) / 256) * 2 >= uint32_t(sm_count))) {
+        launch_gemm_epi<256, AROWS>(stream, sm_count, mode, mx, make_map(W, N, K, K, 256), p);
+    } else if (forced == 128 || (!forced && (m_blocks * ((N + 127) / 128) >= uint32_t(sm_count) || M > 256))) {
+        launch_gemm_epi<128, AROWS>(stream, sm_count, mode, mx, make_map(W, N, K, K, 128), p);
+    } else if (forced == 64 || (!forced && m_blocks * ((N + 63) / 64) >= uint32_t(sm_count))) {
+        launch_gemm_epi<64, AROWS>(stream, sm_count, mode, mx, make_map(W, N, K, K, 64), p);
+    } else {
+        launch_gemm_epi<32, AROWS>(stream, sm_count, mode, mx, make_map(W, N, K, K, 32), p);
     }
 }
 
@@ -97,17 +121,9 @@ int gemm(cudaStream_t stream, int sm_count, int mode, const uint16_t* X, uint32_
                "prefill gemm: operands must be 16-byte aligned");
     gemm_tc_params p{};
     p.Y = Y, p.res = res, p.M = M, p.N = N, p.K = K, p.ldy = ldy, p.err = err;
-    const uint32_t m_blocks = (M + kTcBM - 1) / kTcBM;
-    // 256-wide tiles unless they would leave SMs idle
-    const bool wide = m_blocks * ((N + 255) / 256) >= uint32_t(sm_count);
-    const CUtensorMap mx = make_map(X, M, K, ldx, kTcBM);
-    if (wide) {
-        const CUtensorMap mw = make_map(W, N, K, K, 256);
-        launch_gemm_epi<256>(stream, sm_count, mode, mx, mw, p);
-    } else {
-        const CUtensorMap mw = make_map(W, N, K, K, 128);
-        launch_gemm_epi<128>(stream, sm_count, mode, mx, mw, p);
-    }
+    // a decode batch of <= 32 rows stages only 32 rows of X per k block (see tc_stages)
+    if (M <= 32) launch_gemm_bn<32>(stream, sm_count, mode, X, ldx, W, p);
+    else launch_gemm_bn<128>(stream, sm_count, mode, X, ldx, W, p);
     return 1;
 }
 
@@ -126,9 +142,10 @@ int rmsnorm_rows(cudaStream_t stream, uint16_t* out, const uint16_t* x, const ui
     return 1;
 }
 int rope_append(cudaStream_t stream, const uint16_t* qkv, uint16_t* q, uint16_t* kcache_layer, uint16_t* vcache_layer, const float* fcos, const float* fsin,
-                uint32_t rows, uint32_t seq, uint32_t start_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq)
+                uint32_t rows, uint32_t seq, uint32_t start_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, const int32_t* row_seq, const int32_t* row_pos)
 {
-    rope_append_kernel<<<dim3(H + 2 * KV, rows), hd / 2, 0, stream>>>(qkv, (H + 2 * KV) * hd, q, kcache_layer, vcache_layer, fcos, fsin, seq, start_pos, H, KV, hd, max_seq);
+    rope_append_kernel<<<rows, 256, 0, stream>>>(qkv, (H + 2 * KV) * hd, q, kcache_layer, vcache_layer, fcos, fsin, row_seq, row_pos, seq, start_pos, H, KV, hd,
+                                                 max_seq);
     MC_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
@@ -140,23 +157,58 @@ int prefill_attn(cudaStream_t stream, const uint16_t* q, const uint16_t* kcache_
     p.q = q, p.out = out, p.rows = rows, p.start_pos = start_pos, p.H = H, p.KV = KV, p.max_seq = max_seq, p.scale = scale;
     p.kc = kcache_layer + size_t(seq) * KV * max_seq * hd;
     p.vc = vcache_layer + size_t(seq) * KV * max_seq * hd;
-    const dim3 grid((rows + 63) / 64, H);
+    const uint32_t n_rep = H / KV;
+    p.rep = (n_rep == 2 || n_rep == 4 || n_rep == 8) ? n_rep : 1;
+    const uint32_t qt = 128 / p.rep;
+    const dim3 grid(H / p.rep, (rows + qt - 1) / qt);
     const size_t smem = size_t(4) * 64 * (hd + 8) * 2;
-    if (hd == 64) {
-        prefill_attn_kernel<64><<<grid, 128, smem, stream>>>(p);
-    } else {
-        static bool configured[8] = {false};
-        int dev = 0;
-        MC_CUDA_CHECK(cudaGetDevice(&dev));
-        if (!configured[dev & 7]) {
-            MC_CUDA_CHECK(cudaFuncSetAttribute(prefill_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            configured[dev & 7] = true;
+    uint32_t sbits;
+    memcpy(&sbits, &scale, 4);
+    const bool pow2 = (sbits & 0x007fffffu) == 0 && scale > 1e-30f; // exact power of two (and far from the subnormal range)
+    auto launch = [&](auto kernel) {
+        if (smem > 48 * 1024) {
+            // once per device would do; the call is cheap and idempotent
+            MC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         }
-        prefill_attn_kernel<128><<<grid, 128, smem, stream>>>(p);
+        kernel<<<grid, 256, smem, stream>>>(p);
+    };
+    if (hd == 64) {
+        if (pow2) launch(prefill_attn_kernel<64, true>);
+        else launch(prefill_attn_kernel<64, false>);
+    } else {
+        if (pow2) launch(prefill_attn_kernel<128, true>);
+        else launch(prefill_attn_kernel<128, false>);
     }
     MC_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
+
+int decode_attn_gqa(cudaStream_t stream, const uint16_t* q, const uint16_t* kcache_layer, const uint16_t* vcache_layer, uint16_t* out, uint32_t rows,
+                    const int32_t* row_seq, const int32_t* row_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, float scale)
+{
+    MC_REQUIRE(decode_attn_gqa_supported(H, KV, hd), "batched decode attention: head_dim must be 64 or 128 and at most 8 query heads per KV head");
+    dattn_params p{};
+    p.q = q, p.kc = kcache_layer, p.vc = vcache_layer, p.out = out, p.row_seq = row_seq, p.row_pos = row_pos, p.H = H, p.KV = KV, p.max_seq = max_seq, p.scale = scale;
+    const dim3 grid(KV, rows);
+    const size_t smem = size_t(4) * 64 * (hd + 8) * 2 + 32 * sizeof(float);
+    uint32_t sbits;
+    memcpy(&sbits, &scale, 4);
+    const bool pow2 = (sbits & 0x007fffffu) == 0 && scale > 1e-30f;
+    auto launch = [&](auto kernel) {
+        if (smem > 48 * 1024) MC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        kernel<<<grid, 128, smem, stream>>>(p);
+    };
+    if (hd == 64) {
+        if (pow2) launch(decode_attn_gqa_kernel<64, true>);
+        else launch(decode_attn_gqa_kernel<64, false>);
+    } else {
+        if (pow2) launch(decode_attn_gqa_kernel<128, true>);
+        else launch(decode_attn_gqa_kernel<128, false>);
+    }
+    MC_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+bool decode_attn_gqa_supported(uint32_t H, uint32_t KV, uint32_t hd) { return (hd == 64 || hd == 128) && KV > 0 && H % KV == 0 && H / KV <= 8; }
 
 } // namespace tc
 } // namespace mc

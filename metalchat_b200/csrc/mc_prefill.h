@@ -19,12 +19,20 @@ int gemm(cudaStream_t stream, int sm_count, int mode, const uint16_t* X, uint32_
 
 int embed_rows(cudaStream_t stream, uint16_t* out, const uint16_t* table, const int32_t* ids, uint32_t rows, uint32_t D);
 int rmsnorm_rows(cudaStream_t stream, uint16_t* out, const uint16_t* x, const uint16_t* w, uint32_t rows, uint32_t D, float eps);
-// qkv [rows, (H + 2 KV) hd] -> q [rows, H hd] rotated, K/V cache rows [seq][kv][start_pos + row] of one layer
+// qkv [rows, (H + 2 KV) hd] -> q [rows, H hd] rotated, K/V cache rows [seq][kv][start_pos + row] of one layer;
+// with row_seq / row_pos (device arrays) every row carries its own sequence and position (batched decode)
 int rope_append(cudaStream_t stream, const uint16_t* qkv, uint16_t* q, uint16_t* kcache_layer, uint16_t* vcache_layer, const float* fcos, const float* fsin,
-                uint32_t rows, uint32_t seq, uint32_t start_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq);
+                uint32_t rows, uint32_t seq, uint32_t start_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, const int32_t* row_seq = nullptr,
+                const int32_t* row_pos = nullptr);
 // causal attention of `rows` consecutive positions of sequence `seq` against its cache (positions 0 .. start_pos + row)
 int prefill_attn(cudaStream_t stream, const uint16_t* q, const uint16_t* kcache_layer, const uint16_t* vcache_layer, uint16_t* out, uint32_t rows, uint32_t seq,
                  uint32_t start_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, float scale);
+
+// one decode step of `rows` sequences: row r attends keys 0 .. row_pos[r] of sequence row_seq[r]; the H / KV query heads of a KV head
+// share one pass over its cache (grouped-query attention)
+bool decode_attn_gqa_supported(uint32_t H, uint32_t KV, uint32_t hd);
+int decode_attn_gqa(cudaStream_t stream, const uint16_t* q, const uint16_t* kcache_layer, const uint16_t* vcache_layer, uint16_t* out, uint32_t rows,
+                    const int32_t* row_seq, const int32_t* row_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, float scale);
 
 } // namespace tc
 } // namespace mc
