@@ -851,6 +851,7 @@ void enqueue_rows_tc(mc_llama* m, launcher& L, uint32_t rows)
     uint16_t *x = m->x.as<uint16_t>(), *h = m->h.as<uint16_t>(), *n = m->dt_n.as<uint16_t>(), *qkv = m->dt_qkv.as<uint16_t>();
     uint16_t *q = m->q.as<uint16_t>(), *attn = m->attn.as<uint16_t>(), *z = m->z.as<uint16_t>();
     int* err = m->errflag.as<int>();
+    tc::set_pdl(L.pdl);
     auto count = [&](int k) { L.count += uint32_t(k), m->dev->launches.fetch_add(uint64_t(k)); };
     L.go(embed_kernel, dim3(rows), dim3(256), 0, x, D, (const void*)m->tok.w.p, (const float*)m->tok.scales.p, m->tok.fmt, D, c.vocab, m->ids.as<int32_t>());
     for (uint32_t li = 0; li < c.n_layers; li++) {
@@ -866,11 +867,8 @@ void enqueue_rows_tc(mc_llama* m, launcher& L, uint32_t rows)
         } else {
             const attn_params a = attn_params_of(m, li, 0);
             const size_t smem = attn_smem(m, kAttnCluster);
-            const bool pdl = L.pdl;
-            L.pdl = false; // the producer above is a plain launch
             if (hd == 64) L.go_cluster(attn_decode_kernel<64>, dim3(H * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
             else L.go_cluster(attn_decode_kernel<128>, dim3(H * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
-            L.pdl = pdl;
         }
         count(tc::gemm(s, sms, tc::GEMM_RESIDUAL, attn, QO, ly.wo.w.as<uint16_t>(), h, x, rows, D, QO, D, err));
         count(tc::rmsnorm_rows(s, n, h, ly.ffn_norm.as<uint16_t>(), rows, D, c.norm_eps));
@@ -897,10 +895,7 @@ void enqueue_decode_step(mc_llama* m, launcher& L, uint32_t n, const mc_sampler_
     }
     if (decode_tc_eligible(m, n)) {
         enqueue_rows_tc(m, L, n);
-        const bool pdl = L.pdl;
-        L.pdl = false;
         enqueue_sample(m, L, n, sc, advance);
-        L.pdl = pdl;
         return;
     }
     for (uint32_t r0 = 0; r0 < n; r0 += kMaxMB) {
@@ -1475,6 +1470,7 @@ void prefill_tc(mc_llama* m, uint32_t seq, const int32_t* ids, uint32_t len, uin
     int* err = m->errflag.as<int>();
     uint32_t launches = 0;
     launcher L{m, s, false};
+    tc::set_pdl(!(c.flags & MC_LLAMA_NO_PDL));
     for (uint32_t t0 = 0; t0 < len; t0 += cap) {
         const uint32_t rows = std::min(cap, len - t0), pos0 = start_pos + t0;
         MC_CUDA_CHECK(cudaMemcpyAsync(m->pf_ids.p, ids + t0, size_t(rows) * 4, cudaMemcpyHostToDevice, s));
@@ -1876,6 +1872,7 @@ mc_status mc_gemm_bf16(mc_device* dev, mc_buffer* y, mc_buffer* x, mc_buffer* w,
     const uint32_t ncols = mode == tc::GEMM_SWIGLU ? N / 2 : N;
     MC_REQUIRE(w->size >= size_t(N) * K * 2 && x->size >= size_t(M) * K * 2 && y->size >= size_t(M) * ncols * 2, "gemm_bf16: buffer too small");
     MC_REQUIRE(mode != tc::GEMM_RESIDUAL || (res && res->size >= size_t(M) * N * 2), "gemm_bf16: residual buffer missing or too small");
+    tc::set_pdl(false);
     dbuf err;
     err.alloc(4);
     cudaStream_t s = dev->stream;

@@ -64,6 +64,10 @@ __device__ __forceinline__ float block_sum_256(float v, float* scratch /* [8] */
     return t;
 }
 
+// programmatic dependent launch: let the next kernel of the stream start its prologue / wait for the previous kernel's results
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 constexpr int kTcBM = 128;      // prompt rows per tile (the M of the MMA = the 128 TMEM lanes)
 constexpr int kTcBK = 64;       // k per stage: 128 bytes per row = one swizzle atom, four MMAs of K = 16
 constexpr int kTcThreads = 192; // producer warp | MMA warp | 4 epilogue warps
@@ -172,24 +176,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     const uint32_t m_blocks = (p.M + kTcBM - 1) / kTcBM, n_blocks = (p.N + BN - 1) / BN;
     const uint32_t n_tiles = m_blocks * n_blocks, k_blocks = p.K / kTcBK;
 
+    pdl_trigger();
     if (warp == 0) {
         if (lane == 0) {
-            uint32_t it = 0;
-            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            // every tile walks k from its own starting block: CTAs that share an X (or W) tile would otherwise request the same L2
+            // lines in lockstep.  The start depends only on the 256-column group and the 128-row block of the outputs, so a row's
+            // bits do not depend on the tile width or on how many rows share the call.
+            const uint32_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+            const uint32_t total = my_tiles * k_blocks;
+            auto coords = [&](uint32_t it, uint32_t& kx, uint32_t& mrow, uint32_t& nrow) {
+                const uint32_t tile = blockIdx.x + (it / k_blocks) * gridDim.x, kb = it % k_blocks;
                 const uint32_t mb = tile % m_blocks, nb = tile / m_blocks;
-                // every tile walks k from its own starting block: CTAs that share an X (or W) tile would otherwise request the
-                // same L2 lines in lockstep, and a line's slice serves them one after the other (measured: ~540 cycles per k block
-                // for ANY tile size before the rotation).  The start depends only on the 256-column group and the 128-row block of
-                // the outputs, so a row's bits do not depend on the tile width or on how many rows share the call.
                 const uint32_t rot = (((nb * BN) >> 8) * 11u + mb * 5u) % k_blocks;
-                for (uint32_t kb = 0; kb < k_blocks; kb++, it++) {
-                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
-                    const uint32_t kk = kb + rot < k_blocks ? kb + rot : kb + rot - k_blocks;
-                    tc_wait(bar_empty + s * 8, ph ^ 1u, dead, p.err);
-                    mbar_expect_tx(bar_full + s * 8, A_BYTES + B_BYTES);
-                    tc_tma_load(a0 + s * A_BYTES, &tmX, kk * kTcBK, mb * kTcBM, bar_full + s * 8);
-                    tc_tma_load(b0 + s * B_BYTES, &tmW, kk * kTcBK, nb * BN, bar_full + s * 8);
-                }
+                kx = (kb + rot < k_blocks ? kb + rot : kb + rot - k_blocks) * kTcBK, mrow = mb * kTcBM, nrow = nb * BN;
+            };
+            // the weights do not depend on the previous kernel of the stream: the first ring-full of W tiles is requested before
+            // griddepcontrol.wait, the X tiles (its output) after
+            const uint32_t pre = total < uint32_t(STAGES) ? total : uint32_t(STAGES);
+            uint32_t kx, mrow, nrow;
+            for (uint32_t it = 0; it < pre; it++) {
+                coords(it, kx, mrow, nrow);
+                mbar_expect_tx(bar_full + it * 8, A_BYTES + B_BYTES);
+                tc_tma_load(b0 + it * B_BYTES, &tmW, kx, nrow, bar_full + it * 8);
+            }
+            pdl_sync();
+            for (uint32_t it = 0; it < pre; it++) {
+                coords(it, kx, mrow, nrow);
+                tc_tma_load(a0 + it * A_BYTES, &tmX, kx, mrow, bar_full + it * 8);
+            }
+            for (uint32_t it = pre; it < total; it++) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                coords(it, kx, mrow, nrow);
+                tc_wait(bar_empty + s * 8, ph ^ 1u, dead, p.err);
+                mbar_expect_tx(bar_full + s * 8, A_BYTES + B_BYTES);
+                tc_tma_load(a0 + s * A_BYTES, &tmX, kx, mrow, bar_full + s * 8);
+                tc_tma_load(b0 + s * B_BYTES, &tmW, kx, nrow, bar_full + s * 8);
             }
         }
     } else if (warp == 1) {
@@ -217,6 +238,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     } else {
         const uint32_t quarter = warp & 3u; // a warp reaches TMEM lanes 32 (warp % 4) .. +31
         uint32_t lt = 0;
+        pdl_sync(); // the residual rows and the output buffer belong to earlier kernels of the stream until they have finished
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, lt++) {
             const uint32_t mb = tile % m_blocks, nb = tile / m_blocks;
             const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
@@ -287,10 +309,183 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     }
 }
 
+// ---- decode-batch GEMM: split-K over a thread-block cluster --------------------------------------------------------------------
+// M <= 32 rows (a decode batch) against a matrix too small to give every SM a 256-row tile: an M = 128 MMA occupies the tensor
+// core for >= 128 cycles whatever its N (the A operand is read at 32 bytes per cycle), so the weight stream of an SM is
+// N x 32 bytes per 128 cycles -- wide weight tiles are mandatory, and parallelism has to come from K.  A cluster of `ks` CTAs
+// shares one 128-row weight tile: CTA r multiplies k blocks [r, r+1) * K/ks, parks its fp32 partial tile in shared memory, and
+// after one cluster barrier every CTA sums a 128/ks-column slice over the ranks IN RANK ORDER through distributed shared memory
+// (ld.shared::cluster), rounds once and applies the fused tail.  No global scratch, no atomics, deterministic.
+constexpr int kSkBN = 128, kSkRows = 32, kSkStages = 4, kSkRedPitch = kSkBN + 4;
+constexpr int kSkABytes = kSkRows * kTcBK * 2, kSkBBytes = kSkBN * kTcBK * 2;
+constexpr int kSkSmem = kTcHdr + kSkStages * kSkABytes + kSkStages * kSkBBytes + kSkRows * kSkRedPitch * 4 + 1024;
+static_assert(kSkStages * kSkABytes == kTcBM * kTcBK * 2, "the MMA reads a 128-row window from every A stage: it must stay inside the ring");
+
+__device__ __forceinline__ uint32_t cluster_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_size()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_barrier()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_cluster_f4(uint32_t local_addr, uint32_t rank)
+{
+    uint32_t ra;
+    float4 v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+    return v;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kTcThreads, 2) gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const gemm_tc_params p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t base = smem_u32(smem);
+    const uint32_t bar_full = base, bar_empty = base + 64, bar_tfull = base + 128, tmem_slot = base + 136;
+    volatile int* dead = reinterpret_cast<volatile int*>(smem + 144);
+    const uint32_t a0 = base + kTcHdr, b0 = a0 + kSkStages * kSkABytes;
+    float* red = reinterpret_cast<float*>(smem + kTcHdr + kSkStages * (kSkABytes + kSkBBytes)); // [32][kSkRedPitch] fp32 partial tile
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank(), ks = cluster_size();
+    const uint32_t n0 = (blockIdx.x / ks) * kSkBN;
+    const uint32_t kb_per = (p.K / kTcBK) / ks, kb0 = rank * kb_per;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kSkStages; s++) mbar_init(bar_full + s * 8, 1), mbar_init(bar_empty + s * 8, 1);
+        mbar_init(bar_tfull, 1);
+        *dead = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(uint32_t(kSkBN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + 136);
+
+    pdl_trigger();
+    if (warp == 0) {
+        if (lane == 0) {
+            // weight tiles first (independent of the previous kernel), then griddepcontrol.wait, then the X tiles
+            const uint32_t pre = kb_per < uint32_t(kSkStages) ? kb_per : uint32_t(kSkStages);
+            for (uint32_t kb = 0; kb < pre; kb++) {
+                mbar_expect_tx(bar_full + kb * 8, kSkABytes + kSkBBytes);
+                tc_tma_load(b0 + kb * kSkBBytes, &tmW, (kb0 + kb) * kTcBK, n0, bar_full + kb * 8);
+            }
+            pdl_sync();
+            for (uint32_t kb = 0; kb < pre; kb++) tc_tma_load(a0 + kb * kSkABytes, &tmX, (kb0 + kb) * kTcBK, 0, bar_full + kb * 8);
+            for (uint32_t kb = pre; kb < kb_per; kb++) {
+                const uint32_t s = kb % kSkStages, ph = (kb / kSkStages) & 1u;
+                tc_wait(bar_empty + s * 8, ph ^ 1u, dead, p.err);
+                mbar_expect_tx(bar_full + s * 8, kSkABytes + kSkBBytes);
+                tc_tma_load(a0 + s * kSkABytes, &tmX, (kb0 + kb) * kTcBK, 0, bar_full + s * 8);
+                tc_tma_load(b0 + s * kSkBBytes, &tmW, (kb0 + kb) * kTcBK, n0, bar_full + s * 8);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc_idesc(kTcBM, kSkBN);
+            for (uint32_t kb = 0; kb < kb_per; kb++) {
+                const uint32_t s = kb % kSkStages, ph = (kb / kSkStages) & 1u;
+                tc_wait(bar_full + s * 8, ph, dead, p.err);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // rows 32..127 of the A window are whatever the ring holds: they only reach accumulator lanes nobody reads
+                const uint64_t da = tc_smem_desc(a0 + s * kSkABytes), db = tc_smem_desc(b0 + s * kSkBBytes);
+#pragma unroll
+                for (uint32_t k = 0; k < kTcBK / 16; k++) tc_mma(tmem, da + k * 2, db + k * 2, idesc, (kb | k) != 0);
+                tc_commit(bar_empty + s * 8);
+            }
+            tc_commit(bar_tfull);
+        }
+    } else if (warp == 4) {
+        // TMEM lanes 0..31 (the batch rows) belong to the warp with warp % 4 == 0: park the fp32 partial tile in shared memory
+        tc_wait(bar_tfull, 0, dead, p.err);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (uint32_t cb = 0; cb < uint32_t(kSkBN); cb += 32) {
+            uint32_t v[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                  "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                  "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+                  "=r"(v[31])
+                : "r"(tmem + cb)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float4* dst = reinterpret_cast<float4*>(red + lane * kSkRedPitch + cb);
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncwarp();
+    __syncthreads();
+    cluster_barrier(); // every rank's partial tile is in its shared memory
+    pdl_sync();        // residual rows / output buffer: earlier kernels of the stream have finished
+
+    // this CTA joins columns [rank, rank + 1) * 128 / ks of the tile: 8 columns per thread and step, ranks in order
+    const uint32_t w8 = (kSkBN / ks) >> 3, col0 = rank * (kSkBN / ks);
+    const uint32_t red_addr = smem_u32(red);
+    for (uint32_t u = threadIdx.x; u < p.M * w8; u += kTcThreads) {
+        const uint32_t row = u / w8, c = col0 + (u % w8) * 8;
+        if (n0 + c >= p.N) continue;
+        float y[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        for (uint32_t r = 0; r < ks; r++) {
+            const uint32_t a = red_addr + (row * kSkRedPitch + c) * 4;
+            const float4 lo = ld_cluster_f4(a, r), hi = ld_cluster_f4(a + 16, r);
+            y[0] += lo.x, y[1] += lo.y, y[2] += lo.z, y[3] += lo.w, y[4] += hi.x, y[5] += hi.y, y[6] += hi.z, y[7] += hi.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) y[j] = rbf(y[j]); // the bmm output buffer is T (kernel/bmm.metal:76)
+        if (EPI == EPI_SWIGLU) {
+            const uint2 o = make_uint2(pack2(__fmul_rn(silu_bf16(y[0]), y[1]), __fmul_rn(silu_bf16(y[2]), y[3])),
+                                       pack2(__fmul_rn(silu_bf16(y[4]), y[5]), __fmul_rn(silu_bf16(y[6]), y[7])));
+            *reinterpret_cast<uint2*>(p.Y + size_t(row) * p.ldy + ((n0 + c) >> 1)) = o;
+        } else {
+            uint32_t o[4];
+            if (EPI == EPI_RESIDUAL) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(p.res + size_t(row) * p.ldy + n0 + c);
+                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) o[j] = pack2(__fadd_rn(bf_lo(rw[j]), y[2 * j]), __fadd_rn(bf_hi(rw[j]), y[2 * j + 1]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) o[j] = pack2(y[2 * j], y[2 * j + 1]);
+            }
+            *reinterpret_cast<uint4*>(p.Y + size_t(row) * p.ldy + n0 + c) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    cluster_barrier(); // nobody leaves while a peer may still read its partial tile
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(uint32_t(kSkBN)) : "memory");
+    }
+}
+
 // ---- the row-wise kernels around the prefill GEMMs --------------------------------------------------------------
 // gather the embedding rows of a prompt chunk (kernel/embedding.metal:25-70), bf16 table
 __global__ void __launch_bounds__(256) embed_rows_kernel(uint16_t* out, const uint16_t* table, const int32_t* ids, uint32_t D)
 {
+    pdl_trigger();
+    pdl_sync();
     const uint4* src = reinterpret_cast<const uint4*>(table + size_t(ids[blockIdx.x]) * D);
     uint4* dst = reinterpret_cast<uint4*>(out + size_t(blockIdx.x) * D);
     for (uint32_t k = threadIdx.x; k < D / 8; k += 256) dst[k] = src[k];
@@ -299,6 +494,8 @@ __global__ void __launch_bounds__(256) embed_rows_kernel(uint16_t* out, const ui
 __global__ void __launch_bounds__(256) rmsnorm_rows_kernel(uint16_t* out, const uint16_t* x, const uint16_t* w, uint32_t D, float eps)
 {
     __shared__ float scr[8];
+    pdl_trigger();
+    pdl_sync();
     const uint16_t* xr = x + size_t(blockIdx.x) * D;
     float part = 0.0f;
     for (uint32_t k = threadIdx.x * 8; k < D; k += 256 * 8) {
@@ -331,6 +528,8 @@ __global__ void __launch_bounds__(256) rope_append_kernel(const uint16_t* qkv, u
                                                           const float* fsin, const int32_t* row_seq, const int32_t* row_pos, uint32_t seq, uint32_t start_pos, uint32_t H,
                                                           uint32_t KV, uint32_t hd, uint32_t max_seq)
 {
+    pdl_trigger();
+    pdl_sync();
     // prompt: rows are consecutive positions of one sequence; batched decode: every row carries its own (sequence, position)
     const uint32_t row = blockIdx.x, half = hd >> 1, pos = row_pos ? uint32_t(row_pos[row]) : start_pos + row;
     if (row_seq) seq = uint32_t(row_seq[row]);
@@ -427,6 +626,8 @@ template <int HD, bool POW2> __global__ void __launch_bounds__(256, HD == 64 ? 2
     const uint16_t* kbase = p.kc + size_t(kvh) * p.max_seq * HD;
     const uint16_t* vbase = p.vc + size_t(kvh) * p.max_seq * HD;
 
+    pdl_trigger();
+    pdl_sync();
     // Q fragments (A operand, row-major 16 x HD)
     uint32_t qa[HD / 16][4];
     {
@@ -585,6 +786,8 @@ template <int HD, bool POW2> __global__ void __launch_bounds__(128) decode_attn_
     const uint32_t sbase = smem_u32(psm);
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const uint32_t kvh = blockIdx.x, row = blockIdx.y, n_rep = p.H / p.KV;
+    pdl_trigger();
+    pdl_sync();
     const uint32_t seq = uint32_t(p.row_seq[row]), pos = uint32_t(p.row_pos[row]);
     const uint32_t n_keys = pos + 1, n_tiles = (n_keys + 63) / 64;
     const uint16_t* kbase = p.kc + (size_t(seq) * p.KV + kvh) * p.max_seq * HD;

@@ -15,6 +15,30 @@ namespace tc {
 
 namespace {
 
+thread_local bool g_pdl = false; // programmatic dependent launch for the kernels launched by this thread (tc::set_pdl)
+
+// every kernel of this file goes through here: optional cluster dimension, optional programmatic stream serialization
+template <typename... KArgs, typename... Args>
+void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, unsigned cluster, Args&&... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    unsigned n = 0;
+    if (cluster > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster, attr[n].val.clusterDim.y = 1, attr[n].val.clusterDim.z = 1;
+        n++;
+    }
+    if (g_pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        n++;
+    }
+    cfg.attrs = attr, cfg.numAttrs = n;
+    MC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+}
+
 using encode_fn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -69,8 +93,7 @@ template <int BN, int EPI, int AROWS> void launch_gemm(cudaStream_t s, int sm_co
     }
     const uint32_t tiles = ((p.M + kTcBM - 1) / kTcBM) * ((p.N + BN - 1) / BN);
     const uint32_t grid = tiles < uint32_t(sm_count) ? tiles : uint32_t(sm_count);
-    kernel<<<grid, kTcThreads, tc_smem_bytes(BN, AROWS), s>>>(mx, mw, p);
-    MC_CUDA_CHECK(cudaGetLastError());
+    launch_k(kernel, dim3(grid), dim3(kTcThreads), tc_smem_bytes(BN, AROWS), s, 1, mx, mw, p);
 }
 template <int BN, int AROWS> void launch_gemm_epi(cudaStream_t s, int sm_count, int mode, const CUtensorMap& mx, const CUtensorMap& mw, const gemm_tc_params& p)
 {
@@ -106,7 +129,32 @@ void launch_gemm_bn(cudaStream_t stream, int sm_count, int mode, const uint16_t*
     }
 }
 
+// decode-batch GEMM split over k inside a cluster (gemm_tc_splitk_kernel): the smallest power-of-two split that gives every SM a CTA
+template <int EPI> void launch_splitk(cudaStream_t s, uint32_t ks, const CUtensorMap& mx, const CUtensorMap& mw, const gemm_tc_params& p)
+{
+    auto kernel = gemm_tc_splitk_kernel<EPI>;
+    static bool configured[8] = {false};
+    int dev = 0;
+    MC_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!configured[dev & 7]) {
+        MC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkSmem));
+        configured[dev & 7] = true;
+    }
+    launch_k(kernel, dim3(((p.N + kSkBN - 1) / kSkBN) * ks), dim3(kTcThreads), kSkSmem, s, ks, mx, mw, p);
+}
+uint32_t splitk_factor(uint32_t N, uint32_t K, int sm_count)
+{
+    static const int off = getenv("MC_TC_NO_SPLITK") != nullptr;
+    const uint32_t tiles = (N + kSkBN - 1) / kSkBN, k_blocks = K / kTcBK;
+    if (off || tiles * 2 >= 3 * uint32_t(sm_count)) return 0; // enough 256-row tiles for the persistent kernel
+    uint32_t ks = 1;
+    while (ks < 8 && tiles * ks < uint32_t(sm_count) && k_blocks % (ks * 2) == 0 && k_blocks / (ks * 2) >= 2) ks *= 2;
+    return ks;
+}
+
 } // namespace
+
+void set_pdl(bool on) { g_pdl = on; }
 
 bool gemm_supported(uint32_t N, uint32_t K, uint32_t ldx, uint32_t ldy)
 {
@@ -121,8 +169,17 @@ int gemm(cudaStream_t stream, int sm_count, int mode, const uint16_t* X, uint32_
                "prefill gemm: operands must be 16-byte aligned");
     gemm_tc_params p{};
     p.Y = Y, p.res = res, p.M = M, p.N = N, p.K = K, p.ldy = ldy, p.err = err;
-    // a decode batch of <= 32 rows stages only 32 rows of X per k block (see tc_stages)
-    if (M <= 32) launch_gemm_bn<32>(stream, sm_count, mode, X, ldx, W, p);
+    // a decode batch of <= 32 rows stages only 32 rows of X per k block (see tc_stages); small matrices are split over k
+    const uint32_t ks = M <= 32 ? splitk_factor(N, K, sm_count) : 0;
+    if (ks) {
+        const CUtensorMap mx = make_map(X, M, K, ldx, kSkRows), mw = make_map(W, N, K, K, kSkBN);
+        switch (mode) {
+        case GEMM_STORE: launch_splitk<EPI_NONE>(stream, ks, mx, mw, p); break;
+        case GEMM_RESIDUAL: launch_splitk<EPI_RESIDUAL>(stream, ks, mx, mw, p); break;
+        case GEMM_SWIGLU: launch_splitk<EPI_SWIGLU>(stream, ks, mx, mw, p); break;
+        default: throw error(MC_ERR_INVALID, "prefill gemm: unknown epilogue");
+        }
+    } else if (M <= 32) launch_gemm_bn<32>(stream, sm_count, mode, X, ldx, W, p);
     else launch_gemm_bn<128>(stream, sm_count, mode, X, ldx, W, p);
     return 1;
 }
@@ -130,23 +187,20 @@ int gemm(cudaStream_t stream, int sm_count, int mode, const uint16_t* X, uint32_
 int embed_rows(cudaStream_t stream, uint16_t* out, const uint16_t* table, const int32_t* ids, uint32_t rows, uint32_t D)
 {
     MC_REQUIRE(D % 8 == 0, "prefill embedding: dim must be a multiple of 8");
-    embed_rows_kernel<<<rows, 256, 0, stream>>>(out, table, ids, D);
-    MC_CUDA_CHECK(cudaGetLastError());
+    launch_k(embed_rows_kernel, dim3(rows), dim3(256), 0, stream, 1, out, table, ids, D);
     return 1;
 }
 int rmsnorm_rows(cudaStream_t stream, uint16_t* out, const uint16_t* x, const uint16_t* w, uint32_t rows, uint32_t D, float eps)
 {
     MC_REQUIRE(D % 8 == 0, "prefill rmsnorm: dim must be a multiple of 8");
-    rmsnorm_rows_kernel<<<rows, 256, 0, stream>>>(out, x, w, D, eps);
-    MC_CUDA_CHECK(cudaGetLastError());
+    launch_k(rmsnorm_rows_kernel, dim3(rows), dim3(256), 0, stream, 1, out, x, w, D, eps);
     return 1;
 }
 int rope_append(cudaStream_t stream, const uint16_t* qkv, uint16_t* q, uint16_t* kcache_layer, uint16_t* vcache_layer, const float* fcos, const float* fsin,
                 uint32_t rows, uint32_t seq, uint32_t start_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, const int32_t* row_seq, const int32_t* row_pos)
 {
-    rope_append_kernel<<<rows, 256, 0, stream>>>(qkv, (H + 2 * KV) * hd, q, kcache_layer, vcache_layer, fcos, fsin, row_seq, row_pos, seq, start_pos, H, KV, hd,
-                                                 max_seq);
-    MC_CUDA_CHECK(cudaGetLastError());
+    launch_k(rope_append_kernel, dim3(rows), dim3(256), 0, stream, 1, qkv, (H + 2 * KV) * hd, q, kcache_layer, vcache_layer, fcos, fsin, row_seq, row_pos, seq,
+             start_pos, H, KV, hd, max_seq);
     return 1;
 }
 int prefill_attn(cudaStream_t stream, const uint16_t* q, const uint16_t* kcache_layer, const uint16_t* vcache_layer, uint16_t* out, uint32_t rows, uint32_t seq,
@@ -170,7 +224,7 @@ int prefill_attn(cudaStream_t stream, const uint16_t* q, const uint16_t* kcache_
             // once per device would do; the call is cheap and idempotent
             MC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         }
-        kernel<<<grid, 256, smem, stream>>>(p);
+        launch_k(kernel, grid, dim3(256), smem, stream, 1, p);
     };
     if (hd == 64) {
         if (pow2) launch(prefill_attn_kernel<64, true>);
@@ -196,7 +250,7 @@ int decode_attn_gqa(cudaStream_t stream, const uint16_t* q, const uint16_t* kcac
     const bool pow2 = (sbits & 0x007fffffu) == 0 && scale > 1e-30f;
     auto launch = [&](auto kernel) {
         if (smem > 48 * 1024) MC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        kernel<<<grid, 128, smem, stream>>>(p);
+        launch_k(kernel, grid, dim3(128), smem, stream, 1, p);
     };
     if (hd == 64) {
         if (pow2) launch(decode_attn_gqa_kernel<64, true>);

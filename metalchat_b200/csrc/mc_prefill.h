@@ -9,6 +9,11 @@ namespace tc {
 
 enum { GEMM_STORE = 0, GEMM_RESIDUAL = 2, GEMM_SWIGLU = 3 };
 
+// Kernels launched by the calling thread from now on carry the programmatic-stream-serialization attribute: every kernel of this
+// file starts with griddepcontrol.launch_dependents and waits (griddepcontrol.wait) before it touches the previous kernel's results,
+// so its prologue -- barrier setup, TMEM allocation, the first ring-full of weight tiles -- overlaps the previous kernel's tail.
+void set_pdl(bool on);
+
 // shapes the tcgen05 GEMM accepts (TMA needs 16-byte row pitches; tiles are 64 wide in k and 32 wide in the epilogue)
 bool gemm_supported(uint32_t N, uint32_t K, uint32_t ldx, uint32_t ldy);
 
