@@ -134,7 +134,9 @@ enum {
     MC_LLAMA_NO_PDL = 1u << 2,    /* no programmatic dependent launch between decode kernels    */
     MC_LLAMA_MEGAKERNEL = 1u << 3, /* experimental: the whole decode step as ONE persistent kernel with grid barriers */
     MC_LLAMA_NO_STREAM = 1u << 4,  /* do not use the streaming persistent kernel (TMA weight ring): per-op kernels under a CUDA graph */
-    MC_LLAMA_NO_TC_PREFILL = 1u << 5 /* prompts go through the 4-row GEMV kernels instead of the tcgen05 GEMM path */
+    MC_LLAMA_NO_TC_PREFILL = 1u << 5, /* prompts go through the 4-row GEMV kernels instead of the tcgen05 GEMM path */
+    MC_LLAMA_NO_SHADOW = 1u << 6      /* quantised models: do not keep the resident bf16 image (2 bytes per weight) that the tensor-core
+                                         prompt / batch path multiplies; prompts and batches then take the packed GEMV kernels */
 };
 typedef struct mc_sampler_config {
     uint32_t mode;       /* 0 greedy argmax (lowest index on ties); 1 top-k -> nucleus -> multinomial (nn/sampling.h:306-316) */

@@ -67,6 +67,7 @@ struct dlinear {
     dbuf scales;           // fp32 [N,K/group] or [N]
     dbuf lora_b;           // bf16 [N, rank]
     dbuf q8, s32;          // staging until finalize: int8 [N,K] and fp32 [N,K/32] (or [N]) in the reference layout
+    dbuf wd;               // quantised models: resident bf16 image r(r(q) * r(s)) for the tensor-core prompt / batch path
     size_t stream_bytes() const { return w.bytes + scales.bytes + lora_b.bytes; }
 };
 
@@ -116,6 +117,7 @@ struct mc_llama {
     dbuf pf_ids, pf_x, pf_h, pf_n, pf_qkv, pf_q, pf_attn, pf_z;
     uint32_t pf_rows = 0;
     dbuf dt_n, dt_qkv;         // batched decode on the tensor cores: normed rows and un-rotated q|k|v rows of one step
+    dbuf pf_t, pf_ax, dt_t;    // quantised models: r(x . Wd^T) before the adaptor term, r(A . x)
     dbuf ids, pos, row_seq, uniforms, out_log, step_counter, pval, pidx, lora_ax, pack_bad, cand;
     int32_t* pinned = nullptr; // host staging: ids | pos | out
     float scale_bf16 = 0.0f;
@@ -129,13 +131,13 @@ struct mc_llama {
         if (pinned) cudaFreeHost(pinned);
         for (auto& l : layers) {
             for (dbuf* b : {&l.attn_norm, &l.ffn_norm, &l.lora_a_qkv, &l.lora_a_o, &l.lora_a_13, &l.lora_a_2}) b->release();
-            for (dlinear* d : {&l.wqkv, &l.wo, &l.w13, &l.w2}) d->w.release(), d->scales.release(), d->lora_b.release(), d->q8.release(), d->s32.release();
+            for (dlinear* d : {&l.wqkv, &l.wo, &l.w13, &l.w2}) d->w.release(), d->scales.release(), d->lora_b.release(), d->q8.release(), d->s32.release(), d->wd.release();
         }
-        for (dlinear* d : {&tok, &out}) d->w.release(), d->scales.release(), d->lora_b.release(), d->q8.release(), d->s32.release();
+        for (dlinear* d : {&tok, &out}) d->w.release(), d->scales.release(), d->lora_b.release(), d->q8.release(), d->s32.release(), d->wd.release();
         for (int k = 0; k < kTpMaxWorld; k++)
             if (tp_peer_base[k] && uint32_t(k) != cfg.tp_rank) cudaIpcCloseMemHandle(tp_peer_base[k]);
         for (dbuf* b : {&st_ll, &st_timing, &layer_arena, &bar, &errflag, &mega_timing, &tp_region, &tp_local, &norm, &fcos, &fsin, &kcache, &vcache, &x, &h, &q, &attn, &z, &logits, &logits_tmp, &hidden_save, &io_in, &io_out, &ids, &pos, &row_seq,
-                        &uniforms, &out_log, &step_counter, &pval, &pidx, &lora_ax, &pack_bad, &cand, &pf_ids, &pf_x, &pf_h, &pf_n, &pf_qkv, &pf_q, &pf_attn, &pf_z, &dt_n, &dt_qkv})
+                        &uniforms, &out_log, &step_counter, &pval, &pidx, &lora_ax, &pack_bad, &cand, &pf_ids, &pf_x, &pf_h, &pf_n, &pf_qkv, &pf_q, &pf_attn, &pf_z, &dt_n, &dt_qkv, &pf_t, &pf_ax, &dt_t})
             b->release();
     }
 };
@@ -823,6 +825,29 @@ void enqueue_sample(mc_llama* m, launcher& L, uint32_t rows, const mc_sampler_co
          kArgmaxBlocks, m->ids.as<int32_t>(), m->pos.as<int32_t>(), m->out_log.as<int32_t>(), m->step_counter.as<int32_t>(), rows, advance);
 }
 
+// One linear of a block on the tensor-core path.  bf16 models: a single GEMM with the fused tail.  QLoRA models: the GEMM runs on the
+// resident bf16 image and stores r(x . Wd^T); the adaptor term and the tail follow (quantization/lora.h:115-122):
+//   y = r(r(x . Wd^T) + r(r(B . r(A . x)) * r(scale))), then residual add / SiLU*mul / plain store.
+struct tc_scratch {
+    uint16_t* t;   // [rows, max N] r(x . Wd^T)
+    uint16_t* ax;  // [rows, 3 * rank]
+};
+uint32_t tc_linear(mc_llama* m, cudaStream_t s, int mode, const uint16_t* X, uint32_t ldx, const dlinear& d, const dbuf& lora_a, uint32_t a_rows, uint32_t slices,
+                   uint16_t* Y, const uint16_t* res, uint32_t rows, uint32_t N, uint32_t K, uint32_t ldy, const tc_scratch& sc)
+{
+    const mc_llama_config& c = m->cfg;
+    const int sms = m->dev->prop.multiProcessorCount;
+    int* err = m->errflag.as<int>();
+    if (!c.quant) return uint32_t(tc::gemm(s, sms, mode, X, ldx, d.w.as<uint16_t>(), Y, res, rows, N, K, ldy, err));
+    uint32_t n = 0;
+    const uint32_t ax_ld = 3 * c.lora_rank;
+    n += tc::lora_ax_rows(s, sc.ax, ax_ld, X, ldx, lora_a.as<uint16_t>(), rows, a_rows, K);
+    n += tc::gemm(s, sms, tc::GEMM_STORE, X, ldx, d.wd.as<uint16_t>(), sc.t, nullptr, rows, N, K, N, err);
+    n += tc::lora_epilogue(s, mode, sc.t, Y, res, sc.ax, ax_ld, d.lora_b.as<uint16_t>(), rows, N, ldy, c.lora_rank, slices, m->Hl * c.head_dim,
+                           (m->Hl + m->KVl) * c.head_dim, bf16_bits_to_f32(f32_to_bf16_bits(c.lora_scale)));
+    return n;
+}
+
 // ---- batched decode on the tensor cores -------------------------------------------------------------------------------------
 // Many sequences per step (BASELINE.json "batch 32"): every linear of the step is ONE tcgen05 GEMM over all rows, so the
 // weights are streamed once per step instead of once per 4 rows; attention stays the per-(row, head) cluster kernel.
@@ -837,7 +862,8 @@ uint32_t decode_tc_min_rows()
 bool decode_tc_eligible(const mc_llama* m, uint32_t n)
 {
     const mc_llama_config& c = m->cfg;
-    if ((c.flags & MC_LLAMA_NO_TC_PREFILL) || c.quant || c.tp_world != 1 || m->tok.fmt != WF_BF16 || n < decode_tc_min_rows() || !m->dt_n.p) return false;
+    if ((c.flags & MC_LLAMA_NO_TC_PREFILL) || c.tp_world != 1 || n < decode_tc_min_rows() || !m->dt_n.p) return false;
+    if (c.quant && (!m->layers[0].wqkv.wd.p || !m->out.wd.p || c.lora_rank % 2 != 0)) return false;
     const uint32_t D = c.dim, QO = m->Hl * c.head_dim, QKV = (m->Hl + 2 * m->KVl) * c.head_dim, F = m->Fl;
     return tc::gemm_supported(QKV, D, D, QKV) && tc::gemm_supported(D, QO, QO, D) && tc::gemm_supported(2 * F, D, D, F) && tc::gemm_supported(D, F, F, D) &&
            tc::gemm_supported(m->Vl, D, D, m->Vl);
@@ -850,6 +876,8 @@ void enqueue_rows_tc(mc_llama* m, launcher& L, uint32_t rows)
     const int sms = m->dev->prop.multiProcessorCount;
     uint16_t *x = m->x.as<uint16_t>(), *h = m->h.as<uint16_t>(), *n = m->dt_n.as<uint16_t>(), *qkv = m->dt_qkv.as<uint16_t>();
     uint16_t *q = m->q.as<uint16_t>(), *attn = m->attn.as<uint16_t>(), *z = m->z.as<uint16_t>();
+    const tc_scratch sc{m->dt_t.as<uint16_t>(), m->lora_ax.as<uint16_t>()};
+    const uint32_t rank = c.lora_rank;
     int* err = m->errflag.as<int>();
     tc::set_pdl(L.pdl);
     auto count = [&](int k) { L.count += uint32_t(k), m->dev->launches.fetch_add(uint64_t(k)); };
@@ -859,7 +887,7 @@ void enqueue_rows_tc(mc_llama* m, launcher& L, uint32_t rows)
         uint16_t* kc = m->kcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
         uint16_t* vc = m->vcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
         count(tc::rmsnorm_rows(s, n, x, ly.attn_norm.as<uint16_t>(), rows, D, c.norm_eps));
-        count(tc::gemm(s, sms, tc::GEMM_STORE, n, D, ly.wqkv.w.as<uint16_t>(), qkv, nullptr, rows, QKV, D, QKV, err));
+        count(tc_linear(m, s, tc::GEMM_STORE, n, D, ly.wqkv, ly.lora_a_qkv, 3 * rank, 3, qkv, nullptr, rows, QKV, D, QKV, sc));
         count(tc::rope_append(s, qkv, q, kc, vc, m->fcos.as<float>(), m->fsin.as<float>(), rows, 0, 0, H, KV, hd, c.max_seq_len, m->row_seq.as<int32_t>(),
                               m->pos.as<int32_t>()));
         if (tc::decode_attn_gqa_supported(H, KV, hd)) {
@@ -870,14 +898,15 @@ void enqueue_rows_tc(mc_llama* m, launcher& L, uint32_t rows)
             if (hd == 64) L.go_cluster(attn_decode_kernel<64>, dim3(H * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
             else L.go_cluster(attn_decode_kernel<128>, dim3(H * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
         }
-        count(tc::gemm(s, sms, tc::GEMM_RESIDUAL, attn, QO, ly.wo.w.as<uint16_t>(), h, x, rows, D, QO, D, err));
+        count(tc_linear(m, s, tc::GEMM_RESIDUAL, attn, QO, ly.wo, ly.lora_a_o, rank, 1, h, x, rows, D, QO, D, sc));
         count(tc::rmsnorm_rows(s, n, h, ly.ffn_norm.as<uint16_t>(), rows, D, c.norm_eps));
-        count(tc::gemm(s, sms, tc::GEMM_SWIGLU, n, D, ly.w13.w.as<uint16_t>(), z, nullptr, rows, 2 * F, D, F, err));
-        count(tc::gemm(s, sms, tc::GEMM_RESIDUAL, z, F, ly.w2.w.as<uint16_t>(), x, h, rows, D, F, D, err));
+        count(tc_linear(m, s, tc::GEMM_SWIGLU, n, D, ly.w13, ly.lora_a_13, 2 * rank, 2, z, nullptr, rows, 2 * F, D, F, sc));
+        count(tc_linear(m, s, tc::GEMM_RESIDUAL, z, F, ly.w2, ly.lora_a_2, rank, 1, x, h, rows, D, F, D, sc));
     }
     count(tc::rmsnorm_rows(s, n, x, m->norm.as<uint16_t>(), rows, D, c.norm_eps));
-    const dlinear& hw = m->tied ? m->tok : m->out;
-    count(tc::gemm(s, sms, tc::GEMM_STORE, n, D, hw.w.as<uint16_t>(), m->logits.as<uint16_t>(), nullptr, rows, m->Vl, D, m->Vl, err));
+    // vocabulary projection: the (tied) bf16 table, or the cached bf16 image of the int8 output matrix (quantization/linear.h:50-53)
+    const uint16_t* head_w = c.quant ? m->out.wd.as<uint16_t>() : (m->tied ? m->tok : m->out).w.as<uint16_t>();
+    count(tc::gemm(s, sms, tc::GEMM_STORE, n, D, head_w, m->logits.as<uint16_t>(), nullptr, rows, m->Vl, D, m->Vl, err));
 }
 
 // one decode step for rows [0, n): forward in chunks of kMaxMB rows, then sample
@@ -1248,9 +1277,10 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
     m->x.alloc(size_t(R) * D * 2), m->h.alloc(size_t(R) * D * 2);
     m->q.alloc(size_t(R) * m->Hl * hd * 2), m->attn.alloc(size_t(R) * m->Hl * hd * 2);
     m->z.alloc(size_t(R) * m->Fl * 2);
-    if (!c.quant && c.tp_world == 1 && c.n_seqs >= decode_tc_min_rows()) {
+    if (c.tp_world == 1 && c.n_seqs >= decode_tc_min_rows()) {
         m->dt_n.alloc(size_t(R) * D * 2);
         m->dt_qkv.alloc(size_t(R) * (m->Hl + 2 * m->KVl) * hd * 2);
+        if (c.quant) m->dt_t.alloc(size_t(R) * std::max(std::max((m->Hl + 2 * m->KVl) * hd, 2 * m->Fl), D) * 2);
     }
     {
         // tagged-word exchange buffers of the streaming kernel (8 bytes per word = two bf16 + tag)
@@ -1400,6 +1430,21 @@ mc_status mc_llama_finalize(mc_llama* m)
             MC_CUDA_CHECK(cudaMemset(m->pack_bad.p, 0, 4));
             throw error(MC_ERR_INVALID, "quantised weights outside the int4 range [-8, 7] cannot be packed (quantization/lora.h stores int4-range values in int8)");
         }
+        // resident bf16 image of every quantised matrix for the tensor-core prompt / batch path (the reference dequantises the whole
+        // matrix on every call, quantization/lora.h:115, and caches the output projection, quantization/linear.h:50-53)
+        if (m->cfg.tp_world == 1 && !(m->cfg.flags & MC_LLAMA_NO_SHADOW)) {
+            for (dlayer& ly : m->layers)
+                for (dlinear* d : {&ly.wqkv, &ly.wo, &ly.w13, &ly.w2}) {
+                    if (!d->q8.p) continue;
+                    d->wd.alloc(size_t(d->N) * d->K * 2);
+                    tc::dequant_group(s, d->wd.as<uint16_t>(), d->q8.as<int8_t>(), d->s32.as<float>(), d->N, d->K, m->cfg.group_size);
+                }
+            if (m->out.q8.p) {
+                m->out.wd.alloc(size_t(m->out.N) * m->out.K * 2);
+                tc::dequant_group(s, m->out.wd.as<uint16_t>(), m->out.q8.as<int8_t>(), m->out.scales.as<float>(), m->out.N, m->out.K, m->out.K);
+            }
+            MC_CUDA_CHECK(cudaStreamSynchronize(s));
+        }
         for (dlayer& ly : m->layers)
             for (dlinear* d : {&ly.wqkv, &ly.wo, &ly.w13, &ly.w2}) d->q8.release(), d->s32.release();
         m->out.q8.release();
@@ -1423,6 +1468,10 @@ mc_status mc_llama_weight_bytes(mc_llama* m, uint64_t* streamed_per_step, uint64
     res = stream + m->kcache.bytes + m->vcache.bytes;
     if (!m->tied) res += m->tok.stream_bytes();
     else res += m->tok.w.bytes - size_t(m->Vl) * m->cfg.dim * 2;
+    // quantised models: the resident bf16 image used by the tensor-core prompt / batch path (not part of the batch-1 stream)
+    for (auto& ly : m->layers)
+        for (const dlinear* d : {&ly.wqkv, &ly.wo, &ly.w13, &ly.w2}) res += d->wd.bytes;
+    res += m->out.wd.bytes;
     if (streamed_per_step) *streamed_per_step = stream;
     if (resident) *resident = res;
     MC_API_END
@@ -1446,7 +1495,8 @@ bool prefill_tc_eligible(const mc_llama* m, uint32_t len)
 {
     const mc_llama_config& c = m->cfg;
     static const bool env_off = getenv("MC_NO_TC_PREFILL") != nullptr;
-    if (env_off || (c.flags & MC_LLAMA_NO_TC_PREFILL) || c.quant || c.tp_world != 1 || m->tok.fmt != WF_BF16 || len < prefill_tc_min_rows()) return false;
+    if (env_off || (c.flags & MC_LLAMA_NO_TC_PREFILL) || c.tp_world != 1 || len < prefill_tc_min_rows()) return false;
+    if (c.quant && (!m->layers[0].wqkv.wd.p || c.lora_rank % 2 != 0)) return false; // quantised: needs the bf16 image (mc_llama_finalize)
     if (c.head_dim != 64 && c.head_dim != 128) return false;
     const uint32_t D = c.dim, QO = m->Hl * c.head_dim, QKV = (m->Hl + 2 * m->KVl) * c.head_dim, F = m->Fl;
     return tc::gemm_supported(QKV, D, D, QKV) && tc::gemm_supported(D, QO, QO, D) && tc::gemm_supported(2 * F, D, D, F) && tc::gemm_supported(D, F, F, D);
@@ -1458,15 +1508,18 @@ void prefill_tc(mc_llama* m, uint32_t seq, const int32_t* ids, uint32_t len, uin
     cudaStream_t s = m->dev->stream;
     const int sms = m->dev->prop.multiProcessorCount;
     const uint32_t cap = std::min<uint32_t>(kPfChunk, c.max_seq_len);
+    const uint32_t rank = c.lora_rank, maxN = std::max(std::max(QKV, 2 * F), D);
     if (m->pf_rows < cap) {
         m->pf_ids.alloc(size_t(cap) * 4);
         m->pf_x.alloc(size_t(cap) * D * 2), m->pf_h.alloc(size_t(cap) * D * 2), m->pf_n.alloc(size_t(cap) * D * 2);
         m->pf_qkv.alloc(size_t(cap) * QKV * 2), m->pf_q.alloc(size_t(cap) * QO * 2), m->pf_attn.alloc(size_t(cap) * QO * 2);
         m->pf_z.alloc(size_t(cap) * F * 2);
+        if (c.quant) m->pf_t.alloc(size_t(cap) * maxN * 2), m->pf_ax.alloc(size_t(cap) * 3 * rank * 2);
         m->pf_rows = cap;
     }
     uint16_t *x = m->pf_x.as<uint16_t>(), *h = m->pf_h.as<uint16_t>(), *n = m->pf_n.as<uint16_t>(), *qkv = m->pf_qkv.as<uint16_t>();
     uint16_t *q = m->pf_q.as<uint16_t>(), *attn = m->pf_attn.as<uint16_t>(), *z = m->pf_z.as<uint16_t>();
+    const tc_scratch sc{m->pf_t.as<uint16_t>(), m->pf_ax.as<uint16_t>()};
     int* err = m->errflag.as<int>();
     uint32_t launches = 0;
     launcher L{m, s, false};
@@ -1474,28 +1527,39 @@ void prefill_tc(mc_llama* m, uint32_t seq, const int32_t* ids, uint32_t len, uin
     for (uint32_t t0 = 0; t0 < len; t0 += cap) {
         const uint32_t rows = std::min(cap, len - t0), pos0 = start_pos + t0;
         MC_CUDA_CHECK(cudaMemcpyAsync(m->pf_ids.p, ids + t0, size_t(rows) * 4, cudaMemcpyHostToDevice, s));
-        launches += tc::embed_rows(s, x, m->tok.w.as<uint16_t>(), m->pf_ids.as<int32_t>(), rows, D);
+        // embedding gather (bf16 rows, or int8 rows with one scale: quantization/lora.h:160-170)
+        L.go(embed_kernel, dim3(rows), dim3(256), 0, x, D, (const void*)m->tok.w.p, (const float*)m->tok.scales.p, m->tok.fmt, D, c.vocab,
+             (const int32_t*)m->pf_ids.as<int32_t>());
         for (uint32_t li = 0; li < c.n_layers; li++) {
             dlayer& ly = m->layers[li];
             uint16_t* kc = m->kcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
             uint16_t* vc = m->vcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
             launches += tc::rmsnorm_rows(s, n, x, ly.attn_norm.as<uint16_t>(), rows, D, c.norm_eps);
-            launches += tc::gemm(s, sms, tc::GEMM_STORE, n, D, ly.wqkv.w.as<uint16_t>(), qkv, nullptr, rows, QKV, D, QKV, err);
+            launches += tc_linear(m, s, tc::GEMM_STORE, n, D, ly.wqkv, ly.lora_a_qkv, 3 * rank, 3, qkv, nullptr, rows, QKV, D, QKV, sc);
             launches += tc::rope_append(s, qkv, q, kc, vc, m->fcos.as<float>(), m->fsin.as<float>(), rows, seq, pos0, H, KV, hd, c.max_seq_len);
             launches += tc::prefill_attn(s, q, kc, vc, attn, rows, seq, pos0, H, KV, hd, c.max_seq_len, m->scale_bf16);
-            launches += tc::gemm(s, sms, tc::GEMM_RESIDUAL, attn, QO, ly.wo.w.as<uint16_t>(), h, x, rows, D, QO, D, err);
+            launches += tc_linear(m, s, tc::GEMM_RESIDUAL, attn, QO, ly.wo, ly.lora_a_o, rank, 1, h, x, rows, D, QO, D, sc);
             launches += tc::rmsnorm_rows(s, n, h, ly.ffn_norm.as<uint16_t>(), rows, D, c.norm_eps);
-            launches += tc::gemm(s, sms, tc::GEMM_SWIGLU, n, D, ly.w13.w.as<uint16_t>(), z, nullptr, rows, 2 * F, D, F, err);
-            launches += tc::gemm(s, sms, tc::GEMM_RESIDUAL, z, F, ly.w2.w.as<uint16_t>(), x, h, rows, D, F, D, err);
+            launches += tc_linear(m, s, tc::GEMM_SWIGLU, n, D, ly.w13, ly.lora_a_13, 2 * rank, 2, z, nullptr, rows, 2 * F, D, F, sc);
+            launches += tc_linear(m, s, tc::GEMM_RESIDUAL, z, F, ly.w2, ly.lora_a_2, rank, 1, x, h, rows, D, F, D, sc);
         }
         if (t0 + rows >= len) {
             // only the last position is projected (nn/llama.h:128-133)
             const uint16_t* last = x + size_t(rows - 1) * D;
-            gemv_launch<PRO_RMSNORM, EPI_NONE>(L, head_params(m, last, 1, m->logits.as<uint16_t>() + size_t(seq) * m->Vl));
+            uint16_t* dst = m->logits.as<uint16_t>() + size_t(seq) * m->Vl;
+            if (c.quant) {
+                qgemv_params qh{};
+                qh.g = head_params(m, last, 1, dst);
+                qh.scales = m->out.scales.p; // int8 rows with one scale per row, no adaptor (quantization/linear.h:17-64)
+                qgemv_launch<WF_W8ROW, PRO_RMSNORM, EPI_NONE>(L, qh);
+            } else {
+                gemv_launch<PRO_RMSNORM, EPI_NONE>(L, head_params(m, last, 1, dst));
+            }
             MC_CUDA_CHECK(cudaMemcpyAsync(m->hidden_save.as<uint16_t>() + size_t(seq) * D, last, size_t(D) * 2, cudaMemcpyDeviceToDevice, s));
         }
         MC_CUDA_CHECK(cudaStreamSynchronize(s)); // pf_ids is reused by the next chunk; `ids` may be pageable
     }
+    (void)err;
     m->dev->launches.fetch_add(launches);
     int flag = 0;
     MC_CUDA_CHECK(cudaMemcpy(&flag, err, 4, cudaMemcpyDeviceToHost));

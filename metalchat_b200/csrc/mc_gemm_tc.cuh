@@ -900,5 +900,92 @@ template <int HD, bool POW2> __global__ void __launch_bounds__(128) decode_attn_
     }
 }
 
+// ---- QLoRA models on the tensor-core path --------------------------------------------------------------------------------------
+// The reference dequantises the whole matrix to bf16 on every call, w = r(r(q) * r(s)) (quantization/lora.h:115, kernel/mul.metal:76-77),
+// and quantization::linear caches its dequantised weight (quantization/linear.h:50-53).  For prompts and decode batches the engine
+// keeps that bf16 image resident (a shadow of the packed int4 stream that batch-1 decode reads) and runs the GEMMs above on it; the
+// adaptor term y = r(y + r(r(B . r(A . x)) * r(scale))) is applied by the two small kernels below with the reference's rounding points.
+__global__ void __launch_bounds__(256) dequant_group_kernel(uint16_t* out, const int8_t* q, const float* scales, uint64_t n8, uint32_t K, uint32_t group)
+{
+    // 8 weights per thread (one group of 32 spans 4 threads); scales [N, K / group]
+    for (uint64_t i = uint64_t(blockIdx.x) * 256 + threadIdx.x; i < n8; i += uint64_t(gridDim.x) * 256) {
+        const uint64_t e = i * 8, row = e / K;
+        const uint32_t k = uint32_t(e - row * K);
+        const float s = rbf(scales[row * (K / group) + k / group]);
+        const uint2 v = *reinterpret_cast<const uint2*>(q + e);
+        const uint32_t w[2] = {v.x, v.y};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float a = float(int8_t((w[j >> 1] >> ((j & 1) * 16)) & 0xff)), b = float(int8_t((w[j >> 1] >> ((j & 1) * 16 + 8)) & 0xff));
+            o[j] = pack2(__fmul_rn(a, s), __fmul_rn(b, s));
+        }
+        *reinterpret_cast<uint4*>(out + e) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+// ax[m, j] = r(sum_k x[m, k] * A[j, k])  (the adaptor's first bmm, kernel/bmm.metal:76); grid = rows, 8 warps deal the R adaptor rows
+__global__ void __launch_bounds__(256) lora_ax_rows_kernel(uint16_t* ax, uint32_t ax_ld, const uint16_t* x, uint32_t ldx, const uint16_t* A, uint32_t R, uint32_t K)
+{
+    pdl_trigger();
+    pdl_sync();
+    const uint32_t row = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint16_t* xr = x + size_t(row) * ldx;
+    for (uint32_t j = warp; j < R; j += 8) {
+        const uint16_t* ar = A + size_t(j) * K;
+        float acc = 0.0f;
+        for (uint32_t k = lane * 8; k < K; k += 256) {
+            const uint4 xv = *reinterpret_cast<const uint4*>(xr + k), av = *reinterpret_cast<const uint4*>(ar + k);
+            acc = fmaf(bf_lo(xv.x), bf_lo(av.x), acc), acc = fmaf(bf_hi(xv.x), bf_hi(av.x), acc);
+            acc = fmaf(bf_lo(xv.y), bf_lo(av.y), acc), acc = fmaf(bf_hi(xv.y), bf_hi(av.y), acc);
+            acc = fmaf(bf_lo(xv.z), bf_lo(av.z), acc), acc = fmaf(bf_hi(xv.z), bf_hi(av.z), acc);
+            acc = fmaf(bf_lo(xv.w), bf_lo(av.w), acc), acc = fmaf(bf_hi(xv.w), bf_hi(av.w), acc);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) ax[size_t(row) * ax_ld + j] = f32_to_bf16_bits(acc);
+    }
+}
+// y2 = r(y + r(r(B . ax) * scale))  (quantization/lora.h:115-122), then the fused tail of the linear; thread = two adjacent columns.
+//   slices: 1 = one adaptor, 2 = w1|w3 row-interleaved (column parity picks the adaptor), 3 = q|k|v (column ranges pick it)
+struct lora_epi_params {
+    const uint16_t* y;   // [rows, N] r(x . Wd^T)
+    uint16_t* out;       // EPI_NONE / EPI_RESIDUAL: [rows, ldo]; EPI_SWIGLU: [rows, ldo] with N/2 columns (may alias y only for EPI_NONE)
+    const uint16_t* res; // EPI_RESIDUAL
+    const uint16_t* ax;  // [rows, ax_ld]
+    const uint16_t* B;   // [N, rank]
+    uint32_t N, ldo, ax_ld, rank, slices, cols0, cols1;
+    float scale;         // r(lora scale)
+};
+template <int EPI> __global__ void __launch_bounds__(256) lora_epilogue_kernel(const lora_epi_params p)
+{
+    pdl_trigger();
+    pdl_sync();
+    const uint32_t row = blockIdx.y, n = (blockIdx.x * 256 + threadIdx.x) * 2;
+    if (n >= p.N) return;
+    const uint32_t yy = *reinterpret_cast<const uint32_t*>(p.y + size_t(row) * p.N + n);
+    float v[2] = {bf_lo(yy), bf_hi(yy)};
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        const uint32_t col = n + c;
+        const uint32_t slice = p.slices == 2 ? (col & 1u) : (p.slices == 3 ? (col < p.cols0 ? 0u : (col < p.cols1 ? 1u : 2u)) : 0u);
+        const uint16_t* a = p.ax + size_t(row) * p.ax_ld + slice * p.rank;
+        const uint16_t* b = p.B + size_t(col) * p.rank;
+        float l = 0.0f;
+        for (uint32_t j = 0; j < p.rank; j += 2) {
+            const uint32_t av = *reinterpret_cast<const uint32_t*>(a + j), bv = *reinterpret_cast<const uint32_t*>(b + j);
+            l = fmaf(bf_lo(av), bf_lo(bv), l), l = fmaf(bf_hi(av), bf_hi(bv), l);
+        }
+        v[c] = rbf(__fadd_rn(v[c], rbf(__fmul_rn(rbf(l), p.scale))));
+    }
+    if (EPI == EPI_SWIGLU) {
+        p.out[size_t(row) * p.ldo + (n >> 1)] = f32_to_bf16_bits(__fmul_rn(silu_bf16(v[0]), v[1])); // (nn/transformer.h:57-59)
+    } else if (EPI == EPI_RESIDUAL) {
+        const uint32_t r = *reinterpret_cast<const uint32_t*>(p.res + size_t(row) * p.ldo + n);
+        *reinterpret_cast<uint32_t*>(p.out + size_t(row) * p.ldo + n) = pack2(__fadd_rn(bf_lo(r), v[0]), __fadd_rn(bf_hi(r), v[1]));
+    } else {
+        *reinterpret_cast<uint32_t*>(p.out + size_t(row) * p.ldo + n) = pack2(v[0], v[1]);
+    }
+}
+
 } // namespace tc
 } // namespace mc

@@ -6,6 +6,7 @@
 #include "mc_gemm_tc.cuh"
 #include "mc_prefill.h"
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -263,6 +264,38 @@ int decode_attn_gqa(cudaStream_t stream, const uint16_t* q, const uint16_t* kcac
     return 1;
 }
 bool decode_attn_gqa_supported(uint32_t H, uint32_t KV, uint32_t hd) { return (hd == 64 || hd == 128) && KV > 0 && H % KV == 0 && H / KV <= 8; }
+
+int dequant_group(cudaStream_t stream, uint16_t* out, const int8_t* q, const float* scales, uint32_t N, uint32_t K, uint32_t group)
+{
+    MC_REQUIRE(K % 8 == 0 && group % 8 == 0 && K % group == 0, "dequant: K and the group size must be multiples of 8");
+    const uint64_t n8 = uint64_t(N) * K / 8;
+    const unsigned blocks = unsigned(std::min<uint64_t>((n8 + 255) / 256, 148 * 16));
+    dequant_group_kernel<<<blocks, 256, 0, stream>>>(out, q, scales, n8, K, group);
+    MC_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+int lora_ax_rows(cudaStream_t stream, uint16_t* ax, uint32_t ax_ld, const uint16_t* x, uint32_t ldx, const uint16_t* A, uint32_t rows, uint32_t R, uint32_t K)
+{
+    MC_REQUIRE(K % 256 == 0 && ldx % 8 == 0, "lora: K must be a multiple of 256");
+    launch_k(lora_ax_rows_kernel, dim3(rows), dim3(256), 0, stream, 1, ax, ax_ld, x, ldx, A, R, K);
+    return 1;
+}
+int lora_epilogue(cudaStream_t stream, int mode, const uint16_t* y, uint16_t* out, const uint16_t* res, const uint16_t* ax, uint32_t ax_ld, const uint16_t* B,
+                  uint32_t rows, uint32_t N, uint32_t ldo, uint32_t rank, uint32_t slices, uint32_t cols0, uint32_t cols1, float scale)
+{
+    MC_REQUIRE(N % 2 == 0 && rank % 2 == 0 && ldo % 2 == 0, "lora epilogue: N, rank and the output pitch must be even");
+    lora_epi_params p{};
+    p.y = y, p.out = out, p.res = res, p.ax = ax, p.B = B, p.N = N, p.ldo = ldo, p.ax_ld = ax_ld, p.rank = rank, p.slices = slices, p.cols0 = cols0, p.cols1 = cols1,
+    p.scale = scale;
+    const dim3 grid((N / 2 + 255) / 256, rows);
+    switch (mode) {
+    case GEMM_STORE: launch_k(lora_epilogue_kernel<EPI_NONE>, grid, dim3(256), 0, stream, 1, p); break;
+    case GEMM_RESIDUAL: launch_k(lora_epilogue_kernel<EPI_RESIDUAL>, grid, dim3(256), 0, stream, 1, p); break;
+    case GEMM_SWIGLU: launch_k(lora_epilogue_kernel<EPI_SWIGLU>, grid, dim3(256), 0, stream, 1, p); break;
+    default: throw error(MC_ERR_INVALID, "lora epilogue: unknown mode");
+    }
+    return 1;
+}
 
 } // namespace tc
 } // namespace mc

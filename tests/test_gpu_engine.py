@@ -221,11 +221,11 @@ QNAMES = [f"{l}.{s}" for l in ("attention.wq", "attention.wk", "attention.wv", "
 QDT = {"weight": np.int8, "scales": np.float32, "adaptor.A.weight": np.uint16, "adaptor.B.weight": np.uint16}
 
 
-def make_qengine(cfgd, seed=0x5EED, n_seqs=1, from_oracle=None):
+def make_qengine(cfgd, seed=0x5EED, n_seqs=1, from_oracle=None, flags=0):
     from metalchat_b200 import capi
 
     gpu = accelerator()
-    m = capi.Llama(gpu.dev, capi.llama_config(**cfgd, quant=1, n_seqs=n_seqs))
+    m = capi.Llama(gpu.dev, capi.llama_config(**cfgd, quant=1, n_seqs=n_seqs, flags=flags))
     if from_oracle is None:
         m.init_random(seed)
     else:

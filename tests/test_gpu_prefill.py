@@ -212,3 +212,72 @@ def test_batched_decode_on_tensor_cores_matches_oracle(cfgd):
         c.prefill(p, seq=s)
     ids = c.decode(firsts, pos)
     assert ids.tolist() == ta[0].tolist()
+
+
+# ---- QLoRA models on the tensor-core path: resident bf16 image r(r(q) r(s)) + the adaptor kernels -------------------------------------
+@pytest.mark.parametrize("cfgd,n_prompt", [(SMALL, 70), (HD128, 33)])
+def test_quant_tc_prefill_matches_oracle_and_packed_prefill(cfgd, n_prompt):
+    from metalchat_b200 import capi
+    from tests.test_gpu_engine import make_qengine, near_top
+
+    ids = np.random.default_rng(n_prompt + 1).integers(0, cfgd["vocab"], size=n_prompt).tolist()
+    o = orc.Llama(orc.make_cfg(**cfgd, quant=1), BF16)
+    o.init_random(0x5EED)
+    want_logits, want_hidden = o.forward(ids, 0, want_hidden=True)
+    a = make_qengine(cfgd)                                   # bf16 image + tcgen05 GEMMs + adaptor kernels
+    b = make_qengine(cfgd, flags=capi.LLAMA_NO_SHADOW)       # packed int4 GEMV kernels, 4 rows per pass
+    a.prefill(ids)
+    b.prefill(ids)
+    assert a.weight_bytes()[1] > b.weight_bytes()[1]         # the image is resident, and accounted for
+    assert a.weight_bytes()[0] == b.weight_bytes()[0]        # the batch-1 stream is the packed one either way
+    for layer in range(cfgd["n_layers"]):
+        for which in (0, 1):
+            ga = a.cache(0, layer, which, n_prompt).reshape(-1)
+            gb = b.cache(0, layer, which, n_prompt).reshape(-1)
+            want = o.cache(0, layer, which)[: ga.size]
+            assert max_rel(unbf(ga), unbf(want)) < 1e-2
+            assert max_rel(unbf(ga), unbf(gb)) < 1e-2
+    k0 = a.cache(0, 0, 0, n_prompt).reshape(-1)
+    assert np.mean(k0 == o.cache(0, 0, 0)[: k0.size]) > 0.97
+    assert max_rel(unbf(a.hidden()), unbf(want_hidden[-1])) < 1e-2
+    assert max_rel(unbf(a.logits()), unbf(want_logits)) < 1e-2
+    assert max_rel(unbf(a.logits()), unbf(b.logits())) < 1e-2
+    tok, pos = orc.argmax(BF16, want_logits), n_prompt
+    for _ in range(8):
+        got = int(a.decode([tok], [pos])[0])
+        lg = o.forward([tok], pos)
+        tok = orc.argmax(BF16, lg)
+        assert near_top(lg, got), (got, tok)
+        pos += 1
+
+
+def test_quant_batched_decode_on_tensor_cores_matches_oracle():
+    from metalchat_b200 import capi
+    from tests.test_gpu_engine import make_qengine, near_top
+
+    cfgd, n = SMALL, 12
+    a = make_qengine(cfgd, n_seqs=n)
+    b = make_qengine(cfgd, n_seqs=n, flags=capi.LLAMA_NO_SHADOW)
+    o = orc.Llama(orc.make_cfg(**cfgd, quant=1), BF16)
+    o.init_random(0x5EED)
+    prompts = [[(13 * s + 7 * t + 2) % cfgd["vocab"] for t in range(3 + s)] for s in range(n)]
+    for s, p in enumerate(prompts):
+        a.prefill(p, seq=s)
+        b.prefill(p, seq=s)
+    firsts = [int(np.argmax(unbf(b.logits(s)))) for s in range(n)]
+    pos = [len(p) for p in prompts]
+    ta, _ = a.decode_loop(firsts, pos, 4)
+    b.decode_loop(firsts, pos, 4)
+    for s in range(n):
+        assert max_rel(unbf(a.logits(s)), unbf(b.logits(s))) < 3e-2, s
+    for s in (2, 9):
+        o.forward(prompts[s], 0)
+        tok, p = firsts[s], pos[s]
+        for step in range(4):
+            lg = o.forward([tok], p)
+            want = orc.argmax(BF16, lg)
+            got = int(ta[step, s])
+            assert got == want or near_top(lg, got), (s, step, got, want)
+            if got != want:
+                break
+            tok, p = want, p + 1
