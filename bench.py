@@ -206,19 +206,20 @@ def prefill_flops(shape: dict, S: int):
     return linear, attn, head
 
 
-def run_prefill(args, shape_name, shape):
+def run_prefill(args, shape_name, shape, quant=0):
     """Prompt throughput (BASELINE.json metric "prefill tok/s @2048"): a step = one prompt of --prompt positions through the
     tensor-core prompt path (tcgen05 GEMMs + causal attention), logits of the last position produced."""
     rank, world, local = dist_env()
     S = args.prompt
-    workload = f"llama-{shape_name} bf16 prefill of {S} positions (BASELINE.json configs[3] prompt phase), 1 sequence per GPU"
+    fmt_name = "QLoRA int4 (resident bf16 image + adaptor kernels)" if quant else "bf16"
+    workload = f"llama-{shape_name} {fmt_name} prefill of {S} positions (BASELINE.json configs[3] prompt phase), 1 sequence per GPU"
     if args.impl == "reference":
         if rank != 0:
             return
         from oracle import orc
 
         n = 64
-        m = orc.Llama(orc.make_cfg(**shape, max_seq_len=max(128, n)), orc.BF16)
+        m = orc.Llama(orc.make_cfg(**shape, max_seq_len=max(128, n), quant=quant), orc.BF16)
         m.init_random(0x5EED)
         ids = np.random.default_rng(1).integers(0, shape["vocab"], size=n).tolist()
         t0 = time.perf_counter()
@@ -243,7 +244,8 @@ def run_prefill(args, shape_name, shape):
     from metalchat_b200 import capi
 
     dev = capi.Device(local)
-    m = capi.Llama(dev, capi.llama_config(**shape, max_seq_len=S, quant=0, n_seqs=1, flags=capi.LLAMA_NO_TC_PREFILL if args.per_op else 0))
+    m = capi.Llama(dev, capi.llama_config(**shape, max_seq_len=S, quant=quant, n_seqs=1,
+                                          flags=(capi.LLAMA_NO_TC_PREFILL if args.per_op else 0) | (capi.LLAMA_W4_PACKED if quant else 0)))
     m.init_random(0x5EED)
     m.finalize()
     rng = np.random.default_rng(0x5EED + rank)
@@ -291,7 +293,7 @@ def run_prefill(args, shape_name, shape):
     roof = {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None, "peak_source": peak_src,
             "kernel": "whole prompt step (gemm_tc_kernel = tcgen05 GEMMs carry %.1f%% of the flops; causal attention on mma.sync)" % (100 * lin / (lin + att + head)),
             "algorithmic_flops_per_step": lin + att + head}
-    if not args.per_op:
+    if not args.per_op and not quant:
         # the dominant kernel alone: the four GEMM shapes of a block, CUDA events on the engine stream (mc_gemm_bf16)
         D, F = shape["dim"], shape["ffn_dim"]
         QKV = (shape["n_heads"] + 2 * shape["n_kv_heads"]) * shape["head_dim"]
@@ -318,7 +320,7 @@ def run_prefill(args, shape_name, shape):
     tokens = steps * S * world
     line = {
         "metric": "prefill_tokens_per_s", "value": tokens / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
-        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if not quant else "bf16 activations, int4 weights (bf16 dequant), fp32 accumulate",
         "data": "synthetic ids, random-init weights (counter-hash seed 0x5EED)",
         "config": {"workload": workload, "prompt": S, "parallelism": f"{world} replica(s)",
                    "path": "4-row GEMV prompt path" if args.per_op else "tcgen05 GEMM prompt path",
@@ -331,7 +333,7 @@ def run_prefill(args, shape_name, shape):
         from oracle import orc
 
         n = 32
-        o = orc.Llama(orc.make_cfg(**shape, max_seq_len=128), orc.BF16)
+        o = orc.Llama(orc.make_cfg(**shape, max_seq_len=128, quant=quant), orc.BF16)
         o.init_random(0x5EED)
         t0 = time.perf_counter()
         o.forward(prompts[0][:n].tolist(), 0)
@@ -360,8 +362,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.workload.endswith("-prefill"):
-        shape_name = args.workload.split("-")[0]
-        run_prefill(args, shape_name, SHAPES[shape_name])
+        shape_name, fmt = args.workload.split("-")[:2]
+        run_prefill(args, shape_name, SHAPES[shape_name], quant=0 if fmt == "bf16" else 1)
         return
     shape_name, fmt = args.workload.split("-")
     shape = SHAPES[shape_name]

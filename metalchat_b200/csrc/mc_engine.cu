@@ -829,21 +829,20 @@ void enqueue_sample(mc_llama* m, launcher& L, uint32_t rows, const mc_sampler_co
 // resident bf16 image and stores r(x . Wd^T); the adaptor term and the tail follow (quantization/lora.h:115-122):
 //   y = r(r(x . Wd^T) + r(r(B . r(A . x)) * r(scale))), then residual add / SiLU*mul / plain store.
 struct tc_scratch {
-    uint16_t* t;   // [rows, max N] r(x . Wd^T)
-    uint16_t* ax;  // [rows, 3 * rank]
+    uint16_t* t;   // [rows, max (N + padded adaptor rows)]: r(x . Wd^T) | r(x . A^T)
 };
-uint32_t tc_linear(mc_llama* m, cudaStream_t s, int mode, const uint16_t* X, uint32_t ldx, const dlinear& d, const dbuf& lora_a, uint32_t a_rows, uint32_t slices,
-                   uint16_t* Y, const uint16_t* res, uint32_t rows, uint32_t N, uint32_t K, uint32_t ldy, const tc_scratch& sc)
+uint32_t tc_pad_rows(uint32_t a_rows) { return (a_rows + 31) & ~31u; }
+uint32_t tc_linear(mc_llama* m, cudaStream_t s, int mode, const uint16_t* X, uint32_t ldx, const dlinear& d, uint32_t a_rows, uint32_t slices, uint16_t* Y,
+                   const uint16_t* res, uint32_t rows, uint32_t N, uint32_t K, uint32_t ldy, const tc_scratch& sc)
 {
     const mc_llama_config& c = m->cfg;
     const int sms = m->dev->prop.multiProcessorCount;
     int* err = m->errflag.as<int>();
     if (!c.quant) return uint32_t(tc::gemm(s, sms, mode, X, ldx, d.w.as<uint16_t>(), Y, res, rows, N, K, ldy, err));
     uint32_t n = 0;
-    const uint32_t ax_ld = 3 * c.lora_rank;
-    n += tc::lora_ax_rows(s, sc.ax, ax_ld, X, ldx, lora_a.as<uint16_t>(), rows, a_rows, K);
-    n += tc::gemm(s, sms, tc::GEMM_STORE, X, ldx, d.wd.as<uint16_t>(), sc.t, nullptr, rows, N, K, N, err);
-    n += tc::lora_epilogue(s, mode, sc.t, Y, res, sc.ax, ax_ld, d.lora_b.as<uint16_t>(), rows, N, ldy, c.lora_rank, slices, m->Hl * c.head_dim,
+    const uint32_t Next = N + tc_pad_rows(a_rows);
+    n += tc::gemm(s, sms, tc::GEMM_STORE, X, ldx, d.wd.as<uint16_t>(), sc.t, nullptr, rows, Next, K, Next, err);
+    n += tc::lora_epilogue(s, mode, sc.t, Next, Y, res, d.lora_b.as<uint16_t>(), rows, N, ldy, c.lora_rank, slices, m->Hl * c.head_dim,
                            (m->Hl + m->KVl) * c.head_dim, bf16_bits_to_f32(f32_to_bf16_bits(c.lora_scale)));
     return n;
 }
@@ -863,7 +862,7 @@ bool decode_tc_eligible(const mc_llama* m, uint32_t n)
 {
     const mc_llama_config& c = m->cfg;
     if ((c.flags & MC_LLAMA_NO_TC_PREFILL) || c.tp_world != 1 || n < decode_tc_min_rows() || !m->dt_n.p) return false;
-    if (c.quant && (!m->layers[0].wqkv.wd.p || !m->out.wd.p || c.lora_rank % 2 != 0)) return false;
+    if (c.quant && (!m->layers[0].wqkv.wd.p || !m->out.wd.p || c.lora_rank % 2 != 0 || c.lora_rank > 16)) return false;
     const uint32_t D = c.dim, QO = m->Hl * c.head_dim, QKV = (m->Hl + 2 * m->KVl) * c.head_dim, F = m->Fl;
     return tc::gemm_supported(QKV, D, D, QKV) && tc::gemm_supported(D, QO, QO, D) && tc::gemm_supported(2 * F, D, D, F) && tc::gemm_supported(D, F, F, D) &&
            tc::gemm_supported(m->Vl, D, D, m->Vl);
@@ -876,7 +875,7 @@ void enqueue_rows_tc(mc_llama* m, launcher& L, uint32_t rows)
     const int sms = m->dev->prop.multiProcessorCount;
     uint16_t *x = m->x.as<uint16_t>(), *h = m->h.as<uint16_t>(), *n = m->dt_n.as<uint16_t>(), *qkv = m->dt_qkv.as<uint16_t>();
     uint16_t *q = m->q.as<uint16_t>(), *attn = m->attn.as<uint16_t>(), *z = m->z.as<uint16_t>();
-    const tc_scratch sc{m->dt_t.as<uint16_t>(), m->lora_ax.as<uint16_t>()};
+    const tc_scratch sc{m->dt_t.as<uint16_t>()};
     const uint32_t rank = c.lora_rank;
     int* err = m->errflag.as<int>();
     tc::set_pdl(L.pdl);
@@ -887,7 +886,7 @@ void enqueue_rows_tc(mc_llama* m, launcher& L, uint32_t rows)
         uint16_t* kc = m->kcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
         uint16_t* vc = m->vcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
         count(tc::rmsnorm_rows(s, n, x, ly.attn_norm.as<uint16_t>(), rows, D, c.norm_eps));
-        count(tc_linear(m, s, tc::GEMM_STORE, n, D, ly.wqkv, ly.lora_a_qkv, 3 * rank, 3, qkv, nullptr, rows, QKV, D, QKV, sc));
+        count(tc_linear(m, s, tc::GEMM_STORE, n, D, ly.wqkv, 3 * rank, 3, qkv, nullptr, rows, QKV, D, QKV, sc));
         count(tc::rope_append(s, qkv, q, kc, vc, m->fcos.as<float>(), m->fsin.as<float>(), rows, 0, 0, H, KV, hd, c.max_seq_len, m->row_seq.as<int32_t>(),
                               m->pos.as<int32_t>()));
         if (tc::decode_attn_gqa_supported(H, KV, hd)) {
@@ -898,10 +897,10 @@ void enqueue_rows_tc(mc_llama* m, launcher& L, uint32_t rows)
             if (hd == 64) L.go_cluster(attn_decode_kernel<64>, dim3(H * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
             else L.go_cluster(attn_decode_kernel<128>, dim3(H * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
         }
-        count(tc_linear(m, s, tc::GEMM_RESIDUAL, attn, QO, ly.wo, ly.lora_a_o, rank, 1, h, x, rows, D, QO, D, sc));
+        count(tc_linear(m, s, tc::GEMM_RESIDUAL, attn, QO, ly.wo, rank, 1, h, x, rows, D, QO, D, sc));
         count(tc::rmsnorm_rows(s, n, h, ly.ffn_norm.as<uint16_t>(), rows, D, c.norm_eps));
-        count(tc_linear(m, s, tc::GEMM_SWIGLU, n, D, ly.w13, ly.lora_a_13, 2 * rank, 2, z, nullptr, rows, 2 * F, D, F, sc));
-        count(tc_linear(m, s, tc::GEMM_RESIDUAL, z, F, ly.w2, ly.lora_a_2, rank, 1, x, h, rows, D, F, D, sc));
+        count(tc_linear(m, s, tc::GEMM_SWIGLU, n, D, ly.w13, 2 * rank, 2, z, nullptr, rows, 2 * F, D, F, sc));
+        count(tc_linear(m, s, tc::GEMM_RESIDUAL, z, F, ly.w2, rank, 1, x, h, rows, D, F, D, sc));
     }
     count(tc::rmsnorm_rows(s, n, x, m->norm.as<uint16_t>(), rows, D, c.norm_eps));
     // vocabulary projection: the (tied) bf16 table, or the cached bf16 image of the int8 output matrix (quantization/linear.h:50-53)
@@ -1280,7 +1279,7 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
     if (c.tp_world == 1 && c.n_seqs >= decode_tc_min_rows()) {
         m->dt_n.alloc(size_t(R) * D * 2);
         m->dt_qkv.alloc(size_t(R) * (m->Hl + 2 * m->KVl) * hd * 2);
-        if (c.quant) m->dt_t.alloc(size_t(R) * std::max(std::max((m->Hl + 2 * m->KVl) * hd, 2 * m->Fl), D) * 2);
+        if (c.quant) m->dt_t.alloc(size_t(R) * (std::max(std::max((m->Hl + 2 * m->KVl) * hd, 2 * m->Fl), D) + 128) * 2);
     }
     {
         // tagged-word exchange buffers of the streaming kernel (8 bytes per word = two bf16 + tag)
@@ -1436,8 +1435,13 @@ mc_status mc_llama_finalize(mc_llama* m)
             for (dlayer& ly : m->layers)
                 for (dlinear* d : {&ly.wqkv, &ly.wo, &ly.w13, &ly.w2}) {
                     if (!d->q8.p) continue;
-                    d->wd.alloc(size_t(d->N) * d->K * 2);
+                    // rows [0, N): r(r(q) * r(s)); rows [N, N + R): the stacked adaptor A of this linear; zero rows up to a multiple of 32
+                    const dbuf& A = d == &ly.wqkv ? ly.lora_a_qkv : (d == &ly.wo ? ly.lora_a_o : (d == &ly.w13 ? ly.lora_a_13 : ly.lora_a_2));
+                    const uint32_t R = uint32_t(A.bytes / (size_t(d->K) * 2)), Rpad = (R + 31) & ~31u;
+                    d->wd.alloc(size_t(d->N + Rpad) * d->K * 2);
                     tc::dequant_group(s, d->wd.as<uint16_t>(), d->q8.as<int8_t>(), d->s32.as<float>(), d->N, d->K, m->cfg.group_size);
+                    MC_CUDA_CHECK(cudaMemsetAsync(d->wd.as<uint16_t>() + size_t(d->N) * d->K, 0, size_t(Rpad) * d->K * 2, s));
+                    MC_CUDA_CHECK(cudaMemcpyAsync(d->wd.as<uint16_t>() + size_t(d->N) * d->K, A.p, size_t(R) * d->K * 2, cudaMemcpyDeviceToDevice, s));
                 }
             if (m->out.q8.p) {
                 m->out.wd.alloc(size_t(m->out.N) * m->out.K * 2);
@@ -1496,7 +1500,7 @@ bool prefill_tc_eligible(const mc_llama* m, uint32_t len)
     const mc_llama_config& c = m->cfg;
     static const bool env_off = getenv("MC_NO_TC_PREFILL") != nullptr;
     if (env_off || (c.flags & MC_LLAMA_NO_TC_PREFILL) || c.tp_world != 1 || len < prefill_tc_min_rows()) return false;
-    if (c.quant && (!m->layers[0].wqkv.wd.p || c.lora_rank % 2 != 0)) return false; // quantised: needs the bf16 image (mc_llama_finalize)
+    if (c.quant && (!m->layers[0].wqkv.wd.p || c.lora_rank % 2 != 0 || c.lora_rank > 16)) return false; // quantised: needs the bf16 image (mc_llama_finalize)
     if (c.head_dim != 64 && c.head_dim != 128) return false;
     const uint32_t D = c.dim, QO = m->Hl * c.head_dim, QKV = (m->Hl + 2 * m->KVl) * c.head_dim, F = m->Fl;
     return tc::gemm_supported(QKV, D, D, QKV) && tc::gemm_supported(D, QO, QO, D) && tc::gemm_supported(2 * F, D, D, F) && tc::gemm_supported(D, F, F, D);
@@ -1514,12 +1518,12 @@ void prefill_tc(mc_llama* m, uint32_t seq, const int32_t* ids, uint32_t len, uin
         m->pf_x.alloc(size_t(cap) * D * 2), m->pf_h.alloc(size_t(cap) * D * 2), m->pf_n.alloc(size_t(cap) * D * 2);
         m->pf_qkv.alloc(size_t(cap) * QKV * 2), m->pf_q.alloc(size_t(cap) * QO * 2), m->pf_attn.alloc(size_t(cap) * QO * 2);
         m->pf_z.alloc(size_t(cap) * F * 2);
-        if (c.quant) m->pf_t.alloc(size_t(cap) * maxN * 2), m->pf_ax.alloc(size_t(cap) * 3 * rank * 2);
+        if (c.quant) m->pf_t.alloc(size_t(cap) * (maxN + tc_pad_rows(3 * rank)) * 2);
         m->pf_rows = cap;
     }
     uint16_t *x = m->pf_x.as<uint16_t>(), *h = m->pf_h.as<uint16_t>(), *n = m->pf_n.as<uint16_t>(), *qkv = m->pf_qkv.as<uint16_t>();
     uint16_t *q = m->pf_q.as<uint16_t>(), *attn = m->pf_attn.as<uint16_t>(), *z = m->pf_z.as<uint16_t>();
-    const tc_scratch sc{m->pf_t.as<uint16_t>(), m->pf_ax.as<uint16_t>()};
+    const tc_scratch sc{m->pf_t.as<uint16_t>()};
     int* err = m->errflag.as<int>();
     uint32_t launches = 0;
     launcher L{m, s, false};
@@ -1535,13 +1539,13 @@ void prefill_tc(mc_llama* m, uint32_t seq, const int32_t* ids, uint32_t len, uin
             uint16_t* kc = m->kcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
             uint16_t* vc = m->vcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
             launches += tc::rmsnorm_rows(s, n, x, ly.attn_norm.as<uint16_t>(), rows, D, c.norm_eps);
-            launches += tc_linear(m, s, tc::GEMM_STORE, n, D, ly.wqkv, ly.lora_a_qkv, 3 * rank, 3, qkv, nullptr, rows, QKV, D, QKV, sc);
+            launches += tc_linear(m, s, tc::GEMM_STORE, n, D, ly.wqkv, 3 * rank, 3, qkv, nullptr, rows, QKV, D, QKV, sc);
             launches += tc::rope_append(s, qkv, q, kc, vc, m->fcos.as<float>(), m->fsin.as<float>(), rows, seq, pos0, H, KV, hd, c.max_seq_len);
             launches += tc::prefill_attn(s, q, kc, vc, attn, rows, seq, pos0, H, KV, hd, c.max_seq_len, m->scale_bf16);
-            launches += tc_linear(m, s, tc::GEMM_RESIDUAL, attn, QO, ly.wo, ly.lora_a_o, rank, 1, h, x, rows, D, QO, D, sc);
+            launches += tc_linear(m, s, tc::GEMM_RESIDUAL, attn, QO, ly.wo, rank, 1, h, x, rows, D, QO, D, sc);
             launches += tc::rmsnorm_rows(s, n, h, ly.ffn_norm.as<uint16_t>(), rows, D, c.norm_eps);
-            launches += tc_linear(m, s, tc::GEMM_SWIGLU, n, D, ly.w13, ly.lora_a_13, 2 * rank, 2, z, nullptr, rows, 2 * F, D, F, sc);
-            launches += tc_linear(m, s, tc::GEMM_RESIDUAL, z, F, ly.w2, ly.lora_a_2, rank, 1, x, h, rows, D, F, D, sc);
+            launches += tc_linear(m, s, tc::GEMM_SWIGLU, n, D, ly.w13, 2 * rank, 2, z, nullptr, rows, 2 * F, D, F, sc);
+            launches += tc_linear(m, s, tc::GEMM_RESIDUAL, z, F, ly.w2, rank, 1, x, h, rows, D, F, D, sc);
         }
         if (t0 + rows >= len) {
             // only the last position is projected (nn/llama.h:128-133)

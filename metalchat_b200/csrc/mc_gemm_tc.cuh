@@ -923,67 +923,61 @@ __global__ void __launch_bounds__(256) dequant_group_kernel(uint16_t* out, const
         *reinterpret_cast<uint4*>(out + e) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
-// ax[m, j] = r(sum_k x[m, k] * A[j, k])  (the adaptor's first bmm, kernel/bmm.metal:76); grid = rows, 8 warps deal the R adaptor rows
-__global__ void __launch_bounds__(256) lora_ax_rows_kernel(uint16_t* ax, uint32_t ax_ld, const uint16_t* x, uint32_t ldx, const uint16_t* A, uint32_t R, uint32_t K)
-{
-    pdl_trigger();
-    pdl_sync();
-    const uint32_t row = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint16_t* xr = x + size_t(row) * ldx;
-    for (uint32_t j = warp; j < R; j += 8) {
-        const uint16_t* ar = A + size_t(j) * K;
-        float acc = 0.0f;
-        for (uint32_t k = lane * 8; k < K; k += 256) {
-            const uint4 xv = *reinterpret_cast<const uint4*>(xr + k), av = *reinterpret_cast<const uint4*>(ar + k);
-            acc = fmaf(bf_lo(xv.x), bf_lo(av.x), acc), acc = fmaf(bf_hi(xv.x), bf_hi(av.x), acc);
-            acc = fmaf(bf_lo(xv.y), bf_lo(av.y), acc), acc = fmaf(bf_hi(xv.y), bf_hi(av.y), acc);
-            acc = fmaf(bf_lo(xv.z), bf_lo(av.z), acc), acc = fmaf(bf_hi(xv.z), bf_hi(av.z), acc);
-            acc = fmaf(bf_lo(xv.w), bf_lo(av.w), acc), acc = fmaf(bf_hi(xv.w), bf_hi(av.w), acc);
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if (lane == 0) ax[size_t(row) * ax_ld + j] = f32_to_bf16_bits(acc);
-    }
-}
-// y2 = r(y + r(r(B . ax) * scale))  (quantization/lora.h:115-122), then the fused tail of the linear; thread = two adjacent columns.
+// y2 = r(y + r(r(B . ax) * scale))  (quantization/lora.h:115-122), then the fused tail of the linear.  Thread = two adjacent columns
+// (their B rows stay in registers) x 16 rows; ax = r(A . x) arrives as extra columns of the GEMM output (the stacked adaptor rows are
+// appended to the bf16 image, so the same tcgen05 GEMM produces both products with the rounding of kernel/bmm.metal:76).
 //   slices: 1 = one adaptor, 2 = w1|w3 row-interleaved (column parity picks the adaptor), 3 = q|k|v (column ranges pick it)
+constexpr int kLoraRows = 16, kLoraMaxRank = 16;
 struct lora_epi_params {
-    const uint16_t* y;   // [rows, N] r(x . Wd^T)
-    uint16_t* out;       // EPI_NONE / EPI_RESIDUAL: [rows, ldo]; EPI_SWIGLU: [rows, ldo] with N/2 columns (may alias y only for EPI_NONE)
+    const uint16_t* y;   // [rows, ldy]: columns [0, N) = r(x . Wd^T), columns [N, N + slices * rank) = r(x . A^T)
+    uint16_t* out;       // EPI_NONE / EPI_RESIDUAL: [rows, ldo]; EPI_SWIGLU: [rows, ldo] with N/2 columns
     const uint16_t* res; // EPI_RESIDUAL
-    const uint16_t* ax;  // [rows, ax_ld]
     const uint16_t* B;   // [N, rank]
-    uint32_t N, ldo, ax_ld, rank, slices, cols0, cols1;
+    uint32_t rows, N, ldy, ldo, rank, slices, cols0, cols1;
     float scale;         // r(lora scale)
 };
 template <int EPI> __global__ void __launch_bounds__(256) lora_epilogue_kernel(const lora_epi_params p)
 {
     pdl_trigger();
     pdl_sync();
-    const uint32_t row = blockIdx.y, n = (blockIdx.x * 256 + threadIdx.x) * 2;
+    const uint32_t n = (blockIdx.x * 256 + threadIdx.x) * 2, row0 = blockIdx.y * kLoraRows;
     if (n >= p.N) return;
-    const uint32_t yy = *reinterpret_cast<const uint32_t*>(p.y + size_t(row) * p.N + n);
-    float v[2] = {bf_lo(yy), bf_hi(yy)};
+    float bw[2][kLoraMaxRank];
+    uint32_t slice[2];
 #pragma unroll
     for (int c = 0; c < 2; c++) {
         const uint32_t col = n + c;
-        const uint32_t slice = p.slices == 2 ? (col & 1u) : (p.slices == 3 ? (col < p.cols0 ? 0u : (col < p.cols1 ? 1u : 2u)) : 0u);
-        const uint16_t* a = p.ax + size_t(row) * p.ax_ld + slice * p.rank;
+        slice[c] = p.slices == 2 ? (col & 1u) : (p.slices == 3 ? (col < p.cols0 ? 0u : (col < p.cols1 ? 1u : 2u)) : 0u);
         const uint16_t* b = p.B + size_t(col) * p.rank;
-        float l = 0.0f;
-        for (uint32_t j = 0; j < p.rank; j += 2) {
-            const uint32_t av = *reinterpret_cast<const uint32_t*>(a + j), bv = *reinterpret_cast<const uint32_t*>(b + j);
-            l = fmaf(bf_lo(av), bf_lo(bv), l), l = fmaf(bf_hi(av), bf_hi(bv), l);
-        }
-        v[c] = rbf(__fadd_rn(v[c], rbf(__fmul_rn(rbf(l), p.scale))));
+#pragma unroll
+        for (int j = 0; j < kLoraMaxRank; j++) bw[c][j] = uint32_t(j) < p.rank ? bf16_bits_to_f32(b[j]) : 0.0f;
     }
-    if (EPI == EPI_SWIGLU) {
-        p.out[size_t(row) * p.ldo + (n >> 1)] = f32_to_bf16_bits(__fmul_rn(silu_bf16(v[0]), v[1])); // (nn/transformer.h:57-59)
-    } else if (EPI == EPI_RESIDUAL) {
-        const uint32_t r = *reinterpret_cast<const uint32_t*>(p.res + size_t(row) * p.ldo + n);
-        *reinterpret_cast<uint32_t*>(p.out + size_t(row) * p.ldo + n) = pack2(__fadd_rn(bf_lo(r), v[0]), __fadd_rn(bf_hi(r), v[1]));
-    } else {
-        *reinterpret_cast<uint32_t*>(p.out + size_t(row) * p.ldo + n) = pack2(v[0], v[1]);
+    const uint32_t row_end = min(row0 + uint32_t(kLoraRows), p.rows);
+    for (uint32_t row = row0; row < row_end; row++) {
+        const uint16_t* yr = p.y + size_t(row) * p.ldy;
+        const uint32_t yy = *reinterpret_cast<const uint32_t*>(yr + n);
+        float v[2] = {bf_lo(yy), bf_hi(yy)};
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const uint16_t* a = yr + p.N + slice[c] * p.rank;
+            float l = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kLoraMaxRank; j += 2) {
+                if (uint32_t(j) < p.rank) {
+                    const uint32_t av = *reinterpret_cast<const uint32_t*>(a + j);
+                    l = fmaf(bf_lo(av), bw[c][j], l), l = fmaf(bf_hi(av), bw[c][j + 1], l);
+                }
+            }
+            v[c] = rbf(__fadd_rn(v[c], rbf(__fmul_rn(rbf(l), p.scale))));
+        }
+        if (EPI == EPI_SWIGLU) {
+            p.out[size_t(row) * p.ldo + (n >> 1)] = f32_to_bf16_bits(__fmul_rn(silu_bf16(v[0]), v[1])); // (nn/transformer.h:57-59)
+        } else if (EPI == EPI_RESIDUAL) {
+            const uint32_t r = *reinterpret_cast<const uint32_t*>(p.res + size_t(row) * p.ldo + n);
+            *reinterpret_cast<uint32_t*>(p.out + size_t(row) * p.ldo + n) = pack2(__fadd_rn(bf_lo(r), v[0]), __fadd_rn(bf_hi(r), v[1]));
+        } else {
+            *reinterpret_cast<uint32_t*>(p.out + size_t(row) * p.ldo + n) = pack2(v[0], v[1]);
+        }
     }
 }
 

@@ -274,20 +274,14 @@ int dequant_group(cudaStream_t stream, uint16_t* out, const int8_t* q, const flo
     MC_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
-int lora_ax_rows(cudaStream_t stream, uint16_t* ax, uint32_t ax_ld, const uint16_t* x, uint32_t ldx, const uint16_t* A, uint32_t rows, uint32_t R, uint32_t K)
+int lora_epilogue(cudaStream_t stream, int mode, const uint16_t* y, uint32_t ldy, uint16_t* out, const uint16_t* res, const uint16_t* B, uint32_t rows, uint32_t N,
+                  uint32_t ldo, uint32_t rank, uint32_t slices, uint32_t cols0, uint32_t cols1, float scale)
 {
-    MC_REQUIRE(K % 256 == 0 && ldx % 8 == 0, "lora: K must be a multiple of 256");
-    launch_k(lora_ax_rows_kernel, dim3(rows), dim3(256), 0, stream, 1, ax, ax_ld, x, ldx, A, R, K);
-    return 1;
-}
-int lora_epilogue(cudaStream_t stream, int mode, const uint16_t* y, uint16_t* out, const uint16_t* res, const uint16_t* ax, uint32_t ax_ld, const uint16_t* B,
-                  uint32_t rows, uint32_t N, uint32_t ldo, uint32_t rank, uint32_t slices, uint32_t cols0, uint32_t cols1, float scale)
-{
-    MC_REQUIRE(N % 2 == 0 && rank % 2 == 0 && ldo % 2 == 0, "lora epilogue: N, rank and the output pitch must be even");
+    MC_REQUIRE(N % 2 == 0 && rank % 2 == 0 && rank <= uint32_t(kLoraMaxRank) && ldo % 2 == 0 && ldy % 2 == 0, "lora epilogue: even N / pitches and an even rank <= 16");
     lora_epi_params p{};
-    p.y = y, p.out = out, p.res = res, p.ax = ax, p.B = B, p.N = N, p.ldo = ldo, p.ax_ld = ax_ld, p.rank = rank, p.slices = slices, p.cols0 = cols0, p.cols1 = cols1,
+    p.y = y, p.out = out, p.res = res, p.B = B, p.rows = rows, p.N = N, p.ldy = ldy, p.ldo = ldo, p.rank = rank, p.slices = slices, p.cols0 = cols0, p.cols1 = cols1,
     p.scale = scale;
-    const dim3 grid((N / 2 + 255) / 256, rows);
+    const dim3 grid((N / 2 + 255) / 256, (rows + kLoraRows - 1) / kLoraRows);
     switch (mode) {
     case GEMM_STORE: launch_k(lora_epilogue_kernel<EPI_NONE>, grid, dim3(256), 0, stream, 1, p); break;
     case GEMM_RESIDUAL: launch_k(lora_epilogue_kernel<EPI_RESIDUAL>, grid, dim3(256), 0, stream, 1, p); break;

@@ -40,11 +40,11 @@ int decode_attn_gqa(cudaStream_t stream, const uint16_t* q, const uint16_t* kcac
                     const int32_t* row_seq, const int32_t* row_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, float scale);
 
 // QLoRA on the tensor-core path: bf16 image of a group-quantised matrix, w = r(r(q) * r(s)) (kernel/mul.metal:76-77; group == K gives the
-// per-row scale of quantization::linear), the adaptor's first product ax = r(x . A^T), and y2 = r(y + r(r(B . ax) * scale)) + the fused tail
+// per-row scale of quantization::linear), and y2 = r(y + r(r(B . ax) * scale)) + the fused tail
 int dequant_group(cudaStream_t stream, uint16_t* out, const int8_t* q, const float* scales, uint32_t N, uint32_t K, uint32_t group);
-int lora_ax_rows(cudaStream_t stream, uint16_t* ax, uint32_t ax_ld, const uint16_t* x, uint32_t ldx, const uint16_t* A, uint32_t rows, uint32_t R, uint32_t K);
-int lora_epilogue(cudaStream_t stream, int mode, const uint16_t* y, uint16_t* out, const uint16_t* res, const uint16_t* ax, uint32_t ax_ld, const uint16_t* B,
-                  uint32_t rows, uint32_t N, uint32_t ldo, uint32_t rank, uint32_t slices, uint32_t cols0, uint32_t cols1, float scale);
+// y [rows, ldy]: columns [0, N) = r(x . Wd^T), columns [N, ...) = r(x . A^T) (the stacked adaptor rows are appended to the bf16 image)
+int lora_epilogue(cudaStream_t stream, int mode, const uint16_t* y, uint32_t ldy, uint16_t* out, const uint16_t* res, const uint16_t* B, uint32_t rows, uint32_t N,
+                  uint32_t ldo, uint32_t rank, uint32_t slices, uint32_t cols0, uint32_t cols1, float scale);
 
 } // namespace tc
 } // namespace mc
