@@ -934,13 +934,14 @@ struct lora_epi_params {
     const uint16_t* res; // EPI_RESIDUAL
     const uint16_t* B;   // [N, rank]
     uint32_t rows, N, ldy, ldo, rank, slices, cols0, cols1;
+    uint32_t rows_per_cta; // 16 for prompts (B rows amortised), 4 for decode batches (more CTAs)
     float scale;         // r(lora scale)
 };
 template <int EPI> __global__ void __launch_bounds__(256) lora_epilogue_kernel(const lora_epi_params p)
 {
     pdl_trigger();
     pdl_sync();
-    const uint32_t n = (blockIdx.x * 256 + threadIdx.x) * 2, row0 = blockIdx.y * kLoraRows;
+    const uint32_t n = (blockIdx.x * 256 + threadIdx.x) * 2, row0 = blockIdx.y * p.rows_per_cta;
     if (n >= p.N) return;
     float bw[2][kLoraMaxRank];
     uint32_t slice[2];
@@ -952,7 +953,7 @@ template <int EPI> __global__ void __launch_bounds__(256) lora_epilogue_kernel(c
 #pragma unroll
         for (int j = 0; j < kLoraMaxRank; j++) bw[c][j] = uint32_t(j) < p.rank ? bf16_bits_to_f32(b[j]) : 0.0f;
     }
-    const uint32_t row_end = min(row0 + uint32_t(kLoraRows), p.rows);
+    const uint32_t row_end = min(row0 + p.rows_per_cta, p.rows);
     for (uint32_t row = row0; row < row_end; row++) {
         const uint16_t* yr = p.y + size_t(row) * p.ldy;
         const uint32_t yy = *reinterpret_cast<const uint32_t*>(yr + n);

@@ -281,7 +281,8 @@ int lora_epilogue(cudaStream_t stream, int mode, const uint16_t* y, uint32_t ldy
     lora_epi_params p{};
     p.y = y, p.out = out, p.res = res, p.B = B, p.rows = rows, p.N = N, p.ldy = ldy, p.ldo = ldo, p.rank = rank, p.slices = slices, p.cols0 = cols0, p.cols1 = cols1,
     p.scale = scale;
-    const dim3 grid((N / 2 + 255) / 256, (rows + kLoraRows - 1) / kLoraRows);
+    p.rows_per_cta = rows <= 64 ? 4u : uint32_t(kLoraRows);
+    const dim3 grid((N / 2 + 255) / 256, (rows + p.rows_per_cta - 1) / p.rows_per_cta);
     switch (mode) {
     case GEMM_STORE: launch_k(lora_epilogue_kernel<EPI_NONE>, grid, dim3(256), 0, stream, 1, p); break;
     case GEMM_RESIDUAL: launch_k(lora_epilogue_kernel<EPI_RESIDUAL>, grid, dim3(256), 0, stream, 1, p); break;
