@@ -77,25 +77,40 @@ struct tp_exchange {
     unsigned* done;                    // local: CTAs of the producer that have finished
     unsigned* epoch;                   // local: exchanges published so far
     int* err;                          // local: set when a flag wait times out
+    uint32_t nowait;                   // diagnostics (MC_TP_NOWAIT): do not wait for the peers' flags -- results are wrong, the step time tells what the waits cost
 };
 __device__ __forceinline__ float* tp_slot(const tp_exchange& t, float* buf, uint32_t parity, uint32_t src)
 {
     return buf + (size_t(parity) * t.world + src) * t.rows_max * t.dim;
 }
-// producer side, after the epilogue stores: the last CTA publishes the new epoch to every peer
-__device__ __forceinline__ void tp_publish(const tp_exchange& t)
+// producer side, after the epilogue stores (which go to this rank's OWN slot): the last CTA to finish copies the finished partial
+// vector to every peer with 16-byte stores over NVLink (scattered 4-byte remote stores from every warp cost ~30-50 us per exchange:
+// profiles/bench_r01b_8b_bf16_tp*.json), then publishes the new epoch to every peer
+__device__ __forceinline__ void tp_publish(const tp_exchange& t, uint32_t rows, uint32_t parity, unsigned* smem_word)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        __threadfence();
         const unsigned prev = atomicAdd(t.done, 1u);
-        if (prev == gridDim.x - 1) {
-            *t.done = 0;
-            const unsigned e = *t.epoch + 1;
-            *t.epoch = e;
-            __threadfence_system();
-            for (uint32_t k = 0; k < t.world; k++) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(t.peer_flag[k] + t.rank), "r"(e) : "memory");
-        }
+        *smem_word = prev == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (*smem_word == 0u) return;
+    __threadfence(); // the other CTAs' partials (released by their fences before the counter) are visible from here on
+    const uint32_t n4 = rows * t.dim / 4;
+    const float4* src = reinterpret_cast<const float4*>(tp_slot(t, t.peer_buf[t.rank], parity, t.rank));
+    for (uint32_t k = 0; k < t.world; k++) {
+        if (k == t.rank) continue;
+        float4* dst = reinterpret_cast<float4*>(tp_slot(t, t.peer_buf[k], parity, t.rank));
+        for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldcg(src + i);
+    }
+    __syncthreads(); // the copies of every thread happen before thread 0's single system-scope fence (cumulativity)
+    if (threadIdx.x == 0) {
+        *t.done = 0;
+        const unsigned e = *t.epoch + 1;
+        *t.epoch = e;
+        __threadfence_system();
+        for (uint32_t k = 0; k < t.world; k++) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(t.peer_flag[k] + t.rank), "r"(e) : "memory");
     }
 }
 // consumer side: wait until every rank has published epoch e; returns e (0 on timeout)
@@ -104,7 +119,7 @@ __device__ __forceinline__ unsigned tp_wait(const tp_exchange& t, unsigned* smem
     if (threadIdx.x == 0) {
         const unsigned e = *reinterpret_cast<volatile unsigned*>(t.epoch);
         unsigned ok = e;
-        for (uint32_t k = 0; k < t.world; k++) {
+        for (uint32_t k = 0; k < t.world && !t.nowait; k++) {
             unsigned v = 0;
             unsigned long long spins = 0;
             for (;;) {
@@ -511,13 +526,10 @@ __device__ __forceinline__ void gemv_body(const gemv_params& p, unsigned char* s
                 y1 = rbf(__fadd_rn(y1, rbf(__fmul_rn(rbf(l1), p.lora_scale))));
             }
             if (EPI == EPI_PARTIAL_TP) {
-                // unrounded fp32 partial sums go to every rank's exchange buffer (P2P stores over NVLink)
-                const uint32_t parity = tp_parity;
-                for (uint32_t k = 0; k < p.tp.world; k++) {
-                    float* dst = tp_slot(p.tp, p.tp.peer_buf[k], parity, p.tp.rank) + size_t(m) * p.tp.dim;
-                    dst[r0] = a;
-                    dst[r1] = b;
-                }
+                // unrounded fp32 partial sums go to this rank's own slot; tp_publish copies the finished vector to the peers
+                float* dst = tp_slot(p.tp, p.tp.peer_buf[p.tp.rank], tp_parity, p.tp.rank) + size_t(m) * p.tp.dim;
+                dst[r0] = a;
+                dst[r1] = b;
             } else if (EPI == EPI_NONE) {
                 p.y[size_t(m) * p.ldy + r0] = f32_to_bf16_bits(y0);
                 p.y[size_t(m) * p.ldy + r1] = f32_to_bf16_bits(y1);
@@ -580,7 +592,7 @@ __device__ __forceinline__ void gemv_body(const gemv_params& p, unsigned char* s
             p.am_idx[threadIdx.x * gridDim.x + blockIdx.x] = bi;
         }
     }
-    if (EPI == EPI_PARTIAL_TP) tp_publish(p.tp);
+    if (EPI == EPI_PARTIAL_TP) tp_publish(p.tp, p.rows, tp_parity, reinterpret_cast<unsigned*>(sscr));
     if (MEGA) {
         stamp(sy.timing, 2);
         grid_arrive(sy.bar);

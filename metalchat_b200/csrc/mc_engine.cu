@@ -388,6 +388,8 @@ tp_exchange tp_of(mc_llama* m)
         t.peer_flag[k] = reinterpret_cast<uint32_t*>(static_cast<char*>(m->tp_peer_base[k]) + m->tp_off_flags);
     }
     t.done = m->tp_local.as<unsigned>(), t.epoch = m->tp_local.as<unsigned>() + 1, t.err = m->errflag.as<int>();
+    static const uint32_t nowait = getenv("MC_TP_NOWAIT") ? 1u : 0u;
+    t.nowait = nowait;
     return t;
 }
 // makes `p` consume the previous row-parallel GEMV's partial sums: rows = r(res + r(sum)), stored to `out` by CTA 0
