@@ -281,3 +281,21 @@ def test_quant_batched_decode_on_tensor_cores_matches_oracle():
             if got != want:
                 break
             tok, p = want, p + 1
+
+
+def test_tc_prefill_longer_than_one_chunk():
+    # 2100 positions: the engine walks the prompt in chunks of 2048 rows; the second chunk attends the cached prefix
+    from metalchat_b200 import capi
+
+    cfgd = dict(SMALL, max_seq_len=2304)
+    ids = np.random.default_rng(9).integers(0, cfgd["vocab"], size=2100).tolist()
+    a = make_engine(cfgd)
+    b = make_engine(cfgd, flags=capi.LLAMA_NO_TC_PREFILL)
+    a.prefill(ids)
+    b.prefill(ids)
+    for which in (0, 1):
+        ga, gb = a.cache(0, 0, which, 2100).reshape(-1), b.cache(0, 0, which, 2100).reshape(-1)
+        assert np.mean(ga == gb) > 0.98
+        gl, hl = a.cache(0, 2, which, 2100).reshape(2100, -1), b.cache(0, 2, which, 2100).reshape(2100, -1)
+        assert max_rel(unbf(gl[2040:]), unbf(hl[2040:])) < 2e-2  # rows on both sides of the chunk boundary
+    assert max_rel(unbf(a.logits()), unbf(b.logits())) < 2e-2
