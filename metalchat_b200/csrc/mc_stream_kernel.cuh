@@ -670,7 +670,8 @@ __device__ __forceinline__ void st_mma_packed(const st_params& P, const st_gemv&
     const uint32_t kt_b = min(kts, warp * per), kt_e = min(kts, kt_b + per);
     const uint32_t brow = gq < P.rows ? gq : 0;
     const uint32_t xb = c.act_addr + brow * P.act_pitch + 4 * t;      // B fragment base of this lane
-    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc2[4] = {0.0f, 0.0f, 0.0f, 0.0f}; // two chains: consecutive mma do not wait for each other
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc2[4] = {0.0f, 0.0f, 0.0f, 0.0f}; // independent chains: consecutive mma do not wait for each other
+    float acc3[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc4[4] = {0.0f, 0.0f, 0.0f, 0.0f}; // (int4: four mma per k-tile, one chain each: 806 -> 763 us per step)
     st_dbg(dbg, dblk, 0, 0);
     // operands of one k-tile: the packed weights, (int4) the group scales, the B fragments.  The loads are volatile asm, i.e.
     // kept in program order, so the k-tile loop is software-pipelined by hand: the operands of k-tile i+1 are requested
@@ -705,8 +706,10 @@ __device__ __forceinline__ void st_mma_packed(const st_params& P, const st_gemv&
                 const uint32_t a1 = hmul2_bf16(hsub2_bf16(and_or(w >> 4, nib_mask, nib_magic), 0x43084308u), sh);
                 const uint32_t a2 = hmul2_bf16(hsub2_bf16(and_or(w >> 8, nib_mask, nib_magic), 0x43084308u), sg);
                 const uint32_t a3 = hmul2_bf16(hsub2_bf16(and_or(w >> 12, nib_mask, nib_magic), 0x43084308u), sh);
-                if (j & 1) mma_bf16_16816(acc2, a0, a1, a2, a3, o.b0[j], o.b1[j]);
-                else mma_bf16_16816(acc, a0, a1, a2, a3, o.b0[j], o.b1[j]);
+                if (j == 0) mma_bf16_16816(acc, a0, a1, a2, a3, o.b0[j], o.b1[j]);
+                else if (j == 1) mma_bf16_16816(acc2, a0, a1, a2, a3, o.b0[j], o.b1[j]);
+                else if (j == 2) mma_bf16_16816(acc3, a0, a1, a2, a3, o.b0[j], o.b1[j]);
+                else mma_bf16_16816(acc4, a0, a1, a2, a3, o.b0[j], o.b1[j]);
             }
         } else {
 #pragma unroll
@@ -743,7 +746,7 @@ __device__ __forceinline__ void st_mma_packed(const st_params& P, const st_gemv&
     }
     st_dbg(dbg, dblk, 2, 0);
 #pragma unroll
-    for (int i = 0; i < 4; i++) acc[i] += acc2[i];
+    for (int i = 0; i < 4; i++) acc[i] = (acc[i] + acc2[i]) + (acc3[i] + acc4[i]);
     // mma row g = unit su*8+g row r0, row g+8 = its row r1: rope pairs keep that order, adjacent-row units interleave
     if (g.qkv_map) st_hand_over(c, bl, acc, gq, gq + 8);
     else st_hand_over(c, bl, acc, 2 * gq, 2 * gq + 1);
