@@ -58,6 +58,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
     return d;
 }
 
+// (x & mask) | magic in ONE LOP3 (with immediate operands the compiler emits two); mask / magic are kept in registers by the caller
+__device__ __forceinline__ uint32_t q_and_or(uint32_t x, uint32_t mask, uint32_t magic)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(x), "r"(mask), "r"(magic));
+    return d;
+}
+
 struct qgemv_params {
     gemv_params g;            // shapes, activations, epilogue operands (g.W = packed weights, g.N rows, g.K)
     const void* scales;       // WF_W4: packed bf16 scales; WF_W8ROW: fp32 [N] per-row scales
@@ -192,6 +200,8 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_q_kernel(const qgemv_par
             }
         }
         float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        uint32_t nib_mask = 0x000f000fu, nib_magic = 0x43004300u; // in registers (not folded back into immediates): one LOP3 per nibble pair
+        asm volatile("" : "+r"(nib_mask), "+r"(nib_magic));
         const uint32_t sn = su + sstride;
         const bool next_active = sn < supers;
         float rs0 = 0.0f, rs1 = 0.0f; // WF_W8ROW: r(scale) of rows r0 / r1
@@ -238,10 +248,10 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_q_kernel(const qgemv_par
                                 const uint32_t w = words[j];
                                 const uint32_t sg = j < 2 ? s_g0 : s_g1, sh = j < 2 ? s_h0 : s_h1;
                                 // nibble -> bf16 (128 + n) -> q = n - 8 (exact) -> r(q * r(s))   (kernel/mul.metal:76-77)
-                                const uint32_t a0 = hmul2_bf16(hsub2_bf16((w & 0x000f000fu) | 0x43004300u, 0x43084308u), sg);
-                                const uint32_t a1 = hmul2_bf16(hsub2_bf16(((w >> 4) & 0x000f000fu) | 0x43004300u, 0x43084308u), sh);
-                                const uint32_t a2 = hmul2_bf16(hsub2_bf16(((w >> 8) & 0x000f000fu) | 0x43004300u, 0x43084308u), sg);
-                                const uint32_t a3 = hmul2_bf16(hsub2_bf16(((w >> 12) & 0x000f000fu) | 0x43004300u, 0x43084308u), sh);
+                                const uint32_t a0 = hmul2_bf16(hsub2_bf16(q_and_or(w, nib_mask, nib_magic), 0x43084308u), sg);
+                                const uint32_t a1 = hmul2_bf16(hsub2_bf16(q_and_or(w >> 4, nib_mask, nib_magic), 0x43084308u), sh);
+                                const uint32_t a2 = hmul2_bf16(hsub2_bf16(q_and_or(w >> 8, nib_mask, nib_magic), 0x43084308u), sg);
+                                const uint32_t a3 = hmul2_bf16(hsub2_bf16(q_and_or(w >> 12, nib_mask, nib_magic), 0x43084308u), sh);
                                 const uint32_t b0 = *reinterpret_cast<const uint32_t*>(xk + j * 16);
                                 const uint32_t b1 = *reinterpret_cast<const uint32_t*>(xk + j * 16 + 8);
                                 mma_bf16_16816(c, a0, a1, a2, a3, b0, b1);
