@@ -856,7 +856,7 @@ uint32_t decode_tc_min_rows()
 {
     static const uint32_t v = [] {
         const char* e = getenv("MC_TC_DECODE_MIN");
-        return e ? uint32_t(atoi(e)) : 9u;
+        return e ? uint32_t(atoi(e)) : 5u; // measured (1B, B200): 4 rows = one GEMV pass ties with the GEMM path; from 5 rows on the GEMV needs two passes and loses 2x
     }();
     return v;
 }
