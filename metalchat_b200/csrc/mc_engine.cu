@@ -889,11 +889,13 @@ void enqueue_rows_tc(mc_llama* m, launcher& L, uint32_t rows)
         uint16_t* vc = m->vcache.as<uint16_t>() + size_t(li) * kv_layer_elems(m);
         count(tc::rmsnorm_rows(s, n, x, ly.attn_norm.as<uint16_t>(), rows, D, c.norm_eps));
         count(tc_linear(m, s, tc::GEMM_STORE, n, D, ly.wqkv, 3 * rank, 3, qkv, nullptr, rows, QKV, D, QKV, sc));
-        count(tc::rope_append(s, qkv, q, kc, vc, m->fcos.as<float>(), m->fsin.as<float>(), rows, 0, 0, H, KV, hd, c.max_seq_len, m->row_seq.as<int32_t>(),
-                              m->pos.as<int32_t>()));
         if (tc::decode_attn_gqa_supported(H, KV, hd)) {
-            count(tc::decode_attn_gqa(s, q, kc, vc, attn, rows, m->row_seq.as<int32_t>(), m->pos.as<int32_t>(), H, KV, hd, c.max_seq_len, m->scale_bf16));
+            // RoPE, the KV append and the attention of the step in one launch
+            count(tc::decode_attn_gqa(s, nullptr, kc, vc, attn, rows, m->row_seq.as<int32_t>(), m->pos.as<int32_t>(), H, KV, hd, c.max_seq_len, m->scale_bf16, qkv,
+                                      m->fcos.as<float>(), m->fsin.as<float>()));
         } else {
+            count(tc::rope_append(s, qkv, q, kc, vc, m->fcos.as<float>(), m->fsin.as<float>(), rows, 0, 0, H, KV, hd, c.max_seq_len, m->row_seq.as<int32_t>(),
+                                  m->pos.as<int32_t>()));
             const attn_params a = attn_params_of(m, li, 0);
             const size_t smem = attn_smem(m, kAttnCluster);
             if (hd == 64) L.go_cluster(attn_decode_kernel<64>, dim3(H * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);

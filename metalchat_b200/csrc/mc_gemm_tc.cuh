@@ -768,9 +768,13 @@ template <int HD, bool POW2> __global__ void __launch_bounds__(256, HD == 64 ? 2
 // Same two passes and rounding points as the prompt kernel above; the four per-warp partial sums / outputs are joined in
 // warp order through shared memory.
 struct dattn_params {
-    const uint16_t* q;  // [rows, H*hd] rotated
-    const uint16_t* kc; // this layer: [n_seqs][KV][max_seq][hd]
-    const uint16_t* vc;
+    const uint16_t* q;  // [rows, H*hd] rotated (when qkv == nullptr)
+    const uint16_t* qkv; // or: [rows, (H + 2 KV) * hd] un-rotated q|k|v rows of this step -- the kernel rotates q and k (kernel/rope.metal:47-58)
+                         // and appends k', v to the cache itself (nn/cache.h:207-214), one launch less per block
+    const float* fcos;
+    const float* fsin;
+    uint16_t* kc;       // this layer: [n_seqs][KV][max_seq][hd]
+    uint16_t* vc;
     uint16_t* out;      // [rows, H*hd]
     const int32_t* row_seq;
     const int32_t* row_pos;
@@ -790,12 +794,47 @@ template <int HD, bool POW2> __global__ void __launch_bounds__(128) decode_attn_
     pdl_sync();
     const uint32_t seq = uint32_t(p.row_seq[row]), pos = uint32_t(p.row_pos[row]);
     const uint32_t n_keys = pos + 1, n_tiles = (n_keys + 63) / 64;
-    const uint16_t* kbase = p.kc + (size_t(seq) * p.KV + kvh) * p.max_seq * HD;
-    const uint16_t* vbase = p.vc + (size_t(seq) * p.KV + kvh) * p.max_seq * HD;
+    uint16_t* kbase = p.kc + (size_t(seq) * p.KV + kvh) * p.max_seq * HD;
+    uint16_t* vbase = p.vc + (size_t(seq) * p.KV + kvh) * p.max_seq * HD;
+    constexpr uint32_t half = HD / 2;
 
     // Q fragments: mma row g = query head kvh * n_rep + g (rows >= n_rep and rows 8..15 are zero padding)
     uint32_t qa[HD / 16][4];
-    {
+    if (p.qkv) {
+        const uint16_t* src = p.qkv + size_t(row) * (p.H + 2 * p.KV) * HD;
+        // this KV head's new key, rotated, and value go to the cache first (this CTA is the only reader of that cache row in this launch)
+        {
+            const uint16_t* ks = src + size_t(p.H + kvh) * HD;
+            for (uint32_t j = tid; j < half; j += 128) {
+                const float a = bf16_bits_to_f32(ks[j]), b = bf16_bits_to_f32(ks[j + half]);
+                const float cs = p.fcos[size_t(pos) * half + j], sn = p.fsin[size_t(pos) * half + j];
+                kbase[size_t(pos) * HD + j] = f32_to_bf16_bits(__fsub_rn(__fmul_rn(cs, a), __fmul_rn(sn, b)));
+                kbase[size_t(pos) * HD + j + half] = f32_to_bf16_bits(__fadd_rn(__fmul_rn(sn, a), __fmul_rn(cs, b)));
+            }
+            const uint16_t* vs = src + size_t(p.H + p.KV + kvh) * HD;
+            for (uint32_t c = tid; c < HD / 8; c += 128) *reinterpret_cast<uint4*>(vbase + size_t(pos) * HD + c * 8) = *reinterpret_cast<const uint4*>(vs + c * 8);
+        }
+        // q rows rotated in registers: the partner of element d < hd/2 is d + hd/2, the same lane's fragment HD/32 k-steps further
+        const bool valid = g < n_rep;
+        const uint16_t* ql = src + size_t(kvh * n_rep + (valid ? g : 0)) * HD;
+#pragma unroll
+        for (int ks = 0; ks < HD / 32; ks++) {
+#pragma unroll
+            for (int h8 = 0; h8 < 2; h8++) {
+                const uint32_t d = ks * 16 + h8 * 8 + 2 * t;
+                const uint32_t lo = *reinterpret_cast<const uint32_t*>(ql + d), hi = *reinterpret_cast<const uint32_t*>(ql + d + half);
+                const float2 cs = *reinterpret_cast<const float2*>(p.fcos + size_t(pos) * half + d), sn = *reinterpret_cast<const float2*>(p.fsin + size_t(pos) * half + d);
+                const float a0 = bf_lo(lo), a1 = bf_hi(lo), b0 = bf_lo(hi), b1 = bf_hi(hi);
+                const uint32_t r_lo = pack2(__fsub_rn(__fmul_rn(cs.x, a0), __fmul_rn(sn.x, b0)), __fsub_rn(__fmul_rn(cs.y, a1), __fmul_rn(sn.y, b1)));
+                const uint32_t r_hi = pack2(__fadd_rn(__fmul_rn(sn.x, a0), __fmul_rn(cs.x, b0)), __fadd_rn(__fmul_rn(sn.y, a1), __fmul_rn(cs.y, b1)));
+                qa[ks][h8 * 2] = valid ? r_lo : 0u;
+                qa[ks + HD / 32][h8 * 2] = valid ? r_hi : 0u;
+            }
+            qa[ks][1] = qa[ks][3] = qa[ks + HD / 32][1] = qa[ks + HD / 32][3] = 0u;
+        }
+        __threadfence(); // the appended cache row is read back through cp.async (L2) below
+        __syncthreads();
+    } else {
         const bool valid = g < n_rep;
         const uint16_t* ql = p.q + size_t(row) * p.H * HD + size_t(kvh * n_rep + (valid ? g : 0)) * HD;
 #pragma unroll

@@ -238,11 +238,14 @@ int prefill_attn(cudaStream_t stream, const uint16_t* q, const uint16_t* kcache_
     return 1;
 }
 
-int decode_attn_gqa(cudaStream_t stream, const uint16_t* q, const uint16_t* kcache_layer, const uint16_t* vcache_layer, uint16_t* out, uint32_t rows,
-                    const int32_t* row_seq, const int32_t* row_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, float scale)
+int decode_attn_gqa(cudaStream_t stream, const uint16_t* q, uint16_t* kcache_layer, uint16_t* vcache_layer, uint16_t* out, uint32_t rows,
+                    const int32_t* row_seq, const int32_t* row_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, float scale, const uint16_t* qkv,
+                    const float* fcos, const float* fsin)
 {
     MC_REQUIRE(decode_attn_gqa_supported(H, KV, hd), "batched decode attention: head_dim must be 64 or 128 and at most 8 query heads per KV head");
+    MC_REQUIRE(q || (qkv && fcos && fsin), "batched decode attention: rotated q rows, or un-rotated q|k|v rows with the rope tables");
     dattn_params p{};
+    p.qkv = qkv, p.fcos = fcos, p.fsin = fsin;
     p.q = q, p.kc = kcache_layer, p.vc = vcache_layer, p.out = out, p.row_seq = row_seq, p.row_pos = row_pos, p.H = H, p.KV = KV, p.max_seq = max_seq, p.scale = scale;
     const dim3 grid(KV, rows);
     const size_t smem = size_t(4) * 64 * (hd + 8) * 2 + 32 * sizeof(float);

@@ -36,8 +36,10 @@ int prefill_attn(cudaStream_t stream, const uint16_t* q, const uint16_t* kcache_
 // one decode step of `rows` sequences: row r attends keys 0 .. row_pos[r] of sequence row_seq[r]; the H / KV query heads of a KV head
 // share one pass over its cache (grouped-query attention)
 bool decode_attn_gqa_supported(uint32_t H, uint32_t KV, uint32_t hd);
-int decode_attn_gqa(cudaStream_t stream, const uint16_t* q, const uint16_t* kcache_layer, const uint16_t* vcache_layer, uint16_t* out, uint32_t rows,
-                    const int32_t* row_seq, const int32_t* row_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, float scale);
+// With qkv (un-rotated q|k|v rows of the step, [rows, (H + 2 KV) hd]) the kernel rotates q and k and appends k', v itself (q may be null).
+int decode_attn_gqa(cudaStream_t stream, const uint16_t* q, uint16_t* kcache_layer, uint16_t* vcache_layer, uint16_t* out, uint32_t rows,
+                    const int32_t* row_seq, const int32_t* row_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, float scale,
+                    const uint16_t* qkv = nullptr, const float* fcos = nullptr, const float* fsin = nullptr);
 
 // QLoRA on the tensor-core path: bf16 image of a group-quantised matrix, w = r(r(q) * r(s)) (kernel/mul.metal:76-77; group == K gives the
 // per-row scale of quantization::linear), and y2 = r(y + r(r(B . ax) * scale)) + the fused tail

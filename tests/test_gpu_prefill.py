@@ -194,6 +194,13 @@ def test_batched_decode_on_tensor_cores_matches_oracle(cfgd):
     tb, _ = b.decode_loop(firsts, pos, 5)
     for s in range(n):
         assert max_rel(unbf(a.logits(s)), unbf(b.logits(s))) < 2e-2, s
+    # the attention kernel of the batched path rotates q / k and appends k', v itself: the appended cache rows must be the GEMV path's
+    for s in (0, 7):
+        if np.array_equal(ta[:, s], tb[:, s]):  # same token history
+            n_pos = pos[s] + 5
+            for which in (0, 1):
+                ga, gb = a.cache(s, 0, which, n_pos)[pos[s]:].reshape(-1), b.cache(s, 0, which, n_pos)[pos[s]:].reshape(-1)
+                assert np.mean(ga == gb) > 0.97 and max_rel(unbf(ga), unbf(gb)) < 1e-2, (s, which)
     # sequences 3 and 10 against the oracle, token by token
     for s in (3, 10):
         o.forward(prompts[s], 0)
