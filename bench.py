@@ -87,6 +87,17 @@ def dist_env():
     return rank, world, local
 
 
+def host_threads_for_reference():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 alone and may use every host core it is
+    allowed to (set before the oracle library -- and with it the OpenMP runtime -- is loaded)."""
+    if "TORCHELASTIC_RUN_ID" in os.environ or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+        os.environ["OMP_NUM_THREADS"] = str(n)
+
+
 def cpu_baseline(shape: dict, quant: int, steps: int):
     """The oracle port of the reference path timed on this host's cores (checker code, timed as the baseline)."""
     from oracle import orc
@@ -107,6 +118,7 @@ def run_reference(args, shape, quant, workload):
     rank, world, _ = dist_env()
     if rank != 0:
         return
+    host_threads_for_reference()
     from oracle import orc
 
     cfg = orc.make_cfg(**shape, max_seq_len=1024, quant=quant)
@@ -187,6 +199,27 @@ def measure_gemv_family(capi, dev, shape, hbm_peak):
     return out, tot_b / tot_t / 1e9
 
 
+def init_dist(local: int):
+    """One process per GPU over NCCL.  The communicator is created (first collective) with stdout pointed at stderr: NCCL prints its
+    version banner on stdout, and this program's stdout carries exactly one JSON line."""
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local)
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    return dist
+
+
 def tensor_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -216,6 +249,7 @@ def run_prefill(args, shape_name, shape, quant=0):
     if args.impl == "reference":
         if rank != 0:
             return
+        host_threads_for_reference()
         from oracle import orc
 
         n = 64
@@ -235,12 +269,7 @@ def run_prefill(args, shape_name, shape, quant=0):
         return
     import torch
 
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dist = init_dist(local) if world > 1 else None
     from metalchat_b200 import capi
 
     dev = capi.Device(local)
@@ -377,12 +406,7 @@ def main():
     rank, world, local = dist_env()
     import torch
 
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dist = init_dist(local) if world > 1 else None
 
     from metalchat_b200 import capi
 
