@@ -338,14 +338,25 @@ __device__ __forceinline__ void gemv_body(const gemv_params& p, unsigned char* s
         const unsigned e = tp_wait(p.tp, reinterpret_cast<unsigned*>(sscr));
         const uint32_t parity = (e - 1) & 1u;
         const float* mine = p.tp.peer_buf[p.tp.rank];
+        // four consecutive k per thread, all loads of a row issued before the first use (a scalar loop serialised K / 256 L2 round trips:
+        // ~10 us per exchange, profiles/r01b_tp2_per_kernel_profile_8b_v2.txt); ranks are still summed in rank order
         for (uint32_t m = 0; m < p.rows; m++) {
-            for (uint32_t k = threadIdx.x; k < p.K; k += kGemvThreads) {
-                float sum = 0.0f;
-                for (uint32_t src = 0; src < p.tp.world; src++)
-                    sum += tp_slot(p.tp, const_cast<float*>(mine), parity, src)[size_t(m) * p.tp.dim + k];
-                const uint16_t h = f32_to_bf16_bits(__fadd_rn(bf16_bits_to_f32(p.tp_res[size_t(m) * p.ldx + k]), rbf(sum)));
-                sx[size_t(m) * p.K + k] = h;
-                if (blockIdx.x == 0) p.tp_out[size_t(m) * p.ldx + k] = h;
+#pragma unroll 2
+            for (uint32_t k = threadIdx.x * 4; k < p.K; k += kGemvThreads * 4) {
+                float4 part[kTpMaxWorld];
+#pragma unroll
+                for (uint32_t src = 0; src < uint32_t(kTpMaxWorld); src++)
+                    if (src < p.tp.world) part[src] = __ldcg(reinterpret_cast<const float4*>(tp_slot(p.tp, const_cast<float*>(mine), parity, src) + size_t(m) * p.tp.dim + k));
+                const uint2 rv = *reinterpret_cast<const uint2*>(p.tp_res + size_t(m) * p.ldx + k);
+                float4 sum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+                for (uint32_t src = 0; src < uint32_t(kTpMaxWorld); src++)
+                    if (src < p.tp.world) sum.x += part[src].x, sum.y += part[src].y, sum.z += part[src].z, sum.w += part[src].w;
+                uint2 hv;
+                hv.x = uint32_t(f32_to_bf16_bits(__fadd_rn(bf_lo(rv.x), rbf(sum.x)))) | (uint32_t(f32_to_bf16_bits(__fadd_rn(bf_hi(rv.x), rbf(sum.y)))) << 16);
+                hv.y = uint32_t(f32_to_bf16_bits(__fadd_rn(bf_lo(rv.y), rbf(sum.z)))) | (uint32_t(f32_to_bf16_bits(__fadd_rn(bf_hi(rv.y), rbf(sum.w)))) << 16);
+                *reinterpret_cast<uint2*>(sx + size_t(m) * p.K + k) = hv;
+                if (blockIdx.x == 0) *reinterpret_cast<uint2*>(p.tp_out + size_t(m) * p.ldx + k) = hv;
             }
         }
         __syncthreads();
