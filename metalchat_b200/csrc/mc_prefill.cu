@@ -148,8 +148,12 @@ uint32_t splitk_factor(uint32_t N, uint32_t K, int sm_count)
     static const int off = getenv("MC_TC_NO_SPLITK") != nullptr;
     const uint32_t tiles = (N + kSkBN - 1) / kSkBN, k_blocks = K / kTcBK;
     if (off || tiles * 2 >= 3 * uint32_t(sm_count)) return 0; // enough 256-row tiles for the persistent kernel
+    static const uint32_t ks_max = [] {
+        const char* e = getenv("MC_TC_KS_MAX"); // experiments: cap the cluster size of the k split
+        return e ? uint32_t(atoi(e)) : 8u;
+    }();
     uint32_t ks = 1;
-    while (ks < 8 && tiles * ks < uint32_t(sm_count) && k_blocks % (ks * 2) == 0 && k_blocks / (ks * 2) >= 2) ks *= 2;
+    while (ks < ks_max && tiles * ks < uint32_t(sm_count) && k_blocks % (ks * 2) == 0 && k_blocks / (ks * 2) >= 2) ks *= 2;
     return ks;
 }
 
