@@ -29,6 +29,7 @@ sys.path.insert(0, str(ROOT))
 SHAPES = {
     "1b": dict(dim=2048, n_layers=16, n_heads=32, n_kv_heads=8, head_dim=64, ffn_dim=8192, vocab=128256),
     "8b": dict(dim=4096, n_layers=32, n_heads=32, n_kv_heads=8, head_dim=128, ffn_dim=14336, vocab=128256),
+    "70b": dict(dim=8192, n_layers=80, n_heads=64, n_kv_heads=8, head_dim=128, ffn_dim=28672, vocab=128256),  # 141 GB in bf16: needs --tp
 }
 KV_LEN = 512
 METRIC = "decode_tokens_per_s"
