@@ -1,13 +1,19 @@
 #!/usr/bin/env python
-"""bench.py — decode tokens/s of the B200 engine on BASELINE.json's configs[1]
-(Llama-3.2-1B-shaped bf16, batch 1, 512-token KV cache, random-init weights, synthetic ids).
+"""bench.py — decode tokens/s of the B200 engine.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload 1b-bf16|1b-w4|1b-bf16-prefill|8b-bf16-prefill] [--batch B] [--per-op] [--prompt S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload 1b-bf16|1b-w4|8b-bf16|70b-bf16|*-prefill] [--batch B]
+                    [--per-op] [--prompt S] [--replicas] [--no-also]
 
-A "step" is one decode step (one token per sequence).  Prints ONE JSON line (see DESIGN.md
-"Measurement").  `value` is device-timed (CUDA events on the engine's stream, token fed back on
-the device); `e2e` goes through mc_llama_decode with host buffers every step (H2D ids/pos, D2H id).
-`--impl reference` times the CPU oracle port of the reference path (the reference is Metal-only).
+N = 1 (default): BASELINE.json configs[1] -- Llama-3.2-1B-shaped bf16, batch 1, 512-token KV cache, random-init weights, synthetic
+ids -- is the headline line; the other single-GPU workloads of the metric (1B int4 batch 1 = the north-star target, 1B bf16 batch 32,
+1B prefill 2048, 8B bf16 batch 1) are measured in the SAME run and ride in `also` so that the driver observes them too.
+N > 1: ONE Llama-3.1-8B-shaped bf16 model (configs[3], decode phase) sharded tensor-parallel over the N GPUs, the same workload at
+every N ("scaling": "strong"); its single-GPU figure is `also[workload == 8b-bf16]` of the N = 1 line and, measured again on rank 0 of
+the N > 1 run, `strong_scaling_base`.  `--replicas` runs N independent copies of the N = 1 workload instead (weak scaling).
+
+A "step" is one decode step (one token per sequence).  Prints ONE JSON line (see DESIGN.md "Measurement").  `value` is device-timed
+(CUDA events on the engine's stream, token fed back on the device); `e2e` goes through mc_llama_decode with host buffers every step
+(H2D ids/pos, D2H id).  `--impl reference` times the CPU oracle port of the reference path (the reference is Metal-only).
 """
 from __future__ import annotations
 
@@ -101,7 +107,13 @@ def host_threads_for_reference():
 
 def cpu_baseline(shape: dict, quant: int, steps: int):
     """The oracle port of the reference path timed on this host's cores (checker code, timed as the baseline)."""
+    host_threads_for_reference()
     from oracle import orc
+
+    try:  # torchrun exports OMP_NUM_THREADS=1 and an OpenMP runtime may already be up: size the pool explicitly
+        orc.set_num_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        orc.set_num_threads(os.cpu_count() or 1)
 
     cfg = orc.make_cfg(**shape, max_seq_len=1024, quant=quant)
     m = orc.Llama(cfg, orc.BF16)
@@ -122,6 +134,10 @@ def run_reference(args, shape, quant, workload):
     host_threads_for_reference()
     from oracle import orc
 
+    try:
+        orc.set_num_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        orc.set_num_threads(os.cpu_count() or 1)
     cfg = orc.make_cfg(**shape, max_seq_len=1024, quant=quant)
     m = orc.Llama(cfg, orc.BF16)
     m.init_random(0x5EED)
@@ -375,65 +391,38 @@ def run_prefill(args, shape_name, shape, quant=0):
         dist.destroy_process_group()
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=256)
-    ap.add_argument("--warmup", type=int, default=16)
-    ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="1b-bf16")
-    ap.add_argument("--batch", type=int, default=1)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-roofline", action="store_true", help="skip the isolated per-shape GEMV timing of the per-op path")
-    ap.add_argument("--roofline-gemv", action="store_true", help="add the isolated per-shape timing of the per-op GEMV kernel")
-    ap.add_argument("--per-op", action="store_true", help="per-op kernels under a CUDA graph instead of the streaming persistent kernel")
-    ap.add_argument("--prompt", type=int, default=2048, help="prompt length of the *-prefill workloads")
-    ap.add_argument("--tp", action="store_true", help="N > 1: ONE model sharded tensor-parallel over the N GPUs (strong scaling) instead of N replicas")
-    args = ap.parse_args()
-    args.warmup = max(3, args.warmup)
-    if args.workload.endswith("-prefill"):
-        shape_name, fmt = args.workload.split("-")[:2]
-        run_prefill(args, shape_name, SHAPES[shape_name], quant=0 if fmt == "bf16" else 1)
-        return
-    shape_name, fmt = args.workload.split("-")
+def workload_name(shape_name, fmt, batch, quant):
+    idx = {"1b": 1 if quant == 0 else 2, "8b": 3, "70b": 4}.get(shape_name, 1)
+    return f"llama-{'3.2' if shape_name == '1b' else '3.1'}-{shape_name} {fmt} decode, batch {batch}, {KV_LEN}-token KV cache (BASELINE.json configs[{idx}])"
+
+
+def measure_decode(capi, torch, dist, dev, shape_name, fmt, batch, steps, warmup, rank, world, local, tp_on=False, per_op=False, e2e=True,
+                   clocks_index=None, workload_key=None):
+    """One decode workload on this rank's GPU (or this rank's shard when tp_on): builds the model, fills a KV_LEN-token cache per
+    sequence with the engine's own prefill, warms up, then times `steps` decode steps (CUDA events on the engine's stream inside
+    mc_llama_decode_loop; max over ranks) and the same number of steps through the per-token call with host buffers."""
     shape = SHAPES[shape_name]
     quant = 0 if fmt == "bf16" else 1
-    workload = f"llama-3.2-{shape_name} {fmt} decode, batch {args.batch}, {KV_LEN}-token KV cache (BASELINE.json configs[{1 if quant == 0 else 2}])"
-
-    if args.impl == "reference":
-        run_reference(args, shape, quant, workload)
-        return
-
-    rank, world, local = dist_env()
-    import torch
-
-    dist = init_dist(local) if world > 1 else None
-
-    from metalchat_b200 import capi
-
-    dev = capi.Device(local)
-    steps = min(args.steps, 1024 - KV_LEN - args.warmup - 8)
-    tp_on = args.tp and world > 1
-    flags = (capi.LLAMA_W4_PACKED if quant else 0) | (capi.LLAMA_NO_STREAM if args.per_op else 0)
+    flags = (capi.LLAMA_W4_PACKED if quant else 0) | (capi.LLAMA_NO_STREAM if per_op else 0)
+    steps = max(1, min(steps, 1024 - KV_LEN - warmup - 8))
     if tp_on:
         from metalchat_b200 import tp
 
-        m = tp.create(dev, **shape, max_seq_len=1024, quant=quant, n_seqs=args.batch, flags=flags)
+        m = tp.create(dev, **shape, max_seq_len=1024, quant=quant, n_seqs=batch, flags=flags)
     else:
-        m = capi.Llama(dev, capi.llama_config(**shape, max_seq_len=1024, quant=quant, n_seqs=args.batch, flags=flags))
+        m = capi.Llama(dev, capi.llama_config(**shape, max_seq_len=1024, quant=quant, n_seqs=batch, flags=flags))
     m.init_random(0x5EED)
     m.finalize()
     streamed, resident = m.weight_bytes()
-    B = args.batch
-    # KV cache: KV_LEN positions per sequence written by the engine's own prefill of hash-generated ids
+    B = batch
     rng = np.random.default_rng(0x5EED + (0 if tp_on else rank))  # tensor parallel: every rank feeds the same ids
-    for s in range(B):
-        m.prefill(rng.integers(0, shape["vocab"], size=KV_LEN, dtype=np.int32), 0, s)
+    for sq in range(B):
+        m.prefill(rng.integers(0, shape["vocab"], size=KV_LEN, dtype=np.int32), 0, sq)
     if tp_on:
         # the vocabulary is sharded: one greedy step on the device gives every rank the global argmax
         first = m.decode(np.zeros(B, np.int32), np.full(B, KV_LEN, np.int32)).tolist()
     else:
-        first = [int(np.argmax((m.logits(s).astype(np.uint32) << 16).view(np.float32))) for s in range(B)]
+        first = [int(np.argmax((m.logits(sq).astype(np.uint32) << 16).view(np.float32))) for sq in range(B)]
     pos0 = [KV_LEN] * B
 
     def barrier():
@@ -442,75 +431,209 @@ def main():
             torch.cuda.synchronize()
             dist.barrier()
 
-    # warm-up (instantiates the CUDA graph), then the timed region
-    m.decode_loop(first, pos0, args.warmup)
+    m.decode_loop(first, pos0, warmup)  # warm-up (instantiates the CUDA graph)
     barrier()
     l0 = dev.launches()
-    with ClockSampler(local) as clocks:
+    sampler = ClockSampler(local if clocks_index is None else clocks_index)
+    with sampler as clocks:
         barrier()
-        toks, ms = m.decode_loop(first, [KV_LEN + args.warmup] * B, steps)
+        toks, ms = m.decode_loop(first, [KV_LEN + warmup] * B, steps)
         barrier()
-        # end-to-end through the public per-token call with host buffers
-        ids = np.array(first, np.int32)
-        t0 = time.perf_counter()
-        for i in range(steps):
-            ids = m.decode(ids, np.full(B, KV_LEN + args.warmup + i, np.int32))
-        dev.synchronize()
-        e2e_s = time.perf_counter() - t0
+        e2e_ms = None
+        if e2e:
+            ids = np.array(first, np.int32)
+            t0 = time.perf_counter()
+            for i in range(steps):
+                ids = m.decode(ids, np.full(B, KV_LEN + warmup + i, np.int32))
+            dev.synchronize()
+            e2e_ms = (time.perf_counter() - t0) * 1e3
     launches = dev.launches() - l0
     if dist is not None:
-        t = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, e2e_ms or 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
-    else:
-        e2e_ms = e2e_s * 1e3
+        ms, e2e_max = float(t[0]), float(t[1])
+        e2e_ms = e2e_max if e2e else None
+    hbm_peak, peak_src = peaks()
+    tokens = steps * B * (1 if tp_on else world)
+    kv_bytes = 2 * shape["n_layers"] * (shape["n_kv_heads"] // (world if tp_on else 1)) * shape["head_dim"] * 2 * (KV_LEN + warmup + steps // 2) * B
+    step_bytes = streamed + kv_bytes
+    step_gbs = step_bytes / (ms * 1e-3 / steps) / 1e9
+    streaming = m.launches_per_step() == 1
+    kname = ("decode_stream_kernel (persistent: the whole decode step is one kernel; `steps` steps per launch)" if streaming
+             else "whole decode step (per-op kernels under one CUDA graph; the GEMV / GEMM family streams >97% of the bytes)")
+    # algorithmic bytes of one step (weights + norms + adaptors streamed once, KV read once) / device time of one step, both of the
+    # timed region above (CUDA events on the engine's stream around the launches)
+    roof = {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak, "traffic": None,
+            "kernel": kname, "peak_source": peak_src, "algorithmic_bytes_per_step": step_bytes}
+    ncu = ROOT / "profiles" / "r02_ncu_stream_summary.json"
+    if not ncu.exists():
+        ncu = ROOT / "profiles" / "r01_ncu_stream_summary.json"
+    if streaming and ncu.exists():
+        try:
+            t = json.loads(ncu.read_text()).get((workload_key or f"{shape_name}-{fmt}") if B == 1 else "", {})
+            if t:
+                roof["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
+                roof["traffic_source"] = t.get("source", "ncu --set full, one launch of one step") + f" ({ncu.name})"
+        except Exception:
+            pass
+    res = {
+        "workload": workload_name(shape_name, fmt, B, quant), "shape": shape, "quant": quant, "batch": B, "steps": steps, "ms": ms, "tokens": tokens,
+        "value": tokens / (ms * 1e-3), "ms_per_step": ms / steps, "e2e_value": (tokens / (e2e_ms * 1e-3)) if e2e_ms else None,
+        "e2e_ms_per_step": (e2e_ms / steps) if e2e_ms else None, "launches": int(launches), "launches_per_step": m.launches_per_step(),
+        "streaming": streaming, "streamed": streamed, "resident": resident, "roofline": roof, "clocks": clocks.summary(),
+        "dtype": "bf16" if quant == 0 else "bf16 activations, int4 weights (bf16 dequant), fp32 accumulate",
+    }
+    m.close()
+    return res
+
+
+def measure_prefill_brief(capi, torch, dev, shape_name, quant, S, steps, warmup):
+    """Prompt throughput of one sequence on this GPU for the `also` list (the full line: --workload 1b-bf16-prefill)."""
+    shape = SHAPES[shape_name]
+    m = capi.Llama(dev, capi.llama_config(**shape, max_seq_len=S, quant=quant, n_seqs=1, flags=capi.LLAMA_W4_PACKED if quant else 0))
+    m.init_random(0x5EED)
+    m.finalize()
+    rng = np.random.default_rng(0x5EED)
+    prompts = [rng.integers(0, shape["vocab"], size=S, dtype=np.int32) for _ in range(4)]
+    for i in range(warmup):
+        m.prefill(prompts[i % 4], 0, 0)
+    dev.synchronize()
+    st = torch.cuda.ExternalStream(dev.stream())
+    l0 = dev.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for i in range(steps):
+        m.prefill(prompts[i % 4], 0, 0)
+    e1.record(st)
+    dev.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = dev.launches() - l0
+    t0 = time.perf_counter()
+    for i in range(steps):
+        m.prefill(prompts[i % 4], 0, 0)
+        m.logits(0)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    lin, att, head = prefill_flops(shape, S)
+    peak, peak_src = tensor_peak()
+    tf = (lin + att + head) / (ms / steps * 1e-3) / 1e12
+    m.close()
+    return {"workload": f"llama-{shape_name} {'QLoRA int4' if quant else 'bf16'} prefill of {S} positions (BASELINE.json configs[3] prompt phase, 1B shape), 1 sequence",
+            "metric": "prefill_tokens_per_s", "value": steps * S / (ms * 1e-3), "unit": "tokens/s", "steps": steps, "ms_per_step": ms / steps,
+            "e2e": {"value": steps * S / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 4 * S, "d2h_bytes_per_step": 2 * shape["vocab"]},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "whole prompt step (tcgen05 GEMMs + causal attention)", "algorithmic_flops_per_step": lin + att + head}}
+
+
+def brief(res):
+    """Compact `also` entry of a decode measurement."""
+    r = res["roofline"]
+    return {"workload": res["workload"], "metric": METRIC, "value": res["value"], "unit": "tokens/s", "steps": res["steps"], "ms_per_step": res["ms_per_step"],
+            "dtype": res["dtype"], "path": "streaming persistent kernel" if res["streaming"] else "per-op kernels + CUDA graph",
+            "e2e": {"value": res["e2e_value"], "unit": "tokens/s", "h2d_bytes_per_step": 8 * res["batch"], "d2h_bytes_per_step": 4 * res["batch"]},
+            "gpu_launches": res["launches"], "launches_per_step": res["launches_per_step"],
+            "roofline": {k: r[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "algorithmic_bytes_per_step")},
+            "clocks": res["clocks"]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default=None, help="default: 1b-bf16 on one GPU (configs[1]), 8b-bf16 tensor-parallel on several (configs[3])")
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the isolated per-shape GEMV timing of the per-op path")
+    ap.add_argument("--roofline-gemv", action="store_true", help="add the isolated per-shape timing of the per-op GEMV kernel")
+    ap.add_argument("--per-op", action="store_true", help="per-op kernels under a CUDA graph instead of the streaming persistent kernel")
+    ap.add_argument("--prompt", type=int, default=2048, help="prompt length of the *-prefill workloads")
+    ap.add_argument("--tp", action="store_true", help="N > 1: ONE model sharded tensor-parallel over the N GPUs (the default for N > 1)")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: N independent replicas of the single-GPU workload (weak scaling) instead of one sharded model")
+    ap.add_argument("--no-also", action="store_true", help="N = 1 default line: skip the additional workloads of the `also` list")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    rank, world, local = dist_env()
+    tp_on = world > 1 and not args.replicas
+    default_line = args.workload is None and args.batch == 1 and not args.per_op
+    if args.workload is None:
+        args.workload = "8b-bf16" if tp_on else "1b-bf16"
+    if args.workload.endswith("-prefill"):
+        shape_name, fmt = args.workload.split("-")[:2]
+        run_prefill(args, shape_name, SHAPES[shape_name], quant=0 if fmt == "bf16" else 1)
+        return
+    shape_name, fmt = args.workload.split("-")
+    shape = SHAPES[shape_name]
+    quant = 0 if fmt == "bf16" else 1
+    workload = workload_name(shape_name, fmt, args.batch, quant)
+
+    if args.impl == "reference":
+        run_reference(args, shape, quant, workload)
+        return
+
+    import torch
+
+    dist = init_dist(local) if world > 1 else None
+
+    from metalchat_b200 import capi
+
+    dev = capi.Device(local)
+    base = None
+    if tp_on and default_line and rank == 0:
+        # strong-scaling base: the same workload on ONE GPU (this rank's), measured in this run before the sharded model
+        try:
+            b = measure_decode(capi, torch, None, dev, shape_name, fmt, args.batch, min(args.steps, 64), args.warmup, 0, 1, local, e2e=False)
+            base = {"n_gpus": 1, "value": b["value"], "unit": "tokens/s", "ms_per_step": b["ms_per_step"], "roofline_frac": b["roofline"]["frac"],
+                    "how": "same workload on one GPU (rank 0's), measured in this run before the sharded model"}
+        except Exception as e:  # e.g. the model does not fit one GPU
+            base = {"n_gpus": 1, "unavailable": str(e)[:200]}
+    res = measure_decode(capi, torch, dist, dev, shape_name, fmt, args.batch, args.steps, args.warmup, rank, world, local, tp_on=tp_on, per_op=args.per_op)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    hbm_peak, peak_src = peaks()
-    tokens = steps * B * (1 if tp_on else world)
-    value = tokens / (ms * 1e-3)
-    kv_bytes = 2 * shape["n_layers"] * shape["n_kv_heads"] * shape["head_dim"] * 2 * (KV_LEN + args.warmup + steps // 2) * B
-    step_bytes = streamed + kv_bytes
-    step_gbs = step_bytes / (ms * 1e-3 / steps) / 1e9
-    streaming = m.launches_per_step() == 1
-    kname = ("decode_stream_kernel (persistent: the whole decode step is one kernel; `steps` steps per launch)" if streaming
-             else "whole decode step (per-op kernels under one CUDA graph; the GEMV family streams >97% of the bytes)")
-    # algorithmic bytes of one step (weights + norms + adaptors streamed once, KV read once) / device time of one step, both of the
-    # timed region above (CUDA events on the engine's stream around the launches)
-    roof = {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak, "traffic": None,
-            "kernel": kname, "peak_source": peak_src, "algorithmic_bytes_per_step": step_bytes}
-    ncu = ROOT / "profiles" / "r01_ncu_stream_summary.json"
-    if streaming and ncu.exists():
-        try:
-            t = json.loads(ncu.read_text()).get(args.workload if B == 1 else "", {})
-            if t:
-                roof["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
-                roof["traffic_source"] = t.get("source", "ncu --set full, one launch of one step")
-        except Exception:
-            pass
+    roof = res["roofline"]
     if args.roofline_gemv and quant == 0:
+        hbm_peak, _ = peaks()
         per, fam = measure_gemv_family(capi, dev, shape, hbm_peak)
         roof.update({"per_op_gemv_family": {"achieved": fam, "frac": fam / hbm_peak, "per_shape": per,
                                             "note": "isolated CUDA-event timing of the per-op GEMV kernel, weights cycled through a >L2 ring"}})
+    B = args.batch
     line = {
-        "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
-        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong" if tp_on else "weak", "vs_baseline": None,
-        "dtype": "bf16" if quant == 0 else "bf16 activations, int4 weights (bf16 dequant), fp32 accumulate",
+        "metric": METRIC, "value": res["value"], "unit": "tokens/s", "n_gpus": world, "steps": res["steps"], "warmup": args.warmup,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong" if tp_on else "weak", "vs_baseline": None,
+        "dtype": res["dtype"],
         "data": "synthetic ids, random-init weights (counter-hash seed 0x5EED)",
-        "config": {"workload": workload, "kv_len": KV_LEN, "batch": B, "parallelism": (f"tp{world}: column/row-split blocks, all-reduce fused into the GEMV kernels over NVLink peer memory; roofline per GPU shard"
+        "config": {"workload": workload, "kv_len": KV_LEN, "batch": B,
+                   "parallelism": (f"tp{world}: ONE model, column/row-split blocks, all-reduce fused into the GEMV kernels over NVLink peer memory; roofline per GPU shard"
                                    if tp_on else f"{world} replica(s), one sequence stream per GPU"),
-                   "path": "streaming persistent kernel" if streaming else "per-op kernels + CUDA graph",
-                   "l2": f"weights streamed per step {streamed / 1e6:.0f} MB > 126 MB L2 (no flush needed)"},
-        "e2e": {"value": tokens / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4 * B,
-                "ms_per_step": e2e_ms / steps},
-        "gpu_launches": int(launches), "launches_per_step": m.launches_per_step(),
-        "clocks": clocks.summary(), "roofline": roof,
+                   "path": "streaming persistent kernel" if res["streaming"] else "per-op kernels + CUDA graph",
+                   "l2": f"weights streamed per step {res['streamed'] / 1e6:.0f} MB > 126 MB L2 (no flush needed)"},
+        "e2e": {"value": res["e2e_value"], "unit": "tokens/s", "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4 * B,
+                "ms_per_step": res["e2e_ms_per_step"]},
+        "gpu_launches": res["launches"], "launches_per_step": res["launches_per_step"],
+        "clocks": res["clocks"], "roofline": roof,
     }
+    if base is not None:
+        line["strong_scaling_base"] = base
+    if default_line and world == 1 and not args.no_also:
+        # the other single-GPU workloads of BASELINE.json's metric, measured in the same run (bounded: ~64 steps each)
+        also = []
+        k = min(args.steps, 64)
+        for sn, f, b in (("1b", "w4", 1), ("1b", "bf16", 32), ("8b", "bf16", 1)):
+            try:
+                also.append(brief(measure_decode(capi, torch, None, dev, sn, f, b, k, args.warmup, 0, 1, local)))
+            except Exception as e:
+                also.append({"workload": workload_name(sn, f, b, 0 if f == "bf16" else 1), "unavailable": str(e)[:300]})
+        try:
+            also.append(measure_prefill_brief(capi, torch, dev, "1b", 0, 2048, 8, 3))
+        except Exception as e:
+            also.append({"workload": "llama-1b bf16 prefill of 2048 positions", "unavailable": str(e)[:300]})
+        line["also"] = also
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(shape, quant, 24)
+        line["cpu_baseline"] = cpu_baseline(shape, quant, 24 if shape_name == "1b" else 4)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

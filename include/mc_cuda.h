@@ -89,6 +89,7 @@ MC_API mc_status mc_heap_destroy(mc_heap* heap);
  * "cumsum_2_bfloat", "hadamard_broadcast_bfloat_int8_t_float" (accelerator.h:175-218).
  * All 71 names of metalchat.metallib resolve.                  */
 MC_API mc_status mc_kernel_lookup(mc_device* dev, const char* name, mc_kernel** out);
+MC_API mc_status mc_kernel_release(mc_kernel* k);                  /* the shared_kernel handle goes out of scope (metal.h:27-28) */
 MC_API mc_status mc_kernel_name(mc_kernel* k, const char** out);
 MC_API mc_status mc_kernel_max_threads(mc_kernel* k, size_t* out); /* 1024, src/kernel.cc:75-79 */
 MC_API mc_status mc_kernel_count(int* count);
@@ -135,8 +136,10 @@ enum {
     MC_LLAMA_MEGAKERNEL = 1u << 3, /* experimental: the whole decode step as ONE persistent kernel with grid barriers */
     MC_LLAMA_NO_STREAM = 1u << 4,  /* do not use the streaming persistent kernel (TMA weight ring): per-op kernels under a CUDA graph */
     MC_LLAMA_NO_TC_PREFILL = 1u << 5, /* prompts go through the 4-row GEMV kernels instead of the tcgen05 GEMM path */
-    MC_LLAMA_NO_SHADOW = 1u << 6      /* quantised models: do not keep the resident bf16 image (2 bytes per weight) that the tensor-core
+    MC_LLAMA_NO_SHADOW = 1u << 6,     /* quantised models: do not keep the resident bf16 image (2 bytes per weight) that the tensor-core
                                          prompt / batch path multiplies; prompts and batches then take the packed GEMV kernels */
+    MC_LLAMA_REF_CHUNK_MASK = 1u << 7 /* prompts of len > 1 at start_pos > 0 do NOT see the cached prefix, exactly like make_causal_mask
+                                         (nn/attention.h:283-299 leaves those columns at -inf); default: the prefix is visible */
 };
 typedef struct mc_sampler_config {
     uint32_t mode;       /* 0 greedy argmax (lowest index on ties); 1 top-k -> nucleus -> multinomial (nn/sampling.h:306-316) */
@@ -204,6 +207,20 @@ MC_API mc_status mc_linear_bf16(mc_device* dev, mc_buffer* y, mc_buffer* x, mc_b
  * K % 64 == 0, N % 32 == 0.  Runs `iters` times; elapsed_ms (may be NULL) receives the CUDA-event time of all of them. */
 MC_API mc_status mc_gemm_bf16(mc_device* dev, mc_buffer* y, mc_buffer* x, mc_buffer* w, mc_buffer* res, uint32_t M, uint32_t N, uint32_t K, int mode,
                               uint32_t iters, float* elapsed_ms);
+/* Decode attention of `rows` single-position queries (nn/attention.h:161-206 from the scores on: bmm, scalar_mul by T(1/sqrt(hd)),
+ * softmax without max shift, bmm; repeat_kv replaced by kv = head / (H / KV)): q, out [rows, H*hd] bf16 (q already rotated), caches
+ * [n_seqs][KV][max_seq][hd] bf16, row r attends positions 0 .. row_pos[r] of sequence row_seq[r] (host arrays).
+ * kernel 0: attn_decode_kernel (per (row, head), cached positions split over a 4-CTA cluster); 1: decode_attn_gqa_kernel (per
+ * (row, KV head), tensor-core tiles, the query heads of a KV head share one pass over its cache). */
+MC_API mc_status mc_attn_decode(mc_device* dev, mc_buffer* out, mc_buffer* q, mc_buffer* kcache, mc_buffer* vcache, uint32_t rows, const int32_t* row_seq,
+                                const int32_t* row_pos, uint32_t n_seqs, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, int kernel);
+/* Causal prompt attention (the same chain with make_causal_mask, nn/attention.h:283-299): `rows` consecutive positions of sequence `seq`
+ * starting at start_pos; row i sees cache positions key_begin .. start_pos + i (key_begin = start_pos is the reference's chunk mask, Q9). */
+MC_API mc_status mc_attn_prefill(mc_device* dev, mc_buffer* out, mc_buffer* q, mc_buffer* kcache, mc_buffer* vcache, uint32_t rows, uint32_t seq, uint32_t start_pos,
+                                 uint32_t key_begin, uint32_t n_seqs, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq);
+/* Embedding gather of the engine (kernel/embedding.metal:25-70): out[r, :] = table[ids[r], :]; with row_scales (fp32 [vocab]) the table is
+ * int8 and the row is dequantised like lora_embedding, r(r(q) * r(s)) (quantization/lora.h:160-170, kernel/mul.metal:76-77). */
+MC_API mc_status mc_embed_rows(mc_device* dev, mc_buffer* out, mc_buffer* table, mc_buffer* row_scales, const int32_t* ids, uint32_t rows, uint32_t D, uint32_t vocab);
 /* QLoRA base linear over packed int4 (quantization/lora.h:94-122 + kernel/mul.metal:59-85 fused, without the adaptor):
  * y[M,N] = r( x[M,K] . r(r(q) * r(s))^T ), M <= 8.  w4 / scales_packed come from mc_pack_w4. */
 MC_API mc_status mc_linear_w4(mc_device* dev, mc_buffer* y, mc_buffer* x, mc_buffer* w4, mc_buffer* scales_packed, uint32_t M, uint32_t N, uint32_t K);

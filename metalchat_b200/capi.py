@@ -16,7 +16,7 @@ LIB_PATH = HERE / "libmc_cuda.so"
 
 MC_OK, MC_ERR_INVALID, MC_ERR_RUNTIME, MC_ERR_ALLOC, MC_ERR_NOT_FOUND, MC_ERR_FULL = range(6)
 MEM_DEVICE, MEM_SHARED, MEM_PINNED = 0, 1, 2
-LLAMA_W4_PACKED, LLAMA_NO_GRAPH, LLAMA_NO_PDL, LLAMA_MEGAKERNEL, LLAMA_NO_STREAM, LLAMA_NO_TC_PREFILL, LLAMA_NO_SHADOW = 1, 2, 4, 8, 16, 32, 64
+LLAMA_W4_PACKED, LLAMA_NO_GRAPH, LLAMA_NO_PDL, LLAMA_MEGAKERNEL, LLAMA_NO_STREAM, LLAMA_NO_TC_PREFILL, LLAMA_NO_SHADOW, LLAMA_REF_CHUNK_MASK = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 class McError(RuntimeError):
@@ -89,6 +89,7 @@ _SIGNATURES = {
     "mc_heap_reset": (C.c_int, [C.c_void_p]),
     "mc_heap_destroy": (C.c_int, [C.c_void_p]),
     "mc_kernel_lookup": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mc_kernel_release": (C.c_int, [C.c_void_p]),
     "mc_kernel_name": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p)]),
     "mc_kernel_max_threads": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
     "mc_kernel_count": (C.c_int, [C.POINTER(C.c_int)]),
@@ -126,6 +127,11 @@ _SIGNATURES = {
     "mc_linear_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "mc_gemm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32,
                                C.POINTER(C.c_float)]),
+    "mc_attn_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                 C.c_uint32, C.c_uint32, C.c_int]),
+    "mc_attn_prefill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                  C.c_uint32, C.c_uint32, C.c_uint32]),
+    "mc_embed_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "mc_linear_w4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "mc_pack_w4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
     "mc_w4_sizes": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
@@ -287,6 +293,17 @@ class Kernel:
         n = C.c_size_t()
         check(lib().mc_kernel_max_threads(self.h, C.byref(n)))
         return n.value
+
+    def release(self):
+        if self.h:
+            lib().mc_kernel_release(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 class CommandBuffer:
@@ -482,3 +499,39 @@ def sample_default(dev: Device, logits_bf16: np.ndarray, uniforms, top_k=50, tem
     ch, tok = np.zeros(rows, np.int32), np.zeros(rows, np.int32)
     check(lib().mc_sample_default(dev.h, buf.h, rows, vocab, C.byref(cfg), _vp(u), _vp(topk), _vp(ps), _vp(pi), _vp(ch), _vp(tok)))
     return dict(topk_idx=topk, probs_sorted=ps, probs_idx=pi, choice=ch, token=tok)
+
+
+def _cache_to_device_layout(c: np.ndarray) -> np.ndarray:
+    """[n_seqs, pos, KV, hd] (the reference's cache layout, nn/cache.h:150-160) -> the engine's [n_seqs, KV, pos, hd]."""
+    return np.ascontiguousarray(np.transpose(c, (0, 2, 1, 3)))
+
+
+def attn_decode(dev: Device, q: np.ndarray, kcache: np.ndarray, vcache: np.ndarray, row_seq, row_pos, kernel: int = 0) -> np.ndarray:
+    """q [rows, H, hd] bf16 bits (rotated); caches [n_seqs, max_seq, KV, hd] bf16 bits -> out [rows, H, hd]."""
+    rows, H, hd = q.shape
+    n_seqs, max_seq, KV, _ = kcache.shape
+    dq, dk, dv = dev.upload(np.ascontiguousarray(q, np.uint16)), dev.upload(_cache_to_device_layout(kcache)), dev.upload(_cache_to_device_layout(vcache))
+    out = dev.alloc(rows * H * hd * 2)
+    rs, rp = np.ascontiguousarray(row_seq, np.int32), np.ascontiguousarray(row_pos, np.int32)
+    check(lib().mc_attn_decode(dev.h, out.h, dq.h, dk.h, dv.h, rows, _vp(rs), _vp(rp), n_seqs, H, KV, hd, max_seq, kernel))
+    return out.read(np.uint16).reshape(rows, H, hd)
+
+
+def attn_prefill(dev: Device, q: np.ndarray, kcache: np.ndarray, vcache: np.ndarray, start_pos: int, key_begin: int = 0, seq: int = 0) -> np.ndarray:
+    rows, H, hd = q.shape
+    n_seqs, max_seq, KV, _ = kcache.shape
+    dq, dk, dv = dev.upload(np.ascontiguousarray(q, np.uint16)), dev.upload(_cache_to_device_layout(kcache)), dev.upload(_cache_to_device_layout(vcache))
+    out = dev.alloc(rows * H * hd * 2)
+    check(lib().mc_attn_prefill(dev.h, out.h, dq.h, dk.h, dv.h, rows, seq, start_pos, key_begin, n_seqs, H, KV, hd, max_seq))
+    return out.read(np.uint16).reshape(rows, H, hd)
+
+
+def embed_rows(dev: Device, table: np.ndarray, ids, row_scales: np.ndarray | None = None) -> np.ndarray:
+    """table [vocab, D]: uint16 bf16 bits, or int8 with fp32 row_scales [vocab]."""
+    vocab, D = table.shape
+    ids = np.ascontiguousarray(ids, np.int32)
+    dt = dev.upload(np.ascontiguousarray(table))
+    ds = dev.upload(np.ascontiguousarray(row_scales, np.float32)) if row_scales is not None else None
+    out = dev.alloc(len(ids) * D * 2)
+    check(lib().mc_embed_rows(dev.h, out.h, dt.h, ds.h if ds is not None else None, _vp(ids), len(ids), D, vocab))
+    return out.read(np.uint16).reshape(len(ids), D)

@@ -148,7 +148,10 @@ struct mc_device {
     cudaStream_t stream = nullptr;
     cudaDeviceProp prop{};
     std::atomic<uint64_t> launches{0};
-    // scratch for op-level kernels that need it (multi-pass sort etc.)
+    // per-device state of the op-level kernels (one process may drive several GPUs)
+    int* bad_ids = nullptr;      // device view of the flag below
+    int* bad_ids_host = nullptr; // mapped pinned int: an embedding kernel saw an out-of-range id (read back by mc_wait)
+    bool sampler_configured = false;
 };
 
 struct mc_buffer {
@@ -180,6 +183,7 @@ constexpr int kMaxSlots = 16;
 
 struct arg_pack {
     arg_slot slot[kMaxSlots];
+    mc_device* dev = nullptr; // the device the kernel is dispatched on (per-device scratch lives there)
     // typed accessors used by the launchers; throw invalid_argument on a mismatch
     template <int N> layout<N> lay(int i) const
     {

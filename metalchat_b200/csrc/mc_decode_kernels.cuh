@@ -630,6 +630,7 @@ struct attn_params {
     const int32_t* row_pos;
     uint32_t n_heads, n_kv_heads, max_seq;
     float scale;            // r(1/sqrt(hd)) stored as T (nn/attention.h:88,115; quirk Q4)
+    uint32_t key_begin;     // first visible cache position (0; the start of the chunk under the reference's chunk mask, quirk Q9)
 };
 
 constexpr int kAttnCluster = 4; // CTAs per (head, row): split of the cached positions, joined through DSMEM
@@ -676,8 +677,9 @@ __device__ __forceinline__ void attn_body(const attn_params& p, unsigned char* s
     const size_t coff = kv_off + (size_t(seq) * p.n_kv_heads + kvh) * p.max_seq * HD;
     const uint16_t* Kc = p.kcache + coff;
     const uint16_t* Vc = p.vcache + coff;
-    const uint32_t chunk = ((P + CL * SLOTS - 1) / (CL * SLOTS)) * SLOTS; // multiple of SLOTS
-    const uint32_t t0 = crank * chunk;
+    const uint32_t kb = min(p.key_begin, P - 1);                               // keys [kb, P) are visible
+    const uint32_t chunk = ((P - kb + CL * SLOTS - 1) / (CL * SLOTS)) * SLOTS; // multiple of SLOTS
+    const uint32_t t0 = min(P, kb + crank * chunk);
     const uint32_t t1 = min(P, t0 + chunk);
     const uint32_t slot = threadIdx.x / LPP, dl = threadIdx.x % LPP;
     const bool vpre = chunk <= IT * SLOTS; // the whole chunk fits one block of loads: fetch V together with K

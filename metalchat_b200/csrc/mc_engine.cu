@@ -85,6 +85,8 @@ struct mc_llama {
     uint32_t Hl = 0, KVl = 0, Fl = 0, Vl = 0; // local (sharded) dims
     bool finalized = false;
     bool tied = true;
+    uint32_t key_begin = 0;     // first visible cache position of the prompt call in flight (MC_LLAMA_REF_CHUNK_MASK: its start_pos)
+    bool image_a_dirty = false; // an adaptor A was replaced after the resident bf16 image had been built: its rows are re-copied by finalize
     std::vector<dlayer> layers;
     dbuf layer_arena;          // all per-layer weights, one fixed stride per layer (the megakernel indexes by layer)
     size_t layer_stride = 0;
@@ -346,6 +348,7 @@ attn_params attn_params_of(mc_llama* m, uint32_t li, uint32_t row0)
     a.out = m->attn.as<uint16_t>() + size_t(row0) * m->Hl * c.head_dim;
     a.row_seq = m->row_seq.as<int32_t>() + row0, a.row_pos = m->pos.as<int32_t>() + row0;
     a.n_heads = m->Hl, a.n_kv_heads = m->KVl, a.max_seq = c.max_seq_len, a.scale = m->scale_bf16;
+    a.key_begin = m->key_begin;
     return a;
 }
 gemv_params wo_params(mc_llama* m, uint32_t li, uint32_t row0, uint32_t rows)
@@ -780,10 +783,9 @@ void launch_sampler(launcher& L, sample_params sp, const mc_sampler_config& sc, 
     const float temp_t = bf16_bits_to_f32(f32_to_bf16_bits(sc.temperature));       // T(temperature)
     sp.inv_t = bf16_bits_to_f32(f32_to_bf16_bits(1.0f / temp_t));                   // T(1 / T(temperature))
     sp.top_p = bf16_bits_to_f32(f32_to_bf16_bits(sc.top_p));
-    static bool configured = false;
-    if (!configured) {
+    if (!L.m->dev->sampler_configured) { // function attributes are per device
         MC_CUDA_CHECK(cudaFuncSetAttribute(sample_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        configured = true;
+        L.m->dev->sampler_configured = true;
     }
     MC_REQUIRE(size_t(sp.sort_n) * 8 <= 160 * 1024, "sampler: vocabulary shard too large for the candidate sort");
     L.go(sample_finish_kernel, dim3(rows), dim3(1024), size_t(sp.sort_n) * 8, sp);
@@ -808,7 +810,7 @@ void enqueue_sample(mc_llama* m, launcher& L, uint32_t rows, const mc_sampler_co
         L.go(argmax_partial_kernel, dim3(kArgmaxBlocks, rows), dim3(256), 0, (const uint16_t*)m->logits.p, m->Vl, m->Vl, m->pval.as<float>(),
              m->pidx.as<int32_t>());
         am_exchange x{};
-        x.world = m->cfg.tp_world, x.rank = m->cfg.tp_rank, x.rows_max = kMaxMB;
+        x.world = m->cfg.tp_world, x.rank = m->cfg.tp_rank, x.rows_max = m->max_rows; // every decode row has its own slot (was kMaxMB: rows >= 4 aliased the next rank's slots)
         for (uint32_t k = 0; k < x.world; k++) {
             char* base = static_cast<char*>(m->tp_peer_base[k]);
             x.peer_val[k] = reinterpret_cast<float*>(base + m->tp_off_amval);
@@ -1061,9 +1063,21 @@ std::vector<slice2d> resolve(mc_llama* m, const std::string& name)
     } else if (name == "tok_embeddings.scales" && Q) {
         out.push_back({m->tok.scales.p, 1, c.vocab, 1, 0, 0, 1, 4, uint64_t(c.vocab), GEN_SCALE});
     } else if (name == "output.weight") {
-        MC_REQUIRE(!m->tied, "output.weight is tied to tok_embeddings.weight in the bf16 model (huggingface/llama.h:103)");
-        out.push_back({staged(m->out.q8, "the weights"), D, m->Vl, D, r * m->Vl, 0, D, 1, uint64_t(c.vocab) * D, GEN_I8});
+        if (!Q) {
+            // the reference always registers an `output` linear (nn/llama.h:79); its HF adaptor aliases it to tok_embeddings
+            // (huggingface/llama.h:103).  Setting it explicitly unties the head: it gets its own [Vl, D] shard from here on.
+            if (!m->out.w.p) {
+                m->out.N = m->Vl, m->out.K = D, m->out.fmt = WF_BF16;
+                m->out.w.alloc(size_t(m->Vl) * D * 2);
+                m->tied = false;
+            }
+            out.push_back({m->out.w.p, D, m->Vl, D, r * m->Vl, 0, D, 2, uint64_t(c.vocab) * D, GEN_BF16});
+        } else {
+            out.push_back({staged(m->out.q8, "the weights"), D, m->Vl, D, r * m->Vl, 0, D, 1, uint64_t(c.vocab) * D, GEN_I8});
+        }
     } else if (name == "output.scales" && Q) {
+        // the cached bf16 image of the output projection (quantization/linear.h:50-53) was built from these scales
+        if (m->out.wd.p) throw error(MC_ERR_INVALID, "parameter output.scales: the dequantised output projection was already built by mc_llama_finalize");
         out.push_back({m->out.scales.p, 1, m->Vl, 1, r * m->Vl, 0, 1, 4, uint64_t(c.vocab), GEN_SCALE});
     } else if (name == "norm.weight") {
         vec(m->norm, D);
@@ -1073,9 +1087,10 @@ std::vector<slice2d> resolve(mc_llama* m, const std::string& name)
         linspec sp;
         if (rest == "attention_norm.weight") vec(ly.attn_norm, D);
         else if (rest == "ffn_norm.weight") vec(ly.ffn_norm, D);
-        else if (ends_with(rest, ".adaptor.A.weight", stem) && Q && linear_spec(m, ly, stem, sp))
+        else if (ends_with(rest, ".adaptor.A.weight", stem) && Q && linear_spec(m, ly, stem, sp)) {
+            if (sp.d->wd.p) m->image_a_dirty = true; // rows [N, N + R) of the bf16 image hold a copy of A
             out.push_back({sp.lora_a->as<uint16_t>() + size_t(sp.a_row0) * sp.Kl, sp.Kl, rank, sp.Kl, 0, sp.src_col0, sp.K_full, 2, uint64_t(rank) * sp.K_full, GEN_BF16});
-        else if (ends_with(rest, ".adaptor.B.weight", stem) && Q && linear_spec(m, ly, stem, sp))
+        } else if (ends_with(rest, ".adaptor.B.weight", stem) && Q && linear_spec(m, ly, stem, sp))
             out.push_back({sp.d->lora_b.as<uint16_t>() + size_t(sp.dst_row0) * rank, size_t(rank) * sp.dst_step, sp.rows, rank, sp.src_row0, 0, rank, 2,
                            uint64_t(sp.N_full) * rank, GEN_BF16});
         else if (ends_with(rest, ".scales", stem) && Q && linear_spec(m, ly, stem, sp))
@@ -1239,12 +1254,13 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
     m->bar.alloc(256);
     MC_CUDA_CHECK(cudaMemset(m->bar.p, 0, 256));
     if (c.tp_world > 1) {
-        const size_t rows_max = kMaxMB, T = c.tp_world;
+        // partial sums travel in passes of kMaxMB rows; the argmax exchange carries every sequence of a step at once
+        const size_t rows_max = kMaxMB, T = c.tp_world, am_rows = std::max<uint32_t>(c.n_seqs, kMaxMB);
         const size_t part = 2 * T * rows_max * D * sizeof(float);
         m->tp_off_flags = part;
         m->tp_off_amval = m->tp_off_flags + 256;
-        m->tp_off_amidx = m->tp_off_amval + ((2 * T * rows_max * 4 + 255) & ~size_t(255));
-        m->tp_off_amflags = m->tp_off_amidx + ((2 * T * rows_max * 4 + 255) & ~size_t(255));
+        m->tp_off_amidx = m->tp_off_amval + ((2 * T * am_rows * 4 + 255) & ~size_t(255));
+        m->tp_off_amflags = m->tp_off_amidx + ((2 * T * am_rows * 4 + 255) & ~size_t(255));
         m->tp_region.alloc(m->tp_off_amflags + 256);
         MC_CUDA_CHECK(cudaMemset(m->tp_region.p, 0, m->tp_region.bytes));
         m->tp_local.alloc(256);
@@ -1371,7 +1387,7 @@ mc_status mc_llama_init_random(mc_llama* m, uint64_t seed)
         if (!Q) {
             bf(prefix + ".weight", tid, inv_sqrt_k, 0.0f);
         } else {
-            i8(prefix + ".weight", tid, -8, 16);
+            i8(prefix + ".weight", tid, -7, 15); // zero-mean int4 range (DESIGN.md "Synthetic data": [-8, 7] has mean -0.5 and collapses the random-init model)
             sc(prefix + ".scales", tid + K_SCALES, inv_sqrt_k * 0.125f);
             bf(prefix + ".adaptor.A.weight", tid + K_LORA_A, inv_sqrt_k, 0.0f);
             bf(prefix + ".adaptor.B.weight", tid + K_LORA_B, 1.0f / std::sqrt(float(c.lora_rank)), 0.0f);
@@ -1438,10 +1454,15 @@ mc_status mc_llama_finalize(mc_llama* m)
         if (m->cfg.tp_world == 1 && !(m->cfg.flags & MC_LLAMA_NO_SHADOW)) {
             for (dlayer& ly : m->layers)
                 for (dlinear* d : {&ly.wqkv, &ly.wo, &ly.w13, &ly.w2}) {
-                    if (!d->q8.p) continue;
                     // rows [0, N): r(r(q) * r(s)); rows [N, N + R): the stacked adaptor A of this linear; zero rows up to a multiple of 32
                     const dbuf& A = d == &ly.wqkv ? ly.lora_a_qkv : (d == &ly.wo ? ly.lora_a_o : (d == &ly.w13 ? ly.lora_a_13 : ly.lora_a_2));
                     const uint32_t R = uint32_t(A.bytes / (size_t(d->K) * 2)), Rpad = (R + 31) & ~31u;
+                    if (!d->q8.p) {
+                        // image built by an earlier finalize: only the adaptor rows can have changed since (the packed weights are final)
+                        if (d->wd.p && m->image_a_dirty)
+                            MC_CUDA_CHECK(cudaMemcpyAsync(d->wd.as<uint16_t>() + size_t(d->N) * d->K, A.p, size_t(R) * d->K * 2, cudaMemcpyDeviceToDevice, s));
+                        continue;
+                    }
                     d->wd.alloc(size_t(d->N + Rpad) * d->K * 2);
                     tc::dequant_group(s, d->wd.as<uint16_t>(), d->q8.as<int8_t>(), d->s32.as<float>(), d->N, d->K, m->cfg.group_size);
                     MC_CUDA_CHECK(cudaMemsetAsync(d->wd.as<uint16_t>() + size_t(d->N) * d->K, 0, size_t(Rpad) * d->K * 2, s));
@@ -1452,6 +1473,7 @@ mc_status mc_llama_finalize(mc_llama* m)
                 tc::dequant_group(s, m->out.wd.as<uint16_t>(), m->out.q8.as<int8_t>(), m->out.scales.as<float>(), m->out.N, m->out.K, m->out.K);
             }
             MC_CUDA_CHECK(cudaStreamSynchronize(s));
+            m->image_a_dirty = false;
         }
         for (dlayer& ly : m->layers)
             for (dlinear* d : {&ly.wqkv, &ly.wo, &ly.w13, &ly.w2}) d->q8.release(), d->s32.release();
@@ -1545,7 +1567,7 @@ void prefill_tc(mc_llama* m, uint32_t seq, const int32_t* ids, uint32_t len, uin
             launches += tc::rmsnorm_rows(s, n, x, ly.attn_norm.as<uint16_t>(), rows, D, c.norm_eps);
             launches += tc_linear(m, s, tc::GEMM_STORE, n, D, ly.wqkv, 3 * rank, 3, qkv, nullptr, rows, QKV, D, QKV, sc);
             launches += tc::rope_append(s, qkv, q, kc, vc, m->fcos.as<float>(), m->fsin.as<float>(), rows, seq, pos0, H, KV, hd, c.max_seq_len);
-            launches += tc::prefill_attn(s, q, kc, vc, attn, rows, seq, pos0, H, KV, hd, c.max_seq_len, m->scale_bf16);
+            launches += tc::prefill_attn(s, q, kc, vc, attn, rows, seq, pos0, H, KV, hd, c.max_seq_len, m->scale_bf16, m->key_begin);
             launches += tc_linear(m, s, tc::GEMM_RESIDUAL, attn, QO, ly.wo, rank, 1, h, x, rows, D, QO, D, sc);
             launches += tc::rmsnorm_rows(s, n, h, ly.ffn_norm.as<uint16_t>(), rows, D, c.norm_eps);
             launches += tc_linear(m, s, tc::GEMM_SWIGLU, n, D, ly.w13, 2 * rank, 2, z, nullptr, rows, 2 * F, D, F, sc);
@@ -1589,6 +1611,15 @@ mc_status mc_llama_prefill(mc_llama* m, uint32_t seq, const int32_t* ids, uint32
     // the sink-cache roll (nn/cache.h:183-204) is not modelled: positions must fit the cache
     MC_REQUIRE(uint64_t(start_pos) + len <= m->cfg.max_seq_len, "prefill: start_pos + len exceeds max_seq_len");
     for (uint32_t i = 0; i < len; i++) MC_REQUIRE(ids[i] >= 0 && uint32_t(ids[i]) < m->cfg.vocab, "prefill: token id out of range");
+    // Quirk Q9 (nn/attention.h:283-299): make_causal_mask leaves the columns of the cached prefix at -inf whenever len > 1, so a
+    // prompt chunk at start_pos > 0 attends only to itself in the reference.  The engine's default is the intended reading (the
+    // prefix is visible: long prompts are chunked internally and multi-turn prompts see their history); MC_LLAMA_REF_CHUNK_MASK
+    // reproduces the reference bit for bit.  Both are checked against the oracle (tests/test_gpu_prefill.py).
+    struct key_begin_scope {
+        mc_llama* m;
+        ~key_begin_scope() { m->key_begin = 0; }
+    } scope{m};
+    m->key_begin = ((m->cfg.flags & MC_LLAMA_REF_CHUNK_MASK) && len > 1) ? start_pos : 0;
     if (prefill_tc_eligible(m, len)) {
         prefill_tc(m, seq, ids, len, start_pos);
         return MC_OK;
@@ -1700,9 +1731,17 @@ mc_status mc_llama_decode_loop(mc_llama* m, uint32_t n, const int32_t* first_ids
     for (uint32_t r = 0; r < n; r++)
         MC_REQUIRE(uint64_t(first_pos[r]) + steps <= m->cfg.max_seq_len, "decode_loop: positions would exceed max_seq_len");
     cudaStream_t s = m->dev->stream;
-    cudaEvent_t e0, e1;
-    MC_CUDA_CHECK(cudaEventCreate(&e0));
-    MC_CUDA_CHECK(cudaEventCreate(&e1));
+    struct event_pair {
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~event_pair()
+        {
+            if (a) cudaEventDestroy(a);
+            if (b) cudaEventDestroy(b);
+        }
+    } ev;
+    MC_CUDA_CHECK(cudaEventCreate(&ev.a));
+    MC_CUDA_CHECK(cudaEventCreate(&ev.b));
+    const cudaEvent_t e0 = ev.a, e1 = ev.b;
     const bool stream = stream_eligible(m, n, sc);
     if (!stream && !(m->cfg.flags & MC_LLAMA_NO_GRAPH)) decode_graph(m, n, sc, 1); // instantiate outside the timed region
     MC_CUDA_CHECK(cudaEventRecord(e0, s));
@@ -1719,7 +1758,6 @@ mc_status mc_llama_decode_loop(mc_llama* m, uint32_t n, const int32_t* first_ids
     MC_CUDA_CHECK(cudaStreamSynchronize(s));
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0), cudaEventDestroy(e1);
     if (elapsed_ms) *elapsed_ms = ms;
     int errv = 0;
     MC_CUDA_CHECK(cudaMemcpy(&errv, m->errflag.p, 4, cudaMemcpyDeviceToHost));
@@ -1988,6 +2026,105 @@ mc_status mc_linear_bf16(mc_device* dev, mc_buffer* y, mc_buffer* x, mc_buffer* 
     p.x = static_cast<const uint16_t*>(x->dptr), p.ldx = K;
     p.y = static_cast<uint16_t*>(y->dptr), p.ldy = N;
     gemv_launch<PRO_NONE, EPI_NONE>(L, p);
+    MC_API_END
+}
+
+// ---- stand-alone attention / embedding kernels (isolated parity tests against the oracle) --------------------------------------
+namespace {
+struct row_arrays {
+    dbuf seq, pos;
+    row_arrays(cudaStream_t s, uint32_t rows, const int32_t* row_seq, const int32_t* row_pos)
+    {
+        seq.alloc(size_t(rows) * 4), pos.alloc(size_t(rows) * 4);
+        MC_CUDA_CHECK(cudaMemcpyAsync(seq.p, row_seq, size_t(rows) * 4, cudaMemcpyHostToDevice, s));
+        MC_CUDA_CHECK(cudaMemcpyAsync(pos.p, row_pos, size_t(rows) * 4, cudaMemcpyHostToDevice, s));
+    }
+    ~row_arrays() { seq.release(), pos.release(); }
+};
+float stored_scale(uint32_t hd) { return bf16_bits_to_f32(f32_to_bf16_bits(1.0f / std::sqrt(float(hd)))); }
+} // namespace
+
+mc_status mc_attn_decode(mc_device* dev, mc_buffer* out, mc_buffer* q, mc_buffer* kcache, mc_buffer* vcache, uint32_t rows, const int32_t* row_seq,
+                         const int32_t* row_pos, uint32_t n_seqs, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, int kernel)
+{
+    MC_API_BEGIN
+    MC_REQUIRE(dev && out && q && kcache && vcache && row_seq && row_pos && rows >= 1, "bad arguments");
+    MC_CUDA_CHECK(cudaSetDevice(dev->ordinal));
+    MC_REQUIRE(hd == 64 || hd == 128, "attn_decode: head_dim must be 64 or 128");
+    MC_REQUIRE(KV >= 1 && H % KV == 0 && max_seq >= 1 && n_seqs >= 1, "attn_decode: bad head / cache geometry");
+    const size_t cache_bytes = size_t(n_seqs) * KV * max_seq * hd * 2, act_bytes = size_t(rows) * H * hd * 2;
+    MC_REQUIRE(kcache->size >= cache_bytes && vcache->size >= cache_bytes && q->size >= act_bytes && out->size >= act_bytes, "attn_decode: buffer too small");
+    for (uint32_t r = 0; r < rows; r++)
+        MC_REQUIRE(row_seq[r] >= 0 && uint32_t(row_seq[r]) < n_seqs && row_pos[r] >= 0 && uint32_t(row_pos[r]) < max_seq, "attn_decode: row sequence / position out of range");
+    cudaStream_t s = dev->stream;
+    row_arrays ra(s, rows, row_seq, row_pos);
+    const float scale = stored_scale(hd);
+    if (kernel == 1) {
+        tc::set_pdl(false);
+        tc::decode_attn_gqa(s, static_cast<const uint16_t*>(q->dptr), static_cast<uint16_t*>(kcache->dptr), static_cast<uint16_t*>(vcache->dptr),
+                            static_cast<uint16_t*>(out->dptr), rows, ra.seq.as<int32_t>(), ra.pos.as<int32_t>(), H, KV, hd, max_seq, scale);
+    } else {
+        MC_REQUIRE(kernel == 0, "attn_decode: kernel must be 0 (cluster-split) or 1 (grouped-query)");
+        mc_llama shim;
+        shim.dev = dev;
+        shim.cfg.head_dim = hd, shim.cfg.max_seq_len = max_seq;
+        launcher L{&shim, s, false};
+        attn_params a{};
+        a.q = static_cast<const uint16_t*>(q->dptr), a.kcache = static_cast<const uint16_t*>(kcache->dptr), a.vcache = static_cast<const uint16_t*>(vcache->dptr);
+        a.out = static_cast<uint16_t*>(out->dptr), a.row_seq = ra.seq.as<int32_t>(), a.row_pos = ra.pos.as<int32_t>();
+        a.n_heads = H, a.n_kv_heads = KV, a.max_seq = max_seq, a.scale = scale;
+        const size_t smem = attn_smem(&shim, kAttnCluster);
+        if (smem > 48 * 1024) {
+            if (hd == 64) MC_CUDA_CHECK(cudaFuncSetAttribute(attn_decode_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            else MC_CUDA_CHECK(cudaFuncSetAttribute(attn_decode_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        }
+        if (hd == 64) L.go_cluster(attn_decode_kernel<64>, dim3(H * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
+        else L.go_cluster(attn_decode_kernel<128>, dim3(H * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
+    }
+    MC_CUDA_CHECK(cudaStreamSynchronize(s));
+    dev->launches.fetch_add(kernel == 1 ? 1 : 0);
+    MC_API_END
+}
+
+mc_status mc_attn_prefill(mc_device* dev, mc_buffer* out, mc_buffer* q, mc_buffer* kcache, mc_buffer* vcache, uint32_t rows, uint32_t seq, uint32_t start_pos,
+                          uint32_t key_begin, uint32_t n_seqs, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq)
+{
+    MC_API_BEGIN
+    MC_REQUIRE(dev && out && q && kcache && vcache && rows >= 1, "bad arguments");
+    MC_CUDA_CHECK(cudaSetDevice(dev->ordinal));
+    MC_REQUIRE(hd == 64 || hd == 128, "attn_prefill: head_dim must be 64 or 128");
+    MC_REQUIRE(KV >= 1 && H % KV == 0 && seq < n_seqs && uint64_t(start_pos) + rows <= max_seq && key_begin <= start_pos, "attn_prefill: bad geometry");
+    const size_t cache_bytes = size_t(n_seqs) * KV * max_seq * hd * 2, act_bytes = size_t(rows) * H * hd * 2;
+    MC_REQUIRE(kcache->size >= cache_bytes && vcache->size >= cache_bytes && q->size >= act_bytes && out->size >= act_bytes, "attn_prefill: buffer too small");
+    tc::set_pdl(false);
+    tc::prefill_attn(dev->stream, static_cast<const uint16_t*>(q->dptr), static_cast<const uint16_t*>(kcache->dptr), static_cast<const uint16_t*>(vcache->dptr),
+                     static_cast<uint16_t*>(out->dptr), rows, seq, start_pos, H, KV, hd, max_seq, stored_scale(hd), key_begin);
+    MC_CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+    dev->launches.fetch_add(1);
+    MC_API_END
+}
+
+mc_status mc_embed_rows(mc_device* dev, mc_buffer* out, mc_buffer* table, mc_buffer* row_scales, const int32_t* ids, uint32_t rows, uint32_t D, uint32_t vocab)
+{
+    MC_API_BEGIN
+    MC_REQUIRE(dev && out && table && ids && rows >= 1 && D % 8 == 0, "bad arguments");
+    MC_CUDA_CHECK(cudaSetDevice(dev->ordinal));
+    const bool q8 = row_scales != nullptr;
+    MC_REQUIRE(table->size >= size_t(vocab) * D * (q8 ? 1 : 2) && out->size >= size_t(rows) * D * 2, "embed_rows: buffer too small");
+    MC_REQUIRE(!q8 || row_scales->size >= size_t(vocab) * 4, "embed_rows: one fp32 scale per table row expected");
+    for (uint32_t r = 0; r < rows; r++) MC_REQUIRE(ids[r] >= 0 && uint32_t(ids[r]) < vocab, "embed_rows: token id out of range");
+    dbuf dids;
+    dids.alloc(size_t(rows) * 4);
+    struct guard {
+        dbuf& b;
+        ~guard() { b.release(); }
+    } g{dids};
+    MC_CUDA_CHECK(cudaMemcpyAsync(dids.p, ids, size_t(rows) * 4, cudaMemcpyHostToDevice, dev->stream));
+    embed_kernel<<<rows, 256, 0, dev->stream>>>(static_cast<uint16_t*>(out->dptr), D, table->dptr, q8 ? static_cast<const float*>(row_scales->dptr) : nullptr,
+                                                 q8 ? WF_W8ROW : WF_BF16, D, vocab, dids.as<int32_t>());
+    MC_CUDA_CHECK(cudaGetLastError());
+    MC_CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+    dev->launches.fetch_add(1);
     MC_API_END
 }
 

@@ -573,6 +573,7 @@ struct pattn_params {
     const uint16_t* vc;
     uint16_t* out;      // [rows, H*hd]
     uint32_t rows, start_pos, H, KV, max_seq;
+    uint32_t key_begin; // first visible key (0; start_pos under the reference's chunk mask, quirk Q9: nn/attention.h:283-299)
     uint32_t rep;       // query heads per CTA: H / KV when that is 1, 2, 4 or 8, else 1
     float scale;        // r(1/sqrt(hd)) stored as T (quirk Q4)
 };
@@ -622,7 +623,8 @@ template <int HD, bool POW2> __global__ void __launch_bounds__(256, HD == 64 ? 2
     const uint32_t r_lo = wr0 + g, r_hi = r_lo + 8;         // the two prompt rows of this thread
     const uint32_t rows_end = min(q0 + qt, p.rows);
     const uint32_t n_keys = p.start_pos + rows_end; // keys visible to the last row of the CTA
-    const uint32_t n_tiles = (n_keys + 63) / 64;
+    const uint32_t kt_first = p.key_begin / 64;     // tiles below the first visible key are never touched
+    const uint32_t n_tiles = (n_keys + 63) / 64 - kt_first;
     const uint16_t* kbase = p.kc + size_t(kvh) * p.max_seq * HD;
     const uint16_t* vbase = p.vc + size_t(kvh) * p.max_seq * HD;
 
@@ -646,7 +648,7 @@ template <int HD, bool POW2> __global__ void __launch_bounds__(256, HD == 64 ? 2
     // job j < n_tiles: pass 1 on key tile j (K only); job j >= n_tiles: pass 2 on key tile j - n_tiles (K and V)
     auto issue = [&](uint32_t job) {
         const bool second = job >= n_tiles;
-        const uint32_t kt = second ? job - n_tiles : job;
+        const uint32_t kt = kt_first + (second ? job - n_tiles : job);
         const uint32_t buf = sbase + (job & 1u) * 2 * TILE;
         constexpr int CH = HD / 8; // 16-byte chunks per row
         for (uint32_t c = tid; c < 64 * CH; c += 256) {
@@ -675,7 +677,7 @@ template <int HD, bool POW2> __global__ void __launch_bounds__(256, HD == 64 ? 2
         }
         __syncthreads();
         const bool second = job >= n_tiles;
-        const uint32_t kt = second ? job - n_tiles : job;
+        const uint32_t kt = kt_first + (second ? job - n_tiles : job);
         const uint32_t kbuf = sbase + (job & 1u) * 2 * TILE, vbuf = kbuf + TILE;
         if (job == n_tiles) {
             // between the passes: the four lanes of a quad hold the partial sums of one row
@@ -702,7 +704,7 @@ template <int HD, bool POW2> __global__ void __launch_bounds__(256, HD == 64 ? 2
             }
             // s = r(r(q.K) * scale), e = exp(s) = ex2(s * log2 e); masked keys drop out  (kernel/bmm.metal:76, scalar_mul,
             // kernel/softmax.metal:46)
-            const bool diagonal = kt * 64 + 63 > p.start_pos + wr0; // some key of the tile is above some row of the warp
+            const bool diagonal = kt * 64 + 63 > p.start_pos + wr0 || kt * 64 < p.key_begin; // some key of the tile is hidden from some row of the warp
             const float sl2e = p.scale * 1.4426950408889634f;
 #pragma unroll
             for (int nt = 0; nt < 8; nt++) {
@@ -717,8 +719,9 @@ template <int HD, bool POW2> __global__ void __launch_bounds__(256, HD == 64 ? 2
                 }
                 if (diagonal) {
                     const uint32_t key = kt * 64 + nt * 8 + 2 * t;
-                    e0 = key <= pos_lo ? e0 : 0.0f, e1 = key + 1 <= pos_lo ? e1 : 0.0f;
-                    e2 = key <= pos_hi ? e2 : 0.0f, e3 = key + 1 <= pos_hi ? e3 : 0.0f;
+                    const bool v0 = key >= p.key_begin, v1 = key + 1 >= p.key_begin;
+                    e0 = v0 && key <= pos_lo ? e0 : 0.0f, e1 = v1 && key + 1 <= pos_lo ? e1 : 0.0f;
+                    e2 = v0 && key <= pos_hi ? e2 : 0.0f, e3 = v1 && key + 1 <= pos_hi ? e3 : 0.0f;
                 }
                 if (!second) {
                     sum_lo += e0 + e1, sum_hi += e2 + e3;

@@ -79,7 +79,8 @@ template <typename T> void launch_bmm(const arg_pack& p, cudaStream_t s)
     auto a = p.tensor<const T, 3>(2);
     auto b = p.tensor<const T, 3>(4);
     MC_REQUIRE(a.size(2) == b.size(1), "bmm: inner dimensions differ");
-    MC_REQUIRE(a.size(0) == b.size(0) || b.size(0) == 1 || true, "bmm: batch mismatch");
+    // no broadcasting over the batch (kernel/bmm.h:36-39 same_dim(weight, 0)); a stride-0 batch view of a 2-D weight is fine
+    MC_REQUIRE(a.size(0) == b.size(0), "bmm: batch mismatch");
     const uint32_t B = a.size(0), M = a.size(1), N = b.size(2);
     if (B == 0 || M == 0 || N == 0) return;
     MC_REQUIRE(B <= 65535, "bmm: batch too large");
@@ -255,7 +256,7 @@ __global__ void embedding_kernel(tview<T, 3> out, tview<const int32_t, 2> ids, t
     for (uint32_t j = blockIdx.y; j < J; j += gridDim.y) {
         const int32_t id = ids.at(i, j);
         if (id < 0 || uint32_t(id) >= w.size(0)) {
-            if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(bad, 1);
+            if (threadIdx.x == 0 && blockIdx.x == 0) *reinterpret_cast<volatile int*>(bad) = 1; // mapped host word: a plain store
             continue;
         }
         for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < E; k += gridDim.x * blockDim.x)
@@ -269,11 +270,15 @@ template <typename T> void launch_embedding(const arg_pack& p, cudaStream_t s)
     auto w = p.tensor<const T, 2>(4);
     if (ids.size(0) == 0 || ids.size(1) == 0 || w.size(1) == 0) return;
     MC_REQUIRE(ids.size(0) <= 65535, "embedding: batch too large");
-    static int* bad = nullptr; // out-of-range ids are skipped (the Metal kernel would read out of bounds)
-    if (!bad) {
-        MC_CUDA_CHECK(cudaMalloc(&bad, sizeof(int)));
-        MC_CUDA_CHECK(cudaMemset(bad, 0, sizeof(int)));
+    // out-of-range ids are skipped (the Metal kernel would read out of bounds) and reported by mc_wait; the flag is a mapped pinned
+    // word owned by the device the kernel runs on
+    MC_REQUIRE(p.dev != nullptr, "embedding: no device bound to the dispatch");
+    if (!p.dev->bad_ids) {
+        MC_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&p.dev->bad_ids_host), sizeof(int), cudaHostAllocMapped));
+        *p.dev->bad_ids_host = 0;
+        MC_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&p.dev->bad_ids), p.dev->bad_ids_host, 0));
     }
+    int* bad = p.dev->bad_ids;
     dim3 grid(ceil_div(w.size(1), 256) > 64 ? 64 : ceil_div(w.size(1), 256), ids.size(1) > 65535 ? 65535 : ids.size(1), ids.size(0));
     embedding_kernel<T><<<grid, 256, 0, s>>>(out, ids, w, bad);
 }

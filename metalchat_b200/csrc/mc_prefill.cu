@@ -209,11 +209,12 @@ int rope_append(cudaStream_t stream, const uint16_t* qkv, uint16_t* q, uint16_t*
     return 1;
 }
 int prefill_attn(cudaStream_t stream, const uint16_t* q, const uint16_t* kcache_layer, const uint16_t* vcache_layer, uint16_t* out, uint32_t rows, uint32_t seq,
-                 uint32_t start_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, float scale)
+                 uint32_t start_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, float scale, uint32_t key_begin)
 {
     MC_REQUIRE(hd == 64 || hd == 128, "prefill attention: head_dim must be 64 or 128");
+    MC_REQUIRE(key_begin <= start_pos, "prefill attention: the first visible key lies beyond the first row");
     pattn_params p{};
-    p.q = q, p.out = out, p.rows = rows, p.start_pos = start_pos, p.H = H, p.KV = KV, p.max_seq = max_seq, p.scale = scale;
+    p.q = q, p.out = out, p.rows = rows, p.start_pos = start_pos, p.H = H, p.KV = KV, p.max_seq = max_seq, p.scale = scale, p.key_begin = key_begin;
     p.kc = kcache_layer + size_t(seq) * KV * max_seq * hd;
     p.vc = vcache_layer + size_t(seq) * KV * max_seq * hd;
     const uint32_t n_rep = H / KV;

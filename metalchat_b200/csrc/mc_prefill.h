@@ -29,9 +29,10 @@ int rmsnorm_rows(cudaStream_t stream, uint16_t* out, const uint16_t* x, const ui
 int rope_append(cudaStream_t stream, const uint16_t* qkv, uint16_t* q, uint16_t* kcache_layer, uint16_t* vcache_layer, const float* fcos, const float* fsin,
                 uint32_t rows, uint32_t seq, uint32_t start_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, const int32_t* row_seq = nullptr,
                 const int32_t* row_pos = nullptr);
-// causal attention of `rows` consecutive positions of sequence `seq` against its cache (positions 0 .. start_pos + row)
+// causal attention of `rows` consecutive positions of sequence `seq` against its cache (positions key_begin .. start_pos + row);
+// key_begin = start_pos reproduces the reference's chunk mask, which hides the cached prefix (quirk Q9, nn/attention.h:283-299)
 int prefill_attn(cudaStream_t stream, const uint16_t* q, const uint16_t* kcache_layer, const uint16_t* vcache_layer, uint16_t* out, uint32_t rows, uint32_t seq,
-                 uint32_t start_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, float scale);
+                 uint32_t start_pos, uint32_t H, uint32_t KV, uint32_t hd, uint32_t max_seq, float scale, uint32_t key_begin = 0);
 
 // one decode step of `rows` sequences: row r attends keys 0 .. row_pos[r] of sequence row_seq[r]; the H / KV query heads of a KV head
 // share one pass over its cache (grouped-query attention)

@@ -66,7 +66,13 @@ mc_status mc_device_create(int ordinal, mc_device** out)
         delete dev;
         throw error(MC_ERR_RUNTIME, "cuda: device '" + nm + "' is not sm_100; this library only ships sm_100a code");
     }
-    MC_CUDA_CHECK(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
+    {
+        const cudaError_t e = cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete dev;
+            MC_CUDA_CHECK(e);
+        }
+    }
     *out = dev;
     MC_API_END
 }
@@ -80,6 +86,7 @@ mc_status mc_device_destroy(mc_device* dev)
             cudaStreamSynchronize(dev->stream);
             cudaStreamDestroy(dev->stream);
         }
+        if (dev->bad_ids_host) cudaFreeHost(dev->bad_ids_host);
         delete dev;
     }
     MC_API_END
@@ -326,6 +333,8 @@ mc_status mc_heap_reset(mc_heap* heap)
 {
     MC_API_BEGIN
     MC_REQUIRE(heap, "null heap");
+    // slices hold a reference on the arena: rewinding under live slices would hand the same bytes out twice
+    if (heap->arena->refs.load() != 1) throw error(MC_ERR_INVALID, "heap reset while slices of it are still alive");
     heap->used = 0;
     MC_API_END
 }
@@ -356,6 +365,13 @@ mc_status mc_kernel_lookup(mc_device* dev, const char* name, mc_kernel** out)
     }
     // hardware_accelerator::load throws when newFunction fails (src/accelerator.cc:121-127)
     throw error(MC_ERR_NOT_FOUND, std::string("cuda: kernel not found: ") + name);
+    MC_API_END
+}
+
+mc_status mc_kernel_release(mc_kernel* k)
+{
+    MC_API_BEGIN
+    delete k;
     MC_API_END
 }
 
@@ -464,6 +480,7 @@ mc_status mc_dispatch(mc_cmdbuf* cb, mc_kernel* k, const uint32_t grid[3], const
         if (grid[d] < group[d]) throw error(MC_ERR_INVALID, "kernel: there are less threads in grid than in group");
     }
     use(cb->dev);
+    cb->args.dev = cb->dev;
     k->entry->launch(cb->args, cb->dev->stream);
     MC_CUDA_CHECK(cudaGetLastError());
     cb->dev->launches.fetch_add(1);
@@ -483,11 +500,16 @@ mc_status mc_on_completed(mc_cmdbuf* cb, void (*fn)(void*, int), void* user)
 struct host_call {
     void (*fn)(void*, int);
     void* user;
+    mc_device* dev;
 };
+// cudaLaunchHostFunc callbacks do not run once the stream is in an error state, so the handlers of a failed command buffer
+// are invoked from mc_wait instead, with the failure status (src/kernel_thread.cc:134-144 passes the buffer's error)
 static void CUDART_CB run_host_call(void* p)
 {
     auto* c = static_cast<host_call*>(p);
-    c->fn(c->user, 0);
+    int bad = 0;
+    if (c->dev->bad_ids_host) bad = *reinterpret_cast<volatile int*>(c->dev->bad_ids_host);
+    c->fn(c->user, bad ? int(MC_ERR_INVALID) : 0);
     delete c;
 }
 
@@ -500,7 +522,7 @@ mc_status mc_commit(mc_cmdbuf* cb)
     cb->committed = true;
     // completion handlers run on a runtime-owned thread, like Metal's (src/kernel_thread.cc:134-144)
     for (auto& h : cb->handlers) {
-        auto* c = new host_call{h.first, h.second};
+        auto* c = new host_call{h.first, h.second, cb->dev};
         MC_CUDA_CHECK(cudaLaunchHostFunc(cb->dev->stream, run_host_call, c));
     }
     MC_CUDA_CHECK(cudaEventRecord(cb->done, cb->dev->stream));
@@ -519,6 +541,12 @@ mc_status mc_wait(mc_cmdbuf* cb, char* err, size_t cap)
         }
         MC_CUDA_CHECK(cudaEventSynchronize(cb->done));
         MC_CUDA_CHECK(cudaGetLastError());
+        // out-of-range ids seen by an embedding kernel of this device (the Metal kernel would read out of bounds): surfaced here,
+        // like a command-buffer error at waitUntilCompleted
+        if (cb->dev->bad_ids_host && *reinterpret_cast<volatile int*>(cb->dev->bad_ids_host)) {
+            *reinterpret_cast<volatile int*>(cb->dev->bad_ids_host) = 0;
+            throw error(MC_ERR_INVALID, "embedding: token id out of range");
+        }
         return MC_OK;
     } catch (const error& e) {
         if (err && cap) snprintf(err, cap, "%s", e.what());

@@ -257,15 +257,18 @@ class LlamaCfg(C.Structure):
         ("head_dim", C.c_uint32), ("ffn_dim", C.c_uint32), ("vocab", C.c_uint32), ("max_seq_len", C.c_uint32),
         ("rope_theta", C.c_float), ("norm_eps", C.c_float),
         ("quant", C.c_uint32), ("lora_rank", C.c_uint32), ("lora_scale", C.c_float), ("group_size", C.c_uint32),
-        ("n_seqs", C.c_uint32),
+        ("n_seqs", C.c_uint32), ("flags", C.c_uint32),
     ]
+
+
+UNTIED_HEAD, PREFIX_VISIBLE = 1, 2  # LlamaCfg.flags (orc_model.h ORC_*)
 
 
 def make_cfg(dim=2048, n_layers=16, n_heads=32, n_kv_heads=8, head_dim=64, ffn_dim=8192, vocab=128256,
              max_seq_len=1024, rope_theta=500000.0, norm_eps=1e-5, quant=0, lora_rank=16, lora_scale=2.0,
-             group_size=32, n_seqs=1) -> LlamaCfg:
+             group_size=32, n_seqs=1, flags=0) -> LlamaCfg:
     return LlamaCfg(dim, n_layers, n_heads, n_kv_heads, head_dim, ffn_dim, vocab, max_seq_len, rope_theta,
-                    norm_eps, quant, lora_rank, lora_scale, group_size, n_seqs)
+                    norm_eps, quant, lora_rank, lora_scale, group_size, n_seqs, flags)
 
 
 class Llama:
@@ -325,6 +328,17 @@ class Llama:
         return sec, toks
 
 
+def sdpa(dt, q, K, V, causal=True, prefix_visible=False):
+    """nn::attention from the scores on: q [len, H, hd], K / V [S, KV, hd] -> o [len, H, hd]."""
+    q, K, V = (np.ascontiguousarray(a) for a in (q, K, V))
+    length, H, hd = q.shape
+    S, KV, _ = K.shape
+    o = np.zeros_like(q)
+    lib().orc_sdpa(dt, _p(o), _p(q), _p(K), _p(V), C.c_uint32(length), C.c_uint32(S), C.c_uint32(H), C.c_uint32(KV), C.c_uint32(hd),
+                   C.c_int(int(causal)), C.c_int(int(prefix_visible)))
+    return o
+
+
 def argmax(dt, logits) -> int:
     return int(lib().orc_argmax(dt, _p(logits), C.c_uint32(len(logits))))
 
@@ -344,3 +358,7 @@ def sample_default(dt, logits, topk=50, temperature=0.6, top_p=0.9, u=0.5, inten
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int):
+    lib().orc_set_num_threads(C.c_int(int(n)))

@@ -179,6 +179,16 @@ void orc_roll(int dt, void* o, const uint32_t* lo, const void* a, const uint32_t
     else roll((uint32_t*)o, L<1>(lo), (const uint32_t*)a, L<1>(la), shift, size, stride);
 }
 
+// torchrun exports OMP_NUM_THREADS=1; the CPU-baseline legs of bench.py size the pool explicitly
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 // ---- model ------------------------------------------------------------------------
 struct orc_model {
     int dtype;
@@ -248,6 +258,21 @@ int orc_llama_forward(void* h, uint32_t seq, const int32_t* ids, uint32_t len, u
     } catch (const std::exception& e) {
         g_err = e.what();
         return 1;
+    }
+}
+// Stand-alone attention (scores -> scale -> mask -> softmax -> values) for the isolated parity tests of the attention kernels.
+// q [len, H, hd] rotated; K / V [S, KV, hd]; causal != 0 builds the reference's mask for len > 1 (prefix_visible selects quirk Q9's
+// intended reading); scale is stored as T(1 / sqrt(hd)) (nn/attention.h:88,115).
+void orc_sdpa(int dt, void* o, const void* q, const void* K, const void* V, uint32_t len, uint32_t S, uint32_t H, uint32_t KV, uint32_t hd, int causal, int prefix_visible)
+{
+    if (dt == 0) {
+        std::vector<bf> mask;
+        if (causal && len > 1) mask = causal_mask<bf>(len, S, prefix_visible != 0);
+        sdpa((const bf*)q, (const bf*)K, (const bf*)V, len, S, H, KV, hd, mask.empty() ? nullptr : mask.data(), bf(1.0f / std::sqrt(float(hd))), (bf*)o);
+    } else {
+        std::vector<float> mask;
+        if (causal && len > 1) mask = causal_mask<float>(len, S, prefix_visible != 0);
+        sdpa((const float*)q, (const float*)K, (const float*)V, len, S, H, KV, hd, mask.empty() ? nullptr : mask.data(), 1.0f / std::sqrt(float(hd)), (float*)o);
     }
 }
 int32_t orc_argmax(int dt, const void* logits, uint32_t vocab)

@@ -32,6 +32,13 @@ struct llama_cfg {
     float lora_scale;    // 2.0 (huggingface/llama.h:166-168)
     uint32_t group_size; // 32
     uint32_t n_seqs;     // independent bs=1 sequences (quirk Q2/Q15: max_batch_size = 1)
+    uint32_t flags;      // ORC_* below
+};
+enum : uint32_t {
+    ORC_UNTIED_HEAD = 1u << 0,   // T-typed model with its own `output` matrix (the reference always registers one, nn/llama.h:79;
+                                 // huggingface/llama.h:103 aliases it to tok_embeddings when the checkpoint has no lm_head)
+    ORC_PREFIX_VISIBLE = 1u << 1 // "intended" chunk mask: the cached prefix columns are 0 instead of -inf when len > 1 and
+                                 // start_pos > 0 (the reference leaves them at -inf, quirk Q9, nn/attention.h:283-299)
 };
 
 // generator kinds (DESIGN.md "Synthetic data")
@@ -143,6 +150,55 @@ template <typename T> static void linear_forward(const linear_t<T>& L, const T* 
     }
 }
 
+// nn::attention::operator() from the scores on (nn/attention.h:195-203): for every (position t, head h)
+//   s = T(q . K[s]) -> T(s * scale) -> [T(s + mask)] -> softmax without max shift (kernel/softmax.metal:40-80) -> o = T(sum_s p[s] V[s]).
+// qr [len, H, hd] rotated queries; Kc / Vc [S.., KV, hd] cache rows 0..S-1; mask [len, S] or null; o [len, H, hd].
+// repeat_interleave (functional/transform.h:80-91) => kv head = h / (H / KV).
+template <typename T>
+static void sdpa(const T* qr, const T* Kc, const T* Vc, uint32_t len, uint32_t S, uint32_t H, uint32_t KV, uint32_t hd, const T* mask, T scale, T* o)
+{
+    const uint32_t reps = H / KV;
+    const uint32_t sm_block = ceil_div(S, kMaxThreads);
+#pragma omp parallel for collapse(2) schedule(static)
+    for (uint32_t hh = 0; hh < H; hh++) {
+        for (uint32_t t = 0; t < len; t++) {
+            const uint32_t kvh = hh / reps;
+            std::vector<T> sc(S), pr(S);
+            const T* qv = &qr[(size_t(t) * H + hh) * hd];
+            for (uint32_t s = 0; s < S; s++) {
+                const T* kv = &Kc[(size_t(s) * KV + kvh) * hd];
+                float acc = 0.0f;
+                for (uint32_t dd = 0; dd < hd; dd++) acc += float(qv[dd]) * float(kv[dd]);
+                T sv = T(acc);                             // bmm
+                sv = T(float(sv) * float(scale));          // scalar_mul
+                if (mask) sv = T(float(sv) + float(mask[size_t(t) * S + s])); // add_broadcast
+                sc[s] = sv;
+            }
+            layout<2> ls{{1, S}, {S, 1}, {0, 0}};
+            softmax(pr.data(), ls, sc.data(), ls, sm_block);
+            T* ov = &o[(size_t(t) * H + hh) * hd];
+            for (uint32_t dd = 0; dd < hd; dd++) {
+                float acc = 0.0f;
+                for (uint32_t s = 0; s < S; s++) acc += float(pr[s]) * float(Vc[(size_t(s) * KV + kvh) * hd + dd]);
+                ov[dd] = T(acc);
+            }
+        }
+    }
+}
+// make_causal_mask (nn/attention.h:283-299): [len, S] filled with -inf, the trailing len x len square gets triu(diagonal = 1), i.e.
+// 0 on and below the diagonal; the columns of the cached prefix stay at -inf (quirk Q9) unless `prefix_visible`.
+template <typename T> static std::vector<T> causal_mask(uint32_t len, uint32_t S, bool prefix_visible)
+{
+    const T ninf = T(-std::numeric_limits<float>::infinity());
+    std::vector<T> mask(size_t(len) * S, ninf);
+    for (uint32_t i = 0; i < len; i++) {
+        for (uint32_t j = 0; j <= i; j++) mask[size_t(i) * S + (S - len) + j] = T(0.0f);
+        if (prefix_visible)
+            for (uint32_t j = 0; j < S - len; j++) mask[size_t(i) * S + j] = T(0.0f);
+    }
+    return mask;
+}
+
 template <typename T> struct layer_t {
     std::vector<T> attn_norm, ffn_norm;
     linear_t<T> wq, wk, wv, wo, w1, w2, w3;
@@ -193,8 +249,8 @@ template <typename T> struct llama {
             setup(l.w3, F, D, lm);
         }
         setup(tok, cfg.vocab, D, cfg.quant ? 2 : 0);
-        tied = !cfg.quant;
-        if (!tied) setup(out, cfg.vocab, D, 2);
+        tied = !cfg.quant && !(cfg.flags & ORC_UNTIED_HEAD);
+        if (!tied) setup(out, cfg.vocab, D, cfg.quant ? 2 : 0);
         norm.assign(D, T(0.0f));
         const uint32_t rows = 2 * cfg.max_seq_len;
         fcos.resize(size_t(rows) * (hd / 2));
@@ -271,7 +327,8 @@ template <typename T> struct llama {
         if (l.mode == 0) {
             gen_T(l.w, seed, tid, inv_sqrt_k, 0.0f);
         } else {
-            gen_q(l.q, seed, tid, -8, 16);
+            gen_q(l.q, seed, tid, -7, 15); // symmetric: a non-zero weight mean (UniformInt[-8,7] has -0.5) feeds a self-reinforcing all-ones mode through RMSNorm
+                                           // and the hidden state degenerates to a constant vector whatever the tokens are
             gen_scales(l.scales, seed, tid + K_SCALES, inv_sqrt_k * 0.125f);
             gen_T(l.A, seed, tid + K_LORA_A, inv_sqrt_k, 0.0f);
             gen_T(l.B, seed, tid + K_LORA_B, 1.0f / std::sqrt(float(l.rank)), 0.0f);
@@ -294,6 +351,7 @@ template <typename T> struct llama {
         gen_T(norm, seed, tid_global(G_NORM), 0.1f, 1.0f);
         if (tok.mode == 0) {
             gen_T(tok.w, seed, tid_global(G_TOK), 0.0625f, 0.0f);
+            if (!tied) gen_T(out.w, seed, tid_global(G_OUT), 1.0f / std::sqrt(float(cfg.dim)), 0.0f);
         } else {
             gen_q(tok.q, seed, tid_global(G_TOK), -127, 255);
             gen_scales(tok.scales, seed, tid_global(G_TOK) + K_SCALES, 0.0625f / 127.0f);
@@ -316,7 +374,7 @@ template <typename T> struct llama {
     void forward(uint32_t seq, const int32_t* ids, uint32_t len, uint32_t start_pos, T* logits)
     {
         const uint32_t D = cfg.dim, H = cfg.n_heads, KV = cfg.n_kv_heads, hd = cfg.head_dim, F = cfg.ffn_dim;
-        const uint32_t reps = H / KV, half = hd / 2;
+        const uint32_t half = hd / 2;
         if (seq >= cfg.n_seqs) throw std::invalid_argument("oracle: sequence index out of range");
         if (start_pos + len > cfg.max_seq_len) {
             // The sink-cache roll (nn/cache.h:183-204) is outside the measured configs.
@@ -337,12 +395,7 @@ template <typename T> struct llama {
         // cached prefix stay at -inf (quirk Q9).
         const uint32_t S = start_pos + len;
         std::vector<T> mask;
-        if (len > 1) {
-            const T ninf = T(-std::numeric_limits<float>::infinity());
-            mask.assign(size_t(len) * S, ninf);
-            for (uint32_t i = 0; i < len; i++)
-                for (uint32_t j = 0; j <= i; j++) mask[size_t(i) * S + (S - len) + j] = T(0.0f);
-        }
+        if (len > 1) mask = causal_mask<T>(len, S, (cfg.flags & ORC_PREFIX_VISIBLE) != 0);
         const T scale = T(1.0f / std::sqrt(float(hd))); // stored as T (nn/attention.h:88,115; quirk Q4)
 
         std::vector<T> n(size_t(len) * D), q(size_t(len) * H * hd), k(size_t(len) * KV * hd), v(size_t(len) * KV * hd);
@@ -368,33 +421,8 @@ template <typename T> struct llama {
             std::vector<T>& Vc = vc[size_t(seq) * cfg.n_layers + li];
             std::copy(kr.begin(), kr.end(), Kc.begin() + size_t(start_pos) * KV * hd);
             std::copy(v.begin(), v.end(), Vc.begin() + size_t(start_pos) * KV * hd);
-            // attention (nn/attention.h:161-206); repeat_interleave => kv head = h / reps
-            const uint32_t sm_block = ceil_div(S, kMaxThreads);
-#pragma omp parallel for collapse(2) schedule(static)
-            for (uint32_t hh = 0; hh < H; hh++) {
-                for (uint32_t t = 0; t < len; t++) {
-                    const uint32_t kvh = hh / reps;
-                    std::vector<T> sc(S), pr(S);
-                    const T* qv = &qr[(size_t(t) * H + hh) * hd];
-                    for (uint32_t s = 0; s < S; s++) {
-                        const T* kv = &Kc[(size_t(s) * KV + kvh) * hd];
-                        float acc = 0.0f;
-                        for (uint32_t dd = 0; dd < hd; dd++) acc += float(qv[dd]) * float(kv[dd]);
-                        T sv = T(acc);                             // bmm
-                        sv = T(float(sv) * float(scale));          // scalar_mul
-                        if (len > 1) sv = T(float(sv) + float(mask[size_t(t) * S + s])); // add_broadcast
-                        sc[s] = sv;
-                    }
-                    layout<2> ls{{1, S}, {S, 1}, {0, 0}};
-                    softmax(pr.data(), ls, sc.data(), ls, sm_block);
-                    T* ov = &o[(size_t(t) * H + hh) * hd];
-                    for (uint32_t dd = 0; dd < hd; dd++) {
-                        float acc = 0.0f;
-                        for (uint32_t s = 0; s < S; s++) acc += float(pr[s]) * float(Vc[(size_t(s) * KV + kvh) * hd + dd]);
-                        ov[dd] = T(acc);
-                    }
-                }
-            }
+            // attention (nn/attention.h:161-206)
+            sdpa(qr.data(), Kc.data(), Vc.data(), len, S, H, KV, hd, len > 1 ? mask.data() : nullptr, scale, o.data());
             linear_forward(L.wo, o.data(), len, a.data());
             for (size_t i = 0; i < h.size(); i++) h[i] = T(float(x[i]) + float(a[i])); // nn/transformer.h:133
             rmsnorm_rows(h.data(), len, L.ffn_norm, n.data());
