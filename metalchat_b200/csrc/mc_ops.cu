@@ -429,14 +429,17 @@ struct pcg32 {
     __device__ float uniform() { return __uint_as_float((next() >> 9) | 0x3f800000u) - 1.0f; }
 };
 template <typename T>
-__global__ void multinomial_kernel(tview<int32_t, 2> out, tview<const T, 2> in, uint64_t init_state, uint64_t init_seq)
+__global__ void multinomial_kernel(tview<int32_t, 2> out, tview<const T, 2> in, uint64_t init_state, uint64_t init_seq, uint64_t avail)
 {
     const uint32_t rows = out.size(0), S = out.size(1), N = in.size(1);
     const uint64_t n = uint64_t(rows) * S;
     for (uint64_t idx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; idx < n; idx += uint64_t(gridDim.x) * blockDim.x) {
         const uint32_t i = uint32_t(idx / S), k = uint32_t(idx % S);
-        // quirk Q10: `a` is read at column sample_size-1, not at the last column (kernel/multinomial.metal:107)
-        const float a = to_f32(in.at(i, S - 1));
+        // quirk Q10: `a` is read at column sample_size-1, not at the last column (kernel/multinomial.metal:107).  With more samples than
+        // columns that address lies in a later row or outside the buffer, where a Metal device read yields 0 -- the reference's own
+        // test draws 8192 samples from rows of 5 and relies on it (test/test_kernel_multinomial.cc:16-54)
+        const uint64_t flat = uint64_t(i) * in.l.strides[0] + uint64_t(S - 1) * in.l.strides[1] + in.l.offsets[0] + in.l.offsets[1];
+        const float a = flat < avail ? to_f32(in.data[flat]) : 0.0f;
         const float b = to_f32(in.at(i, 0));
         pcg32 g(init_state + i, init_seq + k);
         const float r = round_to<T>(__fadd_rn(__fmul_rn(g.uniform(), __fsub_rn(b, a)), a));
@@ -457,8 +460,9 @@ template <typename T> void launch_multinomial(const arg_pack& p, cudaStream_t s)
     const uint64_t n = uint64_t(out.size(0)) * out.size(1);
     if (n == 0) return;
     MC_REQUIRE(in.size(1) > 0, "multinomial: empty distribution");
-    MC_REQUIRE(out.size(1) <= in.size(1), "multinomial: sample_size exceeds the row size (the reference reads out of bounds)");
-    multinomial_kernel<T><<<flat_grid(n), 256, 0, s>>>(out, in, st, sq);
+    const arg_slot& buf = p.slot[3];
+    const uint64_t avail = (buf.buf->size - buf.offset) / sizeof(T); // elements of the bound buffer readable from the tensor's base
+    multinomial_kernel<T><<<flat_grid(n), 256, 0, s>>>(out, in, st, sq, avail);
 }
 
 // ---- element-wise (kernel/mul.metal, arithmetic.metal, activation.metal, logical.metal, copy.metal) ----------------------------------------

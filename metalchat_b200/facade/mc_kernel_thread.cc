@@ -96,6 +96,9 @@ private:
 struct command_buffer {
     mc_cmdbuf* handle = nullptr;
     mc_kernel* pending = nullptr; // kernel of the function being encoded (named at dispatch by the C ABI)
+    // A Metal command buffer retains every buffer bound to it until it has completed (setBuffer); temporaries that the encoder
+    // copies to the device (kernel_thread.h:127-137) live only through that reference.
+    std::vector<metal::shared_buffer> retained;
     std::vector<kernel_callback_type> handlers;
     std::mutex mu;
 
@@ -190,6 +193,8 @@ hardware_function_encoder::encode(metal::shared_buffer buffer, std::size_t offse
     metal::check(mc_set_buffer(
         _M_queue->commands->handle, std::uint32_t(_M_buffer++), buffer->handle, buffer->offset + offset
     ));
+    std::scoped_lock lock(_M_queue->commands->mu);
+    _M_queue->commands->retained.push_back(buffer);
 }
 
 
@@ -285,14 +290,17 @@ kernel_thread::make_ready_at_thread_exit()
         const mc_status status = committed == MC_OK ? mc_wait(commands->handle, err, sizeof(err)) : committed;
 
         std::vector<kernel_callback_type> handlers;
+        std::vector<metal::shared_buffer> retained;
         {
             std::scoped_lock lock(commands->mu);
             handlers.swap(commands->handlers);
+            retained.swap(commands->retained);
         }
         for (auto& handler : handlers) {
             handler();
         }
         handlers.clear();
+        retained.clear();
 
         if (status != MC_OK) {
             const std::string what = committed == MC_OK ? std::string(err) : commit_error;

@@ -346,19 +346,24 @@ template <typename T> uint32_t reverse_cdf_search(const view2<const T>& d, uint3
 // `uniforms` (rows x samples, may be null) injects the draws; otherwise PCG32 with
 // (init_state + row, init_seq + sample).  `intended` selects a = input[row, N-1]
 // instead of the reference's a = input[row, samples-1] (quirk Q10,
-// kernel/multinomial.metal:107).
+// kernel/multinomial.metal:107).  With samples > N that read leaves the row: it lands in a later row, or -- beyond the
+// `avail` elements of the buffer -- outside the allocation, where a Metal device read yields 0; the reference's own test
+// depends on it (test/test_kernel_multinomial.cc:16-54 draws 8192 samples from rows of 5: a = 0, r = u * p_max).
 template <typename T>
 void multinomial(
     int32_t* out, const layout<2>& lo, const T* in, const layout<2>& li, uint64_t init_state,
-    uint64_t init_seq, const float* uniforms, int intended
+    uint64_t init_seq, const float* uniforms, int intended, uint64_t avail = ~uint64_t(0)
 )
 {
     view2<int32_t> o{out, &lo};
     view2<const T> x{in, &li};
     const uint32_t rows = o.size(0), S = o.size(1), N = x.size(1);
+    if (avail == ~uint64_t(0)) avail = uint64_t(x.size(0) - 1) * li.strides[0] + uint64_t(N - 1) * li.strides[1] + li.offsets[0] + li.offsets[1] + 1;
     for (uint32_t i = 0; i < rows; i++) {
         for (uint32_t k = 0; k < S; k++) {
-            const float a = float(x.at(i, intended ? N - 1 : S - 1));
+            const uint32_t ca = intended ? N - 1 : S - 1;
+            const uint64_t flat = uint64_t(i) * li.strides[0] + uint64_t(ca) * li.strides[1] + li.offsets[0] + li.offsets[1];
+            const float a = flat < avail ? float(in[flat]) : 0.0f;
             const float b = float(x.at(i, 0));
             float u;
             if (uniforms) {

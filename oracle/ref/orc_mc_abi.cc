@@ -15,10 +15,12 @@
 #include "../orc_ops.h"
 
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -98,7 +100,8 @@ template <typename T> void reg_typed(std::map<std::string, kernel_fn>& r, const 
     for (uint32_t b = 2; b <= 1024; b *= 2)
         r["cumsum_" + std::to_string(b) + "_" + sfx] = [b](const args& a) { cumsum(a.ptr<T>(1), a.lay<2>(0), a.ptr<const T>(3), a.lay<2>(2), b); };
     r["multinomial_" + sfx] = [](const args& a) {
-        multinomial(a.ptr<int32_t>(1), a.lay<2>(0), a.ptr<const T>(3), a.lay<2>(2), a.scalar<uint64_t>(4), a.scalar<uint64_t>(5), nullptr, 0);
+        multinomial(a.ptr<int32_t>(1), a.lay<2>(0), a.ptr<const T>(3), a.lay<2>(2), a.scalar<uint64_t>(4), a.scalar<uint64_t>(5), nullptr, 0,
+                    (a.s[3].buf->size - a.s[3].offset) / sizeof(T));
     };
     r["add_" + sfx] = [](const args& a) { binary2(a.ptr<T>(1), a.lay<2>(0), a.ptr<const T>(3), a.lay<2>(2), a.ptr<const T>(5), a.lay<2>(4), [](float x, float y) { return x + y; }); };
     r["sub_" + sfx] = [](const args& a) { binary2(a.ptr<T>(1), a.lay<2>(0), a.ptr<const T>(3), a.lay<2>(2), a.ptr<const T>(5), a.lay<2>(4), [](float x, float y) { return x - y; }); };
@@ -224,6 +227,7 @@ mc_status mc_alloc_copy(mc_device*, const void* src, size_t size, int, mc_buffer
 {
     ORC_BEGIN
     mc_buffer* b = new_buffer(size);
+    if (std::getenv("MC_ORC_TRACE")) std::fprintf(stderr, "alloc_copy src %p size %zu first %08x\n", src, size, size >= 4 ? *static_cast<const uint32_t*>(src) : 0u);
     if (size) std::memcpy(b->ptr, src, size);
     *out = b;
     ORC_END
@@ -361,7 +365,23 @@ mc_status mc_dispatch(mc_cmdbuf* cb, mc_kernel* k, const uint32_t grid[3], const
     const uint64_t threads = uint64_t(group[0]) * group[1] * group[2];
     if (threads == 0 || threads > 1024) throw std::invalid_argument("kernel: thread group exceeds 1024 threads");
     (void)grid;
+    if (std::getenv("MC_ORC_TRACE")) {
+        std::fprintf(stderr, "dispatch %s grid <%u,%u,%u> group <%u,%u,%u>:", k->name.c_str(), grid[0], grid[1], grid[2], group[0], group[1], group[2]);
+        for (int i = 0; i < kSlots && cb->a.s[i].kind; i++) {
+            if (cb->a.s[i].kind == 1) {
+                std::fprintf(stderr, " [%d] %zu bytes (", i, cb->a.s[i].nbytes);
+                for (size_t w = 0; w < cb->a.s[i].nbytes / 4 && w < 9; w++) std::fprintf(stderr, "%u ", reinterpret_cast<const uint32_t*>(cb->a.s[i].data)[w]);
+                std::fprintf(stderr, ")");
+            }
+            else std::fprintf(stderr, " [%d] buf %p+%zu", i, cb->a.s[i].buf->ptr, cb->a.s[i].offset);
+        }
+        std::fprintf(stderr, "\n");
+    }
     (*k->fn)(cb->a);
+    if (std::getenv("MC_ORC_TRACE")) {
+        for (int i = 0; i < kSlots && cb->a.s[i].kind; i++)
+            if (cb->a.s[i].kind == 2) std::fprintf(stderr, "   after: [%d] first words %08x %08x (%g)\n", i, cb->a.ptr<uint32_t>(i)[0], cb->a.ptr<uint32_t>(i)[1], cb->a.ptr<float>(i)[0]);
+    }
     cb->dev->launches.fetch_add(1);
     cb->size++;
     for (auto& s : cb->a.s) s = slot();

@@ -246,9 +246,17 @@ def test_quant_tc_prefill_matches_oracle_and_packed_prefill(cfgd, n_prompt):
             assert max_rel(unbf(ga), unbf(gb)) < 1e-2
     k0 = a.cache(0, 0, 0, n_prompt).reshape(-1)
     assert np.mean(k0 == o.cache(0, 0, 0)[: k0.size]) > 0.97
-    assert max_rel(unbf(a.hidden()), unbf(want_hidden[-1])) < 1e-2
-    assert max_rel(unbf(a.logits()), unbf(want_logits)) < 1e-2
-    assert max_rel(unbf(a.logits()), unbf(b.logits())) < 1e-2
+    # Hidden state and logits after all blocks: two bf16 chains (engine, bf16 oracle) are each a rounding-noise distance away from
+    # the fp32 oracle; the engine must be no further from it than the bf16 oracle is (x1.5 + 2e-3 slack), and within 2e-2 of the
+    # bf16 oracle itself (QLoRA adds three bf16 roundings per linear, so single elements end up 1-2 ulps apart after a few blocks).
+    of = orc.Llama(orc.make_cfg(**cfgd, quant=1), F32)
+    of.init_random(0x5EED)
+    f_logits, f_hidden = of.forward(ids, 0, want_hidden=True)
+    assert max_rel(unbf(a.hidden()), f_hidden[-1]) <= 1.5 * max_rel(unbf(want_hidden[-1]), f_hidden[-1]) + 2e-3
+    assert max_rel(unbf(a.logits()), f_logits) <= 1.5 * max_rel(unbf(want_logits), f_logits) + 2e-3
+    assert max_rel(unbf(a.hidden()), unbf(want_hidden[-1])) < 2e-2
+    assert max_rel(unbf(a.logits()), unbf(want_logits)) < 2e-2
+    assert max_rel(unbf(a.logits()), unbf(b.logits())) < 2e-2
     tok, pos = orc.argmax(BF16, want_logits), n_prompt
     for _ in range(8):
         got = int(a.decode([tok], [pos])[0])
