@@ -575,7 +575,9 @@ __device__ __forceinline__ void gemv_body(const gemv_params& p, unsigned char* s
                     const bool is_k = head < p.n_heads + p.n_kv_heads;
                     const uint32_t kvh = is_k ? head - p.n_heads : head - p.n_heads - p.n_kv_heads;
                     uint16_t* base = (is_k ? p.kcache : p.vcache) + adj.kv_off;
-                    uint16_t* dst = base + ((size_t(seq) * p.n_kv_heads + kvh) * p.max_seq + size_t(pos)) * hd + j;
+                    // a position beyond the cache writes the last row: the sink roll has shifted the others (nn/cache.h:183-204)
+                    const uint32_t slot = min(uint32_t(pos), p.max_seq - 1);
+                    uint16_t* dst = base + ((size_t(seq) * p.n_kv_heads + kvh) * p.max_seq + size_t(slot)) * hd + j;
                     dst[0] = f32_to_bf16_bits(y0);
                     dst[half] = f32_to_bf16_bits(y1);
                 }
@@ -672,7 +674,7 @@ __device__ __forceinline__ void attn_body(const attn_params& p, unsigned char* s
     float* sp = spart + SLOTS * HD;              // [chunk] scores / probabilities of this CTA
 
     const int32_t seq = p.row_seq[row];
-    const uint32_t P = uint32_t(p.row_pos[row]) + 1;
+    const uint32_t P = min(uint32_t(p.row_pos[row]), p.max_seq - 1) + 1; // a full (rolled) cache shows all max_seq rows
     const uint32_t kvh = head / (p.n_heads / p.n_kv_heads);
     const size_t coff = kv_off + (size_t(seq) * p.n_kv_heads + kvh) * p.max_seq * HD;
     const uint16_t* Kc = p.kcache + coff;
@@ -896,6 +898,41 @@ template <int MB> __global__ void __launch_bounds__(kGemvThreads, 2) decode_mega
         if (threadIdx.x == 0) {
             *P.step_counter += 1;
             *P.bar = 0; // every CTA has made its last arrival: ready for the next replay
+        }
+    }
+}
+
+// ---- sink-cache roll (nn/cache.h:183-204 + kernel/roll.metal:22-45) --------------------------------------------------------------
+// A decode step at a position beyond the cache keeps the first `pre_len` rows (the sink tokens), moves rows (pre_len, S) one row to
+// the left and writes the new row at S - 1.  The reference allocates a new cache and rolls into it; here the shift is in place:
+// one CTA per (layer, kv head, K|V) stream and decode row, tiles of 2048 16-byte chunks, every tile loaded completely before it is
+// stored one row lower (a tile's loads never touch what an earlier tile stored).  Rows whose position is inside the cache return.
+__global__ void __launch_bounds__(256) kv_roll_kernel(uint16_t* kcache, uint16_t* vcache, size_t kv_layer_stride, const int32_t* row_seq, const int32_t* row_pos,
+                                                      uint32_t n_kv_heads, uint32_t head_dim, uint32_t max_seq, uint32_t pre_len)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t row = blockIdx.y;
+    if (uint32_t(row_pos[row]) < max_seq) return;
+    const uint32_t stream = blockIdx.x, which = stream & 1u, kvh = (stream >> 1) % n_kv_heads, layer = (stream >> 1) / n_kv_heads;
+    uint16_t* base = (which ? vcache : kcache) + size_t(layer) * kv_layer_stride + (size_t(row_seq[row]) * n_kv_heads + kvh) * max_seq * head_dim;
+    const uint32_t row_chunks = head_dim / 8;                          // 16-byte chunks per cache row
+    const uint32_t n_chunks = (max_seq - pre_len - 1) * row_chunks;    // rows (pre_len, S) move to [pre_len, S - 1)
+    const uint4* src = reinterpret_cast<const uint4*>(base + size_t(pre_len + 1) * head_dim);
+    uint4* dst = reinterpret_cast<uint4*>(base + size_t(pre_len) * head_dim);
+    constexpr uint32_t PER = 8;
+    for (uint32_t c0 = 0; c0 < n_chunks; c0 += 256 * PER) {
+        uint4 v[PER];
+#pragma unroll
+        for (uint32_t i = 0; i < PER; i++) {
+            const uint32_t c = c0 + i * 256 + threadIdx.x;
+            if (c < n_chunks) v[i] = src[c];
+        }
+        __syncthreads();
+#pragma unroll
+        for (uint32_t i = 0; i < PER; i++) {
+            const uint32_t c = c0 + i * 256 + threadIdx.x;
+            if (c < n_chunks) dst[c] = v[i];
         }
     }
 }

@@ -85,6 +85,8 @@ struct mc_llama {
     uint32_t Hl = 0, KVl = 0, Fl = 0, Vl = 0; // local (sharded) dims
     bool finalized = false;
     bool tied = true;
+    bool sink_roll = false;     // the decode call in flight reaches positions beyond the cache: every step starts with the sink roll
+    uint32_t rope_rows = 0;     // rows of the RoPE tables (positions 0 .. rope_rows - 1)
     uint32_t key_begin = 0;     // first visible cache position of the prompt call in flight (MC_LLAMA_REF_CHUNK_MASK: its start_pos)
     bool image_a_dirty = false; // an adaptor A was replaced after the resident bf16 image had been built: its rows are re-copied by finalize
     std::vector<dlayer> layers;
@@ -152,6 +154,30 @@ void use(mc_llama* m)
 {
     MC_REQUIRE(m != nullptr, "null model");
     MC_CUDA_CHECK(cudaSetDevice(m->dev->ordinal));
+}
+
+// RoPE tables on the host with the same libm calls as the scalar reference formula (kernel/rope.metal:93-97: 1/pow(theta, 2j/dim),
+// cos/sin of float(pos) * freq).  The reference regenerates its 2 * max_seq_len rows from start_pos whenever a position leaves the
+// table (nn/embedding.h:193-198) -- the value of a row depends on the absolute position only, so the engine keeps ONE table indexed by
+// absolute position and grows it when decode runs past it.
+void build_rope_tables(mc_llama* m, uint32_t rows)
+{
+    const mc_llama_config& c = m->cfg;
+    const uint32_t half = c.head_dim / 2;
+    std::vector<float> hc(size_t(rows) * half), hs(size_t(rows) * half);
+    for (uint32_t i = 0; i < rows; i++) {
+        for (uint32_t j = 0; j < half; j++) {
+            const float freq = 1.0f / std::pow(c.rope_theta, 2.0f * float(j) / float(c.head_dim));
+            const float angle = float(i) * freq;
+            hc[size_t(i) * half + j] = std::cos(angle);
+            hs[size_t(i) * half + j] = std::sin(angle);
+        }
+    }
+    m->fcos.alloc(hc.size() * 4);
+    m->fsin.alloc(hs.size() * 4);
+    MC_CUDA_CHECK(cudaMemcpy(m->fcos.p, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice));
+    MC_CUDA_CHECK(cudaMemcpy(m->fsin.p, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice));
+    m->rope_rows = rows;
 }
 
 size_t kv_layer_elems(const mc_llama* m) { return size_t(m->cfg.n_seqs) * m->KVl * m->cfg.max_seq_len * m->cfg.head_dim; }
@@ -659,7 +685,7 @@ bool stream_eligible(mc_llama* m, uint32_t n, const mc_sampler_config& sc)
     // 8: 3671 vs 3907 - the streaming kernel walks attention items, staged rows and epilogue columns one after the other, so
     // by default it serves single-sequence decode; MC_STREAM_MAX_ROWS raises the limit (the kernel itself handles up to 8).
     static const uint32_t max_rows = getenv("MC_STREAM_MAX_ROWS") ? uint32_t(atoi(getenv("MC_STREAM_MAX_ROWS"))) : 1u;
-    if (c.tp_world != 1 || sc.mode != 0 || n > std::min<uint32_t>(max_rows, kStMaxRows)) return false;
+    if (c.tp_world != 1 || sc.mode != 0 || n > std::min<uint32_t>(max_rows, kStMaxRows) || m->sink_roll) return false;
     if (m->st_ok < 0) {
         m->st_ok = 0;
         stream_geom g;
@@ -917,6 +943,13 @@ void enqueue_rows_tc(mc_llama* m, launcher& L, uint32_t rows)
 // one decode step for rows [0, n): forward in chunks of kMaxMB rows, then sample
 void enqueue_decode_step(mc_llama* m, launcher& L, uint32_t n, const mc_sampler_config& sc, int advance)
 {
+    if (m->sink_roll) {
+        // nn::sink_cache (nn/cache.h:123-126,183-204): pre_len = bit_width(max_seq_len) - 1 sink rows stay, the rest moves one row left
+        uint32_t pre_len = 0;
+        while ((2u << pre_len) <= m->cfg.max_seq_len) pre_len++;
+        L.go(kv_roll_kernel, dim3(m->cfg.n_layers * m->KVl * 2, n), dim3(256), 0, m->kcache.as<uint16_t>(), m->vcache.as<uint16_t>(), kv_layer_elems(m),
+             (const int32_t*)m->row_seq.as<int32_t>(), (const int32_t*)m->pos.as<int32_t>(), m->KVl, m->cfg.head_dim, m->cfg.max_seq_len, pre_len);
+    }
     if (stream_eligible(m, n, sc)) {
         launch_stream(m, L, n, advance, 1);
         return;
@@ -943,7 +976,7 @@ cudaGraphExec_t decode_graph(mc_llama* m, uint32_t n, const mc_sampler_config& s
 {
     uint32_t tbits, pbits;
     memcpy(&tbits, &sc.temperature, 4), memcpy(&pbits, &sc.top_p, 4);
-    const uint64_t key = mix64((uint64_t(n) << 40) ^ (uint64_t(sc.mode) << 36) ^ (uint64_t(sc.intended) << 35) ^ (uint64_t(advance) << 34) ^
+    const uint64_t key = mix64((uint64_t(n) << 40) ^ (uint64_t(m->sink_roll) << 37) ^ (uint64_t(sc.mode) << 36) ^ (uint64_t(sc.intended) << 35) ^ (uint64_t(advance) << 34) ^
                                (uint64_t(sc.top_k) << 24) ^ (uint64_t(tbits) * 0x9E3779B97F4A7C15ull) ^ (uint64_t(pbits) << 1));
     auto it = m->graphs.find(key);
     if (it != m->graphs.end()) return it->second;
@@ -1268,24 +1301,7 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
         m->tp_peer_base[c.tp_rank] = m->tp_region.p;
     }
     m->norm.alloc(size_t(D) * 2);
-    // rope tables on the host with the same libm calls as the scalar reference formula
-    // (kernel/rope.metal:93-97: 1/pow(theta, 2j/dim), cos/sin of pos*freq), 2*max_seq rows (nn/embedding.h:171)
-    {
-        const uint32_t rows = 2 * c.max_seq_len, half = hd / 2;
-        std::vector<float> hc(size_t(rows) * half), hs(size_t(rows) * half);
-        for (uint32_t i = 0; i < rows; i++) {
-            for (uint32_t j = 0; j < half; j++) {
-                const float freq = 1.0f / std::pow(c.rope_theta, 2.0f * float(j) / float(hd));
-                const float angle = float(i) * freq;
-                hc[size_t(i) * half + j] = std::cos(angle);
-                hs[size_t(i) * half + j] = std::sin(angle);
-            }
-        }
-        m->fcos.alloc(hc.size() * 4);
-        m->fsin.alloc(hs.size() * 4);
-        MC_CUDA_CHECK(cudaMemcpy(m->fcos.p, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice));
-        MC_CUDA_CHECK(cudaMemcpy(m->fsin.p, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice));
-    }
+    build_rope_tables(m.get(), 2 * c.max_seq_len); // nn/embedding.h:171: 2 * max_seq_len positions
     const size_t kv_bytes = size_t(c.n_layers) * kv_layer_elems(m.get()) * 2;
     m->kcache.alloc(kv_bytes);
     m->vcache.alloc(kv_bytes);
@@ -1608,8 +1624,9 @@ mc_status mc_llama_prefill(mc_llama* m, uint32_t seq, const int32_t* ids, uint32
     MC_REQUIRE(m->finalized, "mc_llama_finalize must be called before prefill");
     MC_REQUIRE(ids && len > 0, "prefill: empty input");
     MC_REQUIRE(seq < m->cfg.n_seqs, "prefill: sequence index out of range");
-    // the sink-cache roll (nn/cache.h:183-204) is not modelled: positions must fit the cache
-    MC_REQUIRE(uint64_t(start_pos) + len <= m->cfg.max_seq_len, "prefill: start_pos + len exceeds max_seq_len");
+    // Prompts must fit the cache.  (Decode steps beyond it roll the cache like nn::sink_cache, nn/cache.h:183-204; a multi-token call at
+    // start_pos >= max_seq_len would roll by `len` and, with the reference's chunk mask, see only itself -- feed such input token by token.)
+    MC_REQUIRE(uint64_t(start_pos) + len <= m->cfg.max_seq_len, "prefill: start_pos + len exceeds max_seq_len (decode token by token beyond the cache)");
     for (uint32_t i = 0; i < len; i++) MC_REQUIRE(ids[i] >= 0 && uint32_t(ids[i]) < m->cfg.vocab, "prefill: token id out of range");
     // Quirk Q9 (nn/attention.h:283-299): make_causal_mask leaves the columns of the cached prefix at -inf whenever len > 1, so a
     // prompt chunk at start_pos > 0 attends only to itself in the reference.  The engine's default is the intended reading (the
@@ -1675,16 +1692,30 @@ static void check_mega_error(mc_llama* m, int flag)
     }
 }
 
-static void stage_decode_inputs(mc_llama* m, uint32_t n, const int32_t* ids, const int32_t* pos)
+static void stage_decode_inputs(mc_llama* m, uint32_t n, const int32_t* ids, const int32_t* pos, uint32_t steps)
 {
     MC_REQUIRE(n >= 1 && n <= m->cfg.n_seqs, "decode: number of sequences out of range");
     MC_REQUIRE(ids && pos, "decode: null ids/pos");
     const uint32_t R = m->max_rows;
     int32_t* st = m->pinned + 4 * R + 64; // staging image of io_in: ids | pos | row_seq | step counter
+    uint64_t last = 0;
     for (uint32_t r = 0; r < n; r++) {
         MC_REQUIRE(ids[r] >= 0 && uint32_t(ids[r]) < m->cfg.vocab, "decode: token id out of range");
-        MC_REQUIRE(pos[r] >= 0 && uint32_t(pos[r]) < m->cfg.max_seq_len, "decode: position exceeds max_seq_len (sink roll not modelled)");
+        MC_REQUIRE(pos[r] >= 0 && uint64_t(pos[r]) + steps < (1u << 30), "decode: position out of range");
         st[r] = ids[r], st[R + r] = pos[r], st[2 * R + r] = int32_t(r);
+        last = std::max<uint64_t>(last, uint64_t(pos[r]) + steps - 1);
+    }
+    // positions beyond the cache: the sink-cache roll runs at the head of every step of this call (nn/cache.h:183-204); RoPE keeps the
+    // absolute position, so the tables must reach it
+    m->sink_roll = last >= m->cfg.max_seq_len;
+    if (m->sink_roll) MC_REQUIRE(m->cfg.tp_world == 1, "decode: positions beyond max_seq_len are not supported under tensor parallelism");
+    if (last >= m->rope_rows) {
+        MC_CUDA_CHECK(cudaStreamSynchronize(m->dev->stream));
+        uint32_t rows = m->rope_rows;
+        while (rows <= last) rows *= 2;
+        build_rope_tables(m, rows);
+        for (auto& g : m->graphs) cudaGraphExecDestroy(g.second); // the captured launches hold the old table pointers
+        m->graphs.clear();
     }
     st[3 * R] = 0; // step counter
     MC_CUDA_CHECK(cudaMemcpyAsync(m->io_in.p, st, (size_t(3) * R + 1) * 4, cudaMemcpyHostToDevice, m->dev->stream));
@@ -1699,7 +1730,7 @@ mc_status mc_llama_decode(mc_llama* m, uint32_t n, const int32_t* ids, const int
     MC_REQUIRE(out_ids, "decode: null output");
     mc_sampler_config sc{};
     if (sampler) sc = *sampler;
-    stage_decode_inputs(m, n, ids, pos);
+    stage_decode_inputs(m, n, ids, pos, 1);
     if (sc.mode == 1) {
         MC_REQUIRE(uniforms, "decode: the multinomial sampler needs one injected uniform per sequence");
         MC_CUDA_CHECK(cudaMemcpyAsync(m->uniforms.p, uniforms, n * 4, cudaMemcpyHostToDevice, m->dev->stream));
@@ -1723,13 +1754,11 @@ mc_status mc_llama_decode_loop(mc_llama* m, uint32_t n, const int32_t* first_ids
     MC_REQUIRE(steps >= 1 && steps <= kMaxLogSteps, "decode_loop: steps out of range");
     mc_sampler_config sc{};
     if (sampler) sc = *sampler;
-    stage_decode_inputs(m, n, first_ids, first_pos);
+    stage_decode_inputs(m, n, first_ids, first_pos, steps);
     if (sc.mode == 1) {
         MC_REQUIRE(uniforms, "decode_loop: the multinomial sampler needs steps*n injected uniforms");
         MC_CUDA_CHECK(cudaMemcpyAsync(m->uniforms.p, uniforms, size_t(steps) * n * 4, cudaMemcpyHostToDevice, m->dev->stream));
     }
-    for (uint32_t r = 0; r < n; r++)
-        MC_REQUIRE(uint64_t(first_pos[r]) + steps <= m->cfg.max_seq_len, "decode_loop: positions would exceed max_seq_len");
     cudaStream_t s = m->dev->stream;
     struct event_pair {
         cudaEvent_t a = nullptr, b = nullptr;

@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(256) rope_append_kernel(const uint16_t* qkv, u
         const float a0 = bf_lo(lo), a1 = bf_hi(lo), b0 = bf_lo(hi), b1 = bf_hi(hi);
         const uint32_t o_lo = pack2(__fsub_rn(__fmul_rn(cs.x, a0), __fmul_rn(sn.x, b0)), __fsub_rn(__fmul_rn(cs.y, a1), __fmul_rn(sn.y, b1)));
         const uint32_t o_hi = pack2(__fadd_rn(__fmul_rn(sn.x, a0), __fmul_rn(cs.x, b0)), __fadd_rn(__fmul_rn(sn.y, a1), __fmul_rn(cs.y, b1)));
-        uint16_t* dst = head < H ? q + size_t(row) * H * hd + size_t(head) * hd : kcache + ((size_t(seq) * KV + (head - H)) * max_seq + size_t(pos)) * hd;
+        uint16_t* dst = head < H ? q + size_t(row) * H * hd + size_t(head) * hd : kcache + ((size_t(seq) * KV + (head - H)) * max_seq + size_t(min(pos, max_seq - 1))) * hd;
         *reinterpret_cast<uint32_t*>(dst + j) = o_lo;
         *reinterpret_cast<uint32_t*>(dst + j + half) = o_hi;
     }
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(256) rope_append_kernel(const uint16_t* qkv, u
     const uint32_t chunks = KV * (hd >> 3);
     for (uint32_t i = threadIdx.x; i < chunks; i += 256) {
         const uint32_t kvh = i / (hd >> 3), c = (i % (hd >> 3)) * 8;
-        *reinterpret_cast<uint4*>(vcache + ((size_t(seq) * KV + kvh) * max_seq + size_t(pos)) * hd + c) =
+        *reinterpret_cast<uint4*>(vcache + ((size_t(seq) * KV + kvh) * max_seq + size_t(min(pos, max_seq - 1))) * hd + c) =
             *reinterpret_cast<const uint4*>(src_row + size_t(H + KV + kvh) * hd + c);
     }
 }
@@ -795,7 +795,9 @@ template <int HD, bool POW2> __global__ void __launch_bounds__(128) decode_attn_
     const uint32_t kvh = blockIdx.x, row = blockIdx.y, n_rep = p.H / p.KV;
     pdl_trigger();
     pdl_sync();
-    const uint32_t seq = uint32_t(p.row_seq[row]), pos = uint32_t(p.row_pos[row]);
+    // rpos: absolute position (RoPE); pos: cache row of the new key = min(rpos, S - 1) -- beyond the cache the sink roll has already
+    // shifted the older rows (nn/cache.h:183-204)
+    const uint32_t seq = uint32_t(p.row_seq[row]), rpos = uint32_t(p.row_pos[row]), pos = min(rpos, p.max_seq - 1);
     const uint32_t n_keys = pos + 1, n_tiles = (n_keys + 63) / 64;
     uint16_t* kbase = p.kc + (size_t(seq) * p.KV + kvh) * p.max_seq * HD;
     uint16_t* vbase = p.vc + (size_t(seq) * p.KV + kvh) * p.max_seq * HD;
@@ -810,7 +812,7 @@ template <int HD, bool POW2> __global__ void __launch_bounds__(128) decode_attn_
             const uint16_t* ks = src + size_t(p.H + kvh) * HD;
             for (uint32_t j = tid; j < half; j += 128) {
                 const float a = bf16_bits_to_f32(ks[j]), b = bf16_bits_to_f32(ks[j + half]);
-                const float cs = p.fcos[size_t(pos) * half + j], sn = p.fsin[size_t(pos) * half + j];
+                const float cs = p.fcos[size_t(rpos) * half + j], sn = p.fsin[size_t(rpos) * half + j];
                 kbase[size_t(pos) * HD + j] = f32_to_bf16_bits(__fsub_rn(__fmul_rn(cs, a), __fmul_rn(sn, b)));
                 kbase[size_t(pos) * HD + j + half] = f32_to_bf16_bits(__fadd_rn(__fmul_rn(sn, a), __fmul_rn(cs, b)));
             }
@@ -826,7 +828,7 @@ template <int HD, bool POW2> __global__ void __launch_bounds__(128) decode_attn_
             for (int h8 = 0; h8 < 2; h8++) {
                 const uint32_t d = ks * 16 + h8 * 8 + 2 * t;
                 const uint32_t lo = *reinterpret_cast<const uint32_t*>(ql + d), hi = *reinterpret_cast<const uint32_t*>(ql + d + half);
-                const float2 cs = *reinterpret_cast<const float2*>(p.fcos + size_t(pos) * half + d), sn = *reinterpret_cast<const float2*>(p.fsin + size_t(pos) * half + d);
+                const float2 cs = *reinterpret_cast<const float2*>(p.fcos + size_t(rpos) * half + d), sn = *reinterpret_cast<const float2*>(p.fsin + size_t(rpos) * half + d);
                 const float a0 = bf_lo(lo), a1 = bf_hi(lo), b0 = bf_lo(hi), b1 = bf_hi(hi);
                 const uint32_t r_lo = pack2(__fsub_rn(__fmul_rn(cs.x, a0), __fmul_rn(sn.x, b0)), __fsub_rn(__fmul_rn(cs.y, a1), __fmul_rn(sn.y, b1)));
                 const uint32_t r_hi = pack2(__fadd_rn(__fmul_rn(sn.x, a0), __fmul_rn(cs.x, b0)), __fadd_rn(__fmul_rn(sn.y, a1), __fmul_rn(cs.y, b1)));

@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_q_kernel(const qgemv_par
                         const bool is_k = head < p.n_heads + p.n_kv_heads;
                         const uint32_t kvh = is_k ? head - p.n_heads : head - p.n_heads - p.n_kv_heads;
                         uint16_t* base = is_k ? p.kcache : p.vcache;
-                        uint16_t* dst = base + ((size_t(seq) * p.n_kv_heads + kvh) * p.max_seq + size_t(pos)) * hd + j;
+                        uint16_t* dst = base + ((size_t(seq) * p.n_kv_heads + kvh) * p.max_seq + size_t(min(uint32_t(pos), p.max_seq - 1))) * hd + j; // beyond the cache: the last row (sink roll, nn/cache.h:183-204)
                         dst[0] = f32_to_bf16_bits(y0);
                         dst[half] = f32_to_bf16_bits(y1);
                     }

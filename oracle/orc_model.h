@@ -211,7 +211,8 @@ template <typename T> struct llama {
     linear_t<T> out; // output head; mode 0 aliases tok (huggingface/llama.h:103)
     bool tied = true;
     std::vector<T> norm;
-    std::vector<float> fcos, fsin;        // [2*max_seq, hd/2]  (nn/embedding.h:171)
+    std::vector<float> fcos, fsin;        // [2*max_seq, hd/2]  (nn/embedding.h:171), rows = positions rope_start + i
+    uint32_t rope_start = 0;              // nn::rope::_M_start_pos (nn/embedding.h:160-199)
     std::vector<std::vector<T>> kc, vc;   // [seq*layer] -> [max_seq, n_kv, hd]
     std::vector<T> last_hidden;           // hidden state after the last block, [len, dim]
     std::unordered_map<std::string, std::pair<void*, size_t>> named;
@@ -376,10 +377,15 @@ template <typename T> struct llama {
         const uint32_t D = cfg.dim, H = cfg.n_heads, KV = cfg.n_kv_heads, hd = cfg.head_dim, F = cfg.ffn_dim;
         const uint32_t half = hd / 2;
         if (seq >= cfg.n_seqs) throw std::invalid_argument("oracle: sequence index out of range");
-        if (start_pos + len > cfg.max_seq_len) {
-            // The sink-cache roll (nn/cache.h:183-204) is outside the measured configs.
-            throw std::invalid_argument("oracle: start_pos + len exceeds max_seq_len (sink roll not modelled)");
-        }
+        // nn::sink_cache::copy (nn/cache.h:167-216): once start_pos has left the cache, the first pre_len = log2(max_seq_len) rows
+        // (the "sink" tokens, nn/cache.h:123-126) stay, the other rows are rolled left by len (kernel/roll.metal:22-45) and the new
+        // rows go to the end.  A call that straddles the end (start_pos < max_seq_len < start_pos + len) slices past the cache in the
+        // reference; it is rejected here.
+        const uint32_t cache_size = cfg.max_seq_len;
+        const bool overflow = start_pos >= cache_size;
+        if (len > cache_size) throw std::invalid_argument("sink_cache: requested length is larger than the cache size");
+        if (!overflow && start_pos + len > cache_size) throw std::invalid_argument("oracle: the call straddles the end of the cache (undefined in the reference)");
+        const uint32_t write_pos = overflow ? cache_size - len : start_pos;
         // embedding (nn/embedding.h:82-86; lora_embedding quantization/lora.h:160-170)
         std::vector<T> x(size_t(len) * D);
         {
@@ -393,7 +399,7 @@ template <typename T> struct llama {
         }
         // make_causal_mask (nn/attention.h:283-299): only when len > 1; columns of the
         // cached prefix stay at -inf (quirk Q9).
-        const uint32_t S = start_pos + len;
+        const uint32_t S = write_pos + len; // keys visible: cache[0, end_pos) (nn/cache.h:207-214); the mask is [len, min(start_pos + len, max_seq_len)] (nn/llama.h:119-121)
         std::vector<T> mask;
         if (len > 1) mask = causal_mask<T>(len, S, (cfg.flags & ORC_PREFIX_VISIBLE) != 0);
         const T scale = T(1.0f / std::sqrt(float(hd))); // stored as T (nn/attention.h:88,115; quirk Q4)
@@ -408,19 +414,37 @@ template <typename T> struct llama {
             linear_forward(L.wq, n.data(), len, q.data());
             linear_forward(L.wk, n.data(), len, k.data());
             linear_forward(L.wv, n.data(), len, v.data());
-            // rope over [bs*len*n_head, hd] rows (kernel/embedding.h:87-125)
+            // rope over [bs*len*n_head, hd] rows (kernel/embedding.h:87-125) at the ABSOLUTE position; the table covers 2 * max_seq_len
+            // positions and is regenerated from start_pos when the position leaves it (nn/embedding.h:193-198)
+            if (start_pos < rope_start || start_pos >= rope_start + 2 * cfg.max_seq_len) {
+                rope_start = start_pos;
+                layout<2> lt{{2 * cfg.max_seq_len, half}, {half, 1}, {0, 0}};
+                rope_freqs(fcos.data(), lt, fsin.data(), lt, hd, rope_start, cfg.rope_theta);
+            }
             {
                 layout<2> lf{{2 * cfg.max_seq_len, half}, {half, 1}, {0, 0}};
                 layout<2> lq{{len * H, hd}, {hd, 1}, {0, 0}};
                 layout<2> lk{{len * KV, hd}, {hd, 1}, {0, 0}};
-                rope(qr.data(), lq, q.data(), lq, fcos.data(), lf, fsin.data(), lf, 1, H, start_pos);
-                rope(kr.data(), lk, k.data(), lk, fcos.data(), lf, fsin.data(), lf, 1, KV, start_pos);
+                rope(qr.data(), lq, q.data(), lq, fcos.data(), lf, fsin.data(), lf, 1, H, start_pos - rope_start);
+                rope(kr.data(), lk, k.data(), lk, fcos.data(), lf, fsin.data(), lf, 1, KV, start_pos - rope_start);
             }
-            // sink_cache::update (nn/cache.h:133-151,207-214): bit copy into [start_pos, S)
+            // sink_cache::update (nn/cache.h:133-151,167-216): roll when full, then a bit copy into [write_pos, S)
             std::vector<T>& Kc = kc[size_t(seq) * cfg.n_layers + li];
             std::vector<T>& Vc = vc[size_t(seq) * cfg.n_layers + li];
-            std::copy(kr.begin(), kr.end(), Kc.begin() + size_t(start_pos) * KV * hd);
-            std::copy(v.begin(), v.end(), Vc.begin() + size_t(start_pos) * KV * hd);
+            if (overflow) {
+                uint32_t pre_len = 0; // std::bit_width(max_seq_len) - 1
+                while ((2u << pre_len) <= cache_size) pre_len++;
+                const uint32_t post_len = cache_size - pre_len;
+                const size_t row = size_t(KV) * hd;
+                for (std::vector<T>* c : {&Kc, &Vc}) {
+                    std::vector<T> post(c->begin() + size_t(pre_len) * row, c->begin() + size_t(cache_size) * row);
+                    for (uint32_t i = 0; i < post_len; i++) // out[i] = in[(i + shift) % size] along the position axis (kernel/roll.metal:36-41)
+                        std::copy(post.begin() + size_t((i + len) % post_len) * row, post.begin() + size_t((i + len) % post_len + 1) * row,
+                                  c->begin() + size_t(pre_len + i) * row);
+                }
+            }
+            std::copy(kr.begin(), kr.end(), Kc.begin() + size_t(write_pos) * KV * hd);
+            std::copy(v.begin(), v.end(), Vc.begin() + size_t(write_pos) * KV * hd);
             // attention (nn/attention.h:161-206)
             sdpa(qr.data(), Kc.data(), Vc.data(), len, S, H, KV, hd, len > 1 ? mask.data() : nullptr, scale, o.data());
             linear_forward(L.wo, o.data(), len, a.data());

@@ -16,6 +16,9 @@ SHAPES = {"small": dict(dim=512, n_layers=3, n_heads=8, n_kv_heads=2, head_dim=6
 CASES = [("llama", "small", 10, 6, 0), ("llama", "hd128", 20, 4, 0), ("llama", "small", 24, 3, 9), ("qlora", "small", 10, 5, 0),
          ("qlora", "hd128", 12, 3, 5)]
 GEMMA_CASES = [("gemma", "small", 20, 5, 0), ("gemma", "hd128", 40, 4, 0), ("gemma", "small", 30, 3, 12)]
+# decode past max_seq_len (96): nn::sink_cache keeps log2(max_seq_len) sink rows, rolls the rest left and writes at the end
+# (nn/cache.h:183-204, kernel/roll.metal); RoPE keeps the absolute position (nn/embedding.h:193-198)
+SINK_CASES = [("llama", "small", 90, 14, 0), ("qlora", "small", 94, 6, 0)]
 
 
 def available(backend: str) -> bool:

@@ -355,3 +355,51 @@ def test_stream_many_launches_keep_tags_unique():
         tok = int(m2.decode([tok], [3 + s])[0])
         b.append(tok)
     assert a[:, 0].tolist() == b
+
+
+# ---- decode beyond max_seq_len: the sink-cache roll (nn/cache.h:183-204, kernel/roll.metal) ----------------------------------------------
+@pytest.mark.parametrize("quant,flags_name", [(0, "per_op"), (0, "batched_tc"), (1, "per_op")])
+def test_decode_past_the_cache_rolls_like_sink_cache(quant, flags_name):
+    """max_seq_len 96: positions 96.. keep the log2(96) = 6 sink rows, shift the rest left and write the last row; RoPE stays at the
+    absolute position (the tables are regrown past 2 * max_seq_len).  Oracle: orc_model.h forward(), itself bit-identical to the
+    reference's nn::sink_cache code (tests/test_oracle_ref.py SINK_CASES)."""
+    from metalchat_b200 import capi
+
+    n_seqs = 6 if flags_name == "batched_tc" else 1
+    o = orc.Llama(orc.make_cfg(**SMALL, quant=quant, n_seqs=n_seqs), BF16)
+    o.init_random(0x5EED)
+    m = make_qengine(SMALL, n_seqs=n_seqs) if quant else make_engine(SMALL, n_seqs=n_seqs)
+    rng = np.random.default_rng(7)
+    prompts = [[int(x) for x in rng.integers(0, SMALL["vocab"], size=90 - 3 * s)] for s in range(n_seqs)]
+    toks, pos = [], []
+    for s, p in enumerate(prompts):
+        m.prefill(p, 0, s)
+        toks.append(orc.argmax(BF16, o.forward(p, 0, seq=s)))
+        pos.append(len(p))
+    steps = 118  # sequence 0 runs from position 90 to 207: past the cache (96) and past the initial RoPE tables (192)
+    for step in range(steps):
+        got = m.decode(toks, pos)
+        for s in range(n_seqs):
+            lg = o.forward([toks[s]], pos[s], seq=s)
+            want = orc.argmax(BF16, lg)
+            assert near_top(lg, int(got[s])), (flags_name, step, s, pos[s], int(got[s]), want)
+            if s == 0 and step in (5, 6, 7, 60, 117):
+                rel = max_rel(unbf(m.logits(0)), unbf(lg))
+                assert rel < 2e-2, (step, pos[0], rel)
+                kc = m.cache(0, 1, 0, SMALL["max_seq_len"]).reshape(-1)
+                ko = o.cache(0, 1, 0)[: kc.size]
+                assert max_rel(unbf(kc), unbf(ko)) < 2e-2, (step, pos[0])
+            toks[s] = want  # teacher-forced along the oracle's path
+            pos[s] += 1
+    # the device-side loop crosses the boundary too: same tokens as the per-token call from the same state (both on the per-op kernels:
+    # a call that reaches past the cache takes them for all of its steps, and the int4 streaming kernel re-associates its sums)
+    a = make_qengine(SMALL, flags=capi.LLAMA_NO_STREAM) if quant else make_engine(SMALL, flags=capi.LLAMA_NO_STREAM)
+    b = make_qengine(SMALL, flags=capi.LLAMA_NO_STREAM) if quant else make_engine(SMALL, flags=capi.LLAMA_NO_STREAM)
+    for e in (a, b):
+        e.prefill(prompts[0], 0, 0)
+    t_loop, _ = a.decode_loop([5], [90], 12)
+    tok, out = 5, []
+    for i in range(12):
+        tok = int(b.decode([tok], [90 + i])[0])
+        out.append(tok)
+    assert t_loop[:, 0].tolist() == out

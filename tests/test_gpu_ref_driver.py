@@ -22,7 +22,7 @@ def near_top(row_bits, token, ulps=2):
     return float(lf[token]) >= top - ulps * step
 
 
-@pytest.mark.parametrize("kind,shape,n_prompt,n_decode,chunk", ref_driver.CASES + ref_driver.GEMMA_CASES)
+@pytest.mark.parametrize("kind,shape,n_prompt,n_decode,chunk", ref_driver.CASES + ref_driver.GEMMA_CASES + ref_driver.SINK_CASES)
 def test_reference_layers_on_b200_match_the_cpu_run(kind, shape, n_prompt, n_decode, chunk):
     require_gpu()
     cpu = ref_driver.run("cpu", kind, shape, n_prompt, n_decode, chunk)

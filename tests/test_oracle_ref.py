@@ -5,7 +5,8 @@ oracle/_ref/cpu/ref_driver is the reference's unmodified header code -- nn::llam
 by the reference's own huggingface::llama3_qlora_safetensor_serializer::adapt, make_causal_mask, make_default_sampler -- compiled
 where it lies against the façade, with the oracle's op functions as the kernels (oracle/ref/orc_mc_abi.cc).  Its logits must be
 BIT-IDENTICAL to oracle/orc_model.h on the same synthetic weights and ids: prompts with the causal mask, chunked prompts (quirk Q9:
-the cached prefix stays masked), decode steps, head_dim 64 and 128 (quirk Q4), the QLoRA rounding order (Q7/Q8); the reference's
+the cached prefix stays masked), decode steps, decode past max_seq_len (sink-cache roll, quirk Q14, RoPE at the absolute position),
+head_dim 64 and 128 (quirk Q4), the QLoRA rounding order (Q7/Q8); the reference's
 default sampler chain (top-k -> nucleus -> multinomial, quirk Q10) must pick the token the oracle's sample_default picks.
 
 The op-level half of the pin is tests/test_ref_suite_cpu.py (the reference's own unit tests on the same backend)."""
@@ -18,7 +19,7 @@ from tests import ref_driver
 pytestmark = pytest.mark.skipif(not ref_driver.available("cpu"), reason="oracle/_ref/cpu/ref_driver not built (needs /root/reference; run __graft_entry__.build())")
 
 
-@pytest.mark.parametrize("kind,shape,n_prompt,n_decode,chunk", ref_driver.CASES)
+@pytest.mark.parametrize("kind,shape,n_prompt,n_decode,chunk", ref_driver.CASES + ref_driver.SINK_CASES)
 def test_reference_composition_is_bit_identical_to_the_oracle(kind, shape, n_prompt, n_decode, chunk):
     got = ref_driver.run("cpu", kind, shape, n_prompt, n_decode, chunk)
     want = ref_driver.oracle_rows(kind, shape, n_prompt, n_decode, chunk)
