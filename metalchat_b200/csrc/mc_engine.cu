@@ -98,6 +98,7 @@ struct mc_llama {
     void* tp_peer_base[kTpMaxWorld] = {};
     bool tp_connected = false;
     size_t tp_off_flags = 0, tp_off_amval = 0, tp_off_amidx = 0, tp_off_amflags = 0;
+    size_t tp_off_stpart = 0, tp_off_stam = 0, tp_stpart_gen = 0, tp_stam_gen = 0; // streaming kernel: tagged partial sums / argmax pairs, two generations each
     // streaming persistent kernel (mc_stream_kernel.cuh): un-rotated q|k|v rows, split-attention exchange, step flag
     dbuf st_ll, st_timing;     // one arena of tagged words: x | h | z | qkv | attn | scores | argmax partials | ids
     size_t st_off[9] = {};
@@ -659,7 +660,7 @@ bool stream_geometry(const mc_llama* m, uint32_t rows, stream_geom& g)
     const size_t attn_scratch = (size_t(5) * c.head_dim + 1024 + c.max_seq_len + 8) * sizeof(float);
     g.sax_off = uint32_t((std::max(size_t(rows) * g.act_pitch, attn_scratch) + 127) & ~size_t(127));
     g.act_bytes = g.sax_off + (c.quant ? uint32_t(kStMaxRows * 3 * c.lora_rank * sizeof(float) + 127) & ~127u : 0u);
-    const size_t fixed = kStHdrBytes + kStRedBytes + g.act_bytes;
+    const size_t fixed = kStHdrBytes + kStRedBytes + kStTpKeepBytes + g.act_bytes;
     const size_t cap = 232448; // 227 KiB of dynamic shared memory per CTA on sm_100
     g.stage_bytes = c.quant ? kStStageBytesPacked : kStStageBytes;
     if (fixed + 2 * size_t(g.stage_bytes) > cap) return false;
@@ -685,12 +686,17 @@ bool stream_eligible(mc_llama* m, uint32_t n, const mc_sampler_config& sc)
     // 8: 3671 vs 3907 - the streaming kernel walks attention items, staged rows and epilogue columns one after the other, so
     // by default it serves single-sequence decode; MC_STREAM_MAX_ROWS raises the limit (the kernel itself handles up to 8).
     static const uint32_t max_rows = getenv("MC_STREAM_MAX_ROWS") ? uint32_t(atoi(getenv("MC_STREAM_MAX_ROWS"))) : 1u;
-    if (c.tp_world != 1 || sc.mode != 0 || n > std::min<uint32_t>(max_rows, kStMaxRows) || m->sink_roll) return false;
+    if (sc.mode != 0 || n > std::min<uint32_t>(max_rows, kStMaxRows) || m->sink_roll) return false;
+    // tensor parallel: bf16 models whose row-parallel phases fit the per-CTA partial-sum store; MC_TP_NO_STREAM keeps the per-op exchange
+    static const bool tp_stream_off = getenv("MC_TP_NO_STREAM") != nullptr;
+    if (c.tp_world != 1 && (c.quant || !m->tp_connected || tp_stream_off || c.tp_world > uint32_t(kStTpMaxWorld))) return false;
     if (m->st_ok < 0) {
         m->st_ok = 0;
         stream_geom g;
         bool shapes = stream_kc(c.dim) && stream_kc(m->Hl * c.head_dim) && stream_kc(m->Fl) && c.dim <= 4096 && m->Fl % 2 == 0 && m->Vl % 2 == 0 &&
                       m->dev->prop.multiProcessorCount <= 256 && stream_geometry(m, kStMaxRows, g);
+        // tensor parallel: a CTA keeps the partial sums of at most kStTpBlocks 16-row blocks of a row-parallel phase
+        if (c.tp_world > 1) shapes = shapes && (c.dim + m->dev->prop.multiProcessorCount - 1) / m->dev->prop.multiProcessorCount + 16 <= uint32_t(kStTpBlocks) * 16;
         if (c.quant) // packed layouts: whole super-units of 16 rows, adaptor rows in pairs, rank in 16-byte steps
             shapes = shapes && ((m->Hl + 2 * m->KVl) * c.head_dim) % 16 == 0 && c.dim % 16 == 0 && (2 * m->Fl) % 16 == 0 && m->Vl % 16 == 0 && c.lora_rank % 8 == 0 &&
                      3 * c.lora_rank <= 128 && (c.head_dim / 2) % 8 == 0;
@@ -721,6 +727,12 @@ void launch_stream(mc_llama* m, launcher& L, uint32_t rows, int advance, uint32_
     // tags of a launch are (sequence number << 16) + phase + 1: never 0, unique until the 16-bit sequence wraps
     if ((++m->st_seq & 0xffffu) == 0) {
         MC_CUDA_CHECK(cudaMemsetAsync(m->st_ll.p, 0, m->st_ll.bytes, L.s));
+        if (c.tp_world > 1) {
+            // the generation just left (see mc_llama_create): everything the peers sent into it has been consumed by this rank
+            const size_t old_gen = ((m->st_seq - 1) >> 16) & 1u;
+            MC_CUDA_CHECK(cudaMemsetAsync(m->tp_region.as<char>() + m->tp_off_stpart + old_gen * m->tp_stpart_gen, 0, m->tp_stpart_gen, L.s));
+            MC_CUDA_CHECK(cudaMemsetAsync(m->tp_region.as<char>() + m->tp_off_stam + old_gen * m->tp_stam_gen, 0, m->tp_stam_gen, L.s));
+        }
         ++m->st_seq;
     }
     st_params P{};
@@ -780,6 +792,15 @@ void launch_stream(mc_llama* m, launcher& L, uint32_t rows, int advance, uint32_
     P.am_ll = ll + m->st_off[6], P.ids_ll = ll + m->st_off[7];
     P.out_log = m->out_log.as<int32_t>(), P.step_counter = m->step_counter.as<int32_t>(), P.advance = advance;
     P.err = m->errflag.as<int>();
+    P.tp_world = c.tp_world, P.tp_rank = c.tp_rank, P.tp_dim = D, P.tp_index_base = c.tp_rank * m->Vl;
+    if (c.tp_world > 1) {
+        const size_t gen = (m->st_seq >> 16) & 1u;
+        for (uint32_t k = 0; k < c.tp_world; k++) {
+            char* base = static_cast<char*>(m->tp_peer_base[k]);
+            P.tp_part[k] = reinterpret_cast<uint64_t*>(base + m->tp_off_stpart + gen * m->tp_stpart_gen);
+            P.tp_am[k] = reinterpret_cast<uint64_t*>(base + m->tp_off_stam + gen * m->tp_stam_gen);
+        }
+    }
     P.timing = m->st_timing_on ? m->st_timing.as<unsigned long long>() : nullptr;
     P.dbg = m->st_timing_on ? m->st_timing.as<unsigned long long>() + size_t(m->st_grid) * (c.n_layers * 5 + 1) * 4 : nullptr;
     cudaLaunchConfig_t cfg{};
@@ -1294,7 +1315,15 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
         m->tp_off_amval = m->tp_off_flags + 256;
         m->tp_off_amidx = m->tp_off_amval + ((2 * T * am_rows * 4 + 255) & ~size_t(255));
         m->tp_off_amflags = m->tp_off_amidx + ((2 * T * am_rows * 4 + 255) & ~size_t(255));
-        m->tp_region.alloc(m->tp_off_amflags + 256);
+        // streaming kernel under tensor parallelism: [generation][kind wo | w2][src rank][row][dim] tagged fp32 words and
+        // [generation][src rank][row][2] argmax words.  Tags repeat when the 16-bit launch counter wraps; the generation (bit 16 of
+        // the counter) alternates the region then, and a rank clears the region it has just left: every word a peer sent into it has
+        // been consumed by then, and no peer writes there again before this rank has moved on twice.
+        m->tp_off_stpart = m->tp_off_amflags + 256;
+        m->tp_stpart_gen = size_t(2) * T * kStMaxRows * D * 8;
+        m->tp_off_stam = m->tp_off_stpart + 2 * m->tp_stpart_gen;
+        m->tp_stam_gen = (T * kStMaxRows * 2 * 8 + 255) & ~size_t(255);
+        m->tp_region.alloc(m->tp_off_stam + 2 * m->tp_stam_gen);
         MC_CUDA_CHECK(cudaMemset(m->tp_region.p, 0, m->tp_region.bytes));
         m->tp_local.alloc(256);
         MC_CUDA_CHECK(cudaMemset(m->tp_local.p, 0, 256));

@@ -50,6 +50,9 @@ constexpr int kStMaxRows = 8;                         // activation rows (the n 
 constexpr int kStHdrBytes = 896;                      // mbarriers + flags + reduce scratch
 constexpr int kStRedBufs = 3;                         // cross-warp partial buffers in flight between the mma and the epilogue warps
 constexpr int kStRedBytes = kStRedBufs * kStWarps * 16 * 8 * 4;
+constexpr int kStTpBlocks = 8;                        // tensor parallel: 16-row blocks of a row-parallel phase one CTA may own (148 CTAs: dim <= 18 944)
+constexpr int kStTpKeepBytes = kStTpBlocks * 16 * kStMaxRows * 4; // this rank's fp32 partial sums of those blocks, kept between the two epilogue passes
+constexpr int kStTpMaxWorld = 8;
 
 // Activations travel between CTAs as TAGGED WORDS: one 8-byte word = two bf16 values (low half) + a 32-bit epoch tag
 // (high half), written with one 8-byte store and read with 8/16-byte volatile loads.  The tag is unique per
@@ -119,6 +122,16 @@ struct st_params {
     int* err;
     unsigned long long* timing; // diagnostics (nullable): 4 globaltimer stamps per (CTA, phase)
     unsigned long long* dbg;    // diagnostics (nullable): per-block stamps of CTA 0 in the vocabulary projection: [block][8]
+    // Tensor parallelism (tp_world > 1; the reference is single-device, nn/llama.h:86): this rank holds Hl = H / T heads, Fl = ffn / T
+    // channels and Vl = vocab / T rows of the head.  The row-parallel linears (wo, w2) end in an all-reduce that is FUSED into their
+    // epilogue: every rank's CTA c owns the same output rows, sends its fp32 partial sums as tagged words straight into the peers'
+    // exchange regions over NVLink (peer stores), polls the peers' words in its own region, sums in rank order and goes on with
+    // h = r(x + r(sum)) -- no collective call, no kernel boundary, no separate flag.  The greedy sampler joins (value, index) the same way.
+    uint32_t tp_world, tp_rank;
+    uint64_t* tp_part[kStTpMaxWorld]; // exchange region of every rank as mapped on THIS GPU: [kind 0 wo | 1 w2][src rank][row][dim] tagged words (fp32 payload)
+    uint64_t* tp_am[kStTpMaxWorld];   // [src rank][row][2]: value bits, global index
+    uint32_t tp_dim;                  // = dim (row pitch of the partial-sum words)
+    uint32_t tp_index_base;           // first vocabulary row of this rank's head shard
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------------------------------
@@ -191,6 +204,7 @@ struct st_ctx {
     uint32_t rdy0, fre0;      // shared addresses of ready[kStRedBufs] (partials written), free[kStRedBufs] (partials consumed)
     uint32_t sbar;            // shared address of the end-of-step mbarrier
     float* escr;              // [128] scratch of the epilogue warps
+    float* tpk;               // [kStTpBlocks][16][kStMaxRows] fp32 partial sums of a row-parallel phase (tensor parallel)
     volatile int* dead;       // set when a wait timed out somewhere: every later wait falls through
     float* scr;               // [16] block-reduce scratch
     float* red;               // [2][8 warps][16 rows][8 cols]
@@ -256,6 +270,17 @@ __device__ __forceinline__ uint64_t st_ll_load1(const uint64_t* p)
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
     return a;
 }
+// words exchanged with other GPUs: system scope (the peer's store arrives in this GPU's L2 over NVLink)
+__device__ __forceinline__ void st_ll_store_sys(uint64_t* p, uint32_t payload, uint32_t tag)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"((uint64_t(tag) << 32) | payload) : "memory");
+}
+__device__ __forceinline__ uint64_t st_ll_load1_sys(const uint64_t* p)
+{
+    uint64_t a;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
+    return a;
+}
 // one failed poll: returns true when the caller should give up (another wait timed out, or this one did)
 __device__ __forceinline__ bool st_poll_backoff(const st_ctx& c, unsigned& spins, int where = 0)
 {
@@ -292,6 +317,15 @@ __device__ __forceinline__ uint32_t st_poll1(const st_ctx& c, const uint64_t* p,
 #endif
             return 0;
         }
+    }
+}
+__device__ __forceinline__ uint32_t st_poll1_sys(const st_ctx& c, const uint64_t* p, uint32_t tag, int where)
+{
+    unsigned spins = 0;
+    for (;;) {
+        const uint64_t a = st_ll_load1_sys(p);
+        if (uint32_t(a >> 32) == tag) return uint32_t(a);
+        if (st_poll_backoff(c, spins, where)) return 0;
     }
 }
 __device__ __forceinline__ void st_stamp(unsigned long long* t, unsigned idx)
@@ -853,6 +887,39 @@ template <bool Q> __device__ __forceinline__ void st_epi_gemv(const st_params& P
         }
         if (fast_b) q = *reinterpret_cast<const uint2*>(lora_b + size_t(R) * 16 + 4 * sub);
     };
+    // Tensor parallel, row-parallel phase (wo, w2): pass 1 joins the k-slices of every block of this CTA into fp32 partial sums, keeps
+    // them in shared memory and sends them to the same rows' owner on every peer (tagged words, peer stores over NVLink); pass 2 -- the
+    // block loop below -- polls the peers' words of a block, sums the ranks in rank order and finishes the rows.  The mma warps get
+    // their partial buffers back in pass 1 already; NVLink latency is paid once per phase, not once per block.
+    const bool tp_sum = !Q && P.tp_world > 1 && g.epi == EPI_RESIDUAL;
+    const uint32_t tp_kind = (&g - P.g) == 3 ? 1u : 0u;
+    if (tp_sum) {
+        uint32_t bi = 0;
+        for (uint32_t b = r.b0; b < r.b1; b += bstep, bi++) {
+            uint32_t R, nr;
+            row_of(b, R, nr);
+            st_mbar_wait(c, c.rdy0 + bl.buf * 8, bl.parity);
+            const float* rr = c.red + bl.buf * (kStWarps * 128) + (2 * sub) * 128 + erow * 8;
+#pragma unroll
+            for (uint32_t col = 0; col < uint32_t(kStMaxRows); col++) {
+                if (col >= P.rows) break;
+                float sum = rr[col] + rr[128 + col];
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                if (erow < nr && bi < uint32_t(kStTpBlocks)) {
+                    if (sub == 0) c.tpk[(bi * 16 + erow) * kStMaxRows + col] = sum;
+                    // lane `sub` of a row serves peers sub and sub + 4
+                    for (uint32_t k = sub; k < P.tp_world; k += 4)
+                        if (k != P.tp_rank)
+                            st_ll_store_sys(P.tp_part[k] + (size_t(tp_kind * P.tp_world + P.tp_rank) * kStMaxRows + col) * P.tp_dim + R, __float_as_uint(sum), tag_out);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(c.fre0 + bl.buf * 8);
+            bl.advance();
+        }
+        epi_bar(); // the partial sums kept by one epilogue warp are read by whichever warp owns the row in pass 2 (the same one; cheap)
+    }
     if (r.b0 < r.b1) fetch(r.b0, resw, bq);
     if (Q && g.n_a && r.b0 < r.b1) {
         // every CTA needs all of ax for its LoRA-B epilogue (the barrier: the previous phase may still be reading its own)
@@ -871,15 +938,36 @@ template <bool Q> __device__ __forceinline__ void st_epi_gemv(const st_params& P
         uint32_t sl = 0; // which rank-wide slice of ax this weight row multiplies
         if (g.ax_slices == 2) sl = R & 1u;
         else if (g.ax_slices == 3) sl = R < g.slice_rows0 ? 0u : (R < g.slice_rows1 ? 1u : 2u);
-        st_mbar_wait(c, c.rdy0 + bl.buf * 8, bl.parity);
+        if (!tp_sum) st_mbar_wait(c, c.rdy0 + bl.buf * 8, bl.parity);
         if (is_head) st_dbg(P.dbg, (b - r.b0) / bstep, 4, kStConsumers);
         const float* rr = c.red + bl.buf * (kStWarps * 128) + (2 * sub) * 128 + erow * 8;
+        const uint32_t tp_bi = (b - r.b0) / bstep;
 #pragma unroll
         for (uint32_t col = 0; col < uint32_t(kStMaxRows); col++) {
             if (col >= P.rows) break; // (uniform) the loop is unrolled so that the per-column state stays in registers
-            float sum = rr[col] + rr[128 + col];
-            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            float sum;
+            if (!tp_sum) {
+                sum = rr[col] + rr[128 + col];
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            } else {
+                // all-reduce: the partial sums of the `world` ranks in rank order (this rank's from shared memory, the peers' from the words
+                // they stored into this GPU's exchange region), then ONE rounding: h = r(x + r(sum)) like the single-GPU chain
+                float pv[2] = {0.0f, 0.0f};
+                const bool live = erow < nr && tp_bi < uint32_t(kStTpBlocks);
+#pragma unroll
+                for (uint32_t j = 0; j < 2; j++) {
+                    const uint32_t src = sub + 4 * j;
+                    if (live && src < P.tp_world && src != P.tp_rank)
+                        pv[j] = __uint_as_float(st_poll1_sys(c, P.tp_part[P.tp_rank] + (size_t(tp_kind * P.tp_world + src) * kStMaxRows + col) * P.tp_dim + R, tag_out, 8));
+                }
+                const float own = live ? c.tpk[(tp_bi * 16 + erow) * kStMaxRows + col] : 0.0f;
+                sum = 0.0f;
+                for (uint32_t src = 0; src < P.tp_world; src++) {
+                    const float v = __shfl_sync(0xffffffffu, src < 4 ? pv[0] : pv[1], (lane & ~3u) | (src & 3u));
+                    sum += src == P.tp_rank ? own : v;
+                }
+            }
             float y = rbf(sum); // the bmm output buffer is T (kernel/bmm.metal:76)
             if (lora_b) {
                 // y = r(y + r(r(B . ax) * scale))   (quantization/lora.h:115-122)
@@ -921,9 +1009,11 @@ template <bool Q> __device__ __forceinline__ void st_epi_gemv(const st_params& P
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(c.fre0 + bl.buf * 8);
+        if (!tp_sum) {
+            if (lane == 0) mbar_arrive(c.fre0 + bl.buf * 8);
+            bl.advance();
+        }
         if (is_head) st_dbg(P.dbg, (b - r.b0) / bstep, 5, kStConsumers);
-        bl.advance();
         resw[0] = n_resw[0], resw[1] = n_resw[1], bq = n_bq;
     }
 }
@@ -1130,7 +1220,8 @@ template <bool Q, int HD> __global__ void __launch_bounds__(kStThreads, 1) decod
     c.scr = reinterpret_cast<float*>(smem + 256);
     c.escr = reinterpret_cast<float*>(smem + 320);
     c.red = reinterpret_cast<float*>(smem + kStHdrBytes);
-    c.act = smem + kStHdrBytes + kStRedBytes;
+    c.tpk = reinterpret_cast<float*>(smem + kStHdrBytes + kStRedBytes);
+    c.act = smem + kStHdrBytes + kStRedBytes + kStTpKeepBytes;
     c.act_addr = smem_u32(c.act);
     c.ring_addr = c.act_addr + P.act_bytes;
     c.err = P.err;
@@ -1225,6 +1316,29 @@ template <bool Q, int HD> __global__ void __launch_bounds__(kStThreads, 1) decod
                         const float ov = __shfl_xor_sync(0xffffffffu, v, off);
                         const int32_t oi = __shfl_xor_sync(0xffffffffu, i, off);
                         if (ov > v || (ov == v && oi < i)) v = ov, i = oi;
+                    }
+                    if (P.tp_world > 1) {
+                        // vocabulary-sharded head: every rank sends its (value, global index) winner to all ranks, then picks the global
+                        // winner (lowest index on ties) from the `world` pairs in its own region -- all ranks arrive at the same token
+                        if (i != 0x7fffffff) i += int32_t(P.tp_index_base);
+                        for (uint32_t k = lane; k < P.tp_world; k += 32) {
+                            uint64_t* dst = P.tp_am[k] + (size_t(P.tp_rank) * kStMaxRows + row) * 2;
+                            st_ll_store_sys(dst, __float_as_uint(v), tag_head);
+                            st_ll_store_sys(dst + 1, uint32_t(i), tag_head);
+                        }
+                        v = -INFINITY, i = 0x7fffffff;
+                        for (uint32_t k = lane; k < P.tp_world; k += 32) {
+                            const uint64_t* src = P.tp_am[P.tp_rank] + (size_t(k) * kStMaxRows + row) * 2;
+                            const float ov = __uint_as_float(st_poll1_sys(c, src, tag_head, 9));
+                            const int32_t oi = int32_t(st_poll1_sys(c, src + 1, tag_head, 9));
+                            if (ov > v || (ov == v && oi < i)) v = ov, i = oi;
+                        }
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) {
+                            const float ov = __shfl_xor_sync(0xffffffffu, v, off);
+                            const int32_t oi = __shfl_xor_sync(0xffffffffu, i, off);
+                            if (ov > v || (ov == v && oi < i)) v = ov, i = oi;
+                        }
                     }
                     if (lane == 0) {
                         if (i == 0x7fffffff) i = 0; // all-NaN / -inf row: argmax keeps index 0
