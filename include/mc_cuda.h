@@ -133,7 +133,7 @@ enum {
     MC_LLAMA_W4_PACKED = 1u << 0, /* store QLoRA int8-in-int4-range weights two per byte       */
     MC_LLAMA_NO_GRAPH = 1u << 1,  /* launch kernels directly instead of replaying a CUDA graph  */
     MC_LLAMA_NO_PDL = 1u << 2,    /* no programmatic dependent launch between decode kernels    */
-    MC_LLAMA_MEGAKERNEL = 1u << 3, /* experimental: the whole decode step as ONE persistent kernel with grid barriers */
+    /* 1u << 3 was an experimental grid-barrier megakernel, superseded by the streaming persistent kernel and removed */
     MC_LLAMA_NO_STREAM = 1u << 4,  /* do not use the streaming persistent kernel (TMA weight ring): per-op kernels under a CUDA graph */
     MC_LLAMA_NO_TC_PREFILL = 1u << 5, /* prompts go through the 4-row GEMV kernels instead of the tcgen05 GEMM path */
     MC_LLAMA_NO_SHADOW = 1u << 6,     /* quantised models: do not keep the resident bf16 image (2 bytes per weight) that the tensor-core

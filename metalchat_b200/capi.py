@@ -16,7 +16,7 @@ LIB_PATH = HERE / "libmc_cuda.so"
 
 MC_OK, MC_ERR_INVALID, MC_ERR_RUNTIME, MC_ERR_ALLOC, MC_ERR_NOT_FOUND, MC_ERR_FULL = range(6)
 MEM_DEVICE, MEM_SHARED, MEM_PINNED = 0, 1, 2
-LLAMA_W4_PACKED, LLAMA_NO_GRAPH, LLAMA_NO_PDL, LLAMA_MEGAKERNEL, LLAMA_NO_STREAM, LLAMA_NO_TC_PREFILL, LLAMA_NO_SHADOW, LLAMA_REF_CHUNK_MASK = 1, 2, 4, 8, 16, 32, 64, 128
+LLAMA_W4_PACKED, LLAMA_NO_GRAPH, LLAMA_NO_PDL, LLAMA_NO_STREAM, LLAMA_NO_TC_PREFILL, LLAMA_NO_SHADOW, LLAMA_REF_CHUNK_MASK = 1, 2, 4, 16, 32, 64, 128
 
 
 class McError(RuntimeError):

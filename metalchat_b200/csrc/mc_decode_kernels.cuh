@@ -16,6 +16,9 @@
 #pragma once
 #include "mc_common.cuh"
 
+// non-template kernels of the shared headers get internal linkage: several translation units include them
+#define MC_KERNEL static __global__
+
 namespace mc {
 
 constexpr int kGemvThreads = 256;
@@ -806,108 +809,12 @@ template <int HD> __global__ void __launch_bounds__(256) attn_decode_kernel(cons
     attn_body<HD, kAttnCluster>(p, smem, blockIdx.x / kAttnCluster, blockIdx.y, cluster_ctarank(), 0);
 }
 
-// ---- the persistent decode kernel: one launch per token ---------------------------------------------------------------
-// grid = (resident CTAs per SM) x 148, every CTA walks the same list of phases; a phase hands its output to the next
-// through the grid barrier above.  Phase list per block: QKV | attention | wo | w1-w3 | w2, then the vocab projection
-// with the greedy argmax fused, then one CTA picks the token and advances ids/pos for the next replay.
-struct mega_params {
-    gemv_params g[5];         // qkv, wo, w1-w3, w2 (layer 0 views; layer l adds l * layer_stride bytes to W / norm_w), head
-    attn_params attn;
-    size_t layer_stride;      // bytes between consecutive layers in the weight arena
-    size_t kv_layer_stride;   // elements between consecutive layers in the KV cache
-    size_t g_bytes[5];        // weight bytes of each of the above
-    uint32_t n_layers, rows, head_dim;
-    unsigned* bar;
-    int* err;
-    // sampler feedback
-    int32_t* ids;
-    int32_t* pos;
-    int32_t* out_log;
-    int32_t* step_counter;
-    int32_t advance;
-    unsigned long long* timing; // diagnostics: [phases][3] globaltimer stamps of CTA 0 (nullable)
-};
-
-__device__ __forceinline__ const void* shift(const void* p, size_t bytes) { return static_cast<const char*>(p) + bytes; }
-
-// The parameter block lives in __constant__ memory (one slot per captured graph); the phase loop contains exactly one
-// GEMV body (prologue / epilogue selected at run time, warp-uniform) and one attention body.
-constexpr int kMegaSlots = 24;
-__constant__ mega_params c_mega[kMegaSlots];
-
-template <int MB> __global__ void __launch_bounds__(kGemvThreads, 2) decode_megakernel(const int slot)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    const mega_params& P = c_mega[slot];
-    const unsigned G = gridDim.x;
-    const unsigned n_phases = P.n_layers * 5 + 1;
-#pragma unroll 1
-    for (unsigned phase = 0; phase < n_phases; phase++) {
-        const unsigned li = phase / 5, kind = phase - li * 5; // 0 qkv, 1 attention, 2 wo, 3 w1-w3, 4 w2
-        const bool is_head = phase + 1 == n_phases;
-        const size_t w_off = is_head ? 0 : size_t(li) * P.layer_stride;
-        const size_t kv_off = size_t(li) * P.kv_layer_stride;
-        unsigned long long* tm = P.timing ? P.timing + size_t(phase) * 3 : nullptr;
-        if (kind == 1 && !is_head) {
-            stamp(tm, 0);
-            l2_prefetch_slice(shift(P.g[2].W, w_off), P.g_bytes[2]);
-            grid_wait(mega_sync{P.bar, P.err, phase * G, nullptr, 0, nullptr});
-            stamp(tm, 1);
-            for (uint32_t item = blockIdx.x; item < P.attn.n_heads * P.rows; item += G) {
-                if (P.head_dim == 64) attn_body<64, 1>(P.attn, smem, item % P.attn.n_heads, item / P.attn.n_heads, 0, kv_off);
-                else attn_body<128, 1>(P.attn, smem, item % P.attn.n_heads, item / P.attn.n_heads, 0, kv_off);
-            }
-            stamp(tm, 2);
-            grid_arrive(P.bar);
-        } else {
-            // which GEMV, and which later weights to pull into L2 meanwhile: qkv -> wo, wo -> w2, w1-w3 -> next qkv
-            const unsigned gi = is_head ? 4u : (kind == 0 ? 0u : kind - 1);
-            const void* pf = nullptr;
-            size_t pfb = 0;
-            if (!is_head) {
-                if (kind == 0) pf = shift(P.g[1].W, w_off), pfb = P.g_bytes[1];
-                else if (kind == 2) pf = shift(P.g[3].W, w_off), pfb = P.g_bytes[3];
-                else if (kind == 3 && li + 1 < P.n_layers) pf = shift(P.g[0].W, w_off + P.layer_stride), pfb = P.g_bytes[0];
-            }
-            gemv_body<MB, -1, -1, true, 0>(P.g[gi], smem, mega_sync{P.bar, P.err, phase * G, pf, pfb, tm}, phase_adj{w_off, kv_off, phase == 0});
-        }
-    }
-    const unsigned phase = n_phases;
-    // sampler tail (greedy): CTA 0 joins the per-CTA partials, feeds the id back and advances the position
-    if (blockIdx.x == 0) {
-        grid_wait(mega_sync{P.bar, P.err, phase * G, nullptr, 0, nullptr});
-        stamp(P.timing, phase * 3);
-        if (threadIdx.x < P.rows) {
-            const uint32_t row = threadIdx.x;
-            float bv = -INFINITY;
-            int32_t bi = 0x7fffffff;
-            for (unsigned b = 0; b < G; b++) {
-                const float v = P.g[4].am_val[row * G + b];
-                const int32_t i = P.g[4].am_idx[row * G + b];
-                if (v > bv || (v == bv && i < bi)) bv = v, bi = i;
-            }
-            if (bi == 0x7fffffff) bi = 0;
-            const int32_t step = *P.step_counter;
-            P.out_log[size_t(step) * P.rows + row] = bi;
-            if (P.advance) {
-                P.ids[row] = bi;
-                P.pos[row] += 1;
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            *P.step_counter += 1;
-            *P.bar = 0; // every CTA has made its last arrival: ready for the next replay
-        }
-    }
-}
-
 // ---- sink-cache roll (nn/cache.h:183-204 + kernel/roll.metal:22-45) --------------------------------------------------------------
 // A decode step at a position beyond the cache keeps the first `pre_len` rows (the sink tokens), moves rows (pre_len, S) one row to
 // the left and writes the new row at S - 1.  The reference allocates a new cache and rolls into it; here the shift is in place:
 // one CTA per (layer, kv head, K|V) stream and decode row, tiles of 2048 16-byte chunks, every tile loaded completely before it is
 // stored one row lower (a tile's loads never touch what an earlier tile stored).  Rows whose position is inside the cache return.
-__global__ void __launch_bounds__(256) kv_roll_kernel(uint16_t* kcache, uint16_t* vcache, size_t kv_layer_stride, const int32_t* row_seq, const int32_t* row_pos,
+MC_KERNEL void __launch_bounds__(256) kv_roll_kernel(uint16_t* kcache, uint16_t* vcache, size_t kv_layer_stride, const int32_t* row_seq, const int32_t* row_pos,
                                                       uint32_t n_kv_heads, uint32_t head_dim, uint32_t max_seq, uint32_t pre_len)
 {
     pdl_launch_dependents();
@@ -938,7 +845,7 @@ __global__ void __launch_bounds__(256) kv_roll_kernel(uint16_t* kcache, uint16_t
 }
 
 // ---- K6: embedding gather (kernel/embedding.metal:38-66; lora_embedding quantization/lora.h:160-170) -----------
-__global__ void embed_kernel(uint16_t* x, uint32_t ldx, const void* table, const float* row_scales, int fmt, uint32_t D,
+MC_KERNEL void embed_kernel(uint16_t* x, uint32_t ldx, const void* table, const float* row_scales, int fmt, uint32_t D,
                              uint32_t vocab, const int32_t* ids)
 {
     pdl_launch_dependents();
@@ -960,7 +867,7 @@ __global__ void embed_kernel(uint16_t* x, uint32_t ldx, const void* table, const
 
 // ---- K7g: greedy argmax, lowest index on ties ---------------------------------------------------------------------
 constexpr int kArgmaxBlocks = 64;
-__global__ void __launch_bounds__(256) argmax_partial_kernel(const uint16_t* logits, uint32_t ld, uint32_t n, float* pval, int32_t* pidx)
+MC_KERNEL void __launch_bounds__(256) argmax_partial_kernel(const uint16_t* logits, uint32_t ld, uint32_t n, float* pval, int32_t* pidx)
 {
     pdl_launch_dependents();
     pdl_wait();
@@ -992,7 +899,7 @@ __global__ void __launch_bounds__(256) argmax_partial_kernel(const uint16_t* log
     }
 }
 // final stage + feedback: next id -> ids[row] (input of the next step), pos[row] += 1, log
-__global__ void argmax_final_kernel(const float* pval, const int32_t* pidx, int nblk, int32_t* ids, int32_t* pos, int32_t* out_log,
+MC_KERNEL void argmax_final_kernel(const float* pval, const int32_t* pidx, int nblk, int32_t* ids, int32_t* pos, int32_t* out_log,
                                     int32_t* step_counter, uint32_t rows, int advance)
 {
     pdl_launch_dependents();
@@ -1027,7 +934,7 @@ struct am_exchange {
     unsigned* epoch;                   // local
     int* err;
 };
-__global__ void argmax_final_tp_kernel(const float* pval, const int32_t* pidx, int nblk, int32_t index_base, am_exchange x, int32_t* ids, int32_t* pos,
+MC_KERNEL void argmax_final_tp_kernel(const float* pval, const int32_t* pidx, int nblk, int32_t index_base, am_exchange x, int32_t* ids, int32_t* pos,
                                        int32_t* out_log, int32_t* step_counter, uint32_t rows, int advance)
 {
     pdl_launch_dependents();
@@ -1098,7 +1005,7 @@ __global__ void argmax_final_tp_kernel(const float* pval, const int32_t* pidx, i
 
 // ---- synthetic weights (DESIGN.md "Synthetic data"; same hash as the test oracle) ----------------------------------
 // dst[r * dst_ld + c] = value(src_row0 + r, src_col0 + c) of the [*, src_K] tensor `tid`
-__global__ void gen_bf16_kernel(uint16_t* dst, size_t dst_ld, uint32_t rows, uint32_t cols, uint32_t src_row0, uint32_t src_col0,
+MC_KERNEL void gen_bf16_kernel(uint16_t* dst, size_t dst_ld, uint32_t rows, uint32_t cols, uint32_t src_row0, uint32_t src_col0,
                                 uint32_t src_K, uint64_t seed, uint64_t tid, float scale, float bias)
 {
     const uint64_t n = uint64_t(rows) * cols;
@@ -1111,7 +1018,7 @@ __global__ void gen_bf16_kernel(uint16_t* dst, size_t dst_ld, uint32_t rows, uin
         dst[size_t(r) * dst_ld + c] = f32_to_bf16_bits(v);
     }
 }
-__global__ void gen_f32_scales_kernel(float* dst, size_t dst_ld, uint32_t rows, uint32_t cols, uint32_t src_row0, uint32_t src_col0,
+MC_KERNEL void gen_f32_scales_kernel(float* dst, size_t dst_ld, uint32_t rows, uint32_t cols, uint32_t src_row0, uint32_t src_col0,
                                       uint32_t src_K, uint64_t seed, uint64_t tid, float c0)
 {
     const uint64_t n = uint64_t(rows) * cols;
@@ -1123,7 +1030,7 @@ __global__ void gen_f32_scales_kernel(float* dst, size_t dst_ld, uint32_t rows, 
         dst[size_t(r) * dst_ld + c] = __fmul_rn(__fadd_rn(1.0f, __fmul_rn(0.5f, u)), c0);
     }
 }
-__global__ void gen_i8_kernel(int8_t* dst, size_t dst_ld, uint32_t rows, uint32_t cols, uint32_t src_row0, uint32_t src_col0,
+MC_KERNEL void gen_i8_kernel(int8_t* dst, size_t dst_ld, uint32_t rows, uint32_t cols, uint32_t src_row0, uint32_t src_col0,
                               uint32_t src_K, uint64_t seed, uint64_t tid, int32_t lo, uint32_t range)
 {
     const uint64_t n = uint64_t(rows) * cols;

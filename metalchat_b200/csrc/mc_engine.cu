@@ -90,9 +90,9 @@ struct mc_llama {
     uint32_t key_begin = 0;     // first visible cache position of the prompt call in flight (MC_LLAMA_REF_CHUNK_MASK: its start_pos)
     bool image_a_dirty = false; // an adaptor A was replaced after the resident bf16 image had been built: its rows are re-copied by finalize
     std::vector<dlayer> layers;
-    dbuf layer_arena;          // all per-layer weights, one fixed stride per layer (the megakernel indexes by layer)
+    dbuf layer_arena;          // all per-layer weights, one fixed stride per layer (the streaming kernel indexes by layer)
     size_t layer_stride = 0;
-    dbuf bar, errflag;         // grid barrier counter / timeout flag of the megakernel
+    dbuf bar, errflag;         // (unused counter) / timeout flag of the persistent kernels' bounded waits
     // tensor parallelism: one exchange region per rank (partials | flags | argmax values | argmax flags), IPC-mapped on the peers
     dbuf tp_region, tp_local;  // tp_local: done counter, epoch, argmax epoch
     void* tp_peer_base[kTpMaxWorld] = {};
@@ -103,13 +103,11 @@ struct mc_llama {
     dbuf st_ll, st_timing;     // one arena of tagged words: x | h | z | qkv | attn | scores | argmax partials | ids
     size_t st_off[9] = {};
     uint32_t st_sc_words = 0, st_seq = 0;
+    uint32_t st_last_pos = 0;  // last position any sequence of the decode call in flight reaches (picks the attention variant)
     size_t st_words = 0;       // words of one copy of the tagged-word arena (the arena holds kStMaxRep copies)
     bool st_timing_on = false;
     int st_ok = -1;            // -1 not probed yet, 0 not usable on this device / shape, 1 usable
     uint32_t st_grid = 0;
-    dbuf mega_timing;          // diagnostics: per-phase globaltimer stamps (allocated on demand)
-    bool mega_timing_on = false;
-    int mega_ctas_per_sm[3] = {0, 0, 0};
     dlinear tok, out;
     dbuf norm;
     dbuf fcos, fsin;
@@ -141,7 +139,7 @@ struct mc_llama {
         for (dlinear* d : {&tok, &out}) d->w.release(), d->scales.release(), d->lora_b.release(), d->q8.release(), d->s32.release(), d->wd.release();
         for (int k = 0; k < kTpMaxWorld; k++)
             if (tp_peer_base[k] && uint32_t(k) != cfg.tp_rank) cudaIpcCloseMemHandle(tp_peer_base[k]);
-        for (dbuf* b : {&st_ll, &st_timing, &layer_arena, &bar, &errflag, &mega_timing, &tp_region, &tp_local, &norm, &fcos, &fsin, &kcache, &vcache, &x, &h, &q, &attn, &z, &logits, &logits_tmp, &hidden_save, &io_in, &io_out, &ids, &pos, &row_seq,
+        for (dbuf* b : {&st_ll, &st_timing, &layer_arena, &bar, &errflag, &tp_region, &tp_local, &norm, &fcos, &fsin, &kcache, &vcache, &x, &h, &q, &attn, &z, &logits, &logits_tmp, &hidden_save, &io_in, &io_out, &ids, &pos, &row_seq,
                         &uniforms, &out_log, &step_counter, &pval, &pidx, &lora_ax, &pack_bad, &cand, &pf_ids, &pf_x, &pf_h, &pf_n, &pf_qkv, &pf_q, &pf_attn, &pf_z, &dt_n, &dt_qkv, &pf_t, &pf_ax, &dt_t})
             b->release();
     }
@@ -348,7 +346,7 @@ template <int FMT, int PRO, int EPI> void qgemv_launch(launcher& L, const qgemv_
     }
 }
 
-// parameter blocks of the five GEMVs of layer `li` and of the head, shared by the per-kernel path and the megakernel
+// parameter blocks of the five GEMVs of layer `li` and of the head
 gemv_params qkv_params(mc_llama* m, uint32_t li, uint32_t row0, uint32_t rows)
 {
     const mc_llama_config& c = m->cfg;
@@ -556,96 +554,21 @@ void enqueue_rows(mc_llama* m, launcher& L, uint32_t row0, uint32_t rows, int he
     else if (head_mode == 1) gemv_launch<PRO_RMSNORM, EPI_NONE>(L, head_params(m, x, rows, logits_dst));
 }
 
-// __constant__ parameter slots of the megakernel: a process-wide pool per device, one slot per (model, rows, advance).
-std::mutex g_slot_mutex;
-const mc_llama* g_slot_owner[8][kMegaSlots] = {};
-uint32_t g_slot_key[8][kMegaSlots] = {};
-int mega_slot(mc_llama* m, uint32_t rows, int advance)
-{
-    std::lock_guard<std::mutex> lock(g_slot_mutex);
-    const int d = m->dev->ordinal & 7;
-    const uint32_t key = rows * 2 + uint32_t(advance);
-    for (int i = 0; i < kMegaSlots; i++)
-        if (g_slot_owner[d][i] == m && g_slot_key[d][i] == key) return i;
-    for (int i = 0; i < kMegaSlots; i++)
-        if (g_slot_owner[d][i] == nullptr) {
-            g_slot_owner[d][i] = m, g_slot_key[d][i] = key;
-            return i;
-        }
-    throw error(MC_ERR_RUNTIME, "megakernel: no free parameter slot (too many live models on this device)");
-}
-void release_mega_slots(const mc_llama* m)
-{
-    std::lock_guard<std::mutex> lock(g_slot_mutex);
-    for (auto& dev : g_slot_owner)
-        for (auto& o : dev)
-            if (o == m) o = nullptr;
-}
-
-// The whole decode step of rows [0, rows) as ONE persistent kernel (greedy sampling fused).
-template <int MB> void launch_megakernel(mc_llama* m, launcher& L, uint32_t rows, int advance)
-{
-    auto kernel = decode_megakernel<MB>;
-    const mc_llama_config& c = m->cfg;
-    const uint32_t kmax = std::max(std::max(c.dim, m->Hl * c.head_dim), m->Fl);
-    const size_t smem = std::max(gemv_smem(MB, kmax), attn_smem(m, 1));
-    MC_REQUIRE(smem <= 100 * 1024, "megakernel: activation rows do not fit in shared memory");
-    const int slot = MB == 1 ? 0 : (MB == 2 ? 1 : 2);
-    if (m->mega_ctas_per_sm[slot] == 0) {
-        MC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        int occ = 0;
-        MC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kGemvThreads, smem));
-        MC_REQUIRE(occ >= 1, "megakernel: does not fit on an SM");
-        m->mega_ctas_per_sm[slot] = std::min(occ, 2);
-    }
-    const uint32_t grid = uint32_t(m->dev->prop.multiProcessorCount) * m->mega_ctas_per_sm[slot];
-    mega_params P{};
-    P.g[0] = qkv_params(m, 0, 0, rows), P.g[1] = wo_params(m, 0, 0, rows), P.g[2] = w13_params(m, 0, 0, rows), P.g[3] = w2_params(m, 0, 0, rows);
-    P.g[4] = head_params(m, m->x.as<uint16_t>(), rows, m->logits.as<uint16_t>());
-    P.g[0].pro = PRO_RMSNORM, P.g[0].epi = EPI_QKV;
-    P.g[1].pro = PRO_NONE, P.g[1].epi = EPI_RESIDUAL;
-    P.g[2].pro = PRO_RMSNORM, P.g[2].epi = EPI_SWIGLU;
-    P.g[3].pro = PRO_NONE, P.g[3].epi = EPI_RESIDUAL;
-    P.g[4].pro = PRO_RMSNORM, P.g[4].epi = EPI_NONE;
-    P.attn = attn_params_of(m, 0, 0);
-    P.g[0].embed_table = m->tok.w.as<uint16_t>(), P.g[0].embed_ids = m->ids.as<int32_t>(), P.g[0].embed_out = m->x.as<uint16_t>();
-    P.g[4].am_val = m->pval.as<float>(), P.g[4].am_idx = m->pidx.as<int32_t>();
-    P.layer_stride = m->layer_stride, P.kv_layer_stride = kv_layer_elems(m);
-    P.g_bytes[0] = m->layers[0].wqkv.w.bytes, P.g_bytes[1] = m->layers[0].wo.w.bytes, P.g_bytes[2] = m->layers[0].w13.w.bytes;
-    P.g_bytes[3] = m->layers[0].w2.w.bytes, P.g_bytes[4] = size_t(m->Vl) * c.dim * 2;
-    P.n_layers = c.n_layers, P.rows = rows, P.head_dim = c.head_dim;
-    P.bar = m->bar.as<unsigned>(), P.err = m->errflag.as<int>();
-    P.ids = m->ids.as<int32_t>(), P.pos = m->pos.as<int32_t>(), P.out_log = m->out_log.as<int32_t>();
-    P.step_counter = m->step_counter.as<int32_t>(), P.advance = advance;
-    P.timing = m->mega_timing_on ? m->mega_timing.as<unsigned long long>() : nullptr;
-    // the parameter block goes to a __constant__ slot owned by this (model, rows, advance) combination
-    const int pslot = mega_slot(m, rows, advance);
-    MC_CUDA_CHECK(cudaMemcpyToSymbol(c_mega, &P, sizeof(P), size_t(pslot) * sizeof(mega_params), cudaMemcpyHostToDevice));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kGemvThreads), cfg.dynamicSmemBytes = smem, cfg.stream = L.s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative; // all CTAs must be co-resident for the grid barrier
-    attr[0].val.cooperative = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
-    L.mark();
-    MC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, pslot));
-    L.count++;
-    m->dev->launches.fetch_add(1);
-}
-
 // ---- the streaming persistent kernel (mc_stream_kernel.cuh) ---------------------------------------------------------------
+// k width of the bf16 ring tiles: 1024 (the last tile of a block is shorter when K is not a multiple; K must be a multiple of 256 =
+// 8 mma warps x 32 k), or the whole K when it is shorter than that
 uint32_t stream_kc(uint32_t K)
 {
-    for (uint32_t kc : {1024u, 768u, 512u, 256u})
-        if (K % kc == 0) return kc;
-    return 0;
+    if (K == 0 || K % 256 != 0) return 0;
+    return std::min<uint32_t>(K, 1024u);
 }
 // the kernel is specialised on (packed layers + adaptors, head_dim): each instantiation carries only the code it runs
 using stream_kernel_t = void (*)(const st_params);
-stream_kernel_t stream_kernel_of(bool quant, uint32_t head_dim)
+// the instantiations live in three translation units of their own (mc_stream_{bf16,quant,tp}.cu: they compile in parallel)
+stream_kernel_t stream_kernel_of(bool quant, uint32_t head_dim, bool tp, bool single)
 {
-    if (quant) return head_dim == 64 ? decode_stream_kernel<true, 64> : decode_stream_kernel<true, 128>;
-    return head_dim == 64 ? decode_stream_kernel<false, 64> : decode_stream_kernel<false, 128>;
+    if (tp) return mc::stream_kernel_tp(head_dim, single);
+    return quant ? mc::stream_kernel_quant(head_dim, single) : mc::stream_kernel_bf16(head_dim, single);
 }
 struct stream_geom {
     uint32_t act_pitch, act_bytes, sax_off, n_stages, stage_bytes;
@@ -657,10 +580,10 @@ bool stream_geometry(const mc_llama* m, uint32_t rows, stream_geom& g)
     const uint32_t kmax = std::max(std::max(c.dim, m->Hl * c.head_dim), m->Fl);
     // row pad: 64 bytes make the 16-byte fragment loads of the bf16 path conflict-free, 16 bytes the 4-byte loads of the packed paths
     g.act_pitch = kmax * 2 + (c.quant ? 16 : kStPad);
-    const size_t attn_scratch = (size_t(5) * c.head_dim + 1024 + c.max_seq_len + 8) * sizeof(float);
+    const size_t attn_scratch = (size_t(5) * c.head_dim + 2048 + c.max_seq_len + 8) * sizeof(float); // q, k, q', k', v | per-slot partial outputs | scores
     g.sax_off = uint32_t((std::max(size_t(rows) * g.act_pitch, attn_scratch) + 127) & ~size_t(127));
     g.act_bytes = g.sax_off + (c.quant ? uint32_t(kStMaxRows * 3 * c.lora_rank * sizeof(float) + 127) & ~127u : 0u);
-    const size_t fixed = kStHdrBytes + kStRedBytes + kStTpKeepBytes + g.act_bytes;
+    const size_t fixed = kStHdrBytes + kStRedBytes + (c.tp_world > 1 ? kStTpKeepBytes : 0) + g.act_bytes;
     const size_t cap = 232448; // 227 KiB of dynamic shared memory per CTA on sm_100
     g.stage_bytes = c.quant ? kStStageBytesPacked : kStStageBytes;
     if (fixed + 2 * size_t(g.stage_bytes) > cap) return false;
@@ -681,7 +604,7 @@ bool stream_eligible(mc_llama* m, uint32_t n, const mc_sampler_config& sc)
 {
     const mc_llama_config& c = m->cfg;
     static const bool env_off = getenv("MC_NO_STREAM") != nullptr;
-    if (env_off || (c.flags & (MC_LLAMA_NO_STREAM | MC_LLAMA_MEGAKERNEL))) return false;
+    if (env_off || (c.flags & MC_LLAMA_NO_STREAM)) return false;
     // Measured on B200 (1B bf16, KV 512): 1 sequence 1595 vs 1431 tokens/s (streaming vs per-op), 2: 2500 vs 2552, 4: 3137 vs 3855,
     // 8: 3671 vs 3907 - the streaming kernel walks attention items, staged rows and epilogue columns one after the other, so
     // by default it serves single-sequence decode; MC_STREAM_MAX_ROWS raises the limit (the kernel itself handles up to 8).
@@ -701,11 +624,16 @@ bool stream_eligible(mc_llama* m, uint32_t n, const mc_sampler_config& sc)
             shapes = shapes && ((m->Hl + 2 * m->KVl) * c.head_dim) % 16 == 0 && c.dim % 16 == 0 && (2 * m->Fl) % 16 == 0 && m->Vl % 16 == 0 && c.lora_rank % 8 == 0 &&
                      3 * c.lora_rank <= 128 && (c.head_dim / 2) % 8 == 0;
         if (shapes) {
-            auto kernel = stream_kernel_of(c.quant != 0, c.head_dim);
-            if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) == cudaSuccess) {
-                int occ = 0, coop = 0;
-                cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, m->dev->ordinal);
-                if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kStThreads, g.smem) == cudaSuccess && occ >= 1) {
+            bool ok = true;
+            int occ = 0, coop = 0;
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, m->dev->ordinal);
+            for (bool single : {false, true}) {
+                auto kernel = stream_kernel_of(c.quant != 0, c.head_dim, c.tp_world > 1, single);
+                ok = ok && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) == cudaSuccess && coop &&
+                     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kStThreads, g.smem) == cudaSuccess && occ >= 1;
+            }
+            if (ok) {
+                {
                     m->st_ok = 1;
                     m->st_grid = uint32_t(m->dev->prop.multiProcessorCount);
                 }
@@ -793,6 +721,9 @@ void launch_stream(mc_llama* m, launcher& L, uint32_t rows, int advance, uint32_
     P.out_log = m->out_log.as<int32_t>(), P.step_counter = m->step_counter.as<int32_t>(), P.advance = advance;
     P.err = m->errflag.as<int>();
     P.tp_world = c.tp_world, P.tp_rank = c.tp_rank, P.tp_dim = D, P.tp_index_base = c.tp_rank * m->Vl;
+    // one CTA per attention head while every history of the launch stays short (the host knows the last position of the launch)
+    static const int env_single = getenv("MC_ATTN_SINGLE_MAX") ? atoi(getenv("MC_ATTN_SINGLE_MAX")) : int(kStAttnSingleMax);
+    const bool attn_single = m->st_last_pos < uint32_t(std::max(env_single, 0));
     if (c.tp_world > 1) {
         const size_t gen = (m->st_seq >> 16) & 1u;
         for (uint32_t k = 0; k < c.tp_world; k++) {
@@ -810,7 +741,7 @@ void launch_stream(mc_llama* m, launcher& L, uint32_t rows, int advance, uint32_
     attr[0].val.cooperative = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
     L.mark();
-    MC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, stream_kernel_of(Q, hd), P));
+    MC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, stream_kernel_of(Q, hd, c.tp_world > 1, attn_single), P));
     L.count++;
     m->dev->launches.fetch_add(1);
 }
@@ -973,12 +904,6 @@ void enqueue_decode_step(mc_llama* m, launcher& L, uint32_t n, const mc_sampler_
     }
     if (stream_eligible(m, n, sc)) {
         launch_stream(m, L, n, advance, 1);
-        return;
-    }
-    if (n <= uint32_t(kMaxMB) && sc.mode == 0 && m->tok.fmt == WF_BF16 && m->cfg.tp_world == 1 && (m->cfg.flags & MC_LLAMA_MEGAKERNEL)) {
-        if (n == 1) launch_megakernel<1>(m, L, n, advance);
-        else if (n == 2) launch_megakernel<2>(m, L, n, advance);
-        else launch_megakernel<4>(m, L, n, advance);
         return;
     }
     if (decode_tc_eligible(m, n)) {
@@ -1367,7 +1292,7 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
     m->step_counter.view(m->io_in.as<int32_t>() + 3 * R, 4);
     m->io_out.alloc(16 + size_t(kMaxLogSteps) * R * 4);
     MC_CUDA_CHECK(cudaMemset(m->io_out.p, 0, 16));
-    MC_CUDA_CHECK(cudaMemset(m->io_out.as<char>() + 8, 0x7f, 4)); // (diagnostics: lowest failing wait, see check_mega_error)
+    MC_CUDA_CHECK(cudaMemset(m->io_out.as<char>() + 8, 0x7f, 4)); // (diagnostics: lowest failing wait, see check_device_error)
     m->errflag.view(m->io_out.p, 16), m->out_log.view(m->io_out.as<char>() + 16, size_t(kMaxLogSteps) * R * 4);
     m->uniforms.alloc(size_t(kMaxLogSteps) * R * 4);
     m->cand.alloc(size_t(R) * ((m->Vl + kSampleSlice - 1) / kSampleSlice) * kSampleKeep * 8);
@@ -1387,7 +1312,6 @@ mc_status mc_llama_destroy(mc_llama* m)
     if (m) {
         cudaSetDevice(m->dev->ordinal);
         cudaStreamSynchronize(m->dev->stream);
-        release_mega_slots(m);
         delete m;
     }
     MC_API_END
@@ -1694,7 +1618,7 @@ mc_status mc_llama_prefill(mc_llama* m, uint32_t seq, const int32_t* ids, uint32
     MC_API_END
 }
 
-static void check_mega_error(mc_llama* m, int flag)
+static void check_device_error(mc_llama* m, int flag)
 {
     if (flag) {
 #ifdef ST_DEBUG_WHERE
@@ -1737,6 +1661,7 @@ static void stage_decode_inputs(mc_llama* m, uint32_t n, const int32_t* ids, con
     // positions beyond the cache: the sink-cache roll runs at the head of every step of this call (nn/cache.h:183-204); RoPE keeps the
     // absolute position, so the tables must reach it
     m->sink_roll = last >= m->cfg.max_seq_len;
+    m->st_last_pos = uint32_t(last);
     if (m->sink_roll) MC_REQUIRE(m->cfg.tp_world == 1, "decode: positions beyond max_seq_len are not supported under tensor parallelism");
     if (last >= m->rope_rows) {
         MC_CUDA_CHECK(cudaStreamSynchronize(m->dev->stream));
@@ -1769,7 +1694,7 @@ mc_status mc_llama_decode(mc_llama* m, uint32_t n, const int32_t* ids, const int
     int32_t* st_out = m->pinned + 8 * m->max_rows + 128; // image of io_out: error flag (16 B) | first n log entries
     MC_CUDA_CHECK(cudaMemcpyAsync(st_out, m->io_out.p, 16 + n * 4, cudaMemcpyDeviceToHost, s));
     MC_CUDA_CHECK(cudaStreamSynchronize(s));
-    check_mega_error(m, st_out[0]);
+    check_device_error(m, st_out[0]);
     memcpy(out_ids, st_out + 4, n * 4);
     MC_API_END
 }
@@ -1819,7 +1744,7 @@ mc_status mc_llama_decode_loop(mc_llama* m, uint32_t n, const int32_t* first_ids
     if (elapsed_ms) *elapsed_ms = ms;
     int errv = 0;
     MC_CUDA_CHECK(cudaMemcpy(&errv, m->errflag.p, 4, cudaMemcpyDeviceToHost));
-    check_mega_error(m, errv);
+    check_device_error(m, errv);
     if (out_ids) MC_CUDA_CHECK(cudaMemcpy(out_ids, m->out_log.p, size_t(steps) * n * 4, cudaMemcpyDeviceToHost));
     MC_API_END
 }
@@ -1901,36 +1826,6 @@ mc_status mc_llama_profile_step(mc_llama* m, uint32_t n, float* us, uint32_t cap
             if (v && v < t0) t0 = v;
         *count = uint32_t(std::min<size_t>(n, cap));
         for (size_t i = 0; i < n && i < cap; i++) us[i] = t[i] ? float(t[i] - t0) * 1e-3f : 0.0f;
-        return MC_OK;
-    }
-    if (n <= uint32_t(kMaxMB) && m->cfg.tp_world == 1 && (m->cfg.flags & MC_LLAMA_MEGAKERNEL)) {
-        // megakernel: per-phase stamps of CTA 0; us[3k..3k+2] = {wait, work, until next phase entry} of phase k
-        const uint32_t phases = m->cfg.n_layers * 5 + 1;
-        if (!m->mega_timing.p) m->mega_timing.alloc(size_t(phases + 1) * 3 * 8);
-        MC_CUDA_CHECK(cudaMemsetAsync(m->mega_timing.p, 0, m->mega_timing.bytes, m->dev->stream));
-        MC_CUDA_CHECK(cudaMemsetAsync(m->step_counter.p, 0, 4, m->dev->stream));
-        m->mega_timing_on = true;
-        launcher L{m, m->dev->stream, false};
-        try {
-            enqueue_decode_step(m, L, n, sc, 0);
-        } catch (...) {
-            m->mega_timing_on = false;
-            throw;
-        }
-        m->mega_timing_on = false;
-        MC_CUDA_CHECK(cudaStreamSynchronize(m->dev->stream));
-        std::vector<unsigned long long> t(size_t(phases + 1) * 3);
-        MC_CUDA_CHECK(cudaMemcpy(t.data(), m->mega_timing.p, t.size() * 8, cudaMemcpyDeviceToHost));
-        *count = phases * 3;
-        for (uint32_t k = 0; k < phases; k++) {
-            const float wait = float(t[k * 3 + 1] - t[k * 3 + 0]) * 1e-3f, work = float(t[k * 3 + 2] - t[k * 3 + 1]) * 1e-3f;
-            const float gap = float(t[(k + 1) * 3] - t[k * 3 + 2]) * 1e-3f;
-            if (k * 3 + 2 < cap) us[k * 3] = wait, us[k * 3 + 1] = work, us[k * 3 + 2] = gap;
-        }
-        // the constant slot of (n, advance=0) now holds a timing pointer: refresh it on the next plain launch
-        release_mega_slots(m);
-        for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
-        m->graphs.clear();
         return MC_OK;
     }
     std::vector<cudaEvent_t> ev;

@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_q_kernel(const qgemv_par
 
 // ---- packing (bit-exact round trip; the reference stores one int4-range weight per int8, huggingface/llama.h:152-171) ----
 // q8: int8 [N, K] row-major (values in [-8, 7]); epi selects the unit -> rows mapping of the consumer kernel.
-__global__ void pack_w4_kernel(uint32_t* out, const int8_t* q8, gemv_params p, int epi, int* bad)
+MC_KERNEL void pack_w4_kernel(uint32_t* out, const int8_t* q8, gemv_params p, int epi, int* bad)
 {
     const uint32_t ktiles = p.K / 64, supers = (p.N / 2 + 7) / 8;
     const uint64_t words = uint64_t(supers) * ktiles * 32 * 4;
@@ -388,7 +388,7 @@ __global__ void pack_w4_kernel(uint32_t* out, const int8_t* q8, gemv_params p, i
         out[w] = word;
     }
 }
-__global__ void unpack_w4_kernel(int8_t* q8, const uint32_t* in, gemv_params p, int epi)
+MC_KERNEL void unpack_w4_kernel(int8_t* q8, const uint32_t* in, gemv_params p, int epi)
 {
     const uint32_t ktiles = p.K / 64, supers = (p.N / 2 + 7) / 8;
     const uint64_t words = uint64_t(supers) * ktiles * 32 * 4;
@@ -409,7 +409,7 @@ __global__ void unpack_w4_kernel(int8_t* q8, const uint32_t* in, gemv_params p, 
     }
 }
 // scales fp32 [N, K/32] -> bf16 r(s) in fragment order [super][ktile][g][4]
-__global__ void pack_w4_scales_kernel(uint16_t* out, const float* s, gemv_params p, int epi)
+MC_KERNEL void pack_w4_scales_kernel(uint16_t* out, const float* s, gemv_params p, int epi)
 {
     const uint32_t ktiles = p.K / 64, supers = (p.N / 2 + 7) / 8, groups = p.K / 32;
     const uint64_t n = uint64_t(supers) * ktiles * 8 * 4;
@@ -429,7 +429,7 @@ __global__ void pack_w4_scales_kernel(uint16_t* out, const float* s, gemv_params
     }
 }
 // int8 [N, K] -> fragment order for WF_W8ROW (adjacent-rows units)
-__global__ void pack_w8_kernel(uint32_t* out, const int8_t* q8, gemv_params p, int epi)
+MC_KERNEL void pack_w8_kernel(uint32_t* out, const int8_t* q8, gemv_params p, int epi)
 {
     const uint32_t ktiles = p.K / 32, supers = (p.N / 2 + 7) / 8;
     const uint64_t words = uint64_t(supers) * ktiles * 32 * 4;

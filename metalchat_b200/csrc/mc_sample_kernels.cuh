@@ -45,7 +45,7 @@ __device__ __forceinline__ void bitonic_desc_u64(unsigned long long* s, uint32_t
 }
 
 // grid (blocks, rows): candidates[row][block][64] = the 64 best (key-descending) of logits[row][block*2048 ...]
-__global__ void __launch_bounds__(256) sample_select_kernel(const uint16_t* logits, uint32_t ld, uint32_t vocab, uint32_t index_base,
+MC_KERNEL void __launch_bounds__(256) sample_select_kernel(const uint16_t* logits, uint32_t ld, uint32_t vocab, uint32_t index_base,
                                                             unsigned long long* cand)
 {
     pdl_launch_dependents();
@@ -90,7 +90,7 @@ struct sample_params {
 };
 
 // one CTA (1024 threads) per row
-__global__ void __launch_bounds__(1024) sample_finish_kernel(const sample_params p)
+MC_KERNEL void __launch_bounds__(1024) sample_finish_kernel(const sample_params p)
 {
     pdl_launch_dependents();
     pdl_wait();
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(1024) sample_finish_kernel(const sample_params
 }
 
 // last launch of a sampled decode step: bump the step counter once all rows are done
-__global__ void sample_step_kernel(int32_t* step_counter)
+MC_KERNEL void sample_step_kernel(int32_t* step_counter)
 {
     pdl_launch_dependents();
     pdl_wait();

@@ -435,10 +435,13 @@ template <bool Q> struct st_tile_iter {
             }
             if (blk < b1) {
                 const char* W = st_layer_ptr(P, g, g.W, li);
+                uint32_t kc_this = g.KC;
                 if (!Q || g.fmt == WF_BF16) {
+                    // tiles are KC k wide; when K is not a multiple of KC the last tile of a block is shorter (still a multiple of 256)
+                    kc_this = min(g.KC, g.K - kc);
                     t.kind = ST_T_ROWS, t.nr = min(uint32_t(kStTileRows), b1 - blk);
                     t.src = W + (size_t(blk) * g.K + kc) * 2;
-                    t.row_stride = size_t(g.K) * 2, t.bytes = g.KC * 2, t.pitch = g.KC * 2 + kStPad;
+                    t.row_stride = size_t(g.K) * 2, t.bytes = kc_this * 2, t.pitch = g.KC * 2 + kStPad;
                 } else if (g.fmt == WF_W4) {
                     // [super][ktile of 64 k][lane][16 B] and scales [super][ktile][8][4] bf16
                     const size_t kt0 = size_t(blk) * (g.K >> 6) + (kc >> 6);
@@ -449,7 +452,7 @@ template <bool Q> struct st_tile_iter {
                     const size_t kt0 = size_t(blk) * (g.K >> 5) + (kc >> 5);
                     t.kind = ST_T_W8, t.src = W + kt0 * 512, t.bytes = (g.KC >> 5) * 512;
                 }
-                kc += g.KC;
+                kc += kc_this;
                 if (kc >= g.K) kc = 0, blk += (!Q || g.fmt == WF_BF16) ? uint32_t(kStTileRows) : 1u;
                 return true;
             }
@@ -656,18 +659,19 @@ __device__ __forceinline__ void st_mma_rows(const st_params& P, const st_ctx& c,
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t gq = lane >> 2, t = lane & 3;
     const uint32_t pitch = kc_tile * 2 + kStPad;
-    const uint32_t kw = warp * (kc_tile / kStWarps); // this warp's k-slice inside a tile
-    const uint32_t ksteps = kc_tile / kStWarps / 32;
     const uint32_t brow = gq < P.rows ? gq : 0;      // batch row of this lane's B fragment (unused columns read row 0)
-    const uint32_t b_base = c.act_addr + brow * P.act_pitch + (kw + t * 8) * 2;
     // rows beyond the block read a valid row instead (their results are never stored)
-    const uint32_t a_off = min(gq, nr - 1) * pitch + (kw + t * 8) * 2;
+    const uint32_t a_row = min(gq, nr - 1) * pitch;
     const uint32_t a_hi = (min(gq + 8, nr - 1) - min(gq, nr - 1)) * pitch;
     float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     for (uint32_t kc = 0; kc < K; kc += kc_tile) {
+        // the last tile of a block may be shorter (K not a multiple of the tile width; always a multiple of 256 = 8 warps x 32 k)
+        const uint32_t kc_this = min(kc_tile, K - kc);
+        const uint32_t kw = warp * (kc_this / kStWarps); // this warp's k-slice inside the tile
+        const uint32_t ksteps = kc_this / kStWarps / 32;
         st_mbar_wait(c, c.full0 + cp.stage * 8, cp.parity);
-        const uint32_t tile = c.ring_addr + cp.stage * P.stage_bytes + a_off;
-        const uint32_t bk = b_base + kc * 2;
+        const uint32_t tile = c.ring_addr + cp.stage * P.stage_bytes + a_row + (kw + t * 8) * 2;
+        const uint32_t bk = c.act_addr + brow * P.act_pitch + (kc + kw + t * 8) * 2;
         // the k permutation (lane t reads 8 consecutive k) is applied to both operands
 #pragma unroll 4
         for (uint32_t s = 0; s < ksteps; s++) {
@@ -831,7 +835,7 @@ __device__ __forceinline__ float st_lora_dot(const uint16_t* brow, const float* 
     }
     return l;
 }
-template <bool Q> __device__ __forceinline__ void st_epi_gemv(const st_params& P, const st_gemv& g, const st_ctx& c, st_blk& bl, st_best& best, bool is_head, uint32_t li,
+template <bool Q, bool TP> __device__ __forceinline__ void st_epi_gemv(const st_params& P, const st_gemv& g, const st_ctx& c, st_blk& bl, st_best& best, bool is_head, uint32_t li,
                                             uint32_t tag_out, uint32_t res_tag)
 {
     // Thread (block row, quarter): four consecutive lanes share one of the 16 block rows; each joins two of the eight
@@ -891,9 +895,9 @@ template <bool Q> __device__ __forceinline__ void st_epi_gemv(const st_params& P
     // them in shared memory and sends them to the same rows' owner on every peer (tagged words, peer stores over NVLink); pass 2 -- the
     // block loop below -- polls the peers' words of a block, sums the ranks in rank order and finishes the rows.  The mma warps get
     // their partial buffers back in pass 1 already; NVLink latency is paid once per phase, not once per block.
-    const bool tp_sum = !Q && P.tp_world > 1 && g.epi == EPI_RESIDUAL;
+    const bool tp_sum = TP && g.epi == EPI_RESIDUAL; // (a compile-time false without tensor parallelism: the single-GPU kernels carry none of this code)
     const uint32_t tp_kind = (&g - P.g) == 3 ? 1u : 0u;
-    if (tp_sum) {
+    if constexpr (TP) if (tp_sum) {
         uint32_t bi = 0;
         for (uint32_t b = r.b0; b < r.b1; b += bstep, bi++) {
             uint32_t R, nr;
@@ -945,12 +949,12 @@ template <bool Q> __device__ __forceinline__ void st_epi_gemv(const st_params& P
 #pragma unroll
         for (uint32_t col = 0; col < uint32_t(kStMaxRows); col++) {
             if (col >= P.rows) break; // (uniform) the loop is unrolled so that the per-column state stays in registers
-            float sum;
+            float sum = 0.0f;
             if (!tp_sum) {
                 sum = rr[col] + rr[128 + col];
                 sum += __shfl_xor_sync(0xffffffffu, sum, 1);
                 sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-            } else {
+            } else if constexpr (TP) {
                 // all-reduce: the partial sums of the `world` ranks in rank order (this rank's from shared memory, the peers' from the words
                 // they stored into this GPU's exchange region), then ONE rounding: h = r(x + r(sum)) like the single-GPU chain
                 float pv[2] = {0.0f, 0.0f};
@@ -1019,24 +1023,31 @@ template <bool Q> __device__ __forceinline__ void st_epi_gemv(const st_params& P
 }
 
 // ---- consumers: attention phase ---------------------------------------------------------------------------------------
-// item = (row, head, part).  The four parts of a head split the cached positions for the scores and the head dimensions
-// for the output:
+// item = (row, head, part).  SPLITS = 4: the four parts of a head split the cached positions for the scores and the head dimensions
+// for the output (long histories: four SMs stream one head's K / V); SPLITS = 1: one CTA does a whole head -- no score exchange,
+// i.e. one dependent hop less per block, which is what counts while a head's K / V (<= 1024 positions) is a few round trips of one SM.
 //   1. rotate q and (position owner only) the new k (kernel/rope.metal:47-58); the owner of a kv head appends k', v to the
 //      cache (nn/cache.h:207-214);
-//   2. s[t] = r(r(q.K[t]) * scale) for this part's quarter of the positions, published as tagged words;
-//   3. every part polls ALL scores of the head, p = r(exp(s) / sum exp(s)) (no max shift, kernel/softmax.metal:40-80) in
-//      one fixed order, identical on the four parts;
-//   4. o[d] = r(sum_t p[t] V[t][d]) for this part's quarter of the head dimensions, published as tagged words.
-template <int HD>
+//   2. s[t] = r(r(q.K[t]) * scale) for this part's positions, (SPLITS > 1) published as tagged words;
+//   3. (SPLITS > 1) every part polls ALL scores of the head; p = r(exp(s) / sum exp(s)) (no max shift, kernel/softmax.metal:40-80) in
+//      one fixed order, identical on all parts;
+//   4. o[d] = r(sum_t p[t] V[t][d]) for this part's share of the head dimensions, published as tagged words.
+// Measured on B200 (1B, KV 512): one CTA per head is SLOWER than four (bf16 0.706 vs 0.649 ms per step, int4 0.845 vs 0.763): a single SM has
+// too few loads in flight for a head's 128 KB of K / V, which costs more than the score-exchange hop saves.  The variant stays reachable
+// through MC_ATTN_SINGLE_MAX (positions up to which one CTA takes a whole head); default 0 = never.
+constexpr uint32_t kStAttnSingleMax = 0;
+template <int HD, int SPLITS>
 __device__ __forceinline__ void st_attention(const st_params& P, uint32_t li, uint32_t step, const st_ctx& c, uint32_t tag_in, uint32_t tag_out)
 {
     constexpr int LPP = HD / 8;                 // lanes per cached K position (16 bytes each)
     constexpr int SLOTS = kStConsumers / LPP;   // K positions per sweep
-    constexpr int IT = 5;                       // K sweeps kept in flight
-    constexpr int DQ = HD / kStSplits;          // head dims finished by this part
-    constexpr int VL = DQ / 4;                  // lanes per cached V position (8 bytes = 4 dims each)
+    constexpr int IT = SPLITS == 1 ? 9 : 5;     // K sweeps kept in flight
+    constexpr int DQ = HD / SPLITS;             // head dims finished by this part
+    constexpr int VB = SPLITS == 1 ? 16 : 8;    // bytes of a V row per lane
+    constexpr int VD = VB / 2;                  // head dims per lane
+    constexpr int VL = DQ / VD;                 // lanes per cached V position
     constexpr int VSLOTS = kStConsumers / VL;   // V positions per sweep
-    constexpr int VIT = HD == 64 ? 9 : 18;      // V sweeps held in registers while the scores are exchanged
+    constexpr int VIT = SPLITS == 1 ? 8 : (HD == 64 ? 9 : 18); // V sweeps held in registers while the scores are finished
     const uint32_t tid = threadIdx.x;
     const uint32_t H = P.n_heads, KV = P.n_kv_heads, half = HD / 2, QKVW = (H + 2 * KV) * HD / 2;
     float* rawq = reinterpret_cast<float*>(c.act); // [HD] q as stored by the QKV phase
@@ -1044,19 +1055,19 @@ __device__ __forceinline__ void st_attention(const st_params& P, uint32_t li, ui
     float* sq = rawk + HD;                          // [HD] rotated q
     float* sk = sq + HD;                            // [HD] rotated new k
     float* sv = sk + HD;                            // [HD] new v
-    float* spart = sv + HD;                         // [VSLOTS][DQ] = 1024 floats
+    float* spart = sv + HD;                         // [VSLOTS][DQ] (<= 2048 floats)
     float* sp = spart + VSLOTS * DQ;                // [np] scores, then probabilities
     const uint32_t slot = tid / LPP, dl = tid % LPP;
     const uint32_t vslot = tid / VL, vl = tid % VL;
     const size_t kv_off = size_t(li) * P.kv_layer_stride;
-    const uint32_t n_items = P.rows * H * kStSplits;
+    const uint32_t n_items = P.rows * H * SPLITS;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const uint32_t part = item & (kStSplits - 1), head = (item / kStSplits) % H, row = (item / kStSplits) / H;
+        const uint32_t part = item % SPLITS, head = (item / SPLITS) % H, row = (item / SPLITS) / H;
         const int32_t seq = P.row_seq[row];
         const uint32_t pos = uint32_t(P.pos[row]) + step;
         const uint32_t np = pos + 1;
         const uint32_t kvh = head / (H / KV);
-        const uint32_t chunk = (((np + kStSplits - 1) / kStSplits) + 1) & ~1u; // even: two scores per tagged word
+        const uint32_t chunk = SPLITS == 1 ? np : ((((np + SPLITS - 1) / SPLITS) + 1) & ~1u); // even: two scores per tagged word
         const uint32_t t0 = min(np, part * chunk), t1 = min(np, t0 + chunk);
         const uint32_t tc1 = min(t1, pos); // positions below `pos` come from the cache, `pos` itself is fresh
         const bool own = pos >= t0 && pos < t1;
@@ -1106,6 +1117,12 @@ __device__ __forceinline__ void st_attention(const st_params& P, uint32_t li, ui
         float qv[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) qv[i] = sq[dl * 8 + i];
+        // V rows of the cached positions, this part's dims: requested before the scores are computed, in flight meanwhile
+        auto load_v = [&](uint32_t tt, uint32_t (&dst)[VB / 4]) {
+            const uint16_t* vp = Vc + size_t(tt) * HD + part * DQ + vl * VD;
+            if (VB == 16) asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(dst[0]), "=r"(dst[1]), "=r"(dst[VB / 4 - 2]), "=r"(dst[VB / 4 - 1]) : "l"(vp));
+            else asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(dst[0]), "=r"(dst[1]) : "l"(vp));
+        };
         // scores of this part's cached positions
         for (uint32_t tb = t0; tb < tc1; tb += IT * SLOTS) {
             if (tb != t0) {
@@ -1135,15 +1152,11 @@ __device__ __forceinline__ void st_attention(const st_params& P, uint32_t li, ui
                 if (tt < tc1 && dl == 0) sp[tt] = rbf(__fmul_rn(rbf(d), P.scale));
             }
         }
-        // V rows of ALL cached positions, this part's dims: in flight while the scores are exchanged
-        uint2 vreg[VIT];
+        uint32_t vreg[VIT][VB / 4];
 #pragma unroll
         for (int i = 0; i < VIT; i++) {
             const uint32_t tt = i * VSLOTS + vslot;
-            if (tt < pos) {
-                const uint16_t* vp = Vc + size_t(tt) * HD + part * DQ + vl * 4;
-                asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(vreg[i].x), "=r"(vreg[i].y) : "l"(vp));
-            }
+            if (tt < pos) load_v(tt, vreg[i]);
         }
         if (own && tid < 32) {
             float d = 0.0f;
@@ -1152,50 +1165,58 @@ __device__ __forceinline__ void st_attention(const st_params& P, uint32_t li, ui
             if (tid == 0) sp[pos] = rbf(__fmul_rn(rbf(d), P.scale));
         }
         consumer_bar();
-        // publish this part's scores, two per word
-        uint64_t* sc = P.sc_ll + size_t(item / kStSplits) * P.sc_words;
-        for (uint32_t tt = t0 + 2 * tid; tt < t1; tt += 2 * kStConsumers)
-            st_ll_store(sc + (tt >> 1), pack2(sp[tt], tt + 1 < t1 ? sp[tt + 1] : 0.0f), tag_out);
-        consumer_bar(); // sp is about to be overwritten with everybody's scores
-        for (uint32_t w = tid; w < (np + 1) / 2; w += kStConsumers) {
-            const uint32_t v = st_poll1(c, sc + w, tag_out, 4);
-            sp[2 * w] = bf_lo(v), sp[2 * w + 1] = bf_hi(v);
+        if (SPLITS > 1) {
+            // publish this part's scores, two per word, then collect everybody's
+            uint64_t* sc = P.sc_ll + size_t(item / SPLITS) * P.sc_words;
+            for (uint32_t tt = t0 + 2 * tid; tt < t1; tt += 2 * kStConsumers)
+                st_ll_store(sc + (tt >> 1), pack2(sp[tt], tt + 1 < t1 ? sp[tt + 1] : 0.0f), tag_out);
+            consumer_bar(); // sp is about to be overwritten with everybody's scores
+            for (uint32_t w = tid; w < (np + 1) / 2; w += kStConsumers) {
+                const uint32_t v = st_poll1(c, sc + w, tag_out, 4);
+                sp[2 * w] = bf_lo(v), sp[2 * w + 1] = bf_hi(v);
+            }
+            consumer_bar();
         }
-        consumer_bar();
         float part_sum = 0.0f;
         for (uint32_t i = tid; i < np; i += kStConsumers) part_sum += expf(sp[i]);
         const float total = st_block_sum(part_sum, c.scr);
         const float inv = 1.0f / total;
         for (uint32_t i = tid; i < np; i += kStConsumers) sp[i] = rbf(__fmul_rn(expf(sp[i]), inv));
         consumer_bar();
-        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        float acc[VD];
+#pragma unroll
+        for (int i = 0; i < VD; i++) acc[i] = 0.0f;
+        auto fma_v = [&](float pt, const uint32_t (&v)[VB / 4]) {
+#pragma unroll
+            for (int j = 0; j < VB / 4; j++) {
+                acc[2 * j] = fmaf(pt, bf_lo(v[j]), acc[2 * j]);
+                acc[2 * j + 1] = fmaf(pt, bf_hi(v[j]), acc[2 * j + 1]);
+            }
+        };
 #pragma unroll
         for (int i = 0; i < VIT; i++) {
             const uint32_t tt = i * VSLOTS + vslot;
-            if (tt < pos) {
-                const float pt = sp[tt];
-                acc[0] = fmaf(pt, bf_lo(vreg[i].x), acc[0]);
-                acc[1] = fmaf(pt, bf_hi(vreg[i].x), acc[1]);
-                acc[2] = fmaf(pt, bf_lo(vreg[i].y), acc[2]);
-                acc[3] = fmaf(pt, bf_hi(vreg[i].y), acc[3]);
+            if (tt < pos) fma_v(sp[tt], vreg[i]);
+        }
+        // the rest of the history in batches of VIT sweeps (all loads of a batch in flight together)
+        for (uint32_t tb = VIT * VSLOTS; tb < pos; tb += VIT * VSLOTS) {
+#pragma unroll
+            for (int i = 0; i < VIT; i++) {
+                const uint32_t tt = tb + i * VSLOTS + vslot;
+                if (tt < pos) load_v(tt, vreg[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < VIT; i++) {
+                const uint32_t tt = tb + i * VSLOTS + vslot;
+                if (tt < pos) fma_v(sp[tt], vreg[i]);
             }
         }
-        for (uint32_t tt = VIT * VSLOTS + vslot; tt < pos; tt += VSLOTS) {
-            uint2 vv;
-            const uint16_t* vp = Vc + size_t(tt) * HD + part * DQ + vl * 4;
-            asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(vv.x), "=r"(vv.y) : "l"(vp));
-            const float pt = sp[tt];
-            acc[0] = fmaf(pt, bf_lo(vv.x), acc[0]);
-            acc[1] = fmaf(pt, bf_hi(vv.x), acc[1]);
-            acc[2] = fmaf(pt, bf_lo(vv.y), acc[2]);
-            acc[3] = fmaf(pt, bf_hi(vv.y), acc[3]);
-        }
 #pragma unroll
-        for (int i = 0; i < 4; i++) spart[vslot * DQ + vl * 4 + i] = acc[i];
+        for (int i = 0; i < VD; i++) spart[vslot * DQ + vl * VD + i] = acc[i];
         consumer_bar();
         if (tid < DQ / 2) {
             float o0 = 0.0f, o1 = 0.0f;
-            for (int s = 0; s < VSLOTS; s++) o0 += spart[s * DQ + 2 * tid], o1 += spart[s * DQ + 2 * tid + 1];
+            for (int s2 = 0; s2 < VSLOTS; s2++) o0 += spart[s2 * DQ + 2 * tid], o1 += spart[s2 * DQ + 2 * tid + 1];
             const float pp = sp[pos];
             o0 = fmaf(pp, sv[part * DQ + 2 * tid], o0);
             o1 = fmaf(pp, sv[part * DQ + 2 * tid + 1], o1);
@@ -1207,7 +1228,9 @@ __device__ __forceinline__ void st_attention(const st_params& P, uint32_t li, ui
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------------
 // Q = the model has packed (int4 / int8) layers and LoRA adaptors; the bf16 instantiation carries none of that code
-template <bool Q, int HD> __global__ void __launch_bounds__(kStThreads, 1) decode_stream_kernel(const __grid_constant__ st_params P)
+// TP = tensor-parallel shard (all-reduce fused into the wo / w2 epilogues, cross-rank argmax); ATTN_SPLITS = CTAs per attention head (1: every
+// history of the launch is at most attn_single_max positions, decided by the host; kStSplits otherwise)
+template <bool Q, int HD, bool TP, int ATTN_SPLITS> __global__ void __launch_bounds__(kStThreads, 1) decode_stream_kernel(const __grid_constant__ st_params P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     st_ctx c;
@@ -1221,7 +1244,7 @@ template <bool Q, int HD> __global__ void __launch_bounds__(kStThreads, 1) decod
     c.escr = reinterpret_cast<float*>(smem + 320);
     c.red = reinterpret_cast<float*>(smem + kStHdrBytes);
     c.tpk = reinterpret_cast<float*>(smem + kStHdrBytes + kStRedBytes);
-    c.act = smem + kStHdrBytes + kStRedBytes + kStTpKeepBytes;
+    c.act = smem + kStHdrBytes + kStRedBytes + (TP ? kStTpKeepBytes : 0); // single-GPU kernels give those 4 KiB to the weight ring
     c.act_addr = smem_u32(c.act);
     c.ring_addr = c.act_addr + P.act_bytes;
     c.err = P.err;
@@ -1272,7 +1295,7 @@ template <bool Q, int HD> __global__ void __launch_bounds__(kStThreads, 1) decod
                     // the residual of wo is the x of this layer (embedding: this step's first phase; else the w2 before), of w2 the h of wo
                     const uint32_t tag_out = P.tag_base + gphase + 1;
                     const uint32_t res_tag = kind == 2 ? (li == 0 ? tag_out - 2 : tag_out - 3) : tag_out - 2;
-                    st_epi_gemv<Q>(P, P.g[is_head ? 4u : (kind == 0 ? 0u : kind - 1)], c, bl, best, is_head, is_head ? 0 : li, tag_out, res_tag);
+                    st_epi_gemv<Q, TP>(P, P.g[is_head ? 4u : (kind == 0 ? 0u : kind - 1)], c, bl, best, is_head, is_head ? 0 : li, tag_out, res_tag);
                     st_stamp(P.timing ? P.timing + (size_t(blockIdx.x) * (P.steps * phases_per_step) + gphase) * 4 : nullptr, 1);
                 }
             }
@@ -1317,7 +1340,7 @@ template <bool Q, int HD> __global__ void __launch_bounds__(kStThreads, 1) decod
                         const int32_t oi = __shfl_xor_sync(0xffffffffu, i, off);
                         if (ov > v || (ov == v && oi < i)) v = ov, i = oi;
                     }
-                    if (P.tp_world > 1) {
+                    if constexpr (TP) {
                         // vocabulary-sharded head: every rank sends its (value, global index) winner to all ranks, then picks the global
                         // winner (lowest index on ties) from the `world` pairs in its own region -- all ranks arrive at the same token
                         if (i != 0x7fffffff) i += int32_t(P.tp_index_base);
@@ -1369,7 +1392,7 @@ template <bool Q, int HD> __global__ void __launch_bounds__(kStThreads, 1) decod
                 unsigned long long* tm = P.timing ? P.timing + (size_t(blockIdx.x) * (P.steps * phases_per_step) + gphase) * 4 : nullptr;
                 st_stamp(tm, 0);
                 if (!is_head && kind == 1) {
-                    st_attention<HD>(P, li, step, c, tag_in, tag_out);
+                    st_attention<HD, ATTN_SPLITS>(P, li, step, c, tag_in, tag_out);
                     st_stamp(tm, 2);
                 } else {
                     const st_gemv& g = P.g[is_head ? 4u : (kind == 0 ? 0u : kind - 1)];
@@ -1386,5 +1409,12 @@ template <bool Q, int HD> __global__ void __launch_bounds__(kStThreads, 1) decod
         }
     }
 }
+
+// (packed layers, head_dim, tensor parallel, one CTA per attention head): each instantiation carries only the code it runs.
+// Defined in mc_stream_bf16.cu / mc_stream_quant.cu / mc_stream_tp.cu.
+using stream_kernel_fn = void (*)(const st_params);
+stream_kernel_fn stream_kernel_bf16(uint32_t head_dim, bool single_cta_attention);
+stream_kernel_fn stream_kernel_quant(uint32_t head_dim, bool single_cta_attention);
+stream_kernel_fn stream_kernel_tp(uint32_t head_dim, bool single_cta_attention);
 
 } // namespace mc

@@ -1,0 +1,13 @@
+// metalchat_b200/csrc/mc_stream_quant.cu — instantiations of the streaming persistent decode kernel (mc_stream_kernel.cuh) for
+// QLoRA models (packed int4 layers, int8 tables, LoRA adaptors): head_dim 64 / 128 x one or kStSplits CTAs per attention head.
+#include "mc_stream_kernel.cuh"
+
+namespace mc {
+
+stream_kernel_fn stream_kernel_quant(uint32_t head_dim, bool single)
+{
+    if (single) return head_dim == 64 ? decode_stream_kernel<true, 64, false, 1> : decode_stream_kernel<true, 128, false, 1>;
+    return head_dim == 64 ? decode_stream_kernel<true, 64, false, kStSplits> : decode_stream_kernel<true, 128, false, kStSplits>;
+}
+
+} // namespace mc

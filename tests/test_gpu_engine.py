@@ -65,8 +65,8 @@ def test_device_generator_matches_oracle_bits():
     assert np.array_equal(a.cache(0, 2, 0, len(ids)), b.cache(0, 2, 0, len(ids)))
 
 
-# streaming persistent kernel (default), then the per-op path: graph+PDL, no graph, no PDL, megakernel, megakernel without graph
-@pytest.mark.parametrize("flags", [0, 16, 18, 20, 8, 10])
+# streaming persistent kernel (default), then the per-op path: graph+PDL, no graph, no PDL, and the GEMV prompt path (no tensor-core prefill)
+@pytest.mark.parametrize("flags", [0, 16, 18, 20, 32, 48])
 def test_prefill_and_greedy_decode_match_oracle(flags):
     o = orc.Llama(orc.make_cfg(**SMALL), BF16)
     o.init_random(0x5EED)

@@ -1,5 +1,5 @@
-"""Per-launch (per-op path) or per-phase (megakernel) device times of one decode step.
-Usage: python tools_profile_step.py [1b|8b] [mega|ops]"""
+"""Per-launch (per-op path) or per-phase (streaming kernel) device times of one decode step.
+Usage: python tools/profile_step.py [1b|8b] [stream|ops] [quant]"""
 import sys
 import numpy as np
 import pathlib as _p, sys as _s
@@ -13,7 +13,7 @@ shape = bench.SHAPES[sys.argv[1] if len(sys.argv) > 1 else "1b"]
 mode = sys.argv[2] if len(sys.argv) > 2 else "stream"
 quant = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 dev = capi.Device(0)
-FLAGS = {"mega": capi.LLAMA_MEGAKERNEL, "ops": capi.LLAMA_NO_STREAM, "stream": 0}
+FLAGS = {"ops": capi.LLAMA_NO_STREAM, "stream": 0}
 m = capi.Llama(dev, capi.llama_config(**shape, max_seq_len=1024, flags=FLAGS[mode], quant=quant))
 m.init_random(0x5EED)
 m.finalize()
@@ -59,24 +59,6 @@ if mode == "stream":
         print("head blocks of CTA 0 (us): wait-full, mma, hand-over | epilogue: ready after mma-done, epilogue time")
         for i in range(0, 40, 4):
             print(i, " ".join(f"[{d[j,1]-d[j,0]:.2f} {d[j,2]-d[j,1]:.2f} {d[j,3]-d[j,2]:.2f} | {d[j,4]-d[j,3]:.2f} {d[j,5]-d[j,4]:.2f}]" for j in range(i, i + 4)))
-elif mode == "mega":
-    names = ["qkv", "attn", "wo", "w13", "w2"] * L + ["head"]
-    acc = {}
-    for rep in range(4):
-        us = m.profile_step(1).reshape(-1, 3)
-        m.decode_loop([1], [512], 2)
-        if rep == 0:
-            continue
-        for n, t in zip(names, us):
-            acc.setdefault(n, []).append(t)
-    tot = 0
-    for n, v in acc.items():
-        v = np.array(v)
-        per = v.mean(axis=0)
-        cnt = len(v) / 3
-        tot += per.sum() * cnt
-        print(f"{n:6s} wait {per[0]:7.2f}  work {per[1]:7.2f}  gap {per[2]:7.2f} us  x{cnt:3.0f} = {per.sum() * cnt:8.1f} us")
-    print("sum", tot)
 else:
     names = ["embed"] + ["qkv", "attn", "wo", "w13", "w2"] * L + ["head", "argmax1", "argmax2"]
     acc = {}
