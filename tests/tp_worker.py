@@ -23,8 +23,9 @@ os.environ.setdefault("MC_STREAM_MAX_ROWS", "8")
 
 CONFIGS = {
     "small": dict(dim=512, n_layers=3, n_heads=8, n_kv_heads=2, head_dim=64, ffn_dim=1024, vocab=2000, max_seq_len=96),
-    "hd128": dict(dim=1024, n_layers=2, n_heads=8, n_kv_heads=8, head_dim=128, ffn_dim=2048, vocab=4000, max_seq_len=96),
-    "batch8": dict(dim=512, n_layers=2, n_heads=8, n_kv_heads=8, head_dim=64, ffn_dim=1024, vocab=2000, max_seq_len=64),
+    # (sized so that every rank of an 8-GPU world still holds whole 256-column k-slices of wo and w2)
+    "hd128": dict(dim=2048, n_layers=2, n_heads=16, n_kv_heads=8, head_dim=128, ffn_dim=4096, vocab=4000, max_seq_len=96),
+    "batch8": dict(dim=2048, n_layers=2, n_heads=32, n_kv_heads=8, head_dim=64, ffn_dim=2048, vocab=2000, max_seq_len=64),
     "full": dict(dim=2048, n_layers=16, n_heads=32, n_kv_heads=8, head_dim=64, ffn_dim=8192, vocab=128256, max_seq_len=1024),
 }
 
