@@ -397,7 +397,7 @@ def workload_name(shape_name, fmt, batch, quant):
 
 
 def measure_decode(capi, torch, dist, dev, shape_name, fmt, batch, steps, warmup, rank, world, local, tp_on=False, per_op=False, e2e=True,
-                   clocks_index=None, workload_key=None):
+                   clocks_index=None, workload_key=None, collective="fused"):
     """One decode workload on this rank's GPU (or this rank's shard when tp_on): builds the model, fills a KV_LEN-token cache per
     sequence with the engine's own prefill, warms up, then times `steps` decode steps (CUDA events on the engine's stream inside
     mc_llama_decode_loop; max over ranks) and the same number of steps through the per-token call with host buffers."""
@@ -408,7 +408,7 @@ def measure_decode(capi, torch, dist, dev, shape_name, fmt, batch, steps, warmup
     if tp_on:
         from metalchat_b200 import tp
 
-        m = tp.create(dev, **shape, max_seq_len=1024, quant=quant, n_seqs=batch, flags=flags)
+        m = tp.create(dev, collective=collective, **shape, max_seq_len=1024, quant=quant, n_seqs=batch, flags=flags)
     else:
         m = capi.Llama(dev, capi.llama_config(**shape, max_seq_len=1024, quant=quant, n_seqs=batch, flags=flags))
     m.init_random(0x5EED)
@@ -550,6 +550,8 @@ def main():
     ap.add_argument("--per-op", action="store_true", help="per-op kernels under a CUDA graph instead of the streaming persistent kernel")
     ap.add_argument("--prompt", type=int, default=2048, help="prompt length of the *-prefill workloads")
     ap.add_argument("--tp", action="store_true", help="N > 1: ONE model sharded tensor-parallel over the N GPUs (the default for N > 1)")
+    ap.add_argument("--tp-collective", choices=["fused", "nccl"], default="fused",
+                    help="tensor parallel: the all-reduces of a block fused into the kernels over peer memory (default) or, as a comparator, ncclAllReduce calls between the per-op kernels")
     ap.add_argument("--replicas", action="store_true", help="N > 1: N independent replicas of the single-GPU workload (weak scaling) instead of one sharded model")
     ap.add_argument("--no-also", action="store_true", help="N = 1 default line: skip the additional workloads of the `also` list")
     args = ap.parse_args()
@@ -588,7 +590,8 @@ def main():
                     "how": "same workload on one GPU (rank 0's), measured in this run before the sharded model"}
         except Exception as e:  # e.g. the model does not fit one GPU
             base = {"n_gpus": 1, "unavailable": str(e)[:200]}
-    res = measure_decode(capi, torch, dist, dev, shape_name, fmt, args.batch, args.steps, args.warmup, rank, world, local, tp_on=tp_on, per_op=args.per_op)
+    res = measure_decode(capi, torch, dist, dev, shape_name, fmt, args.batch, args.steps, args.warmup, rank, world, local, tp_on=tp_on, per_op=args.per_op,
+                         collective=args.tp_collective if tp_on else "fused")
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -607,7 +610,9 @@ def main():
         "dtype": res["dtype"],
         "data": "synthetic ids, random-init weights (counter-hash seed 0x5EED)",
         "config": {"workload": workload, "kv_len": KV_LEN, "batch": B,
-                   "parallelism": (f"tp{world}: ONE model, column/row-split blocks, all-reduce fused into the GEMV kernels over NVLink peer memory; roofline per GPU shard"
+                   "parallelism": ((f"tp{world}: ONE model, column/row-split blocks, all-reduce fused into the kernels over NVLink peer memory; roofline per GPU shard"
+                                    if args.tp_collective == "fused" else
+                                    f"tp{world}: ONE model, column/row-split blocks, COMPARATOR: two ncclAllReduce calls per block between the per-op kernels (CUDA graph); roofline per GPU shard")
                                    if tp_on else f"{world} replica(s), one sequence stream per GPU"),
                    "path": "streaming persistent kernel" if res["streaming"] else "per-op kernels + CUDA graph",
                    "l2": f"weights streamed per step {res['streamed'] / 1e6:.0f} MB > 126 MB L2 (no flush needed)"},

@@ -155,6 +155,36 @@ MC_API mc_status mc_llama_destroy(mc_llama* m);
  * "layers.3.attention.wq.weight", "tok_embeddings.weight", "layers.0.feed_forward.w1.scales",
  * "layers.0.attention.wo.adaptor.A.weight".  Data is the FULL (unsharded) tensor in host memory. */
 MC_API mc_status mc_llama_set_tensor(mc_llama* m, const char* name, const void* host, size_t nbytes);
+/* The configuration the model was created with (defaults filled in). */
+MC_API mc_status mc_llama_get_config(mc_llama* m, mc_llama_config* cfg);
+
+/* ---- safetensors -> device (replaces safetensor_document::open / load, src/safetensor.cc:83-153,237-253 and
+ * include/metalchat/safetensor.h:689-747, for the decode path).  `path` is one file or a directory of *.safetensors shards.
+ * The file is mapped read-only; entries point into the mapping and stay valid until mc_safetensors_close. */
+typedef struct mc_safetensors mc_safetensors;
+typedef struct mc_safetensors_entry {
+    const char* name;    /* as written in the file                                              */
+    const char* dtype;   /* BOOL,I8,U8,I16,U16,F16,BF16,I32,U32,F32,F64,I64,U64 (safetensor.h:251-264) */
+    uint32_t rank;
+    uint64_t shape[8];
+    const void* data;    /* host pointer into the mapping                                       */
+    uint64_t nbytes;
+} mc_safetensors_entry;
+MC_API mc_status mc_safetensors_open(const char* path, mc_safetensors** out);
+MC_API mc_status mc_safetensors_close(mc_safetensors* st);
+MC_API mc_status mc_safetensors_count(mc_safetensors* st, uint32_t* n);
+MC_API mc_status mc_safetensors_entry_at(mc_safetensors* st, uint32_t index, mc_safetensors_entry* out);
+MC_API mc_status mc_safetensors_find(mc_safetensors* st, const char* name, mc_safetensors_entry* out);
+MC_API mc_status mc_safetensors_metadata(mc_safetensors* st, const char* key, const char** value); /* NULL when absent */
+/* Loads every parameter of `m` found in `st` (each one the FULL tensor: tensor-parallel ranks take their slices).
+ * MC_LOAD_HF_NAMES: the file uses HuggingFace names (renamed like huggingface/llama.h:88-103; lm_head -> output);
+ * MC_LOAD_META_PERMUTE: Meta-format checkpoint, rows of wq / wk are permuted to the rotate-half order (reference.h:73-94);
+ * MC_LOAD_STRICT: a parameter of the model missing from the file is an error (output.weight of a bf16 model excepted:
+ * it stays tied to the embedding, huggingface/llama.h:103).  fp32 / fp16 tensors of a bf16 model are rounded to bf16. */
+#define MC_LOAD_HF_NAMES 1u
+#define MC_LOAD_META_PERMUTE 2u
+#define MC_LOAD_STRICT 4u
+MC_API mc_status mc_llama_load_safetensors(mc_llama* m, mc_safetensors* st, uint32_t flags, uint32_t* n_loaded);
 /* Device-side synthetic weights: counter-hash generator keyed by (seed, tensor id, index),
  * distributions in DESIGN.md "Synthetic data"; bit-identical to the test oracle's generator. */
 MC_API mc_status mc_llama_init_random(mc_llama* m, uint64_t seed);
@@ -186,6 +216,12 @@ MC_API mc_status mc_llama_launches_per_step(mc_llama* m, uint32_t* kernels);
  * after wo and w2 is fused into the GEMV kernels over NVLink peer memory (DESIGN.md "Multi-GPU"). */
 MC_API mc_status mc_llama_tp_export(mc_llama* m, void* handle, size_t cap);
 MC_API mc_status mc_llama_tp_connect(mc_llama* m, const void* handles, size_t nbytes);
+/* Comparator for measurements only (bench.py --tp-collective nccl): the two all-reduces of a block become ncclAllReduce calls
+ * between the per-op kernels instead of the exchange fused into the kernels.  libnccl.so.2 is resolved with dlopen at this
+ * point (the library does not link against it).  Rank 0 makes the 128-byte id, the host hands it to every rank, every rank
+ * calls mc_llama_tp_use_nccl (a collective call) after mc_llama_tp_connect and before its first step. */
+MC_API mc_status mc_nccl_unique_id(void* id, size_t cap);
+MC_API mc_status mc_llama_tp_use_nccl(mc_llama* m, const void* id, size_t nbytes);
 /* Diagnostics: one ungraphed decode step with a CUDA event before every launch; us[i] = device time of launch i. */
 MC_API mc_status mc_llama_profile_step(mc_llama* m, uint32_t n, float* us, uint32_t cap, uint32_t* count);
 

@@ -61,6 +61,13 @@ def llama_config(dim=2048, n_layers=16, n_heads=32, n_kv_heads=8, head_dim=64, f
                        quant, lora_rank, lora_scale, group_size, n_seqs, tp_rank, tp_world, flags)
 
 
+class SafetensorsEntry(C.Structure):
+    """mc_safetensors_entry of include/mc_cuda.h"""
+    _fields_ = [("name", C.c_char_p), ("dtype", C.c_char_p), ("rank", C.c_uint32), ("shape", C.c_uint64 * 8), ("data", C.c_void_p), ("nbytes", C.c_uint64)]
+
+
+LOAD_HF_NAMES, LOAD_META_PERMUTE, LOAD_STRICT = 1, 2, 4
+
 # every exported symbol of include/mc_cuda.h (checked by tests/test_abi.py against the header)
 _SIGNATURES = {
     "mc_last_error": (C.c_char_p, []),
@@ -108,6 +115,14 @@ _SIGNATURES = {
     "mc_llama_create": (C.c_int, [C.c_void_p, C.POINTER(LlamaConfig), C.POINTER(C.c_void_p)]),
     "mc_llama_destroy": (C.c_int, [C.c_void_p]),
     "mc_llama_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]),
+    "mc_llama_get_config": (C.c_int, [C.c_void_p, C.POINTER(LlamaConfig)]),
+    "mc_safetensors_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mc_safetensors_close": (C.c_int, [C.c_void_p]),
+    "mc_safetensors_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
+    "mc_safetensors_entry_at": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(SafetensorsEntry)]),
+    "mc_safetensors_find": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(SafetensorsEntry)]),
+    "mc_safetensors_metadata": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p)]),
+    "mc_llama_load_safetensors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
     "mc_llama_init_random": (C.c_int, [C.c_void_p, C.c_uint64]),
     "mc_llama_finalize": (C.c_int, [C.c_void_p]),
     "mc_llama_weight_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -121,6 +136,8 @@ _SIGNATURES = {
     "mc_llama_launches_per_step": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "mc_llama_tp_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "mc_llama_tp_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "mc_nccl_unique_id": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "mc_llama_tp_use_nccl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "mc_llama_profile_step": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
     "mc_sample_default": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(SamplerConfig), C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -350,6 +367,66 @@ class CommandBuffer:
             pass
 
 
+_ST_NUMPY = {"BOOL": np.bool_, "I8": np.int8, "U8": np.uint8, "I16": np.int16, "U16": np.uint16, "F16": np.float16, "BF16": np.uint16, "I32": np.int32,
+             "U32": np.uint32, "F32": np.float32, "F64": np.float64, "I64": np.int64, "U64": np.uint64}
+
+
+class Safetensors:
+    """A safetensors file (or a directory of shards) mapped read-only by the library (mc_safetensors_*)."""
+
+    def __init__(self, path):
+        h = C.c_void_p()
+        check(lib().mc_safetensors_open(str(path).encode(), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            check(lib().mc_safetensors_close(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        n = C.c_uint32()
+        check(lib().mc_safetensors_count(self.h, C.byref(n)))
+        return n.value
+
+    @staticmethod
+    def _unpack(e):
+        return {"name": e.name.decode(), "dtype": e.dtype.decode(), "shape": tuple(int(e.shape[i]) for i in range(e.rank)), "nbytes": int(e.nbytes), "data": e.data}
+
+    def entries(self):
+        out = []
+        for i in range(len(self)):
+            e = SafetensorsEntry()
+            check(lib().mc_safetensors_entry_at(self.h, i, C.byref(e)))
+            out.append(self._unpack(e))
+        return out
+
+    def tensor(self, name: str) -> np.ndarray:
+        """A copy of one tensor (BF16 comes back as uint16 bit patterns)."""
+        e = SafetensorsEntry()
+        check(lib().mc_safetensors_find(self.h, name.encode(), C.byref(e)))
+        d = self._unpack(e)
+        raw = C.string_at(d["data"], d["nbytes"]) if d["nbytes"] else b""
+        return np.frombuffer(raw, dtype=_ST_NUMPY[d["dtype"]]).reshape(d["shape"]).copy()
+
+    def metadata(self, key: str):
+        v = C.c_char_p()
+        check(lib().mc_safetensors_metadata(self.h, key.encode(), C.byref(v)))
+        return v.value.decode() if v.value is not None else None
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    check(lib().mc_nccl_unique_id(buf, 128))
+    return buf.raw
+
+
 class Llama:
     """mc_llama: the fused decode engine (transformer<llama3>::transform, transformer.h:357-364)."""
 
@@ -365,6 +442,18 @@ class Llama:
 
     def init_random(self, seed: int = 0x5EED):
         check(lib().mc_llama_init_random(self.h, seed))
+
+    def config(self) -> LlamaConfig:
+        cfg = LlamaConfig()
+        check(lib().mc_llama_get_config(self.h, C.byref(cfg)))
+        return cfg
+
+    def load_safetensors(self, st: "Safetensors", flags: int = LOAD_STRICT) -> int:
+        """safetensors -> device (the loader behind safetensor_document::open / load, src/safetensor.cc:145-153); returns the
+        number of parameters loaded.  Call finalize() afterwards."""
+        n = C.c_uint32()
+        check(lib().mc_llama_load_safetensors(self.h, st.h, flags, C.byref(n)))
+        return n.value
 
     def finalize(self):
         check(lib().mc_llama_finalize(self.h))
@@ -427,6 +516,10 @@ class Llama:
     def tp_connect(self, handles: list[bytes]):
         blob = b"".join(handles)
         check(lib().mc_llama_tp_connect(self.h, blob, len(blob)))
+
+    def tp_use_nccl(self, unique_id: bytes):
+        """Comparator: the block all-reduces as ncclAllReduce calls between the per-op kernels (collective call, every rank)."""
+        check(lib().mc_llama_tp_use_nccl(self.h, unique_id, len(unique_id)))
 
     def launches_per_step(self) -> int:
         n = C.c_uint32()

@@ -19,6 +19,8 @@
 #include "mc_stream_kernel.cuh"
 #include "mc_prefill.h"
 
+#include <dlfcn.h>
+
 #include <cmath>
 #include <map>
 #include <memory>
@@ -79,6 +81,9 @@ struct dlayer {
 
 } // namespace
 
+namespace {
+void nccl_comm_release(void* comm);
+}
 struct mc_llama {
     mc_device* dev = nullptr;
     mc_llama_config cfg{};
@@ -97,6 +102,9 @@ struct mc_llama {
     dbuf tp_region, tp_local;  // tp_local: done counter, epoch, argmax epoch
     void* tp_peer_base[kTpMaxWorld] = {};
     bool tp_connected = false;
+    // comparator (bench.py --tp-collective nccl): the two all-reduces of a block as ncclAllReduce calls between the per-op kernels
+    void* nccl_comm = nullptr;
+    uint32_t tp_host_epoch = 0; // row-parallel GEMVs enqueued so far: its parity is the half of the exchange buffer the next one fills
     size_t tp_off_flags = 0, tp_off_amval = 0, tp_off_amidx = 0, tp_off_amflags = 0;
     size_t tp_off_stpart = 0, tp_off_stam = 0, tp_stpart_gen = 0, tp_stam_gen = 0; // streaming kernel: tagged partial sums / argmax pairs, two generations each
     // streaming persistent kernel (mc_stream_kernel.cuh): un-rotated q|k|v rows, split-attention exchange, step flag
@@ -131,6 +139,7 @@ struct mc_llama {
     ~mc_llama()
     {
         for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+        if (nccl_comm) nccl_comm_release(nccl_comm);
         if (pinned) cudaFreeHost(pinned);
         for (auto& l : layers) {
             for (dbuf* b : {&l.attn_norm, &l.ffn_norm, &l.lora_a_qkv, &l.lora_a_o, &l.lora_a_13, &l.lora_a_2}) b->release();
@@ -407,13 +416,64 @@ gemv_params w2_params(mc_llama* m, uint32_t li, uint32_t row0, uint32_t rows)
     p.ksplit = choose_ksplit(m->dev, p.N, p.K);
     return p;
 }
+// ---- NCCL comparator: libnccl.so.2 is resolved at run time (the library does not link against it; the product path never needs it) ----
+struct nccl_uid {
+    char internal[128];
+};
+struct nccl_api {
+    void* lib = nullptr;
+    int (*get_unique_id)(nccl_uid*) = nullptr;
+    int (*comm_init_rank)(void**, int, nccl_uid, int) = nullptr;
+    int (*all_reduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*comm_destroy)(void*) = nullptr;
+    const char* (*error_string)(int) = nullptr;
+};
+nccl_api& nccl()
+{
+    static nccl_api api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        // the copy torch has already loaded when there is one (one NCCL per process), the system's otherwise
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return;
+        api.lib = lib;
+        api.get_unique_id = reinterpret_cast<decltype(api.get_unique_id)>(dlsym(lib, "ncclGetUniqueId"));
+        api.comm_init_rank = reinterpret_cast<decltype(api.comm_init_rank)>(dlsym(lib, "ncclCommInitRank"));
+        api.all_reduce = reinterpret_cast<decltype(api.all_reduce)>(dlsym(lib, "ncclAllReduce"));
+        api.comm_destroy = reinterpret_cast<decltype(api.comm_destroy)>(dlsym(lib, "ncclCommDestroy"));
+        api.error_string = reinterpret_cast<decltype(api.error_string)>(dlsym(lib, "ncclGetErrorString"));
+    });
+    if (!(api.lib && api.get_unique_id && api.comm_init_rank && api.all_reduce && api.comm_destroy)) throw ::mc::error(MC_ERR_RUNTIME, "libnccl.so.2 could not be loaded");
+    return api;
+}
+void nccl_comm_release(void* comm) { nccl().comm_destroy(comm); }
+void nccl_check(int rc, const char* what)
+{
+    if (rc == 0) return;
+    const char* msg = nccl().error_string ? nccl().error_string(rc) : "?";
+    throw std::runtime_error(std::string(what) + ": " + msg);
+}
+// the all-reduce of the partial sums the row-parallel GEMV enqueued just before has left in this rank's exchange buffer (in place)
+void nccl_all_reduce_partials(mc_llama* m, launcher& L, uint32_t rows)
+{
+    const uint32_t parity = m->tp_host_epoch & 1u;
+    m->tp_host_epoch++;
+    float* buf = m->tp_region.as<float>() + size_t(parity) * kMaxMB * m->cfg.dim;
+    L.mark();
+    nccl_check(nccl().all_reduce(buf, buf, size_t(rows) * m->cfg.dim, /*ncclFloat32*/ 7, /*ncclSum*/ 0, m->nccl_comm, L.s), "ncclAllReduce");
+    L.count++;
+}
+
 tp_exchange tp_of(mc_llama* m)
 {
     tp_exchange t{};
     t.world = m->cfg.tp_world, t.rank = m->cfg.tp_rank, t.rows_max = kMaxMB, t.dim = m->cfg.dim;
+    if (m->nccl_comm) t.world = 1, t.rank = 0; // the partial sums stay local: NCCL reduces them in place between the two kernels
     for (uint32_t k = 0; k < t.world; k++) {
-        t.peer_buf[k] = static_cast<float*>(m->tp_peer_base[k]);
-        t.peer_flag[k] = reinterpret_cast<uint32_t*>(static_cast<char*>(m->tp_peer_base[k]) + m->tp_off_flags);
+        void* base = m->nccl_comm ? m->tp_region.p : m->tp_peer_base[k];
+        t.peer_buf[k] = static_cast<float*>(base);
+        t.peer_flag[k] = reinterpret_cast<uint32_t*>(static_cast<char*>(base) + m->tp_off_flags);
     }
     t.done = m->tp_local.as<unsigned>(), t.epoch = m->tp_local.as<unsigned>() + 1, t.err = m->errflag.as<int>();
     static const uint32_t nowait = getenv("MC_TP_NOWAIT") ? 1u : 0u;
@@ -534,9 +594,11 @@ void enqueue_rows(mc_llama* m, launcher& L, uint32_t row0, uint32_t rows, int he
             // row-parallel wo / w2 push fp32 partials to every rank; the next GEMV's prologue finishes the all-reduce
             go.tp = tp_of(m), g2.tp = tp_of(m);
             gemv_launch<PRO_NONE, EPI_PARTIAL_TP>(L, go);
+            if (m->nccl_comm) nccl_all_reduce_partials(m, L, rows);
             tp_consume(m, g13, x, h); // h = r(x + all-reduced wo output)
             gemv_launch<PRO_RMSNORM, EPI_SWIGLU>(L, g13);
             gemv_launch<PRO_NONE, EPI_PARTIAL_TP>(L, g2);
+            if (m->nccl_comm) nccl_all_reduce_partials(m, L, rows);
         }
     }
     if (tp) {
@@ -612,7 +674,7 @@ bool stream_eligible(mc_llama* m, uint32_t n, const mc_sampler_config& sc)
     if (sc.mode != 0 || n > std::min<uint32_t>(max_rows, kStMaxRows) || m->sink_roll) return false;
     // tensor parallel: bf16 models whose row-parallel phases fit the per-CTA partial-sum store; MC_TP_NO_STREAM keeps the per-op exchange
     static const bool tp_stream_off = getenv("MC_TP_NO_STREAM") != nullptr;
-    if (c.tp_world != 1 && (c.quant || !m->tp_connected || tp_stream_off || c.tp_world > uint32_t(kStTpMaxWorld))) return false;
+    if (c.tp_world != 1 && (c.quant || !m->tp_connected || tp_stream_off || m->nccl_comm || c.tp_world > uint32_t(kStTpMaxWorld))) return false;
     if (m->st_ok < 0) {
         m->st_ok = 0;
         stream_geom g;
@@ -1335,6 +1397,14 @@ mc_status mc_llama_set_tensor(mc_llama* m, const char* name, const void* host, s
     MC_API_END
 }
 
+mc_status mc_llama_get_config(mc_llama* m, mc_llama_config* cfg)
+{
+    MC_API_BEGIN
+    MC_REQUIRE(m && cfg, "bad arguments");
+    *cfg = m->cfg;
+    MC_API_END
+}
+
 mc_status mc_llama_init_random(mc_llama* m, uint64_t seed)
 {
     MC_API_BEGIN
@@ -1874,6 +1944,32 @@ mc_status mc_llama_tp_connect(mc_llama* m, const void* handles, size_t nbytes)
         m->tp_peer_base[k] = p;
     }
     m->tp_connected = true;
+    MC_API_END
+}
+
+mc_status mc_nccl_unique_id(void* id, size_t cap)
+{
+    MC_API_BEGIN
+    MC_REQUIRE(id && cap >= sizeof(nccl_uid), "nccl_unique_id: the buffer must hold 128 bytes");
+    nccl_uid u;
+    nccl_check(nccl().get_unique_id(&u), "ncclGetUniqueId");
+    memcpy(id, &u, sizeof(u));
+    MC_API_END
+}
+
+mc_status mc_llama_tp_use_nccl(mc_llama* m, const void* id, size_t nbytes)
+{
+    MC_API_BEGIN
+    use(m);
+    MC_REQUIRE(m->cfg.tp_world > 1, "tp_use_nccl: the model is not tensor parallel");
+    MC_REQUIRE(id && nbytes == sizeof(nccl_uid), "tp_use_nccl: expected the 128 bytes of mc_nccl_unique_id");
+    MC_REQUIRE(!m->nccl_comm, "tp_use_nccl: already set");
+    MC_REQUIRE(m->tp_host_epoch == 0 && m->graphs.empty(), "tp_use_nccl: call it before the first step");
+    nccl_uid u;
+    memcpy(&u, id, sizeof(u));
+    void* comm = nullptr;
+    nccl_check(nccl().comm_init_rank(&comm, int(m->cfg.tp_world), u, int(m->cfg.tp_rank)), "ncclCommInitRank"); // collective: every rank calls it
+    m->nccl_comm = comm;
     MC_API_END
 }
 

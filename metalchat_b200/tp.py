@@ -31,7 +31,16 @@ def connect(model: capi.Llama, group=None):
     model.tp_connect([bytes(h) for h in handles])
 
 
-def create(dev: capi.Device, group=None, **cfg) -> capi.Llama:
+def use_nccl(model: capi.Llama, group=None):
+    """Comparator (bench.py --tp-collective nccl): the all-reduces of a block go through ncclAllReduce instead of the fused exchange."""
+    import torch.distributed as dist
+
+    box = [capi.nccl_unique_id() if dist.get_rank(group) == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    model.tp_use_nccl(bytes(box[0]))
+
+
+def create(dev: capi.Device, group=None, collective: str = "fused", **cfg) -> capi.Llama:
     """Creates this rank's shard of a tensor-parallel model and wires it to its peers."""
     import torch.distributed as dist
 
@@ -39,4 +48,8 @@ def create(dev: capi.Device, group=None, **cfg) -> capi.Llama:
     m = capi.Llama(dev, capi.llama_config(**cfg, tp_rank=rank, tp_world=world))
     if world > 1:
         connect(m, group)
+        if collective == "nccl":
+            use_nccl(m, group)
+        else:
+            assert collective == "fused", collective
     return m

@@ -20,8 +20,11 @@ def n_gpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-def run_worker(mode, world, per_op, port):
+def run_worker(mode, world, per_op, port, nccl=False):
     env = dict(os.environ)
+    env.pop("MC_TP_NCCL", None)
+    if nccl:
+        env["MC_TP_NCCL"] = "1"
     if per_op:
         env["MC_TP_NO_STREAM"] = "1"
     else:
@@ -47,3 +50,13 @@ def test_tp_matches_single_gpu_and_oracle(mode, per_op):
     assert out["ok"], out
     if not per_op and mode != "batch8":
         assert out["launches_per_step"] == 1, "the streaming kernel did not take the tensor-parallel step"
+
+
+def test_tp_nccl_comparator_decodes_the_same_tokens():
+    """bench.py --tp-collective nccl: ncclAllReduce between the per-op kernels instead of the fused exchange (measurement comparator)."""
+    n = n_gpus()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    out = run_worker("small", 2, True, 29535, nccl=True)
+    assert out["ok"], out
+    assert out["launches_per_step"] > 1

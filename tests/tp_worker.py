@@ -8,7 +8,7 @@ split head) plus a full single-GPU copy.  Modes:
   full            the Llama-3.2-1B-shaped untied-head fixture (tests/golden/llama1b_L16_bf16-untied_p512_s64.json): 512-token prompt, then
                   64 teacher-forced steps judged like tests/test_gpu_golden.py (argmax per step, logits rows at the checkpoints)
 MC_TP_NO_STREAM=1 in the environment selects the per-op kernels (exchange fused into the GEMV kernels) instead of the streaming
-persistent kernel (exchange fused into its wo / w2 epilogues)."""
+persistent kernel (exchange fused into its wo / w2 epilogues); MC_TP_NCCL=1 the NCCL comparator (small / hd128 / batch8 only)."""
 import base64
 import json
 import os
@@ -60,12 +60,13 @@ def main():
     mode = sys.argv[1] if len(sys.argv) > 1 else "small"
     cfgd = CONFIGS[mode]
     dev = capi.Device(local)
-    report = {"world": world, "mode": mode, "path": "per-op" if os.environ.get("MC_TP_NO_STREAM") else "streaming"}
+    collective = "nccl" if os.environ.get("MC_TP_NCCL") else "fused"  # nccl: the comparator of bench.py --tp-collective nccl
+    report = {"world": world, "mode": mode, "path": "per-op + ncclAllReduce" if collective == "nccl" else "per-op" if os.environ.get("MC_TP_NO_STREAM") else "streaming"}
     ok = True
 
     if mode in ("small", "hd128", "batch8"):
         n_seqs = 8 if mode == "batch8" else 1
-        m = tp.create(dev, **cfgd, n_seqs=n_seqs)
+        m = tp.create(dev, collective=collective, **cfgd, n_seqs=n_seqs)
         m.init_random(0x5EED)
         m.finalize()
         single = capi.Llama(dev, capi.llama_config(**cfgd, n_seqs=n_seqs))
