@@ -183,6 +183,8 @@ struct gemv_params {
     int32_t tp_reduce;         // prologue: build the input rows from the peers' partial sums (+ residual)
     const uint16_t* tp_res;    // [rows, ldx] residual added to the reduced sum
     uint16_t* tp_out;          // [rows, ldx] where CTA 0 stores the reduced rows (the next residual)
+    uint32_t tp_col0;          // EPI_PARTIAL_TP: first column of the exchange row this GEMV fills (quantised models: the adaptor's A . x goes behind the dim main sums)
+    uint32_t tp_hold;          // EPI_PARTIAL_TP: fill the slot only; the GEMV launched next publishes the whole exchange row
 };
 
 // ---- grid-wide phase barrier of the persistent decode kernel ---------------------------------------------------
@@ -541,7 +543,7 @@ __device__ __forceinline__ void gemv_body(const gemv_params& p, unsigned char* s
             }
             if (EPI == EPI_PARTIAL_TP) {
                 // unrounded fp32 partial sums go to this rank's own slot; tp_publish copies the finished vector to the peers
-                float* dst = tp_slot(p.tp, p.tp.peer_buf[p.tp.rank], tp_parity, p.tp.rank) + size_t(m) * p.tp.dim;
+                float* dst = tp_slot(p.tp, p.tp.peer_buf[p.tp.rank], tp_parity, p.tp.rank) + size_t(m) * p.tp.dim + p.tp_col0;
                 dst[r0] = a;
                 dst[r1] = b;
             } else if (EPI == EPI_NONE) {
@@ -608,7 +610,7 @@ __device__ __forceinline__ void gemv_body(const gemv_params& p, unsigned char* s
             p.am_idx[threadIdx.x * gridDim.x + blockIdx.x] = bi;
         }
     }
-    if (EPI == EPI_PARTIAL_TP) tp_publish(p.tp, p.rows, tp_parity, reinterpret_cast<unsigned*>(sscr));
+    if (EPI == EPI_PARTIAL_TP && !p.tp_hold) tp_publish(p.tp, p.rows, tp_parity, reinterpret_cast<unsigned*>(sscr));
     if (MEGA) {
         stamp(sy.timing, 2);
         grid_arrive(sy.bar);

@@ -107,6 +107,7 @@ struct mc_llama {
     uint32_t tp_host_epoch = 0; // row-parallel GEMVs enqueued so far: its parity is the half of the exchange buffer the next one fills
     size_t tp_off_flags = 0, tp_off_amval = 0, tp_off_amidx = 0, tp_off_amflags = 0;
     size_t tp_off_stpart = 0, tp_off_stam = 0, tp_stpart_gen = 0, tp_stam_gen = 0; // streaming kernel: tagged partial sums / argmax pairs, two generations each
+    size_t tp_off_stax = 0, tp_stax_gen = 0;                                        // ... and the adaptors' partial A . x (quantised models)
     // streaming persistent kernel (mc_stream_kernel.cuh): un-rotated q|k|v rows, split-attention exchange, step flag
     dbuf st_ll, st_timing;     // one arena of tagged words: x | h | z | qkv | attn | scores | argmax partials | ids
     size_t st_off[9] = {};
@@ -454,12 +455,14 @@ void nccl_check(int rc, const char* what)
     const char* msg = nccl().error_string ? nccl().error_string(rc) : "?";
     throw std::runtime_error(std::string(what) + ": " + msg);
 }
+// floats per exchange row: the dim main sums, then (quantised models) the adaptor's partial A . x of the row-parallel linear
+uint32_t tp_row_floats(const mc_llama* m) { return m->cfg.dim + (m->cfg.quant ? 64u : 0u); }
 // the all-reduce of the partial sums the row-parallel GEMV enqueued just before has left in this rank's exchange buffer (in place)
 void nccl_all_reduce_partials(mc_llama* m, launcher& L, uint32_t rows)
 {
     const uint32_t parity = m->tp_host_epoch & 1u;
     m->tp_host_epoch++;
-    float* buf = m->tp_region.as<float>() + size_t(parity) * kMaxMB * m->cfg.dim;
+    float* buf = m->tp_region.as<float>() + size_t(parity) * kMaxMB * tp_row_floats(m);
     L.mark();
     nccl_check(nccl().all_reduce(buf, buf, size_t(rows) * m->cfg.dim, /*ncclFloat32*/ 7, /*ncclSum*/ 0, m->nccl_comm, L.s), "ncclAllReduce");
     L.count++;
@@ -468,7 +471,7 @@ void nccl_all_reduce_partials(mc_llama* m, launcher& L, uint32_t rows)
 tp_exchange tp_of(mc_llama* m)
 {
     tp_exchange t{};
-    t.world = m->cfg.tp_world, t.rank = m->cfg.tp_rank, t.rows_max = kMaxMB, t.dim = m->cfg.dim;
+    t.world = m->cfg.tp_world, t.rank = m->cfg.tp_rank, t.rows_max = kMaxMB, t.dim = tp_row_floats(m);
     if (m->nccl_comm) t.world = 1, t.rank = 0; // the partial sums stay local: NCCL reduces them in place between the two kernels
     for (uint32_t k = 0; k < t.world; k++) {
         void* base = m->nccl_comm ? m->tp_region.p : m->tp_peer_base[k];
@@ -531,6 +534,25 @@ void enqueue_rows_quant(mc_llama* m, launcher& L, uint32_t row0, uint32_t rows, 
         q.rank = rank, q.lora_scale = lscale;
         return q;
     };
+    const bool tp = c.tp_world > 1;
+    if (tp) MC_REQUIRE(m->tp_connected, "tensor parallel model: mc_llama_tp_connect has not been called");
+    // Row-parallel linear (wo / w2) under tensor parallelism: this rank's k range of the main sums AND of the adaptor's A . x go into
+    // one exchange row [dim | rank] as unrounded fp32 (the adaptor GEMV fills its columns, the main GEMV publishes the row to the
+    // peers); tp_finish_lora_kernel then sums the ranks and applies the roundings, the adaptor term and the residual for all rows.
+    auto row_parallel = [&](const gemv_params& g, const dlinear& d, const dbuf& A) {
+        gemv_params pa{};
+        pa.W = A.p, pa.N = rank, pa.K = g.K, pa.rows = rows, pa.x = g.x, pa.ldx = g.ldx;
+        pa.tp = tp_of(m), pa.tp_col0 = D, pa.tp_hold = 1;
+        gemv_launch<PRO_NONE, EPI_PARTIAL_TP>(L, pa);
+        qgemv_params q{};
+        q.g = g, q.g.tp = tp_of(m);
+        q.scales = d.scales.p, q.rank = rank, q.lora_scale = lscale;
+        qgemv_launch<WF_W4, PRO_NONE, EPI_PARTIAL_TP>(L, q);
+        tp_finish_params f{};
+        f.tp = tp_of(m), f.res = g.res, f.out = g.y, f.lora_b = d.lora_b.as<uint16_t>();
+        f.rows = rows, f.dim = D, f.ld = g.ldy, f.rank = rank, f.lora_scale = lscale;
+        L.go(tp_finish_lora_kernel, dim3((D + 255) / 256), dim3(256), 0, f);
+    };
     for (uint32_t li = 0; li < c.n_layers; li++) {
         dlayer& ly = m->layers[li];
         const gemv_params gq = qkv_params(m, li, row0, rows);
@@ -541,14 +563,20 @@ void enqueue_rows_quant(mc_llama* m, launcher& L, uint32_t row0, uint32_t rows, 
         if (hd == 64) L.go_cluster(attn_decode_kernel<64>, dim3(m->Hl * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
         else L.go_cluster(attn_decode_kernel<128>, dim3(m->Hl * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
         const gemv_params go = wo_params(m, li, row0, rows);
-        lora_a(go, ly.lora_a_o, rank, false);
-        qgemv_launch<WF_W4, PRO_NONE, EPI_RESIDUAL>(L, quant(go, ly.wo, 1));
+        if (tp) row_parallel(go, ly.wo, ly.lora_a_o);
+        else {
+            lora_a(go, ly.lora_a_o, rank, false);
+            qgemv_launch<WF_W4, PRO_NONE, EPI_RESIDUAL>(L, quant(go, ly.wo, 1));
+        }
         const gemv_params g13 = w13_params(m, li, row0, rows);
         lora_a(g13, ly.lora_a_13, 2 * rank, true);
         qgemv_launch<WF_W4, PRO_RMSNORM, EPI_SWIGLU>(L, quant(g13, ly.w13, 2));
         const gemv_params g2 = w2_params(m, li, row0, rows);
-        lora_a(g2, ly.lora_a_2, rank, false);
-        qgemv_launch<WF_W4, PRO_NONE, EPI_RESIDUAL>(L, quant(g2, ly.w2, 1));
+        if (tp) row_parallel(g2, ly.w2, ly.lora_a_2);
+        else {
+            lora_a(g2, ly.lora_a_2, rank, false);
+            qgemv_launch<WF_W4, PRO_NONE, EPI_RESIDUAL>(L, quant(g2, ly.w2, 1));
+        }
     }
     if (head_mode) {
         uint16_t* x = m->x.as<uint16_t>() + size_t(row0) * D;
@@ -629,7 +657,7 @@ using stream_kernel_t = void (*)(const st_params);
 // the instantiations live in three translation units of their own (mc_stream_{bf16,quant,tp}.cu: they compile in parallel)
 stream_kernel_t stream_kernel_of(bool quant, uint32_t head_dim, bool tp, bool single)
 {
-    if (tp) return mc::stream_kernel_tp(head_dim, single);
+    if (tp) return quant ? mc::stream_kernel_tp_quant(head_dim, single) : mc::stream_kernel_tp(head_dim, single);
     return quant ? mc::stream_kernel_quant(head_dim, single) : mc::stream_kernel_bf16(head_dim, single);
 }
 struct stream_geom {
@@ -674,12 +702,13 @@ bool stream_eligible(mc_llama* m, uint32_t n, const mc_sampler_config& sc)
     if (sc.mode != 0 || n > std::min<uint32_t>(max_rows, kStMaxRows) || m->sink_roll) return false;
     // tensor parallel: bf16 models whose row-parallel phases fit the per-CTA partial-sum store; MC_TP_NO_STREAM keeps the per-op exchange
     static const bool tp_stream_off = getenv("MC_TP_NO_STREAM") != nullptr;
-    if (c.tp_world != 1 && (c.quant || !m->tp_connected || tp_stream_off || m->nccl_comm || c.tp_world > uint32_t(kStTpMaxWorld))) return false;
+    if (c.tp_world != 1 && (!m->tp_connected || tp_stream_off || m->nccl_comm || c.tp_world > uint32_t(kStTpMaxWorld))) return false;
     if (m->st_ok < 0) {
         m->st_ok = 0;
         stream_geom g;
-        bool shapes = stream_kc(c.dim) && stream_kc(m->Hl * c.head_dim) && stream_kc(m->Fl) && c.dim <= 4096 && m->Fl % 2 == 0 && m->Vl % 2 == 0 &&
-                      m->dev->prop.multiProcessorCount <= 256 && stream_geometry(m, kStMaxRows, g);
+        // (geometry for the largest row count this model will be served with: 8 rows of an 8B / 70B-shard ffn vector do not fit next to the ring)
+        bool shapes = stream_kc(c.dim) && stream_kc(m->Hl * c.head_dim) && stream_kc(m->Fl) && m->Fl % 2 == 0 && m->Vl % 2 == 0 &&
+                      m->dev->prop.multiProcessorCount <= 256 && stream_geometry(m, std::min<uint32_t>(std::min<uint32_t>(max_rows, kStMaxRows), m->max_rows), g);
         // tensor parallel: a CTA keeps the partial sums of at most kStTpBlocks 16-row blocks of a row-parallel phase
         if (c.tp_world > 1) shapes = shapes && (c.dim + m->dev->prop.multiProcessorCount - 1) / m->dev->prop.multiProcessorCount + 16 <= uint32_t(kStTpBlocks) * 16;
         if (c.quant) // packed layouts: whole super-units of 16 rows, adaptor rows in pairs, rank in 16-byte steps
@@ -722,6 +751,7 @@ void launch_stream(mc_llama* m, launcher& L, uint32_t rows, int advance, uint32_
             const size_t old_gen = ((m->st_seq - 1) >> 16) & 1u;
             MC_CUDA_CHECK(cudaMemsetAsync(m->tp_region.as<char>() + m->tp_off_stpart + old_gen * m->tp_stpart_gen, 0, m->tp_stpart_gen, L.s));
             MC_CUDA_CHECK(cudaMemsetAsync(m->tp_region.as<char>() + m->tp_off_stam + old_gen * m->tp_stam_gen, 0, m->tp_stam_gen, L.s));
+            MC_CUDA_CHECK(cudaMemsetAsync(m->tp_region.as<char>() + m->tp_off_stax + old_gen * m->tp_stax_gen, 0, m->tp_stax_gen, L.s));
         }
         ++m->st_seq;
     }
@@ -792,6 +822,7 @@ void launch_stream(mc_llama* m, launcher& L, uint32_t rows, int advance, uint32_
             char* base = static_cast<char*>(m->tp_peer_base[k]);
             P.tp_part[k] = reinterpret_cast<uint64_t*>(base + m->tp_off_stpart + gen * m->tp_stpart_gen);
             P.tp_am[k] = reinterpret_cast<uint64_t*>(base + m->tp_off_stam + gen * m->tp_stam_gen);
+            P.tp_ax[k] = reinterpret_cast<uint64_t*>(base + m->tp_off_stax + gen * m->tp_stax_gen);
         }
     }
     P.timing = m->st_timing_on ? m->st_timing.as<unsigned long long>() : nullptr;
@@ -1211,7 +1242,8 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
     if (c.quant) {
         MC_REQUIRE(c.group_size == 32, "quantised layout: group_size must be 32 (huggingface/llama.h:167)");
         MC_REQUIRE(c.lora_rank >= 1 && c.lora_rank <= 64, "quantised layout: lora_rank out of range");
-        MC_REQUIRE(c.tp_world == 1, "quantised layout: tensor parallelism is not available");
+        MC_REQUIRE(c.tp_world == 1 || ((c.n_heads / c.tp_world * c.head_dim) % 256 == 0 && (c.ffn_dim / c.tp_world) % 256 == 0),
+                   "quantised layout under tensor parallelism: every rank's slice of n_heads*head_dim and of ffn_dim must be a multiple of 256");
     }
     auto m = std::make_unique<mc_llama>();
     m->dev = dev;
@@ -1297,7 +1329,7 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
     if (c.tp_world > 1) {
         // partial sums travel in passes of kMaxMB rows; the argmax exchange carries every sequence of a step at once
         const size_t rows_max = kMaxMB, T = c.tp_world, am_rows = std::max<uint32_t>(c.n_seqs, kMaxMB);
-        const size_t part = 2 * T * rows_max * D * sizeof(float);
+        const size_t part = 2 * T * rows_max * tp_row_floats(m.get()) * sizeof(float);
         m->tp_off_flags = part;
         m->tp_off_amval = m->tp_off_flags + 256;
         m->tp_off_amidx = m->tp_off_amval + ((2 * T * am_rows * 4 + 255) & ~size_t(255));
@@ -1310,7 +1342,9 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
         m->tp_stpart_gen = size_t(2) * T * kStMaxRows * D * 8;
         m->tp_off_stam = m->tp_off_stpart + 2 * m->tp_stpart_gen;
         m->tp_stam_gen = (T * kStMaxRows * 2 * 8 + 255) & ~size_t(255);
-        m->tp_region.alloc(m->tp_off_stam + 2 * m->tp_stam_gen);
+        m->tp_off_stax = m->tp_off_stam + 2 * m->tp_stam_gen;
+        m->tp_stax_gen = size_t(2) * T * kStMaxRows * kStTpAxCols * 8;
+        m->tp_region.alloc(m->tp_off_stax + 2 * m->tp_stax_gen);
         MC_CUDA_CHECK(cudaMemset(m->tp_region.p, 0, m->tp_region.bytes));
         m->tp_local.alloc(256);
         MC_CUDA_CHECK(cudaMemset(m->tp_local.p, 0, 256));
@@ -1962,6 +1996,7 @@ mc_status mc_llama_tp_use_nccl(mc_llama* m, const void* id, size_t nbytes)
     MC_API_BEGIN
     use(m);
     MC_REQUIRE(m->cfg.tp_world > 1, "tp_use_nccl: the model is not tensor parallel");
+    MC_REQUIRE(m->cfg.quant == 0, "tp_use_nccl: the comparator covers bf16 models only");
     MC_REQUIRE(id && nbytes == sizeof(nccl_uid), "tp_use_nccl: expected the 128 bytes of mc_nccl_unique_id");
     MC_REQUIRE(!m->nccl_comm, "tp_use_nccl: already set");
     MC_REQUIRE(m->tp_host_epoch == 0 && m->graphs.empty(), "tp_use_nccl: call it before the first step");

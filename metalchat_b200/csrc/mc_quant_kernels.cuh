@@ -127,6 +127,8 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_q_kernel(const qgemv_par
     }
     pdl_launch_dependents();
     pdl_wait();
+    unsigned tp_parity = 0;
+    if (EPI == EPI_PARTIAL_TP) tp_parity = *reinterpret_cast<volatile unsigned*>(p.tp.epoch) & 1u; // the epoch this launch will publish is +1
 
     // stage activation rows (zero rows above p.rows: they are the unused columns of the mma)
     for (uint32_t m = 0; m <= p.rows; m++) {
@@ -299,6 +301,14 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_q_kernel(const qgemv_par
             for (int bsel = 0; bsel < 2; bsel++) {
                 if (!(bsel == 0 ? fin0 : fin1)) continue;
                 const uint32_t m = 2 * t + bsel;
+                if (EPI == EPI_PARTIAL_TP) {
+                    // row-parallel linear under tensor parallelism: the unrounded fp32 partial sums of this rank's k range go to its own slot of
+                    // the exchange row; the adaptor term and the rounding follow the all-reduce (tp_finish_lora_kernel)
+                    float* dst = tp_slot(p.tp, p.tp.peer_buf[p.tp.rank], tp_parity, p.tp.rank) + size_t(m) * p.tp.dim;
+                    dst[r0] = bsel == 0 ? c[0] : c[1];
+                    dst[r1] = bsel == 0 ? c[2] : c[3];
+                    continue;
+                }
                 float y0 = rbf(bsel == 0 ? c[0] : c[1]), y1 = rbf(bsel == 0 ? c[2] : c[3]);
                 if (qp.lora_b) {
                     // y = r(y + r(r(B . ax) * scale))   (quantization/lora.h:115-122); 16-byte loads, all issued before use
@@ -356,6 +366,54 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_q_kernel(const qgemv_par
                 }
             }
         }
+    }
+    if (EPI == EPI_PARTIAL_TP) tp_publish(p.tp, p.rows, tp_parity, reinterpret_cast<unsigned*>(sscr));
+}
+
+// Tensor parallel QLoRA, after a row-parallel linear (wo / w2): every rank holds the `world` partial exchange rows
+// [dim main sums | rank adaptor sums] and finishes ALL rows of the residual stream itself, in the reference's order of roundings
+// (quantization/lora.h:115-122, nn/transformer.h:133,139):
+//   y = r(sum_k main_k),  ax = r(sum_k ax_k),  y = r(y + r(r(B . ax) * r(scale))),  out = r(res + y)
+// with the ranks summed in rank order.  One thread per output element; launched between the producer GEMV and the next phase.
+struct tp_finish_params {
+    tp_exchange tp;
+    const uint16_t* res;      // [rows, ld]
+    uint16_t* out;            // [rows, ld]
+    const uint16_t* lora_b;   // [dim, rank] bf16
+    uint32_t rows, dim, ld, rank;
+    float lora_scale;         // r(scale) as fp32
+};
+MC_KERNEL void __launch_bounds__(256) tp_finish_lora_kernel(const tp_finish_params q)
+{
+    __shared__ unsigned word;
+    __shared__ __align__(16) uint16_t sax[kMaxMB][64];
+    pdl_launch_dependents();
+    pdl_wait();
+    const unsigned e = tp_wait(q.tp, &word);
+    const uint32_t parity = (e - 1) & 1u;
+    float* mine = q.tp.peer_buf[q.tp.rank];
+    for (uint32_t i = threadIdx.x; i < q.rows * q.rank; i += blockDim.x) {
+        const uint32_t m = i / q.rank, j = i - m * q.rank;
+        float a = 0.0f;
+        for (uint32_t src = 0; src < q.tp.world; src++) a += __ldcg(tp_slot(q.tp, mine, parity, src) + size_t(m) * q.tp.dim + q.dim + j);
+        sax[m][j] = f32_to_bf16_bits(a);
+    }
+    __syncthreads();
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= q.dim) return;
+    for (uint32_t m = 0; m < q.rows; m++) {
+        float sum = 0.0f;
+        for (uint32_t src = 0; src < q.tp.world; src++) sum += __ldcg(tp_slot(q.tp, mine, parity, src) + size_t(m) * q.tp.dim + k);
+        float y = rbf(sum);
+        const uint16_t* bp = q.lora_b + size_t(k) * q.rank;
+        float l = 0.0f;
+        if ((q.rank & 7u) == 0) {
+            for (uint32_t j = 0; j < q.rank; j += 8) l = dot8(*reinterpret_cast<const uint4*>(bp + j), *reinterpret_cast<const uint4*>(&sax[m][j]), l);
+        } else {
+            for (uint32_t j = 0; j < q.rank; j++) l = fmaf(bf16_bits_to_f32(sax[m][j]), bf16_bits_to_f32(bp[j]), l);
+        }
+        y = rbf(__fadd_rn(y, rbf(__fmul_rn(rbf(l), q.lora_scale))));
+        q.out[size_t(m) * q.ld + k] = f32_to_bf16_bits(__fadd_rn(bf16_bits_to_f32(q.res[size_t(m) * q.ld + k]), y));
     }
 }
 

@@ -53,6 +53,7 @@ constexpr int kStRedBytes = kStRedBufs * kStWarps * 16 * 8 * 4;
 constexpr int kStTpBlocks = 8;                        // tensor parallel: 16-row blocks of a row-parallel phase one CTA may own (148 CTAs: dim <= 18 944)
 constexpr int kStTpKeepBytes = kStTpBlocks * 16 * kStMaxRows * 4; // this rank's fp32 partial sums of those blocks, kept between the two epilogue passes
 constexpr int kStTpMaxWorld = 8;
+constexpr int kStTpAxCols = 64; // adaptor rank <= 64
 
 // Activations travel between CTAs as TAGGED WORDS: one 8-byte word = two bf16 values (low half) + a 32-bit epoch tag
 // (high half), written with one 8-byte store and read with 8/16-byte volatile loads.  The tag is unique per
@@ -130,6 +131,7 @@ struct st_params {
     uint32_t tp_world, tp_rank;
     uint64_t* tp_part[kStTpMaxWorld]; // exchange region of every rank as mapped on THIS GPU: [kind 0 wo | 1 w2][src rank][row][dim] tagged words (fp32 payload)
     uint64_t* tp_am[kStTpMaxWorld];   // [src rank][row][2]: value bits, global index
+    uint64_t* tp_ax[kStTpMaxWorld];   // quantised models: [kind][src rank][row][kStTpAxCols] tagged fp32 partials of the row-parallel adaptors' A . x
     uint32_t tp_dim;                  // = dim (row pitch of the partial-sum words)
     uint32_t tp_index_base;           // first vocabulary row of this rank's head shard
 };
@@ -591,21 +593,29 @@ template <bool Q> __device__ __forceinline__ void st_stage_input(const st_params
                     st_ll_store(const_cast<uint64_t*>(P.g[1].res_ll) + size_t(m) * (P.g[1].N >> 1) + w, *reinterpret_cast<const uint32_t*>(dst + w * 2), tag_out);
                 consumer_bar();
             }
+#define MC_NORM2(d, vv, gg)                                                                          \
+    d = uint32_t(f32_to_bf16_bits(__fmul_rn(__fmul_rn(bf_lo(gg), bf_lo(vv)), inv))) |                \
+        (uint32_t(f32_to_bf16_bits(__fmul_rn(__fmul_rn(bf_hi(gg), bf_hi(vv)), inv))) << 16)
 #pragma unroll
             for (int j = 0; j < NB; j++) {
                 const uint32_t w = tid * 2 + j * (kStConsumers * 2);
                 if (w < n_words) {
                     const uint2 v = *reinterpret_cast<const uint2*>(dst + w * 2);
                     uint2 o;
-#define MC_NORM2(d, vv, gg)                                                                          \
-    d = uint32_t(f32_to_bf16_bits(__fmul_rn(__fmul_rn(bf_lo(gg), bf_lo(vv)), inv))) |                \
-        (uint32_t(f32_to_bf16_bits(__fmul_rn(__fmul_rn(bf_hi(gg), bf_hi(vv)), inv))) << 16)
                     MC_NORM2(o.x, v.x, nw[j].x);
                     MC_NORM2(o.y, v.y, nw[j].y);
-#undef MC_NORM2
                     *reinterpret_cast<uint2*>(dst + w * 2) = o;
                 }
             }
+            // rows wider than the NB prefetched norm-weight words per thread (dim > 4096: the 70B shape): the rest reads its weights here
+            for (uint32_t w = tid * 2 + NB * (kStConsumers * 2); w < n_words; w += kStConsumers * 2) {
+                const uint2 v = *reinterpret_cast<const uint2*>(dst + w * 2), gw = *reinterpret_cast<const uint2*>(norm_w + w * 2);
+                uint2 o;
+                MC_NORM2(o.x, v.x, gw.x);
+                MC_NORM2(o.y, v.y, gw.y);
+                *reinterpret_cast<uint2*>(dst + w * 2) = o;
+            }
+#undef MC_NORM2
         }
     }
     consumer_bar();
@@ -848,10 +858,49 @@ template <bool Q, bool TP> __device__ __forceinline__ void st_epi_gemv(const st_
     const bool storer = sub == 0 && (erow & (fin - 1)) == 0;
     const st_range r(g, Q);
     float* sax = reinterpret_cast<float*>(c.act + P.sax_off); // [8 rows][n_a] r(A . x) of this phase
+    // Tensor parallel, row-parallel phase (wo, w2): see pass 1 / pass 2 below
+    const bool tp_sum = TP && g.epi == EPI_RESIDUAL; // (a compile-time false without tensor parallelism: the single-GPU kernels carry none of this code)
+    const uint32_t tp_kind = (&g - P.g) == 3 ? 1u : 0u;
     if (Q && r.has_a) {
         // the two adaptor rows owned by this CTA: ax = r(A . x) (quantization/lora.h:115), one tagged word per batch row
         st_mbar_wait(c, c.rdy0 + bl.buf * 8, bl.parity);
-        if (et < P.rows) {
+        bool done = false;
+        if constexpr (TP) if (tp_sum) {
+            // row-parallel linear: A holds this rank's k range only, so the two sums are partial.  They go to every peer as tagged fp32
+            // words, the peers' arrive the same way; the ranks are summed in rank order and rounded once, like the single-GPU value.
+            // item = (batch row, source rank, which of the two adaptor rows), dealt over the 64 epilogue threads
+            const uint32_t W = P.tp_world, a0 = 2 * blockIdx.x, items = P.rows * W * 2;
+            float* tmp = c.tpk; // [row][src][2] (pass 1 below has not started yet)
+            auto own = [&](uint32_t row, uint32_t which) {
+                const float* rr = c.red + bl.buf * (kStWarps * 128) + which * 8 + row;
+                float v = 0.0f;
+#pragma unroll
+                for (int w = 0; w < kStWarps; w++) v += rr[w * 128];
+                return v;
+            };
+            auto slot = [&](uint32_t at, uint32_t src, uint32_t row, uint32_t which) {
+                return P.tp_ax[at] + (size_t(tp_kind * W + src) * kStMaxRows + row) * kStTpAxCols + a0 + which;
+            };
+            for (uint32_t i = et; i < items; i += kStEpiThreads) {
+                const uint32_t row = i / (2 * W), k = (i >> 1) % W, which = i & 1u;
+                const float v = own(row, which);
+                if (k == P.tp_rank) tmp[i] = v;
+                else st_ll_store_sys(slot(k, P.tp_rank, row, which), __float_as_uint(v), tag_out);
+            }
+            for (uint32_t i = et; i < items; i += kStEpiThreads) {
+                const uint32_t row = i / (2 * W), k = (i >> 1) % W, which = i & 1u;
+                if (k != P.tp_rank) tmp[i] = __uint_as_float(st_poll1_sys(c, slot(P.tp_rank, k, row, which), tag_out, 9));
+            }
+            epi_bar();
+            if (et < P.rows) {
+                float s0 = 0.0f, s1 = 0.0f;
+                for (uint32_t k = 0; k < W; k++) s0 += tmp[(et * W + k) * 2], s1 += tmp[(et * W + k) * 2 + 1];
+                st_ll_store(g.ax_ll + size_t(et) * (g.n_a >> 1) + blockIdx.x, pack2(s0, s1), tag_out);
+            }
+            epi_bar(); // tmp is pass 1's store from here on
+            done = true;
+        }
+        if (!done && et < P.rows) {
             const float* rr = c.red + bl.buf * (kStWarps * 128) + et;
             float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
@@ -895,8 +944,6 @@ template <bool Q, bool TP> __device__ __forceinline__ void st_epi_gemv(const st_
     // them in shared memory and sends them to the same rows' owner on every peer (tagged words, peer stores over NVLink); pass 2 -- the
     // block loop below -- polls the peers' words of a block, sums the ranks in rank order and finishes the rows.  The mma warps get
     // their partial buffers back in pass 1 already; NVLink latency is paid once per phase, not once per block.
-    const bool tp_sum = TP && g.epi == EPI_RESIDUAL; // (a compile-time false without tensor parallelism: the single-GPU kernels carry none of this code)
-    const uint32_t tp_kind = (&g - P.g) == 3 ? 1u : 0u;
     if constexpr (TP) if (tp_sum) {
         uint32_t bi = 0;
         for (uint32_t b = r.b0; b < r.b1; b += bstep, bi++) {
@@ -1416,5 +1463,6 @@ using stream_kernel_fn = void (*)(const st_params);
 stream_kernel_fn stream_kernel_bf16(uint32_t head_dim, bool single_cta_attention);
 stream_kernel_fn stream_kernel_quant(uint32_t head_dim, bool single_cta_attention);
 stream_kernel_fn stream_kernel_tp(uint32_t head_dim, bool single_cta_attention);
+stream_kernel_fn stream_kernel_tp_quant(uint32_t head_dim, bool single_cta_attention);
 
 } // namespace mc

@@ -60,3 +60,17 @@ def test_tp_nccl_comparator_decodes_the_same_tokens():
     out = run_worker("small", 2, True, 29535, nccl=True)
     assert out["ok"], out
     assert out["launches_per_step"] > 1
+
+
+@pytest.mark.parametrize("per_op", [False, True], ids=["streaming", "per_op"])
+def test_tp_quantised_model_matches_single_gpu_and_oracle(per_op):
+    """BASELINE.json configs[4] in small: the QLoRA layout sharded over the GPUs (column-split wq/wk/wv/w1/w3 with their scales and B rows,
+    row-split wo/w2 with column-split scales and A; the all-reduce carries the main sums and the adaptor's A . x), through the streaming
+    persistent kernel and through the per-op kernels."""
+    n = n_gpus()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    out = run_worker("quant", 2 if n < 4 else 4 if n < 8 else 8, per_op, 29536 + (1 if per_op else 0))
+    assert out["ok"], out
+    if not per_op:
+        assert out["launches_per_step"] == 1, "the streaming kernel did not take the quantised tensor-parallel step"
