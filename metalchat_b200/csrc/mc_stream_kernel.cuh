@@ -608,7 +608,6 @@ template <bool Q> __device__ __forceinline__ void st_stage_input(const st_params
                 }
             }
             // rows wider than the NB prefetched norm-weight words per thread (dim > 4096: the 70B shape): the rest reads its weights here
-#ifndef MC_ST_NO_TAIL
             for (uint32_t w = tid * 2 + NB * (kStConsumers * 2); w < n_words; w += kStConsumers * 2) {
                 const uint2 v = *reinterpret_cast<const uint2*>(dst + w * 2), gw = *reinterpret_cast<const uint2*>(norm_w + w * 2);
                 uint2 o;
@@ -616,7 +615,6 @@ template <bool Q> __device__ __forceinline__ void st_stage_input(const st_params
                 MC_NORM2(o.y, v.y, gw.y);
                 *reinterpret_cast<uint2*>(dst + w * 2) = o;
             }
-#endif
 #undef MC_NORM2
         }
     }
