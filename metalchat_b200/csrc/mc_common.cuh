@@ -5,6 +5,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <atomic>
 #include <cstdint>
@@ -41,6 +42,12 @@ mc_status fail(mc_status code, const std::string& m);
     do {                                                                                          \
         if (!(cond)) throw ::mc::error(MC_ERR_INVALID, std::string(msg));                         \
     } while (0)
+
+// NVTX range for the span of a C-ABI call (header-only NVTX v3: a no-op unless a tool is attached; shows up in nsys / ncu --nvtx)
+struct nvtx_range {
+    explicit nvtx_range(const char* name) { nvtxRangePushA(name); }
+    ~nvtx_range() { nvtxRangePop(); }
+};
 
 #define MC_API_BEGIN try {
 #define MC_API_END                                                                                \

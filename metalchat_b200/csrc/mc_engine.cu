@@ -1416,6 +1416,7 @@ mc_status mc_llama_destroy(mc_llama* m)
 mc_status mc_llama_set_tensor(mc_llama* m, const char* name, const void* host, size_t nbytes)
 {
     MC_API_BEGIN
+    nvtx_range nvtx_("mc_llama_set_tensor");
     use(m);
     MC_REQUIRE(name && host, "bad arguments");
     for (const slice2d& s : resolve(m, name)) {
@@ -1442,6 +1443,7 @@ mc_status mc_llama_get_config(mc_llama* m, mc_llama_config* cfg)
 mc_status mc_llama_init_random(mc_llama* m, uint64_t seed)
 {
     MC_API_BEGIN
+    nvtx_range nvtx_("mc_llama_init_random");
     use(m);
     const mc_llama_config& c = m->cfg;
     const bool Q = c.quant != 0;
@@ -1496,6 +1498,7 @@ mc_status mc_llama_init_random(mc_llama* m, uint64_t seed)
 mc_status mc_llama_finalize(mc_llama* m)
 {
     MC_API_BEGIN
+    nvtx_range nvtx_("mc_llama_finalize");
     use(m);
     if (m->cfg.quant && !m->finalized) {
         cudaStream_t s = m->dev->stream;
@@ -1677,6 +1680,7 @@ void prefill_tc(mc_llama* m, uint32_t seq, const int32_t* ids, uint32_t len, uin
 mc_status mc_llama_prefill(mc_llama* m, uint32_t seq, const int32_t* ids, uint32_t len, uint32_t start_pos)
 {
     MC_API_BEGIN
+    nvtx_range nvtx_("mc_llama_prefill");
     use(m);
     MC_REQUIRE(m->finalized, "mc_llama_finalize must be called before prefill");
     MC_REQUIRE(ids && len > 0, "prefill: empty input");
@@ -1783,6 +1787,7 @@ mc_status mc_llama_decode(mc_llama* m, uint32_t n, const int32_t* ids, const int
                           const mc_sampler_config* sampler, int32_t* out_ids)
 {
     MC_API_BEGIN
+    nvtx_range nvtx_("mc_llama_decode");
     use(m);
     MC_REQUIRE(m->finalized, "mc_llama_finalize must be called before decode");
     MC_REQUIRE(out_ids, "decode: null output");
@@ -1807,6 +1812,7 @@ mc_status mc_llama_decode_loop(mc_llama* m, uint32_t n, const int32_t* first_ids
                                const float* uniforms, const mc_sampler_config* sampler, int32_t* out_ids, float* elapsed_ms)
 {
     MC_API_BEGIN
+    nvtx_range nvtx_("mc_llama_decode_loop");
     use(m);
     MC_REQUIRE(m->finalized, "mc_llama_finalize must be called before decode");
     MC_REQUIRE(steps >= 1 && steps <= kMaxLogSteps, "decode_loop: steps out of range");

@@ -459,6 +459,7 @@ mc_status mc_safetensors_metadata(mc_safetensors* st, const char* key, const cha
 mc_status mc_llama_load_safetensors(mc_llama* m, mc_safetensors* st, uint32_t flags, uint32_t* n_loaded)
 {
     MC_API_BEGIN
+    nvtx_range nvtx_("mc_llama_load_safetensors");
     MC_REQUIRE(m && st, "bad arguments");
     mc_llama_config cfg{};
     if (mc_llama_get_config(m, &cfg) != MC_OK) throw error(MC_ERR_RUNTIME, mc_last_error());
