@@ -769,7 +769,8 @@ void launch_stream(mc_llama* m, launcher& L, uint32_t rows, int advance, uint32_
         g.N = N, g.K = K, g.fmt = d.fmt, g.pro = pro, g.epi = epi, g.layered = layered;
         if (d.fmt == WF_BF16) g.KC = stream_kc(K), g.gran = epi == EPI_SWIGLU ? 4 : 2;
         else g.KC = stream_kc_packed(K, d.fmt == WF_W4 ? 2048 : 1024), g.gran = 16, g.scales = d.scales.p; // 16 KiB tiles
-        if (lora_a && lora_a->p) {
+        static const bool diag_no_lora = getenv("MC_STREAM_DIAG_NO_LORA") != nullptr; // diagnostics: what the adaptor path costs (results are wrong)
+        if (lora_a && lora_a->p && !diag_no_lora) {
             g.lora_a = lora_a->as<uint16_t>(), g.lora_b = d.lora_b.as<uint16_t>(), g.n_a = slices * rank, g.ax_slices = slices;
             g.slice_rows0 = m->Hl * hd, g.slice_rows1 = (m->Hl + m->KVl) * hd;
             g.ax_ll = ax_ll + size_t(which) * kStMaxRows * 128;

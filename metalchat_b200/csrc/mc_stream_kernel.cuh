@@ -697,6 +697,50 @@ __device__ __forceinline__ void st_mma_rows(const st_params& P, const st_ctx& c,
     }
     st_hand_over(c, bl, acc, gq, gq + 8);
 }
+// The two LoRA-A rows owned by this CTA against the staged activation rows: plain fp32 dot products over the whole consumer group
+// (thread t takes the 16-byte chunks t, t + 256, ... of both rows).  An mma tile would spend 16 rows of tensor work on 2 and
+// make the owners the slowest CTAs of the phase (measured: +1.3 us at K = 2048, +2.8 us at K = 8192, on the critical path of ax).
+// Hands the per-warp partial sums over in the layout the epilogue's A-block code reads: [warp][adaptor row][batch row].
+__device__ __forceinline__ void st_dot_a_rows(const st_params& P, const st_ctx& c, st_pipe& cp, st_blk& bl, uint32_t K, uint32_t kc_tile)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t pitch = kc_tile * 2 + kStPad;
+    float a0s[kStMaxRows], a1s[kStMaxRows];
+#pragma unroll
+    for (int m = 0; m < kStMaxRows; m++) a0s[m] = 0.0f, a1s[m] = 0.0f;
+    for (uint32_t kc = 0; kc < K; kc += kc_tile) {
+        st_mbar_wait(c, c.full0 + cp.stage * 8, cp.parity);
+        const uint32_t tile = c.ring_addr + cp.stage * P.stage_bytes;
+        for (uint32_t k = threadIdx.x * 8; k < kc_tile; k += kStConsumers * 8) {
+            const uint4 w0 = lds128(tile + k * 2), w1 = lds128(tile + pitch + k * 2);
+#pragma unroll
+            for (int m = 0; m < kStMaxRows; m++) {
+                if (uint32_t(m) < P.rows) {
+                    const uint4 x = lds128(c.act_addr + uint32_t(m) * P.act_pitch + (kc + k) * 2);
+                    a0s[m] = dot8(w0, x, a0s[m]);
+                    a1s[m] = dot8(w1, x, a1s[m]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(c.empty0 + cp.stage * 8);
+        cp.advance(P.n_stages);
+    }
+#pragma unroll
+    for (int m = 0; m < kStMaxRows; m++) {
+        if (uint32_t(m) < P.rows) a0s[m] = warp_sum(a0s[m]), a1s[m] = warp_sum(a1s[m]);
+    }
+    st_mbar_wait(c, c.fre0 + bl.buf * 8, bl.parity ^ 1u); // the epilogue of the previous use of this buffer is done
+    float* rw = c.red + bl.buf * (kStWarps * 128) + warp * 128;
+    if (lane == 0) {
+#pragma unroll
+        for (int m = 0; m < kStMaxRows; m++)
+            if (uint32_t(m) < P.rows) rw[m] = a0s[m], rw[8 + m] = a1s[m];
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(c.rdy0 + bl.buf * 8);
+    bl.advance();
+}
 // one super-unit of packed weights: in-register dequant with the reference's two roundings r(r(q) * r(s))
 // (kernel/mul.metal:76-77), then mma; see gemv_q_kernel for the fragment layout
 __device__ __forceinline__ void st_dbg(unsigned long long* d, uint32_t blk, uint32_t slot, uint32_t who)
@@ -740,24 +784,32 @@ __device__ __forceinline__ void st_mma_packed(const st_params& P, const st_gemv&
     // (kept in registers through volatile asm so that the compiler does not fold them back into immediates)
     uint32_t nib_mask = 0x000f000fu, nib_magic = 0x43004300u;
     asm volatile("" : "+r"(nib_mask), "+r"(nib_magic));
+    // (tried in round 2, no effect on the step time -- 0.7635 / 0.7638 / 0.7602 ms on one box: a non-volatile mma so that ptxas may hoist the
+    // next fragment's dequant above it, and the dequant of fragment j + 1 written before the mma of fragment j: the loop's issue
+    // efficiency is not what bounds the phase)
+    auto mma_pk = [&](float (&cc)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) { mma_bf16_16816(cc, a0, a1, a2, a3, b0, b1); };
     auto compute = [&](const ops& o) {
         const uint32_t words[4] = {o.wv.x, o.wv.y, o.wv.z, o.wv.w};
         if (FMT == WF_W4) {
             // scales of (row r0, row r1) for k-groups 0 and 1 of this k-tile, as (s,s) bf16x2
             const uint32_t s_g0 = __byte_perm(o.sv.x, 0, 0x1010), s_g1 = __byte_perm(o.sv.x, 0, 0x3232);
             const uint32_t s_h0 = __byte_perm(o.sv.y, 0, 0x1010), s_h1 = __byte_perm(o.sv.y, 0, 0x3232);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
+            auto deq = [&](int j, uint32_t (&a)[4]) {
                 const uint32_t w = words[j];
                 const uint32_t sg = j < 2 ? s_g0 : s_g1, sh = j < 2 ? s_h0 : s_h1;
-                const uint32_t a0 = hmul2_bf16(hsub2_bf16(and_or(w, nib_mask, nib_magic), 0x43084308u), sg);
-                const uint32_t a1 = hmul2_bf16(hsub2_bf16(and_or(w >> 4, nib_mask, nib_magic), 0x43084308u), sh);
-                const uint32_t a2 = hmul2_bf16(hsub2_bf16(and_or(w >> 8, nib_mask, nib_magic), 0x43084308u), sg);
-                const uint32_t a3 = hmul2_bf16(hsub2_bf16(and_or(w >> 12, nib_mask, nib_magic), 0x43084308u), sh);
-                if (j == 0) mma_bf16_16816(acc, a0, a1, a2, a3, o.b0[j], o.b1[j]);
-                else if (j == 1) mma_bf16_16816(acc2, a0, a1, a2, a3, o.b0[j], o.b1[j]);
-                else if (j == 2) mma_bf16_16816(acc3, a0, a1, a2, a3, o.b0[j], o.b1[j]);
-                else mma_bf16_16816(acc4, a0, a1, a2, a3, o.b0[j], o.b1[j]);
+                a[0] = hmul2_bf16(hsub2_bf16(and_or(w, nib_mask, nib_magic), 0x43084308u), sg);
+                a[1] = hmul2_bf16(hsub2_bf16(and_or(w >> 4, nib_mask, nib_magic), 0x43084308u), sh);
+                a[2] = hmul2_bf16(hsub2_bf16(and_or(w >> 8, nib_mask, nib_magic), 0x43084308u), sg);
+                a[3] = hmul2_bf16(hsub2_bf16(and_or(w >> 12, nib_mask, nib_magic), 0x43084308u), sh);
+            };
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t a[4];
+                deq(j, a);
+                if (j == 0) mma_pk(acc, a[0], a[1], a[2], a[3], o.b0[j], o.b1[j]);
+                else if (j == 1) mma_pk(acc2, a[0], a[1], a[2], a[3], o.b0[j], o.b1[j]);
+                else if (j == 2) mma_pk(acc3, a[0], a[1], a[2], a[3], o.b0[j], o.b1[j]);
+                else mma_pk(acc4, a[0], a[1], a[2], a[3], o.b0[j], o.b1[j]);
             }
         } else {
 #pragma unroll
@@ -767,8 +819,8 @@ __device__ __forceinline__ void st_mma_packed(const st_params& P, const st_gemv&
                 const uint32_t a1 = pack_bf16x2(__fmul_rn(s8_to_f32(lo, 2), rs1), __fmul_rn(s8_to_f32(lo, 3), rs1));
                 const uint32_t a2 = pack_bf16x2(__fmul_rn(s8_to_f32(hi, 0), rs0), __fmul_rn(s8_to_f32(hi, 1), rs0));
                 const uint32_t a3 = pack_bf16x2(__fmul_rn(s8_to_f32(hi, 2), rs1), __fmul_rn(s8_to_f32(hi, 3), rs1));
-                if (j & 1) mma_bf16_16816(acc2, a0, a1, a2, a3, o.b0[j], o.b1[j]);
-                else mma_bf16_16816(acc, a0, a1, a2, a3, o.b0[j], o.b1[j]);
+                if (j & 1) mma_pk(acc2, a0, a1, a2, a3, o.b0[j], o.b1[j]);
+                else mma_pk(acc, a0, a1, a2, a3, o.b0[j], o.b1[j]);
             }
         }
     };
@@ -803,7 +855,7 @@ __device__ __forceinline__ void st_mma_packed(const st_params& P, const st_gemv&
 template <bool Q> __device__ __forceinline__ void st_mma_gemv(const st_params& P, const st_gemv& g, const st_ctx& c, st_pipe& cp, st_blk& bl, uint32_t li)
 {
     const st_range r(g, Q);
-    if (Q && r.has_a) st_mma_rows(P, c, cp, bl, g.K, P.kc_a[&g - P.g], 2);
+    if (Q && r.has_a) st_dot_a_rows(P, c, cp, bl, g.K, P.kc_a[&g - P.g]);
     if (!Q || g.fmt == WF_BF16) {
         for (uint32_t r0 = r.b0; r0 < r.b1; r0 += kStTileRows) st_mma_rows(P, c, cp, bl, g.K, g.KC, min(uint32_t(kStTileRows), r.b1 - r0));
     } else if (g.fmt == WF_W4) {
