@@ -108,6 +108,9 @@ struct mc_llama {
     size_t tp_off_flags = 0, tp_off_amval = 0, tp_off_amidx = 0, tp_off_amflags = 0;
     size_t tp_off_stpart = 0, tp_off_stam = 0, tp_stpart_gen = 0, tp_stam_gen = 0; // streaming kernel: tagged partial sums / argmax pairs, two generations each
     size_t tp_off_stax = 0, tp_stax_gen = 0;                                        // ... and the adaptors' partial A . x (quantised models)
+    // tensor-core path under tensor parallelism (bf16 models): fp32 partial sums / bf16 results of a row-parallel GEMM, two halves each
+    size_t tp_off_tc_partial = 0, tp_off_tc_result = 0, tp_off_tc_flags = 0, tp_tc_half_partial = 0, tp_tc_half_result = 0;
+    uint32_t tp_tc_rows = 0; // rows one exchange holds (0: the path is off)
     // streaming persistent kernel (mc_stream_kernel.cuh): un-rotated q|k|v rows, split-attention exchange, step flag
     dbuf st_ll, st_timing;     // one arena of tagged words: x | h | z | qkv | attn | scores | argmax partials | ids
     size_t st_off[9] = {};
@@ -901,6 +904,35 @@ void enqueue_sample(mc_llama* m, launcher& L, uint32_t rows, const mc_sampler_co
          kArgmaxBlocks, m->ids.as<int32_t>(), m->pos.as<int32_t>(), m->out_log.as<int32_t>(), m->step_counter.as<int32_t>(), rows, advance);
 }
 
+// Tensor parallel on the tensor-core path (bf16 models): a row-parallel linear (wo, w2) stores its unrounded fp32 sums into this rank's
+// half `half` (0: wo, 1: w2) of the exchange region, tc::tp_allreduce_rows sums the ranks, rounds, adds the residual and leaves the
+// bf16 rows in every rank's result half.  Returns where the rows are.
+bool tp_tc_ready(const mc_llama* m) { return m->cfg.tp_world > 1 && m->tp_tc_rows != 0 && m->tp_connected && !m->nccl_comm; }
+uint16_t* tp_tc_result(const mc_llama* m, uint32_t half)
+{
+    return reinterpret_cast<uint16_t*>(m->tp_region.as<char>() + m->tp_off_tc_result + half * m->tp_tc_half_result);
+}
+uint32_t tp_tc_row_parallel(mc_llama* m, cudaStream_t s, const uint16_t* X, uint32_t K, const dlinear& d, uint32_t half, const uint16_t* res, uint32_t rows)
+{
+    const mc_llama_config& c = m->cfg;
+    const int sms = m->dev->prop.multiProcessorCount;
+    MC_REQUIRE(rows <= m->tp_tc_rows, "tensor parallel: too many rows for the exchange region");
+    float* mine = reinterpret_cast<float*>(m->tp_region.as<char>() + m->tp_off_tc_partial + half * m->tp_tc_half_partial);
+    uint32_t n = uint32_t(tc::gemm(s, sms, tc::GEMM_PARTIAL_F32, X, K, d.w.as<uint16_t>(), reinterpret_cast<uint16_t*>(mine), nullptr, rows, c.dim, K, c.dim, m->errflag.as<int>()));
+    tc::tp_rows_exchange x{};
+    x.world = c.tp_world, x.rank = c.tp_rank;
+    for (uint32_t k = 0; k < c.tp_world; k++) {
+        char* base = static_cast<char*>(m->tp_peer_base[k]);
+        x.partial[k] = reinterpret_cast<const float*>(base + m->tp_off_tc_partial + half * m->tp_tc_half_partial);
+        x.result[k] = reinterpret_cast<uint16_t*>(base + m->tp_off_tc_result + half * m->tp_tc_half_result);
+        x.ready[k] = reinterpret_cast<uint32_t*>(base + m->tp_off_tc_flags);
+        x.done[k] = reinterpret_cast<uint32_t*>(base + m->tp_off_tc_flags + 64);
+    }
+    x.counter = m->tp_local.as<unsigned>() + 8, x.epoch = m->tp_local.as<unsigned>() + 9, x.err = m->errflag.as<int>();
+    n += uint32_t(tc::tp_allreduce_rows(s, sms, x, res, rows, c.dim));
+    return n;
+}
+
 // One linear of a block on the tensor-core path.  bf16 models: a single GEMM with the fused tail.  QLoRA models: the GEMM runs on the
 // resident bf16 image and stores r(x . Wd^T); the adaptor term and the tail follow (quantization/lora.h:115-122):
 //   y = r(r(x . Wd^T) + r(r(B . r(A . x)) * r(scale))), then residual add / SiLU*mul / plain store.
@@ -937,7 +969,7 @@ uint32_t decode_tc_min_rows()
 bool decode_tc_eligible(const mc_llama* m, uint32_t n)
 {
     const mc_llama_config& c = m->cfg;
-    if ((c.flags & MC_LLAMA_NO_TC_PREFILL) || c.tp_world != 1 || n < decode_tc_min_rows() || !m->dt_n.p) return false;
+    if ((c.flags & MC_LLAMA_NO_TC_PREFILL) || (c.tp_world != 1 && !tp_tc_ready(m)) || n < decode_tc_min_rows() || !m->dt_n.p) return false;
     if (c.quant && (!m->layers[0].wqkv.wd.p || !m->out.wd.p || c.lora_rank % 2 != 0 || c.lora_rank > 16)) return false;
     const uint32_t D = c.dim, QO = m->Hl * c.head_dim, QKV = (m->Hl + 2 * m->KVl) * c.head_dim, F = m->Fl;
     return tc::gemm_supported(QKV, D, D, QKV) && tc::gemm_supported(D, QO, QO, D) && tc::gemm_supported(2 * F, D, D, F) && tc::gemm_supported(D, F, F, D) &&
@@ -953,6 +985,7 @@ void enqueue_rows_tc(mc_llama* m, launcher& L, uint32_t rows)
     uint16_t *q = m->q.as<uint16_t>(), *attn = m->attn.as<uint16_t>(), *z = m->z.as<uint16_t>();
     const tc_scratch sc{m->dt_t.as<uint16_t>()};
     const uint32_t rank = c.lora_rank;
+    const bool tp = c.tp_world > 1;
     int* err = m->errflag.as<int>();
     tc::set_pdl(L.pdl);
     auto count = [&](int k) { L.count += uint32_t(k), m->dev->launches.fetch_add(uint64_t(k)); };
@@ -975,14 +1008,26 @@ void enqueue_rows_tc(mc_llama* m, launcher& L, uint32_t rows)
             if (hd == 64) L.go_cluster(attn_decode_kernel<64>, dim3(H * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
             else L.go_cluster(attn_decode_kernel<128>, dim3(H * kAttnCluster, rows), dim3(256), smem, kAttnCluster, a);
         }
-        count(tc_linear(m, s, tc::GEMM_RESIDUAL, attn, QO, ly.wo, rank, 1, h, x, rows, D, QO, D, sc));
+        if (tp) {
+            // row-parallel wo / w2: fp32 partial sums + all-reduce over NVLink (the residual stream then lives in the exchange region's result halves)
+            count(tp_tc_row_parallel(m, s, attn, QO, ly.wo, 0, x, rows));
+            h = tp_tc_result(m, 0);
+        } else count(tc_linear(m, s, tc::GEMM_RESIDUAL, attn, QO, ly.wo, rank, 1, h, x, rows, D, QO, D, sc));
         count(tc::rmsnorm_rows(s, n, h, ly.ffn_norm.as<uint16_t>(), rows, D, c.norm_eps));
         count(tc_linear(m, s, tc::GEMM_SWIGLU, n, D, ly.w13, 2 * rank, 2, z, nullptr, rows, 2 * F, D, F, sc));
-        count(tc_linear(m, s, tc::GEMM_RESIDUAL, z, F, ly.w2, rank, 1, x, h, rows, D, F, D, sc));
+        if (tp) {
+            count(tp_tc_row_parallel(m, s, z, F, ly.w2, 1, h, rows));
+            x = tp_tc_result(m, 1);
+        } else count(tc_linear(m, s, tc::GEMM_RESIDUAL, z, F, ly.w2, rank, 1, x, h, rows, D, F, D, sc));
+    }
+    if (tp) {
+        // the last hidden rows go back to where the rest of the engine expects them
+        MC_CUDA_CHECK(cudaMemcpyAsync(m->x.p, x, size_t(rows) * D * 2, cudaMemcpyDeviceToDevice, s));
+        x = m->x.as<uint16_t>();
     }
     count(tc::rmsnorm_rows(s, n, x, m->norm.as<uint16_t>(), rows, D, c.norm_eps));
-    // vocabulary projection: the (tied) bf16 table, or the cached bf16 image of the int8 output matrix (quantization/linear.h:50-53)
-    const uint16_t* head_w = c.quant ? m->out.wd.as<uint16_t>() : (m->tied ? m->tok : m->out).w.as<uint16_t>();
+    // vocabulary projection: the (tied) bf16 table (this rank's vocabulary slice), or the cached bf16 image of the int8 output matrix (quantization/linear.h:50-53)
+    const uint16_t* head_w = c.quant ? m->out.wd.as<uint16_t>() : (m->tied ? m->tok.w.as<uint16_t>() + size_t(c.tp_rank) * m->Vl * D : m->out.w.as<uint16_t>());
     count(tc::gemm(s, sms, tc::GEMM_STORE, n, D, head_w, m->logits.as<uint16_t>(), nullptr, rows, m->Vl, D, m->Vl, err));
 }
 
@@ -1345,7 +1390,18 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
         m->tp_stam_gen = (T * kStMaxRows * 2 * 8 + 255) & ~size_t(255);
         m->tp_off_stax = m->tp_off_stam + 2 * m->tp_stam_gen;
         m->tp_stax_gen = size_t(2) * T * kStMaxRows * kStTpAxCols * 8;
-        m->tp_region.alloc(m->tp_off_stax + 2 * m->tp_stax_gen);
+        size_t region_bytes = m->tp_off_stax + 2 * m->tp_stax_gen;
+        if (!c.quant && !(c.flags & MC_LLAMA_NO_TC_PREFILL)) {
+            // prompts and decode batches on the tcgen05 path: a chunk of rows is all-reduced at once (tc::tp_allreduce_rows)
+            m->tp_tc_rows = std::max<uint32_t>(std::min<uint32_t>(2048u, c.max_seq_len), std::max<uint32_t>(c.n_seqs, kMaxMB));
+            m->tp_tc_half_partial = (size_t(m->tp_tc_rows) * D * 4 + 255) & ~size_t(255);
+            m->tp_tc_half_result = (size_t(m->tp_tc_rows) * D * 2 + 255) & ~size_t(255);
+            m->tp_off_tc_partial = (region_bytes + 255) & ~size_t(255);
+            m->tp_off_tc_result = m->tp_off_tc_partial + 2 * m->tp_tc_half_partial;
+            m->tp_off_tc_flags = m->tp_off_tc_result + 2 * m->tp_tc_half_result;
+            region_bytes = m->tp_off_tc_flags + 256;
+        }
+        m->tp_region.alloc(region_bytes);
         MC_CUDA_CHECK(cudaMemset(m->tp_region.p, 0, m->tp_region.bytes));
         m->tp_local.alloc(256);
         MC_CUDA_CHECK(cudaMemset(m->tp_local.p, 0, 256));
@@ -1363,7 +1419,7 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
     m->x.alloc(size_t(R) * D * 2), m->h.alloc(size_t(R) * D * 2);
     m->q.alloc(size_t(R) * m->Hl * hd * 2), m->attn.alloc(size_t(R) * m->Hl * hd * 2);
     m->z.alloc(size_t(R) * m->Fl * 2);
-    if (c.tp_world == 1 && c.n_seqs >= decode_tc_min_rows()) {
+    if ((c.tp_world == 1 || m->tp_tc_rows) && c.n_seqs >= decode_tc_min_rows()) {
         m->dt_n.alloc(size_t(R) * D * 2);
         m->dt_qkv.alloc(size_t(R) * (m->Hl + 2 * m->KVl) * hd * 2);
         if (c.quant) m->dt_t.alloc(size_t(R) * (std::max(std::max((m->Hl + 2 * m->KVl) * hd, 2 * m->Fl), D) + 128) * 2);
@@ -1602,7 +1658,7 @@ bool prefill_tc_eligible(const mc_llama* m, uint32_t len)
 {
     const mc_llama_config& c = m->cfg;
     static const bool env_off = getenv("MC_NO_TC_PREFILL") != nullptr;
-    if (env_off || (c.flags & MC_LLAMA_NO_TC_PREFILL) || c.tp_world != 1 || len < prefill_tc_min_rows()) return false;
+    if (env_off || (c.flags & MC_LLAMA_NO_TC_PREFILL) || (c.tp_world != 1 && !tp_tc_ready(m)) || len < prefill_tc_min_rows()) return false;
     if (c.quant && (!m->layers[0].wqkv.wd.p || c.lora_rank % 2 != 0 || c.lora_rank > 16)) return false; // quantised: needs the bf16 image (mc_llama_finalize)
     if (c.head_dim != 64 && c.head_dim != 128) return false;
     const uint32_t D = c.dim, QO = m->Hl * c.head_dim, QKV = (m->Hl + 2 * m->KVl) * c.head_dim, F = m->Fl;
@@ -1627,6 +1683,8 @@ void prefill_tc(mc_llama* m, uint32_t seq, const int32_t* ids, uint32_t len, uin
     uint16_t *x = m->pf_x.as<uint16_t>(), *h = m->pf_h.as<uint16_t>(), *n = m->pf_n.as<uint16_t>(), *qkv = m->pf_qkv.as<uint16_t>();
     uint16_t *q = m->pf_q.as<uint16_t>(), *attn = m->pf_attn.as<uint16_t>(), *z = m->pf_z.as<uint16_t>();
     const tc_scratch sc{m->pf_t.as<uint16_t>()};
+    const bool tp = c.tp_world > 1;
+    uint16_t* const x0 = x;
     int* err = m->errflag.as<int>();
     uint32_t launches = 0;
     launcher L{m, s, false};
@@ -1635,6 +1693,7 @@ void prefill_tc(mc_llama* m, uint32_t seq, const int32_t* ids, uint32_t len, uin
         const uint32_t rows = std::min(cap, len - t0), pos0 = start_pos + t0;
         MC_CUDA_CHECK(cudaMemcpyAsync(m->pf_ids.p, ids + t0, size_t(rows) * 4, cudaMemcpyHostToDevice, s));
         // embedding gather (bf16 rows, or int8 rows with one scale: quantization/lora.h:160-170)
+        x = x0;
         L.go(embed_kernel, dim3(rows), dim3(256), 0, x, D, (const void*)m->tok.w.p, (const float*)m->tok.scales.p, m->tok.fmt, D, c.vocab,
              (const int32_t*)m->pf_ids.as<int32_t>());
         for (uint32_t li = 0; li < c.n_layers; li++) {
@@ -1645,10 +1704,17 @@ void prefill_tc(mc_llama* m, uint32_t seq, const int32_t* ids, uint32_t len, uin
             launches += tc_linear(m, s, tc::GEMM_STORE, n, D, ly.wqkv, 3 * rank, 3, qkv, nullptr, rows, QKV, D, QKV, sc);
             launches += tc::rope_append(s, qkv, q, kc, vc, m->fcos.as<float>(), m->fsin.as<float>(), rows, seq, pos0, H, KV, hd, c.max_seq_len);
             launches += tc::prefill_attn(s, q, kc, vc, attn, rows, seq, pos0, H, KV, hd, c.max_seq_len, m->scale_bf16, m->key_begin);
-            launches += tc_linear(m, s, tc::GEMM_RESIDUAL, attn, QO, ly.wo, rank, 1, h, x, rows, D, QO, D, sc);
+            if (tp) {
+                // row-parallel wo / w2: fp32 partial sums + all-reduce over NVLink (see tp_tc_row_parallel)
+                launches += tp_tc_row_parallel(m, s, attn, QO, ly.wo, 0, x, rows);
+                h = tp_tc_result(m, 0);
+            } else launches += tc_linear(m, s, tc::GEMM_RESIDUAL, attn, QO, ly.wo, rank, 1, h, x, rows, D, QO, D, sc);
             launches += tc::rmsnorm_rows(s, n, h, ly.ffn_norm.as<uint16_t>(), rows, D, c.norm_eps);
             launches += tc_linear(m, s, tc::GEMM_SWIGLU, n, D, ly.w13, 2 * rank, 2, z, nullptr, rows, 2 * F, D, F, sc);
-            launches += tc_linear(m, s, tc::GEMM_RESIDUAL, z, F, ly.w2, rank, 1, x, h, rows, D, F, D, sc);
+            if (tp) {
+                launches += tp_tc_row_parallel(m, s, z, F, ly.w2, 1, h, rows);
+                x = tp_tc_result(m, 1);
+            } else launches += tc_linear(m, s, tc::GEMM_RESIDUAL, z, F, ly.w2, rank, 1, x, h, rows, D, F, D, sc);
         }
         if (t0 + rows >= len) {
             // only the last position is projected (nn/llama.h:128-133)

@@ -18,12 +18,13 @@
 #pragma once
 #include <cuda.h>
 #include "mc_common.cuh"
+#include "mc_prefill.h"
 
 namespace mc {
 namespace tc {
 
 // epilogues of the prefill GEMM (same meaning as the EPI_* of the decode GEMV kernels)
-enum { EPI_NONE = 0, EPI_RESIDUAL = 2, EPI_SWIGLU = 3 };
+enum { EPI_NONE = 0, EPI_RESIDUAL = 2, EPI_SWIGLU = 3, EPI_PARTIAL = 4 }; // EPI_PARTIAL: unrounded fp32 sums (tensor parallel, row-parallel linear)
 
 // ---- helpers (this translation unit is independent of the decode kernels) -------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -260,7 +261,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                     : "r"(taddr)
                     : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < p.M && n0 + cb < p.N) {
+                if (EPI == EPI_PARTIAL) {
+                    // this rank's k range of a row-parallel linear: the fp32 sums go out unrounded (Y is a float matrix, ldy in floats);
+                    // tp_allreduce_rows_kernel sums the ranks in rank order and applies the one rounding of kernel/bmm.metal:76
+                    if (row < p.M && n0 + cb < p.N) {
+                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.Y) + size_t(row) * p.ldy + n0 + cb);
+#pragma unroll
+                        for (int q = 0; q < 8; q++) dst[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                } else if (row < p.M && n0 + cb < p.N) {
                     float y[32];
 #pragma unroll
                     for (int j = 0; j < 32; j++) y[j] = rbf(__uint_as_float(v[j])); // the bmm output buffer is T (kernel/bmm.metal:76)
@@ -1024,6 +1033,92 @@ template <int EPI> __global__ void __launch_bounds__(256) lora_epilogue_kernel(c
             *reinterpret_cast<uint32_t*>(p.out + size_t(row) * p.ldo + n) = pack2(v[0], v[1]);
         }
     }
+}
+
+
+// ---- tensor parallel: all-reduce of row-parallel partial sums on the tensor-core path (launcher: tc::tp_allreduce_rows) ------------------
+__device__ __forceinline__ bool tp_rows_wait(const uint32_t* flag, uint32_t e, int* err)
+{
+    uint32_t v = 0;
+    for (unsigned long long spins = 0;; spins++) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= e) return true;
+        if (spins > (1ull << 24)) {
+            atomicExch(err, 3);
+            return false;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) tp_allreduce_rows_kernel(const tp_rows_exchange x, const uint16_t* __restrict__ res, uint32_t rows, uint32_t D)
+{
+    __shared__ uint32_t s_e;
+    pdl_trigger();
+    pdl_sync(); // this rank's partial sums (the GEMM launched before) are complete
+    const uint32_t W = x.world, me = x.rank;
+    if (threadIdx.x == 0) {
+        const uint32_t e = *reinterpret_cast<volatile unsigned*>(x.epoch) + 1; // (the epoch moves on only after every CTA of this launch has arrived below)
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            for (uint32_t k = 0; k < W; k++) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(x.ready[k] + me), "r"(e) : "memory");
+        }
+        bool ok = true;
+        for (uint32_t k = 0; k < W && ok; k++) ok = tp_rows_wait(x.ready[me] + k, e, x.err);
+        s_e = ok ? e : 0u;
+    }
+    __syncthreads();
+    const uint32_t e = s_e;
+    if (e != 0u) {
+        // slice `me` of the element range, 8 elements (two float4 per rank in, one uint4 out) per step
+        const uint64_t n8 = uint64_t(rows) * D / 8, per = (n8 + W - 1) / W;
+        const uint64_t b = min(n8, uint64_t(me) * per), en = min(n8, b + per);
+        for (uint64_t i = b + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < en; i += uint64_t(gridDim.x) * blockDim.x) {
+            float4 lo[kTpRowsMaxWorld], hi[kTpRowsMaxWorld];
+#pragma unroll
+            for (uint32_t k = 0; k < uint32_t(kTpRowsMaxWorld); k++) {
+                if (k < W) {
+                    const float* src = x.partial[k] + i * 8;
+                    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(lo[k].x), "=f"(lo[k].y), "=f"(lo[k].z), "=f"(lo[k].w) : "l"(src) : "memory");
+                    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(hi[k].x), "=f"(hi[k].y), "=f"(hi[k].z), "=f"(hi[k].w) : "l"(src + 4) : "memory");
+                }
+            }
+            float s[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (uint32_t k = 0; k < uint32_t(kTpRowsMaxWorld); k++) {
+                if (k < W) s[0] += lo[k].x, s[1] += lo[k].y, s[2] += lo[k].z, s[3] += lo[k].w, s[4] += hi[k].x, s[5] += hi[k].y, s[6] += hi[k].z, s[7] += hi[k].w;
+            }
+            // h = r(x + r(sum))  (kernel/bmm.metal:76, nn/transformer.h:133,139)
+            const uint4 r = *reinterpret_cast<const uint4*>(res + i * 8);
+            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+            uint4 o;
+            o.x = pack2(__fadd_rn(bf_lo(rw[0]), rbf(s[0])), __fadd_rn(bf_hi(rw[0]), rbf(s[1])));
+            o.y = pack2(__fadd_rn(bf_lo(rw[1]), rbf(s[2])), __fadd_rn(bf_hi(rw[1]), rbf(s[3])));
+            o.z = pack2(__fadd_rn(bf_lo(rw[2]), rbf(s[4])), __fadd_rn(bf_hi(rw[2]), rbf(s[5])));
+            o.w = pack2(__fadd_rn(bf_lo(rw[3]), rbf(s[6])), __fadd_rn(bf_hi(rw[3]), rbf(s[7])));
+#pragma unroll
+            for (uint32_t k = 0; k < uint32_t(kTpRowsMaxWorld); k++) {
+                if (k < W) asm volatile("st.relaxed.sys.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(x.result[k] + i * 8), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+            }
+        }
+    }
+    __syncthreads(); // the stores of every thread happen before thread 0's system-scope fence (cumulativity)
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned prev = atomicAdd(x.counter, 1u);
+        if (prev == gridDim.x - 1) {
+            // last CTA of this rank: the slice is in every rank's result buffer
+            *x.counter = 0;
+            if (e != 0u) {
+                *x.epoch = e;
+                __threadfence_system();
+                for (uint32_t k = 0; k < W; k++) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(x.done[k] + me), "r"(e) : "memory");
+            }
+        }
+        // nobody leaves before every rank's slice has arrived here: the kernels launched next read the whole result
+        if (e != 0u)
+            for (uint32_t k = 0; k < W; k++)
+                if (!tp_rows_wait(x.done[me] + k, e, x.err)) break;
+    }
+    __syncthreads();
 }
 
 } // namespace tc

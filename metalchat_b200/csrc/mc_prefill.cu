@@ -102,6 +102,7 @@ template <int BN, int AROWS> void launch_gemm_epi(cudaStream_t s, int sm_count, 
     case GEMM_STORE: launch_gemm<BN, EPI_NONE, AROWS>(s, sm_count, mx, mw, p); break;
     case GEMM_RESIDUAL: launch_gemm<BN, EPI_RESIDUAL, AROWS>(s, sm_count, mx, mw, p); break;
     case GEMM_SWIGLU: launch_gemm<BN, EPI_SWIGLU, AROWS>(s, sm_count, mx, mw, p); break;
+    case GEMM_PARTIAL_F32: launch_gemm<BN, EPI_PARTIAL, AROWS>(s, sm_count, mx, mw, p); break;
     default: throw error(MC_ERR_INVALID, "prefill gemm: unknown epilogue");
     }
 }
@@ -175,7 +176,7 @@ int gemm(cudaStream_t stream, int sm_count, int mode, const uint16_t* X, uint32_
     gemm_tc_params p{};
     p.Y = Y, p.res = res, p.M = M, p.N = N, p.K = K, p.ldy = ldy, p.err = err;
     // a decode batch of <= 32 rows stages only 32 rows of X per k block (see tc_stages); small matrices are split over k
-    const uint32_t ks = M <= 32 ? splitk_factor(N, K, sm_count) : 0;
+    const uint32_t ks = M <= 32 && mode != GEMM_PARTIAL_F32 ? splitk_factor(N, K, sm_count) : 0; // (the partial-sum mode lives in the persistent kernel only)
     if (ks) {
         const CUtensorMap mx = make_map(X, M, K, ldx, kSkRows), mw = make_map(W, N, K, K, kSkBN);
         switch (mode) {
@@ -186,6 +187,16 @@ int gemm(cudaStream_t stream, int sm_count, int mode, const uint16_t* X, uint32_
         }
     } else if (M <= 32) launch_gemm_bn<32>(stream, sm_count, mode, X, ldx, W, p);
     else launch_gemm_bn<128>(stream, sm_count, mode, X, ldx, W, p);
+    return 1;
+}
+
+int tp_allreduce_rows(cudaStream_t stream, int sm_count, const tp_rows_exchange& x, const uint16_t* res, uint32_t rows, uint32_t D)
+{
+    MC_REQUIRE(x.world >= 2 && x.world <= uint32_t(kTpRowsMaxWorld) && x.rank < x.world, "tp all-reduce: bad world / rank");
+    MC_REQUIRE(D % 8 == 0 && rows >= 1, "tp all-reduce: dim must be a multiple of 8");
+    const uint64_t n8 = uint64_t(rows) * D / 8, mine = (n8 + x.world - 1) / x.world;
+    const uint32_t grid = uint32_t(std::min<uint64_t>(uint64_t(sm_count), std::max<uint64_t>(1, (mine + 255) / 256))); // co-resident: the CTAs wait for each other's peers
+    launch_k(tp_allreduce_rows_kernel, dim3(grid), dim3(256), 0, stream, 1, x, res, rows, D);
     return 1;
 }
 

@@ -7,7 +7,7 @@
 namespace mc {
 namespace tc {
 
-enum { GEMM_STORE = 0, GEMM_RESIDUAL = 2, GEMM_SWIGLU = 3 };
+enum { GEMM_STORE = 0, GEMM_RESIDUAL = 2, GEMM_SWIGLU = 3, GEMM_PARTIAL_F32 = 4 }; // GEMM_PARTIAL_F32: Y is a float matrix of unrounded sums, ldy in floats
 
 // Kernels launched by the calling thread from now on carry the programmatic-stream-serialization attribute: every kernel of this
 // file starts with griddepcontrol.launch_dependents and waits (griddepcontrol.wait) before it touches the previous kernel's results,
@@ -21,6 +21,24 @@ bool gemm_supported(uint32_t N, uint32_t K, uint32_t ldx, uint32_t ldy);
 // mode GEMM_SWIGLU writes N/2 columns.  Returns the number of kernels launched (1).
 int gemm(cudaStream_t stream, int sm_count, int mode, const uint16_t* X, uint32_t ldx, const uint16_t* W, uint16_t* Y, const uint16_t* res, uint32_t M, uint32_t N,
          uint32_t K, uint32_t ldy, int* err);
+
+// Tensor parallel, tensor-core path: all-reduce of the fp32 partial sums [rows, D] of a row-parallel linear (GEMM_PARTIAL_F32) over the
+// ranks of one box, fused with the rounding and the residual add:  out = r(res + r(sum over ranks, in rank order)).
+// Reduce-scatter by peer reads + all-gather by peer writes over NVLink: rank r sums slice r of every rank's partial buffer and
+// stores the finished bf16 slice into every rank's result buffer.  Epoch flags (release / acquire at system scope) order the phases;
+// every wait is bounded and raises *err.  The buffers of an exchange alternate between two halves (parity): see mc_engine.cu.
+constexpr int kTpRowsMaxWorld = 8;
+struct tp_rows_exchange {
+    uint32_t world, rank;
+    const float* partial[kTpRowsMaxWorld]; // partial buffer (this parity) of every rank as mapped on this GPU: [rows][D] fp32
+    uint16_t* result[kTpRowsMaxWorld];     // result buffer (this parity) of every rank: [rows][D] bf16
+    uint32_t* ready[kTpRowsMaxWorld];      // flag array [world] of every rank: ready[k][src] = epochs for which src's partial sums are complete
+    uint32_t* done[kTpRowsMaxWorld];       // flag array [world] of every rank: done[k][src] = epochs for which src's slice has arrived in k's result
+    unsigned* counter;                     // local: CTAs of this launch that have stored their part
+    unsigned* epoch;                       // local: exchanges completed so far
+    int* err;
+};
+int tp_allreduce_rows(cudaStream_t stream, int sm_count, const tp_rows_exchange& x, const uint16_t* res, uint32_t rows, uint32_t D);
 
 int embed_rows(cudaStream_t stream, uint16_t* out, const uint16_t* table, const int32_t* ids, uint32_t rows, uint32_t D);
 int rmsnorm_rows(cudaStream_t stream, uint16_t* out, const uint16_t* x, const uint16_t* w, uint32_t rows, uint32_t D, float eps);

@@ -5,6 +5,7 @@ split head) plus a full single-GPU copy.  Modes:
   small / hd128   small configs (head_dim 64 / 128): TP logits vs single-GPU logits, greedy tokens through the per-token call and through
                   the device-side loop equal to the single-GPU engine's and to the oracle's (near-ties excepted)
   batch8          8 sequences per step under TP (the argmax exchange carries every row: ADVICE r01)
+  batch12         12 sequences per step: prompts and steps on the tcgen05 path under TP (fp32 partial GEMMs + tc::tp_allreduce_rows)
   quant           QLoRA layout under TP (BASELINE.json configs[4]): per-op kernels, all-reduce of [main sums | adaptor A . x] rows
   full            the Llama-3.2-1B-shaped untied-head fixture (tests/golden/llama1b_L16_bf16-untied_p512_s64.json): 512-token prompt, then
                   64 teacher-forced steps judged like tests/test_gpu_golden.py (argmax per step, logits rows at the checkpoints)
@@ -27,6 +28,8 @@ CONFIGS = {
     # (sized so that every rank of an 8-GPU world still holds whole 256-column k-slices of wo and w2)
     "hd128": dict(dim=2048, n_layers=2, n_heads=16, n_kv_heads=8, head_dim=128, ffn_dim=4096, vocab=4000, max_seq_len=96),
     "batch8": dict(dim=2048, n_layers=2, n_heads=32, n_kv_heads=8, head_dim=64, ffn_dim=2048, vocab=2000, max_seq_len=64),
+    # 12 sequences per step: the tcgen05 GEMM path under TP (row-parallel GEMMs store fp32 partial sums, tc::tp_allreduce_rows finishes them)
+    "batch12": dict(dim=2048, n_layers=2, n_heads=32, n_kv_heads=8, head_dim=64, ffn_dim=2048, vocab=2048, max_seq_len=96),
     # QLoRA layout (int4 weights + group scales + adaptors, int8 head) sharded the same way; row-parallel linears exchange [main | A . x]
     "quant": dict(dim=2048, n_layers=2, n_heads=32, n_kv_heads=8, head_dim=64, ffn_dim=2048, vocab=2048, max_seq_len=64, quant=1),
     "full": dict(dim=2048, n_layers=16, n_heads=32, n_kv_heads=8, head_dim=64, ffn_dim=8192, vocab=128256, max_seq_len=1024),
@@ -67,8 +70,8 @@ def main():
     report = {"world": world, "mode": mode, "path": "per-op + ncclAllReduce" if collective == "nccl" else "per-op" if os.environ.get("MC_TP_NO_STREAM") else "streaming"}
     ok = True
 
-    if mode in ("small", "hd128", "batch8", "quant"):
-        n_seqs = 8 if mode == "batch8" else 1
+    if mode in ("small", "hd128", "batch8", "batch12", "quant"):
+        n_seqs = 8 if mode == "batch8" else 12 if mode == "batch12" else 1
         m = tp.create(dev, collective=collective, **cfgd, n_seqs=n_seqs)
         m.init_random(0x5EED)
         m.finalize()
