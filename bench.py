@@ -304,11 +304,17 @@ def run_prefill(args, shape_name, shape, quant=0):
     from metalchat_b200 import capi
 
     dev = capi.Device(local)
-    m = capi.Llama(dev, capi.llama_config(**shape, max_seq_len=S, quant=quant, n_seqs=1,
-                                          flags=(capi.LLAMA_NO_TC_PREFILL if args.per_op else 0) | (capi.LLAMA_W4_PACKED if quant else 0)))
+    tp_on = world > 1 and not args.replicas  # ONE model sharded over the GPUs (every rank feeds the same prompt) instead of one replica per GPU
+    pf_flags = (capi.LLAMA_NO_TC_PREFILL if args.per_op else 0) | (capi.LLAMA_W4_PACKED if quant else 0)
+    if tp_on:
+        from metalchat_b200 import tp
+
+        m = tp.create(dev, **shape, max_seq_len=S, quant=quant, n_seqs=1, flags=pf_flags)
+    else:
+        m = capi.Llama(dev, capi.llama_config(**shape, max_seq_len=S, quant=quant, n_seqs=1, flags=pf_flags))
     m.init_random(0x5EED)
     m.finalize()
-    rng = np.random.default_rng(0x5EED + rank)
+    rng = np.random.default_rng(0x5EED + (0 if tp_on else rank))
     prompts = [rng.integers(0, shape["vocab"], size=S, dtype=np.int32) for _ in range(4)]
     steps = min(args.steps, 32)
 
@@ -348,12 +354,14 @@ def run_prefill(args, shape_name, shape, quant=0):
         dist.destroy_process_group()
         return
     lin, att, head = prefill_flops(shape, S)
+    if tp_on:
+        lin, att, head = lin / world, att / world, head / world  # the roofline is per GPU shard
     peak, peak_src = tensor_peak()
     tf = (lin + att + head) / (ms / steps * 1e-3) / 1e12
     roof = {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None, "peak_source": peak_src,
             "kernel": "whole prompt step (gemm_tc_kernel = tcgen05 GEMMs carry %.1f%% of the flops; causal attention on mma.sync)" % (100 * lin / (lin + att + head)),
             "algorithmic_flops_per_step": lin + att + head}
-    if not args.per_op and not quant:
+    if not args.per_op and not quant and not tp_on:
         # the dominant kernel alone: the four GEMM shapes of a block, CUDA events on the engine stream (mc_gemm_bf16)
         D, F = shape["dim"], shape["ffn_dim"]
         QKV = (shape["n_heads"] + 2 * shape["n_kv_heads"]) * shape["head_dim"]
@@ -377,12 +385,14 @@ def run_prefill(args, shape_name, shape, quant=0):
                     b.release()
         roof["gemm_tc_kernel"] = {"achieved": tot_f / tot_t / 1e12, "frac": tot_f / tot_t / 1e12 / peak, "per_shape": per,
                                   "note": "the four GEMMs of one block timed alone (20 back-to-back launches each, operands L2-resident between launches)"}
-    tokens = steps * S * world
+    tokens = steps * S * (1 if tp_on else world)
     line = {
         "metric": "prefill_tokens_per_s", "value": tokens / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
-        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if not quant else "bf16 activations, int4 weights (bf16 dequant), fp32 accumulate",
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong" if tp_on else "weak", "vs_baseline": None, "dtype": "bf16" if not quant else "bf16 activations, int4 weights (bf16 dequant), fp32 accumulate",
         "data": "synthetic ids, random-init weights (counter-hash seed 0x5EED)",
-        "config": {"workload": workload, "prompt": S, "parallelism": f"{world} replica(s)",
+        "config": {"workload": workload, "prompt": S,
+                   "parallelism": (f"tp{world}: ONE model, column/row-split GEMMs, fp32 partial sums all-reduced by tc::tp_allreduce_rows over NVLink peer memory; roofline per GPU shard"
+                                   if tp_on else f"{world} replica(s)"),
                    "path": "4-row GEMV prompt path" if args.per_op else "tcgen05 GEMM prompt path",
                    "l2": "weights of one pass (%.0f MB) > 126 MB L2; four distinct prompts cycled" % (m.weight_bytes()[0] / 1e6)},
         "e2e": {"value": tokens / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 4 * S, "d2h_bytes_per_step": 2 * shape["vocab"],
