@@ -912,13 +912,14 @@ uint16_t* tp_tc_result(const mc_llama* m, uint32_t half)
 {
     return reinterpret_cast<uint16_t*>(m->tp_region.as<char>() + m->tp_off_tc_result + half * m->tp_tc_half_result);
 }
-uint32_t tp_tc_row_parallel(mc_llama* m, cudaStream_t s, const uint16_t* X, uint32_t K, const dlinear& d, uint32_t half, const uint16_t* res, uint32_t rows)
+uint32_t tp_tc_row_parallel(mc_llama* m, cudaStream_t s, const uint16_t* X, uint32_t K, const uint16_t* W, uint32_t width, uint32_t half, const uint16_t* res,
+                            uint32_t rows)
 {
     const mc_llama_config& c = m->cfg;
     const int sms = m->dev->prop.multiProcessorCount;
     MC_REQUIRE(rows <= m->tp_tc_rows, "tensor parallel: too many rows for the exchange region");
     float* mine = reinterpret_cast<float*>(m->tp_region.as<char>() + m->tp_off_tc_partial + half * m->tp_tc_half_partial);
-    uint32_t n = uint32_t(tc::gemm(s, sms, tc::GEMM_PARTIAL_F32, X, K, d.w.as<uint16_t>(), reinterpret_cast<uint16_t*>(mine), nullptr, rows, c.dim, K, c.dim, m->errflag.as<int>()));
+    uint32_t n = uint32_t(tc::gemm(s, sms, tc::GEMM_PARTIAL_F32, X, K, W, reinterpret_cast<uint16_t*>(mine), nullptr, rows, width, K, width, m->errflag.as<int>()));
     tc::tp_rows_exchange x{};
     x.world = c.tp_world, x.rank = c.tp_rank;
     for (uint32_t k = 0; k < c.tp_world; k++) {
@@ -929,8 +930,27 @@ uint32_t tp_tc_row_parallel(mc_llama* m, cudaStream_t s, const uint16_t* X, uint
         x.done[k] = reinterpret_cast<uint32_t*>(base + m->tp_off_tc_flags + 64);
     }
     x.counter = m->tp_local.as<unsigned>() + 8, x.epoch = m->tp_local.as<unsigned>() + 9, x.err = m->errflag.as<int>();
-    n += uint32_t(tc::tp_allreduce_rows(s, sms, x, res, rows, c.dim));
+    n += uint32_t(tc::tp_allreduce_rows(s, sms, x, res, rows, width));
     return n;
+}
+uint32_t tc_pad_rows(uint32_t a_rows);
+// wo / w2 of a tensor-parallel shard on the tensor-core path.  bf16: out = r(res + r(sum of the ranks' x . W^T)), left in the exchange
+// region's result half.  QLoRA: the GEMM runs on the resident image [W | A] of this rank's k range, the all-reduce yields
+// r(x . Wd^T) | r(x . A^T) over the full k, the adaptor epilogue (quantization/lora.h:115-122) and the residual follow into Y.
+// Returns where the rows are.
+uint16_t* tp_tc_linear(mc_llama* m, cudaStream_t s, const uint16_t* X, uint32_t K, const dlinear& d, uint32_t half, const uint16_t* res, uint16_t* Y, uint32_t rows,
+                       uint32_t& launches)
+{
+    const mc_llama_config& c = m->cfg;
+    if (!c.quant) {
+        launches += tp_tc_row_parallel(m, s, X, K, d.w.as<uint16_t>(), c.dim, half, res, rows);
+        return tp_tc_result(m, half);
+    }
+    const uint32_t width = c.dim + tc_pad_rows(c.lora_rank);
+    launches += tp_tc_row_parallel(m, s, X, K, d.wd.as<uint16_t>(), width, half, nullptr, rows);
+    launches += uint32_t(tc::lora_epilogue(s, tc::GEMM_RESIDUAL, tp_tc_result(m, half), width, Y, res, d.lora_b.as<uint16_t>(), rows, c.dim, c.dim, c.lora_rank, 1,
+                                           m->Hl * c.head_dim, (m->Hl + m->KVl) * c.head_dim, bf16_bits_to_f32(f32_to_bf16_bits(c.lora_scale))));
+    return Y;
 }
 
 // One linear of a block on the tensor-core path.  bf16 models: a single GEMM with the fused tail.  QLoRA models: the GEMM runs on the
@@ -1010,17 +1030,19 @@ void enqueue_rows_tc(mc_llama* m, launcher& L, uint32_t rows)
         }
         if (tp) {
             // row-parallel wo / w2: fp32 partial sums + all-reduce over NVLink (the residual stream then lives in the exchange region's result halves)
-            count(tp_tc_row_parallel(m, s, attn, QO, ly.wo, 0, x, rows));
-            h = tp_tc_result(m, 0);
+            uint32_t k = 0;
+            h = tp_tc_linear(m, s, attn, QO, ly.wo, 0, x, m->h.as<uint16_t>(), rows, k);
+            count(int(k));
         } else count(tc_linear(m, s, tc::GEMM_RESIDUAL, attn, QO, ly.wo, rank, 1, h, x, rows, D, QO, D, sc));
         count(tc::rmsnorm_rows(s, n, h, ly.ffn_norm.as<uint16_t>(), rows, D, c.norm_eps));
         count(tc_linear(m, s, tc::GEMM_SWIGLU, n, D, ly.w13, 2 * rank, 2, z, nullptr, rows, 2 * F, D, F, sc));
         if (tp) {
-            count(tp_tc_row_parallel(m, s, z, F, ly.w2, 1, h, rows));
-            x = tp_tc_result(m, 1);
+            uint32_t k = 0;
+            x = tp_tc_linear(m, s, z, F, ly.w2, 1, h, m->x.as<uint16_t>(), rows, k);
+            count(int(k));
         } else count(tc_linear(m, s, tc::GEMM_RESIDUAL, z, F, ly.w2, rank, 1, x, h, rows, D, F, D, sc));
     }
-    if (tp) {
+    if (tp && x != m->x.as<uint16_t>()) {
         // the last hidden rows go back to where the rest of the engine expects them
         MC_CUDA_CHECK(cudaMemcpyAsync(m->x.p, x, size_t(rows) * D * 2, cudaMemcpyDeviceToDevice, s));
         x = m->x.as<uint16_t>();
@@ -1391,11 +1413,13 @@ mc_status mc_llama_create(mc_device* dev, const mc_llama_config* cfg, mc_llama**
         m->tp_off_stax = m->tp_off_stam + 2 * m->tp_stam_gen;
         m->tp_stax_gen = size_t(2) * T * kStMaxRows * kStTpAxCols * 8;
         size_t region_bytes = m->tp_off_stax + 2 * m->tp_stax_gen;
-        if (!c.quant && !(c.flags & MC_LLAMA_NO_TC_PREFILL)) {
-            // prompts and decode batches on the tcgen05 path: a chunk of rows is all-reduced at once (tc::tp_allreduce_rows)
+        if (!(c.flags & MC_LLAMA_NO_TC_PREFILL) && !(c.quant && (c.flags & MC_LLAMA_NO_SHADOW))) {
+            // prompts and decode batches on the tcgen05 path: a chunk of rows is all-reduced at once (tc::tp_allreduce_rows); quantised
+            // models carry the adaptor's A . x columns behind the dim main sums
             m->tp_tc_rows = std::max<uint32_t>(std::min<uint32_t>(2048u, c.max_seq_len), std::max<uint32_t>(c.n_seqs, kMaxMB));
-            m->tp_tc_half_partial = (size_t(m->tp_tc_rows) * D * 4 + 255) & ~size_t(255);
-            m->tp_tc_half_result = (size_t(m->tp_tc_rows) * D * 2 + 255) & ~size_t(255);
+            const size_t width = D + (c.quant ? ((c.lora_rank + 31) & ~31u) : 0u);
+            m->tp_tc_half_partial = (size_t(m->tp_tc_rows) * width * 4 + 255) & ~size_t(255);
+            m->tp_tc_half_result = (size_t(m->tp_tc_rows) * width * 2 + 255) & ~size_t(255);
             m->tp_off_tc_partial = (region_bytes + 255) & ~size_t(255);
             m->tp_off_tc_result = m->tp_off_tc_partial + 2 * m->tp_tc_half_partial;
             m->tp_off_tc_flags = m->tp_off_tc_result + 2 * m->tp_tc_half_result;
@@ -1584,7 +1608,7 @@ mc_status mc_llama_finalize(mc_llama* m)
         }
         // resident bf16 image of every quantised matrix for the tensor-core prompt / batch path (the reference dequantises the whole
         // matrix on every call, quantization/lora.h:115, and caches the output projection, quantization/linear.h:50-53)
-        if (m->cfg.tp_world == 1 && !(m->cfg.flags & MC_LLAMA_NO_SHADOW)) {
+        if (!(m->cfg.flags & MC_LLAMA_NO_SHADOW)) {
             for (dlayer& ly : m->layers)
                 for (dlinear* d : {&ly.wqkv, &ly.wo, &ly.w13, &ly.w2}) {
                     // rows [0, N): r(r(q) * r(s)); rows [N, N + R): the stacked adaptor A of this linear; zero rows up to a multiple of 32
@@ -1706,14 +1730,12 @@ void prefill_tc(mc_llama* m, uint32_t seq, const int32_t* ids, uint32_t len, uin
             launches += tc::prefill_attn(s, q, kc, vc, attn, rows, seq, pos0, H, KV, hd, c.max_seq_len, m->scale_bf16, m->key_begin);
             if (tp) {
                 // row-parallel wo / w2: fp32 partial sums + all-reduce over NVLink (see tp_tc_row_parallel)
-                launches += tp_tc_row_parallel(m, s, attn, QO, ly.wo, 0, x, rows);
-                h = tp_tc_result(m, 0);
+                h = tp_tc_linear(m, s, attn, QO, ly.wo, 0, x, m->pf_h.as<uint16_t>(), rows, launches);
             } else launches += tc_linear(m, s, tc::GEMM_RESIDUAL, attn, QO, ly.wo, rank, 1, h, x, rows, D, QO, D, sc);
             launches += tc::rmsnorm_rows(s, n, h, ly.ffn_norm.as<uint16_t>(), rows, D, c.norm_eps);
             launches += tc_linear(m, s, tc::GEMM_SWIGLU, n, D, ly.w13, 2 * rank, 2, z, nullptr, rows, 2 * F, D, F, sc);
             if (tp) {
-                launches += tp_tc_row_parallel(m, s, z, F, ly.w2, 1, h, rows);
-                x = tp_tc_result(m, 1);
+                x = tp_tc_linear(m, s, z, F, ly.w2, 1, h, x0, rows, launches);
             } else launches += tc_linear(m, s, tc::GEMM_RESIDUAL, z, F, ly.w2, rank, 1, x, h, rows, D, F, D, sc);
         }
         if (t0 + rows >= len) {

@@ -1087,13 +1087,18 @@ __global__ void __launch_bounds__(256) tp_allreduce_rows_kernel(const tp_rows_ex
                 if (k < W) s[0] += lo[k].x, s[1] += lo[k].y, s[2] += lo[k].z, s[3] += lo[k].w, s[4] += hi[k].x, s[5] += hi[k].y, s[6] += hi[k].z, s[7] += hi[k].w;
             }
             // h = r(x + r(sum))  (kernel/bmm.metal:76, nn/transformer.h:133,139)
-            const uint4 r = *reinterpret_cast<const uint4*>(res + i * 8);
-            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
             uint4 o;
-            o.x = pack2(__fadd_rn(bf_lo(rw[0]), rbf(s[0])), __fadd_rn(bf_hi(rw[0]), rbf(s[1])));
-            o.y = pack2(__fadd_rn(bf_lo(rw[1]), rbf(s[2])), __fadd_rn(bf_hi(rw[1]), rbf(s[3])));
-            o.z = pack2(__fadd_rn(bf_lo(rw[2]), rbf(s[4])), __fadd_rn(bf_hi(rw[2]), rbf(s[5])));
-            o.w = pack2(__fadd_rn(bf_lo(rw[3]), rbf(s[6])), __fadd_rn(bf_hi(rw[3]), rbf(s[7])));
+            if (res != nullptr) {
+                const uint4 r = *reinterpret_cast<const uint4*>(res + i * 8);
+                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+                o.x = pack2(__fadd_rn(bf_lo(rw[0]), rbf(s[0])), __fadd_rn(bf_hi(rw[0]), rbf(s[1])));
+                o.y = pack2(__fadd_rn(bf_lo(rw[1]), rbf(s[2])), __fadd_rn(bf_hi(rw[1]), rbf(s[3])));
+                o.z = pack2(__fadd_rn(bf_lo(rw[2]), rbf(s[4])), __fadd_rn(bf_hi(rw[2]), rbf(s[5])));
+                o.w = pack2(__fadd_rn(bf_lo(rw[3]), rbf(s[6])), __fadd_rn(bf_hi(rw[3]), rbf(s[7])));
+            } else {
+                // no residual: the rounded sums themselves (QLoRA: r(x . Wd^T) | r(x . A^T), the adaptor epilogue follows)
+                o.x = pack2(s[0], s[1]), o.y = pack2(s[2], s[3]), o.z = pack2(s[4], s[5]), o.w = pack2(s[6], s[7]);
+            }
 #pragma unroll
             for (uint32_t k = 0; k < uint32_t(kTpRowsMaxWorld); k++) {
                 if (k < W) asm volatile("st.relaxed.sys.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(x.result[k] + i * 8), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");

@@ -33,6 +33,8 @@ def run_worker(mode, world, per_op, port, nccl=False):
            str(ROOT / "tests" / "tp_worker.py"), mode]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, cwd=ROOT, env=env)
     lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    if lines:
+        print(lines[-1])  # (the worker's report, also when its checks failed)
     assert res.returncode == 0 and lines, (res.stdout[-3000:], res.stderr[-4000:])
     out = json.loads(lines[-1])
     print(json.dumps(out))
@@ -74,3 +76,14 @@ def test_tp_quantised_model_matches_single_gpu_and_oracle(per_op):
     assert out["ok"], out
     if not per_op:
         assert out["launches_per_step"] == 1, "the streaming kernel did not take the quantised tensor-parallel step"
+
+
+def test_tp_quantised_batches_and_prompts_on_the_tensor_cores():
+    """12 sequences of the sharded QLoRA model: prompts and decode steps run as tcgen05 GEMMs over the resident bf16 image; the row-parallel
+    linears all-reduce [main sums | adaptor A . x] (tc::tp_allreduce_rows) before the adaptor epilogue."""
+    n = n_gpus()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    out = run_worker("quant12", 2 if n < 4 else 4 if n < 8 else 8, False, 29538)
+    assert out["ok"], out
+    assert out["launches_per_step"] > 1
