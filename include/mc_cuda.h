@@ -212,8 +212,11 @@ MC_API mc_status mc_llama_cache(mc_llama* m, uint32_t seq, uint32_t layer, int w
 MC_API mc_status mc_llama_launches_per_step(mc_llama* m, uint32_t* kernels);
 /* Tensor parallelism (no reference counterpart: the reference is single-device, nn/llama.h:86).  One process per GPU;
  * every rank creates the model with (tp_rank, tp_world), exports a 64-byte IPC handle of its exchange region, the host
- * gathers all handles (torch.distributed / MPI / files) and hands the world x 64 bytes to every rank.  The all-reduce
- * after wo and w2 is fused into the GEMV kernels over NVLink peer memory (DESIGN.md "Multi-GPU"). */
+ * gathers all handles (torch.distributed / MPI / files) and hands the world x 64 bytes to every rank.  bf16 and QLoRA models
+ * shard (column-split wq/wk/wv/w1/w3, row-split wo/w2, vocabulary-split head); every rank makes the same prefill / decode calls
+ * and receives the same token ids.  The all-reduce after wo and w2 never leaves the kernels' own code: tagged words stored into
+ * the peers' memory by the streaming decode kernel, partial-sum pushes by the per-op GEMV kernels, peer reads / writes by the
+ * all-reduce of the tensor-core prompt / batch path -- all over NVLink peer memory, no NCCL (DESIGN.md "Multi-GPU"). */
 MC_API mc_status mc_llama_tp_export(mc_llama* m, void* handle, size_t cap);
 MC_API mc_status mc_llama_tp_connect(mc_llama* m, const void* handles, size_t nbytes);
 /* Comparator for measurements only (bench.py --tp-collective nccl): the two all-reduces of a block become ncclAllReduce calls
