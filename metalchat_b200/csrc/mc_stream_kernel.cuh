@@ -131,6 +131,14 @@ struct st_params {
     uint32_t tp_world, tp_rank;
     uint64_t* tp_part[kStTpMaxWorld]; // exchange region of every rank as mapped on THIS GPU: [kind 0 wo | 1 w2][src rank][row][dim] tagged words (fp32 payload)
     uint64_t* tp_am[kStTpMaxWorld];   // [src rank][row][2]: value bits, global index
+    // arrival counters (opt-in experiment; the tags stay the proof): every CTA adds 1 to arrive[gphase & 7] when its part of phase gphase is
+    // published; the staging of the next GEMV phase waits for the counter before its FIRST load, so the words are asked for once
+    // instead of being polled by 256 threads x 148 CTAs while the producers' stores are still on their way (tools/hop_floor.cu:
+    // 1.63 vs 2.30 us per exchange of a dim-2048 vector -- but the real step got 7 % SLOWER with it, see mc_engine.cu launch_stream).
+    // arrive_base[k] = value of counter k before this launch.
+    unsigned* arrive;
+    uint32_t arrive_base[8];
+    uint32_t arrive_on;
     uint64_t* tp_ax[kStTpMaxWorld];   // quantised models: [kind][src rank][row][kStTpAxCols] tagged fp32 partials of the row-parallel adaptors' A . x
     uint32_t tp_dim;                  // = dim (row pitch of the partial-sum words)
     uint32_t tp_index_base;           // first vocabulary row of this rank's head shard
@@ -330,6 +338,22 @@ __device__ __forceinline__ uint32_t st_poll1_sys(const st_ctx& c, const uint64_t
         if (st_poll_backoff(c, spins, where)) return 0;
     }
 }
+// one thread per CTA: this CTA's part of phase gphase is published
+__device__ __forceinline__ void st_arrive(const st_params& P, uint32_t gphase)
+{
+    if (P.arrive_on) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(P.arrive + (gphase & 7u)) : "memory");
+}
+// one thread per CTA: every CTA has published phase gphase (bounded: after ~20 us the tags take over, which are always checked anyway)
+__device__ __forceinline__ void st_arrived_wait(const st_params& P, uint32_t gphase)
+{
+    if (!P.arrive_on) return;
+    const uint32_t k = gphase & 7u, want = P.arrive_base[k] + gridDim.x * ((gphase >> 3) + 1u);
+    for (uint32_t spins = 0; spins < 4096u; spins++) {
+        uint32_t v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.arrive + k) : "memory");
+        if (int32_t(v - want) >= 0) return;
+    }
+}
 __device__ __forceinline__ void st_stamp(unsigned long long* t, unsigned idx)
 {
     if (t && (threadIdx.x == 0 || threadIdx.x == kStConsumers)) {
@@ -494,7 +518,7 @@ template <bool Q> __device__ __forceinline__ void st_producer(const st_params& P
 // as bf16 in shared memory.  `xres_ll` (first phase of a step only): this CTA also publishes the raw embedding values of
 // the rows it will later own in the wo phase - they are the first residual.
 template <bool Q> __device__ __forceinline__ void st_stage_input(const st_params& P, const st_gemv& g, uint32_t li, const st_ctx& c, bool embed, uint32_t step, uint32_t tag_in,
-                                               uint32_t tag_out)
+                                               uint32_t tag_out, uint32_t gphase)
 {
     constexpr int NB = 4; // tagged 16-byte loads in flight per thread
     const uint32_t tid = threadIdx.x, K = g.K, n_words = K >> 1;
@@ -515,6 +539,11 @@ template <bool Q> __device__ __forceinline__ void st_stage_input(const st_params
             if (id < 0 || uint32_t(id) >= P.vocab) id = 0;
             sids[tid] = id;
         }
+        consumer_bar();
+    }
+    if (!embed && P.arrive_on) {
+        // the producers of the phase before have all arrived: the loads below find their words at the first attempt
+        if (tid == 0) st_arrived_wait(P, gphase - 1);
         consumer_bar();
     }
     for (uint32_t m = 0; m < P.rows; m++) {
@@ -1395,6 +1424,10 @@ template <bool Q, int HD, bool TP, int ATTN_SPLITS> __global__ void __launch_bou
                     const uint32_t tag_out = P.tag_base + gphase + 1;
                     const uint32_t res_tag = kind == 2 ? (li == 0 ? tag_out - 2 : tag_out - 3) : tag_out - 2;
                     st_epi_gemv<Q, TP>(P, P.g[is_head ? 4u : (kind == 0 ? 0u : kind - 1)], c, bl, best, is_head, is_head ? 0 : li, tag_out, res_tag);
+                    if (P.arrive_on) {
+                        epi_bar(); // the stores of both epilogue warps precede the arrival (release, cumulative)
+                        if (et == 0) st_arrive(P, gphase);
+                    }
                     st_stamp(P.timing ? P.timing + (size_t(blockIdx.x) * (P.steps * phases_per_step) + gphase) * 4 : nullptr, 1);
                 }
             }
@@ -1492,10 +1525,14 @@ template <bool Q, int HD, bool TP, int ATTN_SPLITS> __global__ void __launch_bou
                 st_stamp(tm, 0);
                 if (!is_head && kind == 1) {
                     st_attention<HD, ATTN_SPLITS>(P, li, step, c, tag_in, tag_out);
+                    if (P.arrive_on) {
+                        consumer_bar();
+                        if (tid == 0) st_arrive(P, gphase);
+                    }
                     st_stamp(tm, 2);
                 } else {
                     const st_gemv& g = P.g[is_head ? 4u : (kind == 0 ? 0u : kind - 1)];
-                    st_stage_input<Q>(P, g, is_head ? 0 : li, c, li == 0 && kind == 0 && !is_head, step, tag_in, tag_out);
+                    st_stage_input<Q>(P, g, is_head ? 0 : li, c, li == 0 && kind == 0 && !is_head, step, tag_in, tag_out, gphase);
                     st_stamp(tm, 2);
                     st_mma_gemv<Q>(P, g, c, cp, bl, is_head ? 0 : li);
                     if (is_head) {
