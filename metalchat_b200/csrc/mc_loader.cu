@@ -2,8 +2,8 @@
 //
 // Replaces, for the decode path, safetensor_document::open / load of the reference (src/safetensor.cc:83-153,237-253;
 // include/metalchat/safetensor.h:689-747): there the file is mapped and its pages are wrapped as no-copy Metal buffers (unified
-// memory); a B200 has no unified memory, so here the mapping is page-locked in place (cudaHostRegister, read-only) and every
-// tensor goes to its device layout with one strided H2D copy per shard slice (mc_llama_set_tensor: column / row / vocabulary
+// memory); a B200 has no unified memory, so here every tensor goes from the mapping to its device layout with one strided H2D
+// copy per shard slice (mc_llama_set_tensor: column / row / vocabulary
 // slices under tensor parallelism, fused wqkv / w13 rows, int8 -> packed int4 at finalize).  Name handling follows the
 // reference's serializers: HuggingFace names are renamed to the registered layer paths (huggingface/llama.h:88-103), the output
 // projection stays tied to the embedding unless the file carries its own (huggingface/llama.h:103, reference.h:53-59), and
@@ -42,7 +42,6 @@ struct st_file {
     std::string path;
     void* map = nullptr;
     size_t size = 0;
-    bool registered = false;
 };
 
 // ---- a small JSON reader: exactly what a safetensors header needs (objects, arrays, strings, numbers, literals) -------------
@@ -190,7 +189,6 @@ struct mc_safetensors {
     ~mc_safetensors()
     {
         for (st_file& f : files) {
-            if (f.registered) cudaHostUnregister(f.map);
             if (f.map) munmap(f.map, f.size);
         }
     }
@@ -463,13 +461,10 @@ mc_status mc_llama_load_safetensors(mc_llama* m, mc_safetensors* st, uint32_t fl
     MC_REQUIRE(m && st, "bad arguments");
     mc_llama_config cfg{};
     if (mc_llama_get_config(m, &cfg) != MC_OK) throw error(MC_ERR_RUNTIME, mc_last_error());
-    // the H2D copies read the mapping directly once it is page-locked (the reference wraps the same pages as no-copy Metal
-    // buffers, safetensor.h:689-747); a mapping that cannot be registered is still read, through the driver's staging
-    for (st_file& f : st->files)
-        if (!f.registered) {
-            f.registered = cudaHostRegister(f.map, f.size, cudaHostRegisterReadOnly) == cudaSuccess;
-            if (!f.registered) cudaGetLastError();
-        }
+    // The H2D copies read the mapping directly (pageable source: the driver stages it, 11.7 GB/s on the B200 box).  Page-locking the
+    // mapping in place was measured and dropped (tools/hostreg_probe.py): a read-only registration is refused on this platform, and a
+    // private writable mapping registers at 0.5 ms per MiB (the pin breaks copy-on-write: 0.13 s for 256 MiB) -- the 55 GB/s copy that
+    // follows does not earn that back for a tensor that is read once.
     std::map<std::string, const st_entry*> have;
     for (const st_entry& e : st->entries) {
         const std::string name = (flags & MC_LOAD_HF_NAMES) ? hf_to_meta(e.name) : e.name;
