@@ -99,6 +99,19 @@ struct json_reader {
             const char c = *p++;
             if (c == '"') return out;
             if (c != '\\') {
+                // JSON strings hold no raw control characters and are valid UTF-8; names travel as C strings afterwards
+                const unsigned char u = static_cast<unsigned char>(c);
+                if (u < 0x20) bad("control character in a string");
+                if (u >= 0x80) {
+                    const int more = (u & 0xE0) == 0xC0 ? 1 : (u & 0xF0) == 0xE0 ? 2 : (u & 0xF8) == 0xF0 ? 3 : -1;
+                    if (more < 0 || end - p < more || (u == 0xC0 || u == 0xC1) || u > 0xF4) bad("invalid UTF-8 in a string");
+                    out += c;
+                    for (int i = 0; i < more; i++) {
+                        if ((static_cast<unsigned char>(*p) & 0xC0) != 0x80) bad("invalid UTF-8 in a string");
+                        out += *p++;
+                    }
+                    continue;
+                }
                 out += c;
                 continue;
             }
@@ -115,11 +128,15 @@ struct json_reader {
             case 't': out += '\t'; break;
             case 'u': {
                 uint32_t cp = hex4();
-                if (cp >= 0xD800 && cp < 0xDC00 && end - p >= 6 && p[0] == '\\' && p[1] == 'u') {
+                if (cp == 0) bad("\\u0000 in a string");
+                if (cp >= 0xD800 && cp < 0xDC00) {
+                    // a high surrogate is only valid as the first half of a pair
+                    if (!(end - p >= 6 && p[0] == '\\' && p[1] == 'u')) bad("lone surrogate in a string");
                     p += 2;
                     const uint32_t lo = hex4();
+                    if (lo < 0xDC00 || lo >= 0xE000) bad("lone surrogate in a string");
                     cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
-                }
+                } else if (cp >= 0xDC00 && cp < 0xE000) bad("lone surrogate in a string");
                 utf8(out, cp);
                 break;
             }

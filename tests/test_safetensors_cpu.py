@@ -90,3 +90,57 @@ def test_empty_header_and_nested_metadata(tmp_path):
     assert st.metadata("a") == "b" and st.metadata("n") is None
     np.testing.assert_array_equal(st.tensor("t"), np.array([[1, 2], [3, 4]], np.uint8))
     assert len(capi.Safetensors(_raw(tmp_path, b"{}"))) == 0
+
+
+def test_random_and_mutated_headers_never_crash(tmp_path):
+    """The header comes from a file somebody downloaded: whatever the bytes, the reader either loads the file or raises McInvalidArgument."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    good = (b'{"__metadata__":{"format":"pt"},"a.weight":{"dtype":"BF16","shape":[2,4],"data_offsets":[0,16]},'
+            b'"b":{"dtype":"F32","shape":[3],"data_offsets":[16,28]}}')
+    data = bytes(range(28))
+    p = tmp_path / "fuzz.safetensors"
+
+    def attempt(header: bytes, payload: bytes, hlen=None):
+        p.write_bytes(struct.pack("<Q", len(header) if hlen is None else hlen) + header + payload)
+        try:
+            s = capi.Safetensors(p)
+        except capi.McInvalidArgument:
+            return
+        for e in s.entries():  # a file that loads must describe byte ranges inside itself
+            s.tensor(e["name"])
+        s.close()
+
+    attempt(good, data)
+
+    @settings(max_examples=300, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(st.integers(0, len(good) - 1), st.integers(0, 255), st.integers(0, len(good)), st.binary(max_size=40), st.integers(0, 1 << 62))
+    def run(pos, byte, cut, junk, hlen):
+        mutated = bytearray(good)
+        mutated[pos] = byte
+        attempt(bytes(mutated), data)            # one byte flipped
+        attempt(good[:cut], data)                # truncated header
+        attempt(good[:cut] + junk, data)         # truncated + garbage
+        attempt(junk, data)                      # garbage only
+        attempt(good, data[: cut % (len(data) + 1)])  # payload shorter than the offsets say
+        attempt(good, data, hlen)                # header length field lies
+
+    run()
+
+
+@pytest.mark.parametrize("header, what", [
+    (b'{"a\x80b":{"dtype":"U8","shape":[1],"data_offsets":[0,1]}}', "invalid UTF-8"),
+    (b'{"a\x00b":{"dtype":"U8","shape":[1],"data_offsets":[0,1]}}', "control character"),
+    (b'{"a\\u0000b":{"dtype":"U8","shape":[1],"data_offsets":[0,1]}}', "u0000"),
+    (b'{"a\\ud800":{"dtype":"U8","shape":[1],"data_offsets":[0,1]}}', "lone surrogate"),
+    (b'{"a\\udc00":{"dtype":"U8","shape":[1],"data_offsets":[0,1]}}', "lone surrogate"),
+])
+def test_names_that_cannot_travel_as_c_strings_are_rejected(tmp_path, header, what):
+    with pytest.raises(capi.McInvalidArgument, match=what):
+        capi.Safetensors(_raw(tmp_path, header, b"\1"))
+
+
+def test_escaped_and_multibyte_names(tmp_path):
+    st = capi.Safetensors(_raw(tmp_path, '{"t\\u00e9\\ud83d\\ude00 中":{"dtype":"U8","shape":[1],"data_offsets":[0,1]}}'.encode(), b"\7"))
+    assert [e["name"] for e in st.entries()] == ["té\U0001F600 中"]
+    assert int(st.tensor("té\U0001F600 中")[0]) == 7
