@@ -16,7 +16,7 @@ path = os.path.join(tempfile.gettempdir(), "hostreg_probe.bin")
 with open(path, "wb") as f:
     f.write(os.urandom(1 << 20) * (n >> 20))
 attr = C.c_int(-1)
-rt.cudaDeviceGetAttribute(C.byref(attr), 106, 0)  # cudaDevAttrHostRegisterReadOnlySupported
+rt.cudaDeviceGetAttribute(C.byref(attr), 113, 0)  # cudaDevAttrHostRegisterReadOnlySupported (driver_types.h)
 print("cudaDevAttrHostRegisterReadOnlySupported:", attr.value)
 dst = torch.empty(n, dtype=torch.uint8, device="cuda")
 libc = C.CDLL(None, use_errno=True)
