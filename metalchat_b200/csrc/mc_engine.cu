@@ -1703,7 +1703,6 @@ void prefill_tc(mc_llama* m, uint32_t seq, const int32_t* ids, uint32_t len, uin
     const mc_llama_config& c = m->cfg;
     const uint32_t D = c.dim, hd = c.head_dim, H = m->Hl, KV = m->KVl, QO = H * hd, QKV = (H + 2 * KV) * hd, F = m->Fl;
     cudaStream_t s = m->dev->stream;
-    const int sms = m->dev->prop.multiProcessorCount;
     const uint32_t cap = std::min<uint32_t>(kPfChunk, c.max_seq_len);
     const uint32_t rank = c.lora_rank, maxN = std::max(std::max(QKV, 2 * F), D);
     if (m->pf_rows < cap) {

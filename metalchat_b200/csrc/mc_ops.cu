@@ -14,7 +14,6 @@ namespace mc {
 namespace {
 
 constexpr uint32_t kMaxThreads = 1024;
-constexpr uint32_t kWarp = 32;
 
 inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
